@@ -1,0 +1,939 @@
+// highs_b200/csrc/engine.cu -- host side of the B200 PDLP engine + the C ABI (include/b200pdlp.h).
+//
+// The host owns what cuPDLP-C's PDHG_Solve owns (/root/reference/highs/pdlp/cupdlp/
+// cupdlp_solver.c:899-1106): the outer loop, the check schedule (first 10
+// iterations, then every 40), termination, infeasibility detection and the
+// restart decisions (cupdlp_restart.c:3-99, cupdlp_proj.c:88-148).  Everything that
+// touches an n- or m-vector runs in pdhg_kernels.cu.  Between two checks the host
+// does not synchronise: it points state.stop_iter at the next check iteration and
+// replays a CUDA graph of PDHG passes; the adaptive step rule runs on the device.
+#include <nccl.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "host_prep.hpp"
+#include "pdhg_kernels.hpp"
+
+namespace b200 {
+
+static thread_local std::string g_last_error;
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define CUDA_OK(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      throw Error(B200PDLP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " at " + \
+                                         __FILE__ + ":" + std::to_string(__LINE__));               \
+  } while (0)
+#define NCCL_OK(call)                                                                                 \
+  do {                                                                                                \
+    ncclResult_t r_ = (call);                                                                         \
+    if (r_ != ncclSuccess)                                                                            \
+      throw Error(B200PDLP_ERR_NCCL, std::string(#call) + ": " + ncclGetErrorString(r_) + " at " +    \
+                                         __FILE__ + ":" + std::to_string(__LINE__));                  \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { if (p) cudaFree(p); }
+  void alloc(size_t count, bool zero = true) {
+    if (p) { cudaFree(p); p = nullptr; }
+    n = count;
+    CUDA_OK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    if (zero) CUDA_OK(cudaMemset(p, 0, std::max<size_t>(count, 1) * sizeof(T)));
+  }
+  void upload(const T* src, size_t count) {
+    if (count) CUDA_OK(cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  void from(const std::vector<T>& v) { alloc(v.size(), false); upload(v.data(), v.size()); }
+};
+
+struct DeviceMatrix {
+  BlockedCsr host;  // kept for dims / tests (values are released after upload unless keep_host)
+  DevBuf<int> rowptr, col, block_long;
+  DevBuf<double> val, long_partial;
+  DevBuf<int4> blocks, long_rows;
+  DevBuf<unsigned> long_counter;
+  DevCsr dev{};
+  void upload() {
+    rowptr.from(host.rowptr);
+    col.from(host.col);
+    val.from(host.val);
+    block_long.from(host.block_long);
+    std::vector<int4> b(host.blocks.size());
+    for (size_t i = 0; i < b.size(); i++) b[i] = make_int4(host.blocks[i].row_begin, host.blocks[i].row_end, host.blocks[i].nnz_begin, host.blocks[i].nnz_end);
+    blocks.from(b);
+    std::vector<int4> l(host.long_rows.size());
+    for (size_t i = 0; i < l.size(); i++) l[i] = make_int4(host.long_rows[i].row, host.long_rows[i].first_block, host.long_rows[i].nseg, host.long_rows[i].partial_offset);
+    long_rows.from(l);
+    long_partial.alloc(host.n_partials);
+    long_counter.alloc(host.long_rows.size());
+    dev.nrows = host.nrows;
+    dev.nblocks = (int)host.blocks.size();
+    dev.rowptr = rowptr.p; dev.col = col.p; dev.val = val.p; dev.blocks = blocks.p;
+    dev.block_long = block_long.p; dev.long_rows = long_rows.p;
+    dev.long_partial = long_partial.p; dev.long_counter = long_counter.p;
+  }
+};
+
+struct Residuals {      // CUPDLPresobj for one iterate
+  double pobj = 0, dobj = 0, pfeas = 0, dfeas = 0, gap = 0, relgap = 0;
+  double pinf_obj = 0, pinf_res = 1, dinf_obj = 0, dinf_res = 1;
+};
+
+}  // namespace b200
+
+using namespace b200;
+
+struct b200pdlp_form { StdForm f; };
+
+struct b200pdlp_problem {
+  StdForm form;
+  int rank = 0, world = 1, device = 0;
+  int r0 = 0, r1 = 0;              // local rows [r0,r1) of the permuted matrix
+  int n = 0, m = 0, ml = 0;        // form cols, global rows, local rows
+  DeviceMatrix A, AT;              // A_local (ml x n), A_local^T (n x ml)
+  cudaStream_t stream = nullptr;
+  // n-vectors (replicated across ranks)
+  DevBuf<double> x[2], aty[2], xsum, xavg, atyavg, xlr, cost, lower, upper, colscale;
+  // m_local-vectors
+  DevBuf<double> y[2], ax[2], ysum, yavg, axavg, ylr, rhs, rowscale;
+  DevBuf<double> redbuf;           // all-reduce staging: n + 16
+  DevBuf<double> partials;         // reduction scratch
+  DevBuf<unsigned> counters;
+  DevBuf<double> outs;             // device scalars written by check kernels
+  DevBuf<PdhgState> state;
+  PdhgState* hstate = nullptr;     // pinned mirror
+  double* houts = nullptr;         // pinned
+  ncclComm_t comm = nullptr;
+  cudaGraphExec_t graph_main = nullptr, graph_small = nullptr;
+  int graph_main_passes = 0, graph_small_passes = 0;
+  long long launches = 0;
+  int kernels_per_pass = 3;
+  bool has_prepared_solve = false;
+
+  ~b200pdlp_problem() {
+    if (graph_main) cudaGraphExecDestroy(graph_main);
+    if (graph_small) cudaGraphExecDestroy(graph_small);
+    if (comm) ncclCommDestroy(comm);
+    if (hstate) cudaFreeHost(hstate);
+    if (houts) cudaFreeHost(houts);
+    if (stream) cudaStreamDestroy(stream);
+  }
+  ReduceScratch rs(int slot) const {
+    // slot-private partial arrays: 16 accumulators x kMaxEwBlocks-or-nblocks each
+    return ReduceScratch{partials.p + (size_t)slot * scratch_stride, counters.p + slot};
+  }
+  size_t scratch_stride = 0;
+};
+
+namespace b200 {
+
+static constexpr int kSlotK1 = 0, kSlotK2 = 1, kSlotK3 = 2, kSlotChk = 3, kNumSlots = 4;
+static constexpr int kOutsCount = 64;
+
+static void set_device(const b200pdlp_problem* p) { CUDA_OK(cudaSetDevice(p->device)); }
+
+static void allreduce_inplace(b200pdlp_problem* p, double* dptr, size_t count) {
+  if (p->world <= 1) return;
+  if (!p->comm) throw Error(B200PDLP_ERR_STATE, "world > 1 but b200pdlp_comm_init was not called");
+  NCCL_OK(ncclAllReduce(dptr, dptr, count, ncclDouble, ncclSum, p->comm, p->stream));
+}
+
+static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, int rank, int world, b200pdlp_problem* p) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    throw Error(B200PDLP_ERR_CUDA, std::string("no CUDA device: the B200 engine has no CPU fallback (") + cudaGetErrorString(e) + ")");
+  if (prm.device >= 0) p->device = prm.device; else CUDA_OK(cudaGetDevice(&p->device));
+  set_device(p);
+  p->rank = rank; p->world = world;
+  formulate(lp, p->form);
+  scale(p->form, prm.scaling != 0);
+  StdForm& f = p->form;
+  std::vector<int> bounds = partition_rows(f, world);
+  p->r0 = bounds[rank]; p->r1 = bounds[rank + 1];
+  p->n = f.n; p->m = f.m; p->ml = p->r1 - p->r0;
+  build_row_major(f, p->r0, p->r1, p->A.host);
+  build_col_major(f, p->r0, p->r1, p->AT.host);
+  CUDA_OK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  p->A.upload();
+  p->AT.upload();
+  const int n = p->n, ml = p->ml;
+  for (int k = 0; k < 2; k++) { p->x[k].alloc(n); p->aty[k].alloc(n); p->y[k].alloc(ml); p->ax[k].alloc(ml); }
+  p->xsum.alloc(n); p->xavg.alloc(n); p->atyavg.alloc(n); p->xlr.alloc(n);
+  p->ysum.alloc(ml); p->yavg.alloc(ml); p->axavg.alloc(ml); p->ylr.alloc(ml);
+  p->cost.from(f.cost); p->lower.from(f.lower); p->upper.from(f.upper); p->colscale.from(f.col_scale);
+  p->rhs.alloc(ml, false); p->rhs.upload(f.rhs.data() + p->r0, ml);
+  p->rowscale.alloc(ml, false); p->rowscale.upload(f.row_scale.data() + p->r0, ml);
+  p->redbuf.alloc((size_t)std::max(n, p->m) + 16);
+  size_t maxgrid = std::max<size_t>(kMaxEwBlocks, std::max(p->A.host.blocks.size(), p->AT.host.blocks.size()));
+  p->scratch_stride = 16 * maxgrid;
+  p->partials.alloc(p->scratch_stride * kNumSlots);
+  p->counters.alloc(kNumSlots);
+  p->outs.alloc(kOutsCount);
+  p->state.alloc(1);
+  CUDA_OK(cudaMallocHost(&p->hstate, sizeof(PdhgState)));
+  CUDA_OK(cudaMallocHost(&p->houts, kOutsCount * sizeof(double)));
+  memset(p->hstate, 0, sizeof(PdhgState));
+  CUDA_OK(cudaDeviceSynchronize());
+}
+
+// ------------------------------------------------------------------ PDHG passes
+static void enqueue_pass(b200pdlp_problem* p) {
+  cudaStream_t s = p->stream;
+  PdhgState* st = p->state.p;
+  launch_primal_step(s, p->n, st, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->cost.p, p->lower.p,
+                     p->upper.p, p->xsum.p, p->rs(kSlotK1));
+  launch_spmv_dual(s, p->A.dev, st, p->x[0].p, p->x[1].p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p,
+                   p->rhs.p, p->ysum.p, p->form.neq, p->r0, p->rs(kSlotK2));
+  if (p->world == 1) {
+    launch_spmv_primal(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p,
+                       p->rs(kSlotK3));
+  } else {
+    launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->redbuf.p);
+    allreduce_inplace(p, p->redbuf.p, (size_t)p->n + 1);
+    launch_interaction(s, p->n, st, p->redbuf.p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->rs(kSlotK3));
+  }
+}
+
+static cudaGraphExec_t capture_passes(b200pdlp_problem* p, int passes) {
+  cudaGraph_t g = nullptr;
+  CUDA_OK(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+  for (int i = 0; i < passes; i++) enqueue_pass(p);
+  CUDA_OK(cudaStreamEndCapture(p->stream, &g));
+  cudaGraphExec_t ge = nullptr;
+  CUDA_OK(cudaGraphInstantiate(&ge, g, 0));
+  CUDA_OK(cudaGraphDestroy(g));
+  return ge;
+}
+
+static void fill_pow_tables(PdhgState* h) {
+  // step_iter k takes values pow_base+1 ... ; entry t serves k = pow_base+1+t (cupdlp_step.c:279-284)
+  h->pow_base = h->step_iter;
+  for (int t = 0; t < kPowTab; t++) {
+    const double k = (double)(h->step_iter + 1 + t);
+    h->pow_red[t] = std::pow(k + 1.0, -0.3);
+    h->pow_grow[t] = std::pow(k + 1.0, -0.6);
+  }
+}
+
+static void push_state(b200pdlp_problem* p) {
+  CUDA_OK(cudaMemcpyAsync(p->state.p, p->hstate, sizeof(PdhgState), cudaMemcpyHostToDevice, p->stream));
+}
+static void pull_state(b200pdlp_problem* p) {
+  CUDA_OK(cudaMemcpyAsync(p->hstate, p->state.p, sizeof(PdhgState), cudaMemcpyDeviceToHost, p->stream));
+  CUDA_OK(cudaStreamSynchronize(p->stream));
+}
+static void pull_outs(b200pdlp_problem* p, int count) {
+  CUDA_OK(cudaMemcpyAsync(p->houts, p->outs.p, count * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  CUDA_OK(cudaStreamSynchronize(p->stream));
+}
+
+// full A'y (all-reduced over ranks) with the plain kernel
+static void full_aty(b200pdlp_problem* p, const double* y, double* aty) {
+  if (p->world == 1) {
+    launch_spmv_plain(p->stream, p->AT.dev, y, aty);
+    p->launches++;
+  } else {
+    launch_spmv_plain(p->stream, p->AT.dev, y, p->redbuf.p);
+    p->launches++;
+    allreduce_inplace(p, p->redbuf.p, p->n);
+    CUDA_OK(cudaMemcpyAsync(aty, p->redbuf.p, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+  }
+}
+
+struct CheckResult { Residuals it[2]; bool timed_out = false; };
+
+// PDHG_Compute_Average_Iterate + PDHG_Compute_Residuals + PDHG_Compute_Infeas_Residuals
+// (cupdlp_step.c:377-420, cupdlp_solver.c:473-529, :433-471) for current and average iterate
+static CheckResult run_check(b200pdlp_problem* p, bool timed_out_local) {
+  cudaStream_t s = p->stream;
+  PdhgState* h = p->hstate;
+  const StdForm& f = p->form;
+  const int n = p->n, ml = p->ml, cur = h->cur;
+  const double scale = h->sum_step > 0.0 ? 1.0 / h->sum_step : 1.0;
+  launch_average(s, n, p->x[cur].p, p->xsum.p, p->xavg.p, h->pending, h->w_pending, scale);
+  launch_average(s, ml, p->y[cur].p, p->ysum.p, p->yavg.p, h->pending, h->w_pending, scale);
+  p->launches += 2;
+  if (h->pending) { h->pending = 0; push_state(p); }
+  launch_spmv_plain(s, p->A.dev, p->xavg.p, p->axavg.p);
+  p->launches++;
+  full_aty(p, p->yavg.p, p->atyavg.p);
+  ColIter c0{p->x[cur].p, p->aty[cur].p}, c1{p->xavg.p, p->atyavg.p};
+  RowIter r0{p->y[cur].p, p->ax[cur].p}, r1{p->yavg.p, p->axavg.p};
+  double* o = p->outs.p;
+  launch_col_check_a(s, n, 2, c0, c1, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, p->rs(kSlotChk), o);
+  launch_row_check_a(s, ml, 2, r0, r1, p->rhs.p, p->rowscale.p, f.neq, p->r0, p->rs(kSlotChk), o + 14);
+  p->launches += 2;
+  if (p->world > 1) {
+    // row-side partial sums + the time-limit flag travel in one small all-reduce
+    double flag = timed_out_local ? 1.0 : 0.0;
+    CUDA_OK(cudaMemcpyAsync(o + 20, &flag, sizeof(double), cudaMemcpyHostToDevice, s));
+    allreduce_inplace(p, o + 14, 7);
+  }
+  pull_outs(p, 21);
+  CheckResult cr;
+  cr.timed_out = p->world > 1 ? p->houts[20] > 0.0 : timed_out_local;
+  double inv_d[2], inv_p[2], dscale[2], pscale[2];
+  for (int t = 0; t < 2; t++) {
+    const double* a = p->houts + 7 * t;
+    const double* r = p->houts + 14 + 3 * t;
+    Residuals& R = cr.it[t];
+    R.pobj = a[0] * f.sense + f.offset;                        // cupdlp_solver.c:24
+    R.pfeas = std::sqrt(r[1]);
+    double d = r[0];                                           // :79
+    d += a[1];                                                 // :92 / :164
+    d -= a[2];                                                 // :98 / :180
+    R.dobj = d * f.sense + f.offset;                           // :100 / :182
+    R.dfeas = std::sqrt(a[3]);
+    R.gap = R.pobj - R.dobj;                                   // :513-516
+    R.relgap = std::fabs(R.pobj - R.dobj) / (1.0 + std::fabs(R.pobj) + std::fabs(R.dobj));
+    dscale[t] = std::sqrt(r[2] + a[4] + a[5]);                 // :262-266
+    if (dscale[t] < 1e-8) dscale[t] = 1.0;
+    pscale[t] = std::sqrt(a[6]);                               // :367-371
+    if (pscale[t] < 1e-8) pscale[t] = 1.0;
+    inv_d[t] = 1 / dscale[t];
+    inv_p[t] = 1.0 / pscale[t];
+  }
+  launch_col_check_b(s, n, 2, c0, c1, inv_d, inv_p, p->cost.p, p->lower.p, p->upper.p, p->colscale.p,
+                     p->rs(kSlotChk), o + 24);
+  launch_row_check_b(s, ml, 2, r0, r1, inv_p, p->rowscale.p, f.neq, p->r0, p->rs(kSlotChk), o + 30);
+  p->launches += 2;
+  if (p->world > 1) allreduce_inplace(p, o + 30, 2);
+  CUDA_OK(cudaMemcpyAsync(p->houts + 24, o + 24, 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  for (int t = 0; t < 2; t++) {
+    Residuals& R = cr.it[t];
+    const double* b = p->houts + 24 + 3 * t;
+    R.pinf_obj = (R.dobj - f.offset) / f.sense / dscale[t];    // :282-283
+    R.pinf_res = std::sqrt(b[0]);
+    R.dinf_obj = (R.pobj - f.offset) / f.sense / pscale[t];    // :376-377
+    R.dinf_res = std::sqrt(p->houts[30 + t] + b[1] + b[2]);    // :425
+  }
+  return cr;
+}
+
+static double restart_score(double beta, double pf, double df, double gap) {  // cupdlp_restart.c:113-124
+  return std::sqrt(beta * pf * pf + df * df / beta + gap * gap);
+}
+
+struct RestartMemo { double pf_lr = 0, df_lr = 0, gap_lr = 0, pf_lc = 0, df_lc = 0, gap_lc = 0; int last_iter = 0; };
+
+// PDHG_Check_Restart_GPU (cupdlp_restart.c:3-99): 0 none, 1 to average, 2 to current
+static int decide_restart(const PdhgState* h, const CheckResult& c, RestartMemo& mm) {
+  const Residuals &L = c.it[0], &A = c.it[1];
+  if (h->iter == mm.last_iter) {
+    mm.pf_lr = L.pfeas; mm.df_lr = L.dfeas; mm.gap_lr = L.gap;
+    mm.pf_lc = L.pfeas; mm.df_lc = L.dfeas; mm.gap_lc = L.gap;
+    return 0;
+  }
+  const double mu_cur = restart_score(h->beta, L.pfeas, L.dfeas, L.gap);
+  const double mu_avg = restart_score(h->beta, A.pfeas, A.dfeas, A.gap);
+  int choice = mu_cur < mu_avg ? 2 : 1;
+  const double mu_cand = mu_cur < mu_avg ? mu_cur : mu_avg;
+  if ((h->iter - mm.last_iter) >= 0.36 * h->iter) {
+    // artificial restart
+  } else {
+    const double mu_lr = restart_score(h->beta, mm.pf_lr, mm.df_lr, mm.gap_lr);
+    if (!(mu_cand < 0.2 * mu_lr)) {
+      const double mu_lc = restart_score(h->beta, mm.pf_lc, mm.df_lc, mm.gap_lc);
+      if (!(mu_cand < 0.8 * mu_lr && mu_cand > mu_lc)) choice = 0;
+    }
+  }
+  const Residuals& C = mu_cur < mu_avg ? L : A;
+  mm.pf_lc = C.pfeas; mm.df_lc = C.dfeas; mm.gap_lc = C.gap;
+  return choice;
+}
+
+// PDHG_Restart_Iterate_GPU (cupdlp_proj.c:88-148) + PDHG_Compute_Step_Size_Ratio (cupdlp_step.c:147-176)
+static void do_restart(b200pdlp_problem* p, int choice, const CheckResult& c, RestartMemo& mm) {
+  cudaStream_t s = p->stream;
+  PdhgState* h = p->hstate;
+  const int n = p->n, ml = p->ml, cur = h->cur;
+  h->sum_step = 0.0;
+  CUDA_OK(cudaMemsetAsync(p->xsum.p, 0, (size_t)n * sizeof(double), s));
+  CUDA_OK(cudaMemsetAsync(p->ysum.p, 0, (size_t)std::max(ml, 1) * sizeof(double), s));
+  const Residuals& R = choice == 1 ? c.it[1] : c.it[0];
+  mm.pf_lr = R.pfeas; mm.df_lr = R.dfeas; mm.gap_lr = R.gap;
+  if (choice == 1) {
+    CUDA_OK(cudaMemcpyAsync(p->x[cur].p, p->xavg.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(p->y[cur].p, p->yavg.p, (size_t)ml * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(p->ax[cur].p, p->axavg.p, (size_t)ml * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(p->aty[cur].p, p->atyavg.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  }
+  double* o = p->outs.p + 40;
+  launch_diff_norm2(s, n, p->x[cur].p, p->xlr.p, p->rs(kSlotChk), o);
+  launch_diff_norm2(s, ml, p->y[cur].p, p->ylr.p, p->rs(kSlotChk), o + 1);
+  p->launches += 2;
+  if (p->world > 1) allreduce_inplace(p, o + 1, 1);
+  CUDA_OK(cudaMemcpyAsync(p->houts + 40, o, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaMemcpyAsync(p->xlr.p, p->x[cur].p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  CUDA_OK(cudaMemcpyAsync(p->ylr.p, p->y[cur].p, (size_t)ml * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  const double mean = std::sqrt(h->tau * h->sigma);
+  const double dxn = std::sqrt(p->houts[40]), dyn = std::sqrt(p->houts[41]);
+  if (std::fmin(dxn, dyn) > 1e-10) {
+    const double upd = dyn / dxn;
+    const double lg = 0.5 * std::log(upd) + 0.5 * std::log(std::sqrt(h->beta));
+    h->beta = std::exp(lg) * std::exp(lg);
+  }
+  h->tau = mean / std::sqrt(h->beta);
+  h->sigma = h->tau * h->beta;
+  mm.last_iter = h->iter;
+}
+
+// state for the next pass after the host touched tau/sigma/beta (start of
+// PDHG_Update_Iterate_Adaptive_Step_Size, cupdlp_step.c:230-242)
+static void arm_step(PdhgState* h) {
+  h->eta = std::sqrt(h->tau * h->sigma);
+  if (h->adaptive) {
+    h->tau_try = h->eta / std::sqrt(h->beta);
+    h->sigma_try = h->eta * std::sqrt(h->beta);
+  } else {
+    h->tau_try = h->tau;
+    h->sigma_try = h->sigma;
+  }
+}
+
+static double vec_norm2_sq(b200pdlp_problem* p, const double* v, int len, bool reduce_over_ranks) {
+  double* o = p->outs.p + 44;
+  launch_diff_norm2(p->stream, len, v, nullptr, p->rs(kSlotChk), o);
+  p->launches++;
+  if (reduce_over_ranks && p->world > 1) allreduce_inplace(p, o, 1);
+  CUDA_OK(cudaMemcpyAsync(p->houts + 44, o, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  CUDA_OK(cudaStreamSynchronize(p->stream));
+  return p->houts[44];
+}
+
+// PDHG_Power_Method (cupdlp_step.c:71-145): 20 iterations on A A'
+static double power_method(b200pdlp_problem* p) {
+  cudaStream_t s = p->stream;
+  double* q = p->ylr.p;  // scratch (re-zeroed by the caller)
+  launch_fill(s, p->ml, q, 1.0);
+  p->launches++;
+  double lambda = 0.0;
+  for (int it = 0; it < 20; it++) {
+    full_aty(p, q, p->aty[0].p);
+    launch_spmv_plain(s, p->A.dev, p->aty[0].p, p->ax[0].p);
+    p->launches++;
+    CUDA_OK(cudaMemcpyAsync(q, p->ax[0].p, (size_t)p->ml * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    const double qn = std::sqrt(vec_norm2_sq(p, q, p->ml, true));
+    launch_scale(s, p->ml, q, 1.0 / qn);
+    p->launches++;
+    full_aty(p, q, p->aty[0].p);
+    lambda = vec_norm2_sq(p, p->aty[0].p, p->n, false);
+  }
+  return lambda;
+}
+
+static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, const b200pdlp_warm* warm, b200pdlp_result* out) {
+  using clk = std::chrono::steady_clock;
+  set_device(p);
+  const auto t_begin = clk::now();
+  const StdForm& f = p->form;
+  cudaStream_t s = p->stream;
+  const int n = p->n, m = p->m, ml = p->ml;
+  const int interval = prm.check_interval > 0 ? prm.check_interval : 40;
+  const double t_lim = (prm.time_limit > 0 && std::isfinite(prm.time_limit)) ? prm.time_limit : 0.0;
+  const long long launches0 = p->launches;
+  PdhgState* h = p->hstate;
+  memset(h, 0, sizeof(PdhgState));
+  h->adaptive = prm.adaptive_step != 0;
+
+  // ---- initial point: PDHG_PreSolve (hot start, cupdlp_solver.c:1217-1279) + PDHG_Init_Variables (:531-591)
+  std::vector<double> x0(n, 0.0), y0(m, 0.0);
+  if (warm && warm->col_value && warm->row_value && warm->row_dual) {
+    int jc = 0;
+    for (; jc < f.n_orig; jc++) x0[jc] = warm->col_value[jc];
+    for (int i = 0; i < m; i++) {
+      const double mu = f.row_class[i] == kLeq ? -1 : 1;
+      y0[f.row_new_idx[i]] = f.sense * mu * warm->row_dual[i];
+      if (f.row_class[i] == kBound) x0[jc++] = warm->row_value[i];
+    }
+    for (int j = 0; j < n; j++) x0[j] *= f.col_scale[j];
+    for (int i = 0; i < m; i++) y0[i] *= f.row_scale[i];
+  }
+  for (int j = 0; j < n; j++) {  // PDHG_Project_Bounds: upper first, then lower
+    double v = x0[j];
+    v = v < f.upper[j] ? v : f.upper[j];
+    v = v > f.lower[j] ? v : f.lower[j];
+    x0[j] = v;
+  }
+  for (int k = 0; k < 2; k++) {
+    CUDA_OK(cudaMemsetAsync(p->x[k].p, 0, (size_t)n * sizeof(double), s));
+    CUDA_OK(cudaMemsetAsync(p->aty[k].p, 0, (size_t)n * sizeof(double), s));
+    CUDA_OK(cudaMemsetAsync(p->y[k].p, 0, (size_t)std::max(ml, 1) * sizeof(double), s));
+    CUDA_OK(cudaMemsetAsync(p->ax[k].p, 0, (size_t)std::max(ml, 1) * sizeof(double), s));
+  }
+  CUDA_OK(cudaMemcpyAsync(p->x[0].p, x0.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (ml) CUDA_OK(cudaMemcpyAsync(p->y[0].p, y0.data() + p->r0, (size_t)ml * sizeof(double), cudaMemcpyHostToDevice, s));
+
+  // ---- PDHG_Init_Step_Sizes (cupdlp_step.c:312-375)
+  {
+    double a = 0.0, b = 0.0;   // cupdlp_twoNormSquared = dot(x,x), sequential on the reference's CPU path
+    for (int j = 0; j < n; j++) a += f.cost[j] * f.cost[j];
+    for (int i = 0; i < m; i++) b += f.rhs[i] * f.rhs[i];
+    h->beta = std::fmin(a, b) > 1e-6 ? a / b : 1.0;
+    if (h->adaptive) {
+      h->tau = (1.0 / f.amax) / std::sqrt(h->beta);
+      h->sigma = h->tau * h->beta;
+    } else {
+      const double lambda = power_method(p);
+      h->tau = 0.8 / std::sqrt(lambda);
+      h->sigma = h->tau;
+      h->tau /= std::sqrt(h->beta);
+      h->sigma *= std::sqrt(h->beta);
+    }
+  }
+  launch_spmv_plain(s, p->A.dev, p->x[0].p, p->ax[0].p);
+  p->launches++;
+  full_aty(p, p->y[0].p, p->aty[0].p);
+  // sums start at proj(0) like PDHG_Init_Variables :577-583; the average is recomputed at every check
+  {
+    std::vector<double> z(n, 0.0);
+    bool nz = false;
+    for (int j = 0; j < n; j++) {
+      double v = 0.0;
+      v = v < f.upper[j] ? v : f.upper[j];
+      v = v > f.lower[j] ? v : f.lower[j];
+      z[j] = v;
+      nz |= (v != 0.0);
+    }
+    if (nz) CUDA_OK(cudaMemcpyAsync(p->xsum.p, z.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+    else CUDA_OK(cudaMemsetAsync(p->xsum.p, 0, (size_t)n * sizeof(double), s));
+    CUDA_OK(cudaStreamSynchronize(s));
+  }
+  CUDA_OK(cudaMemsetAsync(p->ysum.p, 0, (size_t)std::max(ml, 1) * sizeof(double), s));
+  CUDA_OK(cudaMemsetAsync(p->xlr.p, 0, (size_t)n * sizeof(double), s));
+  CUDA_OK(cudaMemsetAsync(p->ylr.p, 0, (size_t)std::max(ml, 1) * sizeof(double), s));
+  arm_step(h);
+  fill_pow_tables(h);
+  push_state(p);
+  CUDA_OK(cudaStreamSynchronize(s));
+
+  // ---- graphs: one check interval of passes, and a short one for top-ups after rejected steps
+  const int want_main = prm.graph_passes > 0 ? prm.graph_passes : interval;
+  if (!p->graph_main || p->graph_main_passes != want_main) {
+    if (p->graph_main) cudaGraphExecDestroy(p->graph_main);
+    p->graph_main = capture_passes(p, want_main);
+    p->graph_main_passes = want_main;
+  }
+  if (!p->graph_small) { p->graph_small_passes = 4; p->graph_small = capture_passes(p, 4); }
+  p->kernels_per_pass = p->world == 1 ? 3 : 5;
+
+  const double tol_p = prm.tol_primal * (1.0 + f.norm_rhs), tol_d = prm.tol_dual * (1.0 + f.norm_cost);
+  RestartMemo memo;
+  CheckResult chk;
+  int term = B200PDLP_TIMELIMIT_OR_ITERLIMIT, term_iterate = 0, restarts = 0;
+  bool have_check = false;
+  cudaEvent_t ev0, ev1;
+  CUDA_OK(cudaEventCreate(&ev0));
+  CUDA_OK(cudaEventCreate(&ev1));
+  double iter_ms = 0.0;
+  const auto t_loop = clk::now();
+
+  // ---- main loop (cupdlp_solver.c:939-1106)
+  while (h->iter < prm.iter_limit) {
+    const double elapsed = std::chrono::duration<double>(clk::now() - t_loop).count();
+    const bool timed_out_local = t_lim > 0 && elapsed > t_lim;
+    chk = run_check(p, timed_out_local);
+    have_check = true;
+    const Residuals &L = chk.it[0], &A = chk.it[1];
+    if (prm.log_level >= 2)
+      printf("[b200pdlp] it %8d  pobj %+.8e dobj %+.8e  pfeas %.2e dfeas %.2e | avg pobj %+.8e dobj %+.8e pfeas %.2e dfeas %.2e  tau %.3e sigma %.3e\n",
+             h->iter, L.pobj, L.dobj, L.pfeas, L.dfeas, A.pobj, A.dobj, A.pfeas, A.dfeas, h->tau, h->sigma);
+    if (L.pfeas < tol_p && L.dfeas < tol_d && L.relgap < prm.tol_gap) { term = B200PDLP_OPTIMAL; term_iterate = 0; break; }
+    if (A.pfeas < tol_p && A.dfeas < tol_d && A.relgap < prm.tol_gap) { term = B200PDLP_OPTIMAL; term_iterate = 1; break; }
+    {  // PDHG_Check_Infeasibility, cupdlp_solver.c:740-795 (dFeasTol = 1e-8, cupdlp_utils.c:889)
+      const double ft = 1e-8;
+      bool inf = false;
+      for (int t = 0; t < 2; t++) {
+        const Residuals& R = chk.it[t];
+        if (R.pinf_obj > 0.0 && R.pinf_res < ft * R.pinf_obj) inf = true;
+        if (R.dinf_obj < 0.0 && R.dinf_res < -ft * R.dinf_obj) inf = true;
+      }
+      if (inf) { term = B200PDLP_INFEASIBLE_OR_UNBOUNDED; break; }
+    }
+    if (chk.timed_out) { term = B200PDLP_TIMELIMIT_OR_ITERLIMIT; break; }
+    if (h->iter >= prm.iter_limit - 1) { term = B200PDLP_TIMELIMIT_OR_ITERLIMIT; break; }
+    bool dirty = false;
+    if (prm.restart) {
+      const int choice = decide_restart(h, chk, memo);
+      if (choice) { do_restart(p, choice, chk, memo); restarts++; arm_step(h); dirty = true; }
+    }
+    // next check iteration: < 10, multiple of the interval, or iter_limit - 1 (cupdlp_solver.c:953-962)
+    int next = h->iter + 1;
+    while (!(next < 10 || next % interval == 0 || next == prm.iter_limit - 1)) next++;
+    h->stop_iter = next;
+    fill_pow_tables(h);
+    dirty = true;
+    if (dirty) push_state(p);
+    CUDA_OK(cudaEventRecord(ev0, s));
+    while (true) {
+      const int need = next - h->iter;
+      if (need >= p->graph_main_passes / 2 || need > p->graph_small_passes) {
+        CUDA_OK(cudaGraphLaunch(p->graph_main, s));
+        p->launches += (long long)p->graph_main_passes * p->kernels_per_pass;
+      } else if (need > 1) {
+        CUDA_OK(cudaGraphLaunch(p->graph_small, s));
+        p->launches += (long long)p->graph_small_passes * p->kernels_per_pass;
+      } else {
+        enqueue_pass(p);
+        p->launches += p->kernels_per_pass;
+      }
+      pull_state(p);
+      if (h->iter >= next) break;
+      if (h->step_iter - h->pow_base > kPowTab - p->graph_main_passes - 8) { fill_pow_tables(h); push_state(p); }
+    }
+    CUDA_OK(cudaEventRecord(ev1, s));
+    CUDA_OK(cudaEventSynchronize(ev1));
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, ev0, ev1));
+    iter_ms += ms;
+  }
+  const double solve_seconds = std::chrono::duration<double>(clk::now() - t_loop).count();
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+
+  // ---- PDHG_PostSolve (cupdlp_solver.c:1281-1435)
+  const int cur = h->cur;
+  const bool use_avg = (term == B200PDLP_OPTIMAL && term_iterate == 1);
+  const double* dx = use_avg ? p->xavg.p : p->x[cur].p;
+  const double* dy = use_avg ? p->yavg.p : p->y[cur].p;
+  const double* dax = use_avg ? p->axavg.p : p->ax[cur].p;
+  const double* daty = use_avg ? p->atyavg.p : p->aty[cur].p;
+  std::vector<double> hx(n), hy(m, 0.0), hax(m, 0.0), haty(n);
+  CUDA_OK(cudaMemcpyAsync(hx.data(), dx, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaMemcpyAsync(haty.data(), daty, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (p->world == 1) {
+    CUDA_OK(cudaMemcpyAsync(hy.data(), dy, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(hax.data(), dax, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, s));
+  } else {
+    // gather the row-partitioned vectors: zero-padded sum over ranks
+    for (int v = 0; v < 2; v++) {
+      CUDA_OK(cudaMemsetAsync(p->redbuf.p, 0, (size_t)m * sizeof(double), s));
+      CUDA_OK(cudaMemcpyAsync(p->redbuf.p + p->r0, v ? dax : dy, (size_t)ml * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      allreduce_inplace(p, p->redbuf.p, m);
+      CUDA_OK(cudaMemcpyAsync(v ? hax.data() : hy.data(), p->redbuf.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+  }
+  CUDA_OK(cudaStreamSynchronize(s));
+  const double inf = std::numeric_limits<double>::infinity();
+  if (out->col_value && out->col_dual && out->row_value && out->row_dual) {
+    std::vector<double> sp(n, 0.0), sn(n, 0.0);
+    if (have_check) {
+      for (int j = 0; j < n; j++) {   // dSlackPos / dSlackNeg of the returned iterate (cupdlp_solver.c:150-176)
+        double rc = haty[j] * -1.0;
+        rc = rc + 1.0 * f.cost[j];
+        double a = rc > 0.0 ? rc : 0.0;
+        a = a * (f.lower[j] > -inf ? 1.0 : 0.0);
+        double b = rc < 0.0 ? rc : 0.0;
+        b = b * -1.0;
+        b = b * (f.upper[j] < inf ? 1.0 : 0.0);
+        sp[j] = a; sn[j] = b;
+      }
+    }
+    for (int j = 0; j < n; j++) { hx[j] /= f.col_scale[j]; sp[j] *= f.col_scale[j]; sn[j] *= f.col_scale[j]; }
+    for (int i = 0; i < m; i++) { hy[i] /= f.row_scale[i]; hax[i] *= f.row_scale[i]; }
+    for (int j = 0; j < f.n_orig; j++) out->col_value[j] = hx[j];
+    for (int i = 0, j = 0; i < m; i++) {
+      double v = hax[f.row_new_idx[i]];
+      if (f.row_class[i] == kLeq) v = -v;
+      else if (f.row_class[i] == kBound) { v = v + hx[f.n_orig + j]; j++; }
+      out->row_value[i] = v;
+    }
+    for (int j = 0; j < f.n_orig; j++) { double v = sp[j] - sn[j]; out->col_dual[j] = v * f.sense; }
+    for (int i = 0; i < m; i++) {
+      double v = hy[f.row_new_idx[i]] * f.sense;
+      if (f.row_class[i] == kLeq) v = -v;
+      out->row_dual[i] = v;
+    }
+  }
+  out->value_valid = 1; out->dual_valid = 1;
+  out->term_code = term; out->term_iterate = term_iterate;
+  out->iters = h->iter; out->passes = h->passes; out->restarts = restarts;
+  out->kernel_launches = (int)std::min<long long>(p->launches - launches0, 2147483647LL);
+  const Residuals& R = chk.it[use_avg ? 1 : 0];
+  out->primal_obj = R.pobj; out->dual_obj = R.dobj; out->primal_feas = R.pfeas; out->dual_feas = R.dfeas;
+  out->gap = R.gap; out->rel_gap = R.relgap;
+  out->solve_seconds = solve_seconds;
+  out->iter_device_ms = iter_ms;
+  out->setup_seconds += std::chrono::duration<double>(t_loop - t_begin).count();
+  out->form_cols = n; out->form_rows = m; out->form_nnz = f.nnz; out->form_neq = f.neq;
+}
+
+}  // namespace b200
+
+// ============================================================================ C ABI
+template <class F>
+static int guarded(F&& fn) {
+  try {
+    fn();
+    return B200PDLP_OK;
+  } catch (const b200::Error& e) {
+    g_last_error = e.what();
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    g_last_error = "host allocation failed";
+    return B200PDLP_ERR_ALLOC;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return B200PDLP_ERR_STATE;
+  }
+}
+
+static void check_lp(const b200pdlp_lp* lp) {
+  if (!lp || lp->num_col < 0 || lp->num_row < 0 || !lp->a_start || (lp->a_start[lp->num_col] > 0 && (!lp->a_index || !lp->a_value)) ||
+      (lp->num_col > 0 && (!lp->col_cost || !lp->col_lower || !lp->col_upper)) || (lp->num_row > 0 && (!lp->row_lower || !lp->row_upper)))
+    throw Error(B200PDLP_ERR_ARG, "b200pdlp: malformed b200pdlp_lp");
+  if (lp->sense != 1.0 && lp->sense != -1.0) throw Error(B200PDLP_ERR_ARG, "b200pdlp: sense must be +1 or -1");
+}
+
+extern "C" {
+
+const char* b200pdlp_last_error(void) { return g_last_error.c_str(); }
+int b200pdlp_version(void) { return B200PDLP_VERSION; }
+int b200pdlp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+void b200pdlp_default_params(b200pdlp_params* p) {
+  memset(p, 0, sizeof(*p));
+  p->iter_limit = 2147483647;                 // kHighsIInf (HighsOptions.h:1341)
+  p->tol_primal = p->tol_dual = p->tol_gap = 1e-7;
+  p->time_limit = 0.0;
+  p->scaling = 1; p->adaptive_step = 1; p->restart = 1;
+  p->log_level = 0; p->check_interval = 40; p->device = -1; p->graph_passes = 0;
+}
+
+int b200pdlp_problem_create(const b200pdlp_lp* lp, const b200pdlp_params* params, int32_t rank, int32_t world, b200pdlp_problem** out) {
+  return guarded([&] {
+    check_lp(lp);
+    if (!params || !out || world < 1 || rank < 0 || rank >= world) throw Error(B200PDLP_ERR_ARG, "b200pdlp_problem_create: bad arguments");
+    auto* p = new b200pdlp_problem();
+    try { create_problem(*lp, *params, rank, world, p); } catch (...) { delete p; throw; }
+    *out = p;
+  });
+}
+
+void b200pdlp_problem_destroy(b200pdlp_problem* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  delete p;
+}
+
+int b200pdlp_problem_dims(const b200pdlp_problem* p, int32_t dims[8]) {
+  return guarded([&] {
+    if (!p || !dims) throw Error(B200PDLP_ERR_ARG, "null argument");
+    dims[0] = p->n; dims[1] = p->m; dims[2] = p->form.nnz; dims[3] = p->form.neq;
+    dims[4] = p->ml; dims[5] = p->r0; dims[6] = p->A.host.nnz; dims[7] = p->form.n_orig;
+  });
+}
+
+int b200pdlp_problem_get_vector(const b200pdlp_problem* p, int32_t which, double* dst, int32_t cap) {
+  if (!p || !dst) return B200PDLP_ERR_ARG;
+  const std::vector<double>* v = nullptr;
+  switch (which) {
+    case 0: v = &p->form.cost; break;
+    case 1: v = &p->form.lower; break;
+    case 2: v = &p->form.upper; break;
+    case 3: v = &p->form.rhs; break;
+    case 4: v = &p->form.col_scale; break;
+    case 5: v = &p->form.row_scale; break;
+    default: return B200PDLP_ERR_ARG;
+  }
+  if (!v) return B200PDLP_ERR_ARG;
+  const int k = std::min<int>(cap, (int)v->size());
+  memcpy(dst, v->data(), (size_t)k * sizeof(double));
+  return k;
+}
+
+int b200pdlp_problem_get_csr(const b200pdlp_problem* p, int32_t* rowptr, int32_t* col, double* val) {
+  if (!p || !rowptr || !col || !val) return B200PDLP_ERR_ARG;
+  const BlockedCsr& a = p->A.host;
+  memcpy(rowptr, a.rowptr.data(), (size_t)(a.nrows + 1) * sizeof(int));
+  memcpy(col, a.col.data(), (size_t)a.nnz * sizeof(int));
+  memcpy(val, a.val.data(), (size_t)a.nnz * sizeof(double));
+  return B200PDLP_OK;
+}
+
+int b200pdlp_spmv_ax(b200pdlp_problem* p, const double* x, double* ax) {
+  return guarded([&] {
+    if (!p || !x || !ax) throw Error(B200PDLP_ERR_ARG, "null argument");
+    set_device(p);
+    CUDA_OK(cudaMemcpyAsync(p->xavg.p, x, (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    launch_spmv_plain(p->stream, p->A.dev, p->xavg.p, p->axavg.p);
+    p->launches++;
+    CUDA_OK(cudaMemcpyAsync(ax, p->axavg.p, (size_t)p->ml * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CUDA_OK(cudaStreamSynchronize(p->stream));
+    CUDA_OK(cudaGetLastError());
+  });
+}
+
+int b200pdlp_spmv_aty(b200pdlp_problem* p, const double* y, double* aty) {
+  return guarded([&] {
+    if (!p || !y || !aty) throw Error(B200PDLP_ERR_ARG, "null argument");
+    set_device(p);
+    CUDA_OK(cudaMemcpyAsync(p->yavg.p, y, (size_t)p->ml * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    launch_spmv_plain(p->stream, p->AT.dev, p->yavg.p, p->atyavg.p);   // local partial (no all-reduce)
+    p->launches++;
+    CUDA_OK(cudaMemcpyAsync(aty, p->atyavg.p, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CUDA_OK(cudaStreamSynchronize(p->stream));
+    CUDA_OK(cudaGetLastError());
+  });
+}
+
+int b200pdlp_bench_spmv(b200pdlp_problem* p, int32_t which, int32_t reps, float* ms_total) {
+  return guarded([&] {
+    if (!p || !ms_total || reps < 1) throw Error(B200PDLP_ERR_ARG, "bad argument");
+    set_device(p);
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0));
+    CUDA_OK(cudaEventCreate(&e1));
+    CUDA_OK(cudaEventRecord(e0, p->stream));
+    for (int r = 0; r < reps; r++) {
+      if (which == 0) launch_spmv_plain(p->stream, p->A.dev, p->xavg.p, p->axavg.p);
+      else launch_spmv_plain(p->stream, p->AT.dev, p->yavg.p, p->atyavg.p);
+    }
+    p->launches += reps;
+    CUDA_OK(cudaEventRecord(e1, p->stream));
+    CUDA_OK(cudaEventSynchronize(e1));
+    CUDA_OK(cudaEventElapsedTime(ms_total, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CUDA_OK(cudaGetLastError());
+  });
+}
+
+int b200pdlp_problem_solve(b200pdlp_problem* p, const b200pdlp_params* params, const b200pdlp_warm* warm, b200pdlp_result* out) {
+  return guarded([&] {
+    if (!p || !params || !out) throw Error(B200PDLP_ERR_ARG, "null argument");
+    out->setup_seconds = 0.0;
+    solve_on_device(p, *params, warm, out);
+    CUDA_OK(cudaGetLastError());
+  });
+}
+
+int b200pdlp_solve(const b200pdlp_lp* lp, const b200pdlp_params* params, const b200pdlp_warm* warm, b200pdlp_result* out) {
+  return guarded([&] {
+    check_lp(lp);
+    if (!params || !out) throw Error(B200PDLP_ERR_ARG, "null argument");
+    const auto t0 = std::chrono::steady_clock::now();
+    b200pdlp_problem* p = new b200pdlp_problem();
+    try {
+      create_problem(*lp, *params, 0, 1, p);
+      out->setup_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      solve_on_device(p, *params, warm, out);
+      CUDA_OK(cudaGetLastError());
+    } catch (...) {
+      cudaSetDevice(p->device);
+      delete p;
+      throw;
+    }
+    cudaSetDevice(p->device);
+    delete p;
+  });
+}
+
+int b200pdlp_nccl_unique_id(uint8_t id[128]) {
+  return guarded([&] {
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId u;
+    NCCL_OK(ncclGetUniqueId(&u));
+    memcpy(id, &u, 128);
+  });
+}
+
+int b200pdlp_comm_init(b200pdlp_problem* p, const uint8_t id[128]) {
+  return guarded([&] {
+    if (!p || !id) throw Error(B200PDLP_ERR_ARG, "null argument");
+    set_device(p);
+    ncclUniqueId u;
+    memcpy(&u, id, 128);
+    NCCL_OK(ncclCommInitRank(&p->comm, p->world, u, p->rank));
+  });
+}
+
+int b200pdlp_form_create(const b200pdlp_lp* lp, int32_t scaling, b200pdlp_form** out) {
+  return guarded([&] {
+    check_lp(lp);
+    if (!out) throw Error(B200PDLP_ERR_ARG, "null argument");
+    auto* f = new b200pdlp_form();
+    formulate(*lp, f->f);
+    scale(f->f, scaling != 0);
+    *out = f;
+  });
+}
+void b200pdlp_form_destroy(b200pdlp_form* f) { delete f; }
+int b200pdlp_form_dims(const b200pdlp_form* f, int32_t dims[5], double scalars[3]) {
+  if (!f || !dims || !scalars) return B200PDLP_ERR_ARG;
+  dims[0] = f->f.n; dims[1] = f->f.m; dims[2] = f->f.nnz; dims[3] = f->f.neq; dims[4] = f->f.n_orig;
+  scalars[0] = f->f.norm_cost; scalars[1] = f->f.norm_rhs; scalars[2] = f->f.amax;
+  return B200PDLP_OK;
+}
+static const std::vector<double>* form_vector(const StdForm& f, int which) {
+  switch (which) {
+    case 0: return &f.cost;
+    case 1: return &f.lower;
+    case 2: return &f.upper;
+    case 3: return &f.rhs;
+    case 4: return &f.col_scale;
+    case 5: return &f.row_scale;
+  }
+  return nullptr;
+}
+int b200pdlp_form_get_vector(const b200pdlp_form* f, int32_t which, double* dst, int32_t cap) {
+  if (!f || !dst) return B200PDLP_ERR_ARG;
+  const std::vector<double>* v = form_vector(f->f, which);
+  if (!v) return B200PDLP_ERR_ARG;
+  const int k = std::min<int>(cap, (int)v->size());
+  memcpy(dst, v->data(), (size_t)k * sizeof(double));
+  return k;
+}
+int b200pdlp_form_get_csc(const b200pdlp_form* f, int32_t* start, int32_t* index, double* value) {
+  if (!f || !start || !index || !value) return B200PDLP_ERR_ARG;
+  memcpy(start, f->f.cbeg.data(), (size_t)(f->f.n + 1) * sizeof(int));
+  memcpy(index, f->f.cidx.data(), (size_t)f->f.nnz * sizeof(int));
+  memcpy(value, f->f.cval.data(), (size_t)f->f.nnz * sizeof(double));
+  return B200PDLP_OK;
+}
+int b200pdlp_form_get_row_map(const b200pdlp_form* f, int32_t* row_new_idx, int32_t* row_class) {
+  if (!f || !row_new_idx || !row_class) return B200PDLP_ERR_ARG;
+  memcpy(row_new_idx, f->f.row_new_idx.data(), (size_t)f->f.m * sizeof(int));
+  memcpy(row_class, f->f.row_class.data(), (size_t)f->f.m * sizeof(int));
+  return B200PDLP_OK;
+}
+
+int b200pdlp_partition_rows(const b200pdlp_lp* lp, int32_t world, int32_t* bounds) {
+  return guarded([&] {
+    check_lp(lp);
+    if (world < 1 || !bounds) throw Error(B200PDLP_ERR_ARG, "bad argument");
+    StdForm f;
+    formulate(*lp, f);
+    std::vector<int> b = partition_rows(f, world);
+    for (int g = 0; g <= world; g++) bounds[g] = b[g];
+  });
+}
+
+}  // extern "C"

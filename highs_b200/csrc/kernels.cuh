@@ -1,0 +1,128 @@
+// highs_b200/csrc/kernels.cuh -- sm_100a kernels of the PDHG hot path.
+//
+// What the reference does with cuSPARSE SpMV + a chain of element-wise kernels +
+// cuBLAS reductions that synchronise with the host every iteration
+// (/root/reference/highs/pdlp/cupdlp/cuda/cupdlp_cudalinalg.cu:65-94,253-342,
+//  cupdlp_cuda_kernels.cu:166-189,225-311) is three kernels per PDHG pass here:
+//
+//   K1 primal_step_kernel   x' = proj(x - tau (c - A'y)), |x-x'|^2, xSum += w x
+//   K2 spmv<DualEpilogue>   ax' = A x' fused with y' = proj(y + sigma(b - 2ax' + ax)),
+//                           |y-y'|^2, ySum += w y
+//   K3 spmv<PrimalEpilogue> aty' = A'y' fused with (x-x').(aty-aty'); its last block
+//                           evaluates the adaptive step rule ON THE DEVICE
+//                           (cupdlp_step.c:266-285) and flips the double buffer
+//
+// No host synchronisation inside a pass: every kernel reads the PdhgState block
+// in device memory and is a no-op once state.iter reaches state.stop_iter, so the
+// host can enqueue a whole check interval (CUDA graph) and read the state once.
+//
+// All arithmetic is fp64 and un-contracted (compile with -fmad=false): products
+// and sums round separately, in the reference CPU path's operation order, so the
+// element-wise results are bit-identical to HiGHS's CPU pdlp; only the ORDER of
+// the long reductions (norms, dot products) differs (fixed tree instead of a
+// sequential loop), and it is deterministic run to run.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+constexpr int kThreads = 256;          // threads per block, every kernel
+constexpr int kNnzBlk = 2048;          // == host_prep kNnzPerBlock
+constexpr int kPowTab = 128;           // entries of the step-rule power tables
+constexpr int kMaxEwBlocks = 148 * 8;  // grid of the element-wise kernels
+
+// Device-resident control block of the PDHG loop (one per problem).
+struct PdhgState {
+  // step sizes (cupdlp_defs.h CUPDLPstepsize): eta = dStepSizeUpdate carried into the next pass
+  double eta, beta, tau, sigma;      // tau/sigma = dPrimalStep/dDualStep of the last accepted step
+  double tau_try, sigma_try;         // eta/sqrt(beta), eta*sqrt(beta) for the pass about to run
+  double sum_step;                   // dSumPrimalStep (== dSumDualStep)
+  double w_pending;                  // weight of the iterate not yet added to xSum/ySum
+  double dx2, dy2, inter;            // reductions of the running pass
+  double mov, lim;                   // last movement / step limit (diagnostics)
+  int iter;                          // accepted iterations = timers->nIter
+  int step_iter;                     // nStepSizeIter (counts rejected passes too)
+  int cur;                           // which half of the double buffers is current
+  int pending;                       // 1: x[cur], y[cur] still to be added to the sums
+  int stop_iter;                     // passes are no-ops once iter >= stop_iter
+  int adaptive;                      // 1 adaptive line search, 0 fixed step
+  int passes, rejects;
+  int pow_base;                      // step_iter value that pow tables entry 0 belongs to
+  int pad_;
+  double pow_red[kPowTab];           // (k+1)^-0.3 for k = pow_base+1+i   (host-computed, glibc pow)
+  double pow_grow[kPowTab];          // (k+1)^-0.6
+};
+
+struct DevCsr {
+  int nrows, nblocks;
+  const int* __restrict__ rowptr;
+  const int* __restrict__ col;
+  const double* __restrict__ val;
+  const int4* __restrict__ blocks;      // {row_begin,row_end,nnz_begin,nnz_end}
+  const int* __restrict__ block_long;   // long-row id or -1
+  const int4* __restrict__ long_rows;   // {row, first_block, nseg, partial_offset}
+  double* long_partial;
+  unsigned* long_counter;
+};
+
+// scratch of the two-stage deterministic reductions
+struct ReduceScratch {
+  double* partials;   // [nacc][gridDim.x]
+  unsigned* counter;  // ticket of the last-block pattern (self-resetting)
+};
+
+// ----------------------------------------------------------------- reductions
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// sum over the block (fixed tree: lanes, then warps); result valid in thread 0
+__device__ __forceinline__ double block_sum(double v, double* smem /*[kThreads/32]*/) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) smem[wid] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (wid == 0) {
+    r = (lane < kThreads / 32) ? smem[lane] : 0.0;
+    r = warp_sum(r);
+  }
+  return r;
+}
+
+// Writes this block's NACC partial sums; the last block to arrive re-reduces all
+// partials in a fixed order and returns true (sums in out[], valid in thread 0).
+template <int NACC>
+__device__ __forceinline__ bool grid_reduce(const double (&acc)[NACC], ReduceScratch rs, double (&out)[NACC]) {
+  __shared__ double sm[kThreads / 32];
+  __shared__ bool is_last;
+  const int nb = gridDim.x;
+#pragma unroll
+  for (int a = 0; a < NACC; a++) {
+    double s = block_sum(acc[a], sm);
+    if (threadIdx.x == 0) rs.partials[(size_t)a * nb + blockIdx.x] = s;
+  }
+  __threadfence();
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(rs.counter, 1u);
+    is_last = (t == (unsigned)nb - 1u);
+  }
+  __syncthreads();
+  if (!is_last) return false;
+  __threadfence();
+#pragma unroll
+  for (int a = 0; a < NACC; a++) {
+    double s = 0.0;
+    const volatile double* p = rs.partials + (size_t)a * nb;
+    for (int i = threadIdx.x; i < nb; i += kThreads) s += p[i];
+    out[a] = block_sum(s, sm);
+  }
+  if (threadIdx.x == 0) *rs.counter = 0u;
+  return true;
+}
+
+}  // namespace b200

@@ -1,0 +1,566 @@
+// highs_b200/csrc/pdhg_kernels.cu -- kernel definitions + launchers (see kernels.cuh).
+#include "pdhg_kernels.hpp"
+
+namespace b200 {
+
+// =============================================================== K1: primal step
+// PDHG_primalGradientStep (CPU operation order, cupdlp_step.c:28-38):
+//   x' = x; x' += (-tau) c; x' += tau aty; x' = min(x', u); x' = max(x', l)
+// fused with |x - x'|^2 (cupdlp_linalg.c:790) and the deferred average update
+// xSum += w x (PDHG_Update_Average, cupdlp_step.c:436) of the previous accepted step.
+__global__ void __launch_bounds__(kThreads)
+primal_step_kernel(int n, PdhgState* __restrict__ st, double* __restrict__ x0, double* __restrict__ x1,
+                   const double* __restrict__ aty0, const double* __restrict__ aty1,
+                   const double* __restrict__ c, const double* __restrict__ lo, const double* __restrict__ up,
+                   double* __restrict__ xsum, ReduceScratch rs) {
+  if (st->iter >= st->stop_iter) return;
+  const int cur = st->cur;
+  const double tau = st->tau_try, ntau = -tau;
+  const bool pend = st->pending != 0;
+  const double w = st->w_pending;
+  const double* __restrict__ x = cur ? x1 : x0;
+  double* __restrict__ xn = cur ? x0 : x1;
+  const double* __restrict__ aty = cur ? aty1 : aty0;
+  double acc[1] = {0.0};
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const double xc = x[i];
+    if (pend) xsum[i] = xsum[i] + w * xc;
+    double v = xc + ntau * c[i];
+    v = v + tau * aty[i];
+    const double u = up[i], l = lo[i];
+    v = v < u ? v : u;
+    v = v > l ? v : l;
+    xn[i] = v;
+    const double d = xc - v;
+    acc[0] += d * d;
+  }
+  double out[1];
+  if (grid_reduce<1>(acc, rs, out) && threadIdx.x == 0) st->dx2 = out[0];
+}
+
+// ================================================================= blocked SpMV
+// One CTA streams one block of consecutive rows (<= kNnzBlk nonzeros): phase 1
+// loads col/val with aligned 128-bit loads (int4 / 2 x double2), gathers the
+// dense vector through L2 and parks the products in shared memory; phase 2 gives
+// each row to one thread, which adds its products in column order -- the order in
+// which the reference's scatter SpMV accumulates into each output entry
+// (cupdlp_linalg.c:17-33) -- and runs the fused epilogue on the finished row sum.
+// Rows longer than a block are cut into segment blocks; the last segment to
+// finish combines the partial sums in segment order and runs the epilogue.
+struct PlainEpilogue {
+  static constexpr int NACC = 0;
+  const double* __restrict__ in;
+  double* __restrict__ out;
+  __device__ bool begin() { return true; }
+  __device__ const double* input() const { return in; }
+  __device__ void row(int r, double s, double*) const { out[r] = s; }
+  __device__ void finalize(const double*) const {}
+};
+
+// K2: PDHG_dualGradientStep (CPU order, cupdlp_step.c:55-67):
+//   y' = y; y' += sigma b; y' += (-2 sigma) ax'; y' += sigma ax; y'[i>=nEqs] = max(y',0)
+// + |y - y'|^2 + deferred ySum += w y.
+struct DualEpilogue {
+  static constexpr int NACC = 1;
+  PdhgState* st;
+  const double *x0, *x1;       // primal double buffer (input = the NEW x)
+  double *y0, *y1, *ax0, *ax1;
+  const double* b;
+  double* ysum;
+  int neq, row_offset;         // first global row of this rank (equality test is global)
+  // cached from the state block by begin()
+  const double *y, *ax;
+  double *yn, *axn;
+  double sigma, w;
+  bool pend;
+  __device__ bool begin() {
+    if (st->iter >= st->stop_iter) return false;
+    const int cur = st->cur;
+    y = cur ? y1 : y0; yn = cur ? y0 : y1;
+    ax = cur ? ax1 : ax0; axn = cur ? ax0 : ax1;
+    sigma = st->sigma_try; w = st->w_pending; pend = st->pending != 0;
+    x0 = cur ? x0 : x1;   // x0 now = input vector (the NEW x)
+    return true;
+  }
+  __device__ const double* input() const { return x0; }
+  __device__ void row(int r, double s, double* acc) const {
+    axn[r] = s;
+    const double yc = y[r];
+    if (pend) ysum[r] = ysum[r] + w * yc;
+    double v = yc + sigma * b[r];
+    v = v + (-2.0 * sigma) * s;
+    v = v + sigma * ax[r];
+    if (r + row_offset >= neq) v = v > 0.0 ? v : 0.0;
+    yn[r] = v;
+    const double d = yc - v;
+    acc[0] += d * d;
+  }
+  __device__ void finalize(const double* out) const { st->dy2 = out[0]; }
+};
+
+// device-side adaptive step rule, PDHG_Update_Iterate_Adaptive_Step_Size
+// (cupdlp_step.c:236-307) + the bookkeeping of PDHG_Update_Average (:422-442)
+__device__ void step_rule(PdhgState* st, double inter) {
+  const double rb = sqrt(st->beta);
+  const double mov = st->dx2 * 0.5 * rb + st->dy2 / (2.0 * rb);   // cupdlp_linalg.c:800
+  st->inter = inter;
+  st->mov = mov;
+  st->passes++;
+  if (st->adaptive) {
+    const int k = ++st->step_iter;
+    const double eta = st->eta;
+    const double lim = (inter != 0.0) ? mov / fabs(inter) : INFINITY;
+    st->lim = lim;
+    const bool accept = eta <= lim;
+    int t = k - st->pow_base - 1;
+    double pr, pg;
+    if (t >= 0 && t < kPowTab) { pr = st->pow_red[t]; pg = st->pow_grow[t]; }
+    else { pr = pow(k + 1.0, -0.3); pg = pow(k + 1.0, -0.6); }   // never hit: host refills the tables
+    const double first = (1.0 - pr) * lim;
+    const double second = (1.0 + pg) * eta;
+    const double eta_new = fmin(first, second);
+    if (accept) {
+      st->tau = eta_new / rb;
+      st->sigma = eta_new * rb;
+      const double w = sqrt(st->tau * st->sigma);
+      st->sum_step += w;
+      st->w_pending = w;
+      st->pending = 1;
+      st->cur ^= 1;
+      st->iter++;
+      st->eta = w;   // next iteration starts from sqrt(dPrimalStep*dDualStep), cupdlp_step.c:230-231
+    } else {
+      st->eta = eta_new;
+      st->pending = 0;
+      st->rejects++;
+    }
+    st->tau_try = st->eta / rb;
+    st->sigma_try = st->eta * rb;
+  } else {
+    // fixed step (PDHG_Update_Iterate_Constant_Step_Size): always accepted, steps unchanged
+    const double w = sqrt(st->tau * st->sigma);
+    st->sum_step += w;
+    st->w_pending = w;
+    st->pending = 1;
+    st->cur ^= 1;
+    st->iter++;
+  }
+}
+
+// K3: aty' = A'y' fused with the interaction (x - x').(aty - aty')
+// (cupdlp_compute_interaction_and_movement, cupdlp_linalg.c:772-801); the last
+// block then applies the step rule.
+struct PrimalEpilogue {
+  static constexpr int NACC = 1;
+  PdhgState* st;
+  const double *y0, *y1;       // dual double buffer (input = the NEW y)
+  const double *x0, *x1;
+  double *aty0, *aty1;
+  const double *x, *xn, *aty;
+  double* atyn;
+  __device__ bool begin() {
+    if (st->iter >= st->stop_iter) return false;
+    const int cur = st->cur;
+    x = cur ? x1 : x0; xn = cur ? x0 : x1;
+    aty = cur ? aty1 : aty0; atyn = cur ? aty0 : aty1;
+    y0 = cur ? y0 : y1;   // y0 now = input vector (the NEW y)
+    return true;
+  }
+  __device__ const double* input() const { return y0; }
+  __device__ void row(int r, double s, double* acc) const {
+    atyn[r] = s;
+    const double dx = x[r] - xn[r];
+    const double da = aty[r] - s;
+    acc[0] += dx * da;
+  }
+  __device__ void finalize(const double* out) const { step_rule(st, out[0]); }
+};
+
+template <class Epi>
+__global__ void __launch_bounds__(kThreads) spmv_blocked_kernel(DevCsr A, Epi epi_arg, ReduceScratch rs) {
+  __shared__ __align__(16) double prod[kNnzBlk];
+  Epi epi = epi_arg;
+  if (!epi.begin()) return;
+  const int4 d = A.blocks[blockIdx.x];
+  const double* __restrict__ xin = epi.input();
+  // ---- phase 1: stream the block's nonzeros, gather, multiply
+  const int base = d.z & ~3;
+  for (int e = base + 4 * threadIdx.x; e < d.w; e += 4 * kThreads) {
+    const int4 c4 = *reinterpret_cast<const int4*>(A.col + e);
+    const double2 v01 = *reinterpret_cast<const double2*>(A.val + e);
+    const double2 v23 = *reinterpret_cast<const double2*>(A.val + e + 2);
+    const int cc[4] = {c4.x, c4.y, c4.z, c4.w};
+    const double vv[4] = {v01.x, v01.y, v23.x, v23.y};
+    double g[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) g[k] = (e + k >= d.z && e + k < d.w) ? xin[cc[k]] : 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (e + k >= d.z && e + k < d.w) prod[e + k - d.z] = vv[k] * g[k];
+  }
+  __syncthreads();
+  // ---- phase 2: per-row sums in column order + epilogue
+  double acc[Epi::NACC > 0 ? Epi::NACC : 1] = {0.0};
+  const int lid = A.block_long[blockIdx.x];
+  if (lid < 0) {
+    const int nrows = d.y - d.x;
+    for (int r = threadIdx.x; r < nrows; r += kThreads) {
+      const int row = d.x + r;
+      const int b = A.rowptr[row] - d.z, e = A.rowptr[row + 1] - d.z;
+      double s = 0.0;
+      for (int k = b; k < e; k++) s += prod[k];
+      epi.row(row, s, acc);
+    }
+  } else {
+    // segment of a long row: block-wide tree sum of the segment, then hand-off
+    __shared__ double sm[kThreads / 32];
+    double s = 0.0;
+    for (int k = threadIdx.x; k < d.w - d.z; k += kThreads) s += prod[k];
+    s = block_sum(s, sm);
+    if (threadIdx.x == 0) {
+      const int4 lr = A.long_rows[lid];
+      const int seg = blockIdx.x - lr.y;
+      A.long_partial[lr.w + seg] = s;
+      __threadfence();
+      const unsigned t = atomicAdd(&A.long_counter[lid], 1u);
+      if (t == (unsigned)lr.z - 1u) {
+        __threadfence();
+        const volatile double* p = A.long_partial + lr.w;
+        double tot = 0.0;
+        for (int k = 0; k < lr.z; k++) tot += p[k];
+        A.long_counter[lid] = 0u;
+        epi.row(lr.x, tot, acc);
+      }
+    }
+  }
+  if constexpr (Epi::NACC > 0) {
+    double out[Epi::NACC];
+    if (grid_reduce<Epi::NACC>(acc, rs, out) && threadIdx.x == 0) epi.finalize(out);
+  }
+}
+
+// ======================================== multi-GPU K3b: after the all-reduce
+// buf[0..n) = sum over ranks of the partial A_g' y_g', buf[n] = sum of |dy|^2.
+__global__ void __launch_bounds__(kThreads)
+interaction_kernel(int n, PdhgState* __restrict__ st, const double* __restrict__ buf,
+                   const double* __restrict__ x0, const double* __restrict__ x1,
+                   double* __restrict__ aty0, double* __restrict__ aty1, ReduceScratch rs) {
+  if (st->iter >= st->stop_iter) return;
+  const int cur = st->cur;
+  const double* x = cur ? x1 : x0;
+  const double* xn = cur ? x0 : x1;
+  const double* aty = cur ? aty1 : aty0;
+  double* atyn = cur ? aty0 : aty1;
+  double acc[1] = {0.0};
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const double s = buf[i];
+    atyn[i] = s;
+    acc[0] += (x[i] - xn[i]) * (aty[i] - s);
+  }
+  double out[1];
+  if (grid_reduce<1>(acc, rs, out) && threadIdx.x == 0) {
+    st->dy2 = buf[n];
+    step_rule(st, out[0]);
+  }
+}
+
+// copies the local |dy|^2 into the tail slot of the all-reduce buffer
+__global__ void stash_dy2_kernel(PdhgState* st, double* slot) {
+  if (st->iter >= st->stop_iter) { *slot = 0.0; return; }
+  *slot = st->dy2;
+}
+
+// ===================================================== check-iteration kernels
+// PDHG_Compute_Average_Iterate (cupdlp_step.c:377-420): flush the pending
+// weighted iterate into the sum, then avg = sum * (1/sumStep).
+__global__ void __launch_bounds__(kThreads)
+average_kernel(int len, const double* __restrict__ v, double* __restrict__ sum, double* __restrict__ avg,
+               int pending, double w, double scale) {
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < len; i += stride) {
+    double s = sum[i];
+    if (pending) { s = s + w * v[i]; sum[i] = s; }
+    avg[i] = s * scale;
+  }
+}
+
+// column-side pass A for up to two iterates (current, average):
+// PDHG_Compute_Primal_Feasibility's objective (cupdlp_solver.c:23-24),
+// PDHG_Compute_Dual_Feasibility (:69-204) and the norms needed by
+// PDHG_Compute_{Primal,Dual}_Infeasibility (:255-262, :367).
+// out per iterate: 0 c.x, 1 sp.lo_f, 2 sn.up_f, 3 |dual residual|^2, 4 |sp|^2, 5 |sn|^2, 6 |x|^2
+__global__ void __launch_bounds__(kThreads)
+col_check_a_kernel(int n, int nit, ColIter it0, ColIter it1, const double* __restrict__ c,
+                   const double* __restrict__ lo, const double* __restrict__ up,
+                   const double* __restrict__ cs, ReduceScratch rs, double* __restrict__ out) {
+  double acc[14];
+#pragma unroll
+  for (int a = 0; a < 14; a++) acc[a] = 0.0;
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const double ci = c[i], l = lo[i], u = up[i], sc = cs[i];
+    const bool hl = l > -INFINITY, hu = u < INFINITY;
+    const double lf = hl ? l : 0.0, uf = hu ? u : 0.0;
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      if (t >= nit) break;
+      const ColIter& it = t ? it1 : it0;
+      const double x = it.x[i], aty = it.aty[i];
+      double rc = aty * -1.0;
+      rc = rc + 1.0 * ci;
+      double sp = rc > 0.0 ? rc : 0.0;
+      sp = sp * (hl ? 1.0 : 0.0);
+      double sn = rc < 0.0 ? rc : 0.0;
+      sn = sn * -1.0;
+      sn = sn * (hu ? 1.0 : 0.0);
+      double rr = rc + -1.0 * sp;
+      rr = rr + 1.0 * sn;
+      rr = rr * sc;
+      double* a = acc + 7 * t;
+      a[0] += x * ci;
+      a[1] += sp * lf;
+      a[2] += sn * uf;
+      a[3] += rr * rr;
+      a[4] += sp * sp;
+      a[5] += sn * sn;
+      a[6] += x * x;
+    }
+  }
+  double res[14];
+  if (grid_reduce<14>(acc, rs, res) && threadIdx.x == 0)
+    for (int a = 0; a < 14; a++) out[a] = res[a];
+}
+
+// row-side pass A: out per iterate: 0 y.b, 1 |primal residual|^2, 2 |y|^2
+// (cupdlp_solver.c:36-63 for the residual, :79 for y.b)
+__global__ void __launch_bounds__(kThreads)
+row_check_a_kernel(int m, int nit, RowIter it0, RowIter it1, const double* __restrict__ b,
+                   const double* __restrict__ rsca, int neq, int row_offset, ReduceScratch rs,
+                   double* __restrict__ out) {
+  double acc[6];
+#pragma unroll
+  for (int a = 0; a < 6; a++) acc[a] = 0.0;
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < m; i += stride) {
+    const double bi = b[i], sc = rsca[i];
+    const bool ineq = (i + row_offset) >= neq;
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      if (t >= nit) break;
+      const RowIter& it = t ? it1 : it0;
+      const double y = it.y[i], ax = it.ax[i];
+      double r = ax + -1.0 * bi;
+      if (ineq) r = r < 0.0 ? r : 0.0;
+      r = r * sc;
+      double* a = acc + 3 * t;
+      a[0] += y * bi;
+      a[1] += r * r;
+      a[2] += y * y;
+    }
+  }
+  double res[6];
+  if (grid_reduce<6>(acc, rs, res) && threadIdx.x == 0)
+    for (int a = 0; a < 6; a++) out[a] = res[a];
+}
+
+// column-side pass B (needs the ray scales of pass A): per iterate
+// 0 |dual-ray constraint residual|^2 (cupdlp_solver.c:289-303),
+// 1 |lower-bound violation of the primal ray|^2, 2 |upper ...|^2 (:395-423)
+__global__ void __launch_bounds__(kThreads)
+col_check_b_kernel(int n, int nit, ColIter it0, ColIter it1, double inv_dscale0, double inv_dscale1,
+                   double inv_pscale0, double inv_pscale1, const double* __restrict__ c,
+                   const double* __restrict__ lo, const double* __restrict__ up,
+                   const double* __restrict__ cs, ReduceScratch rs, double* __restrict__ out) {
+  double acc[6];
+#pragma unroll
+  for (int a = 0; a < 6; a++) acc[a] = 0.0;
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const double ci = c[i], l = lo[i], u = up[i], sc = cs[i];
+    const double hl = l > -INFINITY ? 1.0 : 0.0, hu = u < INFINITY ? 1.0 : 0.0;
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      if (t >= nit) break;
+      const ColIter& it = t ? it1 : it0;
+      const double ids = t ? inv_dscale1 : inv_dscale0, ips = t ? inv_pscale1 : inv_pscale0;
+      const double x = it.x[i], aty = it.aty[i];
+      double rc = aty * -1.0;
+      rc = rc + 1.0 * ci;
+      double sp = rc > 0.0 ? rc : 0.0;
+      sp = sp * hl;
+      double sn = rc < 0.0 ? rc : 0.0;
+      sn = sn * -1.0;
+      sn = sn * hu;
+      double k = aty * ids;
+      k = k + 1.0 * (sp * ids);
+      k = k + -1.0 * (sn * ids);
+      k = k * sc;
+      const double ray = x * ips;
+      double bl = ray < 0.0 ? ray : 0.0;
+      bl = bl * hl;
+      bl = bl / sc;
+      double bu = ray > 0.0 ? ray : 0.0;
+      bu = bu * hu;
+      bu = bu / sc;
+      double* a = acc + 3 * t;
+      a[0] += k * k;
+      a[1] += bl * bl;
+      a[2] += bu * bu;
+    }
+  }
+  double res[6];
+  if (grid_reduce<6>(acc, rs, res) && threadIdx.x == 0)
+    for (int a = 0; a < 6; a++) out[a] = res[a];
+}
+
+// row-side pass B: per iterate |[A ray]_eq, min([A ray]_ineq, 0)|^2 (cupdlp_solver.c:381-392)
+__global__ void __launch_bounds__(kThreads)
+row_check_b_kernel(int m, int nit, RowIter it0, RowIter it1, double inv_pscale0, double inv_pscale1,
+                   const double* __restrict__ rsca, int neq, int row_offset, ReduceScratch rs,
+                   double* __restrict__ out) {
+  double acc[2] = {0.0, 0.0};
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < m; i += stride) {
+    const double sc = rsca[i];
+    const bool ineq = (i + row_offset) >= neq;
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      if (t >= nit) break;
+      const RowIter& it = t ? it1 : it0;
+      double k = it.ax[i] * (t ? inv_pscale1 : inv_pscale0);
+      if (ineq) k = k < 0.0 ? k : 0.0;
+      k = k * sc;
+      acc[t] += k * k;
+    }
+  }
+  double res[2];
+  if (grid_reduce<2>(acc, rs, res) && threadIdx.x == 0) { out[0] = res[0]; out[1] = res[1]; }
+}
+
+// |a - b|^2 (PDHG_Compute_Step_Size_Ratio, cupdlp_step.c:161-164) and |a|^2
+__global__ void __launch_bounds__(kThreads)
+diff_norm2_kernel(int len, const double* __restrict__ a, const double* __restrict__ b, ReduceScratch rs,
+                  double* __restrict__ out) {
+  double acc[1] = {0.0};
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < len; i += stride) {
+    const double d = b ? (a[i] + -1.0 * b[i]) : a[i];
+    acc[0] += d * d;
+  }
+  double res[1];
+  if (grid_reduce<1>(acc, rs, res) && threadIdx.x == 0) out[0] = res[0];
+}
+
+__global__ void __launch_bounds__(kThreads) scale_kernel(int len, double* __restrict__ v, double w) {
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < len; i += stride) v[i] = v[i] * w;
+}
+
+__global__ void __launch_bounds__(kThreads) fill_kernel(int len, double* __restrict__ v, double w) {
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < len; i += stride) v[i] = w;
+}
+
+// ==================================================================== launchers
+static inline int ew_grid(int len) {
+  int g = (len + kThreads - 1) / kThreads;
+  if (g < 1) g = 1;
+  return g > kMaxEwBlocks ? kMaxEwBlocks : g;
+}
+
+void launch_primal_step(cudaStream_t s, int n, PdhgState* st, double* x0, double* x1, const double* aty0,
+                        const double* aty1, const double* c, const double* lo, const double* up, double* xsum,
+                        ReduceScratch rs) {
+  primal_step_kernel<<<ew_grid(n), kThreads, 0, s>>>(n, st, x0, x1, aty0, aty1, c, lo, up, xsum, rs);
+}
+
+void launch_spmv_plain(cudaStream_t s, const DevCsr& A, const double* in, double* out) {
+  if (A.nblocks == 0) return;
+  PlainEpilogue e{in, out};
+  spmv_blocked_kernel<PlainEpilogue><<<A.nblocks, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr});
+}
+
+void launch_spmv_dual(cudaStream_t s, const DevCsr& A, PdhgState* st, const double* x0, const double* x1,
+                      double* y0, double* y1, double* ax0, double* ax1, const double* b, double* ysum,
+                      int neq, int row_offset, ReduceScratch rs) {
+  DualEpilogue e{};
+  e.st = st; e.x0 = x0; e.x1 = x1; e.y0 = y0; e.y1 = y1; e.ax0 = ax0; e.ax1 = ax1; e.b = b; e.ysum = ysum;
+  e.neq = neq; e.row_offset = row_offset;
+  spmv_blocked_kernel<DualEpilogue><<<A.nblocks, kThreads, 0, s>>>(A, e, rs);
+}
+
+void launch_spmv_primal(cudaStream_t s, const DevCsr& A, PdhgState* st, const double* y0, const double* y1,
+                        const double* x0, const double* x1, double* aty0, double* aty1, ReduceScratch rs) {
+  PrimalEpilogue e{};
+  e.st = st; e.y0 = y0; e.y1 = y1; e.x0 = x0; e.x1 = x1; e.aty0 = aty0; e.aty1 = aty1;
+  spmv_blocked_kernel<PrimalEpilogue><<<A.nblocks, kThreads, 0, s>>>(A, e, rs);
+}
+
+// multi-GPU K3a: partial A_g' y' into buf (input chosen by the device state)
+struct PartialAtyEpilogue {
+  static constexpr int NACC = 0;
+  PdhgState* st;
+  const double *y0, *y1;
+  double* out;
+  __device__ bool begin() {
+    if (st->iter >= st->stop_iter) return false;
+    y0 = st->cur ? y0 : y1;
+    return true;
+  }
+  __device__ const double* input() const { return y0; }
+  __device__ void row(int r, double s, double*) const { out[r] = s; }
+  __device__ void finalize(const double*) const {}
+};
+
+void launch_spmv_partial_aty(cudaStream_t s, const DevCsr& A, PdhgState* st, const double* y0, const double* y1,
+                             double* buf) {
+  PartialAtyEpilogue e{st, y0, y1, buf};
+  spmv_blocked_kernel<PartialAtyEpilogue><<<A.nblocks, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr});
+  stash_dy2_kernel<<<1, 1, 0, s>>>(st, buf + A.nrows);
+}
+
+void launch_interaction(cudaStream_t s, int n, PdhgState* st, const double* buf, const double* x0,
+                        const double* x1, double* aty0, double* aty1, ReduceScratch rs) {
+  interaction_kernel<<<ew_grid(n), kThreads, 0, s>>>(n, st, buf, x0, x1, aty0, aty1, rs);
+}
+
+void launch_average(cudaStream_t s, int len, const double* v, double* sum, double* avg, int pending, double w,
+                    double scale) {
+  if (len == 0) return;
+  average_kernel<<<ew_grid(len), kThreads, 0, s>>>(len, v, sum, avg, pending, w, scale);
+}
+
+void launch_col_check_a(cudaStream_t s, int n, int nit, ColIter a, ColIter b, const double* c, const double* lo,
+                        const double* up, const double* cs, ReduceScratch rs, double* out) {
+  col_check_a_kernel<<<ew_grid(n), kThreads, 0, s>>>(n, nit, a, b, c, lo, up, cs, rs, out);
+}
+void launch_row_check_a(cudaStream_t s, int m, int nit, RowIter a, RowIter b, const double* rhs,
+                        const double* rsca, int neq, int row_offset, ReduceScratch rs, double* out) {
+  row_check_a_kernel<<<ew_grid(m), kThreads, 0, s>>>(m, nit, a, b, rhs, rsca, neq, row_offset, rs, out);
+}
+void launch_col_check_b(cudaStream_t s, int n, int nit, ColIter a, ColIter b, const double inv_d[2],
+                        const double inv_p[2], const double* c, const double* lo, const double* up,
+                        const double* cs, ReduceScratch rs, double* out) {
+  col_check_b_kernel<<<ew_grid(n), kThreads, 0, s>>>(n, nit, a, b, inv_d[0], inv_d[1], inv_p[0], inv_p[1], c, lo,
+                                                     up, cs, rs, out);
+}
+void launch_row_check_b(cudaStream_t s, int m, int nit, RowIter a, RowIter b, const double inv_p[2],
+                        const double* rsca, int neq, int row_offset, ReduceScratch rs, double* out) {
+  row_check_b_kernel<<<ew_grid(m), kThreads, 0, s>>>(m, nit, a, b, inv_p[0], inv_p[1], rsca, neq, row_offset, rs,
+                                                     out);
+}
+void launch_diff_norm2(cudaStream_t s, int len, const double* a, const double* b, ReduceScratch rs, double* out) {
+  diff_norm2_kernel<<<ew_grid(len), kThreads, 0, s>>>(len, a, b, rs, out);
+}
+void launch_scale(cudaStream_t s, int len, double* v, double w) {
+  if (len == 0) return;
+  scale_kernel<<<ew_grid(len), kThreads, 0, s>>>(len, v, w);
+}
+void launch_fill(cudaStream_t s, int len, double* v, double w) {
+  if (len == 0) return;
+  fill_kernel<<<ew_grid(len), kThreads, 0, s>>>(len, v, w);
+}
+
+}  // namespace b200

@@ -1,0 +1,38 @@
+// highs_b200/csrc/pdhg_kernels.hpp -- launcher declarations (host-callable) of pdhg_kernels.cu
+#pragma once
+#include "kernels.cuh"
+
+namespace b200 {
+
+struct ColIter { const double* x; const double* aty; };   // one primal-side iterate (n-vectors)
+struct RowIter { const double* y; const double* ax; };    // one dual-side iterate (m-vectors)
+
+void launch_primal_step(cudaStream_t s, int n, PdhgState* st, double* x0, double* x1, const double* aty0,
+                        const double* aty1, const double* c, const double* lo, const double* up, double* xsum,
+                        ReduceScratch rs);
+void launch_spmv_plain(cudaStream_t s, const DevCsr& A, const double* in, double* out);
+void launch_spmv_dual(cudaStream_t s, const DevCsr& A, PdhgState* st, const double* x0, const double* x1,
+                      double* y0, double* y1, double* ax0, double* ax1, const double* b, double* ysum,
+                      int neq, int row_offset, ReduceScratch rs);
+void launch_spmv_primal(cudaStream_t s, const DevCsr& A, PdhgState* st, const double* y0, const double* y1,
+                        const double* x0, const double* x1, double* aty0, double* aty1, ReduceScratch rs);
+void launch_spmv_partial_aty(cudaStream_t s, const DevCsr& A, PdhgState* st, const double* y0, const double* y1,
+                             double* buf);
+void launch_interaction(cudaStream_t s, int n, PdhgState* st, const double* buf, const double* x0,
+                        const double* x1, double* aty0, double* aty1, ReduceScratch rs);
+void launch_average(cudaStream_t s, int len, const double* v, double* sum, double* avg, int pending, double w,
+                    double scale);
+void launch_col_check_a(cudaStream_t s, int n, int nit, ColIter a, ColIter b, const double* c, const double* lo,
+                        const double* up, const double* cs, ReduceScratch rs, double* out);
+void launch_row_check_a(cudaStream_t s, int m, int nit, RowIter a, RowIter b, const double* rhs,
+                        const double* rsca, int neq, int row_offset, ReduceScratch rs, double* out);
+void launch_col_check_b(cudaStream_t s, int n, int nit, ColIter a, ColIter b, const double inv_d[2],
+                        const double inv_p[2], const double* c, const double* lo, const double* up,
+                        const double* cs, ReduceScratch rs, double* out);
+void launch_row_check_b(cudaStream_t s, int m, int nit, RowIter a, RowIter b, const double inv_p[2],
+                        const double* rsca, int neq, int row_offset, ReduceScratch rs, double* out);
+void launch_diff_norm2(cudaStream_t s, int len, const double* a, const double* b, ReduceScratch rs, double* out);
+void launch_scale(cudaStream_t s, int len, double* v, double w);
+void launch_fill(cudaStream_t s, int len, double* v, double w);
+
+}  // namespace b200

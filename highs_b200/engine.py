@@ -1,0 +1,288 @@
+"""ctypes binding of libb200pdlp.so (C ABI: include/b200pdlp.h).
+
+Plumbing only: it marshals numpy arrays into the C structs.  There is no CPU
+fallback -- if the CUDA extension is missing or no device is visible every compute
+entry point raises `EngineError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .lp import HighsLp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb200pdlp.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+TERM_NAMES = {0: "OPTIMAL", 1: "INFEASIBLE", 2: "UNBOUNDED", 3: "INFEASIBLE_OR_UNBOUNDED",
+              4: "TIMELIMIT_OR_ITERLIMIT", 5: "FEASIBLE"}
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class CLp(C.Structure):
+    _fields_ = [("num_col", C.c_int32), ("num_row", C.c_int32), ("a_start", _ip), ("a_index", _ip),
+                ("a_value", _dp), ("col_cost", _dp), ("col_lower", _dp), ("col_upper", _dp),
+                ("row_lower", _dp), ("row_upper", _dp), ("sense", C.c_double), ("offset", C.c_double)]
+
+
+class CParams(C.Structure):
+    _fields_ = [("iter_limit", C.c_int32), ("tol_primal", C.c_double), ("tol_dual", C.c_double),
+                ("tol_gap", C.c_double), ("time_limit", C.c_double), ("scaling", C.c_int32),
+                ("adaptive_step", C.c_int32), ("restart", C.c_int32), ("log_level", C.c_int32),
+                ("check_interval", C.c_int32), ("device", C.c_int32), ("graph_passes", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
+
+
+class CWarm(C.Structure):
+    _fields_ = [("col_value", _dp), ("row_value", _dp), ("row_dual", _dp)]
+
+
+class CResult(C.Structure):
+    _fields_ = [("col_value", _dp), ("col_dual", _dp), ("row_value", _dp), ("row_dual", _dp),
+                ("value_valid", C.c_int32), ("dual_valid", C.c_int32), ("term_code", C.c_int32),
+                ("term_iterate", C.c_int32), ("iters", C.c_int32), ("passes", C.c_int32),
+                ("restarts", C.c_int32), ("kernel_launches", C.c_int32),
+                ("primal_obj", C.c_double), ("dual_obj", C.c_double), ("primal_feas", C.c_double),
+                ("dual_feas", C.c_double), ("gap", C.c_double), ("rel_gap", C.c_double),
+                ("setup_seconds", C.c_double), ("solve_seconds", C.c_double), ("iter_device_ms", C.c_double),
+                ("form_cols", C.c_int32), ("form_rows", C.c_int32), ("form_nnz", C.c_int32),
+                ("form_neq", C.c_int32)]
+
+
+# every symbol include/b200pdlp.h declares (tests/test_abi.py checks the library exports them all)
+ABI_SYMBOLS = [
+    "b200pdlp_default_params", "b200pdlp_solve", "b200pdlp_problem_create", "b200pdlp_problem_destroy",
+    "b200pdlp_problem_dims", "b200pdlp_problem_get_vector", "b200pdlp_problem_get_csr", "b200pdlp_spmv_ax",
+    "b200pdlp_spmv_aty", "b200pdlp_bench_spmv", "b200pdlp_problem_solve", "b200pdlp_nccl_unique_id",
+    "b200pdlp_comm_init", "b200pdlp_partition_rows", "b200pdlp_last_error", "b200pdlp_version",
+    "b200pdlp_device_count", "b200pdlp_form_create", "b200pdlp_form_destroy", "b200pdlp_form_dims",
+    "b200pdlp_form_get_vector", "b200pdlp_form_get_csc", "b200pdlp_form_get_row_map",
+]
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA extension; raise loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineError(f"{LIB_PATH} is missing: run `python -m highs_b200.build` (nvcc, sm_100a). "
+                              "There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        L.b200pdlp_last_error.restype = C.c_char_p
+        L.b200pdlp_default_params.argtypes = [C.POINTER(CParams)]
+        L.b200pdlp_default_params.restype = None
+        L.b200pdlp_solve.argtypes = [C.POINTER(CLp), C.POINTER(CParams), C.POINTER(CWarm), C.POINTER(CResult)]
+        L.b200pdlp_problem_create.argtypes = [C.POINTER(CLp), C.POINTER(CParams), C.c_int32, C.c_int32,
+                                              C.POINTER(C.c_void_p)]
+        L.b200pdlp_problem_destroy.argtypes = [C.c_void_p]
+        L.b200pdlp_problem_destroy.restype = None
+        L.b200pdlp_problem_dims.argtypes = [C.c_void_p, _ip]
+        L.b200pdlp_problem_get_vector.argtypes = [C.c_void_p, C.c_int32, _dp, C.c_int32]
+        L.b200pdlp_problem_get_csr.argtypes = [C.c_void_p, _ip, _ip, _dp]
+        L.b200pdlp_spmv_ax.argtypes = [C.c_void_p, _dp, _dp]
+        L.b200pdlp_spmv_aty.argtypes = [C.c_void_p, _dp, _dp]
+        L.b200pdlp_bench_spmv.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float)]
+        L.b200pdlp_problem_solve.argtypes = [C.c_void_p, C.POINTER(CParams), C.POINTER(CWarm), C.POINTER(CResult)]
+        L.b200pdlp_nccl_unique_id.argtypes = [C.POINTER(C.c_uint8)]
+        L.b200pdlp_comm_init.argtypes = [C.c_void_p, C.POINTER(C.c_uint8)]
+        L.b200pdlp_partition_rows.argtypes = [C.POINTER(CLp), C.c_int32, _ip]
+        L.b200pdlp_form_create.argtypes = [C.POINTER(CLp), C.c_int32, C.POINTER(C.c_void_p)]
+        L.b200pdlp_form_destroy.argtypes = [C.c_void_p]
+        L.b200pdlp_form_destroy.restype = None
+        L.b200pdlp_form_dims.argtypes = [C.c_void_p, _ip, _dp]
+        L.b200pdlp_form_get_vector.argtypes = [C.c_void_p, C.c_int32, _dp, C.c_int32]
+        L.b200pdlp_form_get_csc.argtypes = [C.c_void_p, _ip, _ip, _dp]
+        L.b200pdlp_form_get_row_map.argtypes = [C.c_void_p, _ip, _ip]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise EngineError(f"{what} failed ({rc}): {lib().b200pdlp_last_error().decode()}")
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def make_clp(lp: HighsLp):
+    a = lp.a_matrix_
+    keep = (a.start_, a.index_, a.value_, lp.col_cost_, lp.col_lower_, lp.col_upper_, lp.row_lower_, lp.row_upper_)
+    c = CLp(lp.num_col_, lp.num_row_, _p(a.start_, _ip), _p(a.index_, _ip), _p(a.value_, _dp), _p(lp.col_cost_, _dp),
+            _p(lp.col_lower_, _dp), _p(lp.col_upper_, _dp), _p(lp.row_lower_, _dp), _p(lp.row_upper_, _dp),
+            float(lp.sense_), float(lp.offset_))
+    return c, keep
+
+
+def make_params(**kw) -> CParams:
+    p = CParams()
+    lib().b200pdlp_default_params(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise TypeError(f"unknown parameter {k}")
+        setattr(p, k, v)
+    return p
+
+
+def _result_dict(res: CResult, arrays) -> dict:
+    cv, cd, rv, rd = arrays
+    out = {k: getattr(res, k) for k, _ in CResult._fields_ if k not in ("col_value", "col_dual", "row_value", "row_dual")}
+    out.update(col_value=cv, col_dual=cd, row_value=rv, row_dual=rd, term_name=TERM_NAMES.get(res.term_code, "?"))
+    return out
+
+
+def _mk_result(lp: HighsLp):
+    n, m = lp.num_col_, lp.num_row_
+    arrays = (np.zeros(n), np.zeros(n), np.zeros(m), np.zeros(m))
+    res = CResult()
+    res.col_value, res.col_dual, res.row_value, res.row_dual = (_p(a, _dp) for a in arrays)
+    return res, arrays
+
+
+def _mk_warm(warm):
+    if warm is None:
+        return None, None
+    arrs = tuple(np.ascontiguousarray(w, dtype=np.float64) for w in warm)  # (col_value, row_value, row_dual)
+    return CWarm(_p(arrs[0], _dp), _p(arrs[1], _dp), _p(arrs[2], _dp)), arrs
+
+
+def solve(lp: HighsLp, warm=None, **params) -> dict:
+    """b200pdlp_solve: host buffers in, host buffers out (formulate+scale+upload+PDHG+download)."""
+    L = lib()
+    clp, keep = make_clp(lp)
+    prm = make_params(**params)
+    res, arrays = _mk_result(lp)
+    w, wk = _mk_warm(warm)
+    _check(L.b200pdlp_solve(C.byref(clp), C.byref(prm), C.byref(w) if w else None, C.byref(res)), "b200pdlp_solve")
+    return _result_dict(res, arrays)
+
+
+class Problem:
+    """Persistent device-resident problem (b200pdlp_problem_*)."""
+
+    def __init__(self, lp: HighsLp, rank: int = 0, world: int = 1, **params):
+        L = lib()
+        self.lp = lp
+        self._clp, self._keep = make_clp(lp)
+        self._prm = make_params(**params)
+        self._h = C.c_void_p()
+        _check(L.b200pdlp_problem_create(C.byref(self._clp), C.byref(self._prm), rank, world, C.byref(self._h)),
+               "b200pdlp_problem_create")
+        d = (C.c_int32 * 8)()
+        _check(L.b200pdlp_problem_dims(self._h, d), "b200pdlp_problem_dims")
+        (self.n, self.m, self.nnz, self.neq, self.m_local, self.row_offset, self.nnz_local, self.n_orig) = list(d)
+
+    def close(self):
+        if self._h:
+            lib().b200pdlp_problem_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def vector(self, which: str) -> np.ndarray:
+        idx = {"cost": 0, "lower": 1, "upper": 2, "rhs": 3, "col_scale": 4, "row_scale": 5}[which]
+        cap = self.n if idx in (0, 1, 2, 4) else self.m
+        out = np.zeros(cap)
+        k = lib().b200pdlp_problem_get_vector(self._h, idx, _p(out, _dp), cap)
+        if k < 0:
+            raise EngineError("b200pdlp_problem_get_vector failed")
+        return out[:k]
+
+    def csr(self):
+        rp = np.zeros(self.m_local + 1, dtype=np.int32)
+        col = np.zeros(max(self.nnz_local, 1), dtype=np.int32)
+        val = np.zeros(max(self.nnz_local, 1))
+        _check(lib().b200pdlp_problem_get_csr(self._h, _p(rp, _ip), _p(col, _ip), _p(val, _dp)), "get_csr")
+        return rp, col[: self.nnz_local], val[: self.nnz_local]
+
+    def spmv_ax(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert x.shape == (self.n,)
+        out = np.zeros(self.m_local)
+        _check(lib().b200pdlp_spmv_ax(self._h, _p(x, _dp), _p(out, _dp)), "b200pdlp_spmv_ax")
+        return out
+
+    def spmv_aty(self, y: np.ndarray) -> np.ndarray:
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        assert y.shape == (self.m_local,)
+        out = np.zeros(self.n)
+        _check(lib().b200pdlp_spmv_aty(self._h, _p(y, _dp), _p(out, _dp)), "b200pdlp_spmv_aty")
+        return out
+
+    def bench_spmv(self, which: int, reps: int) -> float:
+        ms = C.c_float()
+        _check(lib().b200pdlp_bench_spmv(self._h, which, reps, C.byref(ms)), "b200pdlp_bench_spmv")
+        return float(ms.value)
+
+    def comm_init(self, unique_id: bytes):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(lib().b200pdlp_comm_init(self._h, buf), "b200pdlp_comm_init")
+
+    def solve(self, warm=None, **params) -> dict:
+        prm = make_params(**params)
+        res, arrays = _mk_result(self.lp)
+        w, wk = _mk_warm(warm)
+        _check(lib().b200pdlp_problem_solve(self._h, C.byref(prm), C.byref(w) if w else None, C.byref(res)),
+               "b200pdlp_problem_solve")
+        return _result_dict(res, arrays)
+
+
+def nccl_unique_id() -> bytes:
+    buf = (C.c_uint8 * 128)()
+    _check(lib().b200pdlp_nccl_unique_id(buf), "b200pdlp_nccl_unique_id")
+    return bytes(buf)
+
+
+def partition_rows(lp: HighsLp, world: int) -> np.ndarray:
+    clp, keep = make_clp(lp)
+    out = np.zeros(world + 1, dtype=np.int32)
+    _check(lib().b200pdlp_partition_rows(C.byref(clp), world, _p(out, _ip)), "b200pdlp_partition_rows")
+    return out
+
+
+def host_form(lp: HighsLp, scaling: int = 1) -> dict:
+    """Host-only standard form (formulate + scale) as numpy arrays; needs no GPU."""
+    L = lib()
+    clp, keep = make_clp(lp)
+    h = C.c_void_p()
+    _check(L.b200pdlp_form_create(C.byref(clp), scaling, C.byref(h)), "b200pdlp_form_create")
+    try:
+        d = (C.c_int32 * 5)()
+        sc = (C.c_double * 3)()
+        _check(L.b200pdlp_form_dims(h, d, sc), "b200pdlp_form_dims")
+        n, m, nnz, neq, n_orig = list(d)
+        out = dict(n=n, m=m, nnz=nnz, neq=neq, n_orig=n_orig, norm_cost=sc[0], norm_rhs=sc[1], amax=sc[2])
+        for idx, (name, ln) in enumerate([("cost", n), ("lower", n), ("upper", n), ("rhs", m), ("col_scale", n), ("row_scale", m)]):
+            v = np.zeros(max(ln, 1))
+            k = L.b200pdlp_form_get_vector(h, idx, _p(v, _dp), ln)
+            out[name] = v[:k].copy()
+        cbeg = np.zeros(n + 1, dtype=np.int32)
+        cidx = np.zeros(max(nnz, 1), dtype=np.int32)
+        cval = np.zeros(max(nnz, 1))
+        _check(L.b200pdlp_form_get_csc(h, _p(cbeg, _ip), _p(cidx, _ip), _p(cval, _dp)), "form_get_csc")
+        rni = np.zeros(max(m, 1), dtype=np.int32)
+        rcl = np.zeros(max(m, 1), dtype=np.int32)
+        _check(L.b200pdlp_form_get_row_map(h, _p(rni, _ip), _p(rcl, _ip)), "form_get_row_map")
+        out.update(cbeg=cbeg, cidx=cidx[:nnz], cval=cval[:nnz], row_new_idx=rni[:m], row_type=rcl[:m])
+        return out
+    finally:
+        L.b200pdlp_form_destroy(h)
+
+
+def device_count() -> int:
+    return int(lib().b200pdlp_device_count())

@@ -1,0 +1,179 @@
+/* include/b200pdlp.h -- C ABI of the Blackwell-native PDLP engine (libb200pdlp.so).
+ *
+ * This is the drop-in boundary underneath HiGHS's
+ *     HighsStatus solveLpCupdlp(HighsLpSolverObject&)
+ * (/root/reference/highs/pdlp/CupdlpWrapper.cpp:23-278, called from
+ * /root/reference/highs/lp_data/HighsSolve.cpp:97-104).  Plain pointers and
+ * sizes only -- no HiGHS, torch or C++ types -- so the same library is bound
+ * from the C++ shim in highs_b200/csrc/highs_shim.cpp and from
+ * Python (ctypes, highs_b200/engine.py).
+ *
+ * All arithmetic is IEEE fp64; indices are 32-bit (cupdlp_int,
+ * highs/pdlp/cupdlp/glbopts.h:249-253; HighsInt without HIGHSINT64).
+ * Every entry point returns 0 on success and a negative b200pdlp_error
+ * otherwise; b200pdlp_last_error() gives the message.  There is NO CPU
+ * fallback: without a CUDA device the compute entry points fail with
+ * B200PDLP_ERR_CUDA.
+ */
+#ifndef B200PDLP_H_
+#define B200PDLP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200PDLP_VERSION 100
+
+typedef enum {
+  B200PDLP_OK = 0,
+  B200PDLP_ERR_ARG = -1,     /* bad argument */
+  B200PDLP_ERR_CUDA = -2,    /* CUDA runtime / no device */
+  B200PDLP_ERR_NCCL = -3,
+  B200PDLP_ERR_ALLOC = -4,
+  B200PDLP_ERR_STATE = -5
+} b200pdlp_error;
+
+/* termination codes: numbering of cupdlp_defs.h:61-68 */
+typedef enum {
+  B200PDLP_OPTIMAL = 0,
+  B200PDLP_INFEASIBLE = 1,
+  B200PDLP_UNBOUNDED = 2,
+  B200PDLP_INFEASIBLE_OR_UNBOUNDED = 3,
+  B200PDLP_TIMELIMIT_OR_ITERLIMIT = 4,
+  B200PDLP_FEASIBLE = 5
+} b200pdlp_term;
+
+/* HighsLp members read by solveLpCupdlp (HighsLp.h:23-35, CupdlpWrapper.cpp:280-300).
+ * The matrix is column-wise (asserted by the caller, Highs.cpp:4130). */
+typedef struct {
+  int32_t num_col, num_row;
+  const int32_t* a_start;    /* [num_col+1] */
+  const int32_t* a_index;    /* [nnz] row indices */
+  const double* a_value;     /* [nnz] */
+  const double* col_cost;    /* [num_col] */
+  const double* col_lower;   /* [num_col]; <= -1e20 means -inf (CupdlpWrapper.cpp:375-378) */
+  const double* col_upper;
+  const double* row_lower;   /* [num_row]; thresholds +-1e20 (CupdlpWrapper.cpp:316-317) */
+  const double* row_upper;
+  double sense;              /* +1 minimise, -1 maximise (ObjSense) */
+  double offset;
+} b200pdlp_lp;
+
+/* What getUserParamsFromOptions (CupdlpWrapper.cpp:642-717) hands to cuPDLP-C. */
+typedef struct {
+  int32_t iter_limit;        /* pdlp_iteration_limit (N_ITER_LIM) */
+  double tol_primal;         /* D_PRIMAL_TOL */
+  double tol_dual;           /* D_DUAL_TOL */
+  double tol_gap;            /* D_GAP_TOL */
+  double time_limit;         /* D_TIME_LIM, seconds; <= 0 or inf = none */
+  int32_t scaling;           /* IF_SCALING: 1 = Ruiz x10 + Pock-Chambolle(1) */
+  int32_t adaptive_step;     /* E_LINE_SEARCH_METHOD: 1 adaptive, 0 fixed (power method) */
+  int32_t restart;           /* E_RESTART_METHOD: 1 on, 0 off */
+  int32_t log_level;         /* N_LOG_LEVEL 0/1/2 */
+  int32_t check_interval;    /* CUPDLP_RELEASE_INTERVAL; 0 -> 40 */
+  int32_t device;            /* CUDA device ordinal; -1 = current */
+  int32_t graph_passes;      /* PDHG passes captured per CUDA graph; 0 -> check_interval */
+  int32_t reserved[4];
+} b200pdlp_params;
+
+/* Hot start = incoming HighsSolution when value_valid && dual_valid
+ * (PDHG_PreSolve, cupdlp_solver.c:1217-1279).  NULL pointer = cold start. */
+typedef struct {
+  const double* col_value;   /* [num_col] */
+  const double* row_value;   /* [num_row] (slack of BOUND rows) */
+  const double* row_dual;    /* [num_row] */
+} b200pdlp_warm;
+
+typedef struct {
+  /* caller-allocated HighsSolution storage, original LP space, HiGHS signs
+   * (PDHG_PostSolve, cupdlp_solver.c:1281-1435) */
+  double* col_value;         /* [num_col] */
+  double* col_dual;          /* [num_col] */
+  double* row_value;         /* [num_row] */
+  double* row_dual;          /* [num_row] */
+  int32_t value_valid, dual_valid;
+  int32_t term_code;         /* b200pdlp_term */
+  int32_t term_iterate;      /* 0 last iterate, 1 average iterate */
+  int32_t iters;             /* -> HighsInfo::pdlp_iteration_count */
+  int32_t passes;            /* PDHG passes executed (iters + rejected line-search steps) */
+  int32_t restarts;
+  int32_t kernel_launches;   /* kernels this library launched inside the solve */
+  /* cuPDLP-C's own residuals of the returned iterate (unscaled space) */
+  double primal_obj, dual_obj, primal_feas, dual_feas, gap, rel_gap;
+  /* timings, seconds */
+  double setup_seconds;      /* formulate + scale + layout + H2D */
+  double solve_seconds;      /* PDHG loop, host wall clock */
+  double iter_device_ms;     /* CUDA-event time of the PDHG passes only */
+  /* form dimensions actually solved */
+  int32_t form_cols, form_rows, form_nnz, form_neq;
+} b200pdlp_result;
+
+/* ---- whole solve: the function the HiGHS shim calls ------------------------ */
+void b200pdlp_default_params(b200pdlp_params* p);
+int b200pdlp_solve(const b200pdlp_lp* lp, const b200pdlp_params* params,
+                   const b200pdlp_warm* warm, b200pdlp_result* out);
+
+/* ---- persistent problem handle (bench + kernel-level parity tests) --------- */
+typedef struct b200pdlp_problem b200pdlp_problem;
+
+/* formulate + scale on the host, build the blocked row-major layouts of A and
+ * A^T, upload to HBM.  rank/world select a contiguous, nnz-balanced block of
+ * the (permuted) rows for multi-GPU; pass 0/1 for a single GPU. */
+int b200pdlp_problem_create(const b200pdlp_lp* lp, const b200pdlp_params* params,
+                            int32_t rank, int32_t world, b200pdlp_problem** out);
+void b200pdlp_problem_destroy(b200pdlp_problem* p);
+/* dims[0..7] = form cols, form rows (global), nnz (global), neq, local rows,
+ * local row offset, local nnz, original cols */
+int b200pdlp_problem_dims(const b200pdlp_problem* p, int32_t dims[8]);
+/* host copies of the scaled standard form (for parity tests against the oracle):
+ * which = 0 cost, 1 lower, 2 upper, 3 rhs, 4 col_scale, 5 row_scale (doubles);
+ * returns number of doubles written (<= cap) */
+int b200pdlp_problem_get_vector(const b200pdlp_problem* p, int32_t which, double* dst, int32_t cap);
+/* CSR of the scaled matrix (global row numbering of this rank's rows) */
+int b200pdlp_problem_get_csr(const b200pdlp_problem* p, int32_t* rowptr, int32_t* col, double* val);
+
+/* single kernels on host vectors (H2D, kernel, D2H) -- parity tests only:
+ * ax[m_local] = A_local x[n];  aty[n] = A_local^T y[m_local] */
+int b200pdlp_spmv_ax(b200pdlp_problem* p, const double* x, double* ax);
+int b200pdlp_spmv_aty(b200pdlp_problem* p, const double* y, double* aty);
+/* device-pointer variants on the problem's stream (bench roofline loop):
+ * time `reps` back-to-back launches with CUDA events; returns ms in *ms_total */
+int b200pdlp_bench_spmv(b200pdlp_problem* p, int32_t which /*0 Ax, 1 ATy*/, int32_t reps, float* ms_total);
+
+/* run the PDHG loop on an uploaded problem (bench "value": inputs resident in HBM) */
+int b200pdlp_problem_solve(b200pdlp_problem* p, const b200pdlp_params* params,
+                           const b200pdlp_warm* warm, b200pdlp_result* out);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink ---------------------- */
+/* rank 0 obtains the id and ships it to the other ranks (torch.distributed /
+ * any byte transport); every rank then calls comm_init.  id is 128 bytes. */
+int b200pdlp_nccl_unique_id(uint8_t id[128]);
+int b200pdlp_comm_init(b200pdlp_problem* p, const uint8_t id[128]);
+
+/* ---- host-only view of the standard form (no GPU needed; parity tests) -------
+ * formulate (CupdlpWrapper.cpp:280-448) + scale (cupdlp_scaling.c:233-425) only. */
+typedef struct b200pdlp_form b200pdlp_form;
+int b200pdlp_form_create(const b200pdlp_lp* lp, int32_t scaling, b200pdlp_form** out);
+void b200pdlp_form_destroy(b200pdlp_form* f);
+/* dims[0..4] = cols, rows, nnz, neq, original cols; scalars[0..2] = |c|_2, |b|_2 (unscaled), max|a_ij| (scaled) */
+int b200pdlp_form_dims(const b200pdlp_form* f, int32_t dims[5], double scalars[3]);
+/* which = 0 cost, 1 lower, 2 upper, 3 rhs, 4 col_scale, 5 row_scale; returns count written */
+int b200pdlp_form_get_vector(const b200pdlp_form* f, int32_t which, double* dst, int32_t cap);
+int b200pdlp_form_get_csc(const b200pdlp_form* f, int32_t* start, int32_t* index, double* value);
+/* row_new_idx[m], row_class[m] by ORIGINAL row (EQ=0, LEQ=1, GEQ=2, BOUND=3) */
+int b200pdlp_form_get_row_map(const b200pdlp_form* f, int32_t* row_new_idx, int32_t* row_class);
+
+/* host-only helper (no GPU): nnz-balanced contiguous row partition of the
+ * formulated LP; bounds[world+1] receives the row offsets */
+int b200pdlp_partition_rows(const b200pdlp_lp* lp, int32_t world, int32_t* bounds);
+
+const char* b200pdlp_last_error(void);
+int b200pdlp_version(void);
+int b200pdlp_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PDLP_H_ */

@@ -185,3 +185,32 @@ def run_reference(lp=None, mps=None, options=None, want_solution=False, warm=Non
             res.update(col_value=v[:n].copy(), col_dual=v[n:2 * n].copy(), row_value=v[2 * n:2 * n + m].copy(),
                        row_dual=v[2 * n + m:2 * n + 2 * m].copy(), value_valid=bool(vv), dual_valid=bool(dv))
     return res
+
+
+def reference_kkt(lp, solution, model_status_code=7, options=None) -> dict:
+    """Evaluate a HighsSolution with the reference's own lpKktCheck (ref_driver --kkt-of).
+
+    `solution` = dict/obj with col_value, col_dual, row_value, row_dual.  Returns the
+    HighsInfo KKT fields and the model status after lpKktCheck's adjustment, exactly as
+    Highs::run() would report them for that solution (Highs.cpp:1990).
+    """
+    from highs_b200.lp import write_b2lp
+    opts = {"solver": "pdlp", "presolve": "off"}
+    opts.update(options or {})
+    g = (lambda k: solution[k]) if isinstance(solution, dict) else (lambda k: getattr(solution, k))
+    with tempfile.TemporaryDirectory() as td:
+        lp_path = os.path.join(td, "lp.b2lp")
+        write_b2lp(lp_path, lp)
+        sp = os.path.join(td, "sol.bin")
+        cv, cd, rv, rd = (np.asarray(g(k), dtype="<f8") for k in ("col_value", "col_dual", "row_value", "row_dual"))
+        with open(sp, "wb") as f:
+            f.write(np.array([len(cv), len(rv), 1, 1], dtype="<i8").tobytes())
+            for v in (cv, cd, rv, rd):
+                f.write(v.tobytes())
+        cmd = [REF_DRIVER, "--lp", lp_path, "--kkt-of", sp, "--kkt-status", str(int(model_status_code))]
+        for k, v in opts.items():
+            cmd += ["--opt", f"{k}={v}"]
+        out = subprocess.run(cmd, capture_output=True, text=True)
+        if out.returncode != 0:
+            raise RuntimeError(f"ref_driver --kkt-of failed: {out.stderr}")
+        return json.loads(out.stdout.strip().splitlines()[-1])

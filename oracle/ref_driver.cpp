@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "Highs.h"
+#include "lp_data/HighsSolution.h"
 
 static const int64_t kMagic = 0x504C3242;  // "B2LP"
 
@@ -115,7 +116,8 @@ static bool readSol(const std::string& path, HighsSolution& s) {
 }
 
 int main(int argc, char** argv) {
-  std::string lp_path, mps_path, dump_lp, sol_path, warm_path;
+  std::string lp_path, mps_path, dump_lp, sol_path, warm_path, kkt_path;
+  int kkt_status = (int)HighsModelStatus::kOptimal;
   std::vector<std::pair<std::string, std::string>> opts;
   bool quiet = true;
   for (int i = 1; i < argc; i++) {
@@ -126,6 +128,8 @@ int main(int argc, char** argv) {
     else if (a == "--dump-lp") dump_lp = next();
     else if (a == "--sol") sol_path = next();
     else if (a == "--warm") warm_path = next();
+    else if (a == "--kkt-of") kkt_path = next();
+    else if (a == "--kkt-status") kkt_status = atoi(next().c_str());
     else if (a == "--verbose") quiet = false;
     else if (a == "--opt") {
       std::string kv = next();
@@ -160,10 +164,28 @@ int main(int argc, char** argv) {
     if (!readSol(warm_path, ws)) { fprintf(stderr, "cannot read warm start\n"); return 3; }
     highs.setSolution(ws);
   }
-  auto t0 = std::chrono::steady_clock::now();
-  HighsStatus rs = highs.run();
-  double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  const HighsInfo& info = highs.getInfo();
+  // --kkt-of: do not solve; evaluate a GIVEN HighsSolution with the reference's own
+  // lpKktCheck (highs/lp_data/HighsSolution.cpp:1043-1320), i.e. exactly what Highs::run()
+  // does after solveLpCupdlp returns (Highs.cpp:1990).  Used to measure the product's KKT
+  // residuals with the reference's definitions.
+  HighsInfo kkt_info;
+  HighsModelStatus kkt_model_status = (HighsModelStatus)kkt_status;
+  double secs = 0.0;
+  HighsStatus rs = HighsStatus::kOk;
+  if (!kkt_path.empty()) {
+    HighsSolution sol;
+    if (!readSol(kkt_path, sol)) { fprintf(stderr, "cannot read solution\n"); return 3; }
+    HighsBasis basis;
+    kkt_info.invalidate();
+    kkt_info.pdlp_iteration_count = -1;
+    lpKktCheck(kkt_model_status, kkt_info, highs.getLp(), sol, basis, highs.getOptions(), "ref_driver --kkt-of");
+  } else {
+    auto t0 = std::chrono::steady_clock::now();
+    rs = highs.run();
+    secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  const HighsInfo& info = kkt_path.empty() ? highs.getInfo() : kkt_info;
+  const HighsModelStatus final_status = kkt_path.empty() ? highs.getModelStatus() : kkt_model_status;
   const HighsLp& lp = highs.getLp();
   if (!sol_path.empty()) writeSol(sol_path, highs.getSolution());
   printf("{\"run_status\": %d, \"model_status\": \"%s\", \"model_status_code\": %d, "
@@ -177,7 +199,7 @@ int main(int argc, char** argv) {
          "\"max_complementarity_violation\": %.17g, \"num_complementarity_violations\": %d, "
          "\"primal_solution_status\": %d, \"dual_solution_status\": %d, "
          "\"num_col\": %d, \"num_row\": %d, \"num_nz\": %d, \"run_seconds\": %.6f}\n",
-         (int)rs, highs.modelStatusToString(highs.getModelStatus()).c_str(), (int)highs.getModelStatus(),
+         (int)rs, highs.modelStatusToString(final_status).c_str(), (int)final_status,
          (int)info.pdlp_iteration_count, info.objective_function_value,
          info.primal_dual_objective_error,
          (int)info.num_primal_infeasibilities, info.max_primal_infeasibility, info.sum_primal_infeasibilities,
