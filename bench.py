@@ -1,0 +1,294 @@
+#!/usr/bin/env python3
+"""bench.py -- PDHG iterations/s of the B200 PDLP engine on BASELINE.json's synthetic LPs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload S3|S2|S5] [--impl ours|reference]
+
+A "step" is ONE PDHG iteration of the hot path (primal step, A x + dual step, A'y +
+step rule) on the stated LP; the timed region runs exactly K iterations INCLUDING the
+check iterations (average iterate, 2 extra SpMV, residuals, restarts) that fall inside
+them, with the LP resident in HBM (`value`), and the same K iterations through the
+public host-buffer call b200pdlp_solve -- formulate + scale + layout + H2D + K
+iterations + D2H of the HighsSolution -- (`e2e`).  N > 1: the same LP row-partitioned
+over N GPUs, one process per GPU (torchrun), one NCCL all-reduce of A'y per iteration
+("strong" scaling: total work is fixed).  Prints ONE JSON line on rank 0.
+
+--impl reference times the reference's own CPU pdlp (oracle/_ref, the unmodified HiGHS
+built by oracle/build_ref.py) on the same LP on the host cores (it is single-threaded),
+steady-state iterations/s from a two-point fit so that the O(nnz) setup drops out.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {  # name -> (m, n, nnz_per_col, dense_col_nnz)   SURVEY.md 8(d)
+    "S2": (100_000, 100_000, 10, 0),
+    "S3": (1_000_000, 1_000_000, 8, 0),
+    "S5": (1_000_000, 1_000_000, 8, 500_000),
+}
+SEED = 12345
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) > 8:
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_lp(workload):
+    from highs_b200.lp import synthetic_lp
+    m, n, k, dense = WORKLOADS[workload]
+    return synthetic_lp(m, n, k, SEED, dense_col_nnz=dense)
+
+
+def algorithmic_bytes(n, m, nnz):
+    """fp64 values, int32 indices, row pointer / input / output once."""
+    b_ax = 12 * nnz + 4 * (m + 1) + 8 * n + 8 * m
+    b_aty = 12 * nnz + 4 * (n + 1) + 8 * m + 8 * n
+    # fused kernels as built (DESIGN.md "algorithmic bytes"):
+    k1 = 8 * 8 * n                 # read x,c,l,u,aty,xSum; write x',xSum
+    k2 = b_ax + 6 * 8 * m          # + read y,b,ax,ySum; write y',ySum
+    k3 = b_aty + 3 * 8 * n         # + read x,x',aty
+    b_iter = b_ax + b_aty + 72 * n + 56 * m   # SURVEY's perfect-fusion iteration model
+    return dict(ax=b_ax, aty=b_aty, k1=k1, k2=k2, k3=k3, iter=b_iter)
+
+
+def reference_rate(lp_path, iters, limit_a=20):
+    """steady-state iterations/s of the reference CPU pdlp: two-point fit over two iteration limits"""
+    from oracle import binding as ob
+    if not ob.ref_available():
+        return None
+    out = []
+    for lim in (limit_a, limit_a + iters):
+        t = time.monotonic()
+        r = ob.run_reference(lp_path=lp_path, options={"pdlp_iteration_limit": lim + 1})
+        out.append((r["pdlp_iteration_count"], r["run_seconds"], time.monotonic() - t))
+    (ia, ta, _), (ib, tb, _) = out
+    rate = (ib - ia) / max(tb - ta, 1e-9)
+    return dict(rate=rate, iters=ib - ia, seconds=tb - ta, setup_seconds=ta - ia / rate, runs=out)
+
+
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count()
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    from highs_b200.lp import write_b2lp
+    lp = make_lp(args.workload)
+    iters = int(min(max(args.steps, 20), 60 if args.workload != "S2" else 400))
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "lp.b2lp")
+        write_b2lp(path, lp)
+        ref = reference_rate(path, iters)
+    m, n, k, dense = WORKLOADS[args.workload]
+    if ref is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver missing (build with oracle/build_ref.py)"}))
+        return
+    line = {
+        "impl": "reference", "metric": "pdhg_iterations_per_sec", "value": ref["rate"], "unit": "iter/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / ref["rate"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: synthetic random sparse LP m={m} n={n} nnz={lp.a_matrix_.numNz()} seed={SEED}",
+                   "solver": "HiGHS 1.15.1 CPU pdlp (cuPDLP-C), presolve=off, single thread"},
+        "cpu_baseline": {"value": ref["rate"], "unit": "iter/s", "cores": 1, "kind": "reference",
+                         "host_cores_available": cpu_cores(),
+                         "sample": f"{ref['iters']} steady-state iterations (two-point fit over pdlp_iteration_limit, "
+                                   f"{ref['seconds']:.1f} s; setup {ref['setup_seconds']:.1f} s excluded)"},
+        "e2e": {"value": ref["rate"], "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--workload", default="S3", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    from highs_b200 import engine
+    if engine.device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device; the engine has no CPU fallback")
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    lp = make_lp(args.workload)
+    m, n, k, dense = WORKLOADS[args.workload]
+    nnz = lp.a_matrix_.numNz()
+    K, W = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    prob = engine.Problem(lp, rank=rank, world=world, device=local_rank)
+    if world > 1:
+        ids = [engine.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        prob.comm_init(ids[0])
+    # ---- warm-up: W iterations (also captures the CUDA graphs)
+    prob.solve(iter_limit=W + 1)
+    # ---- timed: exactly K iterations, inputs resident in HBM
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.monotonic()
+    res = prob.solve(iter_limit=K + 1)
+    barrier()
+    wall = time.monotonic() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    assert res["iters"] == K, (res["iters"], K)
+    loop_ms = res["loop_device_ms"]
+    if dist is not None:
+        import torch
+        t = torch.tensor([loop_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        loop_ms = float(t.item())
+    value = K / (loop_ms / 1e3)
+    # ---- per-kernel timing in the real pass sequence (roofline of the dominant kernel)
+    reps = 200
+    kms = prob.bench_pass(reps)
+    B = algorithmic_bytes(prob.n, prob.m, prob.nnz)
+    peak, peak_src = measured_peak_gbs()
+    k_us = [1e3 * v / reps for v in kms]
+    if world == 1:
+        dom = 1 if k_us[1] >= k_us[2] else 2
+        dom_bytes = B["k2"] if dom == 1 else B["k3"]
+        dom_name = "K2 spmv_blocked<Dual> (A x' fused with the dual step)" if dom == 1 else "K3 spmv_blocked<Primal> (A'y' fused with the interaction + step rule)"
+    else:
+        dom, dom_bytes, dom_name = 1, None, "K2 spmv_blocked<Dual> on the local row block"
+    spmv_ms = [prob.bench_spmv(w, 5) and prob.bench_spmv(w, 30) / 30 for w in (0, 1)]
+    roofline = None
+    if world == 1:
+        ach = dom_bytes / (k_us[dom] * 1e-6) / 1e9
+        roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "kernel": dom_name, "algorithmic_bytes_per_launch": dom_bytes, "us_per_launch": k_us[dom],
+                    "peak_source": peak_src,
+                    "per_kernel_us": {"K1_primal_step": k_us[0], "K2_Ax_dual": k_us[1], "K3_ATy_interaction": k_us[2]},
+                    "per_kernel_gbs": {"K1": B["k1"] / k_us[0] / 1e3, "K2": B["k2"] / k_us[1] / 1e3, "K3": B["k3"] / k_us[2] / 1e3},
+                    "plain_spmv_gbs": {"Ax": B["ax"] / spmv_ms[0] / 1e6, "ATy": B["aty"] / spmv_ms[1] / 1e6,
+                                       "note": "back-to-back launches of one plain SpMV (116 MB) partly hit the 126 MB L2"},
+                    "iteration_model": {"bytes": B["iter"], "achieved_gbs": B["iter"] * value / 1e9,
+                                        "frac": B["iter"] * value / 1e9 / peak}}
+    # ---- e2e: host buffers through the public C-ABI call (single GPU only)
+    e2e = None
+    if world == 1:
+        prob.close()
+        t0 = time.monotonic()
+        r2 = engine.solve(lp, iter_limit=K + 1, device=local_rank)
+        e2e_wall = time.monotonic() - t0
+        a = lp.a_matrix_
+        h2d = 2 * (12 * nnz + 4 * (n + m)) + 8 * (5 * n + 3 * m)   # both layouts + cost/bounds/scales/x0 + rhs/scale/y0
+        d2h = 8 * (2 * n + 2 * m)
+        e2e = {"value": K / e2e_wall, "unit": "iter/s", "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
+               "wall_seconds": e2e_wall, "setup_seconds": r2["setup_seconds"], "solve_seconds": r2["solve_seconds"],
+               "note": "one b200pdlp_solve call on host buffers: formulate+scale+layout (host), H2D, K iterations, D2H; "
+                       "bytes are per call divided by K"}
+    if rank != 0:
+        return
+    # ---- CPU baseline: the reference itself on this box's host cores (bounded sample)
+    cpu = None
+    if not args.no_cpu_baseline:
+        from highs_b200.lp import write_b2lp
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, "lp.b2lp")
+            write_b2lp(path, lp)
+            ref = reference_rate(path, 40 if args.workload != "S2" else 400)
+        if ref:
+            cpu = {"value": ref["rate"], "unit": "iter/s", "cores": 1, "kind": "reference",
+                   "host_cores_available": cpu_cores(),
+                   "sample": f"{ref['iters']} steady-state iterations of HiGHS CPU pdlp on the same LP (two-point fit, "
+                             f"{ref['seconds']:.1f} s; O(nnz) setup of {ref['setup_seconds']:.1f} s excluded)"}
+    line = {
+        "metric": "pdhg_iterations_per_sec", "value": value, "unit": "iter/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": loop_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: synthetic random sparse LP m={m} n={n} nnz={nnz} seed={SEED}"
+                               + (f" + one column with {dense} nonzeros" if dense else ""),
+                   "options": "solver=pdlp presolve=off, adaptive step + restarts, checks every 40 iterations",
+                   "l2": "inputs larger than L2 (one iteration streams ~0.37 GB vs 126 MB L2)" if args.workload != "S2"
+                         else "working set fits L2 (S2)",
+                   "parallelism": f"row-partition x{world}" if world > 1 else "single GPU"},
+        "gpu_launches": res["kernel_launches"], "passes": res["passes"], "restarts": res["restarts"],
+        "wall_seconds": wall, "pass_device_ms": res["iter_device_ms"],
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

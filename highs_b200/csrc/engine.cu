@@ -138,11 +138,15 @@ struct b200pdlp_problem {
     if (houts) cudaFreeHost(houts);
     if (stream) cudaStreamDestroy(stream);
   }
-  ReduceScratch rs(int slot) const {
+  ReduceScratch rs(int slot, int len) const {
     // slot-private partial arrays: 16 accumulators x kMaxEwBlocks-or-nblocks each
-    return ReduceScratch{partials.p + (size_t)slot * scratch_stride, counters.p + slot};
+    double* t = (ordered && len <= ordered_cap) ? terms.p + (size_t)slot * 16 * ordered_cap : nullptr;
+    return ReduceScratch{partials.p + (size_t)slot * scratch_stride, counters.p + slot, t, len};
   }
   size_t scratch_stride = 0;
+  DevBuf<double> terms;            // ordered-mode term scratch
+  bool ordered = false;
+  int ordered_cap = 0;
 };
 
 namespace b200 {
@@ -189,6 +193,12 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   p->scratch_stride = 16 * maxgrid;
   p->partials.alloc(p->scratch_stride * kNumSlots);
   p->counters.alloc(kNumSlots);
+  {
+    const int omax = prm.ordered_max == 0 ? 4096 : prm.ordered_max;
+    p->ordered = world == 1 && omax > 0 && std::max(p->n, p->m) <= omax;
+    p->ordered_cap = p->ordered ? std::max(std::max(p->n, p->m), 1) : 0;
+    p->terms.alloc(p->ordered ? (size_t)kNumSlots * 16 * p->ordered_cap : 1);
+  }
   p->outs.alloc(kOutsCount);
   p->state.alloc(1);
   CUDA_OK(cudaMallocHost(&p->hstate, sizeof(PdhgState)));
@@ -202,16 +212,16 @@ static void enqueue_pass(b200pdlp_problem* p) {
   cudaStream_t s = p->stream;
   PdhgState* st = p->state.p;
   launch_primal_step(s, p->n, st, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->cost.p, p->lower.p,
-                     p->upper.p, p->xsum.p, p->rs(kSlotK1));
+                     p->upper.p, p->xsum.p, p->rs(kSlotK1, p->n));
   launch_spmv_dual(s, p->A.dev, st, p->x[0].p, p->x[1].p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p,
-                   p->rhs.p, p->ysum.p, p->form.neq, p->r0, p->rs(kSlotK2));
+                   p->rhs.p, p->ysum.p, p->form.neq, p->r0, p->rs(kSlotK2, p->ml));
   if (p->world == 1) {
     launch_spmv_primal(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p,
-                       p->rs(kSlotK3));
+                       p->rs(kSlotK3, p->n));
   } else {
     launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->redbuf.p);
     allreduce_inplace(p, p->redbuf.p, (size_t)p->n + 1);
-    launch_interaction(s, p->n, st, p->redbuf.p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->rs(kSlotK3));
+    launch_interaction(s, p->n, st, p->redbuf.p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->rs(kSlotK3, p->n));
   }
 }
 
@@ -281,8 +291,8 @@ static CheckResult run_check(b200pdlp_problem* p, bool timed_out_local) {
   ColIter c0{p->x[cur].p, p->aty[cur].p}, c1{p->xavg.p, p->atyavg.p};
   RowIter r0{p->y[cur].p, p->ax[cur].p}, r1{p->yavg.p, p->axavg.p};
   double* o = p->outs.p;
-  launch_col_check_a(s, n, 2, c0, c1, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, p->rs(kSlotChk), o);
-  launch_row_check_a(s, ml, 2, r0, r1, p->rhs.p, p->rowscale.p, f.neq, p->r0, p->rs(kSlotChk), o + 14);
+  launch_col_check_a(s, n, 2, c0, c1, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, p->rs(kSlotChk, n), o);
+  launch_row_check_a(s, ml, 2, r0, r1, p->rhs.p, p->rowscale.p, f.neq, p->r0, p->rs(kSlotChk, ml), o + 14);
   p->launches += 2;
   if (p->world > 1) {
     // row-side partial sums + the time-limit flag travel in one small all-reduce
@@ -315,8 +325,8 @@ static CheckResult run_check(b200pdlp_problem* p, bool timed_out_local) {
     inv_p[t] = 1.0 / pscale[t];
   }
   launch_col_check_b(s, n, 2, c0, c1, inv_d, inv_p, p->cost.p, p->lower.p, p->upper.p, p->colscale.p,
-                     p->rs(kSlotChk), o + 24);
-  launch_row_check_b(s, ml, 2, r0, r1, inv_p, p->rowscale.p, f.neq, p->r0, p->rs(kSlotChk), o + 30);
+                     p->rs(kSlotChk, n), o + 24);
+  launch_row_check_b(s, ml, 2, r0, r1, inv_p, p->rowscale.p, f.neq, p->r0, p->rs(kSlotChk, ml), o + 30);
   p->launches += 2;
   if (p->world > 1) allreduce_inplace(p, o + 30, 2);
   CUDA_OK(cudaMemcpyAsync(p->houts + 24, o + 24, 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -381,8 +391,8 @@ static void do_restart(b200pdlp_problem* p, int choice, const CheckResult& c, Re
     CUDA_OK(cudaMemcpyAsync(p->aty[cur].p, p->atyavg.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
   }
   double* o = p->outs.p + 40;
-  launch_diff_norm2(s, n, p->x[cur].p, p->xlr.p, p->rs(kSlotChk), o);
-  launch_diff_norm2(s, ml, p->y[cur].p, p->ylr.p, p->rs(kSlotChk), o + 1);
+  launch_diff_norm2(s, n, p->x[cur].p, p->xlr.p, p->rs(kSlotChk, n), o);
+  launch_diff_norm2(s, ml, p->y[cur].p, p->ylr.p, p->rs(kSlotChk, ml), o + 1);
   p->launches += 2;
   if (p->world > 1) allreduce_inplace(p, o + 1, 1);
   CUDA_OK(cudaMemcpyAsync(p->houts + 40, o, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -416,7 +426,7 @@ static void arm_step(PdhgState* h) {
 
 static double vec_norm2_sq(b200pdlp_problem* p, const double* v, int len, bool reduce_over_ranks) {
   double* o = p->outs.p + 44;
-  launch_diff_norm2(p->stream, len, v, nullptr, p->rs(kSlotChk), o);
+  launch_diff_norm2(p->stream, len, v, nullptr, p->rs(kSlotChk, len), o);
   p->launches++;
   if (reduce_over_ranks && p->world > 1) allreduce_inplace(p, o, 1);
   CUDA_OK(cudaMemcpyAsync(p->houts + 44, o, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
@@ -445,6 +455,17 @@ static double power_method(b200pdlp_problem* p) {
   return lambda;
 }
 
+static void trace_row(b200pdlp_result* out, const PdhgState* h, const CheckResult& c, int restart) {
+  if (!out->trace || out->trace_len >= out->trace_cap) return;
+  double* t = out->trace + (size_t)out->trace_len * B200PDLP_TRACE_COLS;
+  const Residuals &L = c.it[0], &A = c.it[1];
+  t[0] = h->iter; t[1] = L.pobj; t[2] = L.dobj; t[3] = L.pfeas; t[4] = L.dfeas;
+  t[5] = A.pobj; t[6] = A.dobj; t[7] = A.pfeas; t[8] = A.dfeas;
+  t[9] = h->tau; t[10] = h->sigma; t[11] = h->beta; t[12] = restart; t[13] = h->step_iter;
+  t[14] = h->sum_step; t[15] = 0;
+  out->trace_len++;
+}
+
 static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, const b200pdlp_warm* warm, b200pdlp_result* out) {
   using clk = std::chrono::steady_clock;
   set_device(p);
@@ -458,6 +479,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   PdhgState* h = p->hstate;
   memset(h, 0, sizeof(PdhgState));
   h->adaptive = prm.adaptive_step != 0;
+  out->trace_len = 0;
 
   // ---- initial point: PDHG_PreSolve (hot start, cupdlp_solver.c:1217-1279) + PDHG_Init_Variables (:531-591)
   std::vector<double> x0(n, 0.0), y0(m, 0.0);
@@ -549,6 +571,10 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   CUDA_OK(cudaEventCreate(&ev0));
   CUDA_OK(cudaEventCreate(&ev1));
   double iter_ms = 0.0;
+  cudaEvent_t evl0, evl1;
+  CUDA_OK(cudaEventCreate(&evl0));
+  CUDA_OK(cudaEventCreate(&evl1));
+  CUDA_OK(cudaEventRecord(evl0, s));
   const auto t_loop = clk::now();
 
   // ---- main loop (cupdlp_solver.c:939-1106)
@@ -561,8 +587,8 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
     if (prm.log_level >= 2)
       printf("[b200pdlp] it %8d  pobj %+.8e dobj %+.8e  pfeas %.2e dfeas %.2e | avg pobj %+.8e dobj %+.8e pfeas %.2e dfeas %.2e  tau %.3e sigma %.3e\n",
              h->iter, L.pobj, L.dobj, L.pfeas, L.dfeas, A.pobj, A.dobj, A.pfeas, A.dfeas, h->tau, h->sigma);
-    if (L.pfeas < tol_p && L.dfeas < tol_d && L.relgap < prm.tol_gap) { term = B200PDLP_OPTIMAL; term_iterate = 0; break; }
-    if (A.pfeas < tol_p && A.dfeas < tol_d && A.relgap < prm.tol_gap) { term = B200PDLP_OPTIMAL; term_iterate = 1; break; }
+    if (L.pfeas < tol_p && L.dfeas < tol_d && L.relgap < prm.tol_gap) { term = B200PDLP_OPTIMAL; term_iterate = 0; trace_row(out, h, chk, 0); break; }
+    if (A.pfeas < tol_p && A.dfeas < tol_d && A.relgap < prm.tol_gap) { term = B200PDLP_OPTIMAL; term_iterate = 1; trace_row(out, h, chk, 0); break; }
     {  // PDHG_Check_Infeasibility, cupdlp_solver.c:740-795 (dFeasTol = 1e-8, cupdlp_utils.c:889)
       const double ft = 1e-8;
       bool inf = false;
@@ -571,15 +597,17 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
         if (R.pinf_obj > 0.0 && R.pinf_res < ft * R.pinf_obj) inf = true;
         if (R.dinf_obj < 0.0 && R.dinf_res < -ft * R.dinf_obj) inf = true;
       }
-      if (inf) { term = B200PDLP_INFEASIBLE_OR_UNBOUNDED; break; }
+      if (inf) { term = B200PDLP_INFEASIBLE_OR_UNBOUNDED; trace_row(out, h, chk, 0); break; }
     }
-    if (chk.timed_out) { term = B200PDLP_TIMELIMIT_OR_ITERLIMIT; break; }
-    if (h->iter >= prm.iter_limit - 1) { term = B200PDLP_TIMELIMIT_OR_ITERLIMIT; break; }
+    if (chk.timed_out) { term = B200PDLP_TIMELIMIT_OR_ITERLIMIT; trace_row(out, h, chk, 0); break; }
+    if (h->iter >= prm.iter_limit - 1) { term = B200PDLP_TIMELIMIT_OR_ITERLIMIT; trace_row(out, h, chk, 0); break; }
     bool dirty = false;
+    int choice = 0;
     if (prm.restart) {
-      const int choice = decide_restart(h, chk, memo);
+      choice = decide_restart(h, chk, memo);
       if (choice) { do_restart(p, choice, chk, memo); restarts++; arm_step(h); dirty = true; }
     }
+    trace_row(out, h, chk, choice);
     // next check iteration: < 10, multiple of the interval, or iter_limit - 1 (cupdlp_solver.c:953-962)
     int next = h->iter + 1;
     while (!(next < 10 || next % interval == 0 || next == prm.iter_limit - 1)) next++;
@@ -610,9 +638,16 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
     CUDA_OK(cudaEventElapsedTime(&ms, ev0, ev1));
     iter_ms += ms;
   }
+  CUDA_OK(cudaEventRecord(evl1, s));
+  CUDA_OK(cudaEventSynchronize(evl1));
+  float loop_ms = 0.f;
+  CUDA_OK(cudaEventElapsedTime(&loop_ms, evl0, evl1));
   const double solve_seconds = std::chrono::duration<double>(clk::now() - t_loop).count();
   cudaEventDestroy(ev0);
   cudaEventDestroy(ev1);
+  cudaEventDestroy(evl0);
+  cudaEventDestroy(evl1);
+  out->loop_device_ms = loop_ms;
 
   // ---- PDHG_PostSolve (cupdlp_solver.c:1281-1435)
   const int cur = h->cur;
@@ -822,6 +857,54 @@ int b200pdlp_bench_spmv(b200pdlp_problem* p, int32_t which, int32_t reps, float*
     CUDA_OK(cudaEventElapsedTime(ms_total, e0, e1));
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    CUDA_OK(cudaGetLastError());
+  });
+}
+
+int b200pdlp_bench_pass(b200pdlp_problem* p, int32_t reps, float ms[4]) {
+  return guarded([&] {
+    if (!p || !ms || reps < 1) throw Error(B200PDLP_ERR_ARG, "bad argument");
+    set_device(p);
+    cudaStream_t s = p->stream;
+    PdhgState* st = p->state.p;
+    pull_state(p);
+    p->hstate->stop_iter = 2147483647;
+    fill_pow_tables(p->hstate);
+    push_state(p);
+    cudaEvent_t ev[5];
+    for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
+    double acc[4] = {0, 0, 0, 0};
+    for (int r = 0; r < reps; r++) {
+      if (r % 64 == 63) { pull_state(p); fill_pow_tables(p->hstate); push_state(p); }
+      CUDA_OK(cudaEventRecord(ev[0], s));
+      launch_primal_step(s, p->n, st, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->cost.p, p->lower.p,
+                         p->upper.p, p->xsum.p, p->rs(kSlotK1, p->n));
+      CUDA_OK(cudaEventRecord(ev[1], s));
+      launch_spmv_dual(s, p->A.dev, st, p->x[0].p, p->x[1].p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p,
+                       p->rhs.p, p->ysum.p, p->form.neq, p->r0, p->rs(kSlotK2, p->ml));
+      CUDA_OK(cudaEventRecord(ev[2], s));
+      if (p->world == 1) {
+        launch_spmv_primal(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->x[0].p, p->x[1].p, p->aty[0].p,
+                           p->aty[1].p, p->rs(kSlotK3, p->n));
+        CUDA_OK(cudaEventRecord(ev[3], s));
+      } else {
+        launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->redbuf.p);
+        CUDA_OK(cudaEventRecord(ev[3], s));
+        allreduce_inplace(p, p->redbuf.p, (size_t)p->n + 1);
+        launch_interaction(s, p->n, st, p->redbuf.p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p,
+                           p->rs(kSlotK3, p->n));
+      }
+      CUDA_OK(cudaEventRecord(ev[4], s));
+      CUDA_OK(cudaEventSynchronize(ev[4]));
+      p->launches += p->kernels_per_pass;
+      for (int k = 0; k < 4; k++) {
+        float t = 0.f;
+        CUDA_OK(cudaEventElapsedTime(&t, ev[k], ev[k + 1]));
+        acc[k] += t;
+      }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    for (int k = 0; k < 4; k++) ms[k] = (float)acc[k];
     CUDA_OK(cudaGetLastError());
   });
 }

@@ -70,6 +70,12 @@ struct DevCsr {
 struct ReduceScratch {
   double* partials;   // [nacc][gridDim.x]
   unsigned* counter;  // ticket of the last-block pattern (self-resetting)
+  // ORDERED mode (small problems only): every element's term is also parked in
+  // terms[acc][index]; the last block then adds them in index order, one thread per
+  // accumulator -- the summation order of the reference's sequential CPU loops
+  // (cupdlp_linalg.c:111-126,320-336), which makes whole trajectories bit-identical.
+  double* terms;      // nullptr = tree mode
+  int len;            // elements per accumulator in terms[]
 };
 
 // ----------------------------------------------------------------- reductions
@@ -96,6 +102,12 @@ __device__ __forceinline__ double block_sum(double v, double* smem /*[kThreads/3
 
 // Writes this block's NACC partial sums; the last block to arrive re-reduces all
 // partials in a fixed order and returns true (sums in out[], valid in thread 0).
+// term bookkeeping used by every reducing kernel
+__device__ __forceinline__ void add_term(double& acc, double term, const ReduceScratch& rs, int a, int i) {
+  acc += term;
+  if (rs.terms) rs.terms[(size_t)a * rs.len + i] = term;
+}
+
 template <int NACC>
 __device__ __forceinline__ bool grid_reduce(const double (&acc)[NACC], ReduceScratch rs, double (&out)[NACC]) {
   __shared__ double sm[kThreads / 32];
@@ -114,6 +126,20 @@ __device__ __forceinline__ bool grid_reduce(const double (&acc)[NACC], ReduceScr
   __syncthreads();
   if (!is_last) return false;
   __threadfence();
+  if (rs.terms) {
+    __shared__ double seq[NACC];
+    if (threadIdx.x < NACC) {
+      const volatile double* t = rs.terms + (size_t)threadIdx.x * rs.len;
+      double s = 0.0;
+      for (int i = 0; i < rs.len; i++) s += t[i];
+      seq[threadIdx.x] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < NACC; a++) out[a] = seq[a];
+    if (threadIdx.x == 0) *rs.counter = 0u;
+    return true;
+  }
 #pragma unroll
   for (int a = 0; a < NACC; a++) {
     double s = 0.0;

@@ -33,7 +33,7 @@ primal_step_kernel(int n, PdhgState* __restrict__ st, double* __restrict__ x0, d
     v = v > l ? v : l;
     xn[i] = v;
     const double d = xc - v;
-    acc[0] += d * d;
+    add_term(acc[0], d * d, rs, 0, i);
   }
   double out[1];
   if (grid_reduce<1>(acc, rs, out) && threadIdx.x == 0) st->dx2 = out[0];
@@ -54,7 +54,7 @@ struct PlainEpilogue {
   double* __restrict__ out;
   __device__ bool begin() { return true; }
   __device__ const double* input() const { return in; }
-  __device__ void row(int r, double s, double*) const { out[r] = s; }
+  __device__ double row(int r, double s) const { out[r] = s; return 0.0; }
   __device__ void finalize(const double*) const {}
 };
 
@@ -84,7 +84,7 @@ struct DualEpilogue {
     return true;
   }
   __device__ const double* input() const { return x0; }
-  __device__ void row(int r, double s, double* acc) const {
+  __device__ double row(int r, double s) const {
     axn[r] = s;
     const double yc = y[r];
     if (pend) ysum[r] = ysum[r] + w * yc;
@@ -94,7 +94,7 @@ struct DualEpilogue {
     if (r + row_offset >= neq) v = v > 0.0 ? v : 0.0;
     yn[r] = v;
     const double d = yc - v;
-    acc[0] += d * d;
+    return d * d;
   }
   __device__ void finalize(const double* out) const { st->dy2 = out[0]; }
 };
@@ -168,11 +168,11 @@ struct PrimalEpilogue {
     return true;
   }
   __device__ const double* input() const { return y0; }
-  __device__ void row(int r, double s, double* acc) const {
+  __device__ double row(int r, double s) const {
     atyn[r] = s;
     const double dx = x[r] - xn[r];
     const double da = aty[r] - s;
-    acc[0] += dx * da;
+    return dx * da;
   }
   __device__ void finalize(const double* out) const { step_rule(st, out[0]); }
 };
@@ -210,7 +210,8 @@ __global__ void __launch_bounds__(kThreads) spmv_blocked_kernel(DevCsr A, Epi ep
       const int b = A.rowptr[row] - d.z, e = A.rowptr[row + 1] - d.z;
       double s = 0.0;
       for (int k = b; k < e; k++) s += prod[k];
-      epi.row(row, s, acc);
+      const double term = epi.row(row, s);
+      if constexpr (Epi::NACC > 0) add_term(acc[0], term, rs, 0, row);
     }
   } else {
     // segment of a long row: block-wide tree sum of the segment, then hand-off
@@ -230,7 +231,8 @@ __global__ void __launch_bounds__(kThreads) spmv_blocked_kernel(DevCsr A, Epi ep
         double tot = 0.0;
         for (int k = 0; k < lr.z; k++) tot += p[k];
         A.long_counter[lid] = 0u;
-        epi.row(lr.x, tot, acc);
+        const double term = epi.row(lr.x, tot);
+        if constexpr (Epi::NACC > 0) add_term(acc[0], term, rs, 0, lr.x);
       }
     }
   }
@@ -257,7 +259,7 @@ interaction_kernel(int n, PdhgState* __restrict__ st, const double* __restrict__
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
     const double s = buf[i];
     atyn[i] = s;
-    acc[0] += (x[i] - xn[i]) * (aty[i] - s);
+    add_term(acc[0], (x[i] - xn[i]) * (aty[i] - s), rs, 0, i);
   }
   double out[1];
   if (grid_reduce<1>(acc, rs, out) && threadIdx.x == 0) {
@@ -319,13 +321,13 @@ col_check_a_kernel(int n, int nit, ColIter it0, ColIter it1, const double* __res
       rr = rr + 1.0 * sn;
       rr = rr * sc;
       double* a = acc + 7 * t;
-      a[0] += x * ci;
-      a[1] += sp * lf;
-      a[2] += sn * uf;
-      a[3] += rr * rr;
-      a[4] += sp * sp;
-      a[5] += sn * sn;
-      a[6] += x * x;
+      add_term(a[0], x * ci, rs, 7 * t + 0, i);
+      add_term(a[1], sp * lf, rs, 7 * t + 1, i);
+      add_term(a[2], sn * uf, rs, 7 * t + 2, i);
+      add_term(a[3], rr * rr, rs, 7 * t + 3, i);
+      add_term(a[4], sp * sp, rs, 7 * t + 4, i);
+      add_term(a[5], sn * sn, rs, 7 * t + 5, i);
+      add_term(a[6], x * x, rs, 7 * t + 6, i);
     }
   }
   double res[14];
@@ -355,9 +357,9 @@ row_check_a_kernel(int m, int nit, RowIter it0, RowIter it1, const double* __res
       if (ineq) r = r < 0.0 ? r : 0.0;
       r = r * sc;
       double* a = acc + 3 * t;
-      a[0] += y * bi;
-      a[1] += r * r;
-      a[2] += y * y;
+      add_term(a[0], y * bi, rs, 3 * t + 0, i);
+      add_term(a[1], r * r, rs, 3 * t + 1, i);
+      add_term(a[2], y * y, rs, 3 * t + 2, i);
     }
   }
   double res[6];
@@ -405,9 +407,9 @@ col_check_b_kernel(int n, int nit, ColIter it0, ColIter it1, double inv_dscale0,
       bu = bu * hu;
       bu = bu / sc;
       double* a = acc + 3 * t;
-      a[0] += k * k;
-      a[1] += bl * bl;
-      a[2] += bu * bu;
+      add_term(a[0], k * k, rs, 3 * t + 0, i);
+      add_term(a[1], bl * bl, rs, 3 * t + 1, i);
+      add_term(a[2], bu * bu, rs, 3 * t + 2, i);
     }
   }
   double res[6];
@@ -432,7 +434,7 @@ row_check_b_kernel(int m, int nit, RowIter it0, RowIter it1, double inv_pscale0,
       double k = it.ax[i] * (t ? inv_pscale1 : inv_pscale0);
       if (ineq) k = k < 0.0 ? k : 0.0;
       k = k * sc;
-      acc[t] += k * k;
+      add_term(acc[t], k * k, rs, t, i);
     }
   }
   double res[2];
@@ -447,7 +449,7 @@ diff_norm2_kernel(int len, const double* __restrict__ a, const double* __restric
   const int stride = gridDim.x * kThreads;
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < len; i += stride) {
     const double d = b ? (a[i] + -1.0 * b[i]) : a[i];
-    acc[0] += d * d;
+    add_term(acc[0], d * d, rs, 0, i);
   }
   double res[1];
   if (grid_reduce<1>(acc, rs, res) && threadIdx.x == 0) out[0] = res[0];
@@ -479,7 +481,7 @@ void launch_primal_step(cudaStream_t s, int n, PdhgState* st, double* x0, double
 void launch_spmv_plain(cudaStream_t s, const DevCsr& A, const double* in, double* out) {
   if (A.nblocks == 0) return;
   PlainEpilogue e{in, out};
-  spmv_blocked_kernel<PlainEpilogue><<<A.nblocks, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr});
+  spmv_blocked_kernel<PlainEpilogue><<<A.nblocks, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr, nullptr, 0});
 }
 
 void launch_spmv_dual(cudaStream_t s, const DevCsr& A, PdhgState* st, const double* x0, const double* x1,
@@ -510,14 +512,14 @@ struct PartialAtyEpilogue {
     return true;
   }
   __device__ const double* input() const { return y0; }
-  __device__ void row(int r, double s, double*) const { out[r] = s; }
+  __device__ double row(int r, double s) const { out[r] = s; return 0.0; }
   __device__ void finalize(const double*) const {}
 };
 
 void launch_spmv_partial_aty(cudaStream_t s, const DevCsr& A, PdhgState* st, const double* y0, const double* y1,
                              double* buf) {
   PartialAtyEpilogue e{st, y0, y1, buf};
-  spmv_blocked_kernel<PartialAtyEpilogue><<<A.nblocks, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr});
+  spmv_blocked_kernel<PartialAtyEpilogue><<<A.nblocks, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr, nullptr, 0});
   stash_dy2_kernel<<<1, 1, 0, s>>>(st, buf + A.nrows);
 }
 

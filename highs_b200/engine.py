@@ -38,7 +38,7 @@ class CParams(C.Structure):
                 ("tol_gap", C.c_double), ("time_limit", C.c_double), ("scaling", C.c_int32),
                 ("adaptive_step", C.c_int32), ("restart", C.c_int32), ("log_level", C.c_int32),
                 ("check_interval", C.c_int32), ("device", C.c_int32), ("graph_passes", C.c_int32),
-                ("reserved", C.c_int32 * 4)]
+                ("ordered_max", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class CWarm(C.Structure):
@@ -52,16 +52,16 @@ class CResult(C.Structure):
                 ("restarts", C.c_int32), ("kernel_launches", C.c_int32),
                 ("primal_obj", C.c_double), ("dual_obj", C.c_double), ("primal_feas", C.c_double),
                 ("dual_feas", C.c_double), ("gap", C.c_double), ("rel_gap", C.c_double),
-                ("setup_seconds", C.c_double), ("solve_seconds", C.c_double), ("iter_device_ms", C.c_double),
+                ("setup_seconds", C.c_double), ("solve_seconds", C.c_double), ("iter_device_ms", C.c_double), ("loop_device_ms", C.c_double),
                 ("form_cols", C.c_int32), ("form_rows", C.c_int32), ("form_nnz", C.c_int32),
-                ("form_neq", C.c_int32)]
+                ("form_neq", C.c_int32), ("trace", _dp), ("trace_cap", C.c_int32), ("trace_len", C.c_int32)]
 
 
 # every symbol include/b200pdlp.h declares (tests/test_abi.py checks the library exports them all)
 ABI_SYMBOLS = [
     "b200pdlp_default_params", "b200pdlp_solve", "b200pdlp_problem_create", "b200pdlp_problem_destroy",
     "b200pdlp_problem_dims", "b200pdlp_problem_get_vector", "b200pdlp_problem_get_csr", "b200pdlp_spmv_ax",
-    "b200pdlp_spmv_aty", "b200pdlp_bench_spmv", "b200pdlp_problem_solve", "b200pdlp_nccl_unique_id",
+    "b200pdlp_spmv_aty", "b200pdlp_bench_spmv", "b200pdlp_bench_pass", "b200pdlp_problem_solve", "b200pdlp_nccl_unique_id",
     "b200pdlp_comm_init", "b200pdlp_partition_rows", "b200pdlp_last_error", "b200pdlp_version",
     "b200pdlp_device_count", "b200pdlp_form_create", "b200pdlp_form_destroy", "b200pdlp_form_dims",
     "b200pdlp_form_get_vector", "b200pdlp_form_get_csc", "b200pdlp_form_get_row_map",
@@ -92,6 +92,7 @@ def lib():
         L.b200pdlp_spmv_ax.argtypes = [C.c_void_p, _dp, _dp]
         L.b200pdlp_spmv_aty.argtypes = [C.c_void_p, _dp, _dp]
         L.b200pdlp_bench_spmv.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float)]
+        L.b200pdlp_bench_pass.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_float)]
         L.b200pdlp_problem_solve.argtypes = [C.c_void_p, C.POINTER(CParams), C.POINTER(CWarm), C.POINTER(CResult)]
         L.b200pdlp_nccl_unique_id.argtypes = [C.POINTER(C.c_uint8)]
         L.b200pdlp_comm_init.argtypes = [C.c_void_p, C.POINTER(C.c_uint8)]
@@ -137,16 +138,23 @@ def make_params(**kw) -> CParams:
 
 def _result_dict(res: CResult, arrays) -> dict:
     cv, cd, rv, rd = arrays
-    out = {k: getattr(res, k) for k, _ in CResult._fields_ if k not in ("col_value", "col_dual", "row_value", "row_dual")}
+    skip = ("col_value", "col_dual", "row_value", "row_dual", "trace")
+    out = {k: getattr(res, k) for k, _ in CResult._fields_ if k not in skip}
     out.update(col_value=cv, col_dual=cd, row_value=rv, row_dual=rd, term_name=TERM_NAMES.get(res.term_code, "?"))
+    if len(arrays) > 4:
+        out["trace"] = arrays[4][: res.trace_len].copy()
     return out
 
 
-def _mk_result(lp: HighsLp):
+def _mk_result(lp: HighsLp, trace_cap: int = 0):
     n, m = lp.num_col_, lp.num_row_
     arrays = (np.zeros(n), np.zeros(n), np.zeros(m), np.zeros(m))
     res = CResult()
     res.col_value, res.col_dual, res.row_value, res.row_dual = (_p(a, _dp) for a in arrays)
+    if trace_cap > 0:
+        tr = np.zeros((trace_cap, 16))
+        res.trace, res.trace_cap = _p(tr, _dp), trace_cap
+        arrays = arrays + (tr,)
     return res, arrays
 
 
@@ -157,12 +165,12 @@ def _mk_warm(warm):
     return CWarm(_p(arrs[0], _dp), _p(arrs[1], _dp), _p(arrs[2], _dp)), arrs
 
 
-def solve(lp: HighsLp, warm=None, **params) -> dict:
+def solve(lp: HighsLp, warm=None, trace_cap: int = 0, **params) -> dict:
     """b200pdlp_solve: host buffers in, host buffers out (formulate+scale+upload+PDHG+download)."""
     L = lib()
     clp, keep = make_clp(lp)
     prm = make_params(**params)
-    res, arrays = _mk_result(lp)
+    res, arrays = _mk_result(lp, trace_cap)
     w, wk = _mk_warm(warm)
     _check(L.b200pdlp_solve(C.byref(clp), C.byref(prm), C.byref(w) if w else None, C.byref(res)), "b200pdlp_solve")
     return _result_dict(res, arrays)
@@ -229,13 +237,18 @@ class Problem:
         _check(lib().b200pdlp_bench_spmv(self._h, which, reps, C.byref(ms)), "b200pdlp_bench_spmv")
         return float(ms.value)
 
+    def bench_pass(self, reps: int):
+        ms = (C.c_float * 4)()
+        _check(lib().b200pdlp_bench_pass(self._h, reps, ms), "b200pdlp_bench_pass")
+        return [float(v) for v in ms]
+
     def comm_init(self, unique_id: bytes):
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         _check(lib().b200pdlp_comm_init(self._h, buf), "b200pdlp_comm_init")
 
-    def solve(self, warm=None, **params) -> dict:
+    def solve(self, warm=None, trace_cap: int = 0, **params) -> dict:
         prm = make_params(**params)
-        res, arrays = _mk_result(self.lp)
+        res, arrays = _mk_result(self.lp, trace_cap)
         w, wk = _mk_warm(warm)
         _check(lib().b200pdlp_problem_solve(self._h, C.byref(prm), C.byref(w) if w else None, C.byref(res)),
                "b200pdlp_problem_solve")

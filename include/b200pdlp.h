@@ -75,7 +75,9 @@ typedef struct {
   int32_t check_interval;    /* CUPDLP_RELEASE_INTERVAL; 0 -> 40 */
   int32_t device;            /* CUDA device ordinal; -1 = current */
   int32_t graph_passes;      /* PDHG passes captured per CUDA graph; 0 -> check_interval */
-  int32_t reserved[4];
+  int32_t ordered_max;       /* problems with max(cols,rows) <= this reduce in the reference's
+                                sequential order (bit-identical trajectories); 0 -> 4096, <0 -> off */
+  int32_t reserved[3];
 } b200pdlp_params;
 
 /* Hot start = incoming HighsSolution when value_valid && dual_valid
@@ -106,9 +108,17 @@ typedef struct {
   double setup_seconds;      /* formulate + scale + layout + H2D */
   double solve_seconds;      /* PDHG loop, host wall clock */
   double iter_device_ms;     /* CUDA-event time of the PDHG passes only */
+  double loop_device_ms;     /* CUDA-event time of the whole loop: passes + check iterations + restarts */
   /* form dimensions actually solved */
   int32_t form_cols, form_rows, form_nnz, form_neq;
+  /* optional trajectory trace, one row of B200PDLP_TRACE_COLS doubles per check iteration:
+   * 0 iter, 1 pobj, 2 dobj, 3 pfeas, 4 dfeas (current iterate), 5-8 same for the average,
+   * 9 tau, 10 sigma, 11 beta (after a restart's update), 12 restart (0 none, 1 average, 2 current),
+   * 13 nStepSizeIter, 14 sum of step weights, 15 reserved */
+  double* trace;             /* caller-allocated [trace_cap][16] or NULL */
+  int32_t trace_cap, trace_len;
 } b200pdlp_result;
+#define B200PDLP_TRACE_COLS 16
 
 /* ---- whole solve: the function the HiGHS shim calls ------------------------ */
 void b200pdlp_default_params(b200pdlp_params* p);
@@ -141,6 +151,11 @@ int b200pdlp_spmv_aty(b200pdlp_problem* p, const double* y, double* aty);
 /* device-pointer variants on the problem's stream (bench roofline loop):
  * time `reps` back-to-back launches with CUDA events; returns ms in *ms_total */
 int b200pdlp_bench_spmv(b200pdlp_problem* p, int32_t which /*0 Ax, 1 ATy*/, int32_t reps, float* ms_total);
+
+/* per-kernel CUDA-event timing of `reps` PDHG passes in their real sequence (K1 primal step,
+ * K2 A x + dual step, K3 A'y + interaction [+ all-reduce and K3b when world > 1]); call after a
+ * solve (it continues from that state).  ms[0..3] = summed ms of K1, K2, K3, rest */
+int b200pdlp_bench_pass(b200pdlp_problem* p, int32_t reps, float ms[4]);
 
 /* run the PDHG loop on an uploaded problem (bench "value": inputs resident in HBM) */
 int b200pdlp_problem_solve(b200pdlp_problem* p, const b200pdlp_params* params,
