@@ -458,7 +458,9 @@ static double power_method(b200pdlp_problem* p) {
 static void trace_row(b200pdlp_result* out, const PdhgState* h, const CheckResult& c, int restart) {
   if (!out->trace || out->trace_len >= out->trace_cap) return;
   double* t = out->trace + (size_t)out->trace_len * B200PDLP_TRACE_COLS;
-  const Residuals &L = c.it[0], &A = c.it[1];
+  // after a restart to the average the reference re-evaluates the residuals of the (new) current
+  // iterate (cupdlp_proj.c:145), which are those of the average it was copied from
+  const Residuals &L = restart == 1 ? c.it[1] : c.it[0], &A = c.it[1];
   t[0] = h->iter; t[1] = L.pobj; t[2] = L.dobj; t[3] = L.pfeas; t[4] = L.dfeas;
   t[5] = A.pobj; t[6] = A.dobj; t[7] = A.pfeas; t[8] = A.dfeas;
   t[9] = h->tau; t[10] = h->sigma; t[11] = h->beta; t[12] = restart; t[13] = h->step_iter;

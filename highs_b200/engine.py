@@ -137,7 +137,7 @@ def make_params(**kw) -> CParams:
 
 
 def _result_dict(res: CResult, arrays) -> dict:
-    cv, cd, rv, rd = arrays
+    cv, cd, rv, rd = arrays[:4]
     skip = ("col_value", "col_dual", "row_value", "row_dual", "trace")
     out = {k: getattr(res, k) for k, _ in CResult._fields_ if k not in skip}
     out.update(col_value=cv, col_dual=cd, row_value=rv, row_dual=rd, term_name=TERM_NAMES.get(res.term_code, "?"))
