@@ -67,31 +67,38 @@ struct DevBuf {
 };
 
 struct DeviceMatrix {
-  BlockedCsr host;  // kept for dims / tests (values are released after upload unless keep_host)
-  DevBuf<int> rowptr, col, block_long;
-  DevBuf<double> val, long_partial;
-  DevBuf<int4> blocks, long_rows;
+  SellMatrix host;
+  DevBuf<int> col, lcol;
+  DevBuf<double> val, lval, long_partial;
+  DevBuf<int4> slices, segs, long_rows;
   DevBuf<unsigned> long_counter;
-  DevCsr dev{};
+  DevSell dev{};
   void upload() {
-    rowptr.from(host.rowptr);
+    static_assert(sizeof(SellMatrix::Slice) == sizeof(int4) && sizeof(SellMatrix::Seg) == sizeof(int4) &&
+                  sizeof(SellMatrix::LongRow) == sizeof(int4), "descriptor layouts");
     col.from(host.col);
     val.from(host.val);
-    block_long.from(host.block_long);
-    std::vector<int4> b(host.blocks.size());
-    for (size_t i = 0; i < b.size(); i++) b[i] = make_int4(host.blocks[i].row_begin, host.blocks[i].row_end, host.blocks[i].nnz_begin, host.blocks[i].nnz_end);
-    blocks.from(b);
-    std::vector<int4> l(host.long_rows.size());
-    for (size_t i = 0; i < l.size(); i++) l[i] = make_int4(host.long_rows[i].row, host.long_rows[i].first_block, host.long_rows[i].nseg, host.long_rows[i].partial_offset);
-    long_rows.from(l);
+    lcol.from(host.lcol);
+    lval.from(host.lval);
+    slices.alloc(host.slices.size(), false);
+    slices.upload(reinterpret_cast<const int4*>(host.slices.data()), host.slices.size());
+    segs.alloc(host.segs.size(), false);
+    segs.upload(reinterpret_cast<const int4*>(host.segs.data()), host.segs.size());
+    long_rows.alloc(host.long_rows.size(), false);
+    long_rows.upload(reinterpret_cast<const int4*>(host.long_rows.data()), host.long_rows.size());
     long_partial.alloc(host.n_partials);
     long_counter.alloc(host.long_rows.size());
     dev.nrows = host.nrows;
-    dev.nblocks = (int)host.blocks.size();
-    dev.rowptr = rowptr.p; dev.col = col.p; dev.val = val.p; dev.blocks = blocks.p;
-    dev.block_long = block_long.p; dev.long_rows = long_rows.p;
-    dev.long_partial = long_partial.p; dev.long_counter = long_counter.p;
+    dev.nslices = (int)host.slices.size();
+    dev.nblocks_body = (dev.nslices + kThreads / 32 - 1) / (kThreads / 32);
+    dev.nsegs = (int)host.segs.size();
+    dev.slices = slices.p; dev.col = col.p; dev.val = val.p; dev.segs = segs.p; dev.long_rows = long_rows.p;
+    dev.lcol = lcol.p; dev.lval = lval.p; dev.long_partial = long_partial.p; dev.long_counter = long_counter.p;
+    // the big host copies are not needed any more
+    std::vector<int>().swap(host.col); std::vector<double>().swap(host.val);
+    std::vector<int>().swap(host.lcol); std::vector<double>().swap(host.lval);
   }
+  int grid() const { return dev.nblocks_body + dev.nsegs; }
 };
 
 struct Residuals {      // CUPDLPresobj for one iterate
@@ -111,6 +118,10 @@ struct b200pdlp_problem {
   int r0 = 0, r1 = 0;              // local rows [r0,r1) of the permuted matrix
   int n = 0, m = 0, ml = 0;        // form cols, global rows, local rows
   DeviceMatrix A, AT;              // A_local (ml x n), A_local^T (n x ml)
+  Csr csr_local;                   // A_local in standard-form order (tests)
+  std::vector<int> rperm, rinv;    // device row order: rperm[new] = old local row
+  std::vector<int> cperm, cinv;    // device column order: cperm[new] = old column (same on every rank)
+  int neq_local = 0;               // local equality rows (they stay first under rperm)
   cudaStream_t stream = nullptr;
   // n-vectors (replicated across ranks)
   DevBuf<double> x[2], aty[2], xsum, xavg, atyavg, xlr, cost, lower, upper, colscale;
@@ -176,29 +187,54 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   std::vector<int> bounds = partition_rows(f, world);
   p->r0 = bounds[rank]; p->r1 = bounds[rank + 1];
   p->n = f.n; p->m = f.m; p->ml = p->r1 - p->r0;
-  build_row_major(f, p->r0, p->r1, p->A.host);
-  build_col_major(f, p->r0, p->r1, p->AT.host);
-  CUDA_OK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
-  p->A.upload();
-  p->AT.upload();
   const int n = p->n, ml = p->ml;
-  for (int k = 0; k < 2; k++) { p->x[k].alloc(n); p->aty[k].alloc(n); p->y[k].alloc(ml); p->ax[k].alloc(ml); }
-  p->xsum.alloc(n); p->xavg.alloc(n); p->atyavg.alloc(n); p->xlr.alloc(n);
-  p->ysum.alloc(ml); p->yavg.alloc(ml); p->axavg.alloc(ml); p->ylr.alloc(ml);
-  p->cost.from(f.cost); p->lower.from(f.lower); p->upper.from(f.upper); p->colscale.from(f.col_scale);
-  p->rhs.alloc(ml, false); p->rhs.upload(f.rhs.data() + p->r0, ml);
-  p->rowscale.alloc(ml, false); p->rowscale.upload(f.row_scale.data() + p->r0, ml);
-  p->redbuf.alloc((size_t)std::max(n, p->m) + 16);
-  size_t maxgrid = std::max<size_t>(kMaxEwBlocks, std::max(p->A.host.blocks.size(), p->AT.host.blocks.size()));
-  p->scratch_stride = 16 * maxgrid;
-  p->partials.alloc(p->scratch_stride * kNumSlots);
-  p->counters.alloc(kNumSlots);
   {
     const int omax = prm.ordered_max == 0 ? 4096 : prm.ordered_max;
     p->ordered = world == 1 && omax > 0 && std::max(p->n, p->m) <= omax;
-    p->ordered_cap = p->ordered ? std::max(std::max(p->n, p->m), 1) : 0;
-    p->terms.alloc(p->ordered ? (size_t)kNumSlots * 16 * p->ordered_cap : 1);
   }
+  // device ordering: small (ordered-mode) problems keep the reference's row/column order so that
+  // every sum runs in the reference's order; otherwise rows and columns are sorted by length inside
+  // windows so that the sliced-ELL body carries almost no padding.
+  const bool sort = !p->ordered;
+  const int long_threshold = p->ordered ? std::numeric_limits<int>::max() : 512;
+  p->neq_local = std::max(0, std::min(f.neq - p->r0, ml));
+  {
+    Csr at;
+    build_row_major(f, p->r0, p->r1, p->csr_local);
+    build_col_major(f, p->r0, p->r1, at);
+    p->rperm = make_perm(p->csr_local.rowptr, p->neq_local, sort);
+    p->cperm = make_perm(f.cbeg, n, sort);   // GLOBAL column lengths: identical on every rank
+    p->rinv = invert_perm(p->rperm);
+    p->cinv = invert_perm(p->cperm);
+    build_sell(p->csr_local, p->rperm, p->cinv, long_threshold, p->A.host);
+    build_sell(at, p->cperm, p->rinv, long_threshold, p->AT.host);
+  }
+  CUDA_OK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  p->A.upload();
+  p->AT.upload();
+  for (int k = 0; k < 2; k++) { p->x[k].alloc(n); p->aty[k].alloc(n); p->y[k].alloc(ml); p->ax[k].alloc(ml); }
+  p->xsum.alloc(n); p->xavg.alloc(n); p->atyavg.alloc(n); p->xlr.alloc(n);
+  p->ysum.alloc(ml); p->yavg.alloc(ml); p->axavg.alloc(ml); p->ylr.alloc(ml);
+  {
+    std::vector<double> t(std::max(n, ml));
+    auto up_col = [&](DevBuf<double>& d, const std::vector<double>& v) {
+      for (int j = 0; j < n; j++) t[j] = v[p->cperm[j]];
+      d.alloc(n, false); d.upload(t.data(), n);
+    };
+    auto up_row = [&](DevBuf<double>& d, const std::vector<double>& v) {
+      for (int i = 0; i < ml; i++) t[i] = v[p->r0 + p->rperm[i]];
+      d.alloc(ml, false); d.upload(t.data(), ml);
+    };
+    up_col(p->cost, f.cost); up_col(p->lower, f.lower); up_col(p->upper, f.upper); up_col(p->colscale, f.col_scale);
+    up_row(p->rhs, f.rhs); up_row(p->rowscale, f.row_scale);
+  }
+  p->redbuf.alloc((size_t)std::max(n, p->m) + 16);
+  size_t maxgrid = std::max<size_t>(kMaxEwBlocks, std::max(p->A.grid(), p->AT.grid()));
+  p->scratch_stride = 16 * maxgrid;
+  p->partials.alloc(p->scratch_stride * kNumSlots);
+  p->counters.alloc(kNumSlots);
+  p->ordered_cap = p->ordered ? std::max(std::max(p->n, p->m), 1) : 0;
+  p->terms.alloc(p->ordered ? (size_t)kNumSlots * 16 * p->ordered_cap : 1);
   p->outs.alloc(kOutsCount);
   p->state.alloc(1);
   CUDA_OK(cudaMallocHost(&p->hstate, sizeof(PdhgState)));
@@ -214,7 +250,7 @@ static void enqueue_pass(b200pdlp_problem* p) {
   launch_primal_step(s, p->n, st, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->cost.p, p->lower.p,
                      p->upper.p, p->xsum.p, p->rs(kSlotK1, p->n));
   launch_spmv_dual(s, p->A.dev, st, p->x[0].p, p->x[1].p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p,
-                   p->rhs.p, p->ysum.p, p->form.neq, p->r0, p->rs(kSlotK2, p->ml));
+                   p->rhs.p, p->ysum.p, p->neq_local, 0, p->rs(kSlotK2, p->ml));
   if (p->world == 1) {
     launch_spmv_primal(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p,
                        p->rs(kSlotK3, p->n));
@@ -292,7 +328,7 @@ static CheckResult run_check(b200pdlp_problem* p, bool timed_out_local) {
   RowIter r0{p->y[cur].p, p->ax[cur].p}, r1{p->yavg.p, p->axavg.p};
   double* o = p->outs.p;
   launch_col_check_a(s, n, 2, c0, c1, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, p->rs(kSlotChk, n), o);
-  launch_row_check_a(s, ml, 2, r0, r1, p->rhs.p, p->rowscale.p, f.neq, p->r0, p->rs(kSlotChk, ml), o + 14);
+  launch_row_check_a(s, ml, 2, r0, r1, p->rhs.p, p->rowscale.p, p->neq_local, 0, p->rs(kSlotChk, ml), o + 14);
   p->launches += 2;
   if (p->world > 1) {
     // row-side partial sums + the time-limit flag travel in one small all-reduce
@@ -326,7 +362,7 @@ static CheckResult run_check(b200pdlp_problem* p, bool timed_out_local) {
   }
   launch_col_check_b(s, n, 2, c0, c1, inv_d, inv_p, p->cost.p, p->lower.p, p->upper.p, p->colscale.p,
                      p->rs(kSlotChk, n), o + 24);
-  launch_row_check_b(s, ml, 2, r0, r1, inv_p, p->rowscale.p, f.neq, p->r0, p->rs(kSlotChk, ml), o + 30);
+  launch_row_check_b(s, ml, 2, r0, r1, inv_p, p->rowscale.p, p->neq_local, 0, p->rs(kSlotChk, ml), o + 30);
   p->launches += 2;
   if (p->world > 1) allreduce_inplace(p, o + 30, 2);
   CUDA_OK(cudaMemcpyAsync(p->houts + 24, o + 24, 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -508,8 +544,14 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
     CUDA_OK(cudaMemsetAsync(p->y[k].p, 0, (size_t)std::max(ml, 1) * sizeof(double), s));
     CUDA_OK(cudaMemsetAsync(p->ax[k].p, 0, (size_t)std::max(ml, 1) * sizeof(double), s));
   }
-  CUDA_OK(cudaMemcpyAsync(p->x[0].p, x0.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
-  if (ml) CUDA_OK(cudaMemcpyAsync(p->y[0].p, y0.data() + p->r0, (size_t)ml * sizeof(double), cudaMemcpyHostToDevice, s));
+  {
+    std::vector<double> xp(n), yp(std::max(ml, 1));
+    for (int j = 0; j < n; j++) xp[j] = x0[p->cperm[j]];
+    for (int i = 0; i < ml; i++) yp[i] = y0[p->r0 + p->rperm[i]];
+    CUDA_OK(cudaMemcpyAsync(p->x[0].p, xp.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (ml) CUDA_OK(cudaMemcpyAsync(p->y[0].p, yp.data(), (size_t)ml * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+  }
 
   // ---- PDHG_Init_Step_Sizes (cupdlp_step.c:312-375)
   {
@@ -539,7 +581,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
       double v = 0.0;
       v = v < f.upper[j] ? v : f.upper[j];
       v = v > f.lower[j] ? v : f.lower[j];
-      z[j] = v;
+      z[p->cinv[j]] = v;
       nz |= (v != 0.0);
     }
     if (nz) CUDA_OK(cudaMemcpyAsync(p->xsum.p, z.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -659,21 +701,27 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   const double* dax = use_avg ? p->axavg.p : p->ax[cur].p;
   const double* daty = use_avg ? p->atyavg.p : p->aty[cur].p;
   std::vector<double> hx(n), hy(m, 0.0), hax(m, 0.0), haty(n);
-  CUDA_OK(cudaMemcpyAsync(hx.data(), dx, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
-  CUDA_OK(cudaMemcpyAsync(haty.data(), daty, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
-  if (p->world == 1) {
-    CUDA_OK(cudaMemcpyAsync(hy.data(), dy, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CUDA_OK(cudaMemcpyAsync(hax.data(), dax, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, s));
-  } else {
-    // gather the row-partitioned vectors: zero-padded sum over ranks
-    for (int v = 0; v < 2; v++) {
-      CUDA_OK(cudaMemsetAsync(p->redbuf.p, 0, (size_t)m * sizeof(double), s));
-      CUDA_OK(cudaMemcpyAsync(p->redbuf.p + p->r0, v ? dax : dy, (size_t)ml * sizeof(double), cudaMemcpyDeviceToDevice, s));
-      allreduce_inplace(p, p->redbuf.p, m);
-      CUDA_OK(cudaMemcpyAsync(v ? hax.data() : hy.data(), p->redbuf.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, s));
-    }
+  {
+    // device order -> standard-form order
+    std::vector<double> t(std::max(n, std::max(ml, 1)));
+    auto down_col = [&](const double* d, std::vector<double>& h) {
+      CUDA_OK(cudaMemcpyAsync(t.data(), d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+      CUDA_OK(cudaStreamSynchronize(s));
+      for (int j = 0; j < n; j++) h[p->cperm[j]] = t[j];
+    };
+    auto down_row = [&](const double* d, std::vector<double>& h) {
+      if (ml) CUDA_OK(cudaMemcpyAsync(t.data(), d, (size_t)ml * sizeof(double), cudaMemcpyDeviceToHost, s));
+      CUDA_OK(cudaStreamSynchronize(s));
+      for (int i = 0; i < ml; i++) h[p->r0 + p->rperm[i]] = t[i];
+      if (p->world > 1) {   // other ranks' rows: zero-padded sum
+        CUDA_OK(cudaMemcpyAsync(p->redbuf.p, h.data(), (size_t)m * sizeof(double), cudaMemcpyHostToDevice, s));
+        allreduce_inplace(p, p->redbuf.p, m);
+        CUDA_OK(cudaMemcpyAsync(h.data(), p->redbuf.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CUDA_OK(cudaStreamSynchronize(s));
+      }
+    };
+    down_col(dx, hx); down_col(daty, haty); down_row(dy, hy); down_row(dax, hax);
   }
-  CUDA_OK(cudaStreamSynchronize(s));
   const double inf = std::numeric_limits<double>::infinity();
   if (out->col_value && out->col_dual && out->row_value && out->row_dual) {
     std::vector<double> sp(n, 0.0), sn(n, 0.0);
@@ -784,7 +832,7 @@ int b200pdlp_problem_dims(const b200pdlp_problem* p, int32_t dims[8]) {
   return guarded([&] {
     if (!p || !dims) throw Error(B200PDLP_ERR_ARG, "null argument");
     dims[0] = p->n; dims[1] = p->m; dims[2] = p->form.nnz; dims[3] = p->form.neq;
-    dims[4] = p->ml; dims[5] = p->r0; dims[6] = p->A.host.nnz; dims[7] = p->form.n_orig;
+    dims[4] = p->ml; dims[5] = p->r0; dims[6] = p->csr_local.nnz; dims[7] = p->form.n_orig;
   });
 }
 
@@ -808,7 +856,7 @@ int b200pdlp_problem_get_vector(const b200pdlp_problem* p, int32_t which, double
 
 int b200pdlp_problem_get_csr(const b200pdlp_problem* p, int32_t* rowptr, int32_t* col, double* val) {
   if (!p || !rowptr || !col || !val) return B200PDLP_ERR_ARG;
-  const BlockedCsr& a = p->A.host;
+  const Csr& a = p->csr_local;
   memcpy(rowptr, a.rowptr.data(), (size_t)(a.nrows + 1) * sizeof(int));
   memcpy(col, a.col.data(), (size_t)a.nnz * sizeof(int));
   memcpy(val, a.val.data(), (size_t)a.nnz * sizeof(double));
@@ -819,11 +867,14 @@ int b200pdlp_spmv_ax(b200pdlp_problem* p, const double* x, double* ax) {
   return guarded([&] {
     if (!p || !x || !ax) throw Error(B200PDLP_ERR_ARG, "null argument");
     set_device(p);
-    CUDA_OK(cudaMemcpyAsync(p->xavg.p, x, (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    std::vector<double> t(std::max(p->n, std::max(p->ml, 1)));
+    for (int j = 0; j < p->n; j++) t[j] = x[p->cperm[j]];
+    CUDA_OK(cudaMemcpyAsync(p->xavg.p, t.data(), (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     launch_spmv_plain(p->stream, p->A.dev, p->xavg.p, p->axavg.p);
     p->launches++;
-    CUDA_OK(cudaMemcpyAsync(ax, p->axavg.p, (size_t)p->ml * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     CUDA_OK(cudaStreamSynchronize(p->stream));
+    if (p->ml) CUDA_OK(cudaMemcpy(t.data(), p->axavg.p, (size_t)p->ml * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < p->ml; i++) ax[p->rperm[i]] = t[i];
     CUDA_OK(cudaGetLastError());
   });
 }
@@ -832,11 +883,14 @@ int b200pdlp_spmv_aty(b200pdlp_problem* p, const double* y, double* aty) {
   return guarded([&] {
     if (!p || !y || !aty) throw Error(B200PDLP_ERR_ARG, "null argument");
     set_device(p);
-    CUDA_OK(cudaMemcpyAsync(p->yavg.p, y, (size_t)p->ml * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    std::vector<double> t(std::max(p->n, std::max(p->ml, 1)));
+    for (int i = 0; i < p->ml; i++) t[i] = y[p->rperm[i]];
+    if (p->ml) CUDA_OK(cudaMemcpyAsync(p->yavg.p, t.data(), (size_t)p->ml * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     launch_spmv_plain(p->stream, p->AT.dev, p->yavg.p, p->atyavg.p);   // local partial (no all-reduce)
     p->launches++;
-    CUDA_OK(cudaMemcpyAsync(aty, p->atyavg.p, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     CUDA_OK(cudaStreamSynchronize(p->stream));
+    CUDA_OK(cudaMemcpy(t.data(), p->atyavg.p, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int j = 0; j < p->n; j++) aty[p->cperm[j]] = t[j];
     CUDA_OK(cudaGetLastError());
   });
 }
@@ -883,7 +937,7 @@ int b200pdlp_bench_pass(b200pdlp_problem* p, int32_t reps, float ms[4]) {
                          p->upper.p, p->xsum.p, p->rs(kSlotK1, p->n));
       CUDA_OK(cudaEventRecord(ev[1], s));
       launch_spmv_dual(s, p->A.dev, st, p->x[0].p, p->x[1].p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p,
-                       p->rhs.p, p->ysum.p, p->form.neq, p->r0, p->rs(kSlotK2, p->ml));
+                       p->rhs.p, p->ysum.p, p->neq_local, 0, p->rs(kSlotK2, p->ml));
       CUDA_OK(cudaEventRecord(ev[2], s));
       if (p->world == 1) {
         launch_spmv_primal(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->x[0].p, p->x[1].p, p->aty[0].p,

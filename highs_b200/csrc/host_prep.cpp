@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <limits>
+#include <stdexcept>
 
 namespace b200 {
 
@@ -196,44 +197,8 @@ std::vector<int> partition_rows(const StdForm& f, int world) {
   return b;
 }
 
-namespace {
-void cut_blocks(BlockedCsr& a) {
-  a.blocks.clear(); a.block_long.clear(); a.long_rows.clear(); a.n_partials = 0;
-  int r = 0;
-  while (r < a.nrows) {
-    const int len = a.rowptr[r + 1] - a.rowptr[r];
-    if (len > kNnzPerBlock) {
-      const int nseg = (len + kNnzPerBlock - 1) / kNnzPerBlock;
-      BlockedCsr::LongRow lr{r, (int)a.blocks.size(), nseg, a.n_partials};
-      for (int s = 0; s < nseg; s++) {
-        const int b = a.rowptr[r] + s * kNnzPerBlock;
-        a.blocks.push_back({r, r + 1, b, std::min(b + kNnzPerBlock, a.rowptr[r + 1])});
-        a.block_long.push_back((int)a.long_rows.size());
-      }
-      a.n_partials += nseg;
-      a.long_rows.push_back(lr);
-      r++;
-      continue;
-    }
-    int e = r, cnt = 0;
-    while (e < a.nrows && (e - r) < kMaxRowsPerBlock) {
-      const int l = a.rowptr[e + 1] - a.rowptr[e];
-      if (l > kNnzPerBlock || cnt + l > kNnzPerBlock) break;
-      cnt += l;
-      e++;
-    }
-    a.blocks.push_back({r, e, a.rowptr[r], a.rowptr[e]});
-    a.block_long.push_back(-1);
-    r = e;
-  }
-  const size_t padded = ((size_t)a.nnz + 3) / 4 * 4 + 4;
-  a.col.resize(padded, 0);
-  a.val.resize(padded, 0.0);
-}
-}  // namespace
-
-void build_row_major(const StdForm& f, int r0, int r1, BlockedCsr& a) {
-  a = BlockedCsr();
+void build_row_major(const StdForm& f, int r0, int r1, Csr& a) {
+  a = Csr();
   a.nrows = r1 - r0;
   a.ncols = f.n;
   a.rowptr.assign(a.nrows + 1, 0);
@@ -251,13 +216,12 @@ void build_row_major(const StdForm& f, int r0, int r1, BlockedCsr& a) {
       a.col[q] = j;
       a.val[q] = f.cval[p];
     }
-  cut_blocks(a);
 }
 
-void build_col_major(const StdForm& f, int r0, int r1, BlockedCsr& at) {
+void build_col_major(const StdForm& f, int r0, int r1, Csr& at) {
   // rows of A^T = columns of A restricted to rows [r0,r1), entries sorted by row
   // (the order in which the reference's row-scatter A^T y accumulates, cupdlp_linalg.c:73-109)
-  at = BlockedCsr();
+  at = Csr();
   at.nrows = f.n;
   at.ncols = r1 - r0;
   at.rowptr.assign(f.n + 1, 0);
@@ -290,7 +254,87 @@ void build_col_major(const StdForm& f, int r0, int r1, BlockedCsr& at) {
       for (size_t t = 0; t < tmp.size(); t++) { at.col[at.rowptr[j] + t] = tmp[t].first; at.val[at.rowptr[j] + t] = tmp[t].second; }
     }
   }
-  cut_blocks(at);
+}
+
+std::vector<int> make_perm(const std::vector<int>& rowptr, int boundary, bool sort) {
+  const int n = (int)rowptr.size() - 1;
+  std::vector<int> perm(n);
+  for (int i = 0; i < n; i++) perm[i] = i;
+  if (!sort) return perm;
+  auto len = [&](int r) { return rowptr[r + 1] - rowptr[r]; };
+  auto sort_range = [&](int b, int e) {
+    for (int w = b; w < e; w += kSortWindow) {
+      const int we = std::min(w + kSortWindow, e);
+      std::stable_sort(perm.begin() + w, perm.begin() + we, [&](int x, int y) { return len(x) > len(y); });
+    }
+  };
+  boundary = std::max(0, std::min(boundary, n));
+  sort_range(0, boundary);
+  sort_range(boundary, n);
+  return perm;
+}
+
+std::vector<int> invert_perm(const std::vector<int>& perm) {
+  std::vector<int> inv(perm.size());
+  for (size_t i = 0; i < perm.size(); i++) inv[perm[i]] = (int)i;
+  return inv;
+}
+
+void build_sell(const Csr& a, const std::vector<int>& perm, const std::vector<int>& colmap, int long_threshold,
+                SellMatrix& out) {
+  out = SellMatrix();
+  out.nrows = a.nrows;
+  out.ncols = a.ncols;
+  out.nnz = a.nnz;
+  const int nslices = (a.nrows + 31) / 32;
+  out.slices.resize(nslices);
+  auto len = [&](int newrow) { const int r = perm[newrow]; return a.rowptr[r + 1] - a.rowptr[r]; };
+  long long total = 0;
+  for (int s = 0; s < nslices; s++) {
+    int mx = 0;
+    unsigned mask = 0;
+    for (int l = 0; l < 32; l++) {
+      const int nr = s * 32 + l;
+      if (nr >= a.nrows) { mask |= 1u << l; continue; }
+      const int ln = len(nr);
+      if (ln > long_threshold) { mask |= 1u << l; continue; }
+      mx = std::max(mx, ln);
+    }
+    if (total + 32LL * mx > 2000000000LL) throw std::runtime_error("b200pdlp: matrix too large for 32-bit slice offsets");
+    out.slices[s] = {(int)total, mx, mask, 0};
+    total += 32LL * mx;
+  }
+  out.padded = total;
+  out.col.assign((size_t)total + 32, 0);
+  out.val.assign((size_t)total + 32, 0.0);
+  for (int s = 0; s < nslices; s++) {
+    const SellMatrix::Slice& sl = out.slices[s];
+    for (int l = 0; l < 32; l++) {
+      if ((sl.skipmask >> l) & 1u) continue;
+      const int r = perm[s * 32 + l];
+      int k = 0;
+      for (int p = a.rowptr[r]; p < a.rowptr[r + 1]; p++, k++) {
+        out.col[(size_t)sl.ptr + 32 * (size_t)k + l] = colmap[a.col[p]];
+        out.val[(size_t)sl.ptr + 32 * (size_t)k + l] = a.val[p];
+      }
+    }
+  }
+  // long rows -> segments
+  for (int nr = 0; nr < a.nrows; nr++) {
+    const int ln = len(nr);
+    if (ln <= long_threshold) continue;
+    const int r = perm[nr];
+    const int nseg = (ln + kNnzPerBlock - 1) / kNnzPerBlock;
+    const int base = (int)out.lcol.size();
+    out.long_rows.push_back({nr, (int)out.segs.size(), nseg, out.n_partials});
+    for (int p = a.rowptr[r]; p < a.rowptr[r + 1]; p++) { out.lcol.push_back(colmap[a.col[p]]); out.lval.push_back(a.val[p]); }
+    for (int sg = 0; sg < nseg; sg++)
+      out.segs.push_back({nr, base + sg * kNnzPerBlock, std::min(base + (sg + 1) * kNnzPerBlock, base + ln), (int)out.long_rows.size() - 1});
+    out.n_partials += nseg;
+    while (out.lcol.size() % 4) { out.lcol.push_back(0); out.lval.push_back(0.0); }   // segments start 16-byte aligned
+  }
+  out.lcol.resize(out.lcol.size() + 8, 0);
+  out.lval.resize(out.lval.size() + 8, 0.0);
 }
 
 }  // namespace b200

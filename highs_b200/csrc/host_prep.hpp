@@ -29,32 +29,54 @@ struct StdForm {
   double amax = 0.0;                        // max |a_ij| after scaling
 };
 
-// Row-major matrix cut into blocks of consecutive rows holding <= kNnzPerBlock
-// nonzeros; a row longer than that is split into segment blocks whose partial
-// sums are combined by the last segment to finish.
-struct BlockedCsr {
+// plain row-major matrix (CSR); entries of a row keep the order the reference's scatter SpMV adds them in
+struct Csr {
   int nrows = 0, ncols = 0, nnz = 0;
-  std::vector<int> rowptr;       // [nrows+1]
-  std::vector<int> col;          // [nnz padded to a multiple of 4, +4]
+  std::vector<int> rowptr, col;
   std::vector<double> val;
-  struct Block { int row_begin, row_end, nnz_begin, nnz_end; };
-  std::vector<Block> blocks;
-  std::vector<int> block_long;   // per block: long-row id or -1
-  struct LongRow { int row, first_block, nseg, partial_offset; };
+};
+
+// Device layout of one matrix: sliced ELL body + split long rows.
+//  * body: rows (in `perm` order) are grouped in slices of 32; slice s stores its entries k-major /
+//    lane-minor (element (k, lane) at ptr + 32 k + lane), padded with (col 0, val 0) to the longest
+//    row of the slice, so a warp reads col/val fully coalesced and each lane accumulates ITS row in
+//    registers, in the row's own entry order.  Rows are sorted by length inside windows of
+//    kSortWindow rows (never across the equality / inequality boundary) to keep the padding small.
+//  * rows longer than `long_threshold` are left out of the body (their lanes are masked) and cut into
+//    segments of kNnzPerBlock nonzeros; the last segment CTA to finish combines the partial sums.
+struct SellMatrix {
+  int nrows = 0, ncols = 0;
+  long long nnz = 0, padded = 0;
+  struct Slice { int ptr, len; unsigned skipmask; int pad; };
+  std::vector<Slice> slices;
+  std::vector<int> col;
+  std::vector<double> val;
+  struct Seg { int row, nnz_begin, nnz_end, long_id; };
+  struct LongRow { int row, first_seg, nseg, partial_offset; };
+  std::vector<Seg> segs;
   std::vector<LongRow> long_rows;
+  std::vector<int> lcol;
+  std::vector<double> lval;
   int n_partials = 0;
 };
 
-constexpr int kNnzPerBlock = 2048;
-constexpr int kMaxRowsPerBlock = 1024;
+constexpr int kNnzPerBlock = 2048;   // long-row segment size (== kernels.cuh kNnzBlk)
+constexpr int kSortWindow = 8192;
 
 void formulate(const b200pdlp_lp& lp, StdForm& f);
 void scale(StdForm& f, bool do_scale);
 // nnz-balanced contiguous partition of the m rows into `world` parts
 std::vector<int> partition_rows(const StdForm& f, int world);
 // rows [r0,r1) of A, row-major (columns ascending within a row)
-void build_row_major(const StdForm& f, int r0, int r1, BlockedCsr& a);
+void build_row_major(const StdForm& f, int r0, int r1, Csr& a);
 // transpose of rows [r0,r1): n rows, (r1-r0) columns, local row ids ascending
-void build_col_major(const StdForm& f, int r0, int r1, BlockedCsr& at);
+void build_col_major(const StdForm& f, int r0, int r1, Csr& at);
+// new -> old ordering of `count` rows: identity, or (sort) by descending length inside windows that
+// do not straddle `boundary`
+std::vector<int> make_perm(const std::vector<int>& rowptr, int boundary, bool sort);
+std::vector<int> invert_perm(const std::vector<int>& perm);
+// rows of `a` taken in `perm` order, column ids mapped through `colmap` (old -> new)
+void build_sell(const Csr& a, const std::vector<int>& perm, const std::vector<int>& colmap, int long_threshold,
+                SellMatrix& out);
 
 }  // namespace b200

@@ -54,14 +54,18 @@ struct PdhgState {
   double pow_grow[kPowTab];          // (k+1)^-0.6
 };
 
-struct DevCsr {
-  int nrows, nblocks;
-  const int* __restrict__ rowptr;
+// device view of a SellMatrix (host_prep.hpp)
+struct DevSell {
+  int nrows, nslices;
+  int nblocks_body;                       // CTAs that process slices (8 slices = 256 rows each)
+  int nsegs;                              // + one CTA per long-row segment
+  const int4* __restrict__ slices;        // {ptr, len, skipmask, -}
   const int* __restrict__ col;
   const double* __restrict__ val;
-  const int4* __restrict__ blocks;      // {row_begin,row_end,nnz_begin,nnz_end}
-  const int* __restrict__ block_long;   // long-row id or -1
-  const int4* __restrict__ long_rows;   // {row, first_block, nseg, partial_offset}
+  const int4* __restrict__ segs;          // {row, nnz_begin, nnz_end, long_id}
+  const int4* __restrict__ long_rows;     // {row, first_seg, nseg, partial_offset}
+  const int* __restrict__ lcol;
+  const double* __restrict__ lval;
   double* long_partial;
   unsigned* long_counter;
 };

@@ -39,15 +39,16 @@ primal_step_kernel(int n, PdhgState* __restrict__ st, double* __restrict__ x0, d
   if (grid_reduce<1>(acc, rs, out) && threadIdx.x == 0) st->dx2 = out[0];
 }
 
-// ================================================================= blocked SpMV
-// One CTA streams one block of consecutive rows (<= kNnzBlk nonzeros): phase 1
-// loads col/val with aligned 128-bit loads (int4 / 2 x double2), gathers the
-// dense vector through L2 and parks the products in shared memory; phase 2 gives
-// each row to one thread, which adds its products in column order -- the order in
-// which the reference's scatter SpMV accumulates into each output entry
-// (cupdlp_linalg.c:17-33) -- and runs the fused epilogue on the finished row sum.
-// Rows longer than a block are cut into segment blocks; the last segment to
-// finish combines the partial sums in segment order and runs the epilogue.
+// ===================================================================== SpMV
+// Sliced-ELL body: one warp per slice of 32 rows, one lane per row.  A warp reads the slice's
+// col / val arrays fully coalesced (k-major, lane-minor), every lane gathers its dense-vector
+// entry through L2 and accumulates ITS row in a register, in the row's own entry order -- the
+// order in which the reference's scatter SpMV adds into that output entry (cupdlp_linalg.c:17-33)
+// -- then runs the fused epilogue on the finished row sum.  No shared memory, no shuffles: the
+// L1TEX pipe only sees the coalesced streams and the (irreducible) one-line-per-lane gathers.
+// Rows longer than the long-row threshold live outside the body as segments of kNnzBlk nonzeros
+// (one CTA each, tree-summed); the last segment of a row to finish combines the partial sums in
+// segment order and runs the epilogue.
 struct PlainEpilogue {
   static constexpr int NACC = 0;
   const double* __restrict__ in;
@@ -68,7 +69,7 @@ struct DualEpilogue {
   double *y0, *y1, *ax0, *ax1;
   const double* b;
   double* ysum;
-  int neq, row_offset;         // first global row of this rank (equality test is global)
+  int neq, row_offset;         // neq = number of LOCAL equality rows (they come first); row_offset unused
   // cached from the state block by begin()
   const double *y, *ax;
   double *yn, *axn;
@@ -91,7 +92,7 @@ struct DualEpilogue {
     double v = yc + sigma * b[r];
     v = v + (-2.0 * sigma) * s;
     v = v + sigma * ax[r];
-    if (r + row_offset >= neq) v = v > 0.0 ? v : 0.0;
+    if (r >= neq) v = v > 0.0 ? v : 0.0;
     yn[r] = v;
     const double d = yc - v;
     return d * d;
@@ -178,59 +179,55 @@ struct PrimalEpilogue {
 };
 
 template <class Epi>
-__global__ void __launch_bounds__(kThreads) spmv_blocked_kernel(DevCsr A, Epi epi_arg, ReduceScratch rs) {
-  __shared__ __align__(16) double prod[kNnzBlk];
+__global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_arg, ReduceScratch rs) {
   Epi epi = epi_arg;
   if (!epi.begin()) return;
-  const int4 d = A.blocks[blockIdx.x];
   const double* __restrict__ xin = epi.input();
-  // ---- phase 1: stream the block's nonzeros, gather, multiply
-  const int base = d.z & ~3;
-  for (int e = base + 4 * threadIdx.x; e < d.w; e += 4 * kThreads) {
-    const int4 c4 = *reinterpret_cast<const int4*>(A.col + e);
-    const double2 v01 = *reinterpret_cast<const double2*>(A.val + e);
-    const double2 v23 = *reinterpret_cast<const double2*>(A.val + e + 2);
-    const int cc[4] = {c4.x, c4.y, c4.z, c4.w};
-    const double vv[4] = {v01.x, v01.y, v23.x, v23.y};
-    double g[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) g[k] = (e + k >= d.z && e + k < d.w) ? xin[cc[k]] : 0.0;
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-      if (e + k >= d.z && e + k < d.w) prod[e + k - d.z] = vv[k] * g[k];
-  }
-  __syncthreads();
-  // ---- phase 2: per-row sums in column order + epilogue
   double acc[Epi::NACC > 0 ? Epi::NACC : 1] = {0.0};
-  const int lid = A.block_long[blockIdx.x];
-  if (lid < 0) {
-    const int nrows = d.y - d.x;
-    for (int r = threadIdx.x; r < nrows; r += kThreads) {
-      const int row = d.x + r;
-      const int b = A.rowptr[row] - d.z, e = A.rowptr[row + 1] - d.z;
+  if ((int)blockIdx.x < A.nblocks_body) {
+    const int slice = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (slice < A.nslices) {
+      const int4 d = A.slices[slice];
+      const int* __restrict__ cp = A.col + d.x + lane;
+      const double* __restrict__ vp = A.val + d.x + lane;
       double s = 0.0;
-      for (int k = b; k < e; k++) s += prod[k];
-      const double term = epi.row(row, s);
-      if constexpr (Epi::NACC > 0) add_term(acc[0], term, rs, 0, row);
+      int k = 0;
+      for (; k + 4 <= d.y; k += 4) {
+        const int c0 = cp[32 * k], c1 = cp[32 * k + 32], c2 = cp[32 * k + 64], c3 = cp[32 * k + 96];
+        const double v0 = vp[32 * k], v1 = vp[32 * k + 32], v2 = vp[32 * k + 64], v3 = vp[32 * k + 96];
+        const double g0 = xin[c0], g1 = xin[c1], g2 = xin[c2], g3 = xin[c3];
+        s += v0 * g0;
+        s += v1 * g1;
+        s += v2 * g2;
+        s += v3 * g3;
+      }
+      for (; k < d.y; k++) s += vp[32 * k] * xin[cp[32 * k]];
+      const int row = slice * 32 + lane;
+      if (!((unsigned)d.z >> lane & 1u)) {
+        const double term = epi.row(row, s);
+        if constexpr (Epi::NACC > 0) add_term(acc[0], term, rs, 0, row);
+      }
     }
   } else {
-    // segment of a long row: block-wide tree sum of the segment, then hand-off
+    // one segment of a long row
     __shared__ double sm[kThreads / 32];
+    const int4 sg = A.segs[blockIdx.x - A.nblocks_body];
     double s = 0.0;
-    for (int k = threadIdx.x; k < d.w - d.z; k += kThreads) s += prod[k];
+    for (int e = sg.y + threadIdx.x; e < sg.z; e += kThreads) s += A.lval[e] * xin[A.lcol[e]];
     s = block_sum(s, sm);
     if (threadIdx.x == 0) {
-      const int4 lr = A.long_rows[lid];
-      const int seg = blockIdx.x - lr.y;
+      const int4 lr = A.long_rows[sg.w];
+      const int seg = (int)(blockIdx.x - A.nblocks_body) - lr.y;
       A.long_partial[lr.w + seg] = s;
       __threadfence();
-      const unsigned t = atomicAdd(&A.long_counter[lid], 1u);
+      const unsigned t = atomicAdd(&A.long_counter[sg.w], 1u);
       if (t == (unsigned)lr.z - 1u) {
         __threadfence();
         const volatile double* p = A.long_partial + lr.w;
         double tot = 0.0;
-        for (int k = 0; k < lr.z; k++) tot += p[k];
-        A.long_counter[lid] = 0u;
+        for (int q = 0; q < lr.z; q++) tot += p[q];
+        A.long_counter[sg.w] = 0u;
         const double term = epi.row(lr.x, tot);
         if constexpr (Epi::NACC > 0) add_term(acc[0], term, rs, 0, lr.x);
       }
@@ -478,26 +475,26 @@ void launch_primal_step(cudaStream_t s, int n, PdhgState* st, double* x0, double
   primal_step_kernel<<<ew_grid(n), kThreads, 0, s>>>(n, st, x0, x1, aty0, aty1, c, lo, up, xsum, rs);
 }
 
-void launch_spmv_plain(cudaStream_t s, const DevCsr& A, const double* in, double* out) {
-  if (A.nblocks == 0) return;
+void launch_spmv_plain(cudaStream_t s, const DevSell& A, const double* in, double* out) {
+  if (A.nblocks_body + A.nsegs == 0) return;
   PlainEpilogue e{in, out};
-  spmv_blocked_kernel<PlainEpilogue><<<A.nblocks, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr, nullptr, 0});
+  spmv_sell_kernel<PlainEpilogue><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr, nullptr, 0});
 }
 
-void launch_spmv_dual(cudaStream_t s, const DevCsr& A, PdhgState* st, const double* x0, const double* x1,
+void launch_spmv_dual(cudaStream_t s, const DevSell& A, PdhgState* st, const double* x0, const double* x1,
                       double* y0, double* y1, double* ax0, double* ax1, const double* b, double* ysum,
                       int neq, int row_offset, ReduceScratch rs) {
   DualEpilogue e{};
   e.st = st; e.x0 = x0; e.x1 = x1; e.y0 = y0; e.y1 = y1; e.ax0 = ax0; e.ax1 = ax1; e.b = b; e.ysum = ysum;
   e.neq = neq; e.row_offset = row_offset;
-  spmv_blocked_kernel<DualEpilogue><<<A.nblocks, kThreads, 0, s>>>(A, e, rs);
+  spmv_sell_kernel<DualEpilogue><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, rs);
 }
 
-void launch_spmv_primal(cudaStream_t s, const DevCsr& A, PdhgState* st, const double* y0, const double* y1,
+void launch_spmv_primal(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
                         const double* x0, const double* x1, double* aty0, double* aty1, ReduceScratch rs) {
   PrimalEpilogue e{};
   e.st = st; e.y0 = y0; e.y1 = y1; e.x0 = x0; e.x1 = x1; e.aty0 = aty0; e.aty1 = aty1;
-  spmv_blocked_kernel<PrimalEpilogue><<<A.nblocks, kThreads, 0, s>>>(A, e, rs);
+  spmv_sell_kernel<PrimalEpilogue><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, rs);
 }
 
 // multi-GPU K3a: partial A_g' y' into buf (input chosen by the device state)
@@ -516,10 +513,10 @@ struct PartialAtyEpilogue {
   __device__ void finalize(const double*) const {}
 };
 
-void launch_spmv_partial_aty(cudaStream_t s, const DevCsr& A, PdhgState* st, const double* y0, const double* y1,
+void launch_spmv_partial_aty(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
                              double* buf) {
   PartialAtyEpilogue e{st, y0, y1, buf};
-  spmv_blocked_kernel<PartialAtyEpilogue><<<A.nblocks, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr, nullptr, 0});
+  spmv_sell_kernel<PartialAtyEpilogue><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr, nullptr, 0});
   stash_dy2_kernel<<<1, 1, 0, s>>>(st, buf + A.nrows);
 }
 

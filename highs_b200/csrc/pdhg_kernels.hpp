@@ -10,13 +10,13 @@ struct RowIter { const double* y; const double* ax; };    // one dual-side itera
 void launch_primal_step(cudaStream_t s, int n, PdhgState* st, double* x0, double* x1, const double* aty0,
                         const double* aty1, const double* c, const double* lo, const double* up, double* xsum,
                         ReduceScratch rs);
-void launch_spmv_plain(cudaStream_t s, const DevCsr& A, const double* in, double* out);
-void launch_spmv_dual(cudaStream_t s, const DevCsr& A, PdhgState* st, const double* x0, const double* x1,
+void launch_spmv_plain(cudaStream_t s, const DevSell& A, const double* in, double* out);
+void launch_spmv_dual(cudaStream_t s, const DevSell& A, PdhgState* st, const double* x0, const double* x1,
                       double* y0, double* y1, double* ax0, double* ax1, const double* b, double* ysum,
                       int neq, int row_offset, ReduceScratch rs);
-void launch_spmv_primal(cudaStream_t s, const DevCsr& A, PdhgState* st, const double* y0, const double* y1,
+void launch_spmv_primal(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
                         const double* x0, const double* x1, double* aty0, double* aty1, ReduceScratch rs);
-void launch_spmv_partial_aty(cudaStream_t s, const DevCsr& A, PdhgState* st, const double* y0, const double* y1,
+void launch_spmv_partial_aty(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
                              double* buf);
 void launch_interaction(cudaStream_t s, int n, PdhgState* st, const double* buf, const double* x0,
                         const double* x1, double* aty0, double* aty1, ReduceScratch rs);
