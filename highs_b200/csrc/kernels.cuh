@@ -30,7 +30,7 @@ namespace b200 {
 constexpr int kThreads = 256;          // threads per block, every kernel
 constexpr int kNnzBlk = 2048;          // == host_prep kNnzPerBlock
 constexpr int kPowTab = 128;           // entries of the step-rule power tables
-constexpr int kMaxEwBlocks = 148 * 8;  // grid of the element-wise kernels
+constexpr int kMaxEwBlocks = 148 * 16; // grid cap of the element-wise kernels
 
 // Device-resident control block of the PDHG loop (one per problem).
 struct PdhgState {

@@ -22,18 +22,45 @@ primal_step_kernel(int n, PdhgState* __restrict__ st, double* __restrict__ x0, d
   double* __restrict__ xn = cur ? x0 : x1;
   const double* __restrict__ aty = cur ? aty1 : aty0;
   double acc[1] = {0.0};
-  const int stride = gridDim.x * kThreads;
-  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
-    const double xc = x[i];
-    if (pend) xsum[i] = xsum[i] + w * xc;
-    double v = xc + ntau * c[i];
-    v = v + tau * aty[i];
-    const double u = up[i], l = lo[i];
+  auto one = [&](double xc, double ci, double ai, double u, double l, double& out) {
+    double v = xc + ntau * ci;
+    v = v + tau * ai;
     v = v < u ? v : u;
     v = v > l ? v : l;
-    xn[i] = v;
+    out = v;
     const double d = xc - v;
-    add_term(acc[0], d * d, rs, 0, i);
+    return d * d;
+  };
+  // pairs of elements with 128-bit loads/stores (all vectors are cudaMalloc-aligned)
+  const int npair = n >> 1;
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < npair; i += stride) {
+    const double2 xc = reinterpret_cast<const double2*>(x)[i];
+    const double2 ci = reinterpret_cast<const double2*>(c)[i];
+    const double2 ai = reinterpret_cast<const double2*>(aty)[i];
+    const double2 u = reinterpret_cast<const double2*>(up)[i];
+    const double2 l = reinterpret_cast<const double2*>(lo)[i];
+    if (pend) {
+      double2 sm = reinterpret_cast<double2*>(xsum)[i];
+      sm.x = sm.x + w * xc.x;
+      sm.y = sm.y + w * xc.y;
+      reinterpret_cast<double2*>(xsum)[i] = sm;
+    }
+    double2 o;
+    const double t0 = one(xc.x, ci.x, ai.x, u.x, l.x, o.x);
+    const double t1 = one(xc.y, ci.y, ai.y, u.y, l.y, o.y);
+    reinterpret_cast<double2*>(xn)[i] = o;
+    add_term(acc[0], t0, rs, 0, 2 * i);
+    add_term(acc[0], t1, rs, 0, 2 * i + 1);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int i = n - 1;
+    const double xc = x[i];
+    if (pend) xsum[i] = xsum[i] + w * xc;
+    double o;
+    const double t = one(xc, c[i], aty[i], up[i], lo[i], o);
+    xn[i] = o;
+    add_term(acc[0], t, rs, 0, i);
   }
   double out[1];
   if (grid_reduce<1>(acc, rs, out) && threadIdx.x == 0) st->dx2 = out[0];
@@ -55,6 +82,7 @@ struct PlainEpilogue {
   double* __restrict__ out;
   __device__ bool begin() { return true; }
   __device__ const double* input() const { return in; }
+  __device__ void prefetch(int) {}
   __device__ double row(int r, double s) const { out[r] = s; return 0.0; }
   __device__ void finalize(const double*) const {}
 };
@@ -85,13 +113,19 @@ struct DualEpilogue {
     return true;
   }
   __device__ const double* input() const { return x0; }
+  // the row's epilogue operands are requested BEFORE the gather loop so that they arrive under it
+  double p_y, p_b, p_ax, p_ys;
+  __device__ void prefetch(int r) {
+    p_y = y[r]; p_b = b[r]; p_ax = ax[r];
+    p_ys = pend ? ysum[r] : 0.0;
+  }
   __device__ double row(int r, double s) const {
     axn[r] = s;
-    const double yc = y[r];
-    if (pend) ysum[r] = ysum[r] + w * yc;
-    double v = yc + sigma * b[r];
+    const double yc = p_y;
+    if (pend) ysum[r] = p_ys + w * yc;
+    double v = yc + sigma * p_b;
     v = v + (-2.0 * sigma) * s;
-    v = v + sigma * ax[r];
+    v = v + sigma * p_ax;
     if (r >= neq) v = v > 0.0 ? v : 0.0;
     yn[r] = v;
     const double d = yc - v;
@@ -169,10 +203,12 @@ struct PrimalEpilogue {
     return true;
   }
   __device__ const double* input() const { return y0; }
+  double p_x, p_xn, p_aty;
+  __device__ void prefetch(int r) { p_x = x[r]; p_xn = xn[r]; p_aty = aty[r]; }
   __device__ double row(int r, double s) const {
     atyn[r] = s;
-    const double dx = x[r] - xn[r];
-    const double da = aty[r] - s;
+    const double dx = p_x - p_xn;
+    const double da = p_aty - s;
     return dx * da;
   }
   __device__ void finalize(const double* out) const { step_rule(st, out[0]); }
@@ -189,6 +225,9 @@ __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_
     const int lane = threadIdx.x & 31;
     if (slice < A.nslices) {
       const int4 d = A.slices[slice];
+      const int row = slice * 32 + lane;
+      const bool live = !((unsigned)d.z >> lane & 1u);
+      if (live) epi.prefetch(row);
       const int* __restrict__ cp = A.col + d.x + lane;
       const double* __restrict__ vp = A.val + d.x + lane;
       double s = 0.0;
@@ -203,8 +242,7 @@ __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_
         s += v3 * g3;
       }
       for (; k < d.y; k++) s += vp[32 * k] * xin[cp[32 * k]];
-      const int row = slice * 32 + lane;
-      if (!((unsigned)d.z >> lane & 1u)) {
+      if (live) {
         const double term = epi.row(row, s);
         if constexpr (Epi::NACC > 0) add_term(acc[0], term, rs, 0, row);
       }
@@ -228,6 +266,7 @@ __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_
         double tot = 0.0;
         for (int q = 0; q < lr.z; q++) tot += p[q];
         A.long_counter[sg.w] = 0u;
+        epi.prefetch(lr.x);
         const double term = epi.row(lr.x, tot);
         if constexpr (Epi::NACC > 0) add_term(acc[0], term, rs, 0, lr.x);
       }
@@ -472,7 +511,7 @@ static inline int ew_grid(int len) {
 void launch_primal_step(cudaStream_t s, int n, PdhgState* st, double* x0, double* x1, const double* aty0,
                         const double* aty1, const double* c, const double* lo, const double* up, double* xsum,
                         ReduceScratch rs) {
-  primal_step_kernel<<<ew_grid(n), kThreads, 0, s>>>(n, st, x0, x1, aty0, aty1, c, lo, up, xsum, rs);
+  primal_step_kernel<<<ew_grid((n + 1) / 2), kThreads, 0, s>>>(n, st, x0, x1, aty0, aty1, c, lo, up, xsum, rs);
 }
 
 void launch_spmv_plain(cudaStream_t s, const DevSell& A, const double* in, double* out) {
@@ -509,6 +548,7 @@ struct PartialAtyEpilogue {
     return true;
   }
   __device__ const double* input() const { return y0; }
+  __device__ void prefetch(int) {}
   __device__ double row(int r, double s) const { out[r] = s; return 0.0; }
   __device__ void finalize(const double*) const {}
 };
