@@ -112,46 +112,59 @@ __device__ __forceinline__ void add_term(double& acc, double term, const ReduceS
   if (rs.terms) rs.terms[(size_t)a * rs.len + i] = term;
 }
 
+// Two-stage deterministic sum over the grid.  Every warp parks its shuffle-reduced partials in
+// shared memory; after ONE block barrier warps 1.. retire and warp 0 alone writes the block's
+// partials, takes a ticket, and -- if it is the last block of the grid -- re-reduces all block
+// partials in a fixed order.  Returns true in the last block only, with the sums in out[] (valid in
+// thread 0).  Only threads of warp 0 return true/false meaningfully; other warps return false.
 template <int NACC>
 __device__ __forceinline__ bool grid_reduce(const double (&acc)[NACC], ReduceScratch rs, double (&out)[NACC]) {
-  __shared__ double sm[kThreads / 32];
-  __shared__ bool is_last;
+  constexpr int kWarps = kThreads / 32;
+  __shared__ double sm[NACC][kWarps];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nb = gridDim.x;
 #pragma unroll
   for (int a = 0; a < NACC; a++) {
-    double s = block_sum(acc[a], sm);
-    if (threadIdx.x == 0) rs.partials[(size_t)a * nb + blockIdx.x] = s;
+    const double s = warp_sum(acc[a]);
+    if (lane == 0) sm[a][wid] = s;
   }
-  __threadfence();
-  if (threadIdx.x == 0) {
-    unsigned t = atomicAdd(rs.counter, 1u);
-    is_last = (t == (unsigned)nb - 1u);
-  }
+  if (rs.terms) __threadfence();   // ordered mode: every thread's terms[] must be visible to the last block
   __syncthreads();
-  if (!is_last) return false;
+  if (wid != 0) return false;
+  if (lane == 0) {
+#pragma unroll
+    for (int a = 0; a < NACC; a++) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWarps; w++) s += sm[a][w];
+      rs.partials[(size_t)a * nb + blockIdx.x] = s;
+    }
+    __threadfence();
+  }
+  unsigned ticket = 0;
+  if (lane == 0) ticket = atomicAdd(rs.counter, 1u);
+  ticket = __shfl_sync(0xffffffffu, ticket, 0);
+  if (ticket != (unsigned)nb - 1u) return false;
   __threadfence();
   if (rs.terms) {
-    __shared__ double seq[NACC];
-    if (threadIdx.x < NACC) {
-      const volatile double* t = rs.terms + (size_t)threadIdx.x * rs.len;
-      double s = 0.0;
-      for (int i = 0; i < rs.len; i++) s += t[i];
-      seq[threadIdx.x] = s;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int a = 0; a < NACC; a++) out[a] = seq[a];
-    if (threadIdx.x == 0) *rs.counter = 0u;
-    return true;
-  }
-#pragma unroll
-  for (int a = 0; a < NACC; a++) {
+    // ordered mode: lane a adds accumulator a's terms in index order
     double s = 0.0;
-    const volatile double* p = rs.partials + (size_t)a * nb;
-    for (int i = threadIdx.x; i < nb; i += kThreads) s += p[i];
-    out[a] = block_sum(s, sm);
+    if (lane < NACC) {
+      const volatile double* t = rs.terms + (size_t)lane * rs.len;
+      for (int i = 0; i < rs.len; i++) s += t[i];
+    }
+#pragma unroll
+    for (int a = 0; a < NACC; a++) out[a] = __shfl_sync(0xffffffffu, s, a);
+  } else {
+#pragma unroll
+    for (int a = 0; a < NACC; a++) {
+      double s = 0.0;
+      const volatile double* p = rs.partials + (size_t)a * nb;
+      for (int i = lane; i < nb; i += 32) s += p[i];
+      out[a] = warp_sum(s);
+    }
   }
-  if (threadIdx.x == 0) *rs.counter = 0u;
+  if (lane == 0) *rs.counter = 0u;
   return true;
 }
 

@@ -232,10 +232,22 @@ __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_
       const double* __restrict__ vp = A.val + d.x + lane;
       double s = 0.0;
       int k = 0;
+      for (; k + 8 <= d.y; k += 8) {
+        int c[8];
+        double v[8], g[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) c[u] = cp[32 * (k + u)];
+#pragma unroll
+        for (int u = 0; u < 8; u++) g[u] = xin[c[u]];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = vp[32 * (k + u)];
+#pragma unroll
+        for (int u = 0; u < 8; u++) s += v[u] * g[u];
+      }
       for (; k + 4 <= d.y; k += 4) {
         const int c0 = cp[32 * k], c1 = cp[32 * k + 32], c2 = cp[32 * k + 64], c3 = cp[32 * k + 96];
-        const double v0 = vp[32 * k], v1 = vp[32 * k + 32], v2 = vp[32 * k + 64], v3 = vp[32 * k + 96];
         const double g0 = xin[c0], g1 = xin[c1], g2 = xin[c2], g3 = xin[c3];
+        const double v0 = vp[32 * k], v1 = vp[32 * k + 32], v2 = vp[32 * k + 64], v3 = vp[32 * k + 96];
         s += v0 * g0;
         s += v1 * g1;
         s += v2 * g2;
