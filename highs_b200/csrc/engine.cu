@@ -13,6 +13,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <stdexcept>
@@ -94,6 +95,8 @@ struct DeviceMatrix {
     dev.nsegs = (int)host.segs.size();
     dev.slices = slices.p; dev.col = col.p; dev.val = val.p; dev.segs = segs.p; dev.long_rows = long_rows.p;
     dev.lcol = lcol.p; dev.lval = lval.p; dev.long_partial = long_partial.p; dev.long_counter = long_counter.p;
+    dev.padded_total = (int)host.padded;
+    dev.prefetch_dist = 0;
     // the big host copies are not needed any more
     std::vector<int>().swap(host.col); std::vector<double>().swap(host.val);
     std::vector<int>().swap(host.lcol); std::vector<double>().swap(host.lval);
@@ -152,12 +155,13 @@ struct b200pdlp_problem {
   ReduceScratch rs(int slot, int len) const {
     // slot-private partial arrays: 16 accumulators x kMaxEwBlocks-or-nblocks each
     double* t = (ordered && len <= ordered_cap) ? terms.p + (size_t)slot * 16 * ordered_cap : nullptr;
-    return ReduceScratch{partials.p + (size_t)slot * scratch_stride, counters.p + slot, t, len};
+    return ReduceScratch{partials.p + (size_t)slot * scratch_stride, counters.p + slot, t, len, exp_flags & 1};
   }
   size_t scratch_stride = 0;
   DevBuf<double> terms;            // ordered-mode term scratch
   bool ordered = false;
   int ordered_cap = 0;
+  int exp_flags = 0;               // B200PDLP_EXP environment switches (timing experiments)
 };
 
 namespace b200 {
@@ -212,6 +216,8 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   CUDA_OK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   p->A.upload();
   p->AT.upload();
+  if (const char* e = getenv("B200PDLP_EXP")) p->exp_flags = atoi(e);
+  if (const char* e = getenv("B200PDLP_PREFETCH")) { p->A.dev.prefetch_dist = atoi(e); p->AT.dev.prefetch_dist = atoi(e); }
   for (int k = 0; k < 2; k++) { p->x[k].alloc(n); p->aty[k].alloc(n); p->y[k].alloc(ml); p->ax[k].alloc(ml); }
   p->xsum.alloc(n); p->xavg.alloc(n); p->atyavg.alloc(n); p->xlr.alloc(n);
   p->ysum.alloc(ml); p->yavg.alloc(ml); p->axavg.alloc(ml); p->ylr.alloc(ml);
@@ -247,17 +253,19 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
 static void enqueue_pass(b200pdlp_problem* p) {
   cudaStream_t s = p->stream;
   PdhgState* st = p->state.p;
+  const ReduceScratch r1 = p->rs(kSlotK1, p->n), r2 = p->rs(kSlotK2, p->ml), r3 = p->rs(kSlotK3, p->n);
   launch_primal_step(s, p->n, st, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->cost.p, p->lower.p,
-                     p->upper.p, p->xsum.p, p->rs(kSlotK1, p->n));
+                     p->upper.p, p->xsum.p, r1);
   launch_spmv_dual(s, p->A.dev, st, p->x[0].p, p->x[1].p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p,
-                   p->rhs.p, p->ysum.p, p->neq_local, 0, p->rs(kSlotK2, p->ml));
+                   p->rhs.p, p->ysum.p, p->neq_local, 0, r2);
   if (p->world == 1) {
-    launch_spmv_primal(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p,
-                       p->rs(kSlotK3, p->n));
+    launch_spmv_primal(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, r3);
+    launch_step_rule(s, st, r1, primal_step_grid(p->n), r2, p->A.grid(), r3, p->AT.grid(), nullptr);
   } else {
-    launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->redbuf.p);
+    launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->redbuf.p, r2.partials, p->A.grid());
     allreduce_inplace(p, p->redbuf.p, (size_t)p->n + 1);
-    launch_interaction(s, p->n, st, p->redbuf.p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->rs(kSlotK3, p->n));
+    launch_interaction(s, p->n, st, p->redbuf.p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, r3);
+    launch_step_rule(s, st, r1, primal_step_grid(p->n), r2, p->A.grid(), r3, interaction_grid(p->n), p->redbuf.p + p->n);
   }
 }
 
@@ -604,7 +612,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
     p->graph_main_passes = want_main;
   }
   if (!p->graph_small) { p->graph_small_passes = 4; p->graph_small = capture_passes(p, 4); }
-  p->kernels_per_pass = p->world == 1 ? 3 : 5;
+  p->kernels_per_pass = p->world == 1 ? 4 : 6;
 
   const double tol_p = prm.tol_primal * (1.0 + f.norm_rhs), tol_d = prm.tol_dual * (1.0 + f.norm_cost);
   RestartMemo memo;
@@ -932,23 +940,25 @@ int b200pdlp_bench_pass(b200pdlp_problem* p, int32_t reps, float ms[4]) {
     double acc[4] = {0, 0, 0, 0};
     for (int r = 0; r < reps; r++) {
       if (r % 64 == 63) { pull_state(p); fill_pow_tables(p->hstate); push_state(p); }
+      const ReduceScratch r1 = p->rs(kSlotK1, p->n), r2 = p->rs(kSlotK2, p->ml), r3 = p->rs(kSlotK3, p->n);
       CUDA_OK(cudaEventRecord(ev[0], s));
       launch_primal_step(s, p->n, st, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->cost.p, p->lower.p,
-                         p->upper.p, p->xsum.p, p->rs(kSlotK1, p->n));
+                         p->upper.p, p->xsum.p, r1);
       CUDA_OK(cudaEventRecord(ev[1], s));
       launch_spmv_dual(s, p->A.dev, st, p->x[0].p, p->x[1].p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p,
-                       p->rhs.p, p->ysum.p, p->neq_local, 0, p->rs(kSlotK2, p->ml));
+                       p->rhs.p, p->ysum.p, p->neq_local, 0, r2);
       CUDA_OK(cudaEventRecord(ev[2], s));
       if (p->world == 1) {
         launch_spmv_primal(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->x[0].p, p->x[1].p, p->aty[0].p,
-                           p->aty[1].p, p->rs(kSlotK3, p->n));
+                           p->aty[1].p, r3);
         CUDA_OK(cudaEventRecord(ev[3], s));
+        launch_step_rule(s, st, r1, primal_step_grid(p->n), r2, p->A.grid(), r3, p->AT.grid(), nullptr);
       } else {
-        launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->redbuf.p);
+        launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->redbuf.p, r2.partials, p->A.grid());
         CUDA_OK(cudaEventRecord(ev[3], s));
         allreduce_inplace(p, p->redbuf.p, (size_t)p->n + 1);
-        launch_interaction(s, p->n, st, p->redbuf.p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p,
-                           p->rs(kSlotK3, p->n));
+        launch_interaction(s, p->n, st, p->redbuf.p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, r3);
+        launch_step_rule(s, st, r1, primal_step_grid(p->n), r2, p->A.grid(), r3, interaction_grid(p->n), p->redbuf.p + p->n);
       }
       CUDA_OK(cudaEventRecord(ev[4], s));
       CUDA_OK(cudaEventSynchronize(ev[4]));

@@ -68,6 +68,8 @@ struct DevSell {
   const double* __restrict__ lval;
   double* long_partial;
   unsigned* long_counter;
+  int prefetch_dist;                      // CTAs ahead whose col/val range is pulled into L2 (0 = off)
+  int padded_total;                       // elements in col/val (end of the last slice)
 };
 
 // scratch of the two-stage deterministic reductions
@@ -80,6 +82,7 @@ struct ReduceScratch {
   // (cupdlp_linalg.c:111-126,320-336), which makes whole trajectories bit-identical.
   double* terms;      // nullptr = tree mode
   int len;            // elements per accumulator in terms[]
+  int flags;          // experiment switches (bit 0: skip the grid reduction -- timing experiments only)
 };
 
 // ----------------------------------------------------------------- reductions
@@ -112,6 +115,31 @@ __device__ __forceinline__ void add_term(double& acc, double term, const ReduceS
   if (rs.terms) rs.terms[(size_t)a * rs.len + i] = term;
 }
 
+// Stage 1 of the per-pass reductions: the block's partial sums go to partials[acc][block]; no fence,
+// no ticket -- the (tiny) step_rule_kernel that follows in the stream adds them up in a fixed order.
+// (A ticketed in-kernel final reduction costs ~15 us per SpMV launch at 4k CTAs: measured, profiles/.)
+template <int NACC>
+__device__ __forceinline__ void block_partials(const double (&acc)[NACC], const ReduceScratch& rs) {
+  constexpr int kWarps = kThreads / 32;
+  __shared__ double smp[NACC][kWarps];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int a = 0; a < NACC; a++) {
+    const double s = warp_sum(acc[a]);
+    if (lane == 0) smp[a][wid] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int a = 0; a < NACC; a++) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWarps; w++) s += smp[a][w];
+      rs.partials[(size_t)a * gridDim.x + blockIdx.x] = s;
+    }
+  }
+}
+
 // Two-stage deterministic sum over the grid.  Every warp parks its shuffle-reduced partials in
 // shared memory; after ONE block barrier warps 1.. retire and warp 0 alone writes the block's
 // partials, takes a ticket, and -- if it is the last block of the grid -- re-reduces all block
@@ -123,6 +151,7 @@ __device__ __forceinline__ bool grid_reduce(const double (&acc)[NACC], ReduceScr
   __shared__ double sm[NACC][kWarps];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nb = gridDim.x;
+  if (rs.flags & 1) return false;
 #pragma unroll
   for (int a = 0; a < NACC; a++) {
     const double s = warp_sum(acc[a]);
@@ -158,10 +187,16 @@ __device__ __forceinline__ bool grid_reduce(const double (&acc)[NACC], ReduceScr
   } else {
 #pragma unroll
     for (int a = 0; a < NACC; a++) {
-      double s = 0.0;
-      const volatile double* p = rs.partials + (size_t)a * nb;
-      for (int i = lane; i < nb; i += 32) s += p[i];
-      out[a] = warp_sum(s);
+      // fixed order: lane l adds partials l, l+32, ... (four independent L2 loads in flight), then a warp tree
+      const double* p = rs.partials + (size_t)a * nb;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int i = lane;
+      for (; i + 96 < nb; i += 128) {
+        const double v0 = __ldcg(p + i), v1 = __ldcg(p + i + 32), v2 = __ldcg(p + i + 64), v3 = __ldcg(p + i + 96);
+        s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+      }
+      for (; i < nb; i += 32) s0 += __ldcg(p + i);
+      out[a] = warp_sum((s0 + s1) + (s2 + s3));
     }
   }
   if (lane == 0) *rs.counter = 0u;

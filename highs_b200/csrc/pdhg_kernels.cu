@@ -62,8 +62,7 @@ primal_step_kernel(int n, PdhgState* __restrict__ st, double* __restrict__ x0, d
     xn[i] = o;
     add_term(acc[0], t, rs, 0, i);
   }
-  double out[1];
-  if (grid_reduce<1>(acc, rs, out) && threadIdx.x == 0) st->dx2 = out[0];
+  block_partials<1>(acc, rs);
 }
 
 // ===================================================================== SpMV
@@ -214,12 +213,76 @@ struct PrimalEpilogue {
   __device__ void finalize(const double* out) const { step_rule(st, out[0]); }
 };
 
+// K4: one CTA adds the block partials of K1 (|dx|^2), K2 (|dy|^2) and K3 (interaction) in a fixed
+// order -- or, in ordered mode, the per-element terms in index order -- and applies the step rule.
+// dy2_override != nullptr (multi-GPU): |dy|^2 is the all-reduced scalar instead of local partials.
+constexpr int kStepThreads = 1024;
+__global__ void __launch_bounds__(kStepThreads)
+step_rule_kernel(PdhgState* __restrict__ st, ReduceScratch r1, int nb1, ReduceScratch r2, int nb2, ReduceScratch r3,
+                 int nb3, const double* __restrict__ dy2_override) {
+  if (st->iter >= st->stop_iter) return;
+  __shared__ double sm[3][kStepThreads / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double tot[3];
+  if (r1.terms) {
+    // ordered mode: thread a adds accumulator a's terms sequentially
+    const ReduceScratch* rr[3] = {&r1, &r2, &r3};
+    double s = 0.0;
+    if (threadIdx.x < 3) {
+      const double* t = rr[threadIdx.x]->terms;
+      const int len = rr[threadIdx.x]->len;
+      for (int i = 0; i < len; i++) s += t[i];
+      sm[threadIdx.x][0] = s;
+    }
+    __syncthreads();
+    tot[0] = sm[0][0]; tot[1] = sm[1][0]; tot[2] = sm[2][0];
+  } else {
+    const double* pp[3] = {r1.partials, r2.partials, r3.partials};
+    const int nb[3] = {nb1, nb2, nb3};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      double s = 0.0;
+      for (int i = threadIdx.x; i < nb[a]; i += kStepThreads) s += pp[a][i];
+      s = warp_sum(s);
+      if (lane == 0) sm[a][wid] = s;
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        double s = lane < kStepThreads / 32 ? sm[a][lane] : 0.0;
+        tot[a] = warp_sum(s);
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    st->dx2 = tot[0];
+    st->dy2 = dy2_override ? *dy2_override : tot[1];
+    step_rule(st, tot[2]);
+  }
+}
+
 template <class Epi>
 __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_arg, ReduceScratch rs) {
   Epi epi = epi_arg;
   if (!epi.begin()) return;
   const double* __restrict__ xin = epi.input();
   double acc[Epi::NACC > 0 ? Epi::NACC : 1] = {0.0};
+  if (A.prefetch_dist > 0 && threadIdx.x == 0) {
+    // pull the col/val range of a CTA that will run one residency wave later into L2, so that its
+    // streaming loads hold their L1 miss slots for an L2 round trip instead of an HBM one
+    const int b2 = blockIdx.x + A.prefetch_dist;
+    if (b2 < A.nblocks_body) {
+      const int s0 = b2 * (kThreads / 32), s1 = s0 + (kThreads / 32);
+      const int p0 = A.slices[s0].x;
+      const int p1 = s1 < A.nslices ? A.slices[s1].x : A.padded_total;
+      const unsigned nb4 = (unsigned)(p1 - p0) * 4u, nb8 = (unsigned)(p1 - p0) * 8u;
+      if (nb4) {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.col + p0), "r"(nb4) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.val + p0), "r"(nb8) : "memory");
+      }
+    }
+  }
   if ((int)blockIdx.x < A.nblocks_body) {
     const int slice = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -284,10 +347,7 @@ __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_
       }
     }
   }
-  if constexpr (Epi::NACC > 0) {
-    double out[Epi::NACC];
-    if (grid_reduce<Epi::NACC>(acc, rs, out) && threadIdx.x == 0) epi.finalize(out);
-  }
+  if constexpr (Epi::NACC > 0) block_partials<Epi::NACC>(acc, rs);
 }
 
 // ======================================== multi-GPU K3b: after the all-reduce
@@ -309,17 +369,25 @@ interaction_kernel(int n, PdhgState* __restrict__ st, const double* __restrict__
     atyn[i] = s;
     add_term(acc[0], (x[i] - xn[i]) * (aty[i] - s), rs, 0, i);
   }
-  double out[1];
-  if (grid_reduce<1>(acc, rs, out) && threadIdx.x == 0) {
-    st->dy2 = buf[n];
-    step_rule(st, out[0]);
-  }
+  block_partials<1>(acc, rs);
 }
 
-// copies the local |dy|^2 into the tail slot of the all-reduce buffer
-__global__ void stash_dy2_kernel(PdhgState* st, double* slot) {
-  if (st->iter >= st->stop_iter) { *slot = 0.0; return; }
-  *slot = st->dy2;
+// multi-GPU: adds the local |dy|^2 block partials of K2 (fixed order) into the tail slot of the
+// all-reduce buffer
+__global__ void __launch_bounds__(kStepThreads) stash_dy2_kernel(PdhgState* st, const double* __restrict__ partials, int nb, double* slot) {
+  __shared__ double sm[kStepThreads / 32];
+  if (st->iter >= st->stop_iter) { if (threadIdx.x == 0) *slot = 0.0; return; }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nb; i += kStepThreads) s += partials[i];
+  s = warp_sum(s);
+  if (lane == 0) sm[wid] = s;
+  __syncthreads();
+  if (wid == 0) {
+    s = lane < kStepThreads / 32 ? sm[lane] : 0.0;
+    s = warp_sum(s);
+    if (lane == 0) *slot = s;
+  }
 }
 
 // ===================================================== check-iteration kernels
@@ -529,7 +597,7 @@ void launch_primal_step(cudaStream_t s, int n, PdhgState* st, double* x0, double
 void launch_spmv_plain(cudaStream_t s, const DevSell& A, const double* in, double* out) {
   if (A.nblocks_body + A.nsegs == 0) return;
   PlainEpilogue e{in, out};
-  spmv_sell_kernel<PlainEpilogue><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr, nullptr, 0});
+  spmv_sell_kernel<PlainEpilogue><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr, nullptr, 0, 0});
 }
 
 void launch_spmv_dual(cudaStream_t s, const DevSell& A, PdhgState* st, const double* x0, const double* x1,
@@ -566,11 +634,19 @@ struct PartialAtyEpilogue {
 };
 
 void launch_spmv_partial_aty(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
-                             double* buf) {
+                             double* buf, const double* dy2_partials, int dy2_nb) {
   PartialAtyEpilogue e{st, y0, y1, buf};
-  spmv_sell_kernel<PartialAtyEpilogue><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr, nullptr, 0});
-  stash_dy2_kernel<<<1, 1, 0, s>>>(st, buf + A.nrows);
+  spmv_sell_kernel<PartialAtyEpilogue><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr, nullptr, 0, 0});
+  stash_dy2_kernel<<<1, kStepThreads, 0, s>>>(st, dy2_partials, dy2_nb, buf + A.nrows);
 }
+
+void launch_step_rule(cudaStream_t s, PdhgState* st, ReduceScratch r1, int nb1, ReduceScratch r2, int nb2,
+                      ReduceScratch r3, int nb3, const double* dy2_override) {
+  step_rule_kernel<<<1, kStepThreads, 0, s>>>(st, r1, nb1, r2, nb2, r3, nb3, dy2_override);
+}
+
+int primal_step_grid(int n) { return ew_grid((n + 1) / 2); }
+int interaction_grid(int n) { return ew_grid(n); }
 
 void launch_interaction(cudaStream_t s, int n, PdhgState* st, const double* buf, const double* x0,
                         const double* x1, double* aty0, double* aty1, ReduceScratch rs) {

@@ -17,7 +17,11 @@ void launch_spmv_dual(cudaStream_t s, const DevSell& A, PdhgState* st, const dou
 void launch_spmv_primal(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
                         const double* x0, const double* x1, double* aty0, double* aty1, ReduceScratch rs);
 void launch_spmv_partial_aty(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
-                             double* buf);
+                             double* buf, const double* dy2_partials, int dy2_nb);
+void launch_step_rule(cudaStream_t s, PdhgState* st, ReduceScratch r1, int nb1, ReduceScratch r2, int nb2,
+                      ReduceScratch r3, int nb3, const double* dy2_override);
+int primal_step_grid(int n);
+int interaction_grid(int n);
 void launch_interaction(cudaStream_t s, int n, PdhgState* st, const double* buf, const double* x0,
                         const double* x1, double* aty0, double* aty1, ReduceScratch rs);
 void launch_average(cudaStream_t s, int len, const double* v, double* sum, double* avg, int pending, double w,
