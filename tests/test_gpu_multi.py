@@ -1,0 +1,56 @@
+"""Row-partitioned solve over 2 GPUs (one process per GPU, NCCL all-reduce of A'y per iteration)
+against the single-GPU solve of the same LP.  Skipped with fewer than 2 devices."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import json, os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+from highs_b200 import engine
+from highs_b200.lp import synthetic_lp
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+lp = synthetic_lp(30000, 24000, 6, 17, dense_col_nnz=9000)
+prob = engine.Problem(lp, rank=rank, world=world, device=lr)
+ids = [engine.nccl_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(ids, src=0)
+prob.comm_init(ids[0])
+res = prob.solve(tol_primal=1e-5, tol_dual=1e-5, tol_gap=1e-5, iter_limit=100000)
+if rank == 0:
+    np.savez(sys.argv[1], col_value=res["col_value"], row_dual=res["row_dual"], row_value=res["row_value"],
+             col_dual=res["col_dual"], iters=res["iters"], term=res["term_code"])
+dist.barrier()
+dist.destroy_process_group()
+''' % ROOT
+
+
+def test_two_gpu_row_partition(engine_lib, tmp_path):
+    from highs_b200 import engine
+    from highs_b200.lp import synthetic_lp
+    if engine.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    w = tmp_path / "worker.py"
+    w.write_text(WORKER)
+    out = tmp_path / "res.npz"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29611", str(w), str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    multi = dict(np.load(out))
+    lp = synthetic_lp(30000, 24000, 6, 17, dense_col_nnz=9000)
+    single = engine.solve(lp, tol_primal=1e-5, tol_dual=1e-5, tol_gap=1e-5, iter_limit=100000)
+    assert int(multi["term"]) == single["term_code"] == 0
+    o1, o2 = lp.objectiveValue(multi["col_value"]), lp.objectiveValue(single["col_value"])
+    assert abs(o1 - o2) <= 1e-4 * (1 + abs(o2))     # both converged to kkt 1e-5: same optimum
+    A = lp.a_matrix_.to_scipy()
+    assert np.allclose(A @ multi["col_value"], multi["row_value"], atol=1e-8 * (1 + np.abs(multi["row_value"]).max()))
