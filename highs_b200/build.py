@@ -57,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if r.returncode != 0:
             raise RuntimeError(f"compile failed: {' '.join(cmd)}")
     if force or _newer(LIB, objs):
-        cmd = [_nvcc()] + ARCH + ["-shared", "-o", LIB] + objs + ["-lnccl", "-lcudart"]
+        cmd = [_nvcc()] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

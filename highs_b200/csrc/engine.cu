@@ -7,7 +7,8 @@
 // touches an n- or m-vector runs in pdhg_kernels.cu.  Between two checks the host
 // does not synchronise: it points state.stop_iter at the next check iteration and
 // replays a CUDA graph of PDHG passes; the adaptive step rule runs on the device.
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is bound at run time (see NcclApi below)
 
 #include <algorithm>
 #include <chrono>
@@ -43,9 +44,44 @@ struct Error : std::runtime_error {
   do {                                                                                                \
     ncclResult_t r_ = (call);                                                                         \
     if (r_ != ncclSuccess)                                                                            \
-      throw Error(B200PDLP_ERR_NCCL, std::string(#call) + ": " + ncclGetErrorString(r_) + " at " +    \
+      throw Error(B200PDLP_ERR_NCCL, std::string(#call) + ": " + nccl().GetErrorString(r_) + " at " + \
                                          __FILE__ + ":" + std::to_string(__LINE__));                  \
   } while (0)
+
+// NCCL is bound lazily with dlopen/dlsym: a single-GPU solve needs no NCCL at all, and in a
+// process that already carries a libnccl.so.2 (PyTorch bundles its own, newer than the system one)
+// we must use THAT copy instead of dragging a second one in at link time.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+  static NcclApi& get() {
+    static NcclApi api = load();
+    return api;
+  }
+  static NcclApi load() {
+    NcclApi a;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);          // already in the process?
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return a;
+    a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))dlsym(h, "ncclCommInitRank");
+    a.AllReduce = (decltype(a.AllReduce))dlsym(h, "ncclAllReduce");
+    a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
+    a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
+    a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.CommDestroy && a.GetErrorString;
+    return a;
+  }
+};
+static NcclApi& nccl() {
+  NcclApi& a = NcclApi::get();
+  if (!a.ok) throw Error(B200PDLP_ERR_NCCL, "libnccl.so.2 not found: multi-GPU solves need NCCL");
+  return a;
+}
 
 template <class T>
 struct DevBuf {
@@ -147,7 +183,7 @@ struct b200pdlp_problem {
   ~b200pdlp_problem() {
     if (graph_main) cudaGraphExecDestroy(graph_main);
     if (graph_small) cudaGraphExecDestroy(graph_small);
-    if (comm) ncclCommDestroy(comm);
+    if (comm) NcclApi::get().CommDestroy(comm);
     if (hstate) cudaFreeHost(hstate);
     if (houts) cudaFreeHost(houts);
     if (stream) cudaStreamDestroy(stream);
@@ -174,7 +210,7 @@ static void set_device(const b200pdlp_problem* p) { CUDA_OK(cudaSetDevice(p->dev
 static void allreduce_inplace(b200pdlp_problem* p, double* dptr, size_t count) {
   if (p->world <= 1) return;
   if (!p->comm) throw Error(B200PDLP_ERR_STATE, "world > 1 but b200pdlp_comm_init was not called");
-  NCCL_OK(ncclAllReduce(dptr, dptr, count, ncclDouble, ncclSum, p->comm, p->stream));
+  NCCL_OK(nccl().AllReduce(dptr, dptr, count, ncclDouble, ncclSum, p->comm, p->stream));
 }
 
 static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, int rank, int world, b200pdlp_problem* p) {
@@ -1009,7 +1045,7 @@ int b200pdlp_nccl_unique_id(uint8_t id[128]) {
   return guarded([&] {
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
     ncclUniqueId u;
-    NCCL_OK(ncclGetUniqueId(&u));
+    NCCL_OK(nccl().GetUniqueId(&u));
     memcpy(id, &u, 128);
   });
 }
@@ -1020,7 +1056,7 @@ int b200pdlp_comm_init(b200pdlp_problem* p, const uint8_t id[128]) {
     set_device(p);
     ncclUniqueId u;
     memcpy(&u, id, 128);
-    NCCL_OK(ncclCommInitRank(&p->comm, p->world, u, p->rank));
+    NCCL_OK(nccl().CommInitRank(&p->comm, p->world, u, p->rank));
   });
 }
 

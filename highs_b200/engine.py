@@ -70,6 +70,24 @@ ABI_SYMBOLS = [
 _lib = None
 
 
+def _preload_nccl():
+    """The engine binds NCCL at run time by SONAME (dlopen "libnccl.so.2").  If PyTorch's bundled,
+    newer NCCL is installed, load THAT copy first so that the engine and a later `import torch` share
+    one NCCL (the system libnccl lacks symbols torch needs)."""
+    import importlib.util
+    import sys
+    if "torch" in sys.modules:
+        return
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            cand = os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+    except Exception:
+        pass
+
+
 def lib():
     """Load the CUDA extension; raise loudly if it has not been built."""
     global _lib
@@ -77,6 +95,7 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise EngineError(f"{LIB_PATH} is missing: run `python -m highs_b200.build` (nvcc, sm_100a). "
                               "There is no CPU fallback.")
+        _preload_nccl()
         L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
         L.b200pdlp_last_error.restype = C.c_char_p
         L.b200pdlp_default_params.argtypes = [C.POINTER(CParams)]
