@@ -15,6 +15,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpdlp_oracle.so")
 REF_DRIVER = os.path.join(HERE, "_ref", "ref_driver")
+DROPIN_DRIVER = os.path.join(HERE, "_ref", "ref_driver_b200")   # HiGHS + highs_shim.cpp + libb200pdlp.so
 TRACE_COLS = 16
 
 TERM_NAMES = {0: "OPTIMAL", 1: "INFEASIBLE", 2: "UNBOUNDED", 3: "INFEASIBLE_OR_UNBOUNDED",
@@ -147,13 +148,20 @@ def ref_available() -> bool:
     return os.path.exists(REF_DRIVER)
 
 
-def run_reference(lp=None, mps=None, options=None, want_solution=False, warm=None, lp_path=None, timeout=None) -> dict:
-    """Run the UNMODIFIED reference (oracle/_ref) through Highs::run(); returns its JSON line."""
+def dropin_available() -> bool:
+    return os.path.exists(DROPIN_DRIVER)
+
+
+def run_reference(lp=None, mps=None, options=None, want_solution=False, warm=None, lp_path=None, timeout=None,
+                  driver=None) -> dict:
+    """Run the UNMODIFIED reference (oracle/_ref) through Highs::run(); returns its JSON line.
+    driver=DROPIN_DRIVER runs the same Highs::run() with the B200 shim linked in place of
+    CupdlpWrapper.cpp (the drop-in integration)."""
     from highs_b200.lp import write_b2lp
     opts = {"solver": "pdlp", "presolve": "off"}
     opts.update(options or {})
     with tempfile.TemporaryDirectory() as td:
-        cmd = [REF_DRIVER]
+        cmd = [driver or REF_DRIVER]
         if mps is not None:
             cmd += ["--mps", mps]
         else:

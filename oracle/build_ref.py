@@ -107,7 +107,27 @@ def main():
     nj.append(f"build {lib}: link {' '.join(objs)}")
     nj.append(f"build {drv}: exe {os.path.join(HERE, 'ref_driver.cpp')} | {lib}\n"
               f"  cxxincs = {incs} -w\n  libdir = {OUT}")
-    nj.append(f"default {lib} {drv}")
+    # --- drop-in demonstration: the same objects MINUS the reference wrapper
+    # (CupdlpWrapper.cpp), PLUS highs_b200/csrc/highs_shim.cpp, linked against libb200pdlp.so.
+    shim_src = os.path.join(os.path.dirname(HERE), "highs_b200", "csrc", "highs_shim.cpp")
+    eng_dir = os.path.join(os.path.dirname(HERE), "highs_b200")
+    lib2 = os.path.join(OUT, "libhighs_b200.so")
+    drv2 = os.path.join(OUT, "ref_driver_b200")
+    shim_o = os.path.join(OUT, "obj", "highs_shim.o")
+    # (the vendored cuPDLP-C objects stay in the library only because HiPDLP -- solver=hipdlp -- uses
+    #  their logging utilities, e.g. debugPdlpRestartLog; nothing on the solver=pdlp path calls them)
+    keep = [o for o, s_ in zip(objs, srcs) if not s_.endswith("pdlp/CupdlpWrapper.cpp")]
+    nj.append("rule cxxshim\n  command = g++ -std=c++11 $cxxflags_shim -c $in -o $out")
+    nj.append(f"build {shim_o}: cxxshim {shim_src}\n  cxxflags_shim = {common} -I{os.path.join(os.path.dirname(HERE), 'include')}")
+    nj.append("rule linkshim\n  command = g++ -shared -o $out $in -L$engdir -lb200pdlp '-Wl,-rpath,$engdir' -lpthread -lm -ldl")
+    nj.append(f"build {lib2}: linkshim {' '.join(keep)} {shim_o}\n  engdir = {eng_dir}")
+    nj.append("rule exeshim\n  command = g++ -std=c++11 -O2 $cxxincs $in -o $out -L$libdir -lhighs_b200 -L$engdir -lb200pdlp '-Wl,-rpath,$$ORIGIN' '-Wl,-rpath,$engdir' -lpthread")
+    nj.append(f"build {drv2}: exeshim {os.path.join(HERE, 'ref_driver.cpp')} | {lib2}\n"
+              f"  cxxincs = {incs} -w\n  libdir = {OUT}\n  engdir = {eng_dir}")
+    if "--shim" in sys.argv and os.path.exists(os.path.join(eng_dir, "libb200pdlp.so")):
+        nj.append(f"default {lib} {drv} {lib2} {drv2}")
+    else:
+        nj.append(f"default {lib} {drv}")
     njp = os.path.join(OUT, "build.ninja")
     open(njp, "w").write("\n".join(nj) + "\n")
     if force:
