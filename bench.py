@@ -285,6 +285,8 @@ def main():
                    "parallelism": f"row-partition x{world}" if world > 1 else "single GPU"},
         "gpu_launches": res["kernel_launches"], "passes": res["passes"], "restarts": res["restarts"],
         "wall_seconds": wall, "pass_device_ms": res["iter_device_ms"],
+        "phase_us": (None if world == 1 else {"primal_shard+allgather": k_us[0], "Ax+dual": k_us[1], "partial_ATy": k_us[2],
+                                              "reduce_scatter+step_rule": k_us[3]}),
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
     }
     print(json.dumps(line))

@@ -55,6 +55,8 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool ok = false;
@@ -71,9 +73,11 @@ struct NcclApi {
     a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(h, "ncclGetUniqueId");
     a.CommInitRank = (decltype(a.CommInitRank))dlsym(h, "ncclCommInitRank");
     a.AllReduce = (decltype(a.AllReduce))dlsym(h, "ncclAllReduce");
+    a.AllGather = (decltype(a.AllGather))dlsym(h, "ncclAllGather");
+    a.ReduceScatter = (decltype(a.ReduceScatter))dlsym(h, "ncclReduceScatter");
     a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
     a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
-    a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.CommDestroy && a.GetErrorString;
+    a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.AllGather && a.ReduceScatter && a.CommDestroy && a.GetErrorString;
     return a;
   }
 };
@@ -161,6 +165,10 @@ struct b200pdlp_problem {
   std::vector<int> rperm, rinv;    // device row order: rperm[new] = old local row
   std::vector<int> cperm, cinv;    // device column order: cperm[new] = old column (same on every rank)
   int neq_local = 0;               // local equality rows (they stay first under rperm)
+  // multi-GPU column sharding (world > 1): rank g owns device columns [c0, c0 + nl_real); n-vectors are
+  // allocated with nl = shard_len entries (zero padded); full vectors use G segments of seg_len
+  int nl = 0, nl_real = 0, c0 = 0, shard_len = 0, seg_len = 0;
+  DevBuf<double> xfull, part, red, send;
   cudaStream_t stream = nullptr;
   // n-vectors (replicated across ranks)
   DevBuf<double> x[2], aty[2], xsum, xavg, atyavg, xlr, cost, lower, upper, colscale;
@@ -213,6 +221,24 @@ static void allreduce_inplace(b200pdlp_problem* p, double* dptr, size_t count) {
   NCCL_OK(nccl().AllReduce(dptr, dptr, count, ncclDouble, ncclSum, p->comm, p->stream));
 }
 
+static void need_comm(b200pdlp_problem* p) {
+  if (!p->comm) throw Error(B200PDLP_ERR_STATE, "world > 1 but b200pdlp_comm_init was not called");
+}
+// shards (+ scalar tails) of every rank -> xfull
+static void gather_shards(b200pdlp_problem* p) {
+  need_comm(p);
+  NCCL_OK(nccl().AllGather(p->send.p, p->xfull.p, (size_t)p->seg_len, ncclDouble, p->comm, p->stream));
+}
+// sum over ranks of `part`, my segment -> red
+static void reduce_scatter_part(b200pdlp_problem* p) {
+  need_comm(p);
+  NCCL_OK(nccl().ReduceScatter(p->part.p, p->red.p, (size_t)p->seg_len, ncclDouble, ncclSum, p->comm, p->stream));
+}
+// position of device column j in a segmented full vector
+static inline size_t seg_pos(const b200pdlp_problem* p, int j) {
+  return p->world == 1 ? (size_t)j : (size_t)(j / p->shard_len) * p->seg_len + (size_t)(j % p->shard_len);
+}
+
 static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, int rank, int world, b200pdlp_problem* p) {
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -246,7 +272,19 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
     p->cperm = make_perm(f.cbeg, n, sort);   // GLOBAL column lengths: identical on every rank
     p->rinv = invert_perm(p->rperm);
     p->cinv = invert_perm(p->cperm);
-    build_sell(p->csr_local, p->rperm, p->cinv, long_threshold, p->A.host);
+    if (world == 1) {
+      p->nl = p->nl_real = n; p->c0 = 0; p->shard_len = n; p->seg_len = n;
+      build_sell(p->csr_local, p->rperm, p->cinv, long_threshold, p->A.host);
+    } else {
+      p->shard_len = ((n + world - 1) / world + 1) & ~1;          // even: 16-byte aligned segments
+      p->seg_len = p->shard_len + 2;
+      p->nl = p->shard_len;
+      p->c0 = rank * p->shard_len;
+      p->nl_real = std::max(0, std::min(p->shard_len, n - p->c0));
+      std::vector<int> colpos(n);                                   // old column -> position in the segmented x
+      for (int j = 0; j < n; j++) colpos[j] = (int)seg_pos(p, p->cinv[j]);
+      build_sell(p->csr_local, p->rperm, colpos, long_threshold, p->A.host);
+    }
     build_sell(at, p->cperm, p->rinv, long_threshold, p->AT.host);
   }
   CUDA_OK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
@@ -254,20 +292,26 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   p->AT.upload();
   if (const char* e = getenv("B200PDLP_EXP")) p->exp_flags = atoi(e);
   if (const char* e = getenv("B200PDLP_PREFETCH")) { p->A.dev.prefetch_dist = atoi(e); p->AT.dev.prefetch_dist = atoi(e); }
-  for (int k = 0; k < 2; k++) { p->x[k].alloc(n); p->aty[k].alloc(n); p->y[k].alloc(ml); p->ax[k].alloc(ml); }
-  p->xsum.alloc(n); p->xavg.alloc(n); p->atyavg.alloc(n); p->xlr.alloc(n);
+  const int nl = p->nl;
+  for (int k = 0; k < 2; k++) { p->x[k].alloc(nl); p->aty[k].alloc(nl); p->y[k].alloc(ml); p->ax[k].alloc(ml); }
+  p->xsum.alloc(nl); p->xavg.alloc(nl); p->atyavg.alloc(nl); p->xlr.alloc(nl);
   p->ysum.alloc(ml); p->yavg.alloc(ml); p->axavg.alloc(ml); p->ylr.alloc(ml);
+  if (world > 1) {
+    p->xfull.alloc((size_t)world * p->seg_len); p->part.alloc((size_t)world * p->seg_len);
+    p->red.alloc(p->seg_len); p->send.alloc(p->seg_len);
+  }
   {
-    std::vector<double> t(std::max(n, ml));
-    auto up_col = [&](DevBuf<double>& d, const std::vector<double>& v) {
-      for (int j = 0; j < n; j++) t[j] = v[p->cperm[j]];
-      d.alloc(n, false); d.upload(t.data(), n);
+    std::vector<double> t(std::max(std::max(n, nl), ml));
+    auto up_col = [&](DevBuf<double>& d, const std::vector<double>& v, double pad) {
+      // my shard of the column vector in device order (padding: cost 0, bounds [0,0], scale 1)
+      for (int i = 0; i < nl; i++) t[i] = i < p->nl_real ? v[p->cperm[p->c0 + i]] : pad;
+      d.alloc(nl, false); d.upload(t.data(), nl);
     };
     auto up_row = [&](DevBuf<double>& d, const std::vector<double>& v) {
       for (int i = 0; i < ml; i++) t[i] = v[p->r0 + p->rperm[i]];
       d.alloc(ml, false); d.upload(t.data(), ml);
     };
-    up_col(p->cost, f.cost); up_col(p->lower, f.lower); up_col(p->upper, f.upper); up_col(p->colscale, f.col_scale);
+    up_col(p->cost, f.cost, 0.0); up_col(p->lower, f.lower, 0.0); up_col(p->upper, f.upper, 0.0); up_col(p->colscale, f.col_scale, 1.0);
     up_row(p->rhs, f.rhs); up_row(p->rowscale, f.row_scale);
   }
   p->redbuf.alloc((size_t)std::max(n, p->m) + 16);
@@ -286,7 +330,9 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
 }
 
 // ------------------------------------------------------------------ PDHG passes
+static void enqueue_pass_mg(b200pdlp_problem* p);
 static void enqueue_pass(b200pdlp_problem* p) {
+  if (p->world > 1) { enqueue_pass_mg(p); return; }
   cudaStream_t s = p->stream;
   PdhgState* st = p->state.p;
   const ReduceScratch r1 = p->rs(kSlotK1, p->n), r2 = p->rs(kSlotK2, p->ml), r3 = p->rs(kSlotK3, p->n);
@@ -294,15 +340,25 @@ static void enqueue_pass(b200pdlp_problem* p) {
                      p->upper.p, p->xsum.p, r1);
   launch_spmv_dual(s, p->A.dev, st, p->x[0].p, p->x[1].p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p,
                    p->rhs.p, p->ysum.p, p->neq_local, 0, r2);
-  if (p->world == 1) {
-    launch_spmv_primal(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, r3);
-    launch_step_rule(s, st, r1, primal_step_grid(p->n), r2, p->A.grid(), r3, p->AT.grid(), nullptr);
-  } else {
-    launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->redbuf.p, r2.partials, p->A.grid());
-    allreduce_inplace(p, p->redbuf.p, (size_t)p->n + 1);
-    launch_interaction(s, p->n, st, p->redbuf.p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, r3);
-    launch_step_rule(s, st, r1, primal_step_grid(p->n), r2, p->A.grid(), r3, interaction_grid(p->n), p->redbuf.p + p->n);
-  }
+  launch_spmv_primal(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, r3);
+  launch_step_rule(s, st, r1, primal_step_grid(p->n), r2, p->A.grid(), r3, p->AT.grid(), nullptr);
+}
+
+// world > 1: sharded primal step, all-gather, local rows, partial A^T y, reduce-scatter, step rule
+static void enqueue_pass_mg(b200pdlp_problem* p) {
+  cudaStream_t s = p->stream;
+  PdhgState* st = p->state.p;
+  const ReduceScratch r1 = p->rs(kSlotK1, p->nl), r2 = p->rs(kSlotK2, p->ml);
+  launch_primal_shard(s, p->nl, st, p->x[0].p, p->x[1].p, p->aty[0].p, p->red.p, p->cost.p, p->lower.p, p->upper.p,
+                      p->xsum.p, p->send.p, r1);
+  launch_stash_scalars(s, 1, st, r1.partials, primal_shard_grid(p->nl), p->send.p + p->shard_len, 1, 0);
+  gather_shards(p);
+  launch_spmv_dual_mg(s, p->A.dev, st, p->xfull.p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->rhs.p,
+                      p->ysum.p, p->neq_local, r2);
+  launch_stash_scalars(s, 2, st, r2.partials, p->A.grid(), p->part.p + p->shard_len, p->world, p->seg_len);
+  launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->part.p, p->shard_len);
+  reduce_scatter_part(p);
+  launch_step_rule_mg(s, st, p->xfull.p, p->world, p->seg_len, p->shard_len, p->red.p);
 }
 
 static cudaGraphExec_t capture_passes(b200pdlp_problem* p, int passes) {
@@ -338,17 +394,28 @@ static void pull_outs(b200pdlp_problem* p, int count) {
   CUDA_OK(cudaStreamSynchronize(p->stream));
 }
 
-// full A'y (all-reduced over ranks) with the plain kernel
+// aty (my column shard) = sum over ranks of A_g^T y   [world == 1: the whole vector]
 static void full_aty(b200pdlp_problem* p, const double* y, double* aty) {
   if (p->world == 1) {
     launch_spmv_plain(p->stream, p->AT.dev, y, aty);
     p->launches++;
   } else {
-    launch_spmv_plain(p->stream, p->AT.dev, y, p->redbuf.p);
+    launch_spmv_partial_aty(p->stream, p->AT.dev, nullptr, y, y, p->part.p, p->shard_len);
     p->launches++;
-    allreduce_inplace(p, p->redbuf.p, p->n);
-    CUDA_OK(cudaMemcpyAsync(aty, p->redbuf.p, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    reduce_scatter_part(p);
+    CUDA_OK(cudaMemcpyAsync(aty, p->red.p, (size_t)p->nl * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
   }
+}
+// ax (my rows) = A_g x, x given as my column shard   [world == 1: the whole vector]
+static void full_ax(b200pdlp_problem* p, const double* x, double* ax) {
+  if (p->world == 1) {
+    launch_spmv_plain(p->stream, p->A.dev, x, ax);
+  } else {
+    CUDA_OK(cudaMemcpyAsync(p->send.p, x, (size_t)p->nl * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    gather_shards(p);
+    launch_spmv_plain(p->stream, p->A.dev, p->xfull.p, ax);
+  }
+  p->launches++;
 }
 
 struct CheckResult { Residuals it[2]; bool timed_out = false; };
@@ -359,26 +426,32 @@ static CheckResult run_check(b200pdlp_problem* p, bool timed_out_local) {
   cudaStream_t s = p->stream;
   PdhgState* h = p->hstate;
   const StdForm& f = p->form;
-  const int n = p->n, ml = p->ml, cur = h->cur;
+  const int n = p->nl, ml = p->ml, cur = h->cur;   // n = column entries held by this rank
+  const int acur = p->world == 1 ? cur : 0;        // multi-GPU keeps one current A^T y shard
   const double scale = h->sum_step > 0.0 ? 1.0 / h->sum_step : 1.0;
+  if (p->world > 1 && h->accepted_last) {
+    // the last accepted pass left its A^T y' in the reduce-scatter buffer: make it current
+    CUDA_OK(cudaMemcpyAsync(p->aty[0].p, p->red.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    h->accepted_last = 0;
+    push_state(p);
+  }
   launch_average(s, n, p->x[cur].p, p->xsum.p, p->xavg.p, h->pending, h->w_pending, scale);
   launch_average(s, ml, p->y[cur].p, p->ysum.p, p->yavg.p, h->pending, h->w_pending, scale);
   p->launches += 2;
   if (h->pending) { h->pending = 0; push_state(p); }
-  launch_spmv_plain(s, p->A.dev, p->xavg.p, p->axavg.p);
-  p->launches++;
+  full_ax(p, p->xavg.p, p->axavg.p);
   full_aty(p, p->yavg.p, p->atyavg.p);
-  ColIter c0{p->x[cur].p, p->aty[cur].p}, c1{p->xavg.p, p->atyavg.p};
+  ColIter c0{p->x[cur].p, p->aty[acur].p}, c1{p->xavg.p, p->atyavg.p};
   RowIter r0{p->y[cur].p, p->ax[cur].p}, r1{p->yavg.p, p->axavg.p};
   double* o = p->outs.p;
   launch_col_check_a(s, n, 2, c0, c1, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, p->rs(kSlotChk, n), o);
   launch_row_check_a(s, ml, 2, r0, r1, p->rhs.p, p->rowscale.p, p->neq_local, 0, p->rs(kSlotChk, ml), o + 14);
   p->launches += 2;
   if (p->world > 1) {
-    // row-side partial sums + the time-limit flag travel in one small all-reduce
+    // column-shard and row-block partial sums + the time-limit flag travel in one small all-reduce
     double flag = timed_out_local ? 1.0 : 0.0;
     CUDA_OK(cudaMemcpyAsync(o + 20, &flag, sizeof(double), cudaMemcpyHostToDevice, s));
-    allreduce_inplace(p, o + 14, 7);
+    allreduce_inplace(p, o, 21);
   }
   pull_outs(p, 21);
   CheckResult cr;
@@ -408,7 +481,7 @@ static CheckResult run_check(b200pdlp_problem* p, bool timed_out_local) {
                      p->rs(kSlotChk, n), o + 24);
   launch_row_check_b(s, ml, 2, r0, r1, inv_p, p->rowscale.p, p->neq_local, 0, p->rs(kSlotChk, ml), o + 30);
   p->launches += 2;
-  if (p->world > 1) allreduce_inplace(p, o + 30, 2);
+  if (p->world > 1) allreduce_inplace(p, o + 24, 8);
   CUDA_OK(cudaMemcpyAsync(p->houts + 24, o + 24, 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CUDA_OK(cudaStreamSynchronize(s));
   for (int t = 0; t < 2; t++) {
@@ -458,7 +531,8 @@ static int decide_restart(const PdhgState* h, const CheckResult& c, RestartMemo&
 static void do_restart(b200pdlp_problem* p, int choice, const CheckResult& c, RestartMemo& mm) {
   cudaStream_t s = p->stream;
   PdhgState* h = p->hstate;
-  const int n = p->n, ml = p->ml, cur = h->cur;
+  const int n = p->nl, ml = p->ml, cur = h->cur;
+  const int acur = p->world == 1 ? cur : 0;
   h->sum_step = 0.0;
   CUDA_OK(cudaMemsetAsync(p->xsum.p, 0, (size_t)n * sizeof(double), s));
   CUDA_OK(cudaMemsetAsync(p->ysum.p, 0, (size_t)std::max(ml, 1) * sizeof(double), s));
@@ -468,13 +542,13 @@ static void do_restart(b200pdlp_problem* p, int choice, const CheckResult& c, Re
     CUDA_OK(cudaMemcpyAsync(p->x[cur].p, p->xavg.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
     CUDA_OK(cudaMemcpyAsync(p->y[cur].p, p->yavg.p, (size_t)ml * sizeof(double), cudaMemcpyDeviceToDevice, s));
     CUDA_OK(cudaMemcpyAsync(p->ax[cur].p, p->axavg.p, (size_t)ml * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    CUDA_OK(cudaMemcpyAsync(p->aty[cur].p, p->atyavg.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(p->aty[acur].p, p->atyavg.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
   }
   double* o = p->outs.p + 40;
   launch_diff_norm2(s, n, p->x[cur].p, p->xlr.p, p->rs(kSlotChk, n), o);
   launch_diff_norm2(s, ml, p->y[cur].p, p->ylr.p, p->rs(kSlotChk, ml), o + 1);
   p->launches += 2;
-  if (p->world > 1) allreduce_inplace(p, o + 1, 1);
+  if (p->world > 1) allreduce_inplace(p, o, 2);
   CUDA_OK(cudaMemcpyAsync(p->houts + 40, o, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CUDA_OK(cudaMemcpyAsync(p->xlr.p, p->x[cur].p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
   CUDA_OK(cudaMemcpyAsync(p->ylr.p, p->y[cur].p, (size_t)ml * sizeof(double), cudaMemcpyDeviceToDevice, s));
@@ -516,6 +590,7 @@ static double vec_norm2_sq(b200pdlp_problem* p, const double* v, int len, bool r
 
 // PDHG_Power_Method (cupdlp_step.c:71-145): 20 iterations on A A'
 static double power_method(b200pdlp_problem* p) {
+  if (p->world > 1) throw Error(B200PDLP_ERR_ARG, "fixed-step mode (adaptive_step = 0) is single-GPU only");
   cudaStream_t s = p->stream;
   double* q = p->ylr.p;  // scratch (re-zeroed by the caller)
   launch_fill(s, p->ml, q, 1.0);
@@ -582,17 +657,24 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
     v = v > f.lower[j] ? v : f.lower[j];
     x0[j] = v;
   }
+  const int nl = p->nl;   // column entries held by this rank (== n on one GPU)
   for (int k = 0; k < 2; k++) {
-    CUDA_OK(cudaMemsetAsync(p->x[k].p, 0, (size_t)n * sizeof(double), s));
-    CUDA_OK(cudaMemsetAsync(p->aty[k].p, 0, (size_t)n * sizeof(double), s));
+    CUDA_OK(cudaMemsetAsync(p->x[k].p, 0, (size_t)nl * sizeof(double), s));
+    CUDA_OK(cudaMemsetAsync(p->aty[k].p, 0, (size_t)nl * sizeof(double), s));
     CUDA_OK(cudaMemsetAsync(p->y[k].p, 0, (size_t)std::max(ml, 1) * sizeof(double), s));
     CUDA_OK(cudaMemsetAsync(p->ax[k].p, 0, (size_t)std::max(ml, 1) * sizeof(double), s));
   }
+  if (p->world > 1) {
+    CUDA_OK(cudaMemsetAsync(p->xfull.p, 0, p->xfull.n * sizeof(double), s));
+    CUDA_OK(cudaMemsetAsync(p->part.p, 0, p->part.n * sizeof(double), s));
+    CUDA_OK(cudaMemsetAsync(p->red.p, 0, p->red.n * sizeof(double), s));
+    CUDA_OK(cudaMemsetAsync(p->send.p, 0, p->send.n * sizeof(double), s));
+  }
   {
-    std::vector<double> xp(n), yp(std::max(ml, 1));
-    for (int j = 0; j < n; j++) xp[j] = x0[p->cperm[j]];
+    std::vector<double> xp(std::max(nl, 1), 0.0), yp(std::max(ml, 1));
+    for (int i = 0; i < p->nl_real; i++) xp[i] = x0[p->cperm[p->c0 + i]];
     for (int i = 0; i < ml; i++) yp[i] = y0[p->r0 + p->rperm[i]];
-    CUDA_OK(cudaMemcpyAsync(p->x[0].p, xp.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(p->x[0].p, xp.data(), (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, s));
     if (ml) CUDA_OK(cudaMemcpyAsync(p->y[0].p, yp.data(), (size_t)ml * sizeof(double), cudaMemcpyHostToDevice, s));
     CUDA_OK(cudaStreamSynchronize(s));
   }
@@ -614,26 +696,26 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
       h->sigma *= std::sqrt(h->beta);
     }
   }
-  launch_spmv_plain(s, p->A.dev, p->x[0].p, p->ax[0].p);
-  p->launches++;
+  full_ax(p, p->x[0].p, p->ax[0].p);
   full_aty(p, p->y[0].p, p->aty[0].p);
   // sums start at proj(0) like PDHG_Init_Variables :577-583; the average is recomputed at every check
   {
-    std::vector<double> z(n, 0.0);
+    std::vector<double> z(std::max(nl, 1), 0.0);
     bool nz = false;
-    for (int j = 0; j < n; j++) {
+    for (int i = 0; i < p->nl_real; i++) {
+      const int j = p->cperm[p->c0 + i];
       double v = 0.0;
       v = v < f.upper[j] ? v : f.upper[j];
       v = v > f.lower[j] ? v : f.lower[j];
-      z[p->cinv[j]] = v;
+      z[i] = v;
       nz |= (v != 0.0);
     }
-    if (nz) CUDA_OK(cudaMemcpyAsync(p->xsum.p, z.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
-    else CUDA_OK(cudaMemsetAsync(p->xsum.p, 0, (size_t)n * sizeof(double), s));
+    if (nz) CUDA_OK(cudaMemcpyAsync(p->xsum.p, z.data(), (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, s));
+    else CUDA_OK(cudaMemsetAsync(p->xsum.p, 0, (size_t)nl * sizeof(double), s));
     CUDA_OK(cudaStreamSynchronize(s));
   }
   CUDA_OK(cudaMemsetAsync(p->ysum.p, 0, (size_t)std::max(ml, 1) * sizeof(double), s));
-  CUDA_OK(cudaMemsetAsync(p->xlr.p, 0, (size_t)n * sizeof(double), s));
+  CUDA_OK(cudaMemsetAsync(p->xlr.p, 0, (size_t)nl * sizeof(double), s));
   CUDA_OK(cudaMemsetAsync(p->ylr.p, 0, (size_t)std::max(ml, 1) * sizeof(double), s));
   arm_step(h);
   fill_pow_tables(h);
@@ -648,7 +730,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
     p->graph_main_passes = want_main;
   }
   if (!p->graph_small) { p->graph_small_passes = 4; p->graph_small = capture_passes(p, 4); }
-  p->kernels_per_pass = p->world == 1 ? 4 : 6;
+  p->kernels_per_pass = p->world == 1 ? 4 : 6;   // ours; NCCL kernels not counted
 
   const double tol_p = prm.tol_primal * (1.0 + f.norm_rhs), tol_d = prm.tol_dual * (1.0 + f.norm_cost);
   RestartMemo memo;
@@ -743,15 +825,26 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   const double* dx = use_avg ? p->xavg.p : p->x[cur].p;
   const double* dy = use_avg ? p->yavg.p : p->y[cur].p;
   const double* dax = use_avg ? p->axavg.p : p->ax[cur].p;
-  const double* daty = use_avg ? p->atyavg.p : p->aty[cur].p;
+  if (p->world > 1 && h->accepted_last && !use_avg) {   // (only when the loop never ran a check, e.g. iter_limit <= 0)
+    CUDA_OK(cudaMemcpyAsync(p->aty[0].p, p->red.p, (size_t)nl * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  }
+  const double* daty = use_avg ? p->atyavg.p : p->aty[p->world == 1 ? cur : 0].p;
   std::vector<double> hx(n), hy(m, 0.0), hax(m, 0.0), haty(n);
   {
     // device order -> standard-form order
-    std::vector<double> t(std::max(n, std::max(ml, 1)));
+    std::vector<double> t(std::max<size_t>(std::max(n, std::max(ml, 1)), p->xfull.n));
     auto down_col = [&](const double* d, std::vector<double>& h) {
-      CUDA_OK(cudaMemcpyAsync(t.data(), d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
-      CUDA_OK(cudaStreamSynchronize(s));
-      for (int j = 0; j < n; j++) h[p->cperm[j]] = t[j];
+      if (p->world == 1) {
+        CUDA_OK(cudaMemcpyAsync(t.data(), d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CUDA_OK(cudaStreamSynchronize(s));
+        for (int j = 0; j < n; j++) h[p->cperm[j]] = t[j];
+      } else {   // all-gather the column shards, then unpack the segmented vector
+        CUDA_OK(cudaMemcpyAsync(p->send.p, d, (size_t)nl * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        gather_shards(p);
+        CUDA_OK(cudaMemcpyAsync(t.data(), p->xfull.p, p->xfull.n * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CUDA_OK(cudaStreamSynchronize(s));
+        for (int j = 0; j < n; j++) h[p->cperm[j]] = t[seg_pos(p, j)];
+      }
     };
     auto down_row = [&](const double* d, std::vector<double>& h) {
       if (ml) CUDA_OK(cudaMemcpyAsync(t.data(), d, (size_t)ml * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -911,10 +1004,12 @@ int b200pdlp_spmv_ax(b200pdlp_problem* p, const double* x, double* ax) {
   return guarded([&] {
     if (!p || !x || !ax) throw Error(B200PDLP_ERR_ARG, "null argument");
     set_device(p);
-    std::vector<double> t(std::max(p->n, std::max(p->ml, 1)));
-    for (int j = 0; j < p->n; j++) t[j] = x[p->cperm[j]];
-    CUDA_OK(cudaMemcpyAsync(p->xavg.p, t.data(), (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-    launch_spmv_plain(p->stream, p->A.dev, p->xavg.p, p->axavg.p);
+    const size_t full = p->world == 1 ? (size_t)p->n : p->xfull.n;
+    std::vector<double> t(std::max<size_t>(full, std::max(p->ml, 1)), 0.0);
+    for (int j = 0; j < p->n; j++) t[seg_pos(p, j)] = x[p->cperm[j]];
+    double* dx = p->world == 1 ? p->xavg.p : p->xfull.p;   // whole x supplied by the caller: no gather needed
+    CUDA_OK(cudaMemcpyAsync(dx, t.data(), full * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    launch_spmv_plain(p->stream, p->A.dev, dx, p->axavg.p);
     p->launches++;
     CUDA_OK(cudaStreamSynchronize(p->stream));
     if (p->ml) CUDA_OK(cudaMemcpy(t.data(), p->axavg.p, (size_t)p->ml * sizeof(double), cudaMemcpyDeviceToHost));
@@ -927,14 +1022,17 @@ int b200pdlp_spmv_aty(b200pdlp_problem* p, const double* y, double* aty) {
   return guarded([&] {
     if (!p || !y || !aty) throw Error(B200PDLP_ERR_ARG, "null argument");
     set_device(p);
-    std::vector<double> t(std::max(p->n, std::max(p->ml, 1)));
+    const size_t full = p->world == 1 ? (size_t)p->n : p->part.n;
+    std::vector<double> t(std::max<size_t>(full, std::max(p->ml, 1)), 0.0);
     for (int i = 0; i < p->ml; i++) t[i] = y[p->rperm[i]];
     if (p->ml) CUDA_OK(cudaMemcpyAsync(p->yavg.p, t.data(), (size_t)p->ml * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-    launch_spmv_plain(p->stream, p->AT.dev, p->yavg.p, p->atyavg.p);   // local partial (no all-reduce)
+    // local partial A_g^T y (no reduction over ranks)
+    if (p->world == 1) launch_spmv_plain(p->stream, p->AT.dev, p->yavg.p, p->atyavg.p);
+    else launch_spmv_partial_aty(p->stream, p->AT.dev, nullptr, p->yavg.p, p->yavg.p, p->part.p, p->shard_len);
     p->launches++;
     CUDA_OK(cudaStreamSynchronize(p->stream));
-    CUDA_OK(cudaMemcpy(t.data(), p->atyavg.p, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToHost));
-    for (int j = 0; j < p->n; j++) aty[p->cperm[j]] = t[j];
+    CUDA_OK(cudaMemcpy(t.data(), p->world == 1 ? p->atyavg.p : p->part.p, full * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int j = 0; j < p->n; j++) aty[p->cperm[j]] = t[seg_pos(p, j)];
     CUDA_OK(cudaGetLastError());
   });
 }
@@ -948,8 +1046,9 @@ int b200pdlp_bench_spmv(b200pdlp_problem* p, int32_t which, int32_t reps, float*
     CUDA_OK(cudaEventCreate(&e1));
     CUDA_OK(cudaEventRecord(e0, p->stream));
     for (int r = 0; r < reps; r++) {
-      if (which == 0) launch_spmv_plain(p->stream, p->A.dev, p->xavg.p, p->axavg.p);
-      else launch_spmv_plain(p->stream, p->AT.dev, p->yavg.p, p->atyavg.p);
+      if (which == 0) launch_spmv_plain(p->stream, p->A.dev, p->world == 1 ? p->xavg.p : p->xfull.p, p->axavg.p);
+      else if (p->world == 1) launch_spmv_plain(p->stream, p->AT.dev, p->yavg.p, p->atyavg.p);
+      else launch_spmv_partial_aty(p->stream, p->AT.dev, nullptr, p->yavg.p, p->yavg.p, p->part.p, p->shard_len);
     }
     p->launches += reps;
     CUDA_OK(cudaEventRecord(e1, p->stream));
@@ -976,25 +1075,36 @@ int b200pdlp_bench_pass(b200pdlp_problem* p, int32_t reps, float ms[4]) {
     double acc[4] = {0, 0, 0, 0};
     for (int r = 0; r < reps; r++) {
       if (r % 64 == 63) { pull_state(p); fill_pow_tables(p->hstate); push_state(p); }
-      const ReduceScratch r1 = p->rs(kSlotK1, p->n), r2 = p->rs(kSlotK2, p->ml), r3 = p->rs(kSlotK3, p->n);
-      CUDA_OK(cudaEventRecord(ev[0], s));
-      launch_primal_step(s, p->n, st, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->cost.p, p->lower.p,
-                         p->upper.p, p->xsum.p, r1);
-      CUDA_OK(cudaEventRecord(ev[1], s));
-      launch_spmv_dual(s, p->A.dev, st, p->x[0].p, p->x[1].p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p,
-                       p->rhs.p, p->ysum.p, p->neq_local, 0, r2);
-      CUDA_OK(cudaEventRecord(ev[2], s));
       if (p->world == 1) {
+        const ReduceScratch r1 = p->rs(kSlotK1, p->n), r2 = p->rs(kSlotK2, p->ml), r3 = p->rs(kSlotK3, p->n);
+        CUDA_OK(cudaEventRecord(ev[0], s));
+        launch_primal_step(s, p->n, st, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->cost.p, p->lower.p,
+                           p->upper.p, p->xsum.p, r1);
+        CUDA_OK(cudaEventRecord(ev[1], s));
+        launch_spmv_dual(s, p->A.dev, st, p->x[0].p, p->x[1].p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p,
+                         p->rhs.p, p->ysum.p, p->neq_local, 0, r2);
+        CUDA_OK(cudaEventRecord(ev[2], s));
         launch_spmv_primal(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->x[0].p, p->x[1].p, p->aty[0].p,
                            p->aty[1].p, r3);
         CUDA_OK(cudaEventRecord(ev[3], s));
         launch_step_rule(s, st, r1, primal_step_grid(p->n), r2, p->A.grid(), r3, p->AT.grid(), nullptr);
       } else {
-        launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->redbuf.p, r2.partials, p->A.grid());
+        // ms[0] = primal shard + all-gather, ms[1] = A x + dual, ms[2] = partial A'y, ms[3] = reduce-scatter + step rule
+        const ReduceScratch r1 = p->rs(kSlotK1, p->nl), r2 = p->rs(kSlotK2, p->ml);
+        CUDA_OK(cudaEventRecord(ev[0], s));
+        launch_primal_shard(s, p->nl, st, p->x[0].p, p->x[1].p, p->aty[0].p, p->red.p, p->cost.p, p->lower.p,
+                            p->upper.p, p->xsum.p, p->send.p, r1);
+        launch_stash_scalars(s, 1, st, r1.partials, primal_shard_grid(p->nl), p->send.p + p->shard_len, 1, 0);
+        gather_shards(p);
+        CUDA_OK(cudaEventRecord(ev[1], s));
+        launch_spmv_dual_mg(s, p->A.dev, st, p->xfull.p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->rhs.p,
+                            p->ysum.p, p->neq_local, r2);
+        launch_stash_scalars(s, 2, st, r2.partials, p->A.grid(), p->part.p + p->shard_len, p->world, p->seg_len);
+        CUDA_OK(cudaEventRecord(ev[2], s));
+        launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->part.p, p->shard_len);
         CUDA_OK(cudaEventRecord(ev[3], s));
-        allreduce_inplace(p, p->redbuf.p, (size_t)p->n + 1);
-        launch_interaction(s, p->n, st, p->redbuf.p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, r3);
-        launch_step_rule(s, st, r1, primal_step_grid(p->n), r2, p->A.grid(), r3, interaction_grid(p->n), p->redbuf.p + p->n);
+        reduce_scatter_part(p);
+        launch_step_rule_mg(s, st, p->xfull.p, p->world, p->seg_len, p->shard_len, p->red.p);
       }
       CUDA_OK(cudaEventRecord(ev[4], s));
       CUDA_OK(cudaEventSynchronize(ev[4]));

@@ -49,7 +49,7 @@ struct PdhgState {
   int adaptive;                      // 1 adaptive line search, 0 fixed step
   int passes, rejects;
   int pow_base;                      // step_iter value that pow tables entry 0 belongs to
-  int pad_;
+  int accepted_last;                 // multi-GPU: the previous pass was accepted (its A^T y' becomes current)
   double pow_red[kPowTab];           // (k+1)^-0.3 for k = pow_base+1+i   (host-computed, glibc pow)
   double pow_grow[kPowTab];          // (k+1)^-0.6
 };

@@ -82,15 +82,16 @@ struct PlainEpilogue {
   __device__ bool begin() { return true; }
   __device__ const double* input() const { return in; }
   __device__ void prefetch(int) {}
-  __device__ double row(int r, double s) const { out[r] = s; return 0.0; }
+  __device__ void row(int r, double s, double*) const { out[r] = s; }
   __device__ void finalize(const double*) const {}
 };
 
 // K2: PDHG_dualGradientStep (CPU order, cupdlp_step.c:55-67):
 //   y' = y; y' += sigma b; y' += (-2 sigma) ax'; y' += sigma ax; y'[i>=nEqs] = max(y',0)
 // + |y - y'|^2 + deferred ySum += w y.
-struct DualEpilogue {
-  static constexpr int NACC = 1;
+template <int NACC_>
+struct DualEpilogueT {
+  static constexpr int NACC = NACC_;
   PdhgState* st;
   const double *x0, *x1;       // primal double buffer (input = the NEW x)
   double *y0, *y1, *ax0, *ax1;
@@ -118,7 +119,7 @@ struct DualEpilogue {
     p_y = y[r]; p_b = b[r]; p_ax = ax[r];
     p_ys = pend ? ysum[r] : 0.0;
   }
-  __device__ double row(int r, double s) const {
+  __device__ void row(int r, double s, double* t) const {
     axn[r] = s;
     const double yc = p_y;
     if (pend) ysum[r] = p_ys + w * yc;
@@ -128,10 +129,13 @@ struct DualEpilogue {
     if (r >= neq) v = v > 0.0 ? v : 0.0;
     yn[r] = v;
     const double d = yc - v;
-    return d * d;
+    t[0] = d * d;
+    if (NACC > 1) t[NACC - 1] = (p_ax - s) * d;   // row-side interaction (AΔx)·Δy, multi-GPU only
   }
   __device__ void finalize(const double* out) const { st->dy2 = out[0]; }
 };
+using DualEpilogue = DualEpilogueT<1>;
+using DualEpilogueMg = DualEpilogueT<2>;
 
 // device-side adaptive step rule, PDHG_Update_Iterate_Adaptive_Step_Size
 // (cupdlp_step.c:236-307) + the bookkeeping of PDHG_Update_Average (:422-442)
@@ -204,11 +208,11 @@ struct PrimalEpilogue {
   __device__ const double* input() const { return y0; }
   double p_x, p_xn, p_aty;
   __device__ void prefetch(int r) { p_x = x[r]; p_xn = xn[r]; p_aty = aty[r]; }
-  __device__ double row(int r, double s) const {
+  __device__ void row(int r, double s, double* t) const {
     atyn[r] = s;
     const double dx = p_x - p_xn;
     const double da = p_aty - s;
-    return dx * da;
+    t[0] = dx * da;
   }
   __device__ void finalize(const double* out) const { step_rule(st, out[0]); }
 };
@@ -318,8 +322,12 @@ __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_
       }
       for (; k < d.y; k++) s += vp[32 * k] * xin[cp[32 * k]];
       if (live) {
-        const double term = epi.row(row, s);
-        if constexpr (Epi::NACC > 0) add_term(acc[0], term, rs, 0, row);
+        double t[Epi::NACC > 0 ? Epi::NACC : 1];
+        epi.row(row, s, t);
+        if constexpr (Epi::NACC > 0) {
+#pragma unroll
+          for (int a = 0; a < Epi::NACC; a++) add_term(acc[a], t[a], rs, a, row);
+        }
       }
     }
   } else {
@@ -342,52 +350,99 @@ __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_
         for (int q = 0; q < lr.z; q++) tot += p[q];
         A.long_counter[sg.w] = 0u;
         epi.prefetch(lr.x);
-        const double term = epi.row(lr.x, tot);
-        if constexpr (Epi::NACC > 0) add_term(acc[0], term, rs, 0, lr.x);
+        double t[Epi::NACC > 0 ? Epi::NACC : 1];
+        epi.row(lr.x, tot, t);
+        if constexpr (Epi::NACC > 0) {
+#pragma unroll
+          for (int a = 0; a < Epi::NACC; a++) add_term(acc[a], t[a], rs, a, lr.x);
+        }
       }
     }
   }
   if constexpr (Epi::NACC > 0) block_partials<Epi::NACC>(acc, rs);
 }
 
-// ======================================== multi-GPU K3b: after the all-reduce
-// buf[0..n) = sum over ranks of the partial A_g' y_g', buf[n] = sum of |dy|^2.
+// ============================================================ multi-GPU kernels
+// World > 1: rank g owns a row block (A_g, A_g^T, y, ax, b) AND a column shard
+// of every n-vector (x, aty, c, l, u, xSum ...).  Full-length vectors exist only as the gather input
+// of K2 (`xfull`) and as the partial A_g^T y (`part`), both laid out in G segments of
+// seg_len = shard_len + 2 whose tail slots carry scalars.  One pass =
+//   M1 primal_shard_kernel   finalize aty on the shard if the last pass was accepted, then the
+//                            trial x' = proj(x - tau(c - aty)) on the shard -> send buffer (+ |dx|^2)
+//   all-gather               x' shards (+ scalar tails) -> xfull on every rank
+//   K2 spmv<DualEpilogueMg>  local rows; |dy|^2 and the ROW-side interaction (AΔx)·Δy
+//   M2 stash_scalars_kernel  block partials of K2 -> the tail slots of every segment of `part`
+//   K3a spmv<PartialAty>     part = A_g^T y'
+//   reduce-scatter           part -> red (my shard of A^T y' + summed scalars)
+//   M3 step_rule_mg_kernel   step rule from the gathered / reduced scalars
 __global__ void __launch_bounds__(kThreads)
-interaction_kernel(int n, PdhgState* __restrict__ st, const double* __restrict__ buf,
-                   const double* __restrict__ x0, const double* __restrict__ x1,
-                   double* __restrict__ aty0, double* __restrict__ aty1, ReduceScratch rs) {
+primal_shard_kernel(int len, PdhgState* __restrict__ st, double* __restrict__ xs0, double* __restrict__ xs1,
+                    double* __restrict__ aty_s, const double* __restrict__ red, const double* __restrict__ c,
+                    const double* __restrict__ lo, const double* __restrict__ up, double* __restrict__ xsum,
+                    double* __restrict__ send, ReduceScratch rs) {
   if (st->iter >= st->stop_iter) return;
   const int cur = st->cur;
-  const double* x = cur ? x1 : x0;
-  const double* xn = cur ? x0 : x1;
-  const double* aty = cur ? aty1 : aty0;
-  double* atyn = cur ? aty0 : aty1;
+  const double tau = st->tau_try, ntau = -tau;
+  const bool pend = st->pending != 0, take = st->accepted_last != 0;
+  const double w = st->w_pending;
+  const double* __restrict__ x = cur ? xs1 : xs0;
+  double* __restrict__ xn = cur ? xs0 : xs1;
   double acc[1] = {0.0};
   const int stride = gridDim.x * kThreads;
-  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
-    const double s = buf[i];
-    atyn[i] = s;
-    add_term(acc[0], (x[i] - xn[i]) * (aty[i] - s), rs, 0, i);
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < len; i += stride) {
+    double ai;
+    if (take) { ai = red[i]; aty_s[i] = ai; } else ai = aty_s[i];
+    const double xc = x[i];
+    if (pend) xsum[i] = xsum[i] + w * xc;
+    double v = xc + ntau * c[i];
+    v = v + tau * ai;
+    const double u = up[i], l = lo[i];
+    v = v < u ? v : u;
+    v = v > l ? v : l;
+    xn[i] = v;
+    send[i] = v;
+    const double d = xc - v;
+    acc[0] += d * d;
   }
   block_partials<1>(acc, rs);
 }
 
-// multi-GPU: adds the local |dy|^2 block partials of K2 (fixed order) into the tail slot of the
-// all-reduce buffer
-__global__ void __launch_bounds__(kStepThreads) stash_dy2_kernel(PdhgState* st, const double* __restrict__ partials, int nb, double* slot) {
-  __shared__ double sm[kStepThreads / 32];
-  if (st->iter >= st->stop_iter) { if (threadIdx.x == 0) *slot = 0.0; return; }
+// sums block partials (fixed order) and writes them to dst[k * stride + slot] for k < copies
+template <int NV>
+__global__ void __launch_bounds__(kStepThreads)
+stash_scalars_kernel(PdhgState* st, const double* __restrict__ partials, int nb, double* dst, int copies, int stride) {
+  __shared__ double sm[NV][kStepThreads / 32];
+  if (st && st->iter >= st->stop_iter) return;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double s = 0.0;
-  for (int i = threadIdx.x; i < nb; i += kStepThreads) s += partials[i];
-  s = warp_sum(s);
-  if (lane == 0) sm[wid] = s;
+#pragma unroll
+  for (int a = 0; a < NV; a++) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nb; i += kStepThreads) s += partials[(size_t)a * nb + i];
+    s = warp_sum(s);
+    if (lane == 0) sm[a][wid] = s;
+  }
   __syncthreads();
   if (wid == 0) {
-    s = lane < kStepThreads / 32 ? sm[lane] : 0.0;
-    s = warp_sum(s);
-    if (lane == 0) *slot = s;
+#pragma unroll
+    for (int a = 0; a < NV; a++) {
+      double s = lane < kStepThreads / 32 ? sm[a][lane] : 0.0;
+      s = warp_sum(s);
+      s = __shfl_sync(0xffffffffu, s, 0);
+      for (int k = lane; k < copies; k += 32) dst[(size_t)k * stride + a] = s;
+    }
   }
+}
+
+__global__ void step_rule_mg_kernel(PdhgState* st, const double* __restrict__ xfull, int world, int seg_len,
+                                    int shard_len, const double* __restrict__ red) {
+  if (threadIdx.x != 0 || st->iter >= st->stop_iter) return;
+  double dx2 = 0.0;
+  for (int g = 0; g < world; g++) dx2 += xfull[(size_t)g * seg_len + shard_len];   // fixed rank order
+  st->dx2 = dx2;
+  st->dy2 = red[shard_len];
+  const int it0 = st->iter;
+  step_rule(st, red[shard_len + 1]);
+  st->accepted_last = st->iter != it0;
 }
 
 // ===================================================== check-iteration kernels
@@ -619,25 +674,54 @@ void launch_spmv_primal(cudaStream_t s, const DevSell& A, PdhgState* st, const d
 // multi-GPU K3a: partial A_g' y' into buf (input chosen by the device state)
 struct PartialAtyEpilogue {
   static constexpr int NACC = 0;
-  PdhgState* st;
+  PdhgState* st;       // nullptr: unconditional (check iterations), input = y0
   const double *y0, *y1;
   double* out;
+  int shard_len;
   __device__ bool begin() {
+    if (!st) return true;
     if (st->iter >= st->stop_iter) return false;
     y0 = st->cur ? y0 : y1;
     return true;
   }
   __device__ const double* input() const { return y0; }
   __device__ void prefetch(int) {}
-  __device__ double row(int r, double s) const { out[r] = s; return 0.0; }
+  // the partial vector is laid out in G segments of (shard_len + 2): the two tail slots of every
+  // segment carry this rank's scalars so that a reduce-scatter delivers their sums to every rank
+  __device__ void row(int r, double s, double*) const { out[r + 2 * (r / shard_len)] = s; }
   __device__ void finalize(const double*) const {}
 };
 
 void launch_spmv_partial_aty(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
-                             double* buf, const double* dy2_partials, int dy2_nb) {
-  PartialAtyEpilogue e{st, y0, y1, buf};
+                             double* part, int shard_len) {
+  PartialAtyEpilogue e{st, y0, y1, part, shard_len};
   spmv_sell_kernel<PartialAtyEpilogue><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr, nullptr, 0, 0});
-  stash_dy2_kernel<<<1, kStepThreads, 0, s>>>(st, dy2_partials, dy2_nb, buf + A.nrows);
+}
+
+void launch_spmv_dual_mg(cudaStream_t s, const DevSell& A, PdhgState* st, const double* xfull, double* y0, double* y1,
+                         double* ax0, double* ax1, const double* b, double* ysum, int neq, ReduceScratch rs) {
+  DualEpilogueMg e{};
+  e.st = st; e.x0 = xfull; e.x1 = xfull; e.y0 = y0; e.y1 = y1; e.ax0 = ax0; e.ax1 = ax1; e.b = b; e.ysum = ysum;
+  e.neq = neq; e.row_offset = 0;
+  spmv_sell_kernel<DualEpilogueMg><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, rs);
+}
+
+void launch_primal_shard(cudaStream_t s, int len, PdhgState* st, double* xs0, double* xs1, double* aty_s,
+                         const double* red, const double* c, const double* lo, const double* up, double* xsum,
+                         double* send, ReduceScratch rs) {
+  primal_shard_kernel<<<ew_grid(len), kThreads, 0, s>>>(len, st, xs0, xs1, aty_s, red, c, lo, up, xsum, send, rs);
+}
+int primal_shard_grid(int len) { return ew_grid(len); }
+
+void launch_stash_scalars(cudaStream_t s, int nv, PdhgState* st, const double* partials, int nb, double* dst, int copies,
+                          int stride) {
+  if (nv == 1) stash_scalars_kernel<1><<<1, kStepThreads, 0, s>>>(st, partials, nb, dst, copies, stride);
+  else stash_scalars_kernel<2><<<1, kStepThreads, 0, s>>>(st, partials, nb, dst, copies, stride);
+}
+
+void launch_step_rule_mg(cudaStream_t s, PdhgState* st, const double* xfull, int world, int seg_len, int shard_len,
+                         const double* red) {
+  step_rule_mg_kernel<<<1, 32, 0, s>>>(st, xfull, world, seg_len, shard_len, red);
 }
 
 void launch_step_rule(cudaStream_t s, PdhgState* st, ReduceScratch r1, int nb1, ReduceScratch r2, int nb2,
@@ -646,12 +730,7 @@ void launch_step_rule(cudaStream_t s, PdhgState* st, ReduceScratch r1, int nb1, 
 }
 
 int primal_step_grid(int n) { return ew_grid((n + 1) / 2); }
-int interaction_grid(int n) { return ew_grid(n); }
 
-void launch_interaction(cudaStream_t s, int n, PdhgState* st, const double* buf, const double* x0,
-                        const double* x1, double* aty0, double* aty1, ReduceScratch rs) {
-  interaction_kernel<<<ew_grid(n), kThreads, 0, s>>>(n, st, buf, x0, x1, aty0, aty1, rs);
-}
 
 void launch_average(cudaStream_t s, int len, const double* v, double* sum, double* avg, int pending, double w,
                     double scale) {

@@ -17,13 +17,20 @@ void launch_spmv_dual(cudaStream_t s, const DevSell& A, PdhgState* st, const dou
 void launch_spmv_primal(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
                         const double* x0, const double* x1, double* aty0, double* aty1, ReduceScratch rs);
 void launch_spmv_partial_aty(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
-                             double* buf, const double* dy2_partials, int dy2_nb);
+                             double* part, int shard_len);
+void launch_spmv_dual_mg(cudaStream_t s, const DevSell& A, PdhgState* st, const double* xfull, double* y0, double* y1,
+                         double* ax0, double* ax1, const double* b, double* ysum, int neq, ReduceScratch rs);
+void launch_primal_shard(cudaStream_t s, int len, PdhgState* st, double* xs0, double* xs1, double* aty_s,
+                         const double* red, const double* c, const double* lo, const double* up, double* xsum,
+                         double* send, ReduceScratch rs);
+int primal_shard_grid(int len);
+void launch_stash_scalars(cudaStream_t s, int nv, PdhgState* st, const double* partials, int nb, double* dst, int copies,
+                          int stride);
+void launch_step_rule_mg(cudaStream_t s, PdhgState* st, const double* xfull, int world, int seg_len, int shard_len,
+                         const double* red);
 void launch_step_rule(cudaStream_t s, PdhgState* st, ReduceScratch r1, int nb1, ReduceScratch r2, int nb2,
                       ReduceScratch r3, int nb3, const double* dy2_override);
 int primal_step_grid(int n);
-int interaction_grid(int n);
-void launch_interaction(cudaStream_t s, int n, PdhgState* st, const double* buf, const double* x0,
-                        const double* x1, double* aty0, double* aty1, ReduceScratch rs);
 void launch_average(cudaStream_t s, int len, const double* v, double* sum, double* avg, int pending, double w,
                     double scale);
 void launch_col_check_a(cudaStream_t s, int n, int nit, ColIter a, ColIter b, const double* c, const double* lo,
