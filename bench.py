@@ -9,7 +9,8 @@ check iterations (average iterate, 2 extra SpMV, residuals, restarts) that fall 
 them, with the LP resident in HBM (`value`), and the same K iterations through the
 public host-buffer call b200pdlp_solve -- formulate + scale + layout + H2D + K
 iterations + D2H of the HighsSolution -- (`e2e`).  N > 1: the same LP row-partitioned
-over N GPUs, one process per GPU (torchrun), one NCCL all-reduce of A'y per iteration
+over N GPUs, one process per GPU (torchrun), reduce-scatter of A'y + all-gather of x per iteration
+(fused into the engine's own kernels over NVLink peer memory; B200PDLP_NO_P2P=1 selects NCCL)
 ("strong" scaling: total work is fixed).  Prints ONE JSON line on rank 0.
 
 --impl reference times the reference's own CPU pdlp (oracle/_ref, the unmodified HiGHS
@@ -199,6 +200,11 @@ def main():
         ids = [engine.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         prob.comm_init(ids[0])
+        if os.environ.get("B200PDLP_NO_P2P", "0") != "1":
+            # fused NVLink path: exchange CUDA-IPC handles of the exchange buffers
+            handles = [None] * world
+            dist.all_gather_object(handles, prob.p2p_export())
+            prob.p2p_import(b"".join(handles))
     # ---- warm-up: W iterations (also captures the CUDA graphs)
     prob.solve(iter_limit=W + 1)
     # ---- timed: exactly K iterations, inputs resident in HBM
@@ -282,7 +288,10 @@ def main():
                    "options": "solver=pdlp presolve=off, adaptive step + restarts, checks every 40 iterations",
                    "l2": "inputs larger than L2 (one iteration streams ~0.37 GB vs 126 MB L2)" if args.workload != "S2"
                          else "working set fits L2 (S2)",
-                   "parallelism": f"row-partition x{world}" if world > 1 else "single GPU"},
+                   "parallelism": (f"row blocks + column shards x{world}, "
+                                   + ("reduce-scatter/all-gather fused into our kernels over NVLink peer memory"
+                                      if os.environ.get("B200PDLP_NO_P2P", "0") != "1" else "NCCL reduce-scatter + all-gather"))
+                   if world > 1 else "single GPU"},
         "gpu_launches": res["kernel_launches"], "passes": res["passes"], "restarts": res["restarts"],
         "wall_seconds": wall, "pass_device_ms": res["iter_device_ms"],
         "phase_us": (None if world == 1 else {"primal_shard+allgather": k_us[0], "Ax+dual": k_us[1], "partial_ATy": k_us[2],

@@ -169,6 +169,12 @@ struct b200pdlp_problem {
   // allocated with nl = shard_len entries (zero padded); full vectors use G segments of seg_len
   int nl = 0, nl_real = 0, c0 = 0, shard_len = 0, seg_len = 0;
   DevBuf<double> xfull, part, red, send;
+  // fused P2P path
+  bool p2p = false;
+  PeerPtrs peers{};
+  std::vector<void*> ipc_opened;
+  DevBuf<unsigned long long> flags, epochs;
+  DevBuf<int> fault;
   cudaStream_t stream = nullptr;
   // n-vectors (replicated across ranks)
   DevBuf<double> x[2], aty[2], xsum, xavg, atyavg, xlr, cost, lower, upper, colscale;
@@ -191,6 +197,7 @@ struct b200pdlp_problem {
   ~b200pdlp_problem() {
     if (graph_main) cudaGraphExecDestroy(graph_main);
     if (graph_small) cudaGraphExecDestroy(graph_small);
+    for (void* q : ipc_opened) cudaIpcCloseMemHandle(q);
     if (comm) NcclApi::get().CommDestroy(comm);
     if (hstate) cudaFreeHost(hstate);
     if (houts) cudaFreeHost(houts);
@@ -299,6 +306,7 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   if (world > 1) {
     p->xfull.alloc((size_t)world * p->seg_len); p->part.alloc((size_t)world * p->seg_len);
     p->red.alloc(p->seg_len); p->send.alloc(p->seg_len);
+    p->flags.alloc(2 * kMaxPeers); p->epochs.alloc(2); p->fault.alloc(1);
   }
   {
     std::vector<double> t(std::max(std::max(n, nl), ml));
@@ -349,6 +357,19 @@ static void enqueue_pass_mg(b200pdlp_problem* p) {
   cudaStream_t s = p->stream;
   PdhgState* st = p->state.p;
   const ReduceScratch r1 = p->rs(kSlotK1, p->nl), r2 = p->rs(kSlotK2, p->ml);
+  if (p->p2p) {
+    // fused compute + collective over NVLink peer memory (5 launches, no NCCL)
+    launch_primal_shard_p2p(s, p->nl, st, p->x[0].p, p->x[1].p, p->aty[0].p, p->peers, p->world, p->rank, p->seg_len,
+                            p->cost.p, p->lower.p, p->upper.p, p->xsum.p, r1);
+    launch_p2p_barrier(s, 0, st, r1.partials, primal_shard_grid(p->nl), p->peers, p->world, p->rank, p->seg_len,
+                       p->shard_len, p->epochs.p, p->fault.p);
+    launch_spmv_dual_mg(s, p->A.dev, st, p->xfull.p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->rhs.p,
+                        p->ysum.p, p->neq_local, r2);
+    launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->part.p, p->shard_len);
+    launch_p2p_barrier(s, 1, st, r2.partials, p->A.grid(), p->peers, p->world, p->rank, p->seg_len, p->shard_len,
+                       p->epochs.p, p->fault.p);
+    return;
+  }
   launch_primal_shard(s, p->nl, st, p->x[0].p, p->x[1].p, p->aty[0].p, p->red.p, p->cost.p, p->lower.p, p->upper.p,
                       p->xsum.p, p->send.p, r1);
   launch_stash_scalars(s, 1, st, r1.partials, primal_shard_grid(p->nl), p->send.p + p->shard_len, 1, 0);
@@ -430,8 +451,9 @@ static CheckResult run_check(b200pdlp_problem* p, bool timed_out_local) {
   const int acur = p->world == 1 ? cur : 0;        // multi-GPU keeps one current A^T y shard
   const double scale = h->sum_step > 0.0 ? 1.0 / h->sum_step : 1.0;
   if (p->world > 1 && h->accepted_last) {
-    // the last accepted pass left its A^T y' in the reduce-scatter buffer: make it current
-    CUDA_OK(cudaMemcpyAsync(p->aty[0].p, p->red.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    // the last accepted pass left its A^T y' un-reduced (P2P) / in the reduce-scatter buffer (NCCL): make it current
+    if (p->p2p) { launch_reduce_part_p2p(s, n, p->aty[0].p, p->peers, p->world, p->rank, p->seg_len); p->launches++; }
+    else CUDA_OK(cudaMemcpyAsync(p->aty[0].p, p->red.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
     h->accepted_last = 0;
     push_state(p);
   }
@@ -730,7 +752,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
     p->graph_main_passes = want_main;
   }
   if (!p->graph_small) { p->graph_small_passes = 4; p->graph_small = capture_passes(p, 4); }
-  p->kernels_per_pass = p->world == 1 ? 4 : 6;   // ours; NCCL kernels not counted
+  p->kernels_per_pass = p->world == 1 ? 4 : (p->p2p ? 5 : 6);   // ours; NCCL kernels not counted
 
   const double tol_p = prm.tol_primal * (1.0 + f.norm_rhs), tol_d = prm.tol_dual * (1.0 + f.norm_cost);
   RestartMemo memo;
@@ -826,7 +848,14 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   const double* dy = use_avg ? p->yavg.p : p->y[cur].p;
   const double* dax = use_avg ? p->axavg.p : p->ax[cur].p;
   if (p->world > 1 && h->accepted_last && !use_avg) {   // (only when the loop never ran a check, e.g. iter_limit <= 0)
-    CUDA_OK(cudaMemcpyAsync(p->aty[0].p, p->red.p, (size_t)nl * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (p->p2p) launch_reduce_part_p2p(s, nl, p->aty[0].p, p->peers, p->world, p->rank, p->seg_len);
+    else CUDA_OK(cudaMemcpyAsync(p->aty[0].p, p->red.p, (size_t)nl * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  }
+  if (p->p2p) {
+    int fault = 0;
+    CUDA_OK(cudaMemcpyAsync(&fault, p->fault.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    if (fault) throw Error(B200PDLP_ERR_STATE, "P2P barrier timed out (a peer rank did not arrive)");
   }
   const double* daty = use_avg ? p->atyavg.p : p->aty[p->world == 1 ? cur : 0].p;
   std::vector<double> hx(n), hy(m, 0.0), hax(m, 0.0), haty(n);
@@ -1091,6 +1120,26 @@ int b200pdlp_bench_pass(b200pdlp_problem* p, int32_t reps, float ms[4]) {
       } else {
         // ms[0] = primal shard + all-gather, ms[1] = A x + dual, ms[2] = partial A'y, ms[3] = reduce-scatter + step rule
         const ReduceScratch r1 = p->rs(kSlotK1, p->nl), r2 = p->rs(kSlotK2, p->ml);
+        if (p->p2p) {
+          CUDA_OK(cudaEventRecord(ev[0], s));
+          launch_primal_shard_p2p(s, p->nl, st, p->x[0].p, p->x[1].p, p->aty[0].p, p->peers, p->world, p->rank,
+                                  p->seg_len, p->cost.p, p->lower.p, p->upper.p, p->xsum.p, r1);
+          launch_p2p_barrier(s, 0, st, r1.partials, primal_shard_grid(p->nl), p->peers, p->world, p->rank, p->seg_len,
+                             p->shard_len, p->epochs.p, p->fault.p);
+          CUDA_OK(cudaEventRecord(ev[1], s));
+          launch_spmv_dual_mg(s, p->A.dev, st, p->xfull.p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->rhs.p,
+                              p->ysum.p, p->neq_local, r2);
+          CUDA_OK(cudaEventRecord(ev[2], s));
+          launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->part.p, p->shard_len);
+          CUDA_OK(cudaEventRecord(ev[3], s));
+          launch_p2p_barrier(s, 1, st, r2.partials, p->A.grid(), p->peers, p->world, p->rank, p->seg_len, p->shard_len,
+                             p->epochs.p, p->fault.p);
+          CUDA_OK(cudaEventRecord(ev[4], s));
+          CUDA_OK(cudaEventSynchronize(ev[4]));
+          p->launches += p->kernels_per_pass;
+          for (int k = 0; k < 4; k++) { float t = 0.f; CUDA_OK(cudaEventElapsedTime(&t, ev[k], ev[k + 1])); acc[k] += t; }
+          continue;
+        }
         CUDA_OK(cudaEventRecord(ev[0], s));
         launch_primal_shard(s, p->nl, st, p->x[0].p, p->x[1].p, p->aty[0].p, p->red.p, p->cost.p, p->lower.p,
                             p->upper.p, p->xsum.p, p->send.p, r1);
@@ -1167,6 +1216,45 @@ int b200pdlp_comm_init(b200pdlp_problem* p, const uint8_t id[128]) {
     ncclUniqueId u;
     memcpy(&u, id, 128);
     NCCL_OK(nccl().CommInitRank(&p->comm, p->world, u, p->rank));
+  });
+}
+
+int b200pdlp_p2p_export(b200pdlp_problem* p, uint8_t handles[B200PDLP_IPC_BYTES]) {
+  return guarded([&] {
+    static_assert(3 * sizeof(cudaIpcMemHandle_t) == B200PDLP_IPC_BYTES, "IPC blob size");
+    if (!p || !handles || p->world < 2) throw Error(B200PDLP_ERR_ARG, "p2p_export needs a multi-GPU problem");
+    set_device(p);
+    cudaIpcMemHandle_t h[3];
+    CUDA_OK(cudaIpcGetMemHandle(&h[0], p->part.p));
+    CUDA_OK(cudaIpcGetMemHandle(&h[1], p->xfull.p));
+    CUDA_OK(cudaIpcGetMemHandle(&h[2], p->flags.p));
+    memcpy(handles, h, sizeof(h));
+  });
+}
+
+int b200pdlp_p2p_import(b200pdlp_problem* p, const uint8_t* all_handles) {
+  return guarded([&] {
+    if (!p || !all_handles || p->world < 2) throw Error(B200PDLP_ERR_ARG, "p2p_import needs a multi-GPU problem");
+    if (p->world > kMaxPeers) throw Error(B200PDLP_ERR_ARG, "too many ranks for the P2P path");
+    set_device(p);
+    for (int g = 0; g < p->world; g++) {
+      if (g == p->rank) {
+        p->peers.part[g] = p->part.p; p->peers.xfull[g] = p->xfull.p; p->peers.flags[g] = p->flags.p;
+        continue;
+      }
+      cudaIpcMemHandle_t h[3];
+      memcpy(h, all_handles + (size_t)g * B200PDLP_IPC_BYTES, sizeof(h));
+      void* q[3];
+      for (int k = 0; k < 3; k++) {
+        CUDA_OK(cudaIpcOpenMemHandle(&q[k], h[k], cudaIpcMemLazyEnablePeerAccess));
+        p->ipc_opened.push_back(q[k]);
+      }
+      p->peers.part[g] = (double*)q[0]; p->peers.xfull[g] = (double*)q[1]; p->peers.flags[g] = (unsigned long long*)q[2];
+    }
+    p->p2p = true;
+    // graphs captured for the NCCL path are stale now
+    if (p->graph_main) { cudaGraphExecDestroy(p->graph_main); p->graph_main = nullptr; }
+    if (p->graph_small) { cudaGraphExecDestroy(p->graph_small); p->graph_small = nullptr; }
   });
 }
 

@@ -72,6 +72,14 @@ struct DevSell {
   int padded_total;                       // elements in col/val (end of the last slice)
 };
 
+// peer-memory view for the fused multi-GPU path (one process per GPU, buffers mapped with CUDA IPC)
+constexpr int kMaxPeers = 16;
+struct PeerPtrs {
+  double* part[kMaxPeers];                 // every rank's partial A_g^T y buffer (G segments of seg_len)
+  double* xfull[kMaxPeers];                // every rank's gathered trial x (G segments of seg_len)
+  unsigned long long* flags[kMaxPeers];    // every rank's barrier flags [2][kMaxPeers]
+};
+
 // scratch of the two-stage deterministic reductions
 struct ReduceScratch {
   double* partials;   // [nacc][gridDim.x]

@@ -407,6 +407,140 @@ primal_shard_kernel(int len, PdhgState* __restrict__ st, double* __restrict__ xs
   block_partials<1>(acc, rs);
 }
 
+// ------------------------------------------------------------ fused P2P variant
+// Same algorithm, but the two collectives are folded into our own kernels over NVLink peer memory
+// (buffers of all ranks mapped with CUDA IPC):
+//   * reduce-scatter  -> the primal shard kernel adds the G partial A_h^T y' it needs straight from
+//                        the peers' `part` buffers (fixed rank order = deterministic), and
+//   * all-gather      -> writes its trial x' shard straight into every peer's `xfull`;
+//   * two flag barriers (one tiny CTA each) order the phases and carry the scalars; the second one
+//     also evaluates the step rule.
+__device__ __forceinline__ double ld_sys(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kThreads)
+primal_shard_p2p_kernel(int len, PdhgState* __restrict__ st, double* __restrict__ xs0, double* __restrict__ xs1,
+                        double* __restrict__ aty_s, PeerPtrs pp, int world, int rank, int seg_len,
+                        const double* __restrict__ c, const double* __restrict__ lo, const double* __restrict__ up,
+                        double* __restrict__ xsum, ReduceScratch rs) {
+  if (st->iter >= st->stop_iter) return;
+  const int cur = st->cur;
+  const double tau = st->tau_try, ntau = -tau;
+  const bool pend = st->pending != 0, take = st->accepted_last != 0;
+  const double w = st->w_pending;
+  const double* __restrict__ x = cur ? xs1 : xs0;
+  double* __restrict__ xn = cur ? xs0 : xs1;
+  const size_t seg = (size_t)rank * seg_len;
+  double acc[1] = {0.0};
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < len; i += stride) {
+    double ai;
+    if (take) {
+      ai = 0.0;
+      for (int h = 0; h < world; h++) ai += ld_sys(pp.part[h] + seg + i);   // reduce-scatter, fused
+      aty_s[i] = ai;
+    } else {
+      ai = aty_s[i];
+    }
+    const double xc = x[i];
+    if (pend) xsum[i] = xsum[i] + w * xc;
+    double v = xc + ntau * c[i];
+    v = v + tau * ai;
+    const double u = up[i], l = lo[i];
+    v = v < u ? v : u;
+    v = v > l ? v : l;
+    xn[i] = v;
+    for (int h = 0; h < world; h++) pp.xfull[h][seg + i] = v;               // all-gather, fused
+    const double d = xc - v;
+    acc[0] += d * d;
+  }
+  __threadfence_system();
+  block_partials<1>(acc, rs);
+}
+
+// only the fused reduce (check iterations: make the accepted A^T y' current without a primal step)
+__global__ void __launch_bounds__(kThreads)
+reduce_part_p2p_kernel(int len, double* __restrict__ dst, PeerPtrs pp, int world, int rank, int seg_len) {
+  const size_t seg = (size_t)rank * seg_len;
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < len; i += stride) {
+    double ai = 0.0;
+    for (int h = 0; h < world; h++) ai += ld_sys(pp.part[h] + seg + i);
+    dst[i] = ai;
+  }
+}
+
+// cross-GPU barrier: lane h signals peer h and waits for peer h.  mode 0 (after the primal shard
+// kernel): first publishes this rank's |dx|^2 into every peer's xfull tail.  mode 1 (after the partial
+// A^T y): first publishes |dy|^2 and the row-side interaction into the local `part` tails, and after
+// the barrier adds all ranks' scalars in rank order and applies the step rule.
+__global__ void __launch_bounds__(kStepThreads)
+p2p_barrier_kernel(int mode, PdhgState* st, const double* __restrict__ partials, int nb, PeerPtrs pp, int world,
+                   int rank, int seg_len, int shard_len, unsigned long long* epochs, int* fault) {
+  __shared__ double sm[2][kStepThreads / 32];
+  __shared__ double tot[2];
+  if (st->iter >= st->stop_iter) return;   // identical on every rank: nobody enters
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nv = mode == 0 ? 1 : 2;
+  for (int a = 0; a < nv; a++) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nb; i += kStepThreads) s += partials[(size_t)a * nb + i];
+    s = warp_sum(s);
+    if (lane == 0) sm[a][wid] = s;
+  }
+  __syncthreads();
+  if (wid == 0) {
+    for (int a = 0; a < nv; a++) {
+      double s = lane < kStepThreads / 32 ? sm[a][lane] : 0.0;
+      s = warp_sum(s);
+      if (lane == 0) tot[a] = s;
+    }
+    __syncwarp();
+    const size_t tail = (size_t)rank * seg_len + shard_len;
+    if (mode == 0) {
+      if (lane < world) pp.xfull[lane][tail] = tot[0];
+    } else {
+      // my scalars go into the tail of EVERY segment of my own buffer: reader r looks at segment r
+      if (lane < world) {
+        double* t = pp.part[rank] + (size_t)lane * seg_len + shard_len;
+        t[0] = tot[0];
+        t[1] = tot[1];
+      }
+    }
+    __threadfence_system();
+    unsigned long long e = 0;
+    if (lane == 0) { e = epochs[mode] + 1; epochs[mode] = e; }
+    e = __shfl_sync(0xffffffffu, e, 0);
+    if (lane < world) {
+      volatile unsigned long long* mine = pp.flags[rank] + mode * kMaxPeers + lane;
+      unsigned long long* theirs = pp.flags[lane] + mode * kMaxPeers + rank;
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(e) : "memory");
+      long long spins = 0;
+      while (*mine < e) {
+        if (++spins > (1LL << 31)) { *fault = 1; break; }   // never hang the device
+      }
+    }
+    __syncwarp();
+    __threadfence_system();
+    if (mode == 1 && lane == 0) {
+      double dx2 = 0.0, dy2 = 0.0, inter = 0.0;
+      for (int g = 0; g < world; g++) dx2 += ld_sys(pp.xfull[rank] + (size_t)g * seg_len + shard_len);
+      for (int h = 0; h < world; h++) {
+        dy2 += ld_sys(pp.part[h] + tail);
+        inter += ld_sys(pp.part[h] + tail + 1);
+      }
+      st->dx2 = dx2;
+      st->dy2 = dy2;
+      const int it0 = st->iter;
+      step_rule(st, inter);
+      st->accepted_last = st->iter != it0;
+    }
+  }
+}
+
 // sums block partials (fixed order) and writes them to dst[k * stride + slot] for k < copies
 template <int NV>
 __global__ void __launch_bounds__(kStepThreads)
@@ -717,6 +851,20 @@ void launch_stash_scalars(cudaStream_t s, int nv, PdhgState* st, const double* p
                           int stride) {
   if (nv == 1) stash_scalars_kernel<1><<<1, kStepThreads, 0, s>>>(st, partials, nb, dst, copies, stride);
   else stash_scalars_kernel<2><<<1, kStepThreads, 0, s>>>(st, partials, nb, dst, copies, stride);
+}
+
+void launch_primal_shard_p2p(cudaStream_t s, int len, PdhgState* st, double* xs0, double* xs1, double* aty_s,
+                             const PeerPtrs& pp, int world, int rank, int seg_len, const double* c, const double* lo,
+                             const double* up, double* xsum, ReduceScratch rs) {
+  primal_shard_p2p_kernel<<<ew_grid(len), kThreads, 0, s>>>(len, st, xs0, xs1, aty_s, pp, world, rank, seg_len, c, lo,
+                                                            up, xsum, rs);
+}
+void launch_reduce_part_p2p(cudaStream_t s, int len, double* dst, const PeerPtrs& pp, int world, int rank, int seg_len) {
+  reduce_part_p2p_kernel<<<ew_grid(len), kThreads, 0, s>>>(len, dst, pp, world, rank, seg_len);
+}
+void launch_p2p_barrier(cudaStream_t s, int mode, PdhgState* st, const double* partials, int nb, const PeerPtrs& pp,
+                        int world, int rank, int seg_len, int shard_len, unsigned long long* epochs, int* fault) {
+  p2p_barrier_kernel<<<1, kStepThreads, 0, s>>>(mode, st, partials, nb, pp, world, rank, seg_len, shard_len, epochs, fault);
 }
 
 void launch_step_rule_mg(cudaStream_t s, PdhgState* st, const double* xfull, int world, int seg_len, int shard_len,

@@ -26,6 +26,12 @@ void launch_primal_shard(cudaStream_t s, int len, PdhgState* st, double* xs0, do
 int primal_shard_grid(int len);
 void launch_stash_scalars(cudaStream_t s, int nv, PdhgState* st, const double* partials, int nb, double* dst, int copies,
                           int stride);
+void launch_primal_shard_p2p(cudaStream_t s, int len, PdhgState* st, double* xs0, double* xs1, double* aty_s,
+                             const PeerPtrs& pp, int world, int rank, int seg_len, const double* c, const double* lo,
+                             const double* up, double* xsum, ReduceScratch rs);
+void launch_reduce_part_p2p(cudaStream_t s, int len, double* dst, const PeerPtrs& pp, int world, int rank, int seg_len);
+void launch_p2p_barrier(cudaStream_t s, int mode, PdhgState* st, const double* partials, int nb, const PeerPtrs& pp,
+                        int world, int rank, int seg_len, int shard_len, unsigned long long* epochs, int* fault);
 void launch_step_rule_mg(cudaStream_t s, PdhgState* st, const double* xfull, int world, int seg_len, int shard_len,
                          const double* red);
 void launch_step_rule(cudaStream_t s, PdhgState* st, ReduceScratch r1, int nb1, ReduceScratch r2, int nb2,

@@ -61,7 +61,7 @@ class CResult(C.Structure):
 ABI_SYMBOLS = [
     "b200pdlp_default_params", "b200pdlp_solve", "b200pdlp_problem_create", "b200pdlp_problem_destroy",
     "b200pdlp_problem_dims", "b200pdlp_problem_get_vector", "b200pdlp_problem_get_csr", "b200pdlp_spmv_ax",
-    "b200pdlp_spmv_aty", "b200pdlp_bench_spmv", "b200pdlp_bench_pass", "b200pdlp_problem_solve", "b200pdlp_nccl_unique_id",
+    "b200pdlp_spmv_aty", "b200pdlp_bench_spmv", "b200pdlp_bench_pass", "b200pdlp_p2p_export", "b200pdlp_p2p_import", "b200pdlp_problem_solve", "b200pdlp_nccl_unique_id",
     "b200pdlp_comm_init", "b200pdlp_partition_rows", "b200pdlp_last_error", "b200pdlp_version",
     "b200pdlp_device_count", "b200pdlp_form_create", "b200pdlp_form_destroy", "b200pdlp_form_dims",
     "b200pdlp_form_get_vector", "b200pdlp_form_get_csc", "b200pdlp_form_get_row_map",
@@ -115,6 +115,8 @@ def lib():
         L.b200pdlp_problem_solve.argtypes = [C.c_void_p, C.POINTER(CParams), C.POINTER(CWarm), C.POINTER(CResult)]
         L.b200pdlp_nccl_unique_id.argtypes = [C.POINTER(C.c_uint8)]
         L.b200pdlp_comm_init.argtypes = [C.c_void_p, C.POINTER(C.c_uint8)]
+        L.b200pdlp_p2p_export.argtypes = [C.c_void_p, C.POINTER(C.c_uint8)]
+        L.b200pdlp_p2p_import.argtypes = [C.c_void_p, C.POINTER(C.c_uint8)]
         L.b200pdlp_partition_rows.argtypes = [C.POINTER(CLp), C.c_int32, _ip]
         L.b200pdlp_form_create.argtypes = [C.POINTER(CLp), C.c_int32, C.POINTER(C.c_void_p)]
         L.b200pdlp_form_destroy.argtypes = [C.c_void_p]
@@ -264,6 +266,15 @@ class Problem:
     def comm_init(self, unique_id: bytes):
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         _check(lib().b200pdlp_comm_init(self._h, buf), "b200pdlp_comm_init")
+
+    def p2p_export(self) -> bytes:
+        buf = (C.c_uint8 * 192)()
+        _check(lib().b200pdlp_p2p_export(self._h, buf), "b200pdlp_p2p_export")
+        return bytes(buf)
+
+    def p2p_import(self, all_handles: bytes):
+        buf = (C.c_uint8 * len(all_handles)).from_buffer_copy(all_handles)
+        _check(lib().b200pdlp_p2p_import(self._h, buf), "b200pdlp_p2p_import")
 
     def solve(self, warm=None, trace_cap: int = 0, **params) -> dict:
         prm = make_params(**params)

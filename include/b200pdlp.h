@@ -167,6 +167,14 @@ int b200pdlp_problem_solve(b200pdlp_problem* p, const b200pdlp_params* params,
 int b200pdlp_nccl_unique_id(uint8_t id[128]);
 int b200pdlp_comm_init(b200pdlp_problem* p, const uint8_t id[128]);
 
+/* fused NVLink path (optional, after comm_init): every rank exports CUDA-IPC handles of its exchange
+ * buffers (B200PDLP_IPC_BYTES bytes), the host application all-gathers them (rank order) and every rank
+ * imports the world x B200PDLP_IPC_BYTES blob.  From then on the per-iteration reduce-scatter and
+ * all-gather run inside the engine's own kernels over peer memory; NCCL is used at check iterations only. */
+#define B200PDLP_IPC_BYTES 192
+int b200pdlp_p2p_export(b200pdlp_problem* p, uint8_t handles[B200PDLP_IPC_BYTES]);
+int b200pdlp_p2p_import(b200pdlp_problem* p, const uint8_t* all_handles);
+
 /* ---- host-only view of the standard form (no GPU needed; parity tests) -------
  * formulate (CupdlpWrapper.cpp:280-448) + scale (cupdlp_scaling.c:233-425) only. */
 typedef struct b200pdlp_form b200pdlp_form;

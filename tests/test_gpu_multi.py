@@ -25,6 +25,10 @@ prob = engine.Problem(lp, rank=rank, world=world, device=lr)
 ids = [engine.nccl_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(ids, src=0)
 prob.comm_init(ids[0])
+if sys.argv[2] == "p2p":
+    handles = [None] * world
+    dist.all_gather_object(handles, prob.p2p_export())
+    prob.p2p_import(b"".join(handles))
 res = prob.solve(tol_primal=1e-5, tol_dual=1e-5, tol_gap=1e-5, iter_limit=100000)
 if rank == 0:
     np.savez(sys.argv[1], col_value=res["col_value"], row_dual=res["row_dual"], row_value=res["row_value"],
@@ -34,7 +38,8 @@ dist.destroy_process_group()
 ''' % ROOT
 
 
-def test_two_gpu_row_partition(engine_lib, tmp_path):
+@pytest.mark.parametrize("mode", ["p2p", "nccl"])
+def test_two_gpu_row_partition(engine_lib, tmp_path, mode):
     from highs_b200 import engine
     from highs_b200.lp import synthetic_lp
     if engine.device_count() < 2:
@@ -43,7 +48,7 @@ def test_two_gpu_row_partition(engine_lib, tmp_path):
     w.write_text(WORKER)
     out = tmp_path / "res.npz"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29611", str(w), str(out)]
+           "--master-port", "29611" if mode == "p2p" else "29612", str(w), str(out), mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     multi = dict(np.load(out))
