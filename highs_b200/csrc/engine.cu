@@ -361,7 +361,7 @@ static void enqueue_pass_mg(b200pdlp_problem* p) {
     // fused compute + collective over NVLink peer memory (5 launches, no NCCL)
     launch_primal_shard_p2p(s, p->nl, st, p->x[0].p, p->x[1].p, p->aty[0].p, p->peers, p->world, p->rank, p->seg_len,
                             p->cost.p, p->lower.p, p->upper.p, p->xsum.p, r1);
-    launch_p2p_barrier(s, 0, st, r1.partials, primal_shard_grid(p->nl), p->peers, p->world, p->rank, p->seg_len,
+    launch_p2p_barrier(s, 0, st, r1.partials, primal_shard_p2p_grid(p->nl), p->peers, p->world, p->rank, p->seg_len,
                        p->shard_len, p->epochs.p, p->fault.p);
     launch_spmv_dual_mg(s, p->A.dev, st, p->xfull.p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->rhs.p,
                         p->ysum.p, p->neq_local, r2);
@@ -1124,7 +1124,7 @@ int b200pdlp_bench_pass(b200pdlp_problem* p, int32_t reps, float ms[4]) {
           CUDA_OK(cudaEventRecord(ev[0], s));
           launch_primal_shard_p2p(s, p->nl, st, p->x[0].p, p->x[1].p, p->aty[0].p, p->peers, p->world, p->rank,
                                   p->seg_len, p->cost.p, p->lower.p, p->upper.p, p->xsum.p, r1);
-          launch_p2p_barrier(s, 0, st, r1.partials, primal_shard_grid(p->nl), p->peers, p->world, p->rank, p->seg_len,
+          launch_p2p_barrier(s, 0, st, r1.partials, primal_shard_p2p_grid(p->nl), p->peers, p->world, p->rank, p->seg_len,
                              p->shard_len, p->epochs.p, p->fault.p);
           CUDA_OK(cudaEventRecord(ev[1], s));
           launch_spmv_dual_mg(s, p->A.dev, st, p->xfull.p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->rhs.p,

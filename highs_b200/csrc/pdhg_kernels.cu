@@ -433,31 +433,52 @@ primal_shard_p2p_kernel(int len, PdhgState* __restrict__ st, double* __restrict_
   const double w = st->w_pending;
   const double* __restrict__ x = cur ? xs1 : xs0;
   double* __restrict__ xn = cur ? xs0 : xs1;
-  const size_t seg = (size_t)rank * seg_len;
+  const size_t seg = (size_t)rank * seg_len;   // even: 16-byte aligned (shard_len and seg_len are even)
   double acc[1] = {0.0};
-  const int stride = gridDim.x * kThreads;
-  for (int i = blockIdx.x * kThreads + threadIdx.x; i < len; i += stride) {
-    double ai;
-    if (take) {
-      ai = 0.0;
-      for (int h = 0; h < world; h++) ai += ld_sys(pp.part[h] + seg + i);   // reduce-scatter, fused
-      aty_s[i] = ai;
-    } else {
-      ai = aty_s[i];
-    }
-    const double xc = x[i];
-    if (pend) xsum[i] = xsum[i] + w * xc;
-    double v = xc + ntau * c[i];
+  auto one = [&](double xc, double ci, double ai, double u, double l, double& out) {
+    double v = xc + ntau * ci;
     v = v + tau * ai;
-    const double u = up[i], l = lo[i];
     v = v < u ? v : u;
     v = v > l ? v : l;
-    xn[i] = v;
-    for (int h = 0; h < world; h++) pp.xfull[h][seg + i] = v;               // all-gather, fused
+    out = v;
     const double d = xc - v;
-    acc[0] += d * d;
+    return d * d;
+  };
+  const int npair = len >> 1;                  // len = shard_len is even
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < npair; i += stride) {
+    double2 ai;
+    if (take) {
+      // reduce-scatter, fused: 128-bit loads straight from every rank's partial A_h^T y' (L1 bypassed;
+      // remote lines are not cached in the local L2), added in rank order
+      ai = make_double2(0.0, 0.0);
+      for (int h = 0; h < world; h++) {
+        const double2 q = __ldcg(reinterpret_cast<const double2*>(pp.part[h] + seg) + i);
+        ai.x += q.x;
+        ai.y += q.y;
+      }
+      reinterpret_cast<double2*>(aty_s)[i] = ai;
+    } else {
+      ai = reinterpret_cast<const double2*>(aty_s)[i];
+    }
+    const double2 xc = reinterpret_cast<const double2*>(x)[i];
+    const double2 ci = reinterpret_cast<const double2*>(c)[i];
+    const double2 u = reinterpret_cast<const double2*>(up)[i];
+    const double2 l = reinterpret_cast<const double2*>(lo)[i];
+    if (pend) {
+      double2 sm = reinterpret_cast<double2*>(xsum)[i];
+      sm.x = sm.x + w * xc.x;
+      sm.y = sm.y + w * xc.y;
+      reinterpret_cast<double2*>(xsum)[i] = sm;
+    }
+    double2 o;
+    acc[0] += one(xc.x, ci.x, ai.x, u.x, l.x, o.x);
+    acc[0] += one(xc.y, ci.y, ai.y, u.y, l.y, o.y);
+    reinterpret_cast<double2*>(xn)[i] = o;
+    for (int h = 0; h < world; h++) reinterpret_cast<double2*>(pp.xfull[h] + seg)[i] = o;   // all-gather, fused
   }
-  __threadfence_system();
+  // no per-thread system fence: the kernel boundary completes the peer stores, and the barrier
+  // kernel that follows fences at system scope before it signals
   block_partials<1>(acc, rs);
 }
 
@@ -468,7 +489,7 @@ reduce_part_p2p_kernel(int len, double* __restrict__ dst, PeerPtrs pp, int world
   const int stride = gridDim.x * kThreads;
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < len; i += stride) {
     double ai = 0.0;
-    for (int h = 0; h < world; h++) ai += ld_sys(pp.part[h] + seg + i);
+    for (int h = 0; h < world; h++) ai += __ldcg(pp.part[h] + seg + i);
     dst[i] = ai;
   }
 }
@@ -846,6 +867,7 @@ void launch_primal_shard(cudaStream_t s, int len, PdhgState* st, double* xs0, do
   primal_shard_kernel<<<ew_grid(len), kThreads, 0, s>>>(len, st, xs0, xs1, aty_s, red, c, lo, up, xsum, send, rs);
 }
 int primal_shard_grid(int len) { return ew_grid(len); }
+int primal_shard_p2p_grid(int len) { return ew_grid((len + 1) / 2); }
 
 void launch_stash_scalars(cudaStream_t s, int nv, PdhgState* st, const double* partials, int nb, double* dst, int copies,
                           int stride) {
@@ -856,7 +878,7 @@ void launch_stash_scalars(cudaStream_t s, int nv, PdhgState* st, const double* p
 void launch_primal_shard_p2p(cudaStream_t s, int len, PdhgState* st, double* xs0, double* xs1, double* aty_s,
                              const PeerPtrs& pp, int world, int rank, int seg_len, const double* c, const double* lo,
                              const double* up, double* xsum, ReduceScratch rs) {
-  primal_shard_p2p_kernel<<<ew_grid(len), kThreads, 0, s>>>(len, st, xs0, xs1, aty_s, pp, world, rank, seg_len, c, lo,
+  primal_shard_p2p_kernel<<<ew_grid((len + 1) / 2), kThreads, 0, s>>>(len, st, xs0, xs1, aty_s, pp, world, rank, seg_len, c, lo,
                                                             up, xsum, rs);
 }
 void launch_reduce_part_p2p(cudaStream_t s, int len, double* dst, const PeerPtrs& pp, int world, int rank, int seg_len) {

@@ -24,6 +24,7 @@ void launch_primal_shard(cudaStream_t s, int len, PdhgState* st, double* xs0, do
                          const double* red, const double* c, const double* lo, const double* up, double* xsum,
                          double* send, ReduceScratch rs);
 int primal_shard_grid(int len);
+int primal_shard_p2p_grid(int len);
 void launch_stash_scalars(cudaStream_t s, int nv, PdhgState* st, const double* partials, int nb, double* dst, int copies,
                           int stride);
 void launch_primal_shard_p2p(cudaStream_t s, int len, PdhgState* st, double* xs0, double* xs1, double* aty_s,
