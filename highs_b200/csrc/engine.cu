@@ -169,6 +169,7 @@ struct b200pdlp_problem {
   // allocated with nl = shard_len entries (zero padded); full vectors use G segments of seg_len
   int nl = 0, nl_real = 0, c0 = 0, shard_len = 0, seg_len = 0;
   DevBuf<double> xfull, part, red, send;
+  DevBuf<int> at_outpos;           // A_g^T body row -> position in the segmented partial vector
   // fused P2P path
   bool p2p = false;
   PeerPtrs peers{};
@@ -292,7 +293,19 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
       for (int j = 0; j < n; j++) colpos[j] = (int)seg_pos(p, p->cinv[j]);
       build_sell(p->csr_local, p->rperm, colpos, long_threshold, p->A.host);
     }
-    build_sell(at, p->cperm, p->rinv, long_threshold, p->AT.host);
+    if (world == 1) {
+      build_sell(at, p->cperm, p->rinv, long_threshold, p->AT.host);
+    } else {
+      // rows of A_g^T in an order sorted by LOCAL length (windows of the global device order, so that
+      // nearby outputs stay nearby); the kernel writes through at_outpos
+      std::vector<int> ordered_rowptr(n + 1, 0);
+      for (int j = 0; j < n; j++) ordered_rowptr[j + 1] = ordered_rowptr[j] + (at.rowptr[p->cperm[j] + 1] - at.rowptr[p->cperm[j]]);
+      std::vector<int> local = make_perm(ordered_rowptr, n, true);   // positions in device order
+      std::vector<int> at_perm(n), outpos(n);
+      for (int r = 0; r < n; r++) { at_perm[r] = p->cperm[local[r]]; outpos[r] = (int)seg_pos(p, local[r]); }
+      build_sell(at, at_perm, p->rinv, long_threshold, p->AT.host);
+      p->at_outpos.from(outpos);
+    }
   }
   CUDA_OK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   p->A.upload();
@@ -365,7 +378,7 @@ static void enqueue_pass_mg(b200pdlp_problem* p) {
                        p->shard_len, p->epochs.p, p->fault.p);
     launch_spmv_dual_mg(s, p->A.dev, st, p->xfull.p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->rhs.p,
                         p->ysum.p, p->neq_local, r2);
-    launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->part.p, p->shard_len);
+    launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->part.p, p->at_outpos.p);
     launch_p2p_barrier(s, 1, st, r2.partials, p->A.grid(), p->peers, p->world, p->rank, p->seg_len, p->shard_len,
                        p->epochs.p, p->fault.p);
     return;
@@ -377,7 +390,7 @@ static void enqueue_pass_mg(b200pdlp_problem* p) {
   launch_spmv_dual_mg(s, p->A.dev, st, p->xfull.p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->rhs.p,
                       p->ysum.p, p->neq_local, r2);
   launch_stash_scalars(s, 2, st, r2.partials, p->A.grid(), p->part.p + p->shard_len, p->world, p->seg_len);
-  launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->part.p, p->shard_len);
+  launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->part.p, p->at_outpos.p);
   reduce_scatter_part(p);
   launch_step_rule_mg(s, st, p->xfull.p, p->world, p->seg_len, p->shard_len, p->red.p);
 }
@@ -421,7 +434,7 @@ static void full_aty(b200pdlp_problem* p, const double* y, double* aty) {
     launch_spmv_plain(p->stream, p->AT.dev, y, aty);
     p->launches++;
   } else {
-    launch_spmv_partial_aty(p->stream, p->AT.dev, nullptr, y, y, p->part.p, p->shard_len);
+    launch_spmv_partial_aty(p->stream, p->AT.dev, nullptr, y, y, p->part.p, p->at_outpos.p);
     p->launches++;
     reduce_scatter_part(p);
     CUDA_OK(cudaMemcpyAsync(aty, p->red.p, (size_t)p->nl * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
@@ -1057,7 +1070,7 @@ int b200pdlp_spmv_aty(b200pdlp_problem* p, const double* y, double* aty) {
     if (p->ml) CUDA_OK(cudaMemcpyAsync(p->yavg.p, t.data(), (size_t)p->ml * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     // local partial A_g^T y (no reduction over ranks)
     if (p->world == 1) launch_spmv_plain(p->stream, p->AT.dev, p->yavg.p, p->atyavg.p);
-    else launch_spmv_partial_aty(p->stream, p->AT.dev, nullptr, p->yavg.p, p->yavg.p, p->part.p, p->shard_len);
+    else launch_spmv_partial_aty(p->stream, p->AT.dev, nullptr, p->yavg.p, p->yavg.p, p->part.p, p->at_outpos.p);
     p->launches++;
     CUDA_OK(cudaStreamSynchronize(p->stream));
     CUDA_OK(cudaMemcpy(t.data(), p->world == 1 ? p->atyavg.p : p->part.p, full * sizeof(double), cudaMemcpyDeviceToHost));
@@ -1077,7 +1090,7 @@ int b200pdlp_bench_spmv(b200pdlp_problem* p, int32_t which, int32_t reps, float*
     for (int r = 0; r < reps; r++) {
       if (which == 0) launch_spmv_plain(p->stream, p->A.dev, p->world == 1 ? p->xavg.p : p->xfull.p, p->axavg.p);
       else if (p->world == 1) launch_spmv_plain(p->stream, p->AT.dev, p->yavg.p, p->atyavg.p);
-      else launch_spmv_partial_aty(p->stream, p->AT.dev, nullptr, p->yavg.p, p->yavg.p, p->part.p, p->shard_len);
+      else launch_spmv_partial_aty(p->stream, p->AT.dev, nullptr, p->yavg.p, p->yavg.p, p->part.p, p->at_outpos.p);
     }
     p->launches += reps;
     CUDA_OK(cudaEventRecord(e1, p->stream));
@@ -1130,7 +1143,7 @@ int b200pdlp_bench_pass(b200pdlp_problem* p, int32_t reps, float ms[4]) {
           launch_spmv_dual_mg(s, p->A.dev, st, p->xfull.p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->rhs.p,
                               p->ysum.p, p->neq_local, r2);
           CUDA_OK(cudaEventRecord(ev[2], s));
-          launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->part.p, p->shard_len);
+          launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->part.p, p->at_outpos.p);
           CUDA_OK(cudaEventRecord(ev[3], s));
           launch_p2p_barrier(s, 1, st, r2.partials, p->A.grid(), p->peers, p->world, p->rank, p->seg_len, p->shard_len,
                              p->epochs.p, p->fault.p);
@@ -1150,7 +1163,7 @@ int b200pdlp_bench_pass(b200pdlp_problem* p, int32_t reps, float ms[4]) {
                             p->ysum.p, p->neq_local, r2);
         launch_stash_scalars(s, 2, st, r2.partials, p->A.grid(), p->part.p + p->shard_len, p->world, p->seg_len);
         CUDA_OK(cudaEventRecord(ev[2], s));
-        launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->part.p, p->shard_len);
+        launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->part.p, p->at_outpos.p);
         CUDA_OK(cudaEventRecord(ev[3], s));
         reduce_scatter_part(p);
         launch_step_rule_mg(s, st, p->xfull.p, p->world, p->seg_len, p->shard_len, p->red.p);

@@ -832,7 +832,7 @@ struct PartialAtyEpilogue {
   PdhgState* st;       // nullptr: unconditional (check iterations), input = y0
   const double *y0, *y1;
   double* out;
-  int shard_len;
+  const int* __restrict__ outpos;
   __device__ bool begin() {
     if (!st) return true;
     if (st->iter >= st->stop_iter) return false;
@@ -842,14 +842,16 @@ struct PartialAtyEpilogue {
   __device__ const double* input() const { return y0; }
   __device__ void prefetch(int) {}
   // the partial vector is laid out in G segments of (shard_len + 2): the two tail slots of every
-  // segment carry this rank's scalars so that a reduce-scatter delivers their sums to every rank
-  __device__ void row(int r, double s, double*) const { out[r + 2 * (r / shard_len)] = s; }
+  // segment carry this rank's scalars so that a reduce-scatter delivers their sums to every rank.
+  // The rows of A_g^T are sorted by their LOCAL length (little ELL padding on every rank), so the
+  // result goes through an index array: outpos[r] = position of that column in the segmented vector.
+  __device__ void row(int r, double s, double*) const { out[outpos[r]] = s; }
   __device__ void finalize(const double*) const {}
 };
 
 void launch_spmv_partial_aty(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
-                             double* part, int shard_len) {
-  PartialAtyEpilogue e{st, y0, y1, part, shard_len};
+                             double* part, const int* outpos) {
+  PartialAtyEpilogue e{st, y0, y1, part, outpos};
   spmv_sell_kernel<PartialAtyEpilogue><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr, nullptr, 0, 0});
 }
 

@@ -17,7 +17,7 @@ void launch_spmv_dual(cudaStream_t s, const DevSell& A, PdhgState* st, const dou
 void launch_spmv_primal(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
                         const double* x0, const double* x1, double* aty0, double* aty1, ReduceScratch rs);
 void launch_spmv_partial_aty(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
-                             double* part, int shard_len);
+                             double* part, const int* outpos);
 void launch_spmv_dual_mg(cudaStream_t s, const DevSell& A, PdhgState* st, const double* xfull, double* y0, double* y1,
                          double* ax0, double* ax1, const double* b, double* ysum, int neq, ReduceScratch rs);
 void launch_primal_shard(cudaStream_t s, int len, PdhgState* st, double* xs0, double* xs1, double* aty_s,
