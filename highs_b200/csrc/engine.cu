@@ -319,7 +319,8 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   if (world > 1) {
     p->xfull.alloc((size_t)world * p->seg_len); p->part.alloc((size_t)world * p->seg_len);
     p->red.alloc(p->seg_len); p->send.alloc(p->seg_len);
-    p->flags.alloc(2 * kMaxPeers); p->epochs.alloc(2); p->fault.alloc(1);
+    p->flags.alloc(4 * kMaxPeers);   // [2][kMaxPeers] epochs + [kMaxPeers][2] scalar mailbox
+    p->epochs.alloc(2); p->fault.alloc(1);
   }
   {
     std::vector<double> t(std::max(std::max(n, nl), ml));

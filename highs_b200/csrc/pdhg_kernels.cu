@@ -521,14 +521,15 @@ p2p_barrier_kernel(int mode, PdhgState* st, const double* __restrict__ partials,
     }
     __syncwarp();
     const size_t tail = (size_t)rank * seg_len + shard_len;
+    // PUSH model: scalars are written into every peer's local memory before the flag, so that after
+    // the barrier nobody has to read across NVLink (a remote scalar read costs ~2.5 us each)
     if (mode == 0) {
       if (lane < world) pp.xfull[lane][tail] = tot[0];
     } else {
-      // my scalars go into the tail of EVERY segment of my own buffer: reader r looks at segment r
       if (lane < world) {
-        double* t = pp.part[rank] + (size_t)lane * seg_len + shard_len;
-        t[0] = tot[0];
-        t[1] = tot[1];
+        double* mb = reinterpret_cast<double*>(pp.flags[lane] + 2 * kMaxPeers) + 2 * rank;   // peer's mailbox slot of this rank
+        mb[0] = tot[0];
+        mb[1] = tot[1];
       }
     }
     __threadfence_system();
@@ -536,22 +537,24 @@ p2p_barrier_kernel(int mode, PdhgState* st, const double* __restrict__ partials,
     if (lane == 0) { e = epochs[mode] + 1; epochs[mode] = e; }
     e = __shfl_sync(0xffffffffu, e, 0);
     if (lane < world) {
-      volatile unsigned long long* mine = pp.flags[rank] + mode * kMaxPeers + lane;
+      const unsigned long long* mine = pp.flags[rank] + mode * kMaxPeers + lane;
       unsigned long long* theirs = pp.flags[lane] + mode * kMaxPeers + rank;
       asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(e) : "memory");
       long long spins = 0;
-      while (*mine < e) {
+      unsigned long long seen = 0;
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
         if (++spins > (1LL << 31)) { *fault = 1; break; }   // never hang the device
-      }
+      } while (seen < e);
     }
     __syncwarp();
-    __threadfence_system();
     if (mode == 1 && lane == 0) {
+      const double* mb = reinterpret_cast<const double*>(pp.flags[rank] + 2 * kMaxPeers);
       double dx2 = 0.0, dy2 = 0.0, inter = 0.0;
-      for (int g = 0; g < world; g++) dx2 += ld_sys(pp.xfull[rank] + (size_t)g * seg_len + shard_len);
-      for (int h = 0; h < world; h++) {
-        dy2 += ld_sys(pp.part[h] + tail);
-        inter += ld_sys(pp.part[h] + tail + 1);
+      for (int g = 0; g < world; g++) {   // local memory, fixed rank order
+        dx2 += ld_sys(pp.xfull[rank] + (size_t)g * seg_len + shard_len);
+        dy2 += ld_sys(mb + 2 * g);
+        inter += ld_sys(mb + 2 * g + 1);
       }
       st->dx2 = dx2;
       st->dy2 = dy2;
