@@ -207,6 +207,9 @@ def main():
             prob.p2p_import(b"".join(handles))
     # ---- warm-up: W iterations (also captures the CUDA graphs)
     prob.solve(iter_limit=W + 1)
+    use_p2p = world > 1 and os.environ.get("B200PDLP_NO_P2P", "0") != "1"
+    if use_p2p:
+        prob.p2p_timeline()   # reset the device-side timeline
     # ---- timed: exactly K iterations, inputs resident in HBM
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -218,6 +221,7 @@ def main():
     wall = time.monotonic() - t0
     clocks = sampler.stop() if rank == 0 else None
     assert res["iters"] == K, (res["iters"], K)
+    timeline = prob.p2p_timeline() if use_p2p else None
     loop_ms = res["loop_device_ms"]
     if dist is not None:
         import torch
@@ -296,7 +300,7 @@ def main():
         "wall_seconds": wall, "pass_device_ms": res["iter_device_ms"],
         "phase_us": (None if world == 1 else {"primal_shard+allgather": k_us[0], "Ax+dual": k_us[1], "partial_ATy": k_us[2],
                                               "reduce_scatter+step_rule": k_us[3]}),
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "p2p_timeline_us": timeline, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
     }
     print(json.dumps(line))
 

@@ -168,7 +168,7 @@ struct b200pdlp_problem {
   // multi-GPU column sharding (world > 1): rank g owns device columns [c0, c0 + nl_real); n-vectors are
   // allocated with nl = shard_len entries (zero padded); full vectors use G segments of seg_len
   int nl = 0, nl_real = 0, c0 = 0, shard_len = 0, seg_len = 0;
-  DevBuf<double> xfull, part, red, send;
+  DevBuf<double> xfull, part, red, send, recv;
   DevBuf<int> at_outpos;           // A_g^T body row -> position in the segmented partial vector
   // fused P2P path
   bool p2p = false;
@@ -318,9 +318,10 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   p->ysum.alloc(ml); p->yavg.alloc(ml); p->axavg.alloc(ml); p->ylr.alloc(ml);
   if (world > 1) {
     p->xfull.alloc((size_t)world * p->seg_len); p->part.alloc((size_t)world * p->seg_len);
+    p->recv.alloc((size_t)world * p->seg_len);
     p->red.alloc(p->seg_len); p->send.alloc(p->seg_len);
     p->flags.alloc(4 * kMaxPeers);   // [2][kMaxPeers] epochs + [kMaxPeers][2] scalar mailbox
-    p->epochs.alloc(2); p->fault.alloc(1);
+    p->epochs.alloc(16); p->fault.alloc(1);
   }
   {
     std::vector<double> t(std::max(std::max(n, nl), ml));
@@ -380,6 +381,7 @@ static void enqueue_pass_mg(b200pdlp_problem* p) {
     launch_spmv_dual_mg(s, p->A.dev, st, p->xfull.p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->rhs.p,
                         p->ysum.p, p->neq_local, r2);
     launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->part.p, p->at_outpos.p);
+    launch_push_part(s, st, p->part.p, p->peers, p->world, p->rank, p->seg_len);
     launch_p2p_barrier(s, 1, st, r2.partials, p->A.grid(), p->peers, p->world, p->rank, p->seg_len, p->shard_len,
                        p->epochs.p, p->fault.p);
     return;
@@ -766,7 +768,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
     p->graph_main_passes = want_main;
   }
   if (!p->graph_small) { p->graph_small_passes = 4; p->graph_small = capture_passes(p, 4); }
-  p->kernels_per_pass = p->world == 1 ? 4 : (p->p2p ? 5 : 6);   // ours; NCCL kernels not counted
+  p->kernels_per_pass = p->world == 1 ? 4 : 6;   // ours; NCCL kernels not counted
 
   const double tol_p = prm.tol_primal * (1.0 + f.norm_rhs), tol_d = prm.tol_dual * (1.0 + f.norm_cost);
   RestartMemo memo;
@@ -1145,6 +1147,7 @@ int b200pdlp_bench_pass(b200pdlp_problem* p, int32_t reps, float ms[4]) {
                               p->ysum.p, p->neq_local, r2);
           CUDA_OK(cudaEventRecord(ev[2], s));
           launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->part.p, p->at_outpos.p);
+          launch_push_part(s, st, p->part.p, p->peers, p->world, p->rank, p->seg_len);
           CUDA_OK(cudaEventRecord(ev[3], s));
           launch_p2p_barrier(s, 1, st, r2.partials, p->A.grid(), p->peers, p->world, p->rank, p->seg_len, p->shard_len,
                              p->epochs.p, p->fault.p);
@@ -1233,15 +1236,32 @@ int b200pdlp_comm_init(b200pdlp_problem* p, const uint8_t id[128]) {
   });
 }
 
+int b200pdlp_p2p_timeline(b200pdlp_problem* p, double out_us[8]) {
+  return guarded([&] {
+    if (!p || !out_us || !p->p2p) throw Error(B200PDLP_ERR_ARG, "p2p_timeline needs the fused multi-GPU path");
+    set_device(p);
+    unsigned long long h[16];
+    CUDA_OK(cudaMemcpy(h, p->epochs.p, sizeof(h), cudaMemcpyDeviceToHost));
+    const double c = h[9] ? 1e-3 / (double)h[9] : 0.0;
+    // per-pass averages in us: primal-shard phase, barrier 0 total, barrier 0 wait, Ax+A'y phase, barrier 1 total,
+    // barrier 1 wait, passes counted
+    out_us[0] = h[3] * c; out_us[1] = h[4] * c; out_us[2] = h[5] * c; out_us[3] = h[6] * c; out_us[4] = h[7] * c;
+    out_us[5] = h[8] * c; out_us[6] = (double)h[9]; out_us[7] = 0.0;
+    unsigned long long z[14] = {0};
+    CUDA_OK(cudaMemcpy(p->epochs.p + 2, z, sizeof(z), cudaMemcpyHostToDevice));
+  });
+}
+
 int b200pdlp_p2p_export(b200pdlp_problem* p, uint8_t handles[B200PDLP_IPC_BYTES]) {
   return guarded([&] {
-    static_assert(3 * sizeof(cudaIpcMemHandle_t) == B200PDLP_IPC_BYTES, "IPC blob size");
+    static_assert(4 * sizeof(cudaIpcMemHandle_t) == B200PDLP_IPC_BYTES, "IPC blob size");
     if (!p || !handles || p->world < 2) throw Error(B200PDLP_ERR_ARG, "p2p_export needs a multi-GPU problem");
     set_device(p);
-    cudaIpcMemHandle_t h[3];
+    cudaIpcMemHandle_t h[4];
     CUDA_OK(cudaIpcGetMemHandle(&h[0], p->part.p));
     CUDA_OK(cudaIpcGetMemHandle(&h[1], p->xfull.p));
     CUDA_OK(cudaIpcGetMemHandle(&h[2], p->flags.p));
+    CUDA_OK(cudaIpcGetMemHandle(&h[3], p->recv.p));
     memcpy(handles, h, sizeof(h));
   });
 }
@@ -1254,16 +1274,18 @@ int b200pdlp_p2p_import(b200pdlp_problem* p, const uint8_t* all_handles) {
     for (int g = 0; g < p->world; g++) {
       if (g == p->rank) {
         p->peers.part[g] = p->part.p; p->peers.xfull[g] = p->xfull.p; p->peers.flags[g] = p->flags.p;
+        p->peers.recv[g] = p->recv.p;
         continue;
       }
-      cudaIpcMemHandle_t h[3];
+      cudaIpcMemHandle_t h[4];
       memcpy(h, all_handles + (size_t)g * B200PDLP_IPC_BYTES, sizeof(h));
-      void* q[3];
-      for (int k = 0; k < 3; k++) {
+      void* q[4];
+      for (int k = 0; k < 4; k++) {
         CUDA_OK(cudaIpcOpenMemHandle(&q[k], h[k], cudaIpcMemLazyEnablePeerAccess));
         p->ipc_opened.push_back(q[k]);
       }
       p->peers.part[g] = (double*)q[0]; p->peers.xfull[g] = (double*)q[1]; p->peers.flags[g] = (unsigned long long*)q[2];
+      p->peers.recv[g] = (double*)q[3];
     }
     p->p2p = true;
     // graphs captured for the NCCL path are stale now

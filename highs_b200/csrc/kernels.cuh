@@ -76,6 +76,7 @@ struct DevSell {
 constexpr int kMaxPeers = 16;
 struct PeerPtrs {
   double* part[kMaxPeers];                 // every rank's partial A_g^T y buffer (G segments of seg_len)
+  double* recv[kMaxPeers];                 // every rank's receive buffer: G slots (one per sender) of seg_len
   double* xfull[kMaxPeers];                // every rank's gathered trial x (G segments of seg_len)
   unsigned long long* flags[kMaxPeers];    // every rank's barrier flags [2][kMaxPeers]
 };

@@ -449,11 +449,11 @@ primal_shard_p2p_kernel(int len, PdhgState* __restrict__ st, double* __restrict_
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < npair; i += stride) {
     double2 ai;
     if (take) {
-      // reduce-scatter, fused: 128-bit loads straight from every rank's partial A_h^T y' (L1 bypassed;
-      // remote lines are not cached in the local L2), added in rank order
+      // reduce-scatter, second half: the G partial A_h^T y' segments that the peers PUSHED into my receive
+      // slots (push_part_kernel), added in rank order
       ai = make_double2(0.0, 0.0);
       for (int h = 0; h < world; h++) {
-        const double2 q = __ldcg(reinterpret_cast<const double2*>(pp.part[h] + seg) + i);
+        const double2 q = __ldcg(reinterpret_cast<const double2*>(pp.recv[rank] + (size_t)h * seg_len) + i);
         ai.x += q.x;
         ai.y += q.y;
       }
@@ -482,6 +482,21 @@ primal_shard_p2p_kernel(int len, PdhgState* __restrict__ st, double* __restrict_
   block_partials<1>(acc, rs);
 }
 
+// reduce-scatter, first half: every rank stores segment r of its partial A_g^T y' into rank r's receive
+// slot (coalesced 128-bit stores over NVLink; posted writes need no round trip)
+__global__ void __launch_bounds__(kThreads)
+push_part_kernel(PdhgState* st, const double* __restrict__ part, PeerPtrs pp, int world, int rank, int seg_len) {
+  if (st && st->iter >= st->stop_iter) return;
+  const int npair = seg_len >> 1;   // includes the scalar tail
+  const int total = npair * world;
+  const int stride = gridDim.x * kThreads;
+  for (int t = blockIdx.x * kThreads + threadIdx.x; t < total; t += stride) {
+    const int r = t / npair, i = t - r * npair;
+    const double2 v = reinterpret_cast<const double2*>(part + (size_t)r * seg_len)[i];
+    reinterpret_cast<double2*>(pp.recv[r] + (size_t)rank * seg_len)[i] = v;
+  }
+}
+
 // only the fused reduce (check iterations: make the accepted A^T y' current without a primal step)
 __global__ void __launch_bounds__(kThreads)
 reduce_part_p2p_kernel(int len, double* __restrict__ dst, PeerPtrs pp, int world, int rank, int seg_len) {
@@ -489,7 +504,7 @@ reduce_part_p2p_kernel(int len, double* __restrict__ dst, PeerPtrs pp, int world
   const int stride = gridDim.x * kThreads;
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < len; i += stride) {
     double ai = 0.0;
-    for (int h = 0; h < world; h++) ai += __ldcg(pp.part[h] + seg + i);
+    for (int h = 0; h < world; h++) ai += __ldcg(pp.recv[rank] + (size_t)h * seg_len + i);
     dst[i] = ai;
   }
 }
@@ -504,6 +519,10 @@ p2p_barrier_kernel(int mode, PdhgState* st, const double* __restrict__ partials,
   __shared__ double sm[2][kStepThreads / 32];
   __shared__ double tot[2];
   if (st->iter >= st->stop_iter) return;   // identical on every rank: nobody enters
+  // device-side timeline (epochs[2..]): [2] last exit stamp, [3+3*mode] sum(entry - previous exit) = the
+  // compute phase before this barrier, [4+3*mode] sum(time inside the barrier), [5+3*mode] sum(wait), [9] count
+  unsigned long long t_entry = 0, t_sig = 0, t_done = 0;
+  if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_entry));
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nv = mode == 0 ? 1 : 2;
   for (int a = 0; a < nv; a++) {
@@ -540,6 +559,7 @@ p2p_barrier_kernel(int mode, PdhgState* st, const double* __restrict__ partials,
       const unsigned long long* mine = pp.flags[rank] + mode * kMaxPeers + lane;
       unsigned long long* theirs = pp.flags[lane] + mode * kMaxPeers + rank;
       asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(e) : "memory");
+      if (lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_sig));
       long long spins = 0;
       unsigned long long seen = 0;
       do {
@@ -548,6 +568,7 @@ p2p_barrier_kernel(int mode, PdhgState* st, const double* __restrict__ partials,
       } while (seen < e);
     }
     __syncwarp();
+    if (lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_done));
     if (mode == 1 && lane == 0) {
       const double* mb = reinterpret_cast<const double*>(pp.flags[rank] + 2 * kMaxPeers);
       double dx2 = 0.0, dy2 = 0.0, inter = 0.0;
@@ -561,6 +582,15 @@ p2p_barrier_kernel(int mode, PdhgState* st, const double* __restrict__ partials,
       const int it0 = st->iter;
       step_rule(st, inter);
       st->accepted_last = st->iter != it0;
+    }
+    if (lane == 0) {
+      unsigned long long t_exit;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_exit));
+      if (epochs[2]) epochs[3 + 3 * mode] += t_entry - epochs[2];
+      epochs[4 + 3 * mode] += t_exit - t_entry;
+      epochs[5 + 3 * mode] += t_done - t_sig;
+      epochs[2] = t_exit;
+      if (mode == 1) epochs[9] += 1;
     }
   }
 }
@@ -885,6 +915,9 @@ void launch_primal_shard_p2p(cudaStream_t s, int len, PdhgState* st, double* xs0
                              const double* up, double* xsum, ReduceScratch rs) {
   primal_shard_p2p_kernel<<<ew_grid((len + 1) / 2), kThreads, 0, s>>>(len, st, xs0, xs1, aty_s, pp, world, rank, seg_len, c, lo,
                                                             up, xsum, rs);
+}
+void launch_push_part(cudaStream_t s, PdhgState* st, const double* part, const PeerPtrs& pp, int world, int rank, int seg_len) {
+  push_part_kernel<<<ew_grid((seg_len / 2) * world), kThreads, 0, s>>>(st, part, pp, world, rank, seg_len);
 }
 void launch_reduce_part_p2p(cudaStream_t s, int len, double* dst, const PeerPtrs& pp, int world, int rank, int seg_len) {
   reduce_part_p2p_kernel<<<ew_grid(len), kThreads, 0, s>>>(len, dst, pp, world, rank, seg_len);

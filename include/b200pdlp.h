@@ -171,9 +171,12 @@ int b200pdlp_comm_init(b200pdlp_problem* p, const uint8_t id[128]);
  * buffers (B200PDLP_IPC_BYTES bytes), the host application all-gathers them (rank order) and every rank
  * imports the world x B200PDLP_IPC_BYTES blob.  From then on the per-iteration reduce-scatter and
  * all-gather run inside the engine's own kernels over peer memory; NCCL is used at check iterations only. */
-#define B200PDLP_IPC_BYTES 192
+#define B200PDLP_IPC_BYTES 256
 int b200pdlp_p2p_export(b200pdlp_problem* p, uint8_t handles[B200PDLP_IPC_BYTES]);
 int b200pdlp_p2p_import(b200pdlp_problem* p, const uint8_t* all_handles);
+/* device-side timeline of the fused path since the last call, per-pass averages in us: [0] primal-shard phase,
+ * [1] barrier 0 total, [2] of which waiting, [3] A x + A'y phase, [4] barrier 1 total, [5] of which waiting, [6] passes */
+int b200pdlp_p2p_timeline(b200pdlp_problem* p, double out_us[8]);
 
 /* ---- host-only view of the standard form (no GPU needed; parity tests) -------
  * formulate (CupdlpWrapper.cpp:280-448) + scale (cupdlp_scaling.c:233-425) only. */
