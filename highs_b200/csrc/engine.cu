@@ -172,6 +172,7 @@ struct b200pdlp_problem {
   DevBuf<int> at_outpos;           // A_g^T body row -> position in the segmented partial vector
   // fused P2P path
   bool p2p = false;
+  int p2p_pull = 0;                // 1: the primal kernel reads the peers' partials over NVLink; 0: peers push them
   PeerPtrs peers{};
   std::vector<void*> ipc_opened;
   DevBuf<unsigned long long> flags, epochs;
@@ -375,13 +376,13 @@ static void enqueue_pass_mg(b200pdlp_problem* p) {
   if (p->p2p) {
     // fused compute + collective over NVLink peer memory (5 launches, no NCCL)
     launch_primal_shard_p2p(s, p->nl, st, p->x[0].p, p->x[1].p, p->aty[0].p, p->peers, p->world, p->rank, p->seg_len,
-                            p->cost.p, p->lower.p, p->upper.p, p->xsum.p, r1);
+                            p->p2p_pull, p->cost.p, p->lower.p, p->upper.p, p->xsum.p, r1);
     launch_p2p_barrier(s, 0, st, r1.partials, primal_shard_p2p_grid(p->nl), p->peers, p->world, p->rank, p->seg_len,
                        p->shard_len, p->epochs.p, p->fault.p);
     launch_spmv_dual_mg(s, p->A.dev, st, p->xfull.p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->rhs.p,
                         p->ysum.p, p->neq_local, r2);
     launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->part.p, p->at_outpos.p);
-    launch_push_part(s, st, p->part.p, p->peers, p->world, p->rank, p->seg_len);
+    if (!p->p2p_pull) launch_push_part(s, st, p->part.p, p->peers, p->world, p->rank, p->seg_len);
     launch_p2p_barrier(s, 1, st, r2.partials, p->A.grid(), p->peers, p->world, p->rank, p->seg_len, p->shard_len,
                        p->epochs.p, p->fault.p);
     return;
@@ -468,7 +469,7 @@ static CheckResult run_check(b200pdlp_problem* p, bool timed_out_local) {
   const double scale = h->sum_step > 0.0 ? 1.0 / h->sum_step : 1.0;
   if (p->world > 1 && h->accepted_last) {
     // the last accepted pass left its A^T y' un-reduced (P2P) / in the reduce-scatter buffer (NCCL): make it current
-    if (p->p2p) { launch_reduce_part_p2p(s, n, p->aty[0].p, p->peers, p->world, p->rank, p->seg_len); p->launches++; }
+    if (p->p2p) { launch_reduce_part_p2p(s, n, p->aty[0].p, p->peers, p->world, p->rank, p->seg_len, p->p2p_pull); p->launches++; }
     else CUDA_OK(cudaMemcpyAsync(p->aty[0].p, p->red.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
     h->accepted_last = 0;
     push_state(p);
@@ -864,7 +865,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   const double* dy = use_avg ? p->yavg.p : p->y[cur].p;
   const double* dax = use_avg ? p->axavg.p : p->ax[cur].p;
   if (p->world > 1 && h->accepted_last && !use_avg) {   // (only when the loop never ran a check, e.g. iter_limit <= 0)
-    if (p->p2p) launch_reduce_part_p2p(s, nl, p->aty[0].p, p->peers, p->world, p->rank, p->seg_len);
+    if (p->p2p) launch_reduce_part_p2p(s, nl, p->aty[0].p, p->peers, p->world, p->rank, p->seg_len, p->p2p_pull);
     else CUDA_OK(cudaMemcpyAsync(p->aty[0].p, p->red.p, (size_t)nl * sizeof(double), cudaMemcpyDeviceToDevice, s));
   }
   if (p->p2p) {
@@ -1139,7 +1140,7 @@ int b200pdlp_bench_pass(b200pdlp_problem* p, int32_t reps, float ms[4]) {
         if (p->p2p) {
           CUDA_OK(cudaEventRecord(ev[0], s));
           launch_primal_shard_p2p(s, p->nl, st, p->x[0].p, p->x[1].p, p->aty[0].p, p->peers, p->world, p->rank,
-                                  p->seg_len, p->cost.p, p->lower.p, p->upper.p, p->xsum.p, r1);
+                                  p->seg_len, p->p2p_pull, p->cost.p, p->lower.p, p->upper.p, p->xsum.p, r1);
           launch_p2p_barrier(s, 0, st, r1.partials, primal_shard_p2p_grid(p->nl), p->peers, p->world, p->rank, p->seg_len,
                              p->shard_len, p->epochs.p, p->fault.p);
           CUDA_OK(cudaEventRecord(ev[1], s));
@@ -1147,7 +1148,7 @@ int b200pdlp_bench_pass(b200pdlp_problem* p, int32_t reps, float ms[4]) {
                               p->ysum.p, p->neq_local, r2);
           CUDA_OK(cudaEventRecord(ev[2], s));
           launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->part.p, p->at_outpos.p);
-          launch_push_part(s, st, p->part.p, p->peers, p->world, p->rank, p->seg_len);
+          if (!p->p2p_pull) launch_push_part(s, st, p->part.p, p->peers, p->world, p->rank, p->seg_len);
           CUDA_OK(cudaEventRecord(ev[3], s));
           launch_p2p_barrier(s, 1, st, r2.partials, p->A.grid(), p->peers, p->world, p->rank, p->seg_len, p->shard_len,
                              p->epochs.p, p->fault.p);
@@ -1288,6 +1289,7 @@ int b200pdlp_p2p_import(b200pdlp_problem* p, const uint8_t* all_handles) {
       p->peers.recv[g] = (double*)q[3];
     }
     p->p2p = true;
+    if (const char* e = getenv("B200PDLP_P2P_PULL")) p->p2p_pull = atoi(e);
     // graphs captured for the NCCL path are stale now
     if (p->graph_main) { cudaGraphExecDestroy(p->graph_main); p->graph_main = nullptr; }
     if (p->graph_small) { cudaGraphExecDestroy(p->graph_small); p->graph_small = nullptr; }

@@ -423,7 +423,7 @@ __device__ __forceinline__ double ld_sys(const double* p) {
 
 __global__ void __launch_bounds__(kThreads)
 primal_shard_p2p_kernel(int len, PdhgState* __restrict__ st, double* __restrict__ xs0, double* __restrict__ xs1,
-                        double* __restrict__ aty_s, PeerPtrs pp, int world, int rank, int seg_len,
+                        double* __restrict__ aty_s, PeerPtrs pp, int world, int rank, int seg_len, int pull,
                         const double* __restrict__ c, const double* __restrict__ lo, const double* __restrict__ up,
                         double* __restrict__ xsum, ReduceScratch rs) {
   if (st->iter >= st->stop_iter) return;
@@ -451,9 +451,11 @@ primal_shard_p2p_kernel(int len, PdhgState* __restrict__ st, double* __restrict_
     if (take) {
       // reduce-scatter, second half: the G partial A_h^T y' segments that the peers PUSHED into my receive
       // slots (push_part_kernel), added in rank order
+      // (pull variant: read the peers' `part` segments over NVLink instead)
       ai = make_double2(0.0, 0.0);
       for (int h = 0; h < world; h++) {
-        const double2 q = __ldcg(reinterpret_cast<const double2*>(pp.recv[rank] + (size_t)h * seg_len) + i);
+        const double* src = pull ? pp.part[h] + seg : pp.recv[rank] + (size_t)h * seg_len;
+        const double2 q = __ldcg(reinterpret_cast<const double2*>(src) + i);
         ai.x += q.x;
         ai.y += q.y;
       }
@@ -499,12 +501,12 @@ push_part_kernel(PdhgState* st, const double* __restrict__ part, PeerPtrs pp, in
 
 // only the fused reduce (check iterations: make the accepted A^T y' current without a primal step)
 __global__ void __launch_bounds__(kThreads)
-reduce_part_p2p_kernel(int len, double* __restrict__ dst, PeerPtrs pp, int world, int rank, int seg_len) {
+reduce_part_p2p_kernel(int len, double* __restrict__ dst, PeerPtrs pp, int world, int rank, int seg_len, int pull) {
   const size_t seg = (size_t)rank * seg_len;
   const int stride = gridDim.x * kThreads;
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < len; i += stride) {
     double ai = 0.0;
-    for (int h = 0; h < world; h++) ai += __ldcg(pp.recv[rank] + (size_t)h * seg_len + i);
+    for (int h = 0; h < world; h++) ai += __ldcg(pull ? pp.part[h] + seg + i : pp.recv[rank] + (size_t)h * seg_len + i);
     dst[i] = ai;
   }
 }
@@ -911,16 +913,17 @@ void launch_stash_scalars(cudaStream_t s, int nv, PdhgState* st, const double* p
 }
 
 void launch_primal_shard_p2p(cudaStream_t s, int len, PdhgState* st, double* xs0, double* xs1, double* aty_s,
-                             const PeerPtrs& pp, int world, int rank, int seg_len, const double* c, const double* lo,
-                             const double* up, double* xsum, ReduceScratch rs) {
-  primal_shard_p2p_kernel<<<ew_grid((len + 1) / 2), kThreads, 0, s>>>(len, st, xs0, xs1, aty_s, pp, world, rank, seg_len, c, lo,
-                                                            up, xsum, rs);
+                             const PeerPtrs& pp, int world, int rank, int seg_len, int pull, const double* c,
+                             const double* lo, const double* up, double* xsum, ReduceScratch rs) {
+  primal_shard_p2p_kernel<<<ew_grid((len + 1) / 2), kThreads, 0, s>>>(len, st, xs0, xs1, aty_s, pp, world, rank, seg_len,
+                                                                      pull, c, lo, up, xsum, rs);
 }
 void launch_push_part(cudaStream_t s, PdhgState* st, const double* part, const PeerPtrs& pp, int world, int rank, int seg_len) {
   push_part_kernel<<<ew_grid((seg_len / 2) * world), kThreads, 0, s>>>(st, part, pp, world, rank, seg_len);
 }
-void launch_reduce_part_p2p(cudaStream_t s, int len, double* dst, const PeerPtrs& pp, int world, int rank, int seg_len) {
-  reduce_part_p2p_kernel<<<ew_grid(len), kThreads, 0, s>>>(len, dst, pp, world, rank, seg_len);
+void launch_reduce_part_p2p(cudaStream_t s, int len, double* dst, const PeerPtrs& pp, int world, int rank, int seg_len,
+                            int pull) {
+  reduce_part_p2p_kernel<<<ew_grid(len), kThreads, 0, s>>>(len, dst, pp, world, rank, seg_len, pull);
 }
 void launch_p2p_barrier(cudaStream_t s, int mode, PdhgState* st, const double* partials, int nb, const PeerPtrs& pp,
                         int world, int rank, int seg_len, int shard_len, unsigned long long* epochs, int* fault) {

@@ -28,10 +28,11 @@ int primal_shard_p2p_grid(int len);
 void launch_stash_scalars(cudaStream_t s, int nv, PdhgState* st, const double* partials, int nb, double* dst, int copies,
                           int stride);
 void launch_primal_shard_p2p(cudaStream_t s, int len, PdhgState* st, double* xs0, double* xs1, double* aty_s,
-                             const PeerPtrs& pp, int world, int rank, int seg_len, const double* c, const double* lo,
-                             const double* up, double* xsum, ReduceScratch rs);
+                             const PeerPtrs& pp, int world, int rank, int seg_len, int pull, const double* c,
+                             const double* lo, const double* up, double* xsum, ReduceScratch rs);
 void launch_push_part(cudaStream_t s, PdhgState* st, const double* part, const PeerPtrs& pp, int world, int rank, int seg_len);
-void launch_reduce_part_p2p(cudaStream_t s, int len, double* dst, const PeerPtrs& pp, int world, int rank, int seg_len);
+void launch_reduce_part_p2p(cudaStream_t s, int len, double* dst, const PeerPtrs& pp, int world, int rank, int seg_len,
+                            int pull);
 void launch_p2p_barrier(cudaStream_t s, int mode, PdhgState* st, const double* partials, int nb, const PeerPtrs& pp,
                         int world, int rank, int seg_len, int shard_len, unsigned long long* epochs, int* fault);
 void launch_step_rule_mg(cudaStream_t s, PdhgState* st, const double* xfull, int world, int seg_len, int shard_len,
