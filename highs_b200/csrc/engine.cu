@@ -340,7 +340,7 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   }
   p->redbuf.alloc((size_t)std::max(n, p->m) + 16);
   size_t maxgrid = std::max<size_t>(kMaxEwBlocks, std::max(p->A.grid(), p->AT.grid()));
-  p->scratch_stride = 16 * maxgrid;
+  p->scratch_stride = 24 * maxgrid;
   p->partials.alloc(p->scratch_stride * kNumSlots);
   p->counters.alloc(kNumSlots);
   p->ordered_cap = p->ordered ? std::max(std::max(p->n, p->m), 1) : 0;
@@ -483,6 +483,40 @@ static CheckResult run_check(b200pdlp_problem* p, bool timed_out_local) {
   ColIter c0{p->x[cur].p, p->aty[acur].p}, c1{p->xavg.p, p->atyavg.p};
   RowIter r0{p->y[cur].p, p->ax[cur].p}, r1{p->yavg.p, p->axavg.p};
   double* o = p->outs.p;
+  if (!p->ordered) {
+    // tree mode: one fused sweep per side, one read-back, one all-reduce (see col_check_fused_kernel)
+    launch_col_check_fused(s, n, c0, c1, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, p->rs(kSlotChk, n), o);
+    launch_row_check_fused(s, ml, r0, r1, p->rhs.p, p->rowscale.p, p->neq_local, p->rs(kSlotChk, ml), o + 20);
+    p->launches += 2;
+    if (p->world > 1) {
+      double flag = timed_out_local ? 1.0 : 0.0;
+      CUDA_OK(cudaMemcpyAsync(o + 28, &flag, sizeof(double), cudaMemcpyHostToDevice, s));
+      allreduce_inplace(p, o, 29);
+    }
+    pull_outs(p, 29);
+    CheckResult cr;
+    cr.timed_out = p->world > 1 ? p->houts[28] > 0.0 : timed_out_local;
+    for (int t = 0; t < 2; t++) {
+      const double* a = p->houts + 10 * t;
+      const double* r = p->houts + 20 + 4 * t;
+      Residuals& R = cr.it[t];
+      R.pobj = a[0] * f.sense + f.offset;
+      R.pfeas = std::sqrt(r[1]);
+      R.dobj = ((r[0] + a[1]) - a[2]) * f.sense + f.offset;
+      R.dfeas = std::sqrt(a[3]);
+      R.gap = R.pobj - R.dobj;
+      R.relgap = std::fabs(R.pobj - R.dobj) / (1.0 + std::fabs(R.pobj) + std::fabs(R.dobj));
+      double dscale = std::sqrt(r[2] + a[4] + a[5]);
+      if (dscale < 1e-8) dscale = 1.0;
+      double pscale = std::sqrt(a[6]);
+      if (pscale < 1e-8) pscale = 1.0;
+      R.pinf_obj = (R.dobj - f.offset) / f.sense / dscale;
+      R.pinf_res = std::sqrt(a[7]) / dscale;
+      R.dinf_obj = (R.pobj - f.offset) / f.sense / pscale;
+      R.dinf_res = std::sqrt(r[3] + a[8] + a[9]) / pscale;
+    }
+    return cr;
+  }
   launch_col_check_a(s, n, 2, c0, c1, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, p->rs(kSlotChk, n), o);
   launch_row_check_a(s, ml, 2, r0, r1, p->rhs.p, p->rowscale.p, p->neq_local, 0, p->rs(kSlotChk, ml), o + 14);
   p->launches += 2;

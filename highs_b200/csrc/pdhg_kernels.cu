@@ -696,6 +696,76 @@ col_check_a_kernel(int n, int nit, ColIter it0, ColIter it1, const double* __res
     for (int a = 0; a < 14; a++) out[a] = res[a];
 }
 
+// Tree-mode (large problems) single-sweep variants: the ray residuals are homogeneous in the ray scale,
+//   |(aty/s + sp/s - sn/s) colScale| = |(aty + sp - sn) colScale| / s,   likewise for the primal ray,
+// so they are accumulated UNSCALED in the same sweep and divided by the scale on the host: one sweep, one
+// read-back (and one all-reduce on several GPUs) per check instead of two.  Not bit-identical to the
+// reference's scale-then-square order, which is why ordered mode keeps the two-sweep kernels above/below.
+// out per iterate (10): 0..6 as col_check_a, 7 |(aty+sp-sn) colScale|^2, 8 |min(x,0) hasLower / colScale|^2,
+// 9 |max(x,0) hasUpper / colScale|^2
+__global__ void __launch_bounds__(kThreads)
+col_check_fused_kernel(int n, ColIter it0, ColIter it1, const double* __restrict__ c, const double* __restrict__ lo,
+                       const double* __restrict__ up, const double* __restrict__ cs, ReduceScratch rs,
+                       double* __restrict__ out) {
+  double acc[20];
+#pragma unroll
+  for (int a = 0; a < 20; a++) acc[a] = 0.0;
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const double ci = c[i], l = lo[i], u = up[i], sc = cs[i];
+    const bool hl = l > -INFINITY, hu = u < INFINITY;
+    const double lf = hl ? l : 0.0, uf = hu ? u : 0.0;
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      const ColIter& it = t ? it1 : it0;
+      const double x = it.x[i], aty = it.aty[i];
+      const double rc = ci - aty;
+      const double sp = hl ? (rc > 0.0 ? rc : 0.0) : 0.0;
+      const double sn = hu ? (rc < 0.0 ? -rc : 0.0) : 0.0;
+      const double rr = (rc - sp + sn) * sc;
+      const double k = (aty + sp - sn) * sc;
+      const double bl = hl ? (x < 0.0 ? x : 0.0) / sc : 0.0;
+      const double bu = hu ? (x > 0.0 ? x : 0.0) / sc : 0.0;
+      double* a = acc + 10 * t;
+      a[0] += x * ci; a[1] += sp * lf; a[2] += sn * uf; a[3] += rr * rr; a[4] += sp * sp; a[5] += sn * sn;
+      a[6] += x * x; a[7] += k * k; a[8] += bl * bl; a[9] += bu * bu;
+    }
+  }
+  double res[20];
+  if (grid_reduce<20>(acc, rs, res) && threadIdx.x == 0)
+    for (int a = 0; a < 20; a++) out[a] = res[a];
+}
+
+// out per iterate (4): 0 y.b, 1 |primal residual|^2, 2 |y|^2, 3 |[ax]_eq, min([ax]_ineq,0) rowScale|^2
+__global__ void __launch_bounds__(kThreads)
+row_check_fused_kernel(int m, RowIter it0, RowIter it1, const double* __restrict__ b, const double* __restrict__ rsca,
+                       int neq, ReduceScratch rs, double* __restrict__ out) {
+  double acc[8];
+#pragma unroll
+  for (int a = 0; a < 8; a++) acc[a] = 0.0;
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < m; i += stride) {
+    const double bi = b[i], sc = rsca[i];
+    const bool ineq = i >= neq;
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      const RowIter& it = t ? it1 : it0;
+      const double y = it.y[i], ax = it.ax[i];
+      double r = ax - bi;
+      if (ineq) r = r < 0.0 ? r : 0.0;
+      r = r * sc;
+      double k = ax;
+      if (ineq) k = k < 0.0 ? k : 0.0;
+      k = k * sc;
+      double* a = acc + 4 * t;
+      a[0] += y * bi; a[1] += r * r; a[2] += y * y; a[3] += k * k;
+    }
+  }
+  double res[8];
+  if (grid_reduce<8>(acc, rs, res) && threadIdx.x == 0)
+    for (int a = 0; a < 8; a++) out[a] = res[a];
+}
+
 // row-side pass A: out per iterate: 0 y.b, 1 |primal residual|^2, 2 |y|^2
 // (cupdlp_solver.c:36-63 for the residual, :79 for y.b)
 __global__ void __launch_bounds__(kThreads)
@@ -952,6 +1022,14 @@ void launch_average(cudaStream_t s, int len, const double* v, double* sum, doubl
 void launch_col_check_a(cudaStream_t s, int n, int nit, ColIter a, ColIter b, const double* c, const double* lo,
                         const double* up, const double* cs, ReduceScratch rs, double* out) {
   col_check_a_kernel<<<ew_grid(n), kThreads, 0, s>>>(n, nit, a, b, c, lo, up, cs, rs, out);
+}
+void launch_col_check_fused(cudaStream_t s, int n, ColIter a, ColIter b, const double* c, const double* lo,
+                            const double* up, const double* cs, ReduceScratch rs, double* out) {
+  col_check_fused_kernel<<<ew_grid(n), kThreads, 0, s>>>(n, a, b, c, lo, up, cs, rs, out);
+}
+void launch_row_check_fused(cudaStream_t s, int m, RowIter a, RowIter b, const double* rhs, const double* rsca, int neq,
+                            ReduceScratch rs, double* out) {
+  row_check_fused_kernel<<<ew_grid(m), kThreads, 0, s>>>(m, a, b, rhs, rsca, neq, rs, out);
 }
 void launch_row_check_a(cudaStream_t s, int m, int nit, RowIter a, RowIter b, const double* rhs,
                         const double* rsca, int neq, int row_offset, ReduceScratch rs, double* out) {

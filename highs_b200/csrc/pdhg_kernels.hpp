@@ -44,6 +44,10 @@ void launch_average(cudaStream_t s, int len, const double* v, double* sum, doubl
                     double scale);
 void launch_col_check_a(cudaStream_t s, int n, int nit, ColIter a, ColIter b, const double* c, const double* lo,
                         const double* up, const double* cs, ReduceScratch rs, double* out);
+void launch_col_check_fused(cudaStream_t s, int n, ColIter a, ColIter b, const double* c, const double* lo,
+                            const double* up, const double* cs, ReduceScratch rs, double* out);
+void launch_row_check_fused(cudaStream_t s, int m, RowIter a, RowIter b, const double* rhs, const double* rsca, int neq,
+                            ReduceScratch rs, double* out);
 void launch_row_check_a(cudaStream_t s, int m, int nit, RowIter a, RowIter b, const double* rhs,
                         const double* rsca, int neq, int row_offset, ReduceScratch rs, double* out);
 void launch_col_check_b(cudaStream_t s, int n, int nit, ColIter a, ColIter b, const double inv_d[2],
