@@ -248,6 +248,13 @@ static inline size_t seg_pos(const b200pdlp_problem* p, int j) {
   return p->world == 1 ? (size_t)j : (size_t)(j / p->shard_len) * p->seg_len + (size_t)(j % p->shard_len);
 }
 
+// sum over ranks of k (<= 32) doubles at dptr, in place
+static void allreduce_small(b200pdlp_problem* p, double* dptr, int k) {
+  if (p->world <= 1) return;
+  if (p->p2p) { launch_p2p_exchange(p->stream, dptr, k, p->peers, p->world, p->rank, p->epochs.p, p->fault.p); p->launches++; }
+  else allreduce_inplace(p, dptr, (size_t)k);
+}
+
 static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, int rank, int world, b200pdlp_problem* p) {
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -321,7 +328,7 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
     p->xfull.alloc((size_t)world * p->seg_len); p->part.alloc((size_t)world * p->seg_len);
     p->recv.alloc((size_t)world * p->seg_len);
     p->red.alloc(p->seg_len); p->send.alloc(p->seg_len);
-    p->flags.alloc(4 * kMaxPeers);   // [2][kMaxPeers] epochs + [kMaxPeers][2] scalar mailbox
+    p->flags.alloc(5 * kMaxPeers + 2 * kMaxPeers * 32);   // [3][16] flags, [16][2] pass mailbox, [2][16][32] check mailbox
     p->epochs.alloc(16); p->fault.alloc(1);
   }
   {
@@ -440,8 +447,17 @@ static void full_aty(b200pdlp_problem* p, const double* y, double* aty) {
   } else {
     launch_spmv_partial_aty(p->stream, p->AT.dev, nullptr, y, y, p->part.p, p->at_outpos.p);
     p->launches++;
-    reduce_scatter_part(p);
-    CUDA_OK(cudaMemcpyAsync(aty, p->red.p, (size_t)p->nl * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    if (p->p2p) {
+      if (!p->p2p_pull) launch_push_part(p->stream, nullptr, p->part.p, p->peers, p->world, p->rank, p->seg_len);
+      launch_p2p_exchange(p->stream, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p);
+      launch_reduce_part_p2p(p->stream, p->nl, aty, p->peers, p->world, p->rank, p->seg_len, p->p2p_pull);
+      // (in pull mode the peers' `part` buffers must stay untouched until everybody has read them)
+      if (p->p2p_pull) launch_p2p_exchange(p->stream, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p);
+      p->launches += 3;
+    } else {
+      reduce_scatter_part(p);
+      CUDA_OK(cudaMemcpyAsync(aty, p->red.p, (size_t)p->nl * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    }
   }
 }
 // ax (my rows) = A_g x, x given as my column shard   [world == 1: the whole vector]
@@ -449,8 +465,14 @@ static void full_ax(b200pdlp_problem* p, const double* x, double* ax) {
   if (p->world == 1) {
     launch_spmv_plain(p->stream, p->A.dev, x, ax);
   } else {
-    CUDA_OK(cudaMemcpyAsync(p->send.p, x, (size_t)p->nl * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
-    gather_shards(p);
+    if (p->p2p) {
+      launch_push_shard(p->stream, x, p->nl, p->peers, p->world, p->rank, p->seg_len);
+      launch_p2p_exchange(p->stream, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p);
+      p->launches += 2;
+    } else {
+      CUDA_OK(cudaMemcpyAsync(p->send.p, x, (size_t)p->nl * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+      gather_shards(p);
+    }
     launch_spmv_plain(p->stream, p->A.dev, p->xfull.p, ax);
   }
   p->launches++;
@@ -469,7 +491,12 @@ static CheckResult run_check(b200pdlp_problem* p, bool timed_out_local) {
   const double scale = h->sum_step > 0.0 ? 1.0 / h->sum_step : 1.0;
   if (p->world > 1 && h->accepted_last) {
     // the last accepted pass left its A^T y' un-reduced (P2P) / in the reduce-scatter buffer (NCCL): make it current
-    if (p->p2p) { launch_reduce_part_p2p(s, n, p->aty[0].p, p->peers, p->world, p->rank, p->seg_len, p->p2p_pull); p->launches++; }
+    if (p->p2p) {
+      launch_reduce_part_p2p(s, n, p->aty[0].p, p->peers, p->world, p->rank, p->seg_len, p->p2p_pull);
+      // nobody may overwrite recv slots / part buffers (check-time A^T ybar) before every rank has consumed them
+      launch_p2p_exchange(s, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p);
+      p->launches += 2;
+    }
     else CUDA_OK(cudaMemcpyAsync(p->aty[0].p, p->red.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
     h->accepted_last = 0;
     push_state(p);
@@ -491,7 +518,7 @@ static CheckResult run_check(b200pdlp_problem* p, bool timed_out_local) {
     if (p->world > 1) {
       double flag = timed_out_local ? 1.0 : 0.0;
       CUDA_OK(cudaMemcpyAsync(o + 28, &flag, sizeof(double), cudaMemcpyHostToDevice, s));
-      allreduce_inplace(p, o, 29);
+      allreduce_small(p, o, 29);
     }
     pull_outs(p, 29);
     CheckResult cr;
@@ -621,7 +648,7 @@ static void do_restart(b200pdlp_problem* p, int choice, const CheckResult& c, Re
   launch_diff_norm2(s, n, p->x[cur].p, p->xlr.p, p->rs(kSlotChk, n), o);
   launch_diff_norm2(s, ml, p->y[cur].p, p->ylr.p, p->rs(kSlotChk, ml), o + 1);
   p->launches += 2;
-  if (p->world > 1) allreduce_inplace(p, o, 2);
+  if (p->world > 1) allreduce_small(p, o, 2);
   CUDA_OK(cudaMemcpyAsync(p->houts + 40, o, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CUDA_OK(cudaMemcpyAsync(p->xlr.p, p->x[cur].p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
   CUDA_OK(cudaMemcpyAsync(p->ylr.p, p->y[cur].p, (size_t)ml * sizeof(double), cudaMemcpyDeviceToDevice, s));
@@ -1282,7 +1309,7 @@ int b200pdlp_p2p_timeline(b200pdlp_problem* p, double out_us[8]) {
     // barrier 1 wait, passes counted
     out_us[0] = h[3] * c; out_us[1] = h[4] * c; out_us[2] = h[5] * c; out_us[3] = h[6] * c; out_us[4] = h[7] * c;
     out_us[5] = h[8] * c; out_us[6] = (double)h[9]; out_us[7] = 0.0;
-    unsigned long long z[14] = {0};
+    unsigned long long z[8] = {0};   // [2..9] only: [0],[1],[10] are live barrier epochs
     CUDA_OK(cudaMemcpy(p->epochs.p + 2, z, sizeof(z), cudaMemcpyHostToDevice));
   });
 }

@@ -499,6 +499,52 @@ push_part_kernel(PdhgState* st, const double* __restrict__ part, PeerPtrs pp, in
   }
 }
 
+// check-iteration collectives of the fused path ------------------------------------------------------
+// all-gather of a column shard: store it into every peer's xfull segment
+__global__ void __launch_bounds__(kThreads)
+push_shard_kernel(const double* __restrict__ src, int len, PeerPtrs pp, int world, int rank, int seg_len) {
+  const size_t seg = (size_t)rank * seg_len;
+  const int npair = len >> 1;
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < npair; i += stride) {
+    const double2 v = reinterpret_cast<const double2*>(src)[i];
+    for (int h = 0; h < world; h++) reinterpret_cast<double2*>(pp.xfull[h] + seg)[i] = v;
+  }
+}
+
+// barrier + all-reduce of k <= 32 scalars (k = 0: pure barrier): every rank writes its values into every
+// peer's mailbox (double-buffered by epoch parity), signals, waits, then adds all ranks' values in rank order
+constexpr int kBigBox = 32;
+__global__ void p2p_exchange_kernel(double* vals, int k, PeerPtrs pp, int world, int rank, unsigned long long* epochs,
+                                    int* fault) {
+  const int lane = threadIdx.x;
+  unsigned long long e = 0;
+  if (lane == 0) { e = epochs[10] + 1; epochs[10] = e; }
+  e = __shfl_sync(0xffffffffu, e, 0);
+  const size_t box = 3 * kMaxPeers + 2 * kMaxPeers + (size_t)(e & 1) * kMaxPeers * kBigBox;
+  if (lane < world)
+    for (int j = 0; j < k; j++) reinterpret_cast<double*>(pp.flags[lane] + box)[rank * kBigBox + j] = vals[j];
+  __threadfence_system();
+  if (lane < world) {
+    const unsigned long long* mine = pp.flags[rank] + 2 * kMaxPeers + lane;
+    unsigned long long* theirs = pp.flags[lane] + 2 * kMaxPeers + rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(e) : "memory");
+    long long spins = 0;
+    unsigned long long seen = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+      if (++spins > (1LL << 31)) { *fault = 1; break; }
+    } while (seen < e);
+  }
+  __syncwarp();
+  if (lane < k) {
+    const double* mb = reinterpret_cast<const double*>(pp.flags[rank] + box);
+    double s = 0.0;
+    for (int g = 0; g < world; g++) s += ld_sys(mb + g * kBigBox + lane);
+    vals[lane] = s;
+  }
+}
+
 // only the fused reduce (check iterations: make the accepted A^T y' current without a primal step)
 __global__ void __launch_bounds__(kThreads)
 reduce_part_p2p_kernel(int len, double* __restrict__ dst, PeerPtrs pp, int world, int rank, int seg_len, int pull) {
@@ -548,7 +594,7 @@ p2p_barrier_kernel(int mode, PdhgState* st, const double* __restrict__ partials,
       if (lane < world) pp.xfull[lane][tail] = tot[0];
     } else {
       if (lane < world) {
-        double* mb = reinterpret_cast<double*>(pp.flags[lane] + 2 * kMaxPeers) + 2 * rank;   // peer's mailbox slot of this rank
+        double* mb = reinterpret_cast<double*>(pp.flags[lane] + 3 * kMaxPeers) + 2 * rank;   // peer's mailbox slot of this rank
         mb[0] = tot[0];
         mb[1] = tot[1];
       }
@@ -572,7 +618,7 @@ p2p_barrier_kernel(int mode, PdhgState* st, const double* __restrict__ partials,
     __syncwarp();
     if (lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_done));
     if (mode == 1 && lane == 0) {
-      const double* mb = reinterpret_cast<const double*>(pp.flags[rank] + 2 * kMaxPeers);
+      const double* mb = reinterpret_cast<const double*>(pp.flags[rank] + 3 * kMaxPeers);
       double dx2 = 0.0, dy2 = 0.0, inter = 0.0;
       for (int g = 0; g < world; g++) {   // local memory, fixed rank order
         dx2 += ld_sys(pp.xfull[rank] + (size_t)g * seg_len + shard_len);
@@ -990,6 +1036,13 @@ void launch_primal_shard_p2p(cudaStream_t s, int len, PdhgState* st, double* xs0
 }
 void launch_push_part(cudaStream_t s, PdhgState* st, const double* part, const PeerPtrs& pp, int world, int rank, int seg_len) {
   push_part_kernel<<<ew_grid((seg_len / 2) * world), kThreads, 0, s>>>(st, part, pp, world, rank, seg_len);
+}
+void launch_push_shard(cudaStream_t s, const double* src, int len, const PeerPtrs& pp, int world, int rank, int seg_len) {
+  push_shard_kernel<<<ew_grid((len + 1) / 2), kThreads, 0, s>>>(src, len, pp, world, rank, seg_len);
+}
+void launch_p2p_exchange(cudaStream_t s, double* vals, int k, const PeerPtrs& pp, int world, int rank,
+                         unsigned long long* epochs, int* fault) {
+  p2p_exchange_kernel<<<1, 32, 0, s>>>(vals, k, pp, world, rank, epochs, fault);
 }
 void launch_reduce_part_p2p(cudaStream_t s, int len, double* dst, const PeerPtrs& pp, int world, int rank, int seg_len,
                             int pull) {

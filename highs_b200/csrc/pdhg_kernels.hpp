@@ -30,6 +30,9 @@ void launch_stash_scalars(cudaStream_t s, int nv, PdhgState* st, const double* p
 void launch_primal_shard_p2p(cudaStream_t s, int len, PdhgState* st, double* xs0, double* xs1, double* aty_s,
                              const PeerPtrs& pp, int world, int rank, int seg_len, int pull, const double* c,
                              const double* lo, const double* up, double* xsum, ReduceScratch rs);
+void launch_push_shard(cudaStream_t s, const double* src, int len, const PeerPtrs& pp, int world, int rank, int seg_len);
+void launch_p2p_exchange(cudaStream_t s, double* vals, int k, const PeerPtrs& pp, int world, int rank,
+                         unsigned long long* epochs, int* fault);
 void launch_push_part(cudaStream_t s, PdhgState* st, const double* part, const PeerPtrs& pp, int world, int rank, int seg_len);
 void launch_reduce_part_p2p(cudaStream_t s, int len, double* dst, const PeerPtrs& pp, int world, int rank, int seg_len,
                             int pull);
