@@ -1350,6 +1350,7 @@ int b200pdlp_p2p_import(b200pdlp_problem* p, const uint8_t* all_handles) {
       p->peers.recv[g] = (double*)q[3];
     }
     p->p2p = true;
+    p->p2p_pull = 1;   // measured slightly faster than the push variant at 2 and 4 GPUs (profiles/r01_multigpu.md)
     if (const char* e = getenv("B200PDLP_P2P_PULL")) p->p2p_pull = atoi(e);
     // graphs captured for the NCCL path are stale now
     if (p->graph_main) { cudaGraphExecDestroy(p->graph_main); p->graph_main = nullptr; }

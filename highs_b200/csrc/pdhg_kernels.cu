@@ -599,7 +599,8 @@ p2p_barrier_kernel(int mode, PdhgState* st, const double* __restrict__ partials,
         mb[1] = tot[1];
       }
     }
-    __threadfence_system();
+    // no fence needed: lane h wrote its scalars to peer h and now releases the flag at peer h (st.release.sys
+    // orders the lane's own earlier stores); data written by earlier KERNELS is complete at the kernel boundary
     unsigned long long e = 0;
     if (lane == 0) { e = epochs[mode] + 1; epochs[mode] = e; }
     e = __shfl_sync(0xffffffffu, e, 0);
