@@ -10,10 +10,52 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <functional>
 #include <limits>
 #include <stdexcept>
+#include <thread>
 
 namespace b200 {
+
+// ---- tiny fork-join helper: the O(nnz) prologue (formulate, 11 scaling sweeps, transposition, ELL build)
+// is the dominant cost of a short solve once the iterations run at ~10^4/s, so it is spread over host cores.
+// Every parallel loop below is arranged so that each output element is produced by exactly one thread with
+// the same arithmetic, in the same order, as the sequential code: results do not depend on the thread count.
+static int host_threads() {
+  static int n = [] {
+    if (const char* e = getenv("B200PDLP_HOST_THREADS")) return std::max(1, atoi(e));
+    const unsigned hc = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(16u, hc ? hc : 1u));
+  }();
+  return n;
+}
+// fn(chunk_index, begin, end) over [0, count) cut into host_threads() contiguous chunks
+static void parallel_chunks(long long count, const std::function<void(int, long long, long long)>& fn, long long min_per_thread = 1 << 15) {
+  int T = host_threads();
+  if (count < 2 * min_per_thread) T = 1;
+  T = (int)std::min<long long>(T, std::max<long long>(1, count / min_per_thread));
+  if (T <= 1) { fn(0, 0, count); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < T; t++) {
+    const long long b = count * t / T, e = count * (t + 1) / T;
+    th.emplace_back([&fn, t, b, e] { fn(t, b, e); });
+  }
+  for (auto& x : th) x.join();
+}
+// column chunks balanced by nonzeros: boundaries[t] .. boundaries[t+1]
+static std::vector<int> balanced_columns(const std::vector<int>& cbeg, int n, int T) {
+  std::vector<int> b(T + 1, n);
+  b[0] = 0;
+  const long long nnz = cbeg[n];
+  for (int t = 1; t < T; t++) {
+    const long long target = nnz * t / T;
+    b[t] = (int)(std::lower_bound(cbeg.begin(), cbeg.begin() + n + 1, (int)target) - cbeg.begin());
+    b[t] = std::max(b[t], b[t - 1]);
+    b[t] = std::min(b[t], n);
+  }
+  return b;
+}
 
 // formulateLP_highs, CupdlpWrapper.cpp:280-448
 void formulate(const b200pdlp_lp& lp, StdForm& f) {
@@ -126,7 +168,11 @@ void apply_to_vectors(StdForm& f, const std::vector<double>& cs, const std::vect
 }  // namespace
 
 // PDHG_Scale_Data with Init_Scaling's fixed recipe: 10 inf-norm Ruiz passes, then
-// Pock-Chambolle with alpha = 1 (cupdlp_scaling.c:47-120, 174-231, 395-409)
+// Pock-Chambolle with alpha = 1 (cupdlp_scaling.c:47-120, 174-231, 395-409).
+// Parallel layout: columns are cut into nnz-balanced chunks, one per thread.  Column norms are private to
+// a chunk.  Row inf-norms (Ruiz) are gathered in per-thread arrays and merged with max (exact, order-free).
+// The row 1-norms of the Pock-Chambolle pass must be added in the reference's order (columns ascending), so
+// they are taken from a row-major index of the nonzeros (built once), one row per thread at a time.
 void scale(StdForm& f, bool do_scale) {
   const int n = f.n, m = f.m;
   double amax = 0.0;
@@ -135,45 +181,109 @@ void scale(StdForm& f, bool do_scale) {
     f.amax = amax;
     return;
   }
-  std::vector<double> cs(n), rs(m), cs_next(n), rs_next(m);
+  const int T = (f.nnz < (1 << 18)) ? 1 : host_threads();
+  const std::vector<int> cb = balanced_columns(f.cbeg, n, T);
+  std::vector<double> cs(n), rs(m), cs_next(n);
+  std::vector<std::vector<double>> rloc(T);           // per-thread row accumulators
+  for (int t = 0; t < T; t++) rloc[t].assign(m, 0.0);
+  auto run_cols = [&](const std::function<void(int, int, int)>& fn) {   // fn(tid, col_begin, col_end)
+    if (T == 1) { fn(0, 0, n); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++) th.emplace_back([&, t] { fn(t, cb[t], cb[t + 1]); });
+    for (auto& x : th) x.join();
+  };
+  auto merge_rows_max = [&](std::vector<double>& dst) {
+    parallel_chunks(m, [&](int, long long b, long long e) {
+      for (long long i = b; i < e; i++) {
+        double v = rloc[0][i];
+        for (int t = 1; t < T; t++) if (rloc[t][i] > v) v = rloc[t][i];
+        dst[i] = v;
+      }
+    });
+  };
+  // row-major index of the nonzeros (position in cval), columns ascending within a row: for the exact row sums
+  std::vector<int> rptr, rpos;
+  auto build_row_index = [&] {
+    rptr.assign(m + 1, 0);
+    for (int p = 0; p < f.nnz; p++) rptr[f.cidx[p] + 1]++;
+    for (int i = 0; i < m; i++) rptr[i + 1] += rptr[i];
+    rpos.resize(f.nnz);
+    std::vector<int> w(rptr.begin(), rptr.end() - 1);
+    for (int p = 0; p < f.nnz; p++) rpos[w[f.cidx[p]]++] = p;   // p ascending = columns ascending
+  };
   // norms for the first Ruiz pass
-  std::fill(rs.begin(), rs.end(), 0.0);
-  for (int j = 0; j < n; j++) {
-    double mx = 0.0;
-    for (int p = f.cbeg[j]; p < f.cbeg[j + 1]; p++) {
-      const double a = std::fabs(f.cval[p]);
-      if (a > mx) mx = a;
-      if (rs[f.cidx[p]] < a) rs[f.cidx[p]] = a;
+  run_cols([&](int t, int c0, int c1) {
+    std::vector<double>& r = rloc[t];
+    for (int j = c0; j < c1; j++) {
+      double mx = 0.0;
+      for (int p = f.cbeg[j]; p < f.cbeg[j + 1]; p++) {
+        const double a = std::fabs(f.cval[p]);
+        if (a > mx) mx = a;
+        if (r[f.cidx[p]] < a) r[f.cidx[p]] = a;
+      }
+      cs[j] = mx;
     }
-    cs[j] = mx;
-  }
+  });
+  merge_rows_max(rs);
   const int kRuiz = 10;
+  std::vector<double> amax_t(T, 0.0);
   for (int it = 0; it <= kRuiz; it++) {
-    // turn the gathered norms into this pass's factors (sqrt, with 0 -> 1)
-    for (int j = 0; j < n; j++) { const double v = std::sqrt(cs[j]); cs[j] = (v == 0.0) ? 1.0 : v; }
-    for (int i = 0; i < m; i++) rs[i] = (rs[i] == 0.0) ? 1.0 : std::sqrt(rs[i]);
-    apply_to_vectors(f, cs, rs);
+    // turn the gathered norms into this pass's factors (sqrt, with 0 -> 1) and apply them to the vectors
+    parallel_chunks(n, [&](int, long long b, long long e) {
+      for (long long j = b; j < e; j++) {
+        const double v = std::sqrt(cs[j]);
+        const double c = (v == 0.0) ? 1.0 : v;
+        cs[j] = c;
+        f.cost[j] /= c; f.lower[j] *= c; f.upper[j] *= c; f.col_scale[j] *= c;
+      }
+    });
+    parallel_chunks(m, [&](int, long long b, long long e) {
+      for (long long i = b; i < e; i++) {
+        const double r = (rs[i] == 0.0) ? 1.0 : std::sqrt(rs[i]);
+        rs[i] = r;
+        f.rhs[i] /= r; f.row_scale[i] *= r;
+      }
+    });
     const bool next_is_pc = (it == kRuiz - 1);  // after the 10th Ruiz pass gather 1-norms
     const bool last = (it == kRuiz);            // the Pock-Chambolle pass itself
-    std::fill(rs_next.begin(), rs_next.end(), 0.0);
-    for (int j = 0; j < n; j++) {
-      double acc = 0.0;
-      const double cj = cs[j];
-      for (int p = f.cbeg[j]; p < f.cbeg[j + 1]; p++) {
-        const int i = f.cidx[p];
-        double v = f.cval[p] / rs[i];   // row division first, then column division (:33-41)
-        v /= cj;
-        f.cval[p] = v;
-        const double a = std::fabs(v);
-        if (last) { if (a > amax) amax = a; }
-        else if (next_is_pc) { acc += a; rs_next[i] += a; }
-        else { if (a > acc) acc = a; if (rs_next[i] < a) rs_next[i] = a; }
+    run_cols([&](int t, int c0, int c1) {
+      std::vector<double>& rn = rloc[t];
+      if (!last && !next_is_pc) std::fill(rn.begin(), rn.end(), 0.0);
+      double am = 0.0;
+      for (int j = c0; j < c1; j++) {
+        double acc = 0.0;
+        const double cj = cs[j];
+        for (int p = f.cbeg[j]; p < f.cbeg[j + 1]; p++) {
+          const int i = f.cidx[p];
+          double v = f.cval[p] / rs[i];   // row division first, then column division (:33-41)
+          v /= cj;
+          f.cval[p] = v;
+          const double a = std::fabs(v);
+          if (last) { if (a > am) am = a; }
+          else if (next_is_pc) { acc += a; }
+          else { if (a > acc) acc = a; if (rn[i] < a) rn[i] = a; }
+        }
+        cs_next[j] = acc;
       }
-      cs_next[j] = acc;
+      amax_t[t] = am;
+    });
+    if (last) break;
+    if (next_is_pc) {
+      // exact row 1-norms in the reference's summation order
+      if (rptr.empty()) build_row_index();
+      parallel_chunks(m, [&](int, long long b, long long e) {
+        for (long long i = b; i < e; i++) {
+          double sum = 0.0;
+          for (int q = rptr[i]; q < rptr[i + 1]; q++) sum += std::fabs(f.cval[rpos[q]]);
+          rs[i] = sum;
+        }
+      });
+    } else {
+      merge_rows_max(rs);
     }
     cs.swap(cs_next);
-    rs.swap(rs_next);
   }
+  for (int t = 0; t < T; t++) amax = std::max(amax, amax_t[t]);
   f.amax = amax;
 }
 
@@ -233,8 +343,9 @@ void build_col_major(const StdForm& f, int r0, int r1, Csr& at) {
   at.nnz = at.rowptr[f.n];
   at.col.assign(at.nnz, 0);
   at.val.assign(at.nnz, 0.0);
+  parallel_chunks(f.n, [&](int, long long j0, long long j1) {
   std::vector<std::pair<int, double>> tmp;
-  for (int j = 0; j < f.n; j++) {
+  for (int j = (int)j0; j < (int)j1; j++) {
     int q = at.rowptr[j];
     bool sorted = true;
     int prev = -1;
@@ -254,6 +365,7 @@ void build_col_major(const StdForm& f, int r0, int r1, Csr& at) {
       for (size_t t = 0; t < tmp.size(); t++) { at.col[at.rowptr[j] + t] = tmp[t].first; at.val[at.rowptr[j] + t] = tmp[t].second; }
     }
   }
+  });
 }
 
 std::vector<int> make_perm(const std::vector<int>& rowptr, int boundary, bool sort) {
@@ -263,10 +375,14 @@ std::vector<int> make_perm(const std::vector<int>& rowptr, int boundary, bool so
   if (!sort) return perm;
   auto len = [&](int r) { return rowptr[r + 1] - rowptr[r]; };
   auto sort_range = [&](int b, int e) {
-    for (int w = b; w < e; w += kSortWindow) {
-      const int we = std::min(w + kSortWindow, e);
-      std::stable_sort(perm.begin() + w, perm.begin() + we, [&](int x, int y) { return len(x) > len(y); });
-    }
+    const long long nwin = ((long long)(e - b) + kSortWindow - 1) / kSortWindow;
+    parallel_chunks(nwin, [&](int, long long w0, long long w1) {
+      for (long long wi = w0; wi < w1; wi++) {
+        const int w = b + (int)wi * kSortWindow;
+        const int we = std::min(w + kSortWindow, e);
+        std::stable_sort(perm.begin() + w, perm.begin() + we, [&](int x, int y) { return len(x) > len(y); });
+      }
+    }, 4);
   };
   boundary = std::max(0, std::min(boundary, n));
   sort_range(0, boundary);
@@ -307,18 +423,20 @@ void build_sell(const Csr& a, const std::vector<int>& perm, const std::vector<in
   out.padded = total;
   out.col.assign((size_t)total + 32, 0);
   out.val.assign((size_t)total + 32, 0.0);
-  for (int s = 0; s < nslices; s++) {
-    const SellMatrix::Slice& sl = out.slices[s];
-    for (int l = 0; l < 32; l++) {
-      if ((sl.skipmask >> l) & 1u) continue;
-      const int r = perm[s * 32 + l];
-      int k = 0;
-      for (int p = a.rowptr[r]; p < a.rowptr[r + 1]; p++, k++) {
-        out.col[(size_t)sl.ptr + 32 * (size_t)k + l] = colmap[a.col[p]];
-        out.val[(size_t)sl.ptr + 32 * (size_t)k + l] = a.val[p];
+  parallel_chunks(nslices, [&](int, long long s0, long long s1) {
+    for (long long s = s0; s < s1; s++) {
+      const SellMatrix::Slice& sl = out.slices[s];
+      for (int l = 0; l < 32; l++) {
+        if ((sl.skipmask >> l) & 1u) continue;
+        const int r = perm[s * 32 + l];
+        int k = 0;
+        for (int p = a.rowptr[r]; p < a.rowptr[r + 1]; p++, k++) {
+          out.col[(size_t)sl.ptr + 32 * (size_t)k + l] = colmap[a.col[p]];
+          out.val[(size_t)sl.ptr + 32 * (size_t)k + l] = a.val[p];
+        }
       }
     }
-  }
+  }, 256);
   // long rows -> segments
   for (int nr = 0; nr < a.nrows; nr++) {
     const int ln = len(nr);

@@ -64,3 +64,14 @@ def test_partition_rows(engine_lib, world):
     rows = np.bincount(lp.a_matrix_.index_, minlength=lp.num_row_)   # all rows GEQ: no permutation
     load = [rows[b[g]:b[g + 1]].sum() + 5 * (b[g + 1] - b[g]) for g in range(world)]
     assert max(load) <= 1.02 * (sum(load) / world) + 64
+
+
+def test_standard_form_threaded_path(engine_lib, oracle):
+    """> 2^18 nonzeros: the multi-threaded scaling sweeps must still be bit-identical to the oracle"""
+    from highs_b200 import engine
+    from highs_b200.lp import synthetic_lp
+    lp = synthetic_lp(120000, 90000, 8, 4, dense_col_nnz=30000)
+    a, b = engine.host_form(lp, 1), oracle.formulate_and_scale(lp, 1)
+    for k in KEYS:
+        assert np.array_equal(a[k], b[k]), k
+    assert a["amax"] == b["amax"]
