@@ -263,8 +263,19 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   if (prm.device >= 0) p->device = prm.device; else CUDA_OK(cudaGetDevice(&p->device));
   set_device(p);
   p->rank = rank; p->world = world;
+  const bool timing = getenv("B200PDLP_TIMING") != nullptr;
+  auto tnow = [] { return std::chrono::steady_clock::now(); };
+  auto t0 = tnow();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    auto t1 = tnow();
+    fprintf(stderr, "[b200pdlp setup] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  };
   formulate(lp, p->form);
+  lap("formulate");
   scale(p->form, prm.scaling != 0);
+  lap("scale");
   StdForm& f = p->form;
   std::vector<int> bounds = partition_rows(f, world);
   p->r0 = bounds[rank]; p->r1 = bounds[rank + 1];
@@ -283,11 +294,14 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   {
     Csr at;
     build_row_major(f, p->r0, p->r1, p->csr_local);
+    lap("row-major transpose");
     build_col_major(f, p->r0, p->r1, at);
+    lap("col-major copy");
     p->rperm = make_perm(p->csr_local.rowptr, p->neq_local, sort);
     p->cperm = make_perm(f.cbeg, n, sort);   // GLOBAL column lengths: identical on every rank
     p->rinv = invert_perm(p->rperm);
     p->cinv = invert_perm(p->cperm);
+    lap("length sorts");
     if (world == 1) {
       p->nl = p->nl_real = n; p->c0 = 0; p->shard_len = n; p->seg_len = n;
       build_sell(p->csr_local, p->rperm, p->cinv, long_threshold, p->A.host);
@@ -315,9 +329,11 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
       p->at_outpos.from(outpos);
     }
   }
+  lap("sliced-ELL build");
   CUDA_OK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   p->A.upload();
   p->AT.upload();
+  lap("matrix upload");
   if (const char* e = getenv("B200PDLP_EXP")) p->exp_flags = atoi(e);
   if (const char* e = getenv("B200PDLP_PREFETCH")) { p->A.dev.prefetch_dist = atoi(e); p->AT.dev.prefetch_dist = atoi(e); }
   const int nl = p->nl;
@@ -358,6 +374,7 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   CUDA_OK(cudaMallocHost(&p->houts, kOutsCount * sizeof(double)));
   memset(p->hstate, 0, sizeof(PdhgState));
   CUDA_OK(cudaDeviceSynchronize());
+  lap("vectors + scratch");
 }
 
 // ------------------------------------------------------------------ PDHG passes

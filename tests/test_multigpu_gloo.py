@@ -1,8 +1,10 @@
-"""world_size-2 tests of the multi-GPU host logic on CPU (gloo): the row partition, the shard's
-standard-form data and the one exchange step per iteration -- all-reduce(sum) of the partial A_g' y_g
-with the scalar |dy|^2 riding in the tail slot (DESIGN.md "Multi-GPU") -- reproduce the single-rank
-quantities.  The SpMV itself is stood in for by scipy on the oracle's scaled matrix; the CUDA kernels
-are exercised by the -m gpu tests."""
+"""world_size-2 tests of the multi-GPU host logic on CPU (gloo): the nnz-balanced row partition, the
+column shards, and the two exchange steps of a PDHG pass in their segmented layout --
+reduce-scatter of the partial A_g' y_g with |dy|^2 and the row-side interaction riding in the two tail slots
+of every segment, and all-gather of the x shards with |dx|^2 in the tail -- reproduce the single-rank
+quantities, including the identity (x-x').(A'y - A'y') == (Ax - Ax').(y - y') that lets the interaction be
+taken on the row side.  The SpMV itself is stood in for by scipy on the oracle's scaled matrix; the CUDA
+kernels are exercised by the -m gpu tests."""
 import os
 import sys
 
@@ -52,6 +54,43 @@ def _worker(rank, world, port, q):
         dist.all_reduce(tb, op=dist.ReduceOp.SUM)
         assert np.allclose(buf[: f["n"]], A.T @ y, rtol=1e-12, atol=1e-12)
         assert np.isclose(buf[f["n"]], np.sum((y - yold) ** 2), rtol=1e-12)
+        # ---- the segmented exchange of one PDHG pass
+        n, m = f["n"], f["m"]
+        shard_len = ((n + world - 1) // world + 1) & ~1
+        seg_len = shard_len + 2
+        pos = lambda j: (j // shard_len) * seg_len + (j % shard_len)
+        c0 = rank * shard_len
+        nl = max(0, min(shard_len, n - c0))
+        rng2 = np.random.default_rng(77)        # identical on every rank (rank 0 consumed extra numbers above)
+        xnew = rng2.standard_normal(n)
+        ynew = rng2.standard_normal(m)
+        # all-gather: my x' shard (+ |dx|^2 partial in the tail) -> xfull on every rank
+        send = np.zeros(seg_len)
+        send[:nl] = xnew[c0:c0 + nl]
+        send[shard_len] = np.sum((x[c0:c0 + nl] - xnew[c0:c0 + nl]) ** 2)
+        gathered = [torch.zeros(seg_len, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(gathered, torch.from_numpy(send))
+        xfull = torch.cat(gathered).numpy()
+        assert np.array_equal(xfull[[pos(j) for j in range(0, n, 97)]], xnew[::97])
+        dx2 = sum(xfull[g * seg_len + shard_len] for g in range(world))
+        assert np.isclose(dx2, np.sum((x - xnew) ** 2), rtol=1e-12)
+        # reduce-scatter (emulated with all-reduce + slice): partial A_g' y' with the scalars in every tail
+        part = np.zeros(world * seg_len)
+        pg = Ag.T @ ynew[r0:r1]
+        idx = np.array([pos(j) for j in range(n)])
+        part[idx] = pg
+        dy2_g = np.sum((y[r0:r1] - ynew[r0:r1]) ** 2)
+        inter_g = np.dot(Ag @ x - Ag @ xnew, y[r0:r1] - ynew[r0:r1])
+        for g in range(world):
+            part[g * seg_len + shard_len] = dy2_g
+            part[g * seg_len + shard_len + 1] = inter_g
+        tp = torch.from_numpy(part)
+        dist.all_reduce(tp)
+        red = part[rank * seg_len:(rank + 1) * seg_len]
+        assert np.allclose(red[:nl], (A.T @ ynew)[c0:c0 + nl], rtol=1e-12, atol=1e-12)
+        assert np.isclose(red[shard_len], np.sum((y - ynew) ** 2), rtol=1e-12)
+        inter_col = np.dot(x - xnew, A.T @ y - A.T @ ynew)      # the reference's column-side form
+        assert np.isclose(red[shard_len + 1], inter_col, rtol=1e-9, atol=1e-9)
         # gather of a row-partitioned vector at the end of the solve = zero-padded sum
         full = np.zeros(f["m"])
         full[r0:r1] = y[r0:r1]
@@ -63,8 +102,9 @@ def _worker(rank, world, port, q):
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         assert tm.item() == world
         q.put((rank, "ok"))
-    except Exception as e:  # pragma: no cover
-        q.put((rank, repr(e)))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
     finally:
         dist.destroy_process_group()
 
