@@ -1375,6 +1375,19 @@ int b200pdlp_p2p_import(b200pdlp_problem* p, const uint8_t* all_handles) {
   });
 }
 
+int b200pdlp_p2p_release(b200pdlp_problem* p) {
+  return guarded([&] {
+    if (!p) throw Error(B200PDLP_ERR_ARG, "null argument");
+    set_device(p);
+    CUDA_OK(cudaStreamSynchronize(p->stream));
+    for (void* q : p->ipc_opened) cudaIpcCloseMemHandle(q);
+    p->ipc_opened.clear();
+    p->p2p = false;
+    if (p->graph_main) { cudaGraphExecDestroy(p->graph_main); p->graph_main = nullptr; }
+    if (p->graph_small) { cudaGraphExecDestroy(p->graph_small); p->graph_small = nullptr; }
+  });
+}
+
 int b200pdlp_form_create(const b200pdlp_lp* lp, int32_t scaling, b200pdlp_form** out) {
   return guarded([&] {
     check_lp(lp);

@@ -61,7 +61,7 @@ class CResult(C.Structure):
 ABI_SYMBOLS = [
     "b200pdlp_default_params", "b200pdlp_solve", "b200pdlp_problem_create", "b200pdlp_problem_destroy",
     "b200pdlp_problem_dims", "b200pdlp_problem_get_vector", "b200pdlp_problem_get_csr", "b200pdlp_spmv_ax",
-    "b200pdlp_spmv_aty", "b200pdlp_bench_spmv", "b200pdlp_bench_pass", "b200pdlp_p2p_export", "b200pdlp_p2p_import", "b200pdlp_p2p_timeline", "b200pdlp_problem_solve", "b200pdlp_nccl_unique_id",
+    "b200pdlp_spmv_aty", "b200pdlp_bench_spmv", "b200pdlp_bench_pass", "b200pdlp_p2p_export", "b200pdlp_p2p_import", "b200pdlp_p2p_timeline", "b200pdlp_p2p_release", "b200pdlp_problem_solve", "b200pdlp_nccl_unique_id",
     "b200pdlp_comm_init", "b200pdlp_partition_rows", "b200pdlp_last_error", "b200pdlp_version",
     "b200pdlp_device_count", "b200pdlp_form_create", "b200pdlp_form_destroy", "b200pdlp_form_dims",
     "b200pdlp_form_get_vector", "b200pdlp_form_get_csc", "b200pdlp_form_get_row_map",
@@ -118,6 +118,7 @@ def lib():
         L.b200pdlp_p2p_export.argtypes = [C.c_void_p, C.POINTER(C.c_uint8)]
         L.b200pdlp_p2p_import.argtypes = [C.c_void_p, C.POINTER(C.c_uint8)]
         L.b200pdlp_p2p_timeline.argtypes = [C.c_void_p, _dp]
+        L.b200pdlp_p2p_release.argtypes = [C.c_void_p]
         L.b200pdlp_partition_rows.argtypes = [C.POINTER(CLp), C.c_int32, _ip]
         L.b200pdlp_form_create.argtypes = [C.POINTER(CLp), C.c_int32, C.POINTER(C.c_void_p)]
         L.b200pdlp_form_destroy.argtypes = [C.c_void_p]
@@ -273,6 +274,9 @@ class Problem:
         _check(lib().b200pdlp_p2p_timeline(self._h, _p(out, _dp)), "b200pdlp_p2p_timeline")
         keys = ["primal_shard_phase", "barrier0_total", "barrier0_wait", "ax_aty_phase", "barrier1_total", "barrier1_wait", "passes"]
         return dict(zip(keys, out[:7].tolist()))
+
+    def p2p_release(self):
+        _check(lib().b200pdlp_p2p_release(self._h), "b200pdlp_p2p_release")
 
     def p2p_export(self) -> bytes:
         buf = (C.c_uint8 * 256)()

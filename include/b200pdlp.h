@@ -174,6 +174,8 @@ int b200pdlp_comm_init(b200pdlp_problem* p, const uint8_t id[128]);
 #define B200PDLP_IPC_BYTES 256
 int b200pdlp_p2p_export(b200pdlp_problem* p, uint8_t handles[B200PDLP_IPC_BYTES]);
 int b200pdlp_p2p_import(b200pdlp_problem* p, const uint8_t* all_handles);
+/* unmap the peers' buffers (call on every rank, then synchronise the ranks, BEFORE any rank destroys its problem) */
+int b200pdlp_p2p_release(b200pdlp_problem* p);
 /* device-side timeline of the fused path since the last call, per-pass averages in us: [0] primal-shard phase,
  * [1] barrier 0 total, [2] of which waiting, [3] A x + A'y phase, [4] barrier 1 total, [5] of which waiting, [6] passes */
 int b200pdlp_p2p_timeline(b200pdlp_problem* p, double out_us[8]);

@@ -33,6 +33,10 @@ res = prob.solve(tol_primal=1e-5, tol_dual=1e-5, tol_gap=1e-5, iter_limit=100000
 if rank == 0:
     np.savez(sys.argv[1], col_value=res["col_value"], row_dual=res["row_dual"], row_value=res["row_value"],
              col_dual=res["col_dual"], iters=res["iters"], term=res["term_code"])
+if sys.argv[2] == "p2p":
+    prob.p2p_release()
+dist.barrier()
+prob.close()
 dist.barrier()
 dist.destroy_process_group()
 ''' % ROOT
