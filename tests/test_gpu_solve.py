@@ -165,3 +165,65 @@ def test_tree_vs_ordered_reductions_agree(engine_lib):
     b = engine.solve(lp)
     assert a["term_name"] == b["term_name"] == "OPTIMAL"
     assert _rel(lp.objectiveValue(a["col_value"]), lp.objectiveValue(b["col_value"])) <= REL_TOL
+
+
+def _ragged_lp(seed):
+    """empty columns and rows, fixed / free / boxed columns, EQ / ranged / free / LEQ / GEQ rows, maximise, offset"""
+    import scipy.sparse as sp
+    from highs_b200.lp import HighsLp, HighsSparseMatrix
+    rng = np.random.default_rng(seed)
+    m, n = 60, 50
+    A = sp.random(m, n, density=0.12, random_state=seed, data_rvs=rng.standard_normal).tolil()
+    A[:, [3, 17]] = 0          # empty columns
+    A[[5, 40], :] = 0          # empty rows
+    A = A.tocsc()
+    A.eliminate_zeros()
+    x0 = rng.random(n)
+    ax = A @ x0
+    kind = rng.integers(0, 5, size=m)
+    rl = np.where(kind == 0, ax, np.where(kind == 1, ax - 0.5, np.where(kind == 2, -np.inf, np.where(kind == 3, ax - 1, -np.inf))))
+    ru = np.where(kind == 0, ax, np.where(kind == 1, np.inf, np.where(kind == 2, ax + 0.5, np.where(kind == 3, ax + 1, np.inf))))
+    rl[5], ru[5] = -1.0, 1.0   # empty ranged row (feasible)
+    rl[40], ru[40] = -np.inf, np.inf
+    lo = np.where(rng.random(n) < 0.7, 0.0, -np.inf)
+    up = np.where(rng.random(n) < 0.4, 2.0, np.inf)
+    lo[7] = up[7] = 0.5        # fixed column
+    lo[3], up[3] = 0.0, 1.0
+    c = rng.standard_normal(n)
+    c[np.isinf(lo) & np.isinf(up)] = 0.0     # keep free columns bounded through zero cost
+    return HighsLp(n, m, c, lo, up, rl, ru, HighsSparseMatrix(n, m, A.indptr, A.indices, A.data), -1 if seed % 2 else 1, 1.25)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_ragged_lp_bit_exact(engine_lib, oracle, seed):
+    from highs_b200 import engine
+    lp = _ragged_lp(seed)
+    kw = dict(tol_primal=1e-5, tol_dual=1e-5, tol_gap=1e-5, iter_limit=40000)
+    res, orc = engine.solve(lp, trace_cap=2048, **kw), oracle.solve(lp, trace_cap=2048, **kw)
+    assert res["term_code"] == orc["term_code"] and res["iters"] == orc["iters"]
+    assert np.array_equal(res["trace"][:, :15], orc["trace"][:, :15])
+    for key in ("col_value", "col_dual", "row_value", "row_dual"):
+        assert np.array_equal(res[key], orc[key]), key
+
+
+def test_time_limit(engine_lib):
+    """D_TIME_LIM: the solve stops at the first check after the limit with kTimeLimit (CupdlpWrapper.cpp:233-236)"""
+    from highs_b200 import pdlp
+    from highs_b200.lp import synthetic_lp
+    lp = synthetic_lp(100000, 100000, 10, seed=3)
+    opt = pdlp.HighsOptions(time_limit=1e-3)
+    sol, info, basis = pdlp.HighsSolution(), pdlp.HighsInfo(), pdlp.HighsBasis()
+    st, ms = pdlp.solveLpCupdlp(opt, pdlp.HighsTimer(), lp, basis, sol, info)
+    assert st == pdlp.HighsStatus.kOk and ms == pdlp.HighsModelStatus.kTimeLimit
+    assert 0 < info.pdlp_iteration_count < 100000 and sol.value_valid
+
+
+def test_dense_column_s5_mini(engine_lib, oracle):
+    """config S5 in miniature (one 50%-dense column: long-row segments in A^T): converges to the oracle's optimum"""
+    from highs_b200 import engine
+    from highs_b200.lp import synthetic_lp
+    lp = synthetic_lp(6000, 6000, 6, seed=2, dense_col_nnz=3000)
+    kw = dict(tol_primal=1e-6, tol_dual=1e-6, tol_gap=1e-6, iter_limit=200000)
+    res, orc = engine.solve(lp, **kw), oracle.solve(lp, **kw)
+    assert res["term_name"] == orc["term_name"] == "OPTIMAL"
+    assert _rel(lp.objectiveValue(res["col_value"]), lp.objectiveValue(orc["col_value"])) <= 1e-5
