@@ -468,8 +468,8 @@ static void full_aty(b200pdlp_problem* p, const double* y, double* aty) {
       if (!p->p2p_pull) launch_push_part(p->stream, nullptr, p->part.p, p->peers, p->world, p->rank, p->seg_len);
       launch_p2p_exchange(p->stream, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p);
       launch_reduce_part_p2p(p->stream, p->nl, aty, p->peers, p->world, p->rank, p->seg_len, p->p2p_pull);
-      // (in pull mode the peers' `part` buffers must stay untouched until everybody has read them)
-      if (p->p2p_pull) launch_p2p_exchange(p->stream, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p);
+      // (pull mode: the peers' `part` buffers stay untouched until their next partial SpMV, which comes after a
+      //  barrier that this rank only passes once it has finished reading)
       p->launches += 3;
     } else {
       reduce_scatter_part(p);
@@ -506,15 +506,20 @@ static CheckResult run_check(b200pdlp_problem* p, bool timed_out_local) {
   const int n = p->nl, ml = p->ml, cur = h->cur;   // n = column entries held by this rank
   const int acur = p->world == 1 ? cur : 0;        // multi-GPU keeps one current A^T y shard
   const double scale = h->sum_step > 0.0 ? 1.0 / h->sum_step : 1.0;
+  const bool fused_pull = p->world > 1 && p->p2p && p->p2p_pull;
   if (p->world > 1 && h->accepted_last) {
     // the last accepted pass left its A^T y' un-reduced (P2P) / in the reduce-scatter buffer (NCCL): make it current
     if (p->p2p) {
       launch_reduce_part_p2p(s, n, p->aty[0].p, p->peers, p->world, p->rank, p->seg_len, p->p2p_pull);
-      // nobody may overwrite recv slots / part buffers (check-time A^T ybar) before every rank has consumed them
-      launch_p2p_exchange(s, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p);
-      p->launches += 2;
+      p->launches++;
+      if (!p->p2p_pull) {
+        // push mode: nobody may overwrite my receive slots (check-time A^T ybar) before I have consumed them
+        launch_p2p_exchange(s, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p);
+        p->launches++;
+      }
+    } else {
+      CUDA_OK(cudaMemcpyAsync(p->aty[0].p, p->red.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
     }
-    else CUDA_OK(cudaMemcpyAsync(p->aty[0].p, p->red.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
     h->accepted_last = 0;
     push_state(p);
   }
@@ -522,8 +527,19 @@ static CheckResult run_check(b200pdlp_problem* p, bool timed_out_local) {
   launch_average(s, ml, p->y[cur].p, p->ysum.p, p->yavg.p, h->pending, h->w_pending, scale);
   p->launches += 2;
   if (h->pending) { h->pending = 0; push_state(p); }
-  full_ax(p, p->xavg.p, p->axavg.p);
-  full_aty(p, p->yavg.p, p->atyavg.p);
+  if (fused_pull) {
+    // one barrier for both exchanges: x-bar shards are stored into every peer's xfull, the partial A_g^T y-bar is
+    // parked in my `recv` buffer (so `part`, which a slower peer may still be reducing from, stays intact)
+    launch_push_shard(s, p->xavg.p, p->nl, p->peers, p->world, p->rank, p->seg_len);
+    launch_spmv_partial_aty(s, p->AT.dev, nullptr, p->yavg.p, p->yavg.p, p->recv.p, p->at_outpos.p);
+    launch_p2p_exchange(s, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p);
+    launch_spmv_plain(s, p->A.dev, p->xfull.p, p->axavg.p);
+    launch_reduce_part_p2p(s, n, p->atyavg.p, p->peers, p->world, p->rank, p->seg_len, 2);
+    p->launches += 5;
+  } else {
+    full_ax(p, p->xavg.p, p->axavg.p);
+    full_aty(p, p->yavg.p, p->atyavg.p);
+  }
   ColIter c0{p->x[cur].p, p->aty[acur].p}, c1{p->xavg.p, p->atyavg.p};
   RowIter r0{p->y[cur].p, p->ax[cur].p}, r1{p->yavg.p, p->axavg.p};
   double* o = p->outs.p;

@@ -552,7 +552,10 @@ reduce_part_p2p_kernel(int len, double* __restrict__ dst, PeerPtrs pp, int world
   const int stride = gridDim.x * kThreads;
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < len; i += stride) {
     double ai = 0.0;
-    for (int h = 0; h < world; h++) ai += __ldcg(pull ? pp.part[h] + seg + i : pp.recv[rank] + (size_t)h * seg_len + i);
+    // pull 0: the peers pushed into my receive slots; 1: read the peers' `part`; 2: read the peers' `recv`
+    // (check iterations park their partial A_g^T ybar there so that `part` keeps the last pass's data)
+    for (int h = 0; h < world; h++)
+      ai += __ldcg(pull == 0 ? pp.recv[rank] + (size_t)h * seg_len + i : (pull == 1 ? pp.part[h] : pp.recv[h]) + seg + i);
     dst[i] = ai;
   }
 }
@@ -762,6 +765,7 @@ col_check_fused_kernel(int n, ColIter it0, ColIter it1, const double* __restrict
     const double ci = c[i], l = lo[i], u = up[i], sc = cs[i];
     const bool hl = l > -INFINITY, hu = u < INFINITY;
     const double lf = hl ? l : 0.0, uf = hu ? u : 0.0;
+    const double isc = 1.0 / sc;
 #pragma unroll
     for (int t = 0; t < 2; t++) {
       const ColIter& it = t ? it1 : it0;
@@ -771,8 +775,8 @@ col_check_fused_kernel(int n, ColIter it0, ColIter it1, const double* __restrict
       const double sn = hu ? (rc < 0.0 ? -rc : 0.0) : 0.0;
       const double rr = (rc - sp + sn) * sc;
       const double k = (aty + sp - sn) * sc;
-      const double bl = hl ? (x < 0.0 ? x : 0.0) / sc : 0.0;
-      const double bu = hu ? (x > 0.0 ? x : 0.0) / sc : 0.0;
+      const double bl = hl ? (x < 0.0 ? x : 0.0) * isc : 0.0;
+      const double bu = hu ? (x > 0.0 ? x : 0.0) * isc : 0.0;
       double* a = acc + 10 * t;
       a[0] += x * ci; a[1] += sp * lf; a[2] += sn * uf; a[3] += rr * rr; a[4] += sp * sp; a[5] += sn * sn;
       a[6] += x * x; a[7] += k * k; a[8] += bl * bl; a[9] += bu * bu;
