@@ -856,7 +856,9 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   CUDA_OK(cudaStreamSynchronize(s));
 
   // ---- graphs: one check interval of passes, and a short one for top-ups after rejected steps
-  const int want_main = prm.graph_passes > 0 ? prm.graph_passes : interval;
+  // a few spare passes per replay: a rejected line-search step then still reaches the next check iteration inside
+  // the same replay (spare passes are no-ops once state.iter == state.stop_iter) instead of costing a host round trip
+  const int want_main = prm.graph_passes > 0 ? prm.graph_passes : interval + 4;
   if (!p->graph_main || p->graph_main_passes != want_main) {
     if (p->graph_main) cudaGraphExecDestroy(p->graph_main);
     p->graph_main = capture_passes(p, want_main);

@@ -83,7 +83,6 @@ struct PlainEpilogue {
   __device__ const double* input() const { return in; }
   __device__ void prefetch(int) {}
   __device__ void row(int r, double s, double*) const { out[r] = s; }
-  __device__ void finalize(const double*) const {}
 };
 
 // K2: PDHG_dualGradientStep (CPU order, cupdlp_step.c:55-67):
@@ -132,7 +131,6 @@ struct DualEpilogueT {
     t[0] = d * d;
     if (NACC > 1) t[NACC - 1] = (p_ax - s) * d;   // row-side interaction (AΔx)·Δy, multi-GPU only
   }
-  __device__ void finalize(const double* out) const { st->dy2 = out[0]; }
 };
 using DualEpilogue = DualEpilogueT<1>;
 using DualEpilogueMg = DualEpilogueT<2>;
@@ -214,7 +212,6 @@ struct PrimalEpilogue {
     const double da = p_aty - s;
     t[0] = dx * da;
   }
-  __device__ void finalize(const double* out) const { step_rule(st, out[0]); }
 };
 
 // K4: one CTA adds the block partials of K1 (|dx|^2), K2 (|dy|^2) and K3 (interaction) in a fixed
@@ -1002,7 +999,6 @@ struct PartialAtyEpilogue {
   // The rows of A_g^T are sorted by their LOCAL length (little ELL padding on every rank), so the
   // result goes through an index array: outpos[r] = position of that column in the segmented vector.
   __device__ void row(int r, double s, double*) const { out[outpos[r]] = s; }
-  __device__ void finalize(const double*) const {}
 };
 
 void launch_spmv_partial_aty(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
