@@ -293,6 +293,7 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   p->neq_local = std::max(0, std::min(f.neq - p->r0, ml));
   {
     Csr at;
+    if (f.rptr.empty()) build_row_index(f);
     build_row_major(f, p->r0, p->r1, p->csr_local);
     lap("row-major transpose");
     build_col_major(f, p->r0, p->r1, at);
@@ -1448,6 +1449,17 @@ int b200pdlp_form_get_csc(const b200pdlp_form* f, int32_t* start, int32_t* index
   memcpy(index, f->f.cidx.data(), (size_t)f->f.nnz * sizeof(int));
   memcpy(value, f->f.cval.data(), (size_t)f->f.nnz * sizeof(double));
   return B200PDLP_OK;
+}
+int b200pdlp_form_get_csr(b200pdlp_form* f, int32_t* rowptr, int32_t* col, double* val) {
+  return guarded([&] {
+    if (!f || !rowptr || !col || !val) throw Error(B200PDLP_ERR_ARG, "null argument");
+    if (f->f.rptr.empty()) build_row_index(f->f);
+    Csr a;
+    build_row_major(f->f, 0, f->f.m, a);
+    memcpy(rowptr, a.rowptr.data(), (size_t)(a.nrows + 1) * sizeof(int));
+    memcpy(col, a.col.data(), (size_t)a.nnz * sizeof(int));
+    memcpy(val, a.val.data(), (size_t)a.nnz * sizeof(double));
+  });
 }
 int b200pdlp_form_get_row_map(const b200pdlp_form* f, int32_t* row_new_idx, int32_t* row_class) {
   if (!f || !row_new_idx || !row_class) return B200PDLP_ERR_ARG;

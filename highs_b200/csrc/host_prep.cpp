@@ -107,20 +107,24 @@ void formulate(const b200pdlp_lp& lp, StdForm& f) {
   f.cbeg.resize(f.n + 1);
   f.cidx.resize(f.nnz);
   f.cval.resize(f.nnz);
-  // structural columns: within a column EQ/BOUND entries first, then LEQ (negated) / GEQ (:410-433)
-  int k = 0;
-  for (int j = 0; j < n0; j++) {
-    f.cbeg[j] = k;
-    for (int p = lp.a_start[j]; p < lp.a_start[j + 1]; p++) {
-      const int c = f.row_class[lp.a_index[p]];
-      if (c == kEq || c == kBound) { f.cidx[k] = f.row_new_idx[lp.a_index[p]]; f.cval[k] = lp.a_value[p]; k++; }
+  // structural columns: within a column EQ/BOUND entries first, then LEQ (negated) / GEQ (:410-433).
+  // A structural column keeps its entry count, so column j starts at a_start[j]: columns are independent.
+  parallel_chunks(n0, [&](int, long long j0, long long j1) {
+    for (int j = (int)j0; j < (int)j1; j++) {
+      int k = lp.a_start[j];
+      f.cbeg[j] = k;
+      for (int p = lp.a_start[j]; p < lp.a_start[j + 1]; p++) {
+        const int c = f.row_class[lp.a_index[p]];
+        if (c == kEq || c == kBound) { f.cidx[k] = f.row_new_idx[lp.a_index[p]]; f.cval[k] = lp.a_value[p]; k++; }
+      }
+      for (int p = lp.a_start[j]; p < lp.a_start[j + 1]; p++) {
+        const int c = f.row_class[lp.a_index[p]];
+        if (c == kLeq) { f.cidx[k] = f.row_new_idx[lp.a_index[p]]; f.cval[k] = -lp.a_value[p]; k++; }
+        else if (c == kGeq) { f.cidx[k] = f.row_new_idx[lp.a_index[p]]; f.cval[k] = lp.a_value[p]; k++; }
+      }
     }
-    for (int p = lp.a_start[j]; p < lp.a_start[j + 1]; p++) {
-      const int c = f.row_class[lp.a_index[p]];
-      if (c == kLeq) { f.cidx[k] = f.row_new_idx[lp.a_index[p]]; f.cval[k] = -lp.a_value[p]; k++; }
-      else if (c == kGeq) { f.cidx[k] = f.row_new_idx[lp.a_index[p]]; f.cval[k] = lp.a_value[p]; k++; }
-    }
-  }
+  }, 4096);
+  int k = nnz0;
   // one slack column per BOUND row: A x - z = 0, lo <= z <= up (:328-331,367-373,439-445)
   int j = n0;
   for (int i = 0; i < m; i++) {
@@ -167,6 +171,45 @@ void apply_to_vectors(StdForm& f, const std::vector<double>& cs, const std::vect
 }
 }  // namespace
 
+// Counting-sort transposition of the nonzero pattern (what csc2csr / cupdlp_dcs_transpose do,
+// cupdlp_cs.c:189-214), parallel: thread t histograms the rows of its column chunk, a prefix over
+// (row, thread) gives every thread its private output range inside each row, and the scatter keeps
+// the global column order.
+void build_row_index(StdForm& f) {
+  const int n = f.n, m = f.m;
+  int T = (f.nnz < (1 << 18)) ? 1 : host_threads();
+  while (T > 1 && (long long)T * m > (1LL << 27)) T /= 2;   // cap the T x m histogram at 512 MB
+  const std::vector<int> cb = balanced_columns(f.cbeg, n, T);
+  std::vector<std::vector<int>> hist(T);
+  auto run = [&](const std::function<void(int)>& fn) {
+    if (T == 1) { fn(0); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++) th.emplace_back([&fn, t] { fn(t); });
+    for (auto& x : th) x.join();
+  };
+  run([&](int t) {
+    hist[t].assign(m, 0);
+    for (int p = f.cbeg[cb[t]]; p < f.cbeg[cb[t + 1]]; p++) hist[t][f.cidx[p]]++;
+  });
+  f.rptr.assign(m + 1, 0);
+  for (int i = 0; i < m; i++) {
+    int c = 0;
+    for (int t = 0; t < T; t++) c += hist[t][i];
+    f.rptr[i + 1] = f.rptr[i] + c;
+  }
+  parallel_chunks(m, [&](int, long long b, long long e) {
+    for (long long i = b; i < e; i++) {
+      int off = f.rptr[i];
+      for (int t = 0; t < T; t++) { const int c = hist[t][i]; hist[t][i] = off; off += c; }
+    }
+  });
+  f.rpos.resize(f.nnz);
+  run([&](int t) {
+    std::vector<int>& w = hist[t];
+    for (int p = f.cbeg[cb[t]]; p < f.cbeg[cb[t + 1]]; p++) f.rpos[w[f.cidx[p]]++] = p;   // p ascending = columns ascending
+  });
+}
+
 // PDHG_Scale_Data with Init_Scaling's fixed recipe: 10 inf-norm Ruiz passes, then
 // Pock-Chambolle with alpha = 1 (cupdlp_scaling.c:47-120, 174-231, 395-409).
 // Parallel layout: columns are cut into nnz-balanced chunks, one per thread.  Column norms are private to
@@ -202,15 +245,8 @@ void scale(StdForm& f, bool do_scale) {
     });
   };
   // row-major index of the nonzeros (position in cval), columns ascending within a row: for the exact row sums
-  std::vector<int> rptr, rpos;
-  auto build_row_index = [&] {
-    rptr.assign(m + 1, 0);
-    for (int p = 0; p < f.nnz; p++) rptr[f.cidx[p] + 1]++;
-    for (int i = 0; i < m; i++) rptr[i + 1] += rptr[i];
-    rpos.resize(f.nnz);
-    std::vector<int> w(rptr.begin(), rptr.end() - 1);
-    for (int p = 0; p < f.nnz; p++) rpos[w[f.cidx[p]]++] = p;   // p ascending = columns ascending
-  };
+  std::vector<int>& rptr = f.rptr;
+  std::vector<int>& rpos = f.rpos;
   // norms for the first Ruiz pass
   run_cols([&](int t, int c0, int c1) {
     std::vector<double>& r = rloc[t];
@@ -270,7 +306,7 @@ void scale(StdForm& f, bool do_scale) {
     if (last) break;
     if (next_is_pc) {
       // exact row 1-norms in the reference's summation order
-      if (rptr.empty()) build_row_index();
+      if (rptr.empty()) build_row_index(f);
       parallel_chunks(m, [&](int, long long b, long long e) {
         for (long long i = b; i < e; i++) {
           double sum = 0.0;
@@ -311,6 +347,24 @@ void build_row_major(const StdForm& f, int r0, int r1, Csr& a) {
   a = Csr();
   a.nrows = r1 - r0;
   a.ncols = f.n;
+  if (!f.rptr.empty() && (int)f.rptr.size() == f.m + 1) {
+    // gather through the row-major index (parallel): position -> column via a position-to-column map
+    std::vector<int> colof(f.nnz);
+    parallel_chunks(f.n, [&](int, long long j0, long long j1) {
+      for (int j = (int)j0; j < (int)j1; j++)
+        for (int p = f.cbeg[j]; p < f.cbeg[j + 1]; p++) colof[p] = j;
+    }, 4096);
+    a.rowptr.resize(a.nrows + 1);
+    const int base = f.rptr[r0];
+    for (int i = 0; i <= a.nrows; i++) a.rowptr[i] = f.rptr[r0 + i] - base;
+    a.nnz = a.rowptr[a.nrows];
+    a.col.resize(a.nnz);
+    a.val.resize(a.nnz);
+    parallel_chunks(a.nnz, [&](int, long long q0, long long q1) {
+      for (long long q = q0; q < q1; q++) { const int p = f.rpos[base + q]; a.col[q] = colof[p]; a.val[q] = f.cval[p]; }
+    });
+    return;
+  }
   a.rowptr.assign(a.nrows + 1, 0);
   for (int p = 0; p < f.nnz; p++) { const int i = f.cidx[p]; if (i >= r0 && i < r1) a.rowptr[i - r0 + 1]++; }
   for (int i = 0; i < a.nrows; i++) a.rowptr[i + 1] += a.rowptr[i];

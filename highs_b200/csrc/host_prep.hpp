@@ -27,6 +27,9 @@ struct StdForm {
   double sense = 1.0, offset = 0.0;
   double norm_cost = 0.0, norm_rhs = 0.0;   // 2-norms of the unscaled cost / rhs
   double amax = 0.0;                        // max |a_ij| after scaling
+  // row-major index of the nonzeros (built once, by scale() or on demand): row i owns positions
+  // rpos[rptr[i] .. rptr[i+1]) of cidx/cval, columns ascending
+  std::vector<int> rptr, rpos;
 };
 
 // plain row-major matrix (CSR); entries of a row keep the order the reference's scatter SpMV adds them in
@@ -64,6 +67,7 @@ constexpr int kNnzPerBlock = 2048;   // long-row segment size (== kernels.cuh kN
 constexpr int kSortWindow = 8192;
 
 void formulate(const b200pdlp_lp& lp, StdForm& f);
+void build_row_index(StdForm& f);   // fills f.rptr / f.rpos (parallel counting sort)
 void scale(StdForm& f, bool do_scale);
 // nnz-balanced contiguous partition of the m rows into `world` parts
 std::vector<int> partition_rows(const StdForm& f, int world);

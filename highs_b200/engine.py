@@ -64,7 +64,7 @@ ABI_SYMBOLS = [
     "b200pdlp_spmv_aty", "b200pdlp_bench_spmv", "b200pdlp_bench_pass", "b200pdlp_p2p_export", "b200pdlp_p2p_import", "b200pdlp_p2p_timeline", "b200pdlp_p2p_release", "b200pdlp_problem_solve", "b200pdlp_nccl_unique_id",
     "b200pdlp_comm_init", "b200pdlp_partition_rows", "b200pdlp_last_error", "b200pdlp_version",
     "b200pdlp_device_count", "b200pdlp_form_create", "b200pdlp_form_destroy", "b200pdlp_form_dims",
-    "b200pdlp_form_get_vector", "b200pdlp_form_get_csc", "b200pdlp_form_get_row_map",
+    "b200pdlp_form_get_vector", "b200pdlp_form_get_csc", "b200pdlp_form_get_csr", "b200pdlp_form_get_row_map",
 ]
 
 _lib = None
@@ -127,6 +127,7 @@ def lib():
         L.b200pdlp_form_get_vector.argtypes = [C.c_void_p, C.c_int32, _dp, C.c_int32]
         L.b200pdlp_form_get_csc.argtypes = [C.c_void_p, _ip, _ip, _dp]
         L.b200pdlp_form_get_row_map.argtypes = [C.c_void_p, _ip, _ip]
+        L.b200pdlp_form_get_csr.argtypes = [C.c_void_p, _ip, _ip, _dp]
         _lib = L
     return _lib
 
@@ -332,7 +333,12 @@ def host_form(lp: HighsLp, scaling: int = 1) -> dict:
         rni = np.zeros(max(m, 1), dtype=np.int32)
         rcl = np.zeros(max(m, 1), dtype=np.int32)
         _check(L.b200pdlp_form_get_row_map(h, _p(rni, _ip), _p(rcl, _ip)), "form_get_row_map")
-        out.update(cbeg=cbeg, cidx=cidx[:nnz], cval=cval[:nnz], row_new_idx=rni[:m], row_type=rcl[:m])
+        rbeg = np.zeros(m + 1, dtype=np.int32)
+        ridx = np.zeros(max(nnz, 1), dtype=np.int32)
+        rval = np.zeros(max(nnz, 1))
+        _check(L.b200pdlp_form_get_csr(h, _p(rbeg, _ip), _p(ridx, _ip), _p(rval, _dp)), "form_get_csr")
+        out.update(cbeg=cbeg, cidx=cidx[:nnz], cval=cval[:nnz], row_new_idx=rni[:m], row_type=rcl[:m],
+                   rbeg=rbeg, ridx=ridx[:nnz], rval=rval[:nnz])
         return out
     finally:
         L.b200pdlp_form_destroy(h)

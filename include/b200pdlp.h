@@ -190,6 +190,8 @@ int b200pdlp_form_dims(const b200pdlp_form* f, int32_t dims[5], double scalars[3
 /* which = 0 cost, 1 lower, 2 upper, 3 rhs, 4 col_scale, 5 row_scale; returns count written */
 int b200pdlp_form_get_vector(const b200pdlp_form* f, int32_t which, double* dst, int32_t cap);
 int b200pdlp_form_get_csc(const b200pdlp_form* f, int32_t* start, int32_t* index, double* value);
+/* row-major copy (the reference's csc2csr, cupdlp_utils.c:1222-1254): rowptr[rows+1], col[nnz], val[nnz] */
+int b200pdlp_form_get_csr(b200pdlp_form* f, int32_t* rowptr, int32_t* col, double* val);
 /* row_new_idx[m], row_class[m] by ORIGINAL row (EQ=0, LEQ=1, GEQ=2, BOUND=3) */
 int b200pdlp_form_get_row_map(const b200pdlp_form* f, int32_t* row_new_idx, int32_t* row_class);
 

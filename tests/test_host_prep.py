@@ -5,7 +5,8 @@ import pytest
 
 from conftest import golden_lp, load_golden
 
-KEYS = ["cost", "lower", "upper", "rhs", "col_scale", "row_scale", "cbeg", "cidx", "cval", "row_new_idx", "row_type"]
+KEYS = ["cost", "lower", "upper", "rhs", "col_scale", "row_scale", "cbeg", "cidx", "cval", "row_new_idx", "row_type",
+        "rbeg", "ridx", "rval"]
 NAMES = sorted({c["name"] for c in load_golden() if "synthetic" not in c})
 
 
