@@ -1,5 +1,5 @@
 import sys, time, os
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 os.environ["B200PDLP_TIMING"] = "1"
 from highs_b200 import engine
 from highs_b200.lp import synthetic_lp
