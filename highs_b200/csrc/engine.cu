@@ -144,6 +144,15 @@ struct DeviceMatrix {
   int grid() const { return dev.nblocks_body + dev.nsegs; }
 };
 
+struct CudaEvent {   // RAII: released on every exit path
+  cudaEvent_t e = nullptr;
+  CudaEvent() { CUDA_OK(cudaEventCreate(&e)); }
+  ~CudaEvent() { if (e) cudaEventDestroy(e); }
+  CudaEvent(const CudaEvent&) = delete;
+  CudaEvent& operator=(const CudaEvent&) = delete;
+  operator cudaEvent_t() const { return e; }
+};
+
 struct Residuals {      // CUPDLPresobj for one iterate
   double pobj = 0, dobj = 0, pfeas = 0, dfeas = 0, gap = 0, relgap = 0;
   double pinf_obj = 0, pinf_res = 1, dinf_obj = 0, dinf_res = 1;
@@ -194,7 +203,6 @@ struct b200pdlp_problem {
   int graph_main_passes = 0, graph_small_passes = 0;
   long long launches = 0;
   int kernels_per_pass = 3;
-  bool has_prepared_solve = false;
 
   ~b200pdlp_problem() {
     if (graph_main) cudaGraphExecDestroy(graph_main);
@@ -208,13 +216,12 @@ struct b200pdlp_problem {
   ReduceScratch rs(int slot, int len) const {
     // slot-private partial arrays: 16 accumulators x kMaxEwBlocks-or-nblocks each
     double* t = (ordered && len <= ordered_cap) ? terms.p + (size_t)slot * 16 * ordered_cap : nullptr;
-    return ReduceScratch{partials.p + (size_t)slot * scratch_stride, counters.p + slot, t, len, exp_flags & 1};
+    return ReduceScratch{partials.p + (size_t)slot * scratch_stride, counters.p + slot, t, len, 0};
   }
   size_t scratch_stride = 0;
   DevBuf<double> terms;            // ordered-mode term scratch
   bool ordered = false;
   int ordered_cap = 0;
-  int exp_flags = 0;               // B200PDLP_EXP environment switches (timing experiments)
 };
 
 namespace b200 {
@@ -335,7 +342,6 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   p->A.upload();
   p->AT.upload();
   lap("matrix upload");
-  if (const char* e = getenv("B200PDLP_EXP")) p->exp_flags = atoi(e);
   if (const char* e = getenv("B200PDLP_PREFETCH")) { p->A.dev.prefetch_dist = atoi(e); p->AT.dev.prefetch_dist = atoi(e); }
   const int nl = p->nl;
   for (int k = 0; k < 2; k++) { p->x[k].alloc(nl); p->aty[k].alloc(nl); p->y[k].alloc(ml); p->ax[k].alloc(ml); }
@@ -873,13 +879,8 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   CheckResult chk;
   int term = B200PDLP_TIMELIMIT_OR_ITERLIMIT, term_iterate = 0, restarts = 0;
   bool have_check = false;
-  cudaEvent_t ev0, ev1;
-  CUDA_OK(cudaEventCreate(&ev0));
-  CUDA_OK(cudaEventCreate(&ev1));
+  CudaEvent ev0, ev1, evl0, evl1;
   double iter_ms = 0.0;
-  cudaEvent_t evl0, evl1;
-  CUDA_OK(cudaEventCreate(&evl0));
-  CUDA_OK(cudaEventCreate(&evl1));
   CUDA_OK(cudaEventRecord(evl0, s));
   const auto t_loop = clk::now();
 
@@ -949,10 +950,6 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   float loop_ms = 0.f;
   CUDA_OK(cudaEventElapsedTime(&loop_ms, evl0, evl1));
   const double solve_seconds = std::chrono::duration<double>(clk::now() - t_loop).count();
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
-  cudaEventDestroy(evl0);
-  cudaEventDestroy(evl1);
   out->loop_device_ms = loop_ms;
 
   // ---- PDHG_PostSolve (cupdlp_solver.c:1281-1435)
