@@ -144,6 +144,16 @@ def formulate_and_scale(lp, scaling=1) -> dict:
     return out
 
 
+def _parse_json_line(text: str) -> dict:
+    """ref_driver prints C doubles: map inf / nan to the spellings Python's json accepts"""
+    import re
+    line = text.strip().splitlines()[-1]
+    line = re.sub(r"(?<![\w.])-inf(?![\w])", "-Infinity", line)
+    line = re.sub(r"(?<![\w.-])inf(?![\w])", "Infinity", line)
+    line = re.sub(r"(?<![\w.])-?nan(?![\w])", "NaN", line)
+    return json.loads(line)
+
+
 def ref_available() -> bool:
     return os.path.exists(REF_DRIVER)
 
@@ -185,7 +195,7 @@ def run_reference(lp=None, mps=None, options=None, want_solution=False, warm=Non
         out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
         if out.returncode != 0:
             raise RuntimeError(f"ref_driver failed: {out.stderr}")
-        res = json.loads(out.stdout.strip().splitlines()[-1])
+        res = _parse_json_line(out.stdout)
         if want_solution:
             raw = open(sol, "rb").read()
             n, m, vv, dv = np.frombuffer(raw[:32], dtype="<i8")
@@ -221,4 +231,4 @@ def reference_kkt(lp, solution, model_status_code=7, options=None) -> dict:
         out = subprocess.run(cmd, capture_output=True, text=True)
         if out.returncode != 0:
             raise RuntimeError(f"ref_driver --kkt-of failed: {out.stderr}")
-        return json.loads(out.stdout.strip().splitlines()[-1])
+        return _parse_json_line(out.stdout)

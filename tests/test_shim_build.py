@@ -20,7 +20,7 @@ def test_shim_exports_the_boundary_symbols():
     assert "getCupdlpLogLevel" in syms                                            # CupdlpWrapper.h:106
     und = subprocess.check_output(["nm", "-D", "--undefined-only", LIB], text=True)
     assert "b200pdlp_solve" in und                                                # forwarded to the C ABI
-    assert "formulateLP_highs" not in syms and "LP_SolvePDHG" not in und.replace("LP_SolvePDHG", "", 0) or True
+    assert "formulateLP_highs" not in syms          # the reference wrapper (and its standard-form builder) is gone
 
 
 @pytest.mark.skipif(not os.path.exists(DRV), reason="oracle/_ref/ref_driver_b200 not built")
@@ -28,9 +28,9 @@ def test_dropin_fails_loudly_without_gpu(engine_lib):
     from highs_b200 import engine
     if engine.device_count() > 0:
         pytest.skip("a GPU is visible")
-    import json
+    from oracle.binding import _parse_json_line
     out = subprocess.run([DRV, "--lp", os.path.join(GOLDEN, "avgas.b2lp"), "--opt", "solver=pdlp", "--opt", "presolve=off"],
                          capture_output=True, text=True)
-    res = json.loads(out.stdout.strip().splitlines()[-1])
+    res = _parse_json_line(out.stdout)
     assert res["run_status"] == -1 and res["model_status_code"] == 4          # HighsStatus::kError, kSolveError
     assert res["pdlp_iteration_count"] == -1
