@@ -198,6 +198,7 @@ struct b200pdlp_problem {
   DevBuf<PdhgState> state;
   PdhgState* hstate = nullptr;     // pinned mirror
   double* houts = nullptr;         // pinned
+  double* hflag = nullptr;         // pinned: time-limit flag of the speculative check
   ncclComm_t comm = nullptr;
   cudaGraphExec_t graph_main = nullptr, graph_small = nullptr;
   int graph_main_passes = 0, graph_small_passes = 0;
@@ -211,6 +212,7 @@ struct b200pdlp_problem {
     if (comm) NcclApi::get().CommDestroy(comm);
     if (hstate) cudaFreeHost(hstate);
     if (houts) cudaFreeHost(houts);
+    if (hflag) cudaFreeHost(hflag);
     if (stream) cudaStreamDestroy(stream);
   }
   ReduceScratch rs(int slot, int len) const {
@@ -379,6 +381,7 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   p->state.alloc(1);
   CUDA_OK(cudaMallocHost(&p->hstate, sizeof(PdhgState)));
   CUDA_OK(cudaMallocHost(&p->houts, kOutsCount * sizeof(double)));
+  CUDA_OK(cudaMallocHost(&p->hflag, 2 * sizeof(double)));
   memset(p->hstate, 0, sizeof(PdhgState));
   CUDA_OK(cudaDeviceSynchronize());
   lap("vectors + scratch");
@@ -504,6 +507,80 @@ static void full_ax(b200pdlp_problem* p, const double* x, double* ax) {
 
 struct CheckResult { Residuals it[2]; bool timed_out = false; };
 
+// host arithmetic on the 29 scalars of the fused (tree-mode) residual sweeps, already in p->houts
+static CheckResult parse_fused_check(b200pdlp_problem* p, bool timed_out_local) {
+  const StdForm& f = p->form;
+  CheckResult cr;
+  cr.timed_out = p->world > 1 ? p->houts[28] > 0.0 : timed_out_local;
+  for (int t = 0; t < 2; t++) {
+    const double* a = p->houts + 10 * t;
+    const double* r = p->houts + 20 + 4 * t;
+    Residuals& R = cr.it[t];
+    R.pobj = a[0] * f.sense + f.offset;
+    R.pfeas = std::sqrt(r[1]);
+    R.dobj = ((r[0] + a[1]) - a[2]) * f.sense + f.offset;
+    R.dfeas = std::sqrt(a[3]);
+    R.gap = R.pobj - R.dobj;
+    R.relgap = std::fabs(R.pobj - R.dobj) / (1.0 + std::fabs(R.pobj) + std::fabs(R.dobj));
+    double dscale = std::sqrt(r[2] + a[4] + a[5]);
+    if (dscale < 1e-8) dscale = 1.0;
+    double pscale = std::sqrt(a[6]);
+    if (pscale < 1e-8) pscale = 1.0;
+    R.pinf_obj = (R.dobj - f.offset) / f.sense / dscale;
+    R.pinf_res = std::sqrt(a[7]) / dscale;
+    R.dinf_obj = (R.pobj - f.offset) / f.sense / pscale;
+    R.dinf_res = std::sqrt(r[3] + a[8] + a[9]) / pscale;
+  }
+  return cr;
+}
+
+// SPECULATIVE check: the same sequence as run_check's tree-mode branch, but enqueued right behind the PDHG passes
+// BEFORE the host has read the state -- every kernel takes buffer parity, pending weight and step sum from the device
+// state block and does nothing unless state.iter has reached state.stop_iter.  The host launch overhead of the ~10
+// kernels hides behind the running pass graph, one synchronisation per check interval remains, and on several GPUs
+// the barriers inside the check no longer wait for every rank's host thread.
+static bool can_speculate_check(const b200pdlp_problem* p) { return !p->ordered && (p->world == 1 || (p->p2p && p->p2p_pull)); }
+
+static void enqueue_check_dev(b200pdlp_problem* p, bool timed_out_local) {
+  cudaStream_t s = p->stream;
+  PdhgState* st = p->state.p;
+  const int n = p->nl, ml = p->ml;
+  if (p->world > 1) {
+    launch_reduce_part_p2p(s, n, p->aty[0].p, p->peers, p->world, p->rank, p->seg_len, 1, st, 1);   // if accepted_last
+    p->launches++;
+  }
+  launch_average_dev(s, n, p->x[0].p, p->x[1].p, p->xsum.p, p->xavg.p, st);
+  launch_average_dev(s, ml, p->y[0].p, p->y[1].p, p->ysum.p, p->yavg.p, st);
+  launch_check_clear(s, st);
+  p->launches += 3;
+  if (p->world == 1) {
+    launch_spmv_plain(s, p->A.dev, p->xavg.p, p->axavg.p, st);
+    launch_spmv_plain(s, p->AT.dev, p->yavg.p, p->atyavg.p, st);
+    p->launches += 2;
+  } else {
+    launch_push_shard(s, p->xavg.p, p->nl, p->peers, p->world, p->rank, p->seg_len, st);
+    launch_spmv_partial_aty(s, p->AT.dev, nullptr, p->yavg.p, p->yavg.p, p->recv.p, p->at_outpos.p, st);
+    launch_p2p_exchange(s, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p, st);
+    launch_spmv_plain(s, p->A.dev, p->xfull.p, p->axavg.p, st);
+    launch_reduce_part_p2p(s, n, p->atyavg.p, p->peers, p->world, p->rank, p->seg_len, 2, st, 0);
+    p->launches += 5;
+  }
+  double* o = p->outs.p;
+  const bool one_aty = p->world > 1;   // multi-GPU keeps a single current A^T y shard
+  ColIter c0{p->x[0].p, p->aty[0].p}, calt{p->x[1].p, one_aty ? p->aty[0].p : p->aty[1].p}, c1{p->xavg.p, p->atyavg.p};
+  RowIter r0{p->y[0].p, p->ax[0].p}, ralt{p->y[1].p, p->ax[1].p}, r1{p->yavg.p, p->axavg.p};
+  launch_col_check_fused(s, n, c0, c1, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, p->rs(kSlotChk, n), o, st, calt);
+  launch_row_check_fused(s, ml, r0, r1, p->rhs.p, p->rowscale.p, p->neq_local, p->rs(kSlotChk, ml), o + 20, st, ralt);
+  p->launches += 2;
+  if (p->world > 1) {
+    p->hflag[0] = timed_out_local ? 1.0 : 0.0;
+    CUDA_OK(cudaMemcpyAsync(o + 28, p->hflag, sizeof(double), cudaMemcpyHostToDevice, s));
+    launch_p2p_exchange(s, o, 29, p->peers, p->world, p->rank, p->epochs.p, p->fault.p, st);
+    p->launches++;
+  }
+  CUDA_OK(cudaMemcpyAsync(p->houts, o, 29 * sizeof(double), cudaMemcpyDeviceToHost, s));
+}
+
 // PDHG_Compute_Average_Iterate + PDHG_Compute_Residuals + PDHG_Compute_Infeas_Residuals
 // (cupdlp_step.c:377-420, cupdlp_solver.c:473-529, :433-471) for current and average iterate
 static CheckResult run_check(b200pdlp_problem* p, bool timed_out_local) {
@@ -561,27 +638,7 @@ static CheckResult run_check(b200pdlp_problem* p, bool timed_out_local) {
       allreduce_small(p, o, 29);
     }
     pull_outs(p, 29);
-    CheckResult cr;
-    cr.timed_out = p->world > 1 ? p->houts[28] > 0.0 : timed_out_local;
-    for (int t = 0; t < 2; t++) {
-      const double* a = p->houts + 10 * t;
-      const double* r = p->houts + 20 + 4 * t;
-      Residuals& R = cr.it[t];
-      R.pobj = a[0] * f.sense + f.offset;
-      R.pfeas = std::sqrt(r[1]);
-      R.dobj = ((r[0] + a[1]) - a[2]) * f.sense + f.offset;
-      R.dfeas = std::sqrt(a[3]);
-      R.gap = R.pobj - R.dobj;
-      R.relgap = std::fabs(R.pobj - R.dobj) / (1.0 + std::fabs(R.pobj) + std::fabs(R.dobj));
-      double dscale = std::sqrt(r[2] + a[4] + a[5]);
-      if (dscale < 1e-8) dscale = 1.0;
-      double pscale = std::sqrt(a[6]);
-      if (pscale < 1e-8) pscale = 1.0;
-      R.pinf_obj = (R.dobj - f.offset) / f.sense / dscale;
-      R.pinf_res = std::sqrt(a[7]) / dscale;
-      R.dinf_obj = (R.pobj - f.offset) / f.sense / pscale;
-      R.dinf_res = std::sqrt(r[3] + a[8] + a[9]) / pscale;
-    }
+    CheckResult cr = parse_fused_check(p, timed_out_local);
     return cr;
   }
   launch_col_check_a(s, n, 2, c0, c1, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, p->rs(kSlotChk, n), o);
@@ -879,6 +936,8 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   CheckResult chk;
   int term = B200PDLP_TIMELIMIT_OR_ITERLIMIT, term_iterate = 0, restarts = 0;
   bool have_check = false;
+  bool have_spec = false, spec_flag = false;   // a speculative check already produced the next check's scalars
+  const bool speculate = can_speculate_check(p);
   CudaEvent ev0, ev1, evl0, evl1;
   double iter_ms = 0.0;
   CUDA_OK(cudaEventRecord(evl0, s));
@@ -888,7 +947,8 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   while (h->iter < prm.iter_limit) {
     const double elapsed = std::chrono::duration<double>(clk::now() - t_loop).count();
     const bool timed_out_local = t_lim > 0 && elapsed > t_lim;
-    chk = run_check(p, timed_out_local);
+    if (have_spec) { chk = parse_fused_check(p, spec_flag); have_spec = false; }
+    else chk = run_check(p, timed_out_local);
     have_check = true;
     const Residuals &L = chk.it[0], &A = chk.it[1];
     if (prm.log_level >= 2)
@@ -923,6 +983,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
     dirty = true;
     if (dirty) push_state(p);
     CUDA_OK(cudaEventRecord(ev0, s));
+    bool have_ev1 = false;
     while (true) {
       const int need = next - h->iter;
       if (need >= p->graph_main_passes / 2 || need > p->graph_small_passes) {
@@ -935,11 +996,18 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
         enqueue_pass(p);
         p->launches += p->kernels_per_pass;
       }
+      if (speculate) {
+        if (!have_ev1) { CUDA_OK(cudaEventRecord(ev1, s)); have_ev1 = true; }
+        const double el = std::chrono::duration<double>(clk::now() - t_loop).count();
+        spec_flag = t_lim > 0 && el > t_lim;
+        enqueue_check_dev(p, spec_flag);
+      }
       pull_state(p);
-      if (h->iter >= next) break;
+      if (h->iter >= next) { have_spec = speculate; break; }
+      have_ev1 = false;
       if (h->step_iter - h->pow_base > kPowTab - p->graph_main_passes - 8) { fill_pow_tables(h); push_state(p); }
     }
-    CUDA_OK(cudaEventRecord(ev1, s));
+    if (!have_ev1) CUDA_OK(cudaEventRecord(ev1, s));
     CUDA_OK(cudaEventSynchronize(ev1));
     float ms = 0.f;
     CUDA_OK(cudaEventElapsedTime(&ms, ev0, ev1));

@@ -75,11 +75,15 @@ primal_step_kernel(int n, PdhgState* __restrict__ st, double* __restrict__ x0, d
 // Rows longer than the long-row threshold live outside the body as segments of kNnzBlk nonzeros
 // (one CTA each, tree-summed); the last segment of a row to finish combines the partial sums in
 // segment order and runs the epilogue.
+// `due` != nullptr: speculative check-iteration launch -- run only if the check iteration has been reached
+__device__ __forceinline__ bool check_not_due(const PdhgState* due) { return due && due->iter < due->stop_iter; }
+
 struct PlainEpilogue {
   static constexpr int NACC = 0;
   const double* __restrict__ in;
   double* __restrict__ out;
-  __device__ bool begin() { return true; }
+  const PdhgState* due;
+  __device__ bool begin() { return !check_not_due(due); }
   __device__ const double* input() const { return in; }
   __device__ void prefetch(int) {}
   __device__ void row(int r, double s, double*) const { out[r] = s; }
@@ -499,7 +503,9 @@ push_part_kernel(PdhgState* st, const double* __restrict__ part, PeerPtrs pp, in
 // check-iteration collectives of the fused path ------------------------------------------------------
 // all-gather of a column shard: store it into every peer's xfull segment
 __global__ void __launch_bounds__(kThreads)
-push_shard_kernel(const double* __restrict__ src, int len, PeerPtrs pp, int world, int rank, int seg_len) {
+push_shard_kernel(const double* __restrict__ src, int len, PeerPtrs pp, int world, int rank, int seg_len,
+                  const PdhgState* due) {
+  if (check_not_due(due)) return;
   const size_t seg = (size_t)rank * seg_len;
   const int npair = len >> 1;
   const int stride = gridDim.x * kThreads;
@@ -513,7 +519,8 @@ push_shard_kernel(const double* __restrict__ src, int len, PeerPtrs pp, int worl
 // peer's mailbox (double-buffered by epoch parity), signals, waits, then adds all ranks' values in rank order
 constexpr int kBigBox = 32;
 __global__ void p2p_exchange_kernel(double* vals, int k, PeerPtrs pp, int world, int rank, unsigned long long* epochs,
-                                    int* fault) {
+                                    int* fault, const PdhgState* due) {
+  if (check_not_due(due)) return;   // identical on every rank
   const int lane = threadIdx.x;
   unsigned long long e = 0;
   if (lane == 0) { e = epochs[10] + 1; epochs[10] = e; }
@@ -544,7 +551,10 @@ __global__ void p2p_exchange_kernel(double* vals, int k, PeerPtrs pp, int world,
 
 // only the fused reduce (check iterations: make the accepted A^T y' current without a primal step)
 __global__ void __launch_bounds__(kThreads)
-reduce_part_p2p_kernel(int len, double* __restrict__ dst, PeerPtrs pp, int world, int rank, int seg_len, int pull) {
+reduce_part_p2p_kernel(int len, double* __restrict__ dst, PeerPtrs pp, int world, int rank, int seg_len, int pull,
+                       const PdhgState* due, int only_if_accepted) {
+  if (check_not_due(due)) return;
+  if (only_if_accepted && !due->accepted_last) return;
   const size_t seg = (size_t)rank * seg_len;
   const int stride = gridDim.x * kThreads;
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < len; i += stride) {
@@ -696,6 +706,31 @@ average_kernel(int len, const double* __restrict__ v, double* __restrict__ sum, 
   }
 }
 
+// Device-parametrised variants for the SPECULATIVE check: enqueued right behind the pass graph, before the host
+// knows the state; they read buffer parity / pending weight / step sum from the state block and do nothing unless
+// the check iteration has been reached.
+__global__ void __launch_bounds__(kThreads)
+average_dev_kernel(int len, const double* __restrict__ v0, const double* __restrict__ v1, double* __restrict__ sum,
+                   double* __restrict__ avg, const PdhgState* __restrict__ st) {
+  if (st->iter < st->stop_iter) return;
+  const double* __restrict__ v = st->cur ? v1 : v0;
+  const bool pending = st->pending != 0;
+  const double w = st->w_pending;
+  const double scale = st->sum_step > 0.0 ? 1.0 / st->sum_step : 1.0;
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < len; i += stride) {
+    double s = sum[i];
+    if (pending) { s = s + w * v[i]; sum[i] = s; }
+    avg[i] = s * scale;
+  }
+}
+// after both averages (and the multi-GPU A^T y materialisation) consumed them
+__global__ void check_clear_kernel(PdhgState* st) {
+  if (st->iter < st->stop_iter) return;
+  st->pending = 0;
+  st->accepted_last = 0;
+}
+
 // column-side pass A for up to two iterates (current, average):
 // PDHG_Compute_Primal_Feasibility's objective (cupdlp_solver.c:23-24),
 // PDHG_Compute_Dual_Feasibility (:69-204) and the norms needed by
@@ -753,7 +788,12 @@ col_check_a_kernel(int n, int nit, ColIter it0, ColIter it1, const double* __res
 __global__ void __launch_bounds__(kThreads)
 col_check_fused_kernel(int n, ColIter it0, ColIter it1, const double* __restrict__ c, const double* __restrict__ lo,
                        const double* __restrict__ up, const double* __restrict__ cs, ReduceScratch rs,
-                       double* __restrict__ out) {
+                       double* __restrict__ out, const PdhgState* __restrict__ st, ColIter alt0) {
+  // st != nullptr (speculative launch): skip unless due; the current iterate is it0 if cur == 0, alt0 otherwise
+  if (st) {
+    if (st->iter < st->stop_iter) return;
+    if (st->cur) it0 = alt0;
+  }
   double acc[20];
 #pragma unroll
   for (int a = 0; a < 20; a++) acc[a] = 0.0;
@@ -787,7 +827,11 @@ col_check_fused_kernel(int n, ColIter it0, ColIter it1, const double* __restrict
 // out per iterate (4): 0 y.b, 1 |primal residual|^2, 2 |y|^2, 3 |[ax]_eq, min([ax]_ineq,0) rowScale|^2
 __global__ void __launch_bounds__(kThreads)
 row_check_fused_kernel(int m, RowIter it0, RowIter it1, const double* __restrict__ b, const double* __restrict__ rsca,
-                       int neq, ReduceScratch rs, double* __restrict__ out) {
+                       int neq, ReduceScratch rs, double* __restrict__ out, const PdhgState* __restrict__ st, RowIter alt0) {
+  if (st) {
+    if (st->iter < st->stop_iter) return;
+    if (st->cur) it0 = alt0;
+  }
   double acc[8];
 #pragma unroll
   for (int a = 0; a < 8; a++) acc[a] = 0.0;
@@ -957,9 +1001,9 @@ void launch_primal_step(cudaStream_t s, int n, PdhgState* st, double* x0, double
   primal_step_kernel<<<ew_grid((n + 1) / 2), kThreads, 0, s>>>(n, st, x0, x1, aty0, aty1, c, lo, up, xsum, rs);
 }
 
-void launch_spmv_plain(cudaStream_t s, const DevSell& A, const double* in, double* out) {
+void launch_spmv_plain(cudaStream_t s, const DevSell& A, const double* in, double* out, const PdhgState* due) {
   if (A.nblocks_body + A.nsegs == 0) return;
-  PlainEpilogue e{in, out};
+  PlainEpilogue e{in, out, due};
   spmv_sell_kernel<PlainEpilogue><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr, nullptr, 0, 0});
 }
 
@@ -982,12 +1026,13 @@ void launch_spmv_primal(cudaStream_t s, const DevSell& A, PdhgState* st, const d
 // multi-GPU K3a: partial A_g' y' into buf (input chosen by the device state)
 struct PartialAtyEpilogue {
   static constexpr int NACC = 0;
-  PdhgState* st;       // nullptr: unconditional (check iterations), input = y0
+  PdhgState* st;       // nullptr: check iterations, input = y0 (then `due` may predicate the launch)
   const double *y0, *y1;
   double* out;
   const int* __restrict__ outpos;
+  const PdhgState* due;
   __device__ bool begin() {
-    if (!st) return true;
+    if (!st) return !check_not_due(due);
     if (st->iter >= st->stop_iter) return false;
     y0 = st->cur ? y0 : y1;
     return true;
@@ -1002,8 +1047,8 @@ struct PartialAtyEpilogue {
 };
 
 void launch_spmv_partial_aty(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
-                             double* part, const int* outpos) {
-  PartialAtyEpilogue e{st, y0, y1, part, outpos};
+                             double* part, const int* outpos, const PdhgState* due) {
+  PartialAtyEpilogue e{st, y0, y1, part, outpos, due};
   spmv_sell_kernel<PartialAtyEpilogue><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr, nullptr, 0, 0});
 }
 
@@ -1038,16 +1083,17 @@ void launch_primal_shard_p2p(cudaStream_t s, int len, PdhgState* st, double* xs0
 void launch_push_part(cudaStream_t s, PdhgState* st, const double* part, const PeerPtrs& pp, int world, int rank, int seg_len) {
   push_part_kernel<<<ew_grid((seg_len / 2) * world), kThreads, 0, s>>>(st, part, pp, world, rank, seg_len);
 }
-void launch_push_shard(cudaStream_t s, const double* src, int len, const PeerPtrs& pp, int world, int rank, int seg_len) {
-  push_shard_kernel<<<ew_grid((len + 1) / 2), kThreads, 0, s>>>(src, len, pp, world, rank, seg_len);
+void launch_push_shard(cudaStream_t s, const double* src, int len, const PeerPtrs& pp, int world, int rank, int seg_len,
+                       const PdhgState* due) {
+  push_shard_kernel<<<ew_grid((len + 1) / 2), kThreads, 0, s>>>(src, len, pp, world, rank, seg_len, due);
 }
 void launch_p2p_exchange(cudaStream_t s, double* vals, int k, const PeerPtrs& pp, int world, int rank,
-                         unsigned long long* epochs, int* fault) {
-  p2p_exchange_kernel<<<1, 32, 0, s>>>(vals, k, pp, world, rank, epochs, fault);
+                         unsigned long long* epochs, int* fault, const PdhgState* due) {
+  p2p_exchange_kernel<<<1, 32, 0, s>>>(vals, k, pp, world, rank, epochs, fault, due);
 }
 void launch_reduce_part_p2p(cudaStream_t s, int len, double* dst, const PeerPtrs& pp, int world, int rank, int seg_len,
-                            int pull) {
-  reduce_part_p2p_kernel<<<ew_grid(len), kThreads, 0, s>>>(len, dst, pp, world, rank, seg_len, pull);
+                            int pull, const PdhgState* due, int only_if_accepted) {
+  reduce_part_p2p_kernel<<<ew_grid(len), kThreads, 0, s>>>(len, dst, pp, world, rank, seg_len, pull, due, only_if_accepted);
 }
 void launch_p2p_barrier(cudaStream_t s, int mode, PdhgState* st, const double* partials, int nb, const PeerPtrs& pp,
                         int world, int rank, int seg_len, int shard_len, unsigned long long* epochs, int* fault) {
@@ -1078,13 +1124,20 @@ void launch_col_check_a(cudaStream_t s, int n, int nit, ColIter a, ColIter b, co
   col_check_a_kernel<<<ew_grid(n), kThreads, 0, s>>>(n, nit, a, b, c, lo, up, cs, rs, out);
 }
 void launch_col_check_fused(cudaStream_t s, int n, ColIter a, ColIter b, const double* c, const double* lo,
-                            const double* up, const double* cs, ReduceScratch rs, double* out) {
-  col_check_fused_kernel<<<ew_grid(n), kThreads, 0, s>>>(n, a, b, c, lo, up, cs, rs, out);
+                            const double* up, const double* cs, ReduceScratch rs, double* out, const PdhgState* st,
+                            ColIter alt) {
+  col_check_fused_kernel<<<ew_grid(n), kThreads, 0, s>>>(n, a, b, c, lo, up, cs, rs, out, st, alt);
 }
 void launch_row_check_fused(cudaStream_t s, int m, RowIter a, RowIter b, const double* rhs, const double* rsca, int neq,
-                            ReduceScratch rs, double* out) {
-  row_check_fused_kernel<<<ew_grid(m), kThreads, 0, s>>>(m, a, b, rhs, rsca, neq, rs, out);
+                            ReduceScratch rs, double* out, const PdhgState* st, RowIter alt) {
+  row_check_fused_kernel<<<ew_grid(m), kThreads, 0, s>>>(m, a, b, rhs, rsca, neq, rs, out, st, alt);
 }
+void launch_average_dev(cudaStream_t s, int len, const double* v0, const double* v1, double* sum, double* avg,
+                        const PdhgState* st) {
+  if (len == 0) return;
+  average_dev_kernel<<<ew_grid(len), kThreads, 0, s>>>(len, v0, v1, sum, avg, st);
+}
+void launch_check_clear(cudaStream_t s, PdhgState* st) { check_clear_kernel<<<1, 1, 0, s>>>(st); }
 void launch_row_check_a(cudaStream_t s, int m, int nit, RowIter a, RowIter b, const double* rhs,
                         const double* rsca, int neq, int row_offset, ReduceScratch rs, double* out) {
   row_check_a_kernel<<<ew_grid(m), kThreads, 0, s>>>(m, nit, a, b, rhs, rsca, neq, row_offset, rs, out);

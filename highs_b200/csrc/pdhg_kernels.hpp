@@ -10,14 +10,14 @@ struct RowIter { const double* y; const double* ax; };    // one dual-side itera
 void launch_primal_step(cudaStream_t s, int n, PdhgState* st, double* x0, double* x1, const double* aty0,
                         const double* aty1, const double* c, const double* lo, const double* up, double* xsum,
                         ReduceScratch rs);
-void launch_spmv_plain(cudaStream_t s, const DevSell& A, const double* in, double* out);
+void launch_spmv_plain(cudaStream_t s, const DevSell& A, const double* in, double* out, const PdhgState* due = nullptr);
 void launch_spmv_dual(cudaStream_t s, const DevSell& A, PdhgState* st, const double* x0, const double* x1,
                       double* y0, double* y1, double* ax0, double* ax1, const double* b, double* ysum,
                       int neq, int row_offset, ReduceScratch rs);
 void launch_spmv_primal(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
                         const double* x0, const double* x1, double* aty0, double* aty1, ReduceScratch rs);
 void launch_spmv_partial_aty(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
-                             double* part, const int* outpos);
+                             double* part, const int* outpos, const PdhgState* due = nullptr);
 void launch_spmv_dual_mg(cudaStream_t s, const DevSell& A, PdhgState* st, const double* xfull, double* y0, double* y1,
                          double* ax0, double* ax1, const double* b, double* ysum, int neq, ReduceScratch rs);
 void launch_primal_shard(cudaStream_t s, int len, PdhgState* st, double* xs0, double* xs1, double* aty_s,
@@ -30,12 +30,13 @@ void launch_stash_scalars(cudaStream_t s, int nv, PdhgState* st, const double* p
 void launch_primal_shard_p2p(cudaStream_t s, int len, PdhgState* st, double* xs0, double* xs1, double* aty_s,
                              const PeerPtrs& pp, int world, int rank, int seg_len, int pull, const double* c,
                              const double* lo, const double* up, double* xsum, ReduceScratch rs);
-void launch_push_shard(cudaStream_t s, const double* src, int len, const PeerPtrs& pp, int world, int rank, int seg_len);
+void launch_push_shard(cudaStream_t s, const double* src, int len, const PeerPtrs& pp, int world, int rank, int seg_len,
+                       const PdhgState* due = nullptr);
 void launch_p2p_exchange(cudaStream_t s, double* vals, int k, const PeerPtrs& pp, int world, int rank,
-                         unsigned long long* epochs, int* fault);
+                         unsigned long long* epochs, int* fault, const PdhgState* due = nullptr);
 void launch_push_part(cudaStream_t s, PdhgState* st, const double* part, const PeerPtrs& pp, int world, int rank, int seg_len);
 void launch_reduce_part_p2p(cudaStream_t s, int len, double* dst, const PeerPtrs& pp, int world, int rank, int seg_len,
-                            int pull);
+                            int pull, const PdhgState* due = nullptr, int only_if_accepted = 0);
 void launch_p2p_barrier(cudaStream_t s, int mode, PdhgState* st, const double* partials, int nb, const PeerPtrs& pp,
                         int world, int rank, int seg_len, int shard_len, unsigned long long* epochs, int* fault);
 void launch_step_rule_mg(cudaStream_t s, PdhgState* st, const double* xfull, int world, int seg_len, int shard_len,
@@ -48,9 +49,14 @@ void launch_average(cudaStream_t s, int len, const double* v, double* sum, doubl
 void launch_col_check_a(cudaStream_t s, int n, int nit, ColIter a, ColIter b, const double* c, const double* lo,
                         const double* up, const double* cs, ReduceScratch rs, double* out);
 void launch_col_check_fused(cudaStream_t s, int n, ColIter a, ColIter b, const double* c, const double* lo,
-                            const double* up, const double* cs, ReduceScratch rs, double* out);
+                            const double* up, const double* cs, ReduceScratch rs, double* out,
+                            const PdhgState* st = nullptr, ColIter alt = ColIter{nullptr, nullptr});
 void launch_row_check_fused(cudaStream_t s, int m, RowIter a, RowIter b, const double* rhs, const double* rsca, int neq,
-                            ReduceScratch rs, double* out);
+                            ReduceScratch rs, double* out, const PdhgState* st = nullptr,
+                            RowIter alt = RowIter{nullptr, nullptr});
+void launch_average_dev(cudaStream_t s, int len, const double* v0, const double* v1, double* sum, double* avg,
+                        const PdhgState* st);
+void launch_check_clear(cudaStream_t s, PdhgState* st);
 void launch_row_check_a(cudaStream_t s, int m, int nit, RowIter a, RowIter b, const double* rhs,
                         const double* rsca, int neq, int row_offset, ReduceScratch rs, double* out);
 void launch_col_check_b(cudaStream_t s, int n, int nit, ColIter a, ColIter b, const double inv_d[2],
