@@ -537,7 +537,7 @@ __global__ void p2p_exchange_kernel(double* vals, int k, PeerPtrs pp, int world,
     unsigned long long seen = 0;
     do {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
-      if (++spins > (1LL << 31)) { *fault = 1; break; }
+      if (++spins > (1LL << 26)) { *fault = 1; break; }
     } while (seen < e);
   }
   __syncwarp();
@@ -623,7 +623,7 @@ p2p_barrier_kernel(int mode, PdhgState* st, const double* __restrict__ partials,
       unsigned long long seen = 0;
       do {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
-        if (++spins > (1LL << 31)) { *fault = 1; break; }   // never hang the device
+        if (++spins > (1LL << 26)) { *fault = 1; break; }   // ~1 min: never hang the device
       } while (seen < e);
     }
     __syncwarp();
