@@ -89,6 +89,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic_bytes(kernel_tag):
+    """dram read + write per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r01_ncu_summary.md, S3 workload); None if the summary is missing"""
+    import re
+    path = os.path.join(ROOT, "profiles", "r01_ncu_summary.md")
+    try:
+        txt = open(path).read()
+    except OSError:
+        return None
+    for sec in txt.split("\n## ")[1:]:
+        if kernel_tag in sec.splitlines()[0]:
+            m = re.search(r"traffic = dram read \+ write\*\* \| ([0-9.]+) (\w+)", sec)
+            if m:
+                return float(m.group(1)) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}.get(m.group(2), 1e6)
+    return None
+
+
 def make_lp(workload):
     from highs_b200.lp import synthetic_lp
     m, n, k, dense = WORKLOADS[workload]
@@ -246,8 +263,10 @@ def main():
     roofline = None
     if world == 1:
         ach = dom_bytes / (k_us[dom] * 1e-6) / 1e9
-        roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                    "kernel": dom_name, "algorithmic_bytes_per_launch": dom_bytes, "us_per_launch": k_us[dom],
+        traffic = ncu_traffic_bytes("DualEpilogue" if dom == 1 else "PrimalEpilogue") if args.workload == "S3" else None
+        roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                    "traffic_source": "profiles/r01_ncu_summary.md (ncu --set full, same kernel, S3)" if traffic else None,
+                    "kernel": dom_name.replace("spmv_blocked", "spmv_sell_kernel"), "algorithmic_bytes_per_launch": dom_bytes, "us_per_launch": k_us[dom],
                     "peak_source": peak_src,
                     "per_kernel_us": {"K1_primal_step": k_us[0], "K2_Ax_dual": k_us[1], "K3_ATy_interaction": k_us[2]},
                     "per_kernel_gbs": {"K1": B["k1"] / k_us[0] / 1e3, "K2": B["k2"] / k_us[1] / 1e3, "K3": B["k3"] / k_us[2] / 1e3},
