@@ -922,14 +922,14 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   // ---- graphs: one check interval of passes, and a short one for top-ups after rejected steps
   // a few spare passes per replay: a rejected line-search step then still reaches the next check iteration inside
   // the same replay (spare passes are no-ops once state.iter == state.stop_iter) instead of costing a host round trip
-  const int want_main = prm.graph_passes > 0 ? prm.graph_passes : interval + 4;
+  const int want_main = std::min(prm.graph_passes > 0 ? prm.graph_passes : interval + 4, kPowTab - 16);   // the step-rule tables cover one replay
   if (!p->graph_main || p->graph_main_passes != want_main) {
     if (p->graph_main) cudaGraphExecDestroy(p->graph_main);
     p->graph_main = capture_passes(p, want_main);
     p->graph_main_passes = want_main;
   }
   if (!p->graph_small) { p->graph_small_passes = 4; p->graph_small = capture_passes(p, 4); }
-  p->kernels_per_pass = p->world == 1 ? 4 : 6;   // ours; NCCL kernels not counted
+  p->kernels_per_pass = p->world == 1 ? 4 : ((p->p2p && p->p2p_pull) ? 5 : 6);   // ours; NCCL kernels not counted
 
   const double tol_p = prm.tol_primal * (1.0 + f.norm_rhs), tol_d = prm.tol_dual * (1.0 + f.norm_cost);
   RestartMemo memo;
