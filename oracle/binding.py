@@ -34,7 +34,7 @@ class OrcLp(C.Structure):
 class OrcParams(C.Structure):
     _fields_ = [("iter_limit", C.c_int), ("tol_primal", C.c_double), ("tol_dual", C.c_double),
                 ("tol_gap", C.c_double), ("time_limit", C.c_double), ("scaling", C.c_int),
-                ("adaptive_step", C.c_int), ("restart", C.c_int)]
+                ("adaptive_step", C.c_int), ("restart", C.c_int), ("interaction_row_side", C.c_int)]
 
 
 class OrcForm(C.Structure):
@@ -95,7 +95,7 @@ def _mk_lp(lp):
 def default_params(**kw) -> dict:
     """Defaults = what HiGHS passes for default options (CupdlpWrapper.cpp:642-717)."""
     p = dict(iter_limit=2147483647, tol_primal=1e-7, tol_dual=1e-7, tol_gap=1e-7, time_limit=0.0,
-             scaling=1, adaptive_step=1, restart=1)
+             scaling=1, adaptive_step=1, restart=1, interaction_row_side=0)
     p.update(kw)
     return p
 
@@ -114,7 +114,7 @@ def solve(lp, warm=None, trace_cap=0, **kw) -> dict:
     res = OrcResult(_p(cv, _dp), _p(cd, _dp), _p(rv, _dp), _p(rd, _dp), vv, dv, 0, 0, 0,
                     0, 0, 0, 0, 0, 0, _p(tr, _dp) if trace_cap else None, trace_cap, 0)
     prm = OrcParams(p["iter_limit"], p["tol_primal"], p["tol_dual"], p["tol_gap"], p["time_limit"],
-                    p["scaling"], p["adaptive_step"], p["restart"])
+                    p["scaling"], p["adaptive_step"], p["restart"], p["interaction_row_side"])
     rc = L.orc_solve(C.byref(clp), C.byref(prm), C.byref(res))
     assert rc == 0
     return dict(col_value=cv, col_dual=cd, row_value=rv, row_dual=rd, term_code=res.term_code,

@@ -443,7 +443,7 @@ static void dual_step(orc_state* s, double* yn, const double* y, const double* a
 }
 
 /* cupdlp_compute_interaction_and_movement (CPU branch), cupdlp_linalg.c:772-801 */
-static void movement_interaction(orc_state* s, double* mov, double* inter) {
+static void movement_interaction(orc_state* s, double* mov, double* inter, int row_side) {
   int k = s->iter % 2, k1 = (s->iter + 1) % 2;
   double rb = sqrt(s->beta);
   double* b = s->bn;
@@ -455,12 +455,17 @@ static void movement_interaction(orc_state* s, double* mov, double* inter) {
   double* b2 = s->bn2;
   vcopy(s->n, b2, s->aty[k]); vaxpy(s->n, -1.0, s->aty[k1], b2);
   *inter = vdot(s->n, b, b2);
+  if (row_side) {   /* Δy'(AΔx): same number in exact arithmetic (cupdlp_step.c:259-264) */
+    double acc = 0.0;
+    for (int i = 0; i < s->m; i++) acc += (s->ax[k][i] - s->ax[k1][i]) * bm[i];
+    *inter = acc;
+  }
   *mov = dx * 0.5 * rb + dy / (2.0 * rb);
 }
 
 /* PDHG_Update_Iterate_Adaptive_Step_Size, cupdlp_step.c:215-310.
  * returns 1 if the time limit fired on a rejected step (CUPDLP_CHECK_TIMEOUT) */
-static int adaptive_update(orc_state* s, double t_begin, double t_lim) {
+static int adaptive_update(orc_state* s, double t_begin, double t_lim, int row_side) {
   int k = s->iter % 2, k1 = (s->iter + 1) % 2;
   double eta = sqrt(s->tau * s->sigma);
   int done = 0;
@@ -472,7 +477,7 @@ static int adaptive_update(orc_state* s, double t_begin, double t_lim) {
     dual_step(s, s->y[k1], s->y[k], s->ax[k], s->ax[k1], sigma);
     orc_aty(s->f, s->y[k1], s->aty[k1]);
     double mov, inter;
-    movement_interaction(s, &mov, &inter);
+    movement_interaction(s, &mov, &inter, row_side);
     double lim = inter != 0.0 ? mov / fabs(inter) : INFINITY;
     if (eta <= lim) done = 1;
     else if (t_lim > 0 && now_seconds() - t_begin > t_lim) return 1;
@@ -641,7 +646,7 @@ int orc_solve(const orc_lp* lp, const orc_params* p, orc_result* r) {
       trace_row(r, s, rs);
     }
     if (p->adaptive_step) {
-      if (adaptive_update(s, t_begin, t_lim)) { r->term_code = ORC_TIMELIMIT_OR_ITERLIMIT; break; }
+      if (adaptive_update(s, t_begin, t_lim, p->interaction_row_side)) { r->term_code = ORC_TIMELIMIT_OR_ITERLIMIT; break; }
     } else {
       constant_update(s);
     }

@@ -45,6 +45,9 @@ typedef struct {
   int scaling;              /* 1 = Ruiz(10)+Pock-Chambolle(1) */
   int adaptive_step;        /* 1 = adaptive line search, 0 = fixed (power method) */
   int restart;              /* 1 = cuPDLP "GPU" restart scheme */
+  int interaction_row_side; /* 0 = reference: (x-x').(A'y-A'y'), cupdlp_linalg.c:797; 1 = (Ax-Ax').(y-y'), the
+                               algebraically identical form cupdlp_step.c:259-264 calls dInteractiony -- what the
+                               multi-GPU engine uses; not bit-identical to the reference */
 } orc_params;
 
 /* standard form produced by formulate+scale (host arrays owned by the struct) */

@@ -75,3 +75,21 @@ def test_oracle_vs_live_reference(oracle):
         assert res["iters"] == ref["pdlp_iteration_count"]
         for k in ("col_value", "col_dual", "row_value", "row_dual"):
             assert np.array_equal(res[k], ref[k]), (trial, k)
+
+
+@pytest.mark.parametrize("name", ["avgas", "afiro", "adlittle", "sctest", "chip", "boxed_row", "restart_lp"])
+def test_row_side_interaction_is_equivalent(oracle, name):
+    """The multi-GPU engine takes the step rule's interaction on the row side, (Ax-Ax').(y-y'), instead of the
+    reference's (x-x').(A'y-A'y') -- the same number in exact arithmetic (cupdlp_step.c:259-264 computes it as
+    dInteractiony).  On the CPU oracle: same termination, and the optimum agrees to the solver tolerance."""
+    import os
+    from conftest import GOLDEN
+    from highs_b200.lp import read_b2lp
+    lp = read_b2lp(os.path.join(GOLDEN, name + ".b2lp"))
+    a = oracle.solve(lp)
+    b = oracle.solve(lp, interaction_row_side=1)
+    assert a["term_code"] == b["term_code"] == 0
+    oa, ob_ = lp.objectiveValue(a["col_value"]), lp.objectiveValue(b["col_value"])
+    assert abs(oa - ob_) <= 1e-6 * (1 + abs(oa))
+    # rounding noise in the interaction is amplified by cancellation, so restarts can land on different checks
+    assert 0.5 * a["iters"] <= b["iters"] <= 2 * a["iters"]
