@@ -286,60 +286,20 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   scale(p->form, prm.scaling != 0);
   lap("scale");
   StdForm& f = p->form;
-  std::vector<int> bounds = partition_rows(f, world);
-  p->r0 = bounds[rank]; p->r1 = bounds[rank + 1];
-  p->n = f.n; p->m = f.m; p->ml = p->r1 - p->r0;
+  {
+    // host layout (row block, device orderings, sliced-ELL of A_g and A_g^T): host_prep.cpp build_layout
+    HostLayout L;
+    build_layout(f, rank, world, prm.ordered_max, L, lap);
+    p->r0 = L.r0; p->r1 = L.r1; p->ml = L.ml; p->neq_local = L.neq_local; p->ordered = L.ordered;
+    p->n = f.n; p->m = f.m;
+    p->nl = L.nl; p->nl_real = L.nl_real; p->c0 = L.c0; p->shard_len = L.shard_len; p->seg_len = L.seg_len;
+    p->csr_local = std::move(L.csr_local);
+    p->rperm = std::move(L.rperm); p->rinv = std::move(L.rinv);
+    p->cperm = std::move(L.cperm); p->cinv = std::move(L.cinv);
+    p->A.host = std::move(L.A); p->AT.host = std::move(L.AT);
+    if (world > 1) p->at_outpos.from(L.at_outpos);
+  }
   const int n = p->n, ml = p->ml;
-  {
-    const int omax = prm.ordered_max == 0 ? 4096 : prm.ordered_max;
-    p->ordered = world == 1 && omax > 0 && std::max(p->n, p->m) <= omax;
-  }
-  // device ordering: small (ordered-mode) problems keep the reference's row/column order so that
-  // every sum runs in the reference's order; otherwise rows and columns are sorted by length inside
-  // windows so that the sliced-ELL body carries almost no padding.
-  const bool sort = !p->ordered;
-  const int long_threshold = p->ordered ? std::numeric_limits<int>::max() : 512;
-  p->neq_local = std::max(0, std::min(f.neq - p->r0, ml));
-  {
-    Csr at;
-    if (f.rptr.empty()) build_row_index(f);
-    build_row_major(f, p->r0, p->r1, p->csr_local);
-    lap("row-major transpose");
-    build_col_major(f, p->r0, p->r1, at);
-    lap("col-major copy");
-    p->rperm = make_perm(p->csr_local.rowptr, p->neq_local, sort);
-    p->cperm = make_perm(f.cbeg, n, sort);   // GLOBAL column lengths: identical on every rank
-    p->rinv = invert_perm(p->rperm);
-    p->cinv = invert_perm(p->cperm);
-    lap("length sorts");
-    if (world == 1) {
-      p->nl = p->nl_real = n; p->c0 = 0; p->shard_len = n; p->seg_len = n;
-      build_sell(p->csr_local, p->rperm, p->cinv, long_threshold, p->A.host);
-    } else {
-      p->shard_len = ((n + world - 1) / world + 1) & ~1;          // even: 16-byte aligned segments
-      p->seg_len = p->shard_len + 2;
-      p->nl = p->shard_len;
-      p->c0 = rank * p->shard_len;
-      p->nl_real = std::max(0, std::min(p->shard_len, n - p->c0));
-      std::vector<int> colpos(n);                                   // old column -> position in the segmented x
-      for (int j = 0; j < n; j++) colpos[j] = (int)seg_pos(p, p->cinv[j]);
-      build_sell(p->csr_local, p->rperm, colpos, long_threshold, p->A.host);
-    }
-    if (world == 1) {
-      build_sell(at, p->cperm, p->rinv, long_threshold, p->AT.host);
-    } else {
-      // rows of A_g^T in an order sorted by LOCAL length (windows of the global device order, so that
-      // nearby outputs stay nearby); the kernel writes through at_outpos
-      std::vector<int> ordered_rowptr(n + 1, 0);
-      for (int j = 0; j < n; j++) ordered_rowptr[j + 1] = ordered_rowptr[j] + (at.rowptr[p->cperm[j] + 1] - at.rowptr[p->cperm[j]]);
-      std::vector<int> local = make_perm(ordered_rowptr, n, true);   // positions in device order
-      std::vector<int> at_perm(n), outpos(n);
-      for (int r = 0; r < n; r++) { at_perm[r] = p->cperm[local[r]]; outpos[r] = (int)seg_pos(p, local[r]); }
-      build_sell(at, at_perm, p->rinv, long_threshold, p->AT.host);
-      p->at_outpos.from(outpos);
-    }
-  }
-  lap("sliced-ELL build");
   CUDA_OK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   p->A.upload();
   p->AT.upload();
@@ -1531,6 +1491,48 @@ int b200pdlp_form_get_row_map(const b200pdlp_form* f, int32_t* row_new_idx, int3
   memcpy(row_new_idx, f->f.row_new_idx.data(), (size_t)f->f.m * sizeof(int));
   memcpy(row_class, f->f.row_class.data(), (size_t)f->f.m * sizeof(int));
   return B200PDLP_OK;
+}
+
+int b200pdlp_form_layout_eval(b200pdlp_form* fh, int32_t rank, int32_t world, int32_t ordered_max, const double* x,
+                              const double* y, double* ax, double* aty, double stats[12]) {
+  return guarded([&] {
+    if (!fh || !x || !y || !ax || !aty || !stats) throw Error(B200PDLP_ERR_ARG, "null argument");
+    if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) throw Error(B200PDLP_ERR_ARG, "bad rank/world");
+    StdForm& f = fh->f;
+    const bool timing = getenv("B200PDLP_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto tl = t0;
+    HostLayout L;
+    build_layout(f, rank, world, ordered_max, L, [&](const char* what) {
+      if (!timing) return;
+      auto t1 = std::chrono::steady_clock::now();
+      fprintf(stderr, "[b200pdlp layout] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - tl).count());
+      tl = t1;
+    });
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    const int n = f.n, ml = L.ml;
+    // x in the kernel-facing layout: device column order, segmented when world > 1
+    std::vector<double> xin((size_t)L.world * L.seg_len + 8, 0.0), out_rows((size_t)std::max(ml, 1), 0.0);
+    for (int j = 0; j < n; j++) xin[L.seg_pos(j)] = x[L.cperm[j]];
+    sell_apply_host(L.A, xin.data(), out_rows.data());
+    for (int i = 0; i < ml; i++) ax[L.r0 + L.rperm[i]] = out_rows[i];
+    // y of the local rows in device row order
+    std::vector<double> yin((size_t)std::max(ml, 1) + 8, 0.0), out_cols((size_t)std::max(n, 1), 0.0);
+    for (int i = 0; i < ml; i++) yin[i] = y[L.r0 + L.rperm[i]];
+    sell_apply_host(L.AT, yin.data(), out_cols.data());
+    if (world == 1) {
+      for (int j = 0; j < n; j++) aty[L.cperm[j]] = out_cols[j];
+    } else {
+      // the kernel writes body row r to part[at_outpos[r]]; undo the segmentation, then the column order
+      std::vector<double> part((size_t)L.world * L.seg_len, 0.0);
+      for (int r = 0; r < n; r++) part[L.at_outpos[r]] = out_cols[r];
+      for (int j = 0; j < n; j++) aty[L.cperm[j]] = part[L.seg_pos(j)];
+    }
+    stats[0] = L.r0; stats[1] = L.r1; stats[2] = L.ordered ? 1 : 0;
+    stats[3] = (double)L.A.padded; stats[4] = (double)L.A.long_rows.size(); stats[5] = (double)L.A.segs.size();
+    stats[6] = (double)L.AT.padded; stats[7] = (double)L.AT.long_rows.size(); stats[8] = (double)L.AT.segs.size();
+    stats[9] = L.shard_len; stats[10] = L.seg_len; stats[11] = ms;
+  });
 }
 
 int b200pdlp_partition_rows(const b200pdlp_lp* lp, int32_t world, int32_t* bounds) {

@@ -509,4 +509,85 @@ void build_sell(const Csr& a, const std::vector<int>& perm, const std::vector<in
   out.lval.resize(out.lval.size() + 8, 0.0);
 }
 
+void build_layout(StdForm& f, int rank, int world, int ordered_max, HostLayout& L,
+                  const std::function<void(const char*)>& lap) {
+  auto mark = [&](const char* what) { if (lap) lap(what); };
+  L = HostLayout();
+  L.rank = rank; L.world = world;
+  const std::vector<int> bounds = partition_rows(f, world);
+  L.r0 = bounds[rank]; L.r1 = bounds[rank + 1];
+  L.ml = L.r1 - L.r0;
+  const int n = f.n, ml = L.ml;
+  {
+    const int omax = ordered_max == 0 ? 4096 : ordered_max;
+    L.ordered = world == 1 && omax > 0 && std::max(f.n, f.m) <= omax;
+  }
+  const bool sort = !L.ordered;
+  const int long_threshold = L.ordered ? std::numeric_limits<int>::max() : 512;
+  L.neq_local = std::max(0, std::min(f.neq - L.r0, ml));
+  Csr at;
+  if (f.rptr.empty()) build_row_index(f);
+  build_row_major(f, L.r0, L.r1, L.csr_local);
+  mark("row-major transpose");
+  build_col_major(f, L.r0, L.r1, at);
+  mark("col-major copy");
+  L.rperm = make_perm(L.csr_local.rowptr, L.neq_local, sort);
+  L.cperm = make_perm(f.cbeg, n, sort);   // GLOBAL column lengths: identical on every rank
+  L.rinv = invert_perm(L.rperm);
+  L.cinv = invert_perm(L.cperm);
+  mark("length sorts");
+  if (world == 1) {
+    L.nl = L.nl_real = n; L.c0 = 0; L.shard_len = n; L.seg_len = n;
+    build_sell(L.csr_local, L.rperm, L.cinv, long_threshold, L.A);
+    build_sell(at, L.cperm, L.rinv, long_threshold, L.AT);
+  } else {
+    L.shard_len = ((n + world - 1) / world + 1) & ~1;          // even: 16-byte aligned segments
+    L.seg_len = L.shard_len + 2;
+    L.nl = L.shard_len;
+    L.c0 = rank * L.shard_len;
+    L.nl_real = std::max(0, std::min(L.shard_len, n - L.c0));
+    std::vector<int> colpos(n);                                   // old column -> position in the segmented x
+    for (int j = 0; j < n; j++) colpos[j] = (int)L.seg_pos(L.cinv[j]);
+    build_sell(L.csr_local, L.rperm, colpos, long_threshold, L.A);
+    // rows of A_g^T in an order sorted by LOCAL length (windows of the global device order, so that
+    // nearby outputs stay nearby); the kernel writes through at_outpos
+    std::vector<int> ordered_rowptr(n + 1, 0);
+    for (int j = 0; j < n; j++) ordered_rowptr[j + 1] = ordered_rowptr[j] + (at.rowptr[L.cperm[j] + 1] - at.rowptr[L.cperm[j]]);
+    const std::vector<int> local = make_perm(ordered_rowptr, n, true);   // positions in device order
+    std::vector<int> at_perm(n);
+    L.at_outpos.resize(n);
+    for (int r = 0; r < n; r++) { at_perm[r] = L.cperm[local[r]]; L.at_outpos[r] = (int)L.seg_pos(local[r]); }
+    build_sell(at, at_perm, L.rinv, long_threshold, L.AT);
+  }
+  mark("sliced-ELL build");
+}
+
+void sell_apply_host(const SellMatrix& a, const double* xin, double* out) {
+  const int nslices = (int)a.slices.size();
+  for (int s = 0; s < nslices; s++) {
+    const SellMatrix::Slice& sl = a.slices[s];
+    for (int l = 0; l < 32; l++) {
+      const int row = s * 32 + l;
+      if (row >= a.nrows) continue;
+      if ((sl.skipmask >> l) & 1u) continue;
+      double acc = 0.0;
+      for (int k = 0; k < sl.len; k++) {
+        const size_t q = (size_t)sl.ptr + 32 * (size_t)k + l;
+        acc += a.val[q] * xin[a.col[q]];
+      }
+      out[row] = acc;
+    }
+  }
+  for (const SellMatrix::LongRow& lr : a.long_rows) {
+    double total = 0.0;
+    for (int sg = 0; sg < lr.nseg; sg++) {
+      const SellMatrix::Seg& g = a.segs[lr.first_seg + sg];
+      double part = 0.0;
+      for (int q = g.nnz_begin; q < g.nnz_end; q++) part += a.lval[q] * xin[a.lcol[q]];
+      total += part;
+    }
+    out[lr.row] = total;
+  }
+}
+
 }  // namespace b200

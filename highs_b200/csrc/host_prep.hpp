@@ -8,6 +8,7 @@
 // and then builds the row-blocked layouts the SpMV kernels stream.
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <vector>
 
 #include "../../include/b200pdlp.h"
@@ -82,5 +83,33 @@ std::vector<int> invert_perm(const std::vector<int>& perm);
 // rows of `a` taken in `perm` order, column ids mapped through `colmap` (old -> new)
 void build_sell(const Csr& a, const std::vector<int>& perm, const std::vector<int>& colmap, int long_threshold,
                 SellMatrix& out);
+
+// Everything the device needs to know about one rank's share of the matrix (host side of
+// b200pdlp_problem_create; also what b200pdlp_form_layout_eval evaluates without a GPU).
+//  * rank g of `world` owns rows [r0, r1) (partition_rows) and, when world > 1, the device columns
+//    [c0, c0 + nl_real); n-vectors are held in segments of shard_len entries, full vectors in `world`
+//    segments of seg_len = shard_len + 2 doubles (the tail carries the pass's scalar sums);
+//  * ordered (single GPU, max(m, n) <= ordered_max): rows/columns keep the reference's order and no row is
+//    split, so that every sum can run in the reference's order; otherwise they are sorted by length in windows.
+struct HostLayout {
+  int rank = 0, world = 1;
+  int r0 = 0, r1 = 0, ml = 0, neq_local = 0;
+  bool ordered = false;
+  Csr csr_local;                  // rows [r0, r1) in standard-form order
+  std::vector<int> rperm, rinv;   // device row order: rperm[new] = old local row
+  std::vector<int> cperm, cinv;   // device column order: cperm[new] = old column (same on every rank)
+  int nl = 0, nl_real = 0, c0 = 0, shard_len = 0, seg_len = 0;
+  SellMatrix A, AT;               // A_g (rows = local device rows; columns = positions in the segmented x)
+                                  // A_g^T (rows = device columns in AT order; columns = local device rows)
+  std::vector<int> at_outpos;     // world > 1: A_g^T body row -> position in the segmented partial vector
+  // position of device column j in a segmented full vector
+  size_t seg_pos(int j) const { return world == 1 ? (size_t)j : (size_t)(j / shard_len) * seg_len + (size_t)(j % shard_len); }
+};
+// `lap`, if given, is called with a stage name after every stage (timing hook)
+void build_layout(StdForm& f, int rank, int world, int ordered_max, HostLayout& L,
+                  const std::function<void(const char*)>& lap = nullptr);
+// host evaluation of a sliced-ELL matrix exactly as the kernels traverse it (body: lane = row, k ascending;
+// long rows: per-segment partial sums, added in segment order): out[row] for row < nrows
+void sell_apply_host(const SellMatrix& a, const double* xin, double* out);
 
 }  // namespace b200

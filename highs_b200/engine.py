@@ -65,6 +65,7 @@ ABI_SYMBOLS = [
     "b200pdlp_comm_init", "b200pdlp_partition_rows", "b200pdlp_last_error", "b200pdlp_version",
     "b200pdlp_device_count", "b200pdlp_form_create", "b200pdlp_form_destroy", "b200pdlp_form_dims",
     "b200pdlp_form_get_vector", "b200pdlp_form_get_csc", "b200pdlp_form_get_csr", "b200pdlp_form_get_row_map",
+    "b200pdlp_form_layout_eval",
 ]
 
 _lib = None
@@ -128,6 +129,7 @@ def lib():
         L.b200pdlp_form_get_csc.argtypes = [C.c_void_p, _ip, _ip, _dp]
         L.b200pdlp_form_get_row_map.argtypes = [C.c_void_p, _ip, _ip]
         L.b200pdlp_form_get_csr.argtypes = [C.c_void_p, _ip, _ip, _dp]
+        L.b200pdlp_form_layout_eval.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, _dp]
         _lib = L
     return _lib
 
@@ -340,6 +342,43 @@ def host_form(lp: HighsLp, scaling: int = 1) -> dict:
         out.update(cbeg=cbeg, cidx=cidx[:nnz], cval=cval[:nnz], row_new_idx=rni[:m], row_type=rcl[:m],
                    rbeg=rbeg, ridx=ridx[:nnz], rval=rval[:nnz])
         return out
+    finally:
+        L.b200pdlp_form_destroy(h)
+
+
+def host_layout_eval(lp: HighsLp, world: int = 1, ordered_max: int = 0, x=None, y=None, scaling: int = 1, seed: int = 0) -> dict:
+    """Host-only: build every rank's device layout of `lp` (as b200pdlp_problem_create would) and evaluate the
+    sliced-ELL data on the host.  Returns ax (assembled over ranks), aty (summed over ranks in rank order), the
+    per-rank partial A_g'y, the per-rank stats and the standard form's column-wise matrix for checking."""
+    L = lib()
+    clp, keep = make_clp(lp)
+    h = C.c_void_p()
+    _check(L.b200pdlp_form_create(C.byref(clp), scaling, C.byref(h)), "b200pdlp_form_create")
+    try:
+        d = (C.c_int32 * 5)()
+        sc = (C.c_double * 3)()
+        _check(L.b200pdlp_form_dims(h, d, sc), "b200pdlp_form_dims")
+        n, m, nnz = d[0], d[1], d[2]
+        rng = np.random.default_rng(seed)
+        x = rng.standard_normal(max(n, 1)) if x is None else np.ascontiguousarray(x, dtype=np.float64)
+        y = rng.standard_normal(max(m, 1)) if y is None else np.ascontiguousarray(y, dtype=np.float64)
+        ax = np.full(max(m, 1), np.nan)
+        aty = np.zeros(max(n, 1))
+        parts, stats = [], []
+        for g in range(world):
+            part = np.full(max(n, 1), np.nan)
+            st = np.zeros(12)
+            _check(L.b200pdlp_form_layout_eval(h, g, world, ordered_max, _p(x, _dp), _p(y, _dp), _p(ax, _dp), _p(part, _dp),
+                                               _p(st, _dp)), "b200pdlp_form_layout_eval")
+            parts.append(part[:n].copy())
+            stats.append(st)
+            aty[:n] += part[:n]
+        cbeg = np.zeros(n + 1, dtype=np.int32)
+        cidx = np.zeros(max(nnz, 1), dtype=np.int32)
+        cval = np.zeros(max(nnz, 1))
+        _check(L.b200pdlp_form_get_csc(h, _p(cbeg, _ip), _p(cidx, _ip), _p(cval, _dp)), "form_get_csc")
+        return dict(n=n, m=m, nnz=nnz, x=x[:n], y=y[:m], ax=ax[:m], aty=aty[:n], parts=parts, stats=stats,
+                    cbeg=cbeg, cidx=cidx[:nnz], cval=cval[:nnz])
     finally:
         L.b200pdlp_form_destroy(h)
 

@@ -195,6 +195,15 @@ int b200pdlp_form_get_csr(b200pdlp_form* f, int32_t* rowptr, int32_t* col, doubl
 /* row_new_idx[m], row_class[m] by ORIGINAL row (EQ=0, LEQ=1, GEQ=2, BOUND=3) */
 int b200pdlp_form_get_row_map(const b200pdlp_form* f, int32_t* row_new_idx, int32_t* row_class);
 
+/* host-only (no GPU): build the device layout of rank `rank` of `world` exactly as b200pdlp_problem_create does
+ * (row block, length-sorted device orderings, sliced ELL of A_g and A_g', long-row segments, segmented column
+ * positions, the A_g' output map) and evaluate it on the host in the kernels' traversal order.
+ * x[n], y[m] in standard-form order; ax[m]: rows [r0,r1) receive A_g x (others untouched); aty[n] = A_g' y_g.
+ * stats: [0] r0 [1] r1 [2] ordered mode [3] A padded slots [4] A long rows [5] A segments [6] A' padded slots
+ *        [7] A' long rows [8] A' segments [9] shard_len [10] seg_len [11] layout build time, ms */
+int b200pdlp_form_layout_eval(b200pdlp_form* f, int32_t rank, int32_t world, int32_t ordered_max, const double* x,
+                              const double* y, double* ax, double* aty, double stats[12]);
+
 /* host-only helper (no GPU): nnz-balanced contiguous row partition of the
  * formulated LP; bounds[world+1] receives the row offsets */
 int b200pdlp_partition_rows(const b200pdlp_lp* lp, int32_t world, int32_t* bounds);
