@@ -826,6 +826,8 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
     CUDA_OK(cudaMemsetAsync(p->part.p, 0, p->part.n * sizeof(double), s));
     CUDA_OK(cudaMemsetAsync(p->red.p, 0, p->red.n * sizeof(double), s));
     CUDA_OK(cudaMemsetAsync(p->send.p, 0, p->send.n * sizeof(double), s));
+    // fused path: nobody may store into a peer's xfull / recv before that peer has cleared them
+    if (p->p2p) { launch_p2p_exchange(s, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p); p->launches++; }
   }
   {
     std::vector<double> xp(std::max(nl, 1), 0.0), yp(std::max(ml, 1));

@@ -3,14 +3,15 @@
 // What the reference does with cuSPARSE SpMV + a chain of element-wise kernels +
 // cuBLAS reductions that synchronise with the host every iteration
 // (/root/reference/highs/pdlp/cupdlp/cuda/cupdlp_cudalinalg.cu:65-94,253-342,
-//  cupdlp_cuda_kernels.cu:166-189,225-311) is three kernels per PDHG pass here:
+//  cupdlp_cuda_kernels.cu:166-189,225-311) is four launches per PDHG pass here:
 //
 //   K1 primal_step_kernel   x' = proj(x - tau (c - A'y)), |x-x'|^2, xSum += w x
 //   K2 spmv<DualEpilogue>   ax' = A x' fused with y' = proj(y + sigma(b - 2ax' + ax)),
 //                           |y-y'|^2, ySum += w y
-//   K3 spmv<PrimalEpilogue> aty' = A'y' fused with (x-x').(aty-aty'); its last block
+//   K3 spmv<PrimalEpilogue> aty' = A'y' fused with (x-x').(aty-aty')
+//   K4 step_rule_kernel     one CTA adds the block partials of K1..K3 in a fixed order and
 //                           evaluates the adaptive step rule ON THE DEVICE
-//                           (cupdlp_step.c:266-285) and flips the double buffer
+//                           (cupdlp_step.c:266-285), flipping the double buffer on acceptance
 //
 // No host synchronisation inside a pass: every kernel reads the PdhgState block
 // in device memory and is a no-op once state.iter reaches state.stop_iter, so the
@@ -116,8 +117,6 @@ __device__ __forceinline__ double block_sum(double v, double* smem /*[kThreads/3
   return r;
 }
 
-// Writes this block's NACC partial sums; the last block to arrive re-reduces all
-// partials in a fixed order and returns true (sums in out[], valid in thread 0).
 // term bookkeeping used by every reducing kernel
 __device__ __forceinline__ void add_term(double& acc, double term, const ReduceScratch& rs, int a, int i) {
   acc += term;

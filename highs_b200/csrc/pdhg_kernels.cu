@@ -189,8 +189,7 @@ __device__ void step_rule(PdhgState* st, double inter) {
 }
 
 // K3: aty' = A'y' fused with the interaction (x - x').(aty - aty')
-// (cupdlp_compute_interaction_and_movement, cupdlp_linalg.c:772-801); the last
-// block then applies the step rule.
+// (cupdlp_compute_interaction_and_movement, cupdlp_linalg.c:772-801); K4 adds the block partials.
 struct PrimalEpilogue {
   static constexpr int NACC = 1;
   PdhgState* st;
@@ -597,11 +596,16 @@ p2p_barrier_kernel(int mode, PdhgState* st, const double* __restrict__ partials,
       if (lane == 0) tot[a] = s;
     }
     __syncwarp();
+    unsigned long long e = 0;
+    if (lane == 0) { e = epochs[mode] + 1; epochs[mode] = e; }
+    e = __shfl_sync(0xffffffffu, e, 0);
+    // |dx|^2 lives in one of the segment's two tail slots, chosen by the parity of the pass: a rank that has left
+    // barrier 1 may already publish the NEXT pass's |dx|^2 while a slower peer is still adding up this pass's
     const size_t tail = (size_t)rank * seg_len + shard_len;
     // PUSH model: scalars are written into every peer's local memory before the flag, so that after
     // the barrier nobody has to read across NVLink (a remote scalar read costs ~2.5 us each)
     if (mode == 0) {
-      if (lane < world) pp.xfull[lane][tail] = tot[0];
+      if (lane < world) pp.xfull[lane][tail + (e & 1)] = tot[0];
     } else {
       if (lane < world) {
         double* mb = reinterpret_cast<double*>(pp.flags[lane] + 3 * kMaxPeers) + 2 * rank;   // peer's mailbox slot of this rank
@@ -611,9 +615,6 @@ p2p_barrier_kernel(int mode, PdhgState* st, const double* __restrict__ partials,
     }
     // no fence needed: lane h wrote its scalars to peer h and now releases the flag at peer h (st.release.sys
     // orders the lane's own earlier stores); data written by earlier KERNELS is complete at the kernel boundary
-    unsigned long long e = 0;
-    if (lane == 0) { e = epochs[mode] + 1; epochs[mode] = e; }
-    e = __shfl_sync(0xffffffffu, e, 0);
     if (lane < world) {
       const unsigned long long* mine = pp.flags[rank] + mode * kMaxPeers + lane;
       unsigned long long* theirs = pp.flags[lane] + mode * kMaxPeers + rank;
@@ -631,8 +632,9 @@ p2p_barrier_kernel(int mode, PdhgState* st, const double* __restrict__ partials,
     if (mode == 1 && lane == 0) {
       const double* mb = reinterpret_cast<const double*>(pp.flags[rank] + 3 * kMaxPeers);
       double dx2 = 0.0, dy2 = 0.0, inter = 0.0;
+      const size_t slot = (size_t)shard_len + (epochs[0] & 1);   // barrier 0 of THIS pass bumped epochs[0] last
       for (int g = 0; g < world; g++) {   // local memory, fixed rank order
-        dx2 += ld_sys(pp.xfull[rank] + (size_t)g * seg_len + shard_len);
+        dx2 += ld_sys(pp.xfull[rank] + (size_t)g * seg_len + slot);
         dy2 += ld_sys(mb + 2 * g);
         inter += ld_sys(mb + 2 * g + 1);
       }
@@ -1010,6 +1012,7 @@ void launch_spmv_plain(cudaStream_t s, const DevSell& A, const double* in, doubl
 void launch_spmv_dual(cudaStream_t s, const DevSell& A, PdhgState* st, const double* x0, const double* x1,
                       double* y0, double* y1, double* ax0, double* ax1, const double* b, double* ysum,
                       int neq, int row_offset, ReduceScratch rs) {
+  if (A.nblocks_body + A.nsegs == 0) return;   // no rows on this rank: nothing to launch, the partial count is 0
   DualEpilogue e{};
   e.st = st; e.x0 = x0; e.x1 = x1; e.y0 = y0; e.y1 = y1; e.ax0 = ax0; e.ax1 = ax1; e.b = b; e.ysum = ysum;
   e.neq = neq; e.row_offset = row_offset;
@@ -1018,6 +1021,7 @@ void launch_spmv_dual(cudaStream_t s, const DevSell& A, PdhgState* st, const dou
 
 void launch_spmv_primal(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
                         const double* x0, const double* x1, double* aty0, double* aty1, ReduceScratch rs) {
+  if (A.nblocks_body + A.nsegs == 0) return;   // no rows on this rank: nothing to launch, the partial count is 0
   PrimalEpilogue e{};
   e.st = st; e.y0 = y0; e.y1 = y1; e.x0 = x0; e.x1 = x1; e.aty0 = aty0; e.aty1 = aty1;
   spmv_sell_kernel<PrimalEpilogue><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, rs);
@@ -1048,12 +1052,14 @@ struct PartialAtyEpilogue {
 
 void launch_spmv_partial_aty(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
                              double* part, const int* outpos, const PdhgState* due) {
+  if (A.nblocks_body + A.nsegs == 0) return;
   PartialAtyEpilogue e{st, y0, y1, part, outpos, due};
   spmv_sell_kernel<PartialAtyEpilogue><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr, nullptr, 0, 0});
 }
 
 void launch_spmv_dual_mg(cudaStream_t s, const DevSell& A, PdhgState* st, const double* xfull, double* y0, double* y1,
                          double* ax0, double* ax1, const double* b, double* ysum, int neq, ReduceScratch rs) {
+  if (A.nblocks_body + A.nsegs == 0) return;   // no rows on this rank: nothing to launch, the partial count is 0
   DualEpilogueMg e{};
   e.st = st; e.x0 = xfull; e.x1 = xfull; e.y0 = y0; e.y1 = y1; e.ax0 = ax0; e.ax1 = ax1; e.b = b; e.ysum = ysum;
   e.neq = neq; e.row_offset = 0;
