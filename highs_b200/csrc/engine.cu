@@ -264,6 +264,18 @@ static void allreduce_small(b200pdlp_problem* p, double* dptr, int k) {
   else allreduce_inplace(p, dptr, (size_t)k);
 }
 
+// B200PDLP_TIMING=1: wall-clock laps of the non-iterating parts on stderr (where does a short solve's time go)
+struct Laps {
+  bool on = getenv("B200PDLP_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void operator()(const char* phase, const char* what) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[b200pdlp %s] %-28s %8.1f ms\n", phase, what, std::chrono::duration<double, std::milli>(t1 - t).count());
+    t = t1;
+  }
+};
+
 static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, int rank, int world, b200pdlp_problem* p) {
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -794,6 +806,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   memset(h, 0, sizeof(PdhgState));
   h->adaptive = prm.adaptive_step != 0;
   out->trace_len = 0;
+  Laps lap;
 
   // ---- initial point: PDHG_PreSolve (hot start, cupdlp_solver.c:1217-1279) + PDHG_Init_Variables (:531-591)
   std::vector<double> x0(n, 0.0), y0(m, 0.0);
@@ -880,6 +893,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   fill_pow_tables(h);
   push_state(p);
   CUDA_OK(cudaStreamSynchronize(s));
+  lap("solve", "initial point + state");
 
   // ---- graphs: one check interval of passes, and a short one for top-ups after rejected steps
   // a few spare passes per replay: a rejected line-search step then still reaches the next check iteration inside
@@ -892,6 +906,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   }
   if (!p->graph_small) { p->graph_small_passes = 4; p->graph_small = capture_passes(p, 4); }
   p->kernels_per_pass = p->world == 1 ? 4 : ((p->p2p && p->p2p_pull) ? 5 : 6);   // ours; NCCL kernels not counted
+  lap("solve", "graph capture");
 
   const double tol_p = prm.tol_primal * (1.0 + f.norm_rhs), tol_d = prm.tol_dual * (1.0 + f.norm_cost);
   RestartMemo memo;
@@ -981,6 +996,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   CUDA_OK(cudaEventElapsedTime(&loop_ms, evl0, evl1));
   const double solve_seconds = std::chrono::duration<double>(clk::now() - t_loop).count();
   out->loop_device_ms = loop_ms;
+  lap("solve", "iterations");
 
   // ---- PDHG_PostSolve (cupdlp_solver.c:1281-1435)
   const int cur = h->cur;
@@ -1029,6 +1045,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
     };
     down_col(dx, hx); down_col(daty, haty); down_row(dy, hy); down_row(dax, hax);
   }
+  lap("solve", "solution download");
   const double inf = std::numeric_limits<double>::infinity();
   if (out->col_value && out->col_dual && out->row_value && out->row_dual) {
     std::vector<double> sp(n, 0.0), sn(n, 0.0);
@@ -1071,6 +1088,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   out->iter_device_ms = iter_ms;
   out->setup_seconds += std::chrono::duration<double>(t_loop - t_begin).count();
   out->form_cols = n; out->form_rows = m; out->form_nnz = f.nnz; out->form_neq = f.neq;
+  lap("solve", "postsolve (host)");
 }
 
 }  // namespace b200
@@ -1338,7 +1356,9 @@ int b200pdlp_solve(const b200pdlp_lp* lp, const b200pdlp_params* params, const b
       throw;
     }
     cudaSetDevice(p->device);
+    Laps lap;
     delete p;
+    lap("solve", "teardown");
   });
 }
 
