@@ -180,6 +180,8 @@ struct b200pdlp_problem {
   DevBuf<double> xfull, part, red, send, recv;
   DevBuf<int> at_outpos;           // A_g^T body row -> position in the segmented partial vector
   // fused P2P path
+  std::vector<int> row_bounds;     // row offsets of every rank's block
+  bool local_link = false;         // peers are problems of this process (logical shards, b200pdlp_p2p_link_local)
   bool p2p = false;
   int p2p_pull = 0;                // 1: the primal kernel reads the peers' partials over NVLink; 0: peers push them
   PeerPtrs peers{};
@@ -203,7 +205,7 @@ struct b200pdlp_problem {
   cudaGraphExec_t graph_main = nullptr, graph_small = nullptr;
   int graph_main_passes = 0, graph_small_passes = 0;
   long long launches = 0;
-  int kernels_per_pass = 3;
+  int kernels_per_pass = 4;
 
   ~b200pdlp_problem() {
     if (graph_main) cudaGraphExecDestroy(graph_main);
@@ -303,6 +305,7 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
     HostLayout L;
     build_layout(f, rank, world, prm.ordered_max, L, lap);
     p->r0 = L.r0; p->r1 = L.r1; p->ml = L.ml; p->neq_local = L.neq_local; p->ordered = L.ordered;
+    p->row_bounds = L.bounds;
     p->n = f.n; p->m = f.m;
     p->nl = L.nl; p->nl_real = L.nl_real; p->c0 = L.c0; p->shard_len = L.shard_len; p->seg_len = L.seg_len;
     p->csr_local = std::move(L.csr_local);
@@ -353,7 +356,8 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   p->state.alloc(1);
   CUDA_OK(cudaMallocHost(&p->hstate, sizeof(PdhgState)));
   CUDA_OK(cudaMallocHost(&p->houts, kOutsCount * sizeof(double)));
-  CUDA_OK(cudaMallocHost(&p->hflag, 2 * sizeof(double)));
+  CUDA_OK(cudaMallocHost(&p->hflag, 4 * sizeof(double)));   // [0] time-limit flag, [2] read-back of the barrier fault word
+  memset(p->hflag, 0, 4 * sizeof(double));
   memset(p->hstate, 0, sizeof(PdhgState));
   CUDA_OK(cudaDeviceSynchronize());
   lap("vectors + scratch");
@@ -431,7 +435,11 @@ static void push_state(b200pdlp_problem* p) {
 }
 static void pull_state(b200pdlp_problem* p) {
   CUDA_OK(cudaMemcpyAsync(p->hstate, p->state.p, sizeof(PdhgState), cudaMemcpyDeviceToHost, p->stream));
+  int* hfault = reinterpret_cast<int*>(p->hflag + 2);
+  if (p->p2p) CUDA_OK(cudaMemcpyAsync(hfault, p->fault.p, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
   CUDA_OK(cudaStreamSynchronize(p->stream));
+  // a barrier gave up waiting for a peer: stop here instead of iterating on inconsistent data
+  if (p->p2p && *hfault) throw Error(B200PDLP_ERR_STATE, "P2P barrier timed out (a peer rank did not arrive)");
 }
 static void pull_outs(b200pdlp_problem* p, int count) {
   CUDA_OK(cudaMemcpyAsync(p->houts, p->outs.p, count * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
@@ -840,6 +848,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
     CUDA_OK(cudaMemsetAsync(p->red.p, 0, p->red.n * sizeof(double), s));
     CUDA_OK(cudaMemsetAsync(p->send.p, 0, p->send.n * sizeof(double), s));
     // fused path: nobody may store into a peer's xfull / recv before that peer has cleared them
+    if (p->p2p) CUDA_OK(cudaMemsetAsync(p->fault.p, 0, sizeof(int), s));
     if (p->p2p) { launch_p2p_exchange(s, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p); p->launches++; }
   }
   {
@@ -1024,6 +1033,16 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
         CUDA_OK(cudaMemcpyAsync(t.data(), d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
         CUDA_OK(cudaStreamSynchronize(s));
         for (int j = 0; j < n; j++) h[p->cperm[j]] = t[j];
+      } else if (p->p2p && !p->comm) {
+        // no NCCL communicator (logical shards of one process): all-gather through the peers' xfull, with a
+        // barrier before anyone reads and one before anyone overwrites
+        launch_push_shard(s, d, nl, p->peers, p->world, p->rank, p->seg_len);
+        launch_p2p_exchange(s, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p);
+        CUDA_OK(cudaMemcpyAsync(t.data(), p->xfull.p, p->xfull.n * sizeof(double), cudaMemcpyDeviceToHost, s));
+        launch_p2p_exchange(s, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p);
+        p->launches += 3;
+        CUDA_OK(cudaStreamSynchronize(s));
+        for (int j = 0; j < n; j++) h[p->cperm[j]] = t[seg_pos(p, j)];
       } else {   // all-gather the column shards, then unpack the segmented vector
         CUDA_OK(cudaMemcpyAsync(p->send.p, d, (size_t)nl * sizeof(double), cudaMemcpyDeviceToDevice, s));
         gather_shards(p);
@@ -1036,7 +1055,28 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
       if (ml) CUDA_OK(cudaMemcpyAsync(t.data(), d, (size_t)ml * sizeof(double), cudaMemcpyDeviceToHost, s));
       CUDA_OK(cudaStreamSynchronize(s));
       for (int i = 0; i < ml; i++) h[p->r0 + p->rperm[i]] = t[i];
-      if (p->world > 1) {   // other ranks' rows: zero-padded sum
+      if (p->world > 1 && p->p2p && !p->comm) {
+        // no NCCL communicator: every rank stores its rows (standard-form order) into slot `rank` of every peer's
+        // receive buffer, seg_len rows at a time; all ranks run the same number of rounds
+        int max_ml = 0;
+        for (int g = 0; g < p->world; g++) max_ml = std::max(max_ml, p->row_bounds[g + 1] - p->row_bounds[g]);
+        if (ml) CUDA_OK(cudaMemcpyAsync(p->redbuf.p, h.data() + p->r0, (size_t)ml * sizeof(double), cudaMemcpyHostToDevice, s));
+        const int rounds = (max_ml + p->seg_len - 1) / p->seg_len;
+        for (int c = 0; c < rounds; c++) {
+          const int off = c * p->seg_len;
+          launch_push_rows(s, p->redbuf.p + off, std::max(0, std::min(ml - off, p->seg_len)), p->peers, p->world, p->rank, p->seg_len);
+          launch_p2p_exchange(s, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p);
+          CUDA_OK(cudaMemcpyAsync(t.data(), p->recv.p, (size_t)p->world * p->seg_len * sizeof(double), cudaMemcpyDeviceToHost, s));
+          launch_p2p_exchange(s, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p);
+          p->launches += 3;
+          CUDA_OK(cudaStreamSynchronize(s));
+          for (int g = 0; g < p->world; g++) {
+            const int mg = p->row_bounds[g + 1] - p->row_bounds[g];
+            const int cnt = std::max(0, std::min(mg - off, p->seg_len));
+            for (int i = 0; i < cnt; i++) h[p->row_bounds[g] + off + i] = t[(size_t)g * p->seg_len + i];
+          }
+        }
+      } else if (p->world > 1) {   // other ranks' rows: zero-padded sum
         CUDA_OK(cudaMemcpyAsync(p->redbuf.p, h.data(), (size_t)m * sizeof(double), cudaMemcpyHostToDevice, s));
         allreduce_inplace(p, p->redbuf.p, m);
         CUDA_OK(cudaMemcpyAsync(h.data(), p->redbuf.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -1254,6 +1294,7 @@ int b200pdlp_bench_pass(b200pdlp_problem* p, int32_t reps, float ms[4]) {
     set_device(p);
     cudaStream_t s = p->stream;
     PdhgState* st = p->state.p;
+    p->kernels_per_pass = p->world == 1 ? 4 : ((p->p2p && p->p2p_pull) ? 5 : 6);
     pull_state(p);
     p->hstate->stop_iter = 2147483647;
     fill_pow_tables(p->hstate);
@@ -1441,6 +1482,43 @@ int b200pdlp_p2p_import(b200pdlp_problem* p, const uint8_t* all_handles) {
   });
 }
 
+int b200pdlp_p2p_link_local(b200pdlp_problem** probs, int32_t count) {
+  return guarded([&] {
+    if (!probs || count < 2 || count > kMaxPeers) throw Error(B200PDLP_ERR_ARG, "p2p_link_local: bad arguments");
+    std::vector<b200pdlp_problem*> by_rank(count, nullptr);
+    for (int k = 0; k < count; k++) {
+      b200pdlp_problem* p = probs[k];
+      if (!p || p->world != count || p->rank < 0 || p->rank >= count || by_rank[p->rank])
+        throw Error(B200PDLP_ERR_ARG, "p2p_link_local: need exactly one problem per rank of the same world");
+      by_rank[p->rank] = p;
+    }
+    for (int k = 0; k < count; k++)
+      if (by_rank[k]->device != by_rank[0]->device) {
+        int ok = 0;
+        CUDA_OK(cudaDeviceCanAccessPeer(&ok, by_rank[k]->device, by_rank[0]->device));
+        if (!ok) throw Error(B200PDLP_ERR_ARG, "p2p_link_local: devices cannot access each other");
+      }
+    for (int k = 0; k < count; k++) {
+      b200pdlp_problem* p = by_rank[k];
+      set_device(p);
+      for (int g = 0; g < count; g++) {
+        if (by_rank[g]->device != p->device) {
+          const cudaError_t e = cudaDeviceEnablePeerAccess(by_rank[g]->device, 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CUDA_OK(e);
+          cudaGetLastError();
+        }
+        p->peers.part[g] = by_rank[g]->part.p; p->peers.xfull[g] = by_rank[g]->xfull.p;
+        p->peers.flags[g] = by_rank[g]->flags.p; p->peers.recv[g] = by_rank[g]->recv.p;
+      }
+      p->p2p = true;
+      p->local_link = true;
+      p->p2p_pull = 1;
+      if (p->graph_main) { cudaGraphExecDestroy(p->graph_main); p->graph_main = nullptr; }
+      if (p->graph_small) { cudaGraphExecDestroy(p->graph_small); p->graph_small = nullptr; }
+    }
+  });
+}
+
 int b200pdlp_p2p_release(b200pdlp_problem* p) {
   return guarded([&] {
     if (!p) throw Error(B200PDLP_ERR_ARG, "null argument");
@@ -1449,6 +1527,7 @@ int b200pdlp_p2p_release(b200pdlp_problem* p) {
     for (void* q : p->ipc_opened) cudaIpcCloseMemHandle(q);
     p->ipc_opened.clear();
     p->p2p = false;
+    p->local_link = false;
     if (p->graph_main) { cudaGraphExecDestroy(p->graph_main); p->graph_main = nullptr; }
     if (p->graph_small) { cudaGraphExecDestroy(p->graph_small); p->graph_small = nullptr; }
   });

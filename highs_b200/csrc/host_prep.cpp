@@ -514,8 +514,8 @@ void build_layout(StdForm& f, int rank, int world, int ordered_max, HostLayout& 
   auto mark = [&](const char* what) { if (lap) lap(what); };
   L = HostLayout();
   L.rank = rank; L.world = world;
-  const std::vector<int> bounds = partition_rows(f, world);
-  L.r0 = bounds[rank]; L.r1 = bounds[rank + 1];
+  L.bounds = partition_rows(f, world);
+  L.r0 = L.bounds[rank]; L.r1 = L.bounds[rank + 1];
   L.ml = L.r1 - L.r0;
   const int n = f.n, ml = L.ml;
   {

@@ -94,6 +94,7 @@ void build_sell(const Csr& a, const std::vector<int>& perm, const std::vector<in
 struct HostLayout {
   int rank = 0, world = 1;
   int r0 = 0, r1 = 0, ml = 0, neq_local = 0;
+  std::vector<int> bounds;        // row offsets of every rank's block (world + 1 entries)
   bool ordered = false;
   Csr csr_local;                  // rows [r0, r1) in standard-form order
   std::vector<int> rperm, rinv;   // device row order: rperm[new] = old local row

@@ -514,12 +514,23 @@ push_shard_kernel(const double* __restrict__ src, int len, PeerPtrs pp, int worl
   }
 }
 
+// solution assembly without NCCL: `len` (<= seg_len) doubles into slot `rank` of every peer's receive buffer
+__global__ void __launch_bounds__(kThreads)
+push_rows_kernel(const double* __restrict__ src, int len, PeerPtrs pp, int world, int rank, int seg_len) {
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < len; i += stride) {
+    const double v = src[i];
+    for (int h = 0; h < world; h++) pp.recv[h][(size_t)rank * seg_len + i] = v;
+  }
+}
+
 // barrier + all-reduce of k <= 32 scalars (k = 0: pure barrier): every rank writes its values into every
 // peer's mailbox (double-buffered by epoch parity), signals, waits, then adds all ranks' values in rank order
 constexpr int kBigBox = 32;
 __global__ void p2p_exchange_kernel(double* vals, int k, PeerPtrs pp, int world, int rank, unsigned long long* epochs,
                                     int* fault, const PdhgState* due) {
   if (check_not_due(due)) return;   // identical on every rank
+  if (*reinterpret_cast<volatile int*>(fault)) return;   // a barrier already timed out: do not wait another minute per launch
   const int lane = threadIdx.x;
   unsigned long long e = 0;
   if (lane == 0) { e = epochs[10] + 1; epochs[10] = e; }
@@ -576,6 +587,7 @@ p2p_barrier_kernel(int mode, PdhgState* st, const double* __restrict__ partials,
   __shared__ double sm[2][kStepThreads / 32];
   __shared__ double tot[2];
   if (st->iter >= st->stop_iter) return;   // identical on every rank: nobody enters
+  if (*reinterpret_cast<volatile int*>(fault)) return;   // a barrier already timed out (the host raises the error)
   // device-side timeline (epochs[2..]): [2] last exit stamp, [3+3*mode] sum(entry - previous exit) = the
   // compute phase before this barrier, [4+3*mode] sum(time inside the barrier), [5+3*mode] sum(wait), [9] count
   unsigned long long t_entry = 0, t_sig = 0, t_done = 0;
@@ -1092,6 +1104,10 @@ void launch_push_part(cudaStream_t s, PdhgState* st, const double* part, const P
 void launch_push_shard(cudaStream_t s, const double* src, int len, const PeerPtrs& pp, int world, int rank, int seg_len,
                        const PdhgState* due) {
   push_shard_kernel<<<ew_grid((len + 1) / 2), kThreads, 0, s>>>(src, len, pp, world, rank, seg_len, due);
+}
+void launch_push_rows(cudaStream_t s, const double* src, int len, const PeerPtrs& pp, int world, int rank, int seg_len) {
+  if (len <= 0) return;
+  push_rows_kernel<<<ew_grid(len), kThreads, 0, s>>>(src, len, pp, world, rank, seg_len);
 }
 void launch_p2p_exchange(cudaStream_t s, double* vals, int k, const PeerPtrs& pp, int world, int rank,
                          unsigned long long* epochs, int* fault, const PdhgState* due) {

@@ -32,6 +32,7 @@ void launch_primal_shard_p2p(cudaStream_t s, int len, PdhgState* st, double* xs0
                              const double* lo, const double* up, double* xsum, ReduceScratch rs);
 void launch_push_shard(cudaStream_t s, const double* src, int len, const PeerPtrs& pp, int world, int rank, int seg_len,
                        const PdhgState* due = nullptr);
+void launch_push_rows(cudaStream_t s, const double* src, int len, const PeerPtrs& pp, int world, int rank, int seg_len);
 void launch_p2p_exchange(cudaStream_t s, double* vals, int k, const PeerPtrs& pp, int world, int rank,
                          unsigned long long* epochs, int* fault, const PdhgState* due = nullptr);
 void launch_push_part(cudaStream_t s, PdhgState* st, const double* part, const PeerPtrs& pp, int world, int rank, int seg_len);

@@ -65,7 +65,7 @@ ABI_SYMBOLS = [
     "b200pdlp_comm_init", "b200pdlp_partition_rows", "b200pdlp_last_error", "b200pdlp_version",
     "b200pdlp_device_count", "b200pdlp_form_create", "b200pdlp_form_destroy", "b200pdlp_form_dims",
     "b200pdlp_form_get_vector", "b200pdlp_form_get_csc", "b200pdlp_form_get_csr", "b200pdlp_form_get_row_map",
-    "b200pdlp_form_layout_eval",
+    "b200pdlp_form_layout_eval", "b200pdlp_p2p_link_local",
 ]
 
 _lib = None
@@ -120,6 +120,7 @@ def lib():
         L.b200pdlp_p2p_import.argtypes = [C.c_void_p, C.POINTER(C.c_uint8)]
         L.b200pdlp_p2p_timeline.argtypes = [C.c_void_p, _dp]
         L.b200pdlp_p2p_release.argtypes = [C.c_void_p]
+        L.b200pdlp_p2p_link_local.argtypes = [C.POINTER(C.c_void_p), C.c_int32]
         L.b200pdlp_partition_rows.argtypes = [C.POINTER(CLp), C.c_int32, _ip]
         L.b200pdlp_form_create.argtypes = [C.POINTER(CLp), C.c_int32, C.POINTER(C.c_void_p)]
         L.b200pdlp_form_destroy.argtypes = [C.c_void_p]
@@ -381,6 +382,42 @@ def host_layout_eval(lp: HighsLp, world: int = 1, ordered_max: int = 0, x=None, 
                     cbeg=cbeg, cidx=cidx[:nnz], cval=cval[:nnz])
     finally:
         L.b200pdlp_form_destroy(h)
+
+
+def solve_logical_shards(lp: HighsLp, world: int, device: int = -1, **params) -> list:
+    """the multi-GPU code path with `world` logical shards inside this process (normally all on one
+    device): one problem per rank, buffers wired to each other with b200pdlp_p2p_link_local, one host thread per rank
+    (ctypes releases the GIL during the solve).  Returns the per-rank result dicts (identical by construction)."""
+    import threading
+    probs = [Problem(lp, rank=g, world=world, device=device, **params) for g in range(world)]
+    try:
+        arr = (C.c_void_p * world)(*[q._h for q in probs])
+        _check(lib().b200pdlp_p2p_link_local(arr, world), "b200pdlp_p2p_link_local")
+        out, err = [None] * world, [None] * world
+
+        def run(g):
+            try:
+                out[g] = probs[g].solve(device=device, **params)
+            except Exception as e:   # noqa: BLE001 -- reported to the caller below
+                err[g] = e
+
+        threads = [threading.Thread(target=run, args=(g,), daemon=True) for g in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for e in err:
+            if e is not None:
+                raise e
+        return out
+    finally:
+        for q in probs:
+            try:
+                q.p2p_release()
+            except Exception:
+                pass
+        for q in probs:
+            q.close()
 
 
 def device_count() -> int:

@@ -176,6 +176,11 @@ int b200pdlp_p2p_export(b200pdlp_problem* p, uint8_t handles[B200PDLP_IPC_BYTES]
 int b200pdlp_p2p_import(b200pdlp_problem* p, const uint8_t* all_handles);
 /* unmap the peers' buffers (call on every rank, then synchronise the ranks, BEFORE any rank destroys its problem) */
 int b200pdlp_p2p_release(b200pdlp_problem* p);
+/* G logical shards inside ONE process ("the same code path must run with G logical shards on 1
+ * device"): probs[] holds one problem per rank of the same world, all created by this process (normally on the
+ * same device); their buffers are wired to each other directly instead of through CUDA IPC, and no NCCL
+ * communicator is needed.  Every rank's b200pdlp_problem_solve must then run on its own host thread. */
+int b200pdlp_p2p_link_local(b200pdlp_problem** probs, int32_t count);
 /* device-side timeline of the fused path since the last call, per-pass averages in us: [0] primal-shard phase,
  * [1] barrier 0 total, [2] of which waiting, [3] A x + A'y phase, [4] barrier 1 total, [5] of which waiting, [6] passes */
 int b200pdlp_p2p_timeline(b200pdlp_problem* p, double out_us[8]);

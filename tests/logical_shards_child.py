@@ -1,0 +1,59 @@
+"""Child process of tests/test_gpu_logical_shards.py: the multi-GPU code path (row blocks + column shards, the fused
+peer-memory kernels, flag barriers, device-side step rule, speculative check, NCCL-free solution assembly) with G
+LOGICAL shards on ONE device -- SURVEY.md 8(e): "the same code path must run with G logical shards on 1 device".
+Run in its own process so that a stuck barrier can be killed by PID without taking the test session along.
+usage: python tests/logical_shards_child.py <world> <case>      prints one JSON line and exits 0 on success"""
+import json
+import os
+import sys
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # one hardware queue per logical rank's stream
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from highs_b200 import engine  # noqa: E402
+from highs_b200.lp import read_b2lp, synthetic_lp  # noqa: E402
+
+
+def main():
+    world, case = int(sys.argv[1]), sys.argv[2]
+    if case == "synthetic":
+        lp = synthetic_lp(6000, 5000, 6, seed=11)
+        prm = dict(iter_limit=20000, tol_primal=1e-6, tol_dual=1e-6, tol_gap=1e-6)
+    elif case == "dense":
+        lp = synthetic_lp(9000, 7000, 5, seed=5, dense_col_nnz=4000)     # long rows of A' on every rank
+        prm = dict(iter_limit=20000, tol_primal=1e-6, tol_dual=1e-6, tol_gap=1e-6)
+    else:
+        lp = read_b2lp(os.path.join(ROOT, "tests", "golden", case + ".b2lp"))
+        prm = dict(iter_limit=200000)
+    one = engine.Problem(lp, ordered_max=-1, **prm)      # single-GPU tree-mode solve = what the shards must reproduce
+    ref = one.solve(ordered_max=-1, **prm)
+    one.close()
+    res = engine.solve_logical_shards(lp, world, **prm)
+    out = dict(world=world, case=case, ref_iters=ref["iters"], ref_term=ref["term_code"], ref_obj=ref["primal_obj"],
+               iters=[r["iters"] for r in res], term=[r["term_code"] for r in res], obj=[r["primal_obj"] for r in res])
+    ok = True
+    for r in res[1:]:   # every rank takes the same decisions and returns the same (complete) solution
+        for k in ("col_value", "col_dual", "row_value", "row_dual"):
+            ok &= bool(np.array_equal(r[k], res[0][k]))
+        ok &= r["iters"] == res[0]["iters"] and r["term_code"] == res[0]["term_code"]
+    out["ranks_identical"] = ok
+    r0 = res[0]
+    ok &= r0["term_code"] == ref["term_code"]
+    if ref["term_code"] == 0:
+        o_ref, o = lp.objectiveValue(ref["col_value"]), lp.objectiveValue(r0["col_value"])
+        out["objective"] = [o_ref, o]
+        ok &= abs(o - o_ref) <= 1e-4 * (1 + abs(o_ref))
+        # primal feasibility of the assembled solution in the ORIGINAL space (row_value must be A x)
+        A = lp.a_matrix_.to_scipy() if hasattr(lp.a_matrix_, "to_scipy") else None
+        if A is not None:
+            ok &= bool(np.allclose(A @ r0["col_value"], r0["row_value"], rtol=1e-8, atol=1e-7))
+    out["ok"] = bool(ok)
+    print(json.dumps(out))
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
