@@ -23,14 +23,21 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.xfail(strict=False, reason="logical-shard path not yet run on hardware (written after the GPU budget was spent)")]
 
 
-@pytest.mark.parametrize("world,case", [(2, "synthetic"), (3, "synthetic"), (2, "adlittle"), (4, "dense")])
+_state = {"broken": False}   # after one failing case the others are not attempted (bounds the time a broken path can cost)
+
+
+@pytest.mark.parametrize("world,case", [(2, "synthetic"), (3, "adlittle"), (4, "dense")])
 def test_logical_shards(world, case):
+    if _state["broken"]:
+        pytest.xfail("an earlier logical-shard case failed; not attempted")
+    _state["broken"] = True
     try:
-        r = subprocess.run([sys.executable, CHILD, str(world), case], capture_output=True, text=True, timeout=420, cwd=ROOT)
+        r = subprocess.run([sys.executable, CHILD, str(world), case], capture_output=True, text=True, timeout=240, cwd=ROOT)
     except subprocess.TimeoutExpired:
-        pytest.fail("logical-shard solve did not finish in 420 s (child killed)")
+        pytest.fail("logical-shard solve did not finish in 240 s (child killed)")
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert r.returncode == 0 and lines, (r.stdout[-2000:], r.stderr[-2000:])
     out = json.loads(lines[-1])
     assert out["ok"] and out["ranks_identical"], out
     assert out["term"][0] == out["ref_term"]
+    _state["broken"] = False
