@@ -104,7 +104,7 @@ struct DevBuf {
   void upload(const T* src, size_t count) {
     if (count) CUDA_OK(cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
   }
-  void from(const std::vector<T>& v) { alloc(v.size(), false); upload(v.data(), v.size()); }
+  template <class A> void from(const std::vector<T, A>& v) { alloc(v.size(), false); upload(v.data(), v.size()); }
 };
 
 struct DeviceMatrix {
@@ -138,7 +138,7 @@ struct DeviceMatrix {
     dev.padded_total = (int)host.padded;
     dev.prefetch_dist = 0;
     // the big host copies are not needed any more
-    std::vector<int>().swap(host.col); std::vector<double>().swap(host.val);
+    RawVec<int>().swap(host.col); RawVec<double>().swap(host.val);
     std::vector<int>().swap(host.lcol); std::vector<double>().swap(host.lval);
   }
   int grid() const { return dev.nblocks_body + dev.nsegs; }

@@ -9,7 +9,13 @@
 #include "host_prep.hpp"
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <pthread.h>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <functional>
 #include <limits>
@@ -30,18 +36,95 @@ static int host_threads() {
   }();
   return n;
 }
+// Persistent worker pool: run_tasks(k, fn) executes fn(0) .. fn(k-1), one task per thread (the caller takes part),
+// and returns when all are done.  The prologue has ~60 short parallel regions; spawning threads for each would cost
+// about as much as the smaller regions themselves.  Workers spin briefly for the next region before they sleep.
+// One region at a time (regions of concurrent callers are serialised); tasks must not start regions themselves.
+namespace {
+class Pool {
+ public:
+  // never destroyed: the workers sleep on the condition variable and end with the process (no join at exit, and a
+  // fork()ed child -- which inherits the object but not the threads -- simply runs its regions inline)
+  static Pool& get() { static Pool* p = new Pool; return *p; }
+  void run_tasks(int k, const std::function<void(int)>& fn) {
+    if (k <= 1 || workers_.empty() || dead_.load(std::memory_order_relaxed)) { for (int t = 0; t < k; t++) fn(t); return; }
+    std::lock_guard<std::mutex> region(region_);
+    unsigned long long g;
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      g = ++gen_;
+      job_ = &fn; ntasks_ = k;
+      remaining_.store(k, std::memory_order_relaxed);
+      ticket_.store(g << 32, std::memory_order_release);
+      wake_.store(g, std::memory_order_release);
+    }
+    cv_.notify_all();
+    work(fn, k, g);
+    // wait for the stragglers (short: spin, then yield)
+    for (int spins = 0; remaining_.load(std::memory_order_acquire) > 0; spins++)
+      if (spins > 2000) std::this_thread::yield();
+    std::lock_guard<std::mutex> lk(m_);
+    job_ = nullptr;
+  }
+ private:
+  Pool() {
+    const int T = host_threads();
+    for (int t = 1; t < T; t++) workers_.emplace_back([this] { loop(); });
+    pthread_atfork(nullptr, nullptr, [] { Pool::get().dead_.store(true); });
+  }
+  // claim tasks of generation g only: a straggler of an earlier region can never take (or miscount) a task of the next
+  void work(const std::function<void(int)>& fn, int k, unsigned long long g) {
+    for (;;) {
+      unsigned long long tk = ticket_.load(std::memory_order_acquire);
+      if ((tk >> 32) != (g & 0xffffffffull)) return;
+      const unsigned t = (unsigned)(tk & 0xffffffffull);
+      if ((int)t >= k) return;
+      if (!ticket_.compare_exchange_weak(tk, tk + 1, std::memory_order_acq_rel)) continue;
+      fn((int)t);
+      remaining_.fetch_sub(1, std::memory_order_acq_rel);
+    }
+  }
+  void loop() {
+    unsigned long long seen = 0;
+    for (;;) {
+      // spin a little for the next region, then sleep on the condition variable
+      bool got = false;
+      for (int spins = 0; spins < 30000; spins++) {
+        if (wake_.load(std::memory_order_acquire) != seen) { got = true; break; }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+      }
+      const std::function<void(int)>* job = nullptr;
+      int k = 0;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        if (!got) cv_.wait(lk, [&] { return wake_.load(std::memory_order_acquire) != seen; });
+        seen = gen_;
+        job = job_; k = ntasks_;
+      }
+      if (job) work(*job, k, seen);
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_, region_;
+  std::condition_variable cv_;
+  const std::function<void(int)>* job_ = nullptr;   // guarded by m_ (with gen_, ntasks_)
+  int ntasks_ = 0;
+  unsigned long long gen_ = 0;
+  std::atomic<unsigned long long> wake_{0}, ticket_{0};
+  std::atomic<int> remaining_{0};
+  std::atomic<bool> dead_{false};
+};
+}  // namespace
+
 // fn(chunk_index, begin, end) over [0, count) cut into host_threads() contiguous chunks
 static void parallel_chunks(long long count, const std::function<void(int, long long, long long)>& fn, long long min_per_thread = 1 << 15) {
   int T = host_threads();
   if (count < 2 * min_per_thread) T = 1;
   T = (int)std::min<long long>(T, std::max<long long>(1, count / min_per_thread));
   if (T <= 1) { fn(0, 0, count); return; }
-  std::vector<std::thread> th;
-  for (int t = 0; t < T; t++) {
-    const long long b = count * t / T, e = count * (t + 1) / T;
-    th.emplace_back([&fn, t, b, e] { fn(t, b, e); });
-  }
-  for (auto& x : th) x.join();
+  Pool::get().run_tasks(T, [&](int t) { fn(t, count * t / T, count * (t + 1) / T); });
 }
 // column chunks balanced by nonzeros: boundaries[t] .. boundaries[t+1]
 static std::vector<int> balanced_columns(const std::vector<int>& cbeg, int n, int T) {
@@ -154,23 +237,6 @@ void formulate(const b200pdlp_lp& lp, StdForm& f) {
   f.norm_rhs = std::sqrt(s);
 }
 
-namespace {
-// divide/multiply the vectors by one pass's factors and fold them into the running scales
-// (scale_problem, cupdlp_scaling.c:17-31, and the cdot updates at :110-111)
-void apply_to_vectors(StdForm& f, const std::vector<double>& cs, const std::vector<double>& rs) {
-  for (int j = 0; j < f.n; j++) {
-    f.cost[j] /= cs[j];
-    f.lower[j] *= cs[j];
-    f.upper[j] *= cs[j];
-    f.col_scale[j] *= cs[j];
-  }
-  for (int i = 0; i < f.m; i++) {
-    f.rhs[i] /= rs[i];
-    f.row_scale[i] *= rs[i];
-  }
-}
-}  // namespace
-
 // Counting-sort transposition of the nonzero pattern (what csc2csr / cupdlp_dcs_transpose do,
 // cupdlp_cs.c:189-214), parallel: thread t histograms the rows of its column chunk, a prefix over
 // (row, thread) gives every thread its private output range inside each row, and the scatter keeps
@@ -181,12 +247,7 @@ void build_row_index(StdForm& f) {
   while (T > 1 && (long long)T * m > (1LL << 27)) T /= 2;   // cap the T x m histogram at 512 MB
   const std::vector<int> cb = balanced_columns(f.cbeg, n, T);
   std::vector<std::vector<int>> hist(T);
-  auto run = [&](const std::function<void(int)>& fn) {
-    if (T == 1) { fn(0); return; }
-    std::vector<std::thread> th;
-    for (int t = 0; t < T; t++) th.emplace_back([&fn, t] { fn(t); });
-    for (auto& x : th) x.join();
-  };
+  auto run = [&](const std::function<void(int)>& fn) { Pool::get().run_tasks(T, fn); };
   run([&](int t) {
     hist[t].assign(m, 0);
     for (int p = f.cbeg[cb[t]]; p < f.cbeg[cb[t + 1]]; p++) hist[t][f.cidx[p]]++;
@@ -204,9 +265,15 @@ void build_row_index(StdForm& f) {
     }
   });
   f.rpos.resize(f.nnz);
+  f.rcol.resize(f.nnz);
   run([&](int t) {
     std::vector<int>& w = hist[t];
-    for (int p = f.cbeg[cb[t]]; p < f.cbeg[cb[t + 1]]; p++) f.rpos[w[f.cidx[p]]++] = p;   // p ascending = columns ascending
+    for (int j = cb[t]; j < cb[t + 1]; j++)
+      for (int p = f.cbeg[j]; p < f.cbeg[j + 1]; p++) {   // p ascending = columns ascending
+        const int q = w[f.cidx[p]]++;
+        f.rpos[q] = p;
+        f.rcol[q] = j;
+      }
   });
 }
 
@@ -224,16 +291,21 @@ void scale(StdForm& f, bool do_scale) {
     f.amax = amax;
     return;
   }
+  const bool timing = getenv("B200PDLP_TIMING") != nullptr;
+  auto tprev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[b200pdlp scale] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - tprev).count());
+    tprev = t1;
+  };
   const int T = (f.nnz < (1 << 18)) ? 1 : host_threads();
   const std::vector<int> cb = balanced_columns(f.cbeg, n, T);
   std::vector<double> cs(n), rs(m), cs_next(n);
-  std::vector<std::vector<double>> rloc(T);           // per-thread row accumulators
-  for (int t = 0; t < T; t++) rloc[t].assign(m, 0.0);
+  std::vector<std::vector<double>> rloc(T);           // per-thread row accumulators, first touched by their owner
   auto run_cols = [&](const std::function<void(int, int, int)>& fn) {   // fn(tid, col_begin, col_end)
     if (T == 1) { fn(0, 0, n); return; }
-    std::vector<std::thread> th;
-    for (int t = 0; t < T; t++) th.emplace_back([&, t] { fn(t, cb[t], cb[t + 1]); });
-    for (auto& x : th) x.join();
+    Pool::get().run_tasks(T, [&](int t) { fn(t, cb[t], cb[t + 1]); });
   };
   auto merge_rows_max = [&](std::vector<double>& dst) {
     parallel_chunks(m, [&](int, long long b, long long e) {
@@ -246,10 +318,11 @@ void scale(StdForm& f, bool do_scale) {
   };
   // row-major index of the nonzeros (position in cval), columns ascending within a row: for the exact row sums
   std::vector<int>& rptr = f.rptr;
-  std::vector<int>& rpos = f.rpos;
+  RawVec<int>& rpos = f.rpos;
   // norms for the first Ruiz pass
   run_cols([&](int t, int c0, int c1) {
     std::vector<double>& r = rloc[t];
+    r.assign(m, 0.0);
     for (int j = c0; j < c1; j++) {
       double mx = 0.0;
       for (int p = f.cbeg[j]; p < f.cbeg[j + 1]; p++) {
@@ -261,6 +334,7 @@ void scale(StdForm& f, bool do_scale) {
     }
   });
   merge_rows_max(rs);
+  lap("first norms");
   const int kRuiz = 10;
   std::vector<double> amax_t(T, 0.0);
   for (int it = 0; it <= kRuiz; it++) {
@@ -303,10 +377,11 @@ void scale(StdForm& f, bool do_scale) {
       }
       amax_t[t] = am;
     });
+    lap(last ? "final sweep" : "sweep");
     if (last) break;
     if (next_is_pc) {
       // exact row 1-norms in the reference's summation order
-      if (rptr.empty()) build_row_index(f);
+      if (rptr.empty()) { build_row_index(f); lap("row index"); }
       parallel_chunks(m, [&](int, long long b, long long e) {
         for (long long i = b; i < e; i++) {
           double sum = 0.0;
@@ -314,8 +389,10 @@ void scale(StdForm& f, bool do_scale) {
           rs[i] = sum;
         }
       });
+      lap("row 1-norms");
     } else {
       merge_rows_max(rs);
+      lap("merge");
     }
     cs.swap(cs_next);
   }
@@ -348,12 +425,7 @@ void build_row_major(const StdForm& f, int r0, int r1, Csr& a) {
   a.nrows = r1 - r0;
   a.ncols = f.n;
   if (!f.rptr.empty() && (int)f.rptr.size() == f.m + 1) {
-    // gather through the row-major index (parallel): position -> column via a position-to-column map
-    std::vector<int> colof(f.nnz);
-    parallel_chunks(f.n, [&](int, long long j0, long long j1) {
-      for (int j = (int)j0; j < (int)j1; j++)
-        for (int p = f.cbeg[j]; p < f.cbeg[j + 1]; p++) colof[p] = j;
-    }, 4096);
+    // gather the values through the row-major index (parallel); the columns were recorded when it was built
     a.rowptr.resize(a.nrows + 1);
     const int base = f.rptr[r0];
     for (int i = 0; i <= a.nrows; i++) a.rowptr[i] = f.rptr[r0 + i] - base;
@@ -361,7 +433,7 @@ void build_row_major(const StdForm& f, int r0, int r1, Csr& a) {
     a.col.resize(a.nnz);
     a.val.resize(a.nnz);
     parallel_chunks(a.nnz, [&](int, long long q0, long long q1) {
-      for (long long q = q0; q < q1; q++) { const int p = f.rpos[base + q]; a.col[q] = colof[p]; a.val[q] = f.cval[p]; }
+      for (long long q = q0; q < q1; q++) { a.col[q] = f.rcol[base + q]; a.val[q] = f.cval[f.rpos[base + q]]; }
     });
     return;
   }
@@ -388,15 +460,23 @@ void build_col_major(const StdForm& f, int r0, int r1, Csr& at) {
   at = Csr();
   at.nrows = f.n;
   at.ncols = r1 - r0;
-  at.rowptr.assign(f.n + 1, 0);
-  for (int j = 0; j < f.n; j++) {
-    int c = 0;
-    for (int p = f.cbeg[j]; p < f.cbeg[j + 1]; p++) c += (f.cidx[p] >= r0 && f.cidx[p] < r1);
-    at.rowptr[j + 1] = at.rowptr[j] + c;
+  if (r0 == 0 && r1 == f.m) {
+    at.rowptr.assign(f.cbeg.begin(), f.cbeg.begin() + f.n + 1);   // all rows: the column lengths themselves
+  } else {
+    std::vector<int> cnt(f.n, 0);
+    parallel_chunks(f.n, [&](int, long long j0, long long j1) {
+      for (int j = (int)j0; j < (int)j1; j++) {
+        int c = 0;
+        for (int p = f.cbeg[j]; p < f.cbeg[j + 1]; p++) c += (f.cidx[p] >= r0 && f.cidx[p] < r1);
+        cnt[j] = c;
+      }
+    }, 4096);
+    at.rowptr.assign(f.n + 1, 0);
+    for (int j = 0; j < f.n; j++) at.rowptr[j + 1] = at.rowptr[j] + cnt[j];
   }
   at.nnz = at.rowptr[f.n];
-  at.col.assign(at.nnz, 0);
-  at.val.assign(at.nnz, 0.0);
+  at.col.resize(at.nnz);   // uninitialised: every entry is written by the loop below
+  at.val.resize(at.nnz);
   parallel_chunks(f.n, [&](int, long long j0, long long j1) {
   std::vector<std::pair<int, double>> tmp;
   for (int j = (int)j0; j < (int)j1; j++) {
@@ -475,18 +555,24 @@ void build_sell(const Csr& a, const std::vector<int>& perm, const std::vector<in
     total += 32LL * mx;
   }
   out.padded = total;
-  out.col.assign((size_t)total + 32, 0);
-  out.val.assign((size_t)total + 32, 0.0);
+  out.col.resize((size_t)total + 32);   // uninitialised: every slot is written below, by the thread that owns the slice
+  out.val.resize((size_t)total + 32);
+  for (int q = 0; q < 32; q++) { out.col[(size_t)total + q] = 0; out.val[(size_t)total + q] = 0.0; }
   parallel_chunks(nslices, [&](int, long long s0, long long s1) {
     for (long long s = s0; s < s1; s++) {
       const SellMatrix::Slice& sl = out.slices[s];
       for (int l = 0; l < 32; l++) {
-        if ((sl.skipmask >> l) & 1u) continue;
-        const int r = perm[s * 32 + l];
         int k = 0;
-        for (int p = a.rowptr[r]; p < a.rowptr[r + 1]; p++, k++) {
-          out.col[(size_t)sl.ptr + 32 * (size_t)k + l] = colmap[a.col[p]];
-          out.val[(size_t)sl.ptr + 32 * (size_t)k + l] = a.val[p];
+        if (!((sl.skipmask >> l) & 1u)) {
+          const int r = perm[s * 32 + l];
+          for (int p = a.rowptr[r]; p < a.rowptr[r + 1]; p++, k++) {
+            out.col[(size_t)sl.ptr + 32 * (size_t)k + l] = colmap[a.col[p]];
+            out.val[(size_t)sl.ptr + 32 * (size_t)k + l] = a.val[p];
+          }
+        }
+        for (; k < sl.len; k++) {   // padding
+          out.col[(size_t)sl.ptr + 32 * (size_t)k + l] = 0;
+          out.val[(size_t)sl.ptr + 32 * (size_t)k + l] = 0.0;
         }
       }
     }

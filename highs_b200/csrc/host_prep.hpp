@@ -9,11 +9,26 @@
 #pragma once
 #include <cstdint>
 #include <functional>
+#include <memory>
+#include <utility>
 #include <vector>
 
 #include "../../include/b200pdlp.h"
 
 namespace b200 {
+
+// std::vector whose resize() leaves new elements uninitialised: the big arrays of the prologue are written exactly
+// once by the threads that fill them, so the pages are first touched in parallel (and on the writer's NUMA node)
+// instead of being zero-filled by one thread beforehand.
+template <class T>
+struct DefaultInitAlloc : std::allocator<T> {
+  template <class U> struct rebind { using other = DefaultInitAlloc<U>; };
+  DefaultInitAlloc() = default;
+  template <class U> DefaultInitAlloc(const DefaultInitAlloc<U>&) {}
+  template <class U> void construct(U* p) { ::new (static_cast<void*>(p)) U; }
+  template <class U, class... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+};
+template <class T> using RawVec = std::vector<T, DefaultInitAlloc<T>>;
 
 enum RowClass : int { kEq = 0, kLeq = 1, kGeq = 2, kBound = 3 };  // cupdlp_defs.h numbering
 
@@ -21,8 +36,9 @@ enum RowClass : int { kEq = 0, kLeq = 1, kGeq = 2, kBound = 3 };  // cupdlp_defs
 struct StdForm {
   int n = 0, m = 0, nnz = 0, neq = 0, n_orig = 0;
   std::vector<double> cost, lower, upper, rhs;
-  std::vector<int> cbeg, cidx;   // column-wise copy (scaled in place)
-  std::vector<double> cval;
+  std::vector<int> cbeg;         // column-wise copy (scaled in place)
+  RawVec<int> cidx;
+  RawVec<double> cval;
   std::vector<double> col_scale, row_scale;
   std::vector<int> row_new_idx, row_class;  // by ORIGINAL row
   double sense = 1.0, offset = 0.0;
@@ -30,14 +46,16 @@ struct StdForm {
   double amax = 0.0;                        // max |a_ij| after scaling
   // row-major index of the nonzeros (built once, by scale() or on demand): row i owns positions
   // rpos[rptr[i] .. rptr[i+1]) of cidx/cval, columns ascending
-  std::vector<int> rptr, rpos;
+  std::vector<int> rptr;
+  RawVec<int> rpos, rcol;   // rcol[q] = column of position rpos[q]
 };
 
 // plain row-major matrix (CSR); entries of a row keep the order the reference's scatter SpMV adds them in
 struct Csr {
   int nrows = 0, ncols = 0, nnz = 0;
-  std::vector<int> rowptr, col;
-  std::vector<double> val;
+  std::vector<int> rowptr;
+  RawVec<int> col;
+  RawVec<double> val;
 };
 
 // Device layout of one matrix: sliced ELL body + split long rows.
@@ -53,8 +71,8 @@ struct SellMatrix {
   long long nnz = 0, padded = 0;
   struct Slice { int ptr, len; unsigned skipmask; int pad; };
   std::vector<Slice> slices;
-  std::vector<int> col;
-  std::vector<double> val;
+  RawVec<int> col;
+  RawVec<double> val;
   struct Seg { int row, nnz_begin, nnz_end, long_id; };
   struct LongRow { int row, first_seg, nseg, partial_offset; };
   std::vector<Seg> segs;

@@ -16,7 +16,7 @@ m, n, k = (int(a) for a in sys.argv[1:4]) if len(sys.argv) >= 4 else (1_000_000,
 lp = synthetic_lp(m, n, k)
 L = engine.lib()
 clp, keep = engine.make_clp(lp)
-for rep in range(3):
+for rep in range(int(__import__("os").environ.get("REPS", "3"))):
     h = C.c_void_p()
     t0 = time.perf_counter()
     assert L.b200pdlp_form_create(C.byref(clp), 1, C.byref(h)) == 0
