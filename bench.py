@@ -171,6 +171,11 @@ def run_reference_arm(args, rank, world):
                          "sample": f"{ref['iters']} steady-state iterations (two-point fit over pdlp_iteration_limit, "
                                    f"{ref['seconds']:.1f} s; setup {ref['setup_seconds']:.1f} s excluded)"},
         "e2e": {"value": ref["rate"], "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        # for reading our arm's e2e (which INCLUDES its setup): the reference's own setup and what its end-to-end rate
+        # would be for the same number of steps, from the two-point fit (value / e2e above stay the steady-state rate)
+        "reference_setup_seconds": ref["setup_seconds"],
+        "e2e_same_steps_projection": {"steps": args.steps, "value": args.steps / (ref["setup_seconds"] + args.steps / ref["rate"]),
+                                      "unit": "iter/s", "note": "steps / (setup + steps / rate); not measured at this step count"},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
