@@ -23,6 +23,7 @@
 
 #include "host_prep.hpp"
 #include "pdhg_kernels.hpp"
+#include "setup_kernels.hpp"
 
 namespace b200 {
 
@@ -278,6 +279,45 @@ struct Laps {
   }
 };
 
+// params.device_scaling: PDHG_Scale_Data on the GPU (setup_kernels.cu).  The unscaled column-major matrix and the
+// vectors go up once, the 10 Ruiz passes run while the host builds the row-major index of the nonzeros (which the
+// Pock-Chambolle row sums and, later, the row-major layout need anyway), and the scaled data come back into `f`, so the
+// rest of the prologue is unchanged.  Bit-identical to host_prep.cpp::scale.
+template <class Lap>
+static void scale_on_device(StdForm& f, Lap& lap) {
+  cudaStream_t s = nullptr;
+  CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } guard{s};
+  const int n = f.n, m = f.m, nnz = f.nnz;
+  DevBuf<int> cbeg, cidx, colof, rptr, rpos;
+  DevBuf<double> cval, cost, lower, upper, colscale, rhs, rowscale, cs, cnorm, rs, rnorm, amax;
+  cbeg.from(f.cbeg); cidx.from(f.cidx); cval.from(f.cval);
+  cost.from(f.cost); lower.from(f.lower); upper.from(f.upper); colscale.from(f.col_scale);
+  rhs.from(f.rhs); rowscale.from(f.row_scale);
+  colof.alloc(nnz, false);
+  cs.alloc(n, false); cnorm.alloc(n, false); rs.alloc(m, false); rnorm.alloc(m, false); amax.alloc(1);
+  lap("scale: upload");
+  DevForm F{n, m, nnz, cbeg.p, cidx.p, colof.p, cval.p, cost.p, lower.p, upper.p, colscale.p, rhs.p, rowscale.p};
+  DevScaleScratch w{cs.p, cnorm.p, rs.p, rnorm.p, amax.p};
+  device_scale_ruiz(s, F, w);
+  CUDA_OK(cudaGetLastError());
+  if (f.rptr.empty()) build_row_index(f);          // host threads, while the device runs the Ruiz passes
+  rptr.from(f.rptr); rpos.from(f.rpos);
+  lap("scale: row index (host) + Ruiz (device)");
+  device_scale_pock_chambolle(s, F, w, rptr.p, rpos.p);
+  CUDA_OK(cudaGetLastError());
+  auto down = [&](auto& dst, const auto& src) {
+    if (!dst.empty()) CUDA_OK(cudaMemcpyAsync(dst.data(), src.p, dst.size() * sizeof(dst[0]), cudaMemcpyDeviceToHost, s));
+  };
+  down(f.cval, cval); down(f.cost, cost); down(f.lower, lower); down(f.upper, upper); down(f.col_scale, colscale);
+  down(f.rhs, rhs); down(f.row_scale, rowscale);
+  double am = 0.0;
+  CUDA_OK(cudaMemcpyAsync(&am, amax.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  f.amax = am;
+  lap("scale: Pock-Chambolle + download");
+}
+
 static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, int rank, int world, b200pdlp_problem* p) {
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -297,7 +337,8 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   };
   formulate(lp, p->form);
   lap("formulate");
-  scale(p->form, prm.scaling != 0);
+  if (prm.scaling != 0 && prm.device_scaling != 0 && p->form.nnz > 0) scale_on_device(p->form, lap);
+  else scale(p->form, prm.scaling != 0);
   lap("scale");
   StdForm& f = p->form;
   {

@@ -1,0 +1,28 @@
+// highs_b200/csrc/setup_kernels.hpp -- device-side PDHG_Scale_Data (see setup_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace b200 {
+
+// the standard form's column-major matrix and vectors, resident on the device (standard-form order)
+struct DevForm {
+  int n, m, nnz;
+  const int* cbeg;   // [n+1]
+  const int* cidx;   // [nnz] row of each nonzero
+  int* colof;        // [nnz] column of each nonzero (filled by device_scale_ruiz)
+  double* cval;      // [nnz] scaled in place
+  double *cost, *lower, *upper, *colscale;   // [n]
+  double *rhs, *rowscale;                    // [m]
+};
+struct DevScaleScratch {
+  double *cs, *cnorm;   // [n]
+  double *rs, *rnorm;   // [m]
+  double* amax;         // [1] max |a_ij| of the scaled matrix
+};
+
+// the 10 Ruiz passes (cupdlp_scaling.c:47-120); needs nothing but the column-major matrix
+void device_scale_ruiz(cudaStream_t s, const DevForm& F, DevScaleScratch& w);
+// the Pock-Chambolle pass (:174-231); rptr[m+1] / rpos[nnz] = device copy of the row-major index of the nonzeros
+void device_scale_pock_chambolle(cudaStream_t s, const DevForm& F, DevScaleScratch& w, const int* rptr, const int* rpos);
+
+}  // namespace b200

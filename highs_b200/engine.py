@@ -38,7 +38,7 @@ class CParams(C.Structure):
                 ("tol_gap", C.c_double), ("time_limit", C.c_double), ("scaling", C.c_int32),
                 ("adaptive_step", C.c_int32), ("restart", C.c_int32), ("log_level", C.c_int32),
                 ("check_interval", C.c_int32), ("device", C.c_int32), ("graph_passes", C.c_int32),
-                ("ordered_max", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("ordered_max", C.c_int32), ("device_scaling", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class CWarm(C.Structure):

@@ -77,7 +77,9 @@ typedef struct {
   int32_t graph_passes;      /* PDHG passes captured per CUDA graph; 0 -> check_interval */
   int32_t ordered_max;       /* problems with max(cols,rows) <= this reduce in the reference's
                                 sequential order (bit-identical trajectories); 0 -> 4096, <0 -> off */
-  int32_t reserved[3];
+  int32_t device_scaling;    /* 1 = run the Ruiz / Pock-Chambolle scaling passes on the GPU (bit-identical to the host
+                                passes; opt-in until it has been validated on hardware); 0 = host threads */
+  int32_t reserved[2];
 } b200pdlp_params;
 
 /* Hot start = incoming HighsSolution when value_valid && dual_valid
