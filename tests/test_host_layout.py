@@ -89,3 +89,17 @@ def test_layout_ragged():
     for world in (1, 2, 4):
         _check(lp, world)
         _check(lp, world, ordered_max=-1)
+
+
+@pytest.mark.parametrize("shape", ["no_rows", "no_cols", "no_nnz", "empty"])
+def test_layout_degenerate(shape):
+    from highs_b200.lp import HighsLp, HighsSparseMatrix, kHighsInf
+    n, m = {"no_rows": (3, 0), "no_cols": (0, 2), "no_nnz": (2, 2), "empty": (0, 0)}[shape]
+    lp = HighsLp(n, m, np.ones(n), np.zeros(n), np.full(n, kHighsInf), np.zeros(m), np.full(m, kHighsInf),
+                 HighsSparseMatrix(n, m, np.zeros(n + 1, dtype=np.int32), np.zeros(0, dtype=np.int32), np.zeros(0)), 1, 0.0, shape)
+    f = engine.host_form(lp, 1)
+    assert (f["n"], f["m"], f["nnz"]) == (n, m, 0) and f["amax"] == 0.0
+    for world in (1, 2, 3):
+        r = engine.host_layout_eval(lp, world=world)
+        assert np.all(r["ax"] == 0.0) and np.all(r["aty"] == 0.0)
+        assert int(r["stats"][0][0]) == 0 and int(r["stats"][-1][1]) == m
