@@ -635,6 +635,7 @@ void build_layout(StdForm& f, int rank, int world, int ordered_max, HostLayout& 
     std::vector<int> colpos(n);                                   // old column -> position in the segmented x
     for (int j = 0; j < n; j++) colpos[j] = (int)L.seg_pos(L.cinv[j]);
     build_sell(L.csr_local, L.rperm, colpos, long_threshold, L.A);
+    L.A.ncols = world * L.seg_len;   // column ids are positions in the segmented x
     // rows of A_g^T in an order sorted by LOCAL length (windows of the global device order, so that
     // nearby outputs stay nearby); the kernel writes through at_outpos
     std::vector<int> ordered_rowptr(n + 1, 0);
@@ -649,19 +650,23 @@ void build_layout(StdForm& f, int rank, int world, int ordered_max, HostLayout& 
 }
 
 void sell_apply_host(const SellMatrix& a, const double* xin, double* out) {
+  // exactly what spmv_sell_kernel does: EVERY lane of a slice runs over the slice's full length (padding included),
+  // so padding must be (col 0, val 0) and every column id must be a valid position of the input vector
   const int nslices = (int)a.slices.size();
   for (int s = 0; s < nslices; s++) {
     const SellMatrix::Slice& sl = a.slices[s];
     for (int l = 0; l < 32; l++) {
       const int row = s * 32 + l;
-      if (row >= a.nrows) continue;
-      if ((sl.skipmask >> l) & 1u) continue;
+      const bool live = row < a.nrows && !((sl.skipmask >> l) & 1u);
       double acc = 0.0;
       for (int k = 0; k < sl.len; k++) {
         const size_t q = (size_t)sl.ptr + 32 * (size_t)k + l;
+        if (q >= a.col.size() || a.col[q] < 0 || a.col[q] >= a.ncols)
+          throw std::runtime_error("sliced ELL: column id outside the input vector");
+        if (!live && (a.val[q] != 0.0 || a.col[q] != 0)) throw std::runtime_error("sliced ELL: padding is not (0, 0)");
         acc += a.val[q] * xin[a.col[q]];
       }
-      out[row] = acc;
+      if (live) out[row] = acc;
     }
   }
   for (const SellMatrix::LongRow& lr : a.long_rows) {
@@ -669,7 +674,10 @@ void sell_apply_host(const SellMatrix& a, const double* xin, double* out) {
     for (int sg = 0; sg < lr.nseg; sg++) {
       const SellMatrix::Seg& g = a.segs[lr.first_seg + sg];
       double part = 0.0;
-      for (int q = g.nnz_begin; q < g.nnz_end; q++) part += a.lval[q] * xin[a.lcol[q]];
+      for (int q = g.nnz_begin; q < g.nnz_end; q++) {
+        if (a.lcol[q] < 0 || a.lcol[q] >= a.ncols) throw std::runtime_error("sliced ELL: long-row column id outside the input vector");
+        part += a.lval[q] * xin[a.lcol[q]];
+      }
       total += part;
     }
     out[lr.row] = total;
