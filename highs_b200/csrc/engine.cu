@@ -115,13 +115,24 @@ struct DeviceMatrix {
   DevBuf<int4> slices, segs, long_rows;
   DevBuf<unsigned> long_counter;
   DevSell dev{};
+  // descriptors only; col/val/lcol/lval are allocated (lcol/lval zeroed) for a device-side fill
+  void upload_plan() {
+    col.alloc((size_t)host.padded + 32, false);
+    val.alloc((size_t)host.padded + 32, false);
+    lcol.alloc((size_t)host.lcount);
+    lval.alloc((size_t)host.lcount);
+    finish_upload();
+  }
   void upload() {
-    static_assert(sizeof(SellMatrix::Slice) == sizeof(int4) && sizeof(SellMatrix::Seg) == sizeof(int4) &&
-                  sizeof(SellMatrix::LongRow) == sizeof(int4), "descriptor layouts");
     col.from(host.col);
     val.from(host.val);
     lcol.from(host.lcol);
     lval.from(host.lval);
+    finish_upload();
+  }
+  void finish_upload() {
+    static_assert(sizeof(SellMatrix::Slice) == sizeof(int4) && sizeof(SellMatrix::Seg) == sizeof(int4) &&
+                  sizeof(SellMatrix::LongRow) == sizeof(int4), "descriptor layouts");
     slices.alloc(host.slices.size(), false);
     slices.upload(reinterpret_cast<const int4*>(host.slices.data()), host.slices.size());
     segs.alloc(host.segs.size(), false);
@@ -279,44 +290,68 @@ struct Laps {
   }
 };
 
-// params.device_scaling: PDHG_Scale_Data on the GPU (setup_kernels.cu).  The unscaled column-major matrix and the
+// params.device_scaling >= 1: PDHG_Scale_Data on the GPU (setup_kernels.cu).  The unscaled column-major matrix and the
 // vectors go up once, the 10 Ruiz passes run while the host builds the row-major index of the nonzeros (which the
 // Pock-Chambolle row sums and, later, the row-major layout need anyway), and the scaled data come back into `f`, so the
 // rest of the prologue is unchanged.  Bit-identical to host_prep.cpp::scale.
-template <class Lap>
-static void scale_on_device(StdForm& f, Lap& lap) {
+// params.device_scaling >= 2 (one GPU): the scaled matrix stays in HBM and the sliced-ELL bodies of A and A' are
+// filled there from the host's PLAN (fill_layouts), so neither layout is built on the host or sent over PCIe.
+struct DeviceSetup {
   cudaStream_t s = nullptr;
-  CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-  struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } guard{s};
-  const int n = f.n, m = f.m, nnz = f.nnz;
+  int n = 0, m = 0, nnz = 0;
   DevBuf<int> cbeg, cidx, colof, rptr, rpos;
   DevBuf<double> cval, cost, lower, upper, colscale, rhs, rowscale, cs, cnorm, rs, rnorm, amax;
-  cbeg.from(f.cbeg); cidx.from(f.cidx); cval.from(f.cval);
-  cost.from(f.cost); lower.from(f.lower); upper.from(f.upper); colscale.from(f.col_scale);
-  rhs.from(f.rhs); rowscale.from(f.row_scale);
-  colof.alloc(nnz, false);
-  cs.alloc(n, false); cnorm.alloc(n, false); rs.alloc(m, false); rnorm.alloc(m, false); amax.alloc(1);
-  lap("scale: upload");
-  DevForm F{n, m, nnz, cbeg.p, cidx.p, colof.p, cval.p, cost.p, lower.p, upper.p, colscale.p, rhs.p, rowscale.p};
-  DevScaleScratch w{cs.p, cnorm.p, rs.p, rnorm.p, amax.p};
-  device_scale_ruiz(s, F, w);
-  CUDA_OK(cudaGetLastError());
-  if (f.rptr.empty()) build_row_index(f);          // host threads, while the device runs the Ruiz passes
-  rptr.from(f.rptr); rpos.from(f.rpos);
-  lap("scale: row index (host) + Ruiz (device)");
-  device_scale_pock_chambolle(s, F, w, rptr.p, rpos.p);
-  CUDA_OK(cudaGetLastError());
-  auto down = [&](auto& dst, const auto& src) {
-    if (!dst.empty()) CUDA_OK(cudaMemcpyAsync(dst.data(), src.p, dst.size() * sizeof(dst[0]), cudaMemcpyDeviceToHost, s));
-  };
-  down(f.cval, cval); down(f.cost, cost); down(f.lower, lower); down(f.upper, upper); down(f.col_scale, colscale);
-  down(f.rhs, rhs); down(f.row_scale, rowscale);
-  double am = 0.0;
-  CUDA_OK(cudaMemcpyAsync(&am, amax.p, sizeof(double), cudaMemcpyDeviceToHost, s));
-  CUDA_OK(cudaStreamSynchronize(s));
-  f.amax = am;
-  lap("scale: Pock-Chambolle + download");
-}
+  DeviceSetup() { CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); }
+  ~DeviceSetup() { if (s) cudaStreamDestroy(s); }
+  DeviceSetup(const DeviceSetup&) = delete;
+  DeviceSetup& operator=(const DeviceSetup&) = delete;
+
+  template <class Lap>
+  void scale(StdForm& f, Lap& lap) {
+    n = f.n; m = f.m; nnz = f.nnz;
+    cbeg.from(f.cbeg); cidx.from(f.cidx); cval.from(f.cval);
+    cost.from(f.cost); lower.from(f.lower); upper.from(f.upper); colscale.from(f.col_scale);
+    rhs.from(f.rhs); rowscale.from(f.row_scale);
+    colof.alloc(nnz, false);
+    cs.alloc(n, false); cnorm.alloc(n, false); rs.alloc(m, false); rnorm.alloc(m, false); amax.alloc(1);
+    lap("scale: upload");
+    DevForm F{n, m, nnz, cbeg.p, cidx.p, colof.p, cval.p, cost.p, lower.p, upper.p, colscale.p, rhs.p, rowscale.p};
+    DevScaleScratch w{cs.p, cnorm.p, rs.p, rnorm.p, amax.p};
+    device_scale_ruiz(s, F, w);
+    CUDA_OK(cudaGetLastError());
+    if (f.rptr.empty()) build_row_index(f);          // host threads, while the device runs the Ruiz passes
+    rptr.from(f.rptr); rpos.from(f.rpos);
+    lap("scale: row index (host) + Ruiz (device)");
+    device_scale_pock_chambolle(s, F, w, rptr.p, rpos.p);
+    CUDA_OK(cudaGetLastError());
+    auto down = [&](auto& dst, const auto& src) {
+      if (!dst.empty()) CUDA_OK(cudaMemcpyAsync(dst.data(), src.p, dst.size() * sizeof(dst[0]), cudaMemcpyDeviceToHost, s));
+    };
+    down(f.cval, cval); down(f.cost, cost); down(f.lower, lower); down(f.upper, upper); down(f.col_scale, colscale);
+    down(f.rhs, rhs); down(f.row_scale, rowscale);
+    double am = 0.0;
+    CUDA_OK(cudaMemcpyAsync(&am, amax.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    f.amax = am;
+    lap("scale: Pock-Chambolle + download");
+  }
+
+  // device-side fill of one planned matrix (world == 1): which = 0: A from the row-major index, 1: A' from the columns
+  void fill(DeviceMatrix& M, int which, const std::vector<int>& perm, const std::vector<int>& colmap) {
+    const SellMatrix& h = M.host;
+    DevBuf<int> dperm, dcolmap;
+    dperm.from(perm); dcolmap.from(colmap);
+    M.upload_plan();
+    SellSource S{};
+    if (which == 0) { S.beg = rptr.p; S.end = rptr.p + 1; S.pos = rpos.p; S.idx = colof.p; }
+    else { S.beg = cbeg.p; S.end = cbeg.p + 1; S.pos = nullptr; S.idx = cidx.p; }
+    S.val = cval.p; S.idx_offset = 0; S.colmap = dcolmap.p;
+    device_fill_sell(s, h.nrows, (int)h.slices.size(), M.slices.p, dperm.p, S, M.col.p, M.val.p, h.padded,
+                     (int)h.long_rows.size(), M.long_rows.p, M.segs.p, M.lcol.p, M.lval.p);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(s));   // dperm / dcolmap go out of scope
+  }
+};
 
 static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, int rank, int world, b200pdlp_problem* p) {
   int ndev = 0;
@@ -337,14 +372,20 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   };
   formulate(lp, p->form);
   lap("formulate");
-  if (prm.scaling != 0 && prm.device_scaling != 0 && p->form.nnz > 0) scale_on_device(p->form, lap);
-  else scale(p->form, prm.scaling != 0);
+  std::unique_ptr<DeviceSetup> dev_setup;
+  if (prm.scaling != 0 && prm.device_scaling != 0 && p->form.nnz > 0) {
+    dev_setup.reset(new DeviceSetup());
+    dev_setup->scale(p->form, lap);
+  } else {
+    scale(p->form, prm.scaling != 0);
+  }
   lap("scale");
   StdForm& f = p->form;
   {
     // host layout (row block, device orderings, sliced-ELL of A_g and A_g^T): host_prep.cpp build_layout
     HostLayout L;
-    build_layout(f, rank, world, prm.ordered_max, L, lap);
+    const bool device_fill = dev_setup && prm.device_scaling >= 2 && world == 1;
+    build_layout(f, rank, world, prm.ordered_max, L, lap, /*plan_only=*/device_fill);
     p->r0 = L.r0; p->r1 = L.r1; p->ml = L.ml; p->neq_local = L.neq_local; p->ordered = L.ordered;
     p->row_bounds = L.bounds;
     p->n = f.n; p->m = f.m;
@@ -357,9 +398,16 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   }
   const int n = p->n, ml = p->ml;
   CUDA_OK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
-  p->A.upload();
-  p->AT.upload();
-  lap("matrix upload");
+  if (dev_setup && prm.device_scaling >= 2 && world == 1) {
+    dev_setup->fill(p->A, 0, p->rperm, p->cinv);
+    dev_setup->fill(p->AT, 1, p->cperm, p->rinv);
+    lap("sliced-ELL fill (device)");
+  } else {
+    p->A.upload();
+    p->AT.upload();
+    lap("matrix upload");
+  }
+  dev_setup.reset();
   if (const char* e = getenv("B200PDLP_PREFETCH")) { p->A.dev.prefetch_dist = atoi(e); p->AT.dev.prefetch_dist = atoi(e); }
   const int nl = p->nl;
   for (int k = 0; k < 2; k++) { p->x[k].alloc(nl); p->aty[k].alloc(nl); p->y[k].alloc(ml); p->ax[k].alloc(ml); }
@@ -1262,7 +1310,14 @@ int b200pdlp_problem_get_vector(const b200pdlp_problem* p, int32_t which, double
 
 int b200pdlp_problem_get_csr(const b200pdlp_problem* p, int32_t* rowptr, int32_t* col, double* val) {
   if (!p || !rowptr || !col || !val) return B200PDLP_ERR_ARG;
-  const Csr& a = p->csr_local;
+  Csr lazy;
+  if (p->csr_local.rowptr.empty()) {
+    // device-filled layouts keep no host copy: rebuild it from the (downloaded) scaled form on demand
+    StdForm& f = const_cast<StdForm&>(p->form);
+    if (f.rptr.empty()) build_row_index(f);
+    build_row_major(f, p->r0, p->r1, lazy);
+  }
+  const Csr& a = p->csr_local.rowptr.empty() ? lazy : p->csr_local;
   memcpy(rowptr, a.rowptr.data(), (size_t)(a.nrows + 1) * sizeof(int));
   memcpy(col, a.col.data(), (size_t)a.nnz * sizeof(int));
   memcpy(val, a.val.data(), (size_t)a.nnz * sizeof(double));
@@ -1652,6 +1707,20 @@ int b200pdlp_form_layout_eval(b200pdlp_form* fh, int32_t rank, int32_t world, in
       tl = t1;
     });
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (world == 1) {
+      // the plan-only path (device-side fill) must produce the same orderings and descriptors
+      HostLayout P;
+      build_layout(f, rank, world, ordered_max, P, nullptr, /*plan_only=*/true);
+      auto same_plan = [](const SellMatrix& a, const SellMatrix& b) {
+        return a.nrows == b.nrows && a.padded == b.padded && a.lcount == b.lcount && a.n_partials == b.n_partials &&
+               a.slices.size() == b.slices.size() && a.segs.size() == b.segs.size() && a.long_rows.size() == b.long_rows.size() &&
+               (a.slices.empty() || !memcmp(a.slices.data(), b.slices.data(), a.slices.size() * sizeof(a.slices[0]))) &&
+               (a.segs.empty() || !memcmp(a.segs.data(), b.segs.data(), a.segs.size() * sizeof(a.segs[0]))) &&
+               (a.long_rows.empty() || !memcmp(a.long_rows.data(), b.long_rows.data(), a.long_rows.size() * sizeof(a.long_rows[0])));
+      };
+      if (P.rperm != L.rperm || P.cperm != L.cperm || !same_plan(P.A, L.A) || !same_plan(P.AT, L.AT))
+        throw Error(B200PDLP_ERR_STATE, "plan-only layout differs from the full layout");
+    }
     const int n = f.n, ml = L.ml;
     // x in the kernel-facing layout: device column order, segmented when world > 1
     std::vector<double> xin((size_t)L.world * L.seg_len + 8, 0.0), out_rows((size_t)std::max(ml, 1), 0.0);

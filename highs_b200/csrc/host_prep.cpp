@@ -530,22 +530,25 @@ std::vector<int> invert_perm(const std::vector<int>& perm) {
   return inv;
 }
 
-void build_sell(const Csr& a, const std::vector<int>& perm, const std::vector<int>& colmap, int long_threshold,
-                SellMatrix& out) {
+// The PLAN of a sliced-ELL matrix depends only on the row lengths: slice offsets and lengths, masked lanes, long-row
+// segments and their offsets in the long-row arrays.  The arrays themselves are filled afterwards -- by the host
+// (fill_sell_host) or, given the plan, by a device kernel that reads the scaled matrix where it already lies in HBM.
+void plan_sell(int nrows, int ncols, long long nnz, const std::vector<int>& perm, const std::function<int(int)>& old_row_len,
+               int long_threshold, SellMatrix& out) {
   out = SellMatrix();
-  out.nrows = a.nrows;
-  out.ncols = a.ncols;
-  out.nnz = a.nnz;
-  const int nslices = (a.nrows + 31) / 32;
+  out.nrows = nrows;
+  out.ncols = ncols;
+  out.nnz = nnz;
+  const int nslices = (nrows + 31) / 32;
   out.slices.resize(nslices);
-  auto len = [&](int newrow) { const int r = perm[newrow]; return a.rowptr[r + 1] - a.rowptr[r]; };
+  auto len = [&](int newrow) { return old_row_len(perm[newrow]); };
   long long total = 0;
   for (int s = 0; s < nslices; s++) {
     int mx = 0;
     unsigned mask = 0;
     for (int l = 0; l < 32; l++) {
       const int nr = s * 32 + l;
-      if (nr >= a.nrows) { mask |= 1u << l; continue; }
+      if (nr >= nrows) { mask |= 1u << l; continue; }
       const int ln = len(nr);
       if (ln > long_threshold) { mask |= 1u << l; continue; }
       mx = std::max(mx, ln);
@@ -555,6 +558,27 @@ void build_sell(const Csr& a, const std::vector<int>& perm, const std::vector<in
     total += 32LL * mx;
   }
   out.padded = total;
+  // long rows -> segments of kNnzPerBlock entries; a row's entries start 16-byte aligned in lcol / lval
+  long long lpos = 0;
+  for (int nr = 0; nr < nrows; nr++) {
+    const int ln = len(nr);
+    if (ln <= long_threshold) continue;
+    const int nseg = (ln + kNnzPerBlock - 1) / kNnzPerBlock;
+    const int base = (int)lpos;
+    out.long_rows.push_back({nr, (int)out.segs.size(), nseg, out.n_partials});
+    for (int sg = 0; sg < nseg; sg++)
+      out.segs.push_back({nr, base + sg * kNnzPerBlock, std::min(base + (sg + 1) * kNnzPerBlock, base + ln), (int)out.long_rows.size() - 1});
+    out.n_partials += nseg;
+    lpos += ln;
+    lpos = (lpos + 3) / 4 * 4;
+    if (lpos > 2000000000LL) throw std::runtime_error("b200pdlp: long rows too large for 32-bit offsets");
+  }
+  out.lcount = lpos + 8;
+}
+
+void fill_sell_host(const Csr& a, const std::vector<int>& perm, const std::vector<int>& colmap, SellMatrix& out) {
+  const long long total = out.padded;
+  const int nslices = (int)out.slices.size();
   out.col.resize((size_t)total + 32);   // uninitialised: every slot is written below, by the thread that owns the slice
   out.val.resize((size_t)total + 32);
   for (int q = 0; q < 32; q++) { out.col[(size_t)total + q] = 0; out.val[(size_t)total + q] = 0.0; }
@@ -577,26 +601,23 @@ void build_sell(const Csr& a, const std::vector<int>& perm, const std::vector<in
       }
     }
   }, 256);
-  // long rows -> segments
-  for (int nr = 0; nr < a.nrows; nr++) {
-    const int ln = len(nr);
-    if (ln <= long_threshold) continue;
-    const int r = perm[nr];
-    const int nseg = (ln + kNnzPerBlock - 1) / kNnzPerBlock;
-    const int base = (int)out.lcol.size();
-    out.long_rows.push_back({nr, (int)out.segs.size(), nseg, out.n_partials});
-    for (int p = a.rowptr[r]; p < a.rowptr[r + 1]; p++) { out.lcol.push_back(colmap[a.col[p]]); out.lval.push_back(a.val[p]); }
-    for (int sg = 0; sg < nseg; sg++)
-      out.segs.push_back({nr, base + sg * kNnzPerBlock, std::min(base + (sg + 1) * kNnzPerBlock, base + ln), (int)out.long_rows.size() - 1});
-    out.n_partials += nseg;
-    while (out.lcol.size() % 4) { out.lcol.push_back(0); out.lval.push_back(0.0); }   // segments start 16-byte aligned
+  out.lcol.assign((size_t)out.lcount, 0);
+  out.lval.assign((size_t)out.lcount, 0.0);
+  for (const SellMatrix::LongRow& lr : out.long_rows) {
+    const int r = perm[lr.row];
+    int q = out.segs[lr.first_seg].nnz_begin;
+    for (int p = a.rowptr[r]; p < a.rowptr[r + 1]; p++, q++) { out.lcol[q] = colmap[a.col[p]]; out.lval[q] = a.val[p]; }
   }
-  out.lcol.resize(out.lcol.size() + 8, 0);
-  out.lval.resize(out.lval.size() + 8, 0.0);
+}
+
+void build_sell(const Csr& a, const std::vector<int>& perm, const std::vector<int>& colmap, int long_threshold,
+                SellMatrix& out) {
+  plan_sell(a.nrows, a.ncols, a.nnz, perm, [&](int r) { return a.rowptr[r + 1] - a.rowptr[r]; }, long_threshold, out);
+  fill_sell_host(a, perm, colmap, out);
 }
 
 void build_layout(StdForm& f, int rank, int world, int ordered_max, HostLayout& L,
-                  const std::function<void(const char*)>& lap) {
+                  const std::function<void(const char*)>& lap, bool plan_only) {
   auto mark = [&](const char* what) { if (lap) lap(what); };
   L = HostLayout();
   L.rank = rank; L.world = world;
@@ -613,6 +634,20 @@ void build_layout(StdForm& f, int rank, int world, int ordered_max, HostLayout& 
   L.neq_local = std::max(0, std::min(f.neq - L.r0, ml));
   Csr at;
   if (f.rptr.empty()) build_row_index(f);
+  if (plan_only) {
+    if (world != 1) throw std::runtime_error("b200pdlp: plan-only layouts are single-GPU");
+    L.rperm = make_perm(f.rptr, L.neq_local, sort);
+    L.cperm = make_perm(f.cbeg, n, sort);
+    L.rinv = invert_perm(L.rperm);
+    L.cinv = invert_perm(L.cperm);
+    mark("length sorts");
+    L.nl = L.nl_real = n; L.c0 = 0; L.shard_len = n; L.seg_len = n;
+    plan_sell(f.m, n, f.nnz, L.rperm, [&](int r) { return f.rptr[r + 1] - f.rptr[r]; }, long_threshold, L.A);
+    plan_sell(n, f.m, f.nnz, L.cperm, [&](int j) { return f.cbeg[j + 1] - f.cbeg[j]; }, long_threshold, L.AT);
+    L.csr_local.nrows = f.m; L.csr_local.ncols = n; L.csr_local.nnz = f.nnz;   // dimensions only
+    mark("sliced-ELL plan");
+    return;
+  }
   build_row_major(f, L.r0, L.r1, L.csr_local);
   mark("row-major transpose");
   build_col_major(f, L.r0, L.r1, at);

@@ -80,6 +80,7 @@ struct SellMatrix {
   std::vector<int> lcol;
   std::vector<double> lval;
   int n_partials = 0;
+  long long lcount = 0;      // entries of lcol / lval (rows padded to multiples of 4, + 8)
 };
 
 constexpr int kNnzPerBlock = 2048;   // long-row segment size (== kernels.cuh kNnzBlk)
@@ -101,6 +102,10 @@ std::vector<int> invert_perm(const std::vector<int>& perm);
 // rows of `a` taken in `perm` order, column ids mapped through `colmap` (old -> new)
 void build_sell(const Csr& a, const std::vector<int>& perm, const std::vector<int>& colmap, int long_threshold,
                 SellMatrix& out);
+// the two halves of build_sell: the plan (descriptors only; needs nothing but the row lengths) and the host fill
+void plan_sell(int nrows, int ncols, long long nnz, const std::vector<int>& perm, const std::function<int(int)>& old_row_len,
+               int long_threshold, SellMatrix& out);
+void fill_sell_host(const Csr& a, const std::vector<int>& perm, const std::vector<int>& colmap, SellMatrix& out);
 
 // Everything the device needs to know about one rank's share of the matrix (host side of
 // b200pdlp_problem_create; also what b200pdlp_form_layout_eval evaluates without a GPU).
@@ -125,8 +130,10 @@ struct HostLayout {
   size_t seg_pos(int j) const { return world == 1 ? (size_t)j : (size_t)(j / shard_len) * seg_len + (size_t)(j % shard_len); }
 };
 // `lap`, if given, is called with a stage name after every stage (timing hook)
+// plan_only (world == 1): only the orderings and the sliced-ELL PLANS (A.col/val and csr_local stay empty) -- the
+// arrays are then filled on the device from the scaled matrix resident there
 void build_layout(StdForm& f, int rank, int world, int ordered_max, HostLayout& L,
-                  const std::function<void(const char*)>& lap = nullptr);
+                  const std::function<void(const char*)>& lap = nullptr, bool plan_only = false);
 // host evaluation of a sliced-ELL matrix exactly as the kernels traverse it (body: lane = row, k ascending;
 // long rows: per-segment partial sums, added in segment order): out[row] for row < nrows
 void sell_apply_host(const SellMatrix& a, const double* xin, double* out);

@@ -169,3 +169,64 @@ void device_scale_pock_chambolle(cudaStream_t s, const DevForm& F, DevScaleScrat
 }
 
 }  // namespace b200
+
+// ------------------------------------------------------------------ sliced-ELL fill on the device
+// Given the PLAN of a sliced-ELL matrix (host_prep.cpp::plan_sell: slice offsets / lengths / masks, long-row
+// segments) the body and the long-row arrays are filled straight from the scaled matrix in HBM, so the 100 MB
+// layouts are never built on the host nor sent over PCIe.  One warp per slice, lane = row: the lane walks ITS
+// row's entries in source order (row-major index for A, a column's storage order for A') and stores them k-major /
+// lane-minor, i.e. fully coalesced; padding is written as (0, 0) by the same lane.
+namespace b200 {
+namespace {
+__global__ void __launch_bounds__(kTpb)
+fill_sell_body_kernel(int nrows, int nslices, const int4* __restrict__ slices, const int* __restrict__ perm, SellSource S,
+                      int* __restrict__ col, double* __restrict__ val) {
+  const int s = (blockIdx.x * kTpb + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= nslices) return;
+  const int4 sl = slices[s];
+  const int row = s * 32 + lane;
+  const bool live = row < nrows && !(((unsigned)sl.z >> lane) & 1u);
+  int b = 0, ln = 0;
+  if (live) { const int r = perm[row]; b = S.beg[r]; ln = S.end[r] - b; }
+  for (int k = 0; k < sl.y; k++) {
+    int c = 0;
+    double v = 0.0;
+    if (k < ln) {
+      const int q = b + k;
+      const int src = S.pos ? S.pos[q] : q;
+      c = S.colmap[S.idx[src] - S.idx_offset];
+      v = S.val[src];
+    }
+    const size_t o = (size_t)sl.x + 32 * (size_t)k + lane;
+    col[o] = c;
+    val[o] = v;
+  }
+}
+
+// one CTA per long row: its entries, in source order, into lcol / lval at the offset the plan assigned
+__global__ void __launch_bounds__(kTpb)
+fill_sell_long_kernel(const int4* __restrict__ long_rows, const int4* __restrict__ segs, const int* __restrict__ perm,
+                      SellSource S, int* __restrict__ lcol, double* __restrict__ lval) {
+  const int4 lr = long_rows[blockIdx.x];
+  const int r = perm[lr.x];
+  const int b = S.beg[r], ln = S.end[r] - b;
+  const int base = segs[lr.y].y;
+  for (int e = threadIdx.x; e < ln; e += kTpb) {
+    const int q = b + e;
+    const int src = S.pos ? S.pos[q] : q;
+    lcol[base + e] = S.colmap[S.idx[src] - S.idx_offset];
+    lval[base + e] = S.val[src];
+  }
+}
+}  // namespace
+
+void device_fill_sell(cudaStream_t s, int nrows, int nslices, const int4* slices, const int* perm, const SellSource& S,
+                      int* col, double* val, long long padded, int n_long, const int4* long_rows, const int4* segs,
+                      int* lcol, double* lval) {
+  if (nslices > 0) fill_sell_body_kernel<<<warp_grid(nslices), kTpb, 0, s>>>(nrows, nslices, slices, perm, S, col, val);
+  cudaMemsetAsync(col + padded, 0, 32 * sizeof(int), s);
+  cudaMemsetAsync(val + padded, 0, 32 * sizeof(double), s);
+  if (n_long > 0) fill_sell_long_kernel<<<n_long, kTpb, 0, s>>>(long_rows, segs, perm, S, lcol, lval);
+}
+
+}  // namespace b200
