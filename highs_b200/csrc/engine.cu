@@ -193,6 +193,7 @@ struct b200pdlp_problem {
   DevBuf<int> at_outpos;           // A_g^T body row -> position in the segmented partial vector
   // fused P2P path
   std::vector<int> row_bounds;     // row offsets of every rank's block
+  bool device_filled = false;      // the sliced-ELL arrays were filled on the device (params.device_scaling >= 2)
   bool local_link = false;         // peers are problems of this process (logical shards, b200pdlp_p2p_link_local)
   bool p2p = false;
   int p2p_pull = 0;                // 1: the primal kernel reads the peers' partials over NVLink; 0: peers push them
@@ -384,7 +385,9 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   {
     // host layout (row block, device orderings, sliced-ELL of A_g and A_g^T): host_prep.cpp build_layout
     HostLayout L;
-    const bool device_fill = dev_setup && prm.device_scaling >= 2 && world == 1;
+    // (unsorted columns: the host path re-sorts them, the device fill reads storage order -- stay on the host then)
+    const bool device_fill = dev_setup && prm.device_scaling >= 2 && world == 1 && columns_sorted(f);
+    p->device_filled = device_fill;
     build_layout(f, rank, world, prm.ordered_max, L, lap, /*plan_only=*/device_fill);
     p->r0 = L.r0; p->r1 = L.r1; p->ml = L.ml; p->neq_local = L.neq_local; p->ordered = L.ordered;
     p->row_bounds = L.bounds;
@@ -398,7 +401,7 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   }
   const int n = p->n, ml = p->ml;
   CUDA_OK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
-  if (dev_setup && prm.device_scaling >= 2 && world == 1) {
+  if (p->device_filled) {
     dev_setup->fill(p->A, 0, p->rperm, p->cinv);
     dev_setup->fill(p->AT, 1, p->cperm, p->rinv);
     lap("sliced-ELL fill (device)");
