@@ -116,11 +116,15 @@ struct DeviceMatrix {
   DevBuf<unsigned> long_counter;
   DevSell dev{};
   // descriptors only; col/val/lcol/lval are allocated (lcol/lval zeroed) for a device-side fill
-  void upload_plan() {
+  // (the long-row arrays are cleared on the stream the fill kernels run on: a cudaMemset on the legacy stream is not
+  //  ordered against a non-blocking stream)
+  void upload_plan(cudaStream_t s) {
     col.alloc((size_t)host.padded + 32, false);
     val.alloc((size_t)host.padded + 32, false);
-    lcol.alloc((size_t)host.lcount);
-    lval.alloc((size_t)host.lcount);
+    lcol.alloc((size_t)host.lcount, false);
+    lval.alloc((size_t)host.lcount, false);
+    CUDA_OK(cudaMemsetAsync(lcol.p, 0, std::max<size_t>((size_t)host.lcount, 1) * sizeof(int), s));
+    CUDA_OK(cudaMemsetAsync(lval.p, 0, std::max<size_t>((size_t)host.lcount, 1) * sizeof(double), s));
     finish_upload();
   }
   void upload() {
@@ -314,7 +318,7 @@ struct DeviceSetup {
     cost.from(f.cost); lower.from(f.lower); upper.from(f.upper); colscale.from(f.col_scale);
     rhs.from(f.rhs); rowscale.from(f.row_scale);
     colof.alloc(nnz, false);
-    cs.alloc(n, false); cnorm.alloc(n, false); rs.alloc(m, false); rnorm.alloc(m, false); amax.alloc(1);
+    cs.alloc(n, false); cnorm.alloc(n, false); rs.alloc(m, false); rnorm.alloc(m, false); amax.alloc(1, false);
     lap("scale: upload");
     DevForm F{n, m, nnz, cbeg.p, cidx.p, colof.p, cval.p, cost.p, lower.p, upper.p, colscale.p, rhs.p, rowscale.p};
     DevScaleScratch w{cs.p, cnorm.p, rs.p, rnorm.p, amax.p};
@@ -342,7 +346,7 @@ struct DeviceSetup {
     const SellMatrix& h = M.host;
     DevBuf<int> dperm, dcolmap;
     dperm.from(perm); dcolmap.from(colmap);
-    M.upload_plan();
+    M.upload_plan(s);
     SellSource S{};
     if (which == 0) { S.beg = rptr.p; S.end = rptr.p + 1; S.pos = rpos.p; S.idx = colof.p; }
     else { S.beg = cbeg.p; S.end = cbeg.p + 1; S.pos = nullptr; S.idx = cidx.p; }
