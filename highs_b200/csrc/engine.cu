@@ -378,7 +378,9 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   formulate(lp, p->form);
   lap("formulate");
   std::unique_ptr<DeviceSetup> dev_setup;
-  if (prm.scaling != 0 && prm.device_scaling != 0 && p->form.nnz > 0) {
+  int dev_level = prm.device_scaling;
+  if (const char* e = getenv("B200PDLP_DEVICE_SETUP")) dev_level = atoi(e);   // experiments: same switch from the environment
+  if (prm.scaling != 0 && dev_level != 0 && p->form.nnz > 0) {
     dev_setup.reset(new DeviceSetup());
     dev_setup->scale(p->form, lap);
   } else {
@@ -390,7 +392,7 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
     // host layout (row block, device orderings, sliced-ELL of A_g and A_g^T): host_prep.cpp build_layout
     HostLayout L;
     // (unsorted columns: the host path re-sorts them, the device fill reads storage order -- stay on the host then)
-    const bool device_fill = dev_setup && prm.device_scaling >= 2 && world == 1 && columns_sorted(f);
+    const bool device_fill = dev_setup && dev_level >= 2 && world == 1 && columns_sorted(f);
     p->device_filled = device_fill;
     build_layout(f, rank, world, prm.ordered_max, L, lap, /*plan_only=*/device_fill);
     p->r0 = L.r0; p->r1 = L.r1; p->ml = L.ml; p->neq_local = L.neq_local; p->ordered = L.ordered;
