@@ -237,8 +237,9 @@ struct b200pdlp_problem {
   ReduceScratch rs(int slot, int len) const {
     // slot-private partial arrays: 16 accumulators x kMaxEwBlocks-or-nblocks each
     double* t = (ordered && len <= ordered_cap) ? terms.p + (size_t)slot * 16 * ordered_cap : nullptr;
-    return ReduceScratch{partials.p + (size_t)slot * scratch_stride, counters.p + slot, t, len, 0};
+    return ReduceScratch{partials.p + (size_t)slot * scratch_stride, counters.p + slot, t, len, pass_flags};
   }
+  int pass_flags = 0;              // ReduceScratch::flags of the pass kernels (B200PDLP_PDL experiment: 2 or 6)
   size_t scratch_stride = 0;
   DevBuf<double> terms;            // ordered-mode term scratch
   bool ordered = false;
@@ -417,6 +418,10 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
     lap("matrix upload");
   }
   dev_setup.reset();
+  if (const char* e = getenv("B200PDLP_PDL")) {   // experiment, single GPU only: programmatic dependent launch of the pass kernels
+    const int v = atoi(e);
+    if (world == 1) p->pass_flags = v >= 2 ? 6 : (v == 1 ? 2 : 0);
+  }
   if (const char* e = getenv("B200PDLP_PREFETCH")) { p->A.dev.prefetch_dist = atoi(e); p->AT.dev.prefetch_dist = atoi(e); }
   const int nl = p->nl;
   for (int k = 0; k < 2; k++) { p->x[k].alloc(nl); p->aty[k].alloc(nl); p->y[k].alloc(ml); p->ax[k].alloc(ml); }

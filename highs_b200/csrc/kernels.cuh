@@ -92,8 +92,19 @@ struct ReduceScratch {
   // (cupdlp_linalg.c:111-126,320-336), which makes whole trajectories bit-identical.
   double* terms;      // nullptr = tree mode
   int len;            // elements per accumulator in terms[]
-  int flags;          // experiment switches (bit 0: skip the grid reduction -- timing experiments only)
+  int flags;          // experiment switches (bit 0: skip the grid reduction -- timing experiments only;
+                      //  bit 1: the kernel was launched with programmatic dependent launch: wait for the preceding
+                      //  grid before the first global read; bit 2: additionally release the dependent grid early)
 };
+
+// Programmatic dependent launch (experiment, B200PDLP_PDL): the launch latency of kernel k+1 hides behind kernel k.
+// Every pass kernel calls this before it touches anything the preceding kernel wrote (the state block first of all).
+__device__ __forceinline__ void pdl_entry(int flags) {
+  if (flags & 2) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (flags & 4) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
+}
 
 // ----------------------------------------------------------------- reductions
 __device__ __forceinline__ double warp_sum(double v) {

@@ -1,6 +1,8 @@
 // highs_b200/csrc/pdhg_kernels.cu -- kernel definitions + launchers (see kernels.cuh).
 #include "pdhg_kernels.hpp"
 
+#include <utility>
+
 namespace b200 {
 
 // =============================================================== K1: primal step
@@ -13,6 +15,7 @@ primal_step_kernel(int n, PdhgState* __restrict__ st, double* __restrict__ x0, d
                    const double* __restrict__ aty0, const double* __restrict__ aty1,
                    const double* __restrict__ c, const double* __restrict__ lo, const double* __restrict__ up,
                    double* __restrict__ xsum, ReduceScratch rs) {
+  pdl_entry(rs.flags);
   if (st->iter >= st->stop_iter) return;
   const int cur = st->cur;
   const double tau = st->tau_try, ntau = -tau;
@@ -224,6 +227,7 @@ constexpr int kStepThreads = 1024;
 __global__ void __launch_bounds__(kStepThreads)
 step_rule_kernel(PdhgState* __restrict__ st, ReduceScratch r1, int nb1, ReduceScratch r2, int nb2, ReduceScratch r3,
                  int nb3, const double* __restrict__ dy2_override) {
+  pdl_entry(r1.flags);
   if (st->iter >= st->stop_iter) return;
   __shared__ double sm[3][kStepThreads / 32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -269,6 +273,7 @@ step_rule_kernel(PdhgState* __restrict__ st, ReduceScratch r1, int nb1, ReduceSc
 template <class Epi>
 __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_arg, ReduceScratch rs) {
   Epi epi = epi_arg;
+  pdl_entry(rs.flags);
   if (!epi.begin()) return;
   const double* __restrict__ xin = epi.input();
   double acc[Epi::NACC > 0 ? Epi::NACC : 1] = {0.0};
@@ -1003,6 +1008,20 @@ __global__ void __launch_bounds__(kThreads) fill_kernel(int len, double* __restr
 }
 
 // ==================================================================== launchers
+// plain <<<>>> launch, or (flags bit 1) a launch with the programmatic-stream-serialization attribute: the grid may be
+// scheduled while its predecessor in the stream is still running; the kernel then waits in pdl_entry()
+template <class... KArgs, class... Args>
+static void launch_k(void (*kernel)(KArgs...), int grid, int block, cudaStream_t s, int flags, Args&&... args) {
+  if (!(flags & 2)) { kernel<<<grid, block, 0, s>>>(std::forward<Args>(args)...); return; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
 static inline int ew_grid(int len) {
   int g = (len + kThreads - 1) / kThreads;
   if (g < 1) g = 1;
@@ -1012,7 +1031,7 @@ static inline int ew_grid(int len) {
 void launch_primal_step(cudaStream_t s, int n, PdhgState* st, double* x0, double* x1, const double* aty0,
                         const double* aty1, const double* c, const double* lo, const double* up, double* xsum,
                         ReduceScratch rs) {
-  primal_step_kernel<<<ew_grid((n + 1) / 2), kThreads, 0, s>>>(n, st, x0, x1, aty0, aty1, c, lo, up, xsum, rs);
+  launch_k(primal_step_kernel, ew_grid((n + 1) / 2), kThreads, s, rs.flags, n, st, x0, x1, aty0, aty1, c, lo, up, xsum, rs);
 }
 
 void launch_spmv_plain(cudaStream_t s, const DevSell& A, const double* in, double* out, const PdhgState* due) {
@@ -1028,7 +1047,7 @@ void launch_spmv_dual(cudaStream_t s, const DevSell& A, PdhgState* st, const dou
   DualEpilogue e{};
   e.st = st; e.x0 = x0; e.x1 = x1; e.y0 = y0; e.y1 = y1; e.ax0 = ax0; e.ax1 = ax1; e.b = b; e.ysum = ysum;
   e.neq = neq; e.row_offset = row_offset;
-  spmv_sell_kernel<DualEpilogue><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, rs);
+  launch_k(spmv_sell_kernel<DualEpilogue>, A.nblocks_body + A.nsegs, kThreads, s, rs.flags, A, e, rs);
 }
 
 void launch_spmv_primal(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
@@ -1036,7 +1055,7 @@ void launch_spmv_primal(cudaStream_t s, const DevSell& A, PdhgState* st, const d
   if (A.nblocks_body + A.nsegs == 0) return;   // no rows on this rank: nothing to launch, the partial count is 0
   PrimalEpilogue e{};
   e.st = st; e.y0 = y0; e.y1 = y1; e.x0 = x0; e.x1 = x1; e.aty0 = aty0; e.aty1 = aty1;
-  spmv_sell_kernel<PrimalEpilogue><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, rs);
+  launch_k(spmv_sell_kernel<PrimalEpilogue>, A.nblocks_body + A.nsegs, kThreads, s, rs.flags, A, e, rs);
 }
 
 // multi-GPU K3a: partial A_g' y' into buf (input chosen by the device state)
@@ -1129,7 +1148,7 @@ void launch_step_rule_mg(cudaStream_t s, PdhgState* st, const double* xfull, int
 
 void launch_step_rule(cudaStream_t s, PdhgState* st, ReduceScratch r1, int nb1, ReduceScratch r2, int nb2,
                       ReduceScratch r3, int nb3, const double* dy2_override) {
-  step_rule_kernel<<<1, kStepThreads, 0, s>>>(st, r1, nb1, r2, nb2, r3, nb3, dy2_override);
+  launch_k(step_rule_kernel, 1, kStepThreads, s, r1.flags, st, r1, nb1, r2, nb2, r3, nb3, dy2_override);
 }
 
 int primal_step_grid(int n) { return ew_grid((n + 1) / 2); }
