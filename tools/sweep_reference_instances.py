@@ -1,0 +1,47 @@
+"""Dev-container tool (reads /root/reference): every check/instances/*.mps of the reference through the host prologue
+(formulate + scale, bit for bit against the oracle) and the device layouts of 1 and 3 ranks (host evaluation against a
+plain sparse product), in reference order and length-sorted.
+usage: python tools/sweep_reference_instances.py        last line: JSON {"ok": n, "bad": [[name, what], ...]}"""
+import glob, os, subprocess, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+from highs_b200 import engine
+from highs_b200.lp import read_b2lp
+from oracle import binding as ob
+KEYS = ["cost", "lower", "upper", "rhs", "col_scale", "row_scale", "cbeg", "cidx", "cval", "row_new_idx", "row_type", "rbeg", "ridx", "rval"]
+drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+tmp = __import__("tempfile").mkdtemp(prefix="b200inst_")
+bad = []; n_ok = 0
+for mps in sorted(glob.glob("/root/reference/check/instances/*.mps")):
+    name = os.path.basename(mps)[:-4]
+    out = f"{tmp}/{name}.b2lp"
+    try:
+        r = subprocess.run([drv, "--mps", mps, "--dump-lp", out, "--opt", "solver=pdlp", "--opt", "pdlp_iteration_limit=1", "--opt", "presolve=off"], capture_output=True, text=True, timeout=120)
+    except subprocess.TimeoutExpired:
+        print(name, "dump timeout"); continue
+    if not os.path.exists(out):
+        print(name, "no dump", r.stderr[-200:]); continue
+    lp = read_b2lp(out)
+    if lp.num_row_ == 0 or lp.a_matrix_.numNz() == 0:
+        print(name, "skipped (no rows / nnz)"); continue
+    try:
+        a, b = engine.host_form(lp, 1), ob.formulate_and_scale(lp, 1)
+        same = lambda u, v: np.array_equal(u, v, equal_nan=True) if np.asarray(u).dtype.kind == "f" else np.array_equal(u, v)
+        diffs = [k for k in KEYS if not same(a[k], b[k])] + [k for k in ("n","m","nnz","neq","amax","norm_cost","norm_rhs") if not same(a[k], b[k])]
+        import scipy.sparse as sp
+        for w in (1, 3):
+            r = engine.host_layout_eval(lp, world=w, seed=1)
+            A = sp.csc_matrix((r["cval"], r["cidx"], r["cbeg"]), shape=(r["m"], r["n"]))
+            sax = np.abs(A) @ np.abs(r["x"]) + 1e-300; say = np.abs(A).T @ np.abs(r["y"]) + 1e-300
+            if not (np.all(np.abs(r["ax"] - A @ r["x"]) <= 1e-12 * sax) and np.all(np.abs(r["aty"] - A.T @ r["y"]) <= 1e-12 * say)):
+                diffs.append(f"layout world {w}")
+            r2 = engine.host_layout_eval(lp, world=w, ordered_max=-1, seed=1)
+            if not (np.all(np.abs(r2["ax"] - A @ r2["x"]) <= 1e-12 * sax) and np.all(np.abs(r2["aty"] - A.T @ r2["y"]) <= 1e-12 * say)):
+                diffs.append(f"sorted layout world {w}")
+        if diffs: bad.append((name, diffs)); print(name, "DIFF", diffs)
+        else: n_ok += 1
+    except Exception as e:
+        bad.append((name, repr(e))); print(name, "EXC", repr(e)[:200])
+import json
+print(json.dumps({"ok": n_ok, "bad": [[k, str(v)] for k, v in bad]}))
