@@ -1,6 +1,7 @@
 """Dev-container tool (reads /root/reference): every check/instances/*.mps of the reference through the host prologue
 (formulate + scale, bit for bit against the oracle) and the device layouts of 1 and 3 ranks (host evaluation against a
-plain sparse product), in reference order and length-sorted.
+plain sparse product), in reference order and length-sorted; and the oracle against the live reference (400 iterations,
+bit for bit) on each of them.
 usage: python tools/sweep_reference_instances.py        last line: JSON {"ok": n, "bad": [[name, what], ...]}"""
 import glob, os, subprocess, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -12,7 +13,7 @@ from oracle import binding as ob
 KEYS = ["cost", "lower", "upper", "rhs", "col_scale", "row_scale", "cbeg", "cidx", "cval", "row_new_idx", "row_type", "rbeg", "ridx", "rval"]
 drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
 tmp = __import__("tempfile").mkdtemp(prefix="b200inst_")
-bad = []; n_ok = 0
+bad = []; n_ok = 0; n_pinned = 0
 for mps in sorted(glob.glob("/root/reference/check/instances/*.mps")):
     name = os.path.basename(mps)[:-4]
     out = f"{tmp}/{name}.b2lp"
@@ -39,9 +40,17 @@ for mps in sorted(glob.glob("/root/reference/check/instances/*.mps")):
             r2 = engine.host_layout_eval(lp, world=w, ordered_max=-1, seed=1)
             if not (np.all(np.abs(r2["ax"] - A @ r2["x"]) <= 1e-12 * sax) and np.all(np.abs(r2["aty"] - A.T @ r2["y"]) <= 1e-12 * say)):
                 diffs.append(f"sorted layout world {w}")
+        # the oracle against the LIVE reference on this instance: 400 PDHG iterations, iteration count and all four
+        # solution vectors bit for bit (pins the oracle far beyond the committed goldens)
+        if lp.a_matrix_.numNz() <= 200000 and not np.isnan(lp.col_cost_).any():
+            ref = ob.run_reference(lp=lp, options={"pdlp_iteration_limit": 400}, want_solution=True)
+            o = ob.solve(lp, iter_limit=400)
+            if ref["pdlp_iteration_count"] != o["iters"] or not all(np.array_equal(ref[k], o[k]) for k in ("col_value", "col_dual", "row_value", "row_dual")):
+                diffs.append(f"oracle vs reference: {ref['pdlp_iteration_count']} / {o['iters']} iterations")
+            n_pinned += 1
         if diffs: bad.append((name, diffs)); print(name, "DIFF", diffs)
         else: n_ok += 1
     except Exception as e:
         bad.append((name, repr(e))); print(name, "EXC", repr(e)[:200])
 import json
-print(json.dumps({"ok": n_ok, "bad": [[k, str(v)] for k, v in bad]}))
+print(json.dumps({"ok": n_ok, "oracle_pinned_on": n_pinned, "bad": [[k, str(v)] for k, v in bad]}))
