@@ -1,7 +1,7 @@
 """Every LP the reference ships for its own tests (check/instances/*.mps, read by the unmodified reference through
 oracle/_ref/ref_driver) through the product's host prologue -- formulate + Ruiz/Pock-Chambolle scaling + transposition,
 bit for bit against the oracle -- and through the device layouts of 1 and 3 ranks, evaluated on the host; and the
-oracle itself against the live reference on each of them (400 iterations: iteration count and solution vectors, bit for bit).
+oracle itself against the live reference on each of them (three option sets -- 400 iterations, 240 without restarts, to 1e-3 -- iteration count and solution vectors, bit for bit).
 Needs /root/reference and oracle/_ref (development container only); about 20 s."""
 import json
 import os

@@ -40,13 +40,17 @@ for mps in sorted(glob.glob("/root/reference/check/instances/*.mps")):
             r2 = engine.host_layout_eval(lp, world=w, ordered_max=-1, seed=1)
             if not (np.all(np.abs(r2["ax"] - A @ r2["x"]) <= 1e-12 * sax) and np.all(np.abs(r2["aty"] - A.T @ r2["y"]) <= 1e-12 * say)):
                 diffs.append(f"sorted layout world {w}")
-        # the oracle against the LIVE reference on this instance: 400 PDHG iterations, iteration count and all four
+        # the oracle against the LIVE reference on this instance (400 iterations; 240 without restarts; to 1e-3 or 1200
+        # iterations): iteration count and all four
         # solution vectors bit for bit (pins the oracle far beyond the committed goldens)
         if lp.a_matrix_.numNz() <= 200000 and not np.isnan(lp.col_cost_).any():
-            ref = ob.run_reference(lp=lp, options={"pdlp_iteration_limit": 400}, want_solution=True)
-            o = ob.solve(lp, iter_limit=400)
-            if ref["pdlp_iteration_count"] != o["iters"] or not all(np.array_equal(ref[k], o[k]) for k in ("col_value", "col_dual", "row_value", "row_dual")):
-                diffs.append(f"oracle vs reference: {ref['pdlp_iteration_count']} / {o['iters']} iterations")
+            for opts, prm in (({"pdlp_iteration_limit": 400}, dict(iter_limit=400)),
+                              ({"pdlp_iteration_limit": 240, "pdlp_cupdlpc_restart_method": 0}, dict(iter_limit=240, restart=0)),
+                              ({"pdlp_iteration_limit": 1200, "kkt_tolerance": 1e-3}, dict(iter_limit=1200, tol_primal=1e-3, tol_dual=1e-3, tol_gap=1e-3))):
+                ref = ob.run_reference(lp=lp, options=opts, want_solution=True)
+                o = ob.solve(lp, **prm)
+                if ref["pdlp_iteration_count"] != o["iters"] or not all(np.array_equal(ref[k], o[k]) for k in ("col_value", "col_dual", "row_value", "row_dual")):
+                    diffs.append(f"oracle vs reference {opts}: {ref['pdlp_iteration_count']} / {o['iters']} iterations")
             n_pinned += 1
         if diffs: bad.append((name, diffs)); print(name, "DIFF", diffs)
         else: n_ok += 1
