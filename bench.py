@@ -156,6 +156,14 @@ def run_reference_arm(args, rank, world):
         path = os.path.join(td, "lp.b2lp")
         write_b2lp(path, lp)
         ref = reference_rate(path, iters)
+        tts = None
+        if ref is not None and args.to_tolerance > 0:
+            from oracle import binding as ob
+            t0 = time.monotonic()
+            r = ob.run_reference(lp_path=path, options={"kkt_tolerance": args.to_tolerance})
+            tts = {"kkt_tolerance": args.to_tolerance, "seconds": time.monotonic() - t0, "run_seconds": r["run_seconds"],
+                   "iterations": r["pdlp_iteration_count"], "status": r.get("model_status"),
+                   "objective": r.get("objective_function_value")}
     m, n, k, dense = WORKLOADS[args.workload]
     if ref is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver missing (build with oracle/build_ref.py)"}))
@@ -178,6 +186,8 @@ def run_reference_arm(args, rank, world):
                                       "unit": "iter/s", "note": "steps / (setup + steps / rate); not measured at this step count"},
         "gpu_launches": 0,
     }
+    if tts is not None:
+        line["time_to_solution"] = tts
     print(json.dumps(line))
 
 
@@ -189,6 +199,9 @@ def main():
     ap.add_argument("--workload", default="S3", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--to-tolerance", type=float, default=0.0,
+                    help="additionally solve the workload to this kkt_tolerance through the host-buffer call and report the "
+                         "wall-clock time to solution (SURVEY.md 8(d)); single GPU / reference arm")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -281,6 +294,7 @@ def main():
                                         "frac": B["iter"] * value / 1e9 / peak}}
     # ---- e2e: host buffers through the public C-ABI call (single GPU only)
     e2e = None
+    tts = None
     if world == 1:
         prob.close()
         t0 = time.monotonic()
@@ -293,6 +307,13 @@ def main():
                "wall_seconds": e2e_wall, "setup_seconds": r2["setup_seconds"], "solve_seconds": r2["solve_seconds"],
                "note": "one b200pdlp_solve call on host buffers: formulate+scale+layout (host), H2D, K iterations, D2H; "
                        "bytes are per call divided by K"}
+        if args.to_tolerance > 0:
+            tol = args.to_tolerance
+            t0 = time.monotonic()
+            r3 = engine.solve(lp, tol_primal=tol, tol_dual=tol, tol_gap=tol, iter_limit=2_000_000, device=local_rank)
+            tts = {"kkt_tolerance": tol, "seconds": time.monotonic() - t0, "iterations": r3["iters"], "status": r3["term_name"],
+                   "objective": lp.objectiveValue(r3["col_value"]), "setup_seconds": r3["setup_seconds"],
+                   "solve_seconds": r3["solve_seconds"]}
     else:
         # N > 1: host buffers -> row/column shards on every GPU (formulate+scale on every rank, layouts, H2D),
         # communicator + peer-memory setup, K iterations, assembled HighsSolution back on the host
@@ -363,6 +384,8 @@ def main():
                                               "reduce_scatter+step_rule": k_us[3]}),
         "p2p_timeline_us": timeline, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
     }
+    if tts is not None:
+        line["time_to_solution"] = tts
     print(json.dumps(line))
 
 
