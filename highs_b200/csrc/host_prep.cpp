@@ -253,11 +253,14 @@ void build_row_index(StdForm& f) {
     for (int p = f.cbeg[cb[t]]; p < f.cbeg[cb[t + 1]]; p++) hist[t][f.cidx[p]]++;
   });
   f.rptr.assign(m + 1, 0);
-  for (int i = 0; i < m; i++) {
-    int c = 0;
-    for (int t = 0; t < T; t++) c += hist[t][i];
-    f.rptr[i + 1] = f.rptr[i] + c;
-  }
+  parallel_chunks(m, [&](int, long long b, long long e) {   // row totals (T x m reads) in parallel ...
+    for (long long i = b; i < e; i++) {
+      int c = 0;
+      for (int t = 0; t < T; t++) c += hist[t][i];
+      f.rptr[i + 1] = c;
+    }
+  });
+  for (int i = 0; i < m; i++) f.rptr[i + 1] += f.rptr[i];   // ... then one short serial scan
   parallel_chunks(m, [&](int, long long b, long long e) {
     for (long long i = b; i < e; i++) {
       int off = f.rptr[i];
