@@ -19,6 +19,7 @@
 #include <limits>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "host_prep.hpp"
@@ -359,7 +360,9 @@ struct DeviceSetup {
   }
 };
 
-static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, int rank, int world, b200pdlp_problem* p) {
+// shared_form != nullptr: the standard form was formulated and scaled already (by another rank of this process)
+static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, int rank, int world, b200pdlp_problem* p,
+                           const StdForm* shared_form = nullptr) {
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -376,12 +379,19 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
     fprintf(stderr, "[b200pdlp setup] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
     t0 = t1;
   };
-  formulate(lp, p->form);
-  lap("formulate");
   std::unique_ptr<DeviceSetup> dev_setup;
   int dev_level = prm.device_scaling;
   if (const char* e = getenv("B200PDLP_DEVICE_SETUP")) dev_level = atoi(e);   // experiments: same switch from the environment
-  if (prm.scaling != 0 && dev_level != 0 && p->form.nnz > 0) {
+  if (shared_form) {
+    p->form = *shared_form;
+    lap("copy of the scaled form");
+  } else {
+    formulate(lp, p->form);
+    lap("formulate");
+  }
+  if (shared_form) {
+    // nothing to scale
+  } else if (prm.scaling != 0 && dev_level != 0 && p->form.nnz > 0) {
     dev_setup.reset(new DeviceSetup());
     dev_setup->scale(p->form, lap);
   } else {
@@ -1511,6 +1521,61 @@ int b200pdlp_solve(const b200pdlp_lp* lp, const b200pdlp_params* params, const b
     delete p;
     lap("solve", "teardown");
   });
+}
+
+// One process, several GPUs (what a HiGHS process would do: Highs::run() is not an MPI program): one problem per
+// device, wired to each other with b200pdlp_p2p_link_local (peer access instead of CUDA IPC, no NCCL), one host
+// thread per rank.  The standard form is formulated and scaled once and copied to the other ranks.
+int b200pdlp_solve_multi(const b200pdlp_lp* lp, const b200pdlp_params* params, const b200pdlp_warm* warm,
+                         b200pdlp_result* out, int32_t ngpus, const int32_t* devices) {
+  if (ngpus <= 1) return b200pdlp_solve(lp, params, warm, out);
+  std::vector<b200pdlp_problem*> probs((size_t)ngpus, nullptr);
+  const int rc = guarded([&] {
+    check_lp(lp);
+    if (!params || !out || ngpus > kMaxPeers) throw Error(B200PDLP_ERR_ARG, "b200pdlp_solve_multi: bad arguments");
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int g = 0; g < ngpus; g++) {
+      b200pdlp_params prm = *params;
+      prm.device = devices ? devices[g] : g;
+      probs[g] = new b200pdlp_problem();
+      create_problem(*lp, prm, g, ngpus, probs[g], g == 0 ? nullptr : &probs[0]->form);
+    }
+    const int lrc = b200pdlp_p2p_link_local(probs.data(), ngpus);
+    if (lrc != B200PDLP_OK) throw Error(lrc, g_last_error);
+    const double setup = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    // every rank assembles the complete solution; ranks > 0 write theirs into scratch
+    const size_t n = (size_t)std::max(lp->num_col, 1), m = (size_t)std::max(lp->num_row, 1);
+    std::vector<std::vector<double>> scratch((size_t)ngpus);
+    std::vector<b200pdlp_result> res((size_t)ngpus);
+    std::vector<int> codes((size_t)ngpus, B200PDLP_OK);
+    std::vector<std::string> msgs((size_t)ngpus);
+    for (int g = 0; g < ngpus; g++) {
+      res[g] = *out;
+      res[g].setup_seconds = 0.0;
+      if (g > 0) {
+        scratch[g].assign(2 * n + 2 * m, 0.0);
+        res[g].col_value = scratch[g].data(); res[g].col_dual = scratch[g].data() + n;
+        res[g].row_value = scratch[g].data() + 2 * n; res[g].row_dual = scratch[g].data() + 2 * n + m;
+        res[g].trace = nullptr; res[g].trace_cap = 0;
+      }
+    }
+    std::vector<std::thread> th;
+    for (int g = 0; g < ngpus; g++)
+      th.emplace_back([&, g] {
+        b200pdlp_params prm = *params;
+        prm.device = probs[g]->device;
+        codes[g] = guarded([&] { solve_on_device(probs[g], prm, warm, &res[g]); CUDA_OK(cudaGetLastError()); });
+        if (codes[g] != B200PDLP_OK) msgs[g] = g_last_error;   // thread-local: hand it to the caller's thread
+      });
+    for (auto& t : th) t.join();
+    for (int g = 0; g < ngpus; g++)
+      if (codes[g] != B200PDLP_OK) throw Error(codes[g], "rank " + std::to_string(g) + ": " + msgs[g]);
+    *out = res[0];
+    out->setup_seconds += setup;
+  });
+  for (b200pdlp_problem* p : probs)
+    if (p) { cudaSetDevice(p->device); p->p2p = false; delete p; }
+  return rc;
 }
 
 int b200pdlp_nccl_unique_id(uint8_t id[128]) {

@@ -19,6 +19,7 @@
 // what it allocated and leaves sibling CUDA contexts alone.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "lp_data/HighsLpSolverObject.h"
 #include "lp_data/HighsSolution.h"
@@ -96,7 +97,11 @@ HighsStatus solveLpCupdlp(const HighsOptions& options, HighsTimer& timer, const 
   res.row_value = highs_solution.row_value.data();
   res.row_dual = highs_solution.row_dual.data();
 
-  const int rc = b200pdlp_solve(&clp, &prm, hot ? &warm : nullptr, &res);
+  // B200PDLP_GPUS=N: N devices of this process (row blocks + column shards, peer memory; b200pdlp_solve_multi)
+  int ngpus = 1;
+  if (const char* e = getenv("B200PDLP_GPUS")) ngpus = std::max(1, std::min(atoi(e), b200pdlp_device_count()));
+  const int rc = ngpus > 1 ? b200pdlp_solve_multi(&clp, &prm, hot ? &warm : nullptr, &res, ngpus, nullptr)
+                           : b200pdlp_solve(&clp, &prm, hot ? &warm : nullptr, &res);
   model_status = HighsModelStatus::kUnknown;
   highs_basis.valid = false;
   if (rc != B200PDLP_OK) {

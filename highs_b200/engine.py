@@ -65,7 +65,7 @@ ABI_SYMBOLS = [
     "b200pdlp_comm_init", "b200pdlp_partition_rows", "b200pdlp_last_error", "b200pdlp_version",
     "b200pdlp_device_count", "b200pdlp_form_create", "b200pdlp_form_destroy", "b200pdlp_form_dims",
     "b200pdlp_form_get_vector", "b200pdlp_form_get_csc", "b200pdlp_form_get_csr", "b200pdlp_form_get_row_map",
-    "b200pdlp_form_layout_eval", "b200pdlp_p2p_link_local",
+    "b200pdlp_form_layout_eval", "b200pdlp_p2p_link_local", "b200pdlp_solve_multi",
 ]
 
 _lib = None
@@ -200,6 +200,20 @@ def solve(lp: HighsLp, warm=None, trace_cap: int = 0, **params) -> dict:
     res, arrays = _mk_result(lp, trace_cap)
     w, wk = _mk_warm(warm)
     _check(L.b200pdlp_solve(C.byref(clp), C.byref(prm), C.byref(w) if w else None, C.byref(res)), "b200pdlp_solve")
+    return _result_dict(res, arrays)
+
+
+def solve_multi(lp: HighsLp, ngpus: int, devices=None, warm=None, **params) -> dict:
+    """b200pdlp_solve_multi: the whole solve on `ngpus` devices of this process (in-process peer linking, no NCCL)."""
+    L = lib()
+    L.b200pdlp_solve_multi.argtypes = [C.POINTER(CLp), C.POINTER(CParams), C.POINTER(CWarm), C.POINTER(CResult), C.c_int32, _ip]
+    clp, keep = make_clp(lp)
+    prm = make_params(**params)
+    res, arrays = _mk_result(lp, 0)
+    w, wk = _mk_warm(warm)
+    dev = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+    _check(L.b200pdlp_solve_multi(C.byref(clp), C.byref(prm), C.byref(w) if w else None, C.byref(res), ngpus,
+                                  _p(dev, _ip) if dev is not None else None), "b200pdlp_solve_multi")
     return _result_dict(res, arrays)
 
 

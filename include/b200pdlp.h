@@ -127,6 +127,12 @@ void b200pdlp_default_params(b200pdlp_params* p);
 int b200pdlp_solve(const b200pdlp_lp* lp, const b200pdlp_params* params,
                    const b200pdlp_warm* warm, b200pdlp_result* out);
 
+/* The same solve on `ngpus` devices of THIS process (devices[g] or, if NULL, ordinals 0..ngpus-1): one problem per device
+ * wired with b200pdlp_p2p_link_local, one host thread per rank, no NCCL.  ngpus <= 1 is b200pdlp_solve.
+ * (what the HiGHS shim uses when B200PDLP_GPUS > 1; the one-process-per-GPU entry points are further below) */
+int b200pdlp_solve_multi(const b200pdlp_lp* lp, const b200pdlp_params* params, const b200pdlp_warm* warm,
+                         b200pdlp_result* out, int32_t ngpus, const int32_t* devices);
+
 /* ---- persistent problem handle (bench + kernel-level parity tests) --------- */
 typedef struct b200pdlp_problem b200pdlp_problem;
 

@@ -31,7 +31,12 @@ def main():
     one = engine.Problem(lp, ordered_max=-1, **prm)      # single-GPU tree-mode solve = what the shards must reproduce
     ref = one.solve(ordered_max=-1, **prm)
     one.close()
-    res = engine.solve_logical_shards(lp, world, **prm)
+    if len(sys.argv) > 3 and sys.argv[3] == "c_entry":
+        # the same thing through the one-call C entry point the HiGHS shim uses for B200PDLP_GPUS > 1, all ranks on device 0
+        r = engine.solve_multi(lp, world, devices=[0] * world, **prm)
+        res = [r, r]
+    else:
+        res = engine.solve_logical_shards(lp, world, **prm)
     out = dict(world=world, case=case, ref_iters=ref["iters"], ref_term=ref["term_code"], ref_obj=ref["primal_obj"],
                iters=[r["iters"] for r in res], term=[r["term_code"] for r in res], obj=[r["primal_obj"] for r in res])
     ok = True

@@ -26,13 +26,14 @@ pytestmark = [pytest.mark.gpu,
 _state = {"broken": False}   # after one failing case the others are not attempted (bounds the time a broken path can cost)
 
 
-@pytest.mark.parametrize("world,case", [(2, "synthetic"), (3, "adlittle"), (4, "dense")])
-def test_logical_shards(world, case):
+@pytest.mark.parametrize("world,case,mode", [(2, "synthetic", "threads"), (3, "adlittle", "threads"), (4, "dense", "threads"),
+                                             (2, "synthetic", "c_entry")])
+def test_logical_shards(world, case, mode):
     if _state["broken"]:
         pytest.xfail("an earlier logical-shard case failed; not attempted")
     _state["broken"] = True
     try:
-        r = subprocess.run([sys.executable, CHILD, str(world), case], capture_output=True, text=True, timeout=240, cwd=ROOT)
+        r = subprocess.run([sys.executable, CHILD, str(world), case, mode], capture_output=True, text=True, timeout=240, cwd=ROOT)
     except subprocess.TimeoutExpired:
         pytest.fail("logical-shard solve did not finish in 240 s (child killed)")
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
