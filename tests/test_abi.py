@@ -58,6 +58,10 @@ def test_no_cpu_fallback(engine_lib):
         engine.solve(lp)
     with pytest.raises(engine.EngineError):
         engine.Problem(lp)
+    with pytest.raises(engine.EngineError, match="no CUDA device"):
+        engine.solve_multi(lp, 2)          # several GPUs from one process: same rule, and a clean error path
+    with pytest.raises(engine.EngineError):
+        engine.solve_logical_shards(lp, 2)
 
 
 def test_bad_arguments(engine_lib):
