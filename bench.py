@@ -232,10 +232,14 @@ def main():
             torch.cuda.synchronize()
 
     prob = engine.Problem(lp, rank=rank, world=world, device=local_rank)
+    # B200PDLP_NO_NCCL=1 (experiment, not yet run on hardware): no NCCL communicator at all -- the fused peer-memory path
+    # also assembles the solution (push_rows_kernel); saves the communicator set-up inside the e2e region
+    no_nccl = os.environ.get("B200PDLP_NO_NCCL", "0") == "1" and os.environ.get("B200PDLP_NO_P2P", "0") != "1"
     if world > 1:
-        ids = [engine.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        prob.comm_init(ids[0])
+        if not no_nccl:
+            ids = [engine.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            prob.comm_init(ids[0])
         if os.environ.get("B200PDLP_NO_P2P", "0") != "1":
             # fused NVLink path: exchange CUDA-IPC handles of the exchange buffers
             handles = [None] * world
@@ -325,9 +329,10 @@ def main():
         barrier()
         t0 = time.monotonic()
         prob2 = engine.Problem(lp, rank=rank, world=world, device=local_rank)
-        ids = [engine.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        prob2.comm_init(ids[0])
+        if not no_nccl:
+            ids = [engine.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            prob2.comm_init(ids[0])
         if use_p2p:
             handles = [None] * world
             dist.all_gather_object(handles, prob2.p2p_export())
