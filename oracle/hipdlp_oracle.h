@@ -1,0 +1,41 @@
+/* oracle/hipdlp_oracle.h -- TEST INFRASTRUCTURE ONLY (same rules as pdlp_oracle.h: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline leg may use it; the product never links it).
+ *
+ * CPU restatement of the reference's HiPDLP engine (`solver=hipdlp`, reflected Halpern PDHG):
+ *   Highs::run -> solveLp -> solveLpHiPdlp (pdlp/HiPdlpWrapper.cpp:26-141) -> PDLPSolver (pdlp/hipdlp/).
+ * SURVEY.md 8(a) row a20, 8(f) rank 2 -- the oracle for the NEXT algorithm mode of the engine.
+ * Parity status: PINNED against oracle/_ref (tests/test_hipdlp_oracle.py: iteration counts and all four
+ * HighsSolution vectors bit for bit on the reference's own LP instances, several option sets).
+ */
+#ifndef HIPDLP_ORACLE_H_
+#define HIPDLP_ORACLE_H_
+
+#include "pdlp_oracle.h"   /* orc_lp */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { HIP_OPTIMAL = 0, HIP_MAXITER = 1 };
+
+typedef struct {
+  double tolerance;          /* pdlp_optimality_tolerance / kkt_tolerance (pdhg.cc:1822-1824) */
+  int max_iterations;        /* pdlp_iteration_limit */
+  int use_ruiz, use_pc, use_l2;   /* pdlp_scaling_mode bits 1 / 4 / 2 (default 5 = Ruiz + PC) */
+  int ruiz_iterations;       /* pdlp_ruiz_iterations (default 10) */
+  int step_size_strategy;    /* 0 fixed, 3 PID (every other option value means PID, pdhg.cc:1854-1863) */
+} hip_params;
+
+typedef struct {
+  double *col_value, *col_dual, *row_value, *row_dual;   /* caller-allocated n, n, m, m */
+  int term_code, iters;
+  double pfeas, dfeas, pobj, dobj, relgap;               /* of the last convergence check (scaled-space objective) */
+  double primal_weight, op_norm_sq;
+} hip_result;
+
+int hip_solve(const orc_lp* lp, const hip_params* prm, hip_result* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
