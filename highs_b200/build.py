@@ -20,7 +20,7 @@ NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-fmad=false", "-Xcompile
                      "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 CXX_FLAGS = ["-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-Wall", "-Wno-sign-compare"]
 
-SOURCES = [("host_prep.cpp", "cxx"), ("pdhg_kernels.cu", "nvcc"), ("setup_kernels.cu", "nvcc"), ("engine.cu", "nvcc")]
+SOURCES = [("host_prep.cpp", "cxx"), ("host_prep_hipdlp.cpp", "cxx"), ("pdhg_kernels.cu", "nvcc"), ("setup_kernels.cu", "nvcc"), ("engine.cu", "nvcc")]
 HEADERS = ["host_prep.hpp", "kernels.cuh", "pdhg_kernels.hpp", "setup_kernels.hpp", os.path.join("..", "..", "include", "b200pdlp.h")]
 
 

@@ -1718,6 +1718,21 @@ int b200pdlp_form_create(const b200pdlp_lp* lp, int32_t scaling, b200pdlp_form**
     *out = f;
   });
 }
+int b200pdlp_hipdlp_form_create(const b200pdlp_lp* lp, int32_t scaling_mode, int32_t ruiz_iterations, b200pdlp_form** out) {
+  return guarded([&] {
+    check_lp(lp);
+    if (!out || ruiz_iterations < 0) throw Error(B200PDLP_ERR_ARG, "bad argument");
+    auto* f = new b200pdlp_form();
+    formulate_hipdlp(*lp, f->f);
+    scale_hipdlp(f->f, scaling_mode, ruiz_iterations);
+    *out = f;
+  });
+}
+int b200pdlp_hipdlp_power_method(const b200pdlp_form* f, double* lambda) {
+  if (!f || !lambda || !f->f.hipdlp) return B200PDLP_ERR_ARG;
+  *lambda = power_method_hipdlp(f->f);
+  return B200PDLP_OK;
+}
 void b200pdlp_form_destroy(b200pdlp_form* f) { delete f; }
 int b200pdlp_form_dims(const b200pdlp_form* f, int32_t dims[5], double scalars[3]) {
   if (!f || !dims || !scalars) return B200PDLP_ERR_ARG;
@@ -1733,6 +1748,7 @@ static const std::vector<double>* form_vector(const StdForm& f, int which) {
     case 3: return &f.rhs;
     case 4: return &f.col_scale;
     case 5: return &f.row_scale;
+    case 6: return &f.row_upper;   // HiPDLP forms only (empty otherwise)
   }
   return nullptr;
 }

@@ -30,7 +30,7 @@ struct DefaultInitAlloc : std::allocator<T> {
 };
 template <class T> using RawVec = std::vector<T, DefaultInitAlloc<T>>;
 
-enum RowClass : int { kEq = 0, kLeq = 1, kGeq = 2, kBound = 3 };  // cupdlp_defs.h numbering
+enum RowClass : int { kEq = 0, kLeq = 1, kGeq = 2, kBound = 3, kFreeRow = 4 };  // cupdlp_defs.h numbering (+ HiPDLP's FREE)
 
 // min c'x  s.t.  A x = b (rows < neq),  A x >= b (rows >= neq),  l <= x <= u
 struct StdForm {
@@ -44,6 +44,9 @@ struct StdForm {
   double sense = 1.0, offset = 0.0;
   double norm_cost = 0.0, norm_rhs = 0.0;   // 2-norms of the unscaled cost / rhs
   double amax = 0.0;                        // max |a_ij| after scaling
+  // HiPDLP mode (host_prep_hipdlp.cpp): rows carry an upper bound as well (rhs = lower), `scaled` = any scaling applied
+  bool hipdlp = false, scaled = false;
+  std::vector<double> row_upper;
   // row-major index of the nonzeros (built once, by scale() or on demand): row i owns positions
   // rpos[rptr[i] .. rptr[i+1]) of cidx/cval, columns ascending
   std::vector<int> rptr;
@@ -87,6 +90,10 @@ constexpr int kNnzPerBlock = 2048;   // long-row segment size (== kernels.cuh kN
 constexpr int kSortWindow = 8192;
 
 void formulate(const b200pdlp_lp& lp, StdForm& f);
+// HiPDLP's own prologue (pdhg.cc:152-358, scaling.cc, pdhg.cc:1529-1671): scaling_mode bits 1 Ruiz, 4 PC, 2 L2
+void formulate_hipdlp(const b200pdlp_lp& lp, StdForm& f);
+void scale_hipdlp(StdForm& f, int scaling_mode, int ruiz_iterations);
+double power_method_hipdlp(const StdForm& f);
 void build_row_index(StdForm& f);   // fills f.rptr / f.rpos (parallel counting sort)
 void scale(StdForm& f, bool do_scale);
 // nnz-balanced contiguous partition of the m rows into `world` parts

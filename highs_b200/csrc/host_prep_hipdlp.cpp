@@ -1,0 +1,221 @@
+// highs_b200/csrc/host_prep_hipdlp.cpp -- host prologue of the engine's SECOND algorithm mode (HiPDLP: reflected
+// Halpern PDHG, `solver=hipdlp`).  Product code (C++), no CUDA.
+//
+// HiPDLP prepares the LP differently from cuPDLP-C, so it gets its own formulate / scale (the layouts and the device
+// side are shared):
+//   PDLPSolver::preprocessLp   /root/reference/highs/pdlp/hipdlp/pdhg.cc:152-358
+//       rows are classified with +-infinity (not +-1e20), free rows are a class of their own, the objective is NOT
+//       multiplied by the sense, a column's entries are sorted by (new row, value), rows keep a lower AND an upper
+//       bound (GEQ: [b, inf], EQ: [b, b], BOUND/FREE: [0, 0] with a slack column, LEQ negated into GEQ);
+//   Scaling::scaleProblem      hipdlp/scaling.cc:23-263
+//       Ruiz (inf-norm) x pdlp_ruiz_iterations, then Pock-Chambolle (alpha = 1), then optionally L2, each applied as
+//       a_ij /= (r_i * c_j) -- ONE division by the product -- with only FINITE bounds scaled;
+//   PDLPSolver::powerMethod    hipdlp/pdhg.cc:1529-1671 (the cuPDLP-C variant: 20 iterations on A A' from the ones vector).
+// The arithmetic follows the reference expression by expression (tests/test_hipdlp_host.py compares with the oracle
+// bit for bit); the loop structure is ours.
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include <utility>
+
+#include "host_prep.hpp"
+
+namespace b200 {
+
+void formulate_hipdlp(const b200pdlp_lp& lp, StdForm& f) {
+  const int n0 = lp.num_col, m = lp.num_row;
+  const double inf = std::numeric_limits<double>::infinity();
+  f = StdForm();
+  f.hipdlp = true;
+  f.n_orig = n0;
+  f.m = m;
+  f.sense = lp.sense;
+  f.offset = lp.offset;
+  f.row_class.resize(m);
+  f.row_new_idx.resize(m);
+  int n_slack = 0, n_eq = 0;
+  for (int i = 0; i < m; i++) {   // pdhg.cc:175-198
+    const bool lo = lp.row_lower[i] > -inf, up = lp.row_upper[i] < inf;
+    int c;
+    if (lo && up) c = (lp.row_lower[i] == lp.row_upper[i]) ? kEq : kBound;
+    else if (lo) c = kGeq;
+    else if (up) c = kLeq;
+    else c = kFreeRow;
+    f.row_class[i] = c;
+    if (c == kBound || c == kFreeRow) n_slack++;
+    if (c == kEq || c == kBound || c == kFreeRow) n_eq++;
+  }
+  f.neq = n_eq;
+  f.n = n0 + n_slack;
+  f.rhs.assign(m, 0.0);
+  f.row_upper.assign(m, 0.0);
+  {
+    int head = 0, tail = n_eq;   // equality-like rows first, original order inside each group (:213-222)
+    for (int i = 0; i < m; i++) {
+      const int c = f.row_class[i];
+      const int k = (c == kEq || c == kBound || c == kFreeRow) ? head++ : tail++;
+      f.row_new_idx[i] = k;
+      switch (c) {               // :247-270
+        case kEq: f.rhs[k] = lp.row_lower[i]; f.row_upper[k] = lp.row_upper[i]; break;
+        case kGeq: f.rhs[k] = lp.row_lower[i]; f.row_upper[k] = inf; break;
+        case kLeq: f.rhs[k] = -lp.row_upper[i]; f.row_upper[k] = inf; break;
+        default: f.rhs[k] = 0.0; f.row_upper[k] = 0.0; break;
+      }
+    }
+  }
+  f.cost.assign(f.n, 0.0);
+  f.lower.resize(f.n);
+  f.upper.resize(f.n);
+  for (int j = 0; j < n0; j++) { f.cost[j] = lp.col_cost[j]; f.lower[j] = lp.col_lower[j]; f.upper[j] = lp.col_upper[j]; }
+  const int nnz0 = lp.a_start[n0];
+  f.nnz = nnz0 + n_slack;
+  f.cbeg.resize(f.n + 1);
+  f.cidx.resize(f.nnz);
+  f.cval.resize(f.nnz);
+  {
+    // structural columns keep their entry count: column j starts at a_start[j]; entries sorted by (row, value) (:300-333)
+    std::vector<std::pair<int, double>> e;
+    for (int j = 0; j < n0; j++) {
+      e.clear();
+      for (int p = lp.a_start[j]; p < lp.a_start[j + 1]; p++) {
+        const int old = lp.a_index[p];
+        e.emplace_back(f.row_new_idx[old], f.row_class[old] == kLeq ? -lp.a_value[p] : lp.a_value[p]);
+      }
+      std::sort(e.begin(), e.end());
+      int k = lp.a_start[j];
+      f.cbeg[j] = k;
+      for (const auto& t : e) { f.cidx[k] = t.first; f.cval[k] = t.second; k++; }
+    }
+  }
+  int k = nnz0, j = n0;
+  for (int i = 0; i < m; i++) {   // one slack column per BOUND / FREE row: A x - z = 0, z in the row's bounds (:235-244,336-346)
+    if (f.row_class[i] != kBound && f.row_class[i] != kFreeRow) continue;
+    f.cbeg[j] = k;
+    f.cidx[k] = f.row_new_idx[i];
+    f.cval[k] = -1.0;
+    k++;
+    f.lower[j] = lp.row_lower[i];
+    f.upper[j] = lp.row_upper[i];
+    j++;
+  }
+  f.cbeg[f.n] = k;
+  f.col_scale.assign(f.n, 1.0);
+  f.row_scale.assign(f.m, 1.0);
+  double s = 0.0;   // norms of the UNSCALED processed data (:353-354): sequential sums like linalg::dot
+  for (int q = 0; q < f.n; q++) s += f.cost[q] * f.cost[q];
+  f.norm_cost = std::sqrt(s);
+  s = 0.0;
+  for (int i = 0; i < f.m; i++) s += f.rhs[i] * f.rhs[i];
+  f.norm_rhs = std::sqrt(s);
+}
+
+namespace {
+// one pass's factors into the data (Scaling::applyScaling, scaling.cc:232-263) and into the running scales
+void apply_hipdlp(StdForm& f, const std::vector<double>& cs, const std::vector<double>& rs) {
+  const double inf = std::numeric_limits<double>::infinity();
+  for (int i = 0; i < f.n; i++) {
+    f.cost[i] /= cs[i];
+    if (f.lower[i] > -inf) f.lower[i] *= cs[i];
+    if (f.upper[i] < inf) f.upper[i] *= cs[i];
+    f.col_scale[i] *= cs[i];
+  }
+  for (int i = 0; i < f.m; i++) {
+    if (f.rhs[i] > -inf) f.rhs[i] /= rs[i];
+    if (f.row_upper[i] < inf) f.row_upper[i] /= rs[i];
+    f.row_scale[i] *= rs[i];
+  }
+  for (int c = 0; c < f.n; c++) {
+    const double cc = cs[c];
+    for (int p = f.cbeg[c]; p < f.cbeg[c + 1]; p++) f.cval[p] /= (rs[f.cidx[p]] * cc);
+  }
+}
+}  // namespace
+
+void scale_hipdlp(StdForm& f, int scaling_mode, int ruiz_iterations) {
+  const int n = f.n, m = f.m;
+  std::vector<double> cs(n), rs(m);
+  f.scaled = false;
+  if (scaling_mode & 1) {   // Ruiz, infinity norm (scaling.cc:56-125)
+    for (int it = 0; it < ruiz_iterations; it++) {
+      std::fill(rs.begin(), rs.end(), 0.0);
+      for (int c = 0; c < n; c++) {
+        double mx = 0.0;
+        for (int p = f.cbeg[c]; p < f.cbeg[c + 1]; p++) {
+          const double a = std::fabs(f.cval[p]);
+          mx = std::max(mx, a);
+          rs[f.cidx[p]] = std::max(rs[f.cidx[p]], a);
+        }
+        double v = (f.cbeg[c] < f.cbeg[c + 1]) ? std::sqrt(mx) : 0.0;
+        if (v == 0.0) v = 1.0;
+        cs[c] = v;
+      }
+      for (int i = 0; i < m; i++) rs[i] = (rs[i] == 0.0) ? 1.0 : std::sqrt(rs[i]);
+      apply_hipdlp(f, cs, rs);
+    }
+    f.scaled = true;
+  }
+  if (scaling_mode & 4) {   // Pock-Chambolle, alpha = 1 (:127-178); pow() kept as in the reference
+    const double alpha = 1.0;
+    std::fill(rs.begin(), rs.end(), 0.0);
+    for (int c = 0; c < n; c++) {
+      double sum = 0.0;
+      for (int p = f.cbeg[c]; p < f.cbeg[c + 1]; p++) {
+        sum += std::pow(std::fabs(f.cval[p]), alpha);
+        rs[f.cidx[p]] += std::pow(std::fabs(f.cval[p]), 2.0 - alpha);
+      }
+      cs[c] = sum > 0.0 ? std::sqrt(std::pow(sum, 1.0 / alpha)) : 1.0;
+    }
+    for (int i = 0; i < m; i++) rs[i] = rs[i] > 0.0 ? std::sqrt(std::pow(rs[i], 1.0 / (2.0 - alpha))) : 1.0;
+    apply_hipdlp(f, cs, rs);
+    f.scaled = true;
+  }
+  if (scaling_mode & 2) {   // L2 (:180-230)
+    std::fill(rs.begin(), rs.end(), 0.0);
+    for (int c = 0; c < n; c++) {
+      double sq = 0.0;
+      for (int p = f.cbeg[c]; p < f.cbeg[c + 1]; p++) {
+        sq += f.cval[p] * f.cval[p];
+        rs[f.cidx[p]] += f.cval[p] * f.cval[p];
+      }
+      cs[c] = sq > 0.0 ? std::sqrt(std::sqrt(sq)) : 1.0;
+    }
+    for (int i = 0; i < m; i++) rs[i] = rs[i] > 0.0 ? std::sqrt(std::sqrt(rs[i])) : 1.0;
+    apply_hipdlp(f, cs, rs);
+    f.scaled = true;
+  }
+  double amax = 0.0;
+  for (int p = 0; p < f.nnz; p++) amax = std::max(amax, std::fabs(f.cval[p]));
+  f.amax = amax;
+}
+
+// lambda_max(A A') estimate: 20 power iterations from the ones vector (pdhg.cc:1529-1671, "cuPDLP-C" branch), with
+// HighsSparseMatrix::product / productTranspose's accumulation order (util/HighsSparseMatrix.cpp:1180-1218)
+double power_method_hipdlp(const StdForm& f) {
+  if (f.n == 0 || f.m == 0) return 1.0;
+  std::vector<double> x(f.m, 1.0), y(f.n), z(f.m);
+  double lambda = 0.0;
+  auto at_times = [&](const std::vector<double>& v, std::vector<double>& out) {
+    for (int c = 0; c < f.n; c++) {
+      double s = 0.0;
+      for (int p = f.cbeg[c]; p < f.cbeg[c + 1]; p++) s += v[f.cidx[p]] * f.cval[p];
+      out[c] = s;
+    }
+  };
+  for (int it = 0; it < 20; it++) {
+    at_times(x, y);
+    std::fill(z.begin(), z.end(), 0.0);
+    for (int c = 0; c < f.n; c++)
+      for (int p = f.cbeg[c]; p < f.cbeg[c + 1]; p++) z[f.cidx[p]] += y[c] * f.cval[p];
+    double zz = 0.0;
+    for (int i = 0; i < f.m; i++) zz += z[i] * z[i];
+    const double zn = std::sqrt(zz);
+    for (int i = 0; i < f.m; i++) z[i] /= zn;
+    at_times(z, y);
+    lambda = 0.0;
+    for (int c = 0; c < f.n; c++) lambda += y[c] * y[c];
+    x = z;
+  }
+  return lambda;
+}
+
+}  // namespace b200

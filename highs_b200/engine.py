@@ -66,6 +66,7 @@ ABI_SYMBOLS = [
     "b200pdlp_device_count", "b200pdlp_form_create", "b200pdlp_form_destroy", "b200pdlp_form_dims",
     "b200pdlp_form_get_vector", "b200pdlp_form_get_csc", "b200pdlp_form_get_csr", "b200pdlp_form_get_row_map",
     "b200pdlp_form_layout_eval", "b200pdlp_p2p_link_local", "b200pdlp_solve_multi",
+    "b200pdlp_hipdlp_form_create", "b200pdlp_hipdlp_power_method",
 ]
 
 _lib = None
@@ -356,6 +357,39 @@ def host_form(lp: HighsLp, scaling: int = 1) -> dict:
         _check(L.b200pdlp_form_get_csr(h, _p(rbeg, _ip), _p(ridx, _ip), _p(rval, _dp)), "form_get_csr")
         out.update(cbeg=cbeg, cidx=cidx[:nnz], cval=cval[:nnz], row_new_idx=rni[:m], row_type=rcl[:m],
                    rbeg=rbeg, ridx=ridx[:nnz], rval=rval[:nnz])
+        return out
+    finally:
+        L.b200pdlp_form_destroy(h)
+
+
+def host_form_hipdlp(lp: HighsLp, scaling_mode: int = 5, ruiz_iterations: int = 10) -> dict:
+    """Host-only HiPDLP standard form (preprocess + scale) and its power-method estimate; needs no GPU."""
+    L = lib()
+    L.b200pdlp_hipdlp_form_create.argtypes = [C.POINTER(CLp), C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+    L.b200pdlp_hipdlp_power_method.argtypes = [C.c_void_p, _dp]
+    clp, keep = make_clp(lp)
+    h = C.c_void_p()
+    _check(L.b200pdlp_hipdlp_form_create(C.byref(clp), scaling_mode, ruiz_iterations, C.byref(h)), "b200pdlp_hipdlp_form_create")
+    try:
+        d = (C.c_int32 * 5)()
+        sc = (C.c_double * 3)()
+        _check(L.b200pdlp_form_dims(h, d, sc), "b200pdlp_form_dims")
+        n, m, nnz, neq, n_orig = list(d)
+        out = dict(n=n, m=m, nnz=nnz, neq=neq, n_orig=n_orig, c_norm=sc[0], rhs_norm=sc[1], amax=sc[2])
+        for idx, (name, ln) in enumerate([("cost", n), ("lower", n), ("upper", n), ("rlo", m), ("col_scale", n), ("row_scale", m), ("rup", m)]):
+            v = np.zeros(max(ln, 1))
+            k = L.b200pdlp_form_get_vector(h, idx, _p(v, _dp), ln)
+            out[name] = v[:k].copy()
+        cbeg = np.zeros(n + 1, dtype=np.int32)
+        cidx = np.zeros(max(nnz, 1), dtype=np.int32)
+        cval = np.zeros(max(nnz, 1))
+        _check(L.b200pdlp_form_get_csc(h, _p(cbeg, _ip), _p(cidx, _ip), _p(cval, _dp)), "form_get_csc")
+        rni = np.zeros(max(m, 1), dtype=np.int32)
+        rcl = np.zeros(max(m, 1), dtype=np.int32)
+        _check(L.b200pdlp_form_get_row_map(h, _p(rni, _ip), _p(rcl, _ip)), "form_get_row_map")
+        lam = np.zeros(1)
+        _check(L.b200pdlp_hipdlp_power_method(h, _p(lam, _dp)), "b200pdlp_hipdlp_power_method")
+        out.update(cbeg=cbeg, cidx=cidx[:nnz], cval=cval[:nnz], new_idx=rni[:m], ctype=rcl[:m], op_norm_sq=float(lam[0]))
         return out
     finally:
         L.b200pdlp_form_destroy(h)

@@ -208,6 +208,14 @@ int b200pdlp_form_get_csr(b200pdlp_form* f, int32_t* rowptr, int32_t* col, doubl
 /* row_new_idx[m], row_class[m] by ORIGINAL row (EQ=0, LEQ=1, GEQ=2, BOUND=3) */
 int b200pdlp_form_get_row_map(const b200pdlp_form* f, int32_t* row_new_idx, int32_t* row_class);
 
+/* HiPDLP mode (solver=hipdlp), host prologue only so far: PDLPSolver::preprocessLp
+ * (hipdlp/pdhg.cc:152-358) + Scaling::scaleProblem (hipdlp/scaling.cc; scaling_mode bits 1 Ruiz, 4 Pock-Chambolle, 2 L2 =
+ * HighsOptions::pdlp_scaling_mode, ruiz_iterations = pdlp_ruiz_iterations).  The form answers the b200pdlp_form_* getters;
+ * rows carry an upper bound too: b200pdlp_form_get_vector(which = 6).  row_class uses 4 for FREE rows. */
+int b200pdlp_hipdlp_form_create(const b200pdlp_lp* lp, int32_t scaling_mode, int32_t ruiz_iterations, b200pdlp_form** out);
+/* PDLPSolver::powerMethod (hipdlp/pdhg.cc:1529-1671): 20 iterations on A A' from the ones vector -> estimate of |A|_2^2 */
+int b200pdlp_hipdlp_power_method(const b200pdlp_form* f, double* lambda);
+
 /* host-only (no GPU): build the device layout of rank `rank` of `world` exactly as b200pdlp_problem_create does
  * (row block, length-sorted device orderings, sliced ELL of A_g and A_g', long-row segments, segmented column
  * positions, the A_g' output map) and evaluate it on the host in the kernels' traversal order.

@@ -153,6 +153,39 @@ def hipdlp_solve(lp, tolerance=1e-7, max_iterations=2147483647, scaling_mode=5, 
                 pobj=res.pobj, dobj=res.dobj, relgap=res.relgap, primal_weight=res.primal_weight, op_norm_sq=res.op_norm_sq)
 
 
+class HipForm(C.Structure):
+    _fields_ = [("n", C.c_int), ("m", C.c_int), ("nnz", C.c_int), ("neq", C.c_int),
+                ("cost", _dp), ("lower", _dp), ("upper", _dp), ("rlo", _dp), ("rup", _dp),
+                ("cbeg", _ip), ("cidx", _ip), ("cval", _dp), ("col_scale", _dp), ("row_scale", _dp),
+                ("new_idx", _ip), ("ctype", _ip), ("c_norm", C.c_double), ("rhs_norm", C.c_double), ("op_norm_sq", C.c_double)]
+
+
+def hipdlp_form(lp, scaling_mode=5, ruiz_iterations=10) -> dict:
+    """HiPDLP's processed + scaled LP and its power-method estimate (oracle/hipdlp_oracle.c::hip_form_build)."""
+    L = lib()
+    clp, keep = _mk_lp(lp)
+    n0, m, nnz0 = lp.num_col_, lp.num_row_, lp.a_matrix_.numNz()
+    nmax, zmax = n0 + m + 1, nnz0 + m + 1
+    a = dict(cost=np.zeros(nmax), lower=np.zeros(nmax), upper=np.zeros(nmax), col_scale=np.zeros(nmax),
+             rlo=np.zeros(m + 1), rup=np.zeros(m + 1), row_scale=np.zeros(m + 1), new_idx=np.zeros(m + 1, dtype=np.int32),
+             ctype=np.zeros(m + 1, dtype=np.int32), cbeg=np.zeros(nmax + 1, dtype=np.int32), cidx=np.zeros(zmax, dtype=np.int32),
+             cval=np.zeros(zmax))
+    f = HipForm(0, 0, 0, 0, _p(a["cost"], _dp), _p(a["lower"], _dp), _p(a["upper"], _dp), _p(a["rlo"], _dp), _p(a["rup"], _dp),
+                _p(a["cbeg"], _ip), _p(a["cidx"], _ip), _p(a["cval"], _dp), _p(a["col_scale"], _dp), _p(a["row_scale"], _dp),
+                _p(a["new_idx"], _ip), _p(a["ctype"], _ip), 0.0, 0.0, 0.0)
+    prm = HipParams(1e-7, 0, int(bool(scaling_mode & 1)), int(bool(scaling_mode & 4)), int(bool(scaling_mode & 2)), ruiz_iterations, 3)
+    L.hip_form_build.argtypes = [C.POINTER(OrcLp), C.POINTER(HipParams), C.POINTER(HipForm)]
+    assert L.hip_form_build(C.byref(clp), C.byref(prm), C.byref(f)) == 0
+    n, nnz = f.n, f.nnz
+    out = dict(n=n, m=m, nnz=nnz, neq=f.neq, c_norm=f.c_norm, rhs_norm=f.rhs_norm, op_norm_sq=f.op_norm_sq)
+    for k in ("cost", "lower", "upper", "col_scale"):
+        out[k] = a[k][:n].copy()
+    for k in ("rlo", "rup", "row_scale", "new_idx", "ctype"):
+        out[k] = a[k][:m].copy()
+    out.update(cbeg=a["cbeg"][: n + 1].copy(), cidx=a["cidx"][:nnz].copy(), cval=a["cval"][:nnz].copy())
+    return out
+
+
 def formulate_and_scale(lp, scaling=1) -> dict:
     """Standard form + scaling + CSR as numpy copies (for kernel-level parity tests)."""
     L = lib()

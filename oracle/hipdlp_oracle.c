@@ -389,6 +389,29 @@ static void update_primal_weight(hip* s) {                             /* pdhg.c
   s->omega = s->primal_weight;
 }
 
+/* the processed + scaled LP and the power-method estimate, for parity tests of the product's host prologue:
+ * arrays are caller-allocated (n0 + m columns, m rows, nnz0 + m nonzeros at most) */
+int hip_form_build(const orc_lp* lp, const hip_params* prm, hip_form* f) {
+  hip S; memset(&S, 0, sizeof(S));
+  hip* s = &S;
+  preprocess(lp, s);
+  scale_problem(s, prm);
+  f->n = s->n; f->m = s->m; f->nnz = s->nnz; f->neq = 0;
+  for (int i = 0; i < s->m; i++) f->neq += s->is_eq[i];
+  memcpy(f->cost, s->cost, sizeof(double) * (size_t)s->n); memcpy(f->lower, s->lower, sizeof(double) * (size_t)s->n);
+  memcpy(f->upper, s->upper, sizeof(double) * (size_t)s->n); memcpy(f->col_scale, s->col_scale, sizeof(double) * (size_t)s->n);
+  memcpy(f->rlo, s->rlo, sizeof(double) * (size_t)s->m); memcpy(f->rup, s->rup, sizeof(double) * (size_t)s->m);
+  memcpy(f->row_scale, s->row_scale, sizeof(double) * (size_t)s->m);
+  memcpy(f->new_idx, s->new_idx, sizeof(int) * (size_t)s->m); memcpy(f->ctype, s->ctype, sizeof(int) * (size_t)s->m);
+  memcpy(f->cbeg, s->cbeg, sizeof(int) * (size_t)(s->n + 1)); memcpy(f->cidx, s->cidx, sizeof(int) * (size_t)s->nnz);
+  memcpy(f->cval, s->cval, sizeof(double) * (size_t)s->nnz);
+  f->c_norm = s->c_norm; f->rhs_norm = s->rhs_norm;
+  f->op_norm_sq = power_method(s);
+  free(s->cost); free(s->lower); free(s->upper); free(s->rlo); free(s->rup); free(s->cbeg); free(s->cidx); free(s->cval);
+  free(s->ctype); free(s->new_idx); free(s->is_eq); free(s->col_scale); free(s->row_scale);
+  return 0;
+}
+
 /* ------------------------------------------------------------------------- driver */
 int hip_solve(const orc_lp* lp, const hip_params* prm, hip_result* out) {
   hip S; memset(&S, 0, sizeof(S));

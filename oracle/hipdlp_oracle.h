@@ -35,6 +35,20 @@ typedef struct {
 
 int hip_solve(const orc_lp* lp, const hip_params* prm, hip_result* out);
 
+/* processed (pdhg.cc:152-358) + scaled (scaling.cc) LP and the power-method estimate of |A|^2 (pdhg.cc:1529-1671);
+ * caller-allocated arrays: n0 + m columns, m rows, nnz0 + m nonzeros at most.
+ * ctype: 0 EQ, 1 LEQ, 2 GEQ, 3 BOUND, 4 FREE by ORIGINAL row; new_idx: original row -> processed row */
+typedef struct {
+  int n, m, nnz, neq;
+  double *cost, *lower, *upper, *rlo, *rup;
+  int *cbeg, *cidx;
+  double* cval;
+  double *col_scale, *row_scale;
+  int *new_idx, *ctype;
+  double c_norm, rhs_norm, op_norm_sq;
+} hip_form;
+int hip_form_build(const orc_lp* lp, const hip_params* prm, hip_form* f);
+
 #ifdef __cplusplus
 }
 #endif
