@@ -199,6 +199,14 @@ struct b200pdlp_problem {
   // fused P2P path
   std::vector<int> row_bounds;     // row offsets of every rank's block
   bool device_filled = false;      // the sliced-ELL arrays were filled on the device (params.device_scaling >= 2)
+  // HiPDLP mode (reflected Halpern PDHG): its own iterate set; cost/lower/upper/colscale/rowscale/rhs (= row lower) are shared
+  struct HipBuffers {
+    DevBuf<double> x, y, xn, yn, rx, ry, xa, ya, aty, axp, atyp, dy, atdy, hslack, sp, sn, rup;
+    DevBuf<HipState> state;
+    HipState* hstate = nullptr;    // pinned
+    cudaGraphExec_t graph = nullptr;
+    ~HipBuffers() { if (graph) cudaGraphExecDestroy(graph); if (hstate) cudaFreeHost(hstate); }
+  } hip;
   bool local_link = false;         // peers are problems of this process (logical shards, b200pdlp_p2p_link_local)
   bool p2p = false;
   int p2p_pull = 0;                // 1: the primal kernel reads the peers' partials over NVLink; 0: peers push them
@@ -1244,6 +1252,278 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   lap("solve", "postsolve (host)");
 }
 
+// =================================================================================================== HiPDLP mode
+// solveLpHiPdlp -> PDLPSolver::solve (/root/reference/highs/pdlp/hipdlp/pdhg.cc:494-707) on the device, single GPU.
+// STATUS: written after round 1's GPU budget was spent; compiled, not yet run on hardware.
+static void create_problem_hipdlp(const b200pdlp_lp& lp, const b200pdlp_hipdlp_params& prm, b200pdlp_problem* p) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    throw Error(B200PDLP_ERR_CUDA, std::string("no CUDA device: the B200 engine has no CPU fallback (") + cudaGetErrorString(e) + ")");
+  if (prm.device >= 0) p->device = prm.device; else CUDA_OK(cudaGetDevice(&p->device));
+  set_device(p);
+  p->rank = 0; p->world = 1;
+  formulate_hipdlp(lp, p->form);
+  scale_hipdlp(p->form, prm.scaling_mode, prm.ruiz_iterations);
+  StdForm& f = p->form;
+  HostLayout L;
+  build_layout(f, 0, 1, prm.ordered_max, L);
+  p->r0 = L.r0; p->r1 = L.r1; p->ml = L.ml; p->neq_local = L.neq_local; p->ordered = L.ordered;
+  p->n = f.n; p->m = f.m;
+  p->nl = L.nl; p->nl_real = L.nl_real; p->c0 = 0; p->shard_len = L.shard_len; p->seg_len = L.seg_len;
+  p->csr_local = std::move(L.csr_local);
+  p->rperm = std::move(L.rperm); p->rinv = std::move(L.rinv);
+  p->cperm = std::move(L.cperm); p->cinv = std::move(L.cinv);
+  p->A.host = std::move(L.A); p->AT.host = std::move(L.AT);
+  CUDA_OK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  p->A.upload();
+  p->AT.upload();
+  const int n = p->n, m = p->m;
+  std::vector<double> t(std::max(std::max(n, m), 1));
+  auto up_col = [&](DevBuf<double>& d, const std::vector<double>& v) {
+    for (int i = 0; i < n; i++) t[i] = v[p->cperm[i]];
+    d.alloc(n, false); d.upload(t.data(), n);
+  };
+  auto up_row = [&](DevBuf<double>& d, const std::vector<double>& v) {
+    for (int i = 0; i < m; i++) t[i] = v[p->rperm[i]];
+    d.alloc(m, false); d.upload(t.data(), m);
+  };
+  up_col(p->cost, f.cost); up_col(p->lower, f.lower); up_col(p->upper, f.upper); up_col(p->colscale, f.col_scale);
+  up_row(p->rhs, f.rhs); up_row(p->hip.rup, f.row_upper); up_row(p->rowscale, f.row_scale);
+  auto& h = p->hip;
+  for (DevBuf<double>* b : {&h.x, &h.xn, &h.rx, &h.xa, &h.aty, &h.atyp, &h.atdy, &h.hslack, &h.sp, &h.sn}) b->alloc(n);
+  for (DevBuf<double>* b : {&h.y, &h.yn, &h.ry, &h.ya, &h.axp, &h.dy}) b->alloc(m);
+  h.state.alloc(1);
+  CUDA_OK(cudaMallocHost(&h.hstate, sizeof(HipState)));
+  size_t maxgrid = std::max<size_t>(kMaxEwBlocks, std::max(p->A.grid(), p->AT.grid()));
+  p->scratch_stride = 24 * maxgrid;
+  p->partials.alloc(p->scratch_stride * kNumSlots);
+  p->counters.alloc(kNumSlots);
+  p->terms.alloc(1);
+  p->ordered_cap = 0;
+  p->outs.alloc(kOutsCount);
+  CUDA_OK(cudaMallocHost(&p->houts, kOutsCount * sizeof(double)));
+  CUDA_OK(cudaDeviceSynchronize());
+}
+
+static void hip_step(b200pdlp_problem* p, int k_offset, int is_major) {
+  auto& h = p->hip;
+  cudaStream_t s = p->stream;
+  launch_hip_primal(s, p->n, h.state.p, k_offset, is_major, h.x.p, h.xa.p, p->cost.p, h.aty.p, p->lower.p, p->upper.p,
+                    h.rx.p, h.xn.p, h.hslack.p);
+  launch_hip_dual(s, p->A.dev, h.state.p, k_offset, is_major, h.rx.p, h.y.p, h.ya.p, p->rhs.p, h.rup.p, h.yn.p, h.ry.p);
+  launch_spmv_plain(s, p->AT.dev, h.y.p, h.aty.p);
+  p->launches += 3;
+}
+
+// the scalars of one check (launch_hip_check) for the iterate (x, y); with_fpe: also the fixed-point error of the major
+// step that produced it.  Leaves them in p->houts[0..8] after ONE synchronisation.
+static void hip_check(b200pdlp_problem* p, const double* x, const double* y, int with_fpe, int use_cached_slack) {
+  auto& h = p->hip;
+  cudaStream_t s = p->stream;
+  if (with_fpe) {
+    launch_hip_diff(s, p->m, y, h.ry.p, h.dy.p);
+    launch_spmv_plain(s, p->AT.dev, h.dy.p, h.atdy.p);
+    p->launches += 2;
+  }
+  launch_spmv_plain(s, p->A.dev, x, h.axp.p);
+  launch_spmv_plain(s, p->AT.dev, y, h.atyp.p);
+  launch_hip_slack(s, p->n, use_cached_slack, h.hslack.p, p->cost.p, h.atyp.p, p->lower.p, p->upper.p, h.sp.p, h.sn.p);
+  HipCheckArgs a{};
+  a.n = p->n; a.m = p->m; a.neq = p->neq_local; a.scaled = p->form.scaled ? 1 : 0; a.offset = p->form.offset;
+  a.x = x; a.y = y; a.ax = h.axp.p; a.aty = h.atyp.p; a.rx = h.rx.p; a.ry = h.ry.p; a.atdy = h.atdy.p;
+  a.xa = h.xa.p; a.ya = h.ya.p; a.c = p->cost.p; a.lo = p->lower.p; a.up = p->upper.p; a.rlo = p->rhs.p;
+  a.colscale = p->colscale.p; a.rowscale = p->rowscale.p; a.sp = h.sp.p; a.sn = h.sn.p;
+  launch_hip_check(s, a, with_fpe, p->ordered ? 1 : 0, p->rs(kSlotChk, std::max(p->n, p->m)), p->outs.p);
+  p->launches += 4;
+  CUDA_OK(cudaMemcpyAsync(p->houts, p->outs.p, 9 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+}
+
+static void solve_hipdlp_on_device(b200pdlp_problem* p, const b200pdlp_lp& lp, const b200pdlp_hipdlp_params& prm, b200pdlp_result* out) {
+  using clk = std::chrono::steady_clock;
+  set_device(p);
+  const auto t_begin = clk::now();
+  const StdForm& f = p->form;
+  auto& h = p->hip;
+  cudaStream_t s = p->stream;
+  const int n = p->n, m = p->m;
+  const long long launches0 = p->launches;
+  // initializeStepSizes (pdhg.cc:1944-1977); the power method runs on the host copy of the scaled matrix for now
+  double omega = (f.norm_cost + 1.0) / (f.norm_rhs + 1.0);
+  double primal_weight = omega, best_primal_weight = omega, best_gap = std::numeric_limits<double>::infinity();
+  double err_sum = 0.0, last_err = 0.0;
+  const double op_norm_sq = power_method_hipdlp(f);
+  const double eta = 0.998 / std::sqrt(op_norm_sq);
+  double primal_step = eta / omega, dual_step = eta * omega;
+  // x = proj_[l,u](0), y = 0; anchors = iterates; A'y (:512-552)
+  {
+    std::vector<double> x0(std::max(n, 1), 0.0);
+    for (int i = 0; i < n; i++) {
+      const int j = p->cperm[i];
+      double v = 0.0;
+      if (v > f.upper[j]) v = f.upper[j];
+      if (v < f.lower[j]) v = f.lower[j];
+      x0[i] = v;
+    }
+    CUDA_OK(cudaMemcpyAsync(h.x.p, x0.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemsetAsync(h.y.p, 0, (size_t)std::max(m, 1) * sizeof(double), s));
+    CUDA_OK(cudaMemcpyAsync(h.xa.p, h.x.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    CUDA_OK(cudaMemsetAsync(h.ya.p, 0, (size_t)std::max(m, 1) * sizeof(double), s));
+    for (DevBuf<double>* b : {&h.xn, &h.rx, &h.hslack, &h.sp, &h.sn, &h.atdy}) CUDA_OK(cudaMemsetAsync(b->p, 0, (size_t)std::max(n, 1) * sizeof(double), s));
+    for (DevBuf<double>* b : {&h.yn, &h.ry, &h.dy}) CUDA_OK(cudaMemsetAsync(b->p, 0, (size_t)std::max(m, 1) * sizeof(double), s));
+    launch_spmv_plain(s, p->AT.dev, h.y.p, h.aty.p);
+    CUDA_OK(cudaStreamSynchronize(s));
+  }
+  auto push_state = [&](int halpern_iteration) {
+    h.hstate->primal_step = primal_step; h.hstate->dual_step = dual_step; h.hstate->halpern_iteration = halpern_iteration;
+    CUDA_OK(cudaMemcpyAsync(h.state.p, h.hstate, sizeof(HipState), cudaMemcpyHostToDevice, s));
+  };
+  if (!h.graph) {   // steps 2 .. 40 of a block: 38 minor steps and the closing major step (:629-632)
+    cudaGraph_t g = nullptr;
+    CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    for (int i = 2; i <= 39; i++) hip_step(p, i, 0);
+    hip_step(p, 40, 1);
+    CUDA_OK(cudaStreamEndCapture(s, &g));
+    CUDA_OK(cudaGraphInstantiate(&h.graph, g, 0));
+    CUDA_OK(cudaGraphDestroy(g));
+    p->launches -= 39 * 3;   // counted when replayed
+  }
+  const double tol = prm.tolerance;
+  const double tol_p = tol * (1.0 + f.norm_rhs), tol_d = tol * (1.0 + f.norm_cost);
+  double pfeas = 0.0, dfeas = 0.0, pobj = 0.0, dobj = 0.0, relgap = 0.0;
+  auto read_check = [&]() {   // checkConvergence, :1474-1527
+    pfeas = std::sqrt(p->houts[3]); dfeas = std::sqrt(p->houts[4]);
+    pobj = p->houts[5]; dobj = p->houts[6];
+    const double gap = pobj - dobj;
+    relgap = std::fabs(gap) / (1.0 + std::fabs(pobj) + std::fabs(dobj));
+    return pfeas < tol_p && dfeas < tol_d && relgap < tol;
+  };
+  auto fpe_from_outs = [&]() {   // computeFixedPointError, :733-739
+    const double movement = p->houts[0] * omega + p->houts[1] / omega;
+    const double interaction = 2.0 * eta * p->houts[2];
+    return std::sqrt(std::max(0.0, movement + interaction));
+  };
+  const double t_lim = (prm.time_limit > 0 && std::isfinite(prm.time_limit)) ? prm.time_limit : 0.0;
+  int term = B200PDLP_TIMELIMIT_OR_ITERLIMIT, iters = 0, halpern_iteration = 0, restarts = 0;
+  bool converged = false, do_restart = false, timed_out = false;
+  double fpe = 0.0, fpe0 = 0.0, last_trial = std::numeric_limits<double>::infinity();
+  const auto t_loop = clk::now();
+  hip_check(p, h.x.p, h.y.p, 0, 0);   // iteration 0 (:566-572)
+  const double* sol_x = h.x.p;
+  const double* sol_y = h.y.p;
+  if (read_check()) { converged = true; }
+  else {
+    while (iters < prm.iter_limit) {
+      if (t_lim > 0 && std::chrono::duration<double>(clk::now() - t_loop).count() > t_lim) { timed_out = true; break; }
+      push_state(halpern_iteration);
+      hip_step(p, 1, 1);
+      if (do_restart) {   // the restart's reference fixed-point error is that of the first step after it (:600-608)
+        hip_check(p, h.xn.p, h.yn.p, 1, 1);
+        fpe = fpe_from_outs(); fpe0 = fpe; do_restart = false;
+      }
+      CUDA_OK(cudaGraphLaunch(h.graph, s));
+      p->launches += 39 * 3;
+      hip_check(p, h.xn.p, h.yn.p, 1, 1);
+      fpe = fpe_from_outs();
+      halpern_iteration += 40;
+      iters += 40;
+      if (prm.log_level >= 2)
+        printf("[b200pdlp hipdlp] it %8d  pobj %+.8e dobj %+.8e  pfeas %.2e dfeas %.2e  fpe %.3e  weight %.3e\n", iters,
+               p->houts[5], p->houts[6], std::sqrt(p->houts[3]), std::sqrt(p->houts[4]), fpe, primal_weight);
+      if (read_check()) { converged = true; sol_x = h.xn.p; sol_y = h.yn.p; break; }
+      // checkRestartCriteria, :901-927
+      do_restart = false;
+      if (iters == 40) do_restart = true;
+      else if (iters > 40) {
+        if (fpe <= 0.2 * fpe0) do_restart = true;
+        else if (fpe <= 0.8 * fpe0 && fpe > last_trial) do_restart = true;
+        else if (halpern_iteration >= 0.36 * iters) do_restart = true;
+      }
+      last_trial = fpe;
+      if (do_restart) {
+        restarts++;
+        if (prm.step_size_strategy != 0) {   // updatePrimalWeightAtRestart (PID), :1979-2050
+          const double pd = std::sqrt(p->houts[7]), dd = std::sqrt(p->houts[8]);
+          const double rel_p = pfeas / (1.0 + f.norm_rhs), rel_d = dfeas / (1.0 + f.norm_cost);
+          const double ratio = (rel_p > 0.0) ? (rel_d / rel_p) : 1e300;
+          if (pd > 1e-16 && dd > 1e-16 && pd < 1e12 && dd < 1e12 && ratio > 1e-8 && ratio < 1e8) {
+            const double error = std::log(dd) - std::log(pd) - std::log(primal_weight);
+            err_sum = 0.3 * err_sum + error;
+            const double delta = error - last_err;
+            primal_weight *= std::exp(0.99 * error + 0.01 * err_sum + 0.0 * delta);
+            last_err = error;
+          } else {
+            primal_weight = best_primal_weight; err_sum = 0.0; last_err = 0.0;
+          }
+          const double gap = (rel_p > 0.0 && rel_d > 0.0) ? std::fabs(std::log10(rel_d / rel_p)) : best_gap;
+          if (gap < best_gap) { best_gap = gap; best_primal_weight = primal_weight; }
+          const double e2 = std::sqrt(primal_step * dual_step);
+          primal_step = e2 / primal_weight;
+          dual_step = e2 * primal_weight;
+          omega = primal_weight;
+        }
+        CUDA_OK(cudaMemcpyAsync(h.xa.p, h.xn.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        CUDA_OK(cudaMemcpyAsync(h.ya.p, h.yn.p, (size_t)std::max(m, 1) * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        CUDA_OK(cudaMemcpyAsync(h.x.p, h.xn.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        CUDA_OK(cudaMemcpyAsync(h.y.p, h.yn.p, (size_t)std::max(m, 1) * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        launch_spmv_plain(s, p->AT.dev, h.y.p, h.aty.p);
+        p->launches++;
+        halpern_iteration = 0;
+        last_trial = std::numeric_limits<double>::infinity();
+      }
+    }
+  }
+  if (converged) term = B200PDLP_OPTIMAL;
+  const double solve_seconds = std::chrono::duration<double>(clk::now() - t_loop).count();
+  // unscaleSolution + postprocess (pdhg.cc:1883-1897, :359-492): the iterate is copied out ONLY on convergence --
+  // an iteration-limited run returns x = y = 0, like the reference
+  std::vector<double> hx(std::max(n, 1), 0.0), hy(std::max(m, 1), 0.0), hsp(std::max(n, 1)), hsn(std::max(n, 1));
+  {
+    std::vector<double> t(std::max(std::max(n, m), 1));
+    auto down_col = [&](const double* d, std::vector<double>& v) {
+      CUDA_OK(cudaMemcpyAsync(t.data(), d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+      CUDA_OK(cudaStreamSynchronize(s));
+      for (int i = 0; i < n; i++) v[p->cperm[i]] = t[i];
+    };
+    if (converged) {
+      down_col(sol_x, hx);
+      if (m) CUDA_OK(cudaMemcpyAsync(t.data(), sol_y, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, s));
+      CUDA_OK(cudaStreamSynchronize(s));
+      for (int i = 0; i < m; i++) hy[p->rperm[i]] = t[i];
+    }
+    down_col(h.sp.p, hsp); down_col(h.sn.p, hsn);
+  }
+  if (f.scaled) {
+    for (int i = 0; i < n; i++) hx[i] /= f.col_scale[i];
+    for (int i = 0; i < m; i++) hy[i] /= f.row_scale[i];
+  }
+  for (int i = 0; i < n; i++) { hsp[i] *= f.col_scale[i]; hsn[i] *= f.col_scale[i]; }
+  if (out->col_value && out->col_dual && out->row_value && out->row_dual) {
+    for (int j = 0; j < f.n_orig; j++) out->col_value[j] = hx[j];
+    for (int i = 0; i < m; i++) {
+      const double d = hy[f.row_new_idx[i]];
+      out->row_dual[i] = f.row_class[i] == kLeq ? -d : d;
+    }
+    for (int i = 0; i < m; i++) out->row_value[i] = 0.0;
+    for (int c = 0; c < lp.num_col; c++) {
+      const double xv = hx[c];
+      for (int q = lp.a_start[c]; q < lp.a_start[c + 1]; q++) out->row_value[lp.a_index[q]] += lp.a_value[q] * xv;
+    }
+    for (int j = 0; j < f.n_orig; j++) { double v = hsp[j] - hsn[j]; v *= f.sense; out->col_dual[j] = v; }
+  }
+  out->value_valid = 1; out->dual_valid = 1;
+  out->term_code = term;
+  out->term_iterate = timed_out ? 2 : 0;   // 2: the time limit, not the iteration limit, ended the run
+  out->iters = iters; out->passes = iters; out->restarts = restarts;
+  out->kernel_launches = (int)std::min<long long>(p->launches - launches0, 2147483647LL);
+  out->primal_obj = pobj; out->dual_obj = dobj; out->primal_feas = pfeas; out->dual_feas = dfeas;
+  out->gap = pobj - dobj; out->rel_gap = relgap;
+  out->solve_seconds = solve_seconds;
+  out->setup_seconds += std::chrono::duration<double>(t_loop - t_begin).count();
+  out->form_cols = n; out->form_rows = m; out->form_nnz = f.nnz; out->form_neq = f.neq;
+}
+
 }  // namespace b200
 
 // ============================================================================ C ABI
@@ -1576,6 +1856,37 @@ int b200pdlp_solve_multi(const b200pdlp_lp* lp, const b200pdlp_params* params, c
   for (b200pdlp_problem* p : probs)
     if (p) { cudaSetDevice(p->device); p->p2p = false; delete p; }
   return rc;
+}
+
+void b200pdlp_hipdlp_default_params(b200pdlp_hipdlp_params* p) {
+  memset(p, 0, sizeof(*p));
+  p->tolerance = 1e-7;
+  p->iter_limit = 2147483647;
+  p->scaling_mode = 5;
+  p->ruiz_iterations = 10;
+  p->step_size_strategy = 3;
+  p->device = -1;
+}
+
+int b200pdlp_solve_hipdlp(const b200pdlp_lp* lp, const b200pdlp_hipdlp_params* params, b200pdlp_result* out) {
+  return guarded([&] {
+    check_lp(lp);
+    if (!params || !out) throw Error(B200PDLP_ERR_ARG, "null argument");
+    const auto t0 = std::chrono::steady_clock::now();
+    b200pdlp_problem* p = new b200pdlp_problem();
+    try {
+      create_problem_hipdlp(*lp, *params, p);
+      out->setup_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      solve_hipdlp_on_device(p, *lp, *params, out);
+      CUDA_OK(cudaGetLastError());
+    } catch (...) {
+      cudaSetDevice(p->device);
+      delete p;
+      throw;
+    }
+    cudaSetDevice(p->device);
+    delete p;
+  });
 }
 
 int b200pdlp_nccl_unique_id(uint8_t id[128]) {

@@ -55,6 +55,13 @@ struct PdhgState {
   double pow_grow[kPowTab];          // (k+1)^-0.6
 };
 
+// HiPDLP mode: the few scalars a Halpern step reads on the device (so that a block of steps is graph-capturable)
+struct HipState {
+  double primal_step, dual_step;
+  int halpern_iteration;   // steps since the last restart BEFORE the block that is running
+  int pad;
+};
+
 // device view of a SellMatrix (host_prep.hpp)
 struct DevSell {
   int nrows, nslices;

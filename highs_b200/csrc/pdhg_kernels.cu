@@ -1207,3 +1207,211 @@ void launch_fill(cudaStream_t s, int len, double* v, double w) {
 }
 
 }  // namespace b200
+
+// =====================================================================================================================
+// HiPDLP mode (solver=hipdlp): reflected Halpern PDHG, /root/reference/highs/pdlp/hipdlp/pdhg.cc:961-1018.
+// One step = primal kernel (projection, reflection, Halpern blend of x) -> A * reflected x fused with the dual
+// projection / reflection / blend of y -> A' y.  There is NO reduction and no step rule inside a step, so a block of
+// steps is a plain chain of kernels (graph) and the trajectory does not depend on any summation order; the reductions
+// live in the checks (fixed-point error, convergence test) every 40 steps.
+// STATUS: written after round 1's GPU budget was spent; compiled, not yet run on hardware (tests/test_gpu_hipdlp.py).
+namespace b200 {
+
+__device__ __forceinline__ double std_max(double a, double b) { return a < b ? b : a; }   // std::max / std::min semantics
+__device__ __forceinline__ double std_min(double a, double b) { return b < a ? b : a; }
+
+// x-side of performHalpernPdhgStep (:974-986, :1006-1009)
+__global__ void __launch_bounds__(kThreads)
+hip_primal_kernel(int n, const HipState* __restrict__ st, int k_offset, int is_major, double* __restrict__ x,
+                  const double* __restrict__ xa, const double* __restrict__ c, const double* __restrict__ aty,
+                  const double* __restrict__ lo, const double* __restrict__ up, double* __restrict__ rx,
+                  double* __restrict__ xn, double* __restrict__ hslack) {
+  const double ps = st->primal_step, rho = 1.0;
+  const int k = st->halpern_iteration + k_offset;
+  const double w = (double)k / (k + 1.0);
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const double xc = x[i];
+    const double temp = xc - ps * (c[i] - aty[i]);
+    const double proj = std_max(lo[i], std_min(temp, up[i]));
+    if (is_major) { xn[i] = proj; hslack[i] = (proj - temp) / ps; }
+    const double r = 2.0 * proj - xc;
+    rx[i] = r;
+    const double blended = rho * r + (1.0 - rho) * xc;
+    x[i] = w * blended + (1.0 - w) * xa[i];
+  }
+}
+
+// y-side (:992-1003, :1010-1013) as the epilogue of ax = A * reflected x
+struct HipDualEpilogue {
+  static constexpr int NACC = 0;
+  const HipState* st;
+  int k_offset, is_major;
+  const double* in;            // reflected x
+  double* y;                   // current dual iterate, blended in place
+  const double *ya, *rlo, *rup;
+  double *yn, *ry;             // written on major steps only (the checks read them)
+  double ds, w;
+  __device__ bool begin() {
+    ds = st->dual_step;
+    const int k = st->halpern_iteration + k_offset;
+    w = (double)k / (k + 1.0);
+    return true;
+  }
+  __device__ const double* input() const { return in; }
+  double p_y, p_ya, p_lo, p_up;
+  __device__ void prefetch(int r) { p_y = y[r]; p_ya = ya[r]; p_lo = rlo[r]; p_up = rup[r]; }
+  __device__ void row(int r, double s, double*) const {
+    const double rho = 1.0;
+    const double temp = p_y / ds - s;
+    const double proj = std_max(-p_up, std_min(temp, -p_lo));
+    const double pd = (temp - proj) * ds;
+    const double refl = 2.0 * pd - p_y;
+    if (is_major) { yn[r] = pd; ry[r] = refl; }
+    const double blended = rho * refl + (1.0 - rho) * p_y;
+    y[r] = w * blended + (1.0 - w) * p_ya;
+  }
+};
+
+void launch_hip_primal(cudaStream_t s, int n, const HipState* st, int k_offset, int is_major, double* x, const double* xa,
+                       const double* c, const double* aty, const double* lo, const double* up, double* rx, double* xn,
+                       double* hslack) {
+  hip_primal_kernel<<<ew_grid(n), kThreads, 0, s>>>(n, st, k_offset, is_major, x, xa, c, aty, lo, up, rx, xn, hslack);
+}
+void launch_hip_dual(cudaStream_t s, const DevSell& A, const HipState* st, int k_offset, int is_major, const double* rx,
+                     double* y, const double* ya, const double* rlo, const double* rup, double* yn, double* ry) {
+  if (A.nblocks_body + A.nsegs == 0) return;
+  HipDualEpilogue e{};
+  e.st = st; e.k_offset = k_offset; e.is_major = is_major; e.in = rx; e.y = y; e.ya = ya; e.rlo = rlo; e.rup = rup;
+  e.yn = yn; e.ry = ry;
+  spmv_sell_kernel<HipDualEpilogue><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr, nullptr, 0, 0});
+}
+
+// ------------------------------------------------------------------------------------------------ checks
+// out = a - b (the dual movement y_next - reflected_y that computeFixedPointError multiplies by A', :722-726)
+__global__ void __launch_bounds__(kThreads) hip_diff_kernel(int len, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < len; i += stride) out[i] = a[i] - b[i];
+}
+void launch_hip_diff(cudaStream_t s, int len, const double* a, const double* b, double* out) {
+  if (len > 0) hip_diff_kernel<<<ew_grid(len), kThreads, 0, s>>>(len, a, b, out);
+}
+
+// dual slacks of the checked iterate (computeDualSlacks, :1322-1378): the cached major-step slack when there is one,
+// otherwise the residual projected by the signs of the bounds
+__global__ void __launch_bounds__(kThreads)
+hip_slack_kernel(int n, int use_cached, const double* __restrict__ hslack, const double* __restrict__ c, const double* __restrict__ aty,
+                 const double* __restrict__ lo, const double* __restrict__ up, double* __restrict__ sp, double* __restrict__ sn) {
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    double slack = 0.0;
+    if (use_cached) slack = hslack[i];
+    else {
+      const double dres = c[i] - aty[i];
+      const bool hl = lo[i] > -INFINITY, hu = up[i] < INFINITY;
+      if (hl && hu) slack = dres;
+      else if (hl) slack = std_max(0.0, dres);
+      else if (hu) slack = std_min(0.0, dres);
+    }
+    sp[i] = std_max(0.0, slack);
+    sn[i] = std_max(0.0, -slack);
+  }
+}
+void launch_hip_slack(cudaStream_t s, int n, int use_cached, const double* hslack, const double* c, const double* aty,
+                      const double* lo, const double* up, double* sp, double* sn) {
+  if (n > 0) hip_slack_kernel<<<ew_grid(n), kThreads, 0, s>>>(n, use_cached, hslack, c, aty, lo, up, sp, sn);
+}
+
+// The scalars of one check, each added in the REFERENCE'S ORDER by one warp (lanes load 32 terms at once, then every
+// lane adds them in index order): bit-identical to the reference's sequential loops at any size, ~1 ns per term.
+//   out[0] |x_next - refl_x|^2   out[1] |y_next - refl_y|^2   out[2] (x_next - refl_x).(A' dy)          (fixed-point error, :709-740)
+//   out[3] |primal residual|^2 (:1297-1320)   out[4] |dual residual|^2 (:1380-1408)
+//   out[5] offset + c.x (:1496-1500)          out[6] offset + b.y + l.sp - u.sn (:1447-1472)
+//   out[7] |x_next - x_anchor|^2              out[8] |y_next - y_anchor|^2                                (PID weight, :1984-1999)
+template <class Term>
+__device__ __forceinline__ double warp_ordered_sum(int len, double init, Term term) {
+  const int lane = threadIdx.x & 31;
+  double sum = init;
+  for (int base = 0; base < len; base += 32) {
+    const int i = base + lane;
+    const double t = i < len ? term(i) : 0.0;
+    const int cnt = (len - base) < 32 ? (len - base) : 32;
+    for (int k = 0; k < cnt; k++) sum = sum + __shfl_sync(0xffffffffu, t, k);
+  }
+  return sum;
+}
+__global__ void __launch_bounds__(9 * 32) hip_check_ordered_kernel(HipCheckArgs a, int with_fpe, double* __restrict__ out) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double v = 0.0;
+  switch (w) {
+    case 0: if (with_fpe) v = warp_ordered_sum(a.n, 0.0, [&](int i) { const double d = a.x[i] - a.rx[i]; return d * d; }); break;
+    case 1: if (with_fpe) v = warp_ordered_sum(a.m, 0.0, [&](int i) { const double d = a.y[i] - a.ry[i]; return d * d; }); break;
+    case 2: if (with_fpe) v = warp_ordered_sum(a.n, 0.0, [&](int i) { return (a.x[i] - a.rx[i]) * a.atdy[i]; }); break;
+    case 3: v = warp_ordered_sum(a.m, 0.0, [&](int i) {
+              double r = a.ax[i] - a.rlo[i];
+              if (i >= a.neq) r = std_min(0.0, r);
+              if (a.scaled) r = r * a.rowscale[i];
+              return r * r; });
+            break;
+    case 4: v = warp_ordered_sum(a.n, 0.0, [&](int i) {
+              double r = (a.c[i] - a.aty[i]) - a.sp[i] + a.sn[i];
+              if (a.scaled) r = r * a.colscale[i];
+              return r * r; });
+            break;
+    case 5: v = warp_ordered_sum(a.n, a.offset, [&](int i) { return a.c[i] * a.x[i]; }); break;
+    case 6: {
+      v = warp_ordered_sum(a.m, a.offset, [&](int i) { return a.rlo[i] * a.y[i]; });
+      // skipped (infinite-bound) columns add nothing in the reference: + 0.0 leaves the running sum unchanged
+      v = warp_ordered_sum(a.n, v, [&](int i) { return a.lo[i] > -INFINITY ? a.lo[i] * a.sp[i] : 0.0; });
+      v = warp_ordered_sum(a.n, v, [&](int i) { return a.up[i] < INFINITY ? -(a.up[i] * a.sn[i]) : 0.0; });
+      break;
+    }
+    case 7: v = warp_ordered_sum(a.n, 0.0, [&](int i) { const double d = a.x[i] - a.xa[i]; return d * d; }); break;
+    case 8: v = warp_ordered_sum(a.m, 0.0, [&](int i) { const double d = a.y[i] - a.ya[i]; return d * d; }); break;
+  }
+  if (lane == 0) out[w] = v;
+}
+// the same scalars with grid-wide tree sums (large problems; deterministic, not the reference's order)
+__global__ void __launch_bounds__(kThreads) hip_check_tree_kernel(HipCheckArgs a, int with_fpe, ReduceScratch rs, double* __restrict__ out) {
+  double acc[9];
+#pragma unroll
+  for (int q = 0; q < 9; q++) acc[q] = 0.0;
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < a.n; i += stride) {
+    if (with_fpe) { const double d = a.x[i] - a.rx[i]; acc[0] += d * d; acc[2] += d * a.atdy[i]; }
+    double r = (a.c[i] - a.aty[i]) - a.sp[i] + a.sn[i];
+    if (a.scaled) r = r * a.colscale[i];
+    acc[4] += r * r;
+    acc[5] += a.c[i] * a.x[i];
+    if (a.lo[i] > -INFINITY) acc[6] += a.lo[i] * a.sp[i];
+    if (a.up[i] < INFINITY) acc[6] -= a.up[i] * a.sn[i];
+    const double d2 = a.x[i] - a.xa[i];
+    acc[7] += d2 * d2;
+  }
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < a.m; i += stride) {
+    if (with_fpe) { const double d = a.y[i] - a.ry[i]; acc[1] += d * d; }
+    double r = a.ax[i] - a.rlo[i];
+    if (i >= a.neq) r = std_min(0.0, r);
+    if (a.scaled) r = r * a.rowscale[i];
+    acc[3] += r * r;
+    acc[6] += a.rlo[i] * a.y[i];
+    const double d2 = a.y[i] - a.ya[i];
+    acc[8] += d2 * d2;
+  }
+  double res[9];
+  if (grid_reduce<9>(acc, rs, res) && threadIdx.x == 0) {
+    for (int q = 0; q < 9; q++) out[q] = res[q];
+    out[5] += a.offset;
+    out[6] += a.offset;
+  }
+}
+void launch_hip_check(cudaStream_t s, const HipCheckArgs& a, int with_fpe, int ordered, ReduceScratch rs, double* out) {
+  if (ordered) hip_check_ordered_kernel<<<1, 9 * 32, 0, s>>>(a, with_fpe, out);
+  else {
+    rs.terms = nullptr;
+    const int len = a.n > a.m ? a.n : a.m;
+    hip_check_tree_kernel<<<ew_grid(len), kThreads, 0, s>>>(a, with_fpe, rs, out);
+  }
+}
+
+}  // namespace b200

@@ -69,4 +69,23 @@ void launch_diff_norm2(cudaStream_t s, int len, const double* a, const double* b
 void launch_scale(cudaStream_t s, int len, double* v, double w);
 void launch_fill(cudaStream_t s, int len, double* v, double w);
 
+// ---- HiPDLP mode (reflected Halpern PDHG; pdhg_kernels.cu, last section)
+struct HipCheckArgs {
+  int n, m, neq, scaled;
+  double offset;
+  const double *x, *y, *ax, *aty;
+  const double *rx, *ry, *atdy;
+  const double *xa, *ya;
+  const double *c, *lo, *up, *rlo, *colscale, *rowscale, *sp, *sn;
+};
+void launch_hip_primal(cudaStream_t s, int n, const HipState* st, int k_offset, int is_major, double* x, const double* xa,
+                       const double* c, const double* aty, const double* lo, const double* up, double* rx, double* xn,
+                       double* hslack);
+void launch_hip_dual(cudaStream_t s, const DevSell& A, const HipState* st, int k_offset, int is_major, const double* rx,
+                     double* y, const double* ya, const double* rlo, const double* rup, double* yn, double* ry);
+void launch_hip_diff(cudaStream_t s, int len, const double* a, const double* b, double* out);
+void launch_hip_slack(cudaStream_t s, int n, int use_cached, const double* hslack, const double* c, const double* aty,
+                      const double* lo, const double* up, double* sp, double* sn);
+void launch_hip_check(cudaStream_t s, const HipCheckArgs& a, int with_fpe, int ordered, ReduceScratch rs, double* out);
+
 }  // namespace b200

@@ -41,6 +41,12 @@ class CParams(C.Structure):
                 ("ordered_max", C.c_int32), ("device_scaling", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
+class CHipdlpParams(C.Structure):
+    _fields_ = [("tolerance", C.c_double), ("iter_limit", C.c_int32), ("scaling_mode", C.c_int32),
+                ("ruiz_iterations", C.c_int32), ("step_size_strategy", C.c_int32), ("time_limit", C.c_double),
+                ("ordered_max", C.c_int32), ("device", C.c_int32), ("log_level", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
 class CWarm(C.Structure):
     _fields_ = [("col_value", _dp), ("row_value", _dp), ("row_dual", _dp)]
 
@@ -66,7 +72,8 @@ ABI_SYMBOLS = [
     "b200pdlp_device_count", "b200pdlp_form_create", "b200pdlp_form_destroy", "b200pdlp_form_dims",
     "b200pdlp_form_get_vector", "b200pdlp_form_get_csc", "b200pdlp_form_get_csr", "b200pdlp_form_get_row_map",
     "b200pdlp_form_layout_eval", "b200pdlp_p2p_link_local", "b200pdlp_solve_multi",
-    "b200pdlp_hipdlp_form_create", "b200pdlp_hipdlp_power_method",
+    "b200pdlp_hipdlp_form_create", "b200pdlp_hipdlp_power_method", "b200pdlp_hipdlp_default_params",
+    "b200pdlp_solve_hipdlp",
 ]
 
 _lib = None
@@ -201,6 +208,25 @@ def solve(lp: HighsLp, warm=None, trace_cap: int = 0, **params) -> dict:
     res, arrays = _mk_result(lp, trace_cap)
     w, wk = _mk_warm(warm)
     _check(L.b200pdlp_solve(C.byref(clp), C.byref(prm), C.byref(w) if w else None, C.byref(res)), "b200pdlp_solve")
+    return _result_dict(res, arrays)
+
+
+def solve_hipdlp(lp: HighsLp, **params) -> dict:
+    """b200pdlp_solve_hipdlp: the HiPDLP mode (reflected Halpern PDHG, solver=hipdlp) on one GPU; parameters are the
+    HighsOptions of the same meaning (tolerance, iter_limit, scaling_mode, ruiz_iterations, step_size_strategy ...)."""
+    L = lib()
+    L.b200pdlp_hipdlp_default_params.argtypes = [C.POINTER(CHipdlpParams)]
+    L.b200pdlp_hipdlp_default_params.restype = None
+    L.b200pdlp_solve_hipdlp.argtypes = [C.POINTER(CLp), C.POINTER(CHipdlpParams), C.POINTER(CResult)]
+    clp, keep = make_clp(lp)
+    prm = CHipdlpParams()
+    L.b200pdlp_hipdlp_default_params(C.byref(prm))
+    for k, v in params.items():
+        if not hasattr(prm, k):
+            raise TypeError(f"unknown parameter {k}")
+        setattr(prm, k, v)
+    res, arrays = _mk_result(lp, 0)
+    _check(L.b200pdlp_solve_hipdlp(C.byref(clp), C.byref(prm), C.byref(res)), "b200pdlp_solve_hipdlp")
     return _result_dict(res, arrays)
 
 

@@ -213,6 +213,26 @@ int b200pdlp_form_get_row_map(const b200pdlp_form* f, int32_t* row_new_idx, int3
  * HighsOptions::pdlp_scaling_mode, ruiz_iterations = pdlp_ruiz_iterations).  The form answers the b200pdlp_form_* getters;
  * rows carry an upper bound too: b200pdlp_form_get_vector(which = 6).  row_class uses 4 for FREE rows. */
 int b200pdlp_hipdlp_form_create(const b200pdlp_lp* lp, int32_t scaling_mode, int32_t ruiz_iterations, b200pdlp_form** out);
+/* The HiPDLP solve on one GPU: what a shim replacing pdlp/HiPdlpWrapper.cpp (solveLpHiPdlp, :26-141) forwards to.
+ * Parameters are the HighsOptions the reference's setup() reads (hipdlp/pdhg.cc:1783-1874).  term_code is B200PDLP_OPTIMAL or
+ * B200PDLP_TIMELIMIT_OR_ITERLIMIT (term_iterate = 2 when it was the time limit); like the reference, a run that does not
+ * converge returns x = y = 0 (the iterate is copied out only on convergence, pdhg.cc:784-899).
+ * STATUS: written after round 1's GPU budget was spent -- compiled, not yet run on hardware. */
+typedef struct {
+  double tolerance;           /* pdlp_optimality_tolerance, or kkt_tolerance when set */
+  int32_t iter_limit;         /* pdlp_iteration_limit */
+  int32_t scaling_mode;       /* pdlp_scaling_mode: bits 1 Ruiz, 2 L2, 4 Pock-Chambolle (default 5); 0 when scaling is off */
+  int32_t ruiz_iterations;    /* pdlp_ruiz_iterations (default 10) */
+  int32_t step_size_strategy; /* pdlp_step_size_strategy: 0 fixed primal weight, anything else PID */
+  double time_limit;          /* seconds; <= 0 or inf = none */
+  int32_t ordered_max;        /* as in b200pdlp_params: checks add in the reference's order up to this size */
+  int32_t device;             /* CUDA device ordinal; -1 = current */
+  int32_t log_level;
+  int32_t reserved[3];
+} b200pdlp_hipdlp_params;
+void b200pdlp_hipdlp_default_params(b200pdlp_hipdlp_params* p);
+int b200pdlp_solve_hipdlp(const b200pdlp_lp* lp, const b200pdlp_hipdlp_params* params, b200pdlp_result* out);
+
 /* PDLPSolver::powerMethod (hipdlp/pdhg.cc:1529-1671): 20 iterations on A A' from the ones vector -> estimate of |A|_2^2 */
 int b200pdlp_hipdlp_power_method(const b200pdlp_form* f, double* lambda);
 

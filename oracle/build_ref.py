@@ -124,8 +124,20 @@ def main():
     nj.append("rule exeshim\n  command = g++ -std=c++11 -O2 $cxxincs $in -o $out -L$libdir -lhighs_b200 -L$engdir -lb200pdlp '-Wl,-rpath,$$ORIGIN' '-Wl,-rpath,$engdir' -lpthread")
     nj.append(f"build {drv2}: exeshim {os.path.join(HERE, 'ref_driver.cpp')} | {lib2}\n"
               f"  cxxincs = {incs} -w\n  libdir = {OUT}\n  engdir = {eng_dir}")
+    # --- the same with the HiPDLP wrapper replaced as well (solver=hipdlp -> the engine's Halpern mode); kept in a THIRD
+    # library so that the validated solver=pdlp drop-in above is untouched while the HiPDLP device mode is unvalidated
+    shim2_src = os.path.join(os.path.dirname(HERE), "highs_b200", "csrc", "highs_shim_hipdlp.cpp")
+    shim2_o = os.path.join(OUT, "obj", "highs_shim_hipdlp.o")
+    lib3 = os.path.join(OUT, "libhighs_b200_hipdlp.so")
+    drv3 = os.path.join(OUT, "ref_driver_b200_hipdlp")
+    keep3 = [o for o, s_ in zip(objs, srcs) if not s_.endswith("pdlp/CupdlpWrapper.cpp") and not s_.endswith("pdlp/HiPdlpWrapper.cpp")]
+    nj.append(f"build {shim2_o}: cxxshim {shim2_src}\n  cxxflags_shim = {common} -I{os.path.join(os.path.dirname(HERE), 'include')}")
+    nj.append(f"build {lib3}: linkshim {' '.join(keep3)} {shim_o} {shim2_o}\n  engdir = {eng_dir}")
+    nj.append("rule exeshim3\n  command = g++ -std=c++11 -O2 $cxxincs $in -o $out -L$libdir -lhighs_b200_hipdlp -L$engdir -lb200pdlp '-Wl,-rpath,$$ORIGIN' '-Wl,-rpath,$engdir' -lpthread")
+    nj.append(f"build {drv3}: exeshim3 {os.path.join(HERE, 'ref_driver.cpp')} | {lib3}\n"
+              f"  cxxincs = {incs} -w\n  libdir = {OUT}\n  engdir = {eng_dir}")
     if "--shim" in sys.argv and os.path.exists(os.path.join(eng_dir, "libb200pdlp.so")):
-        nj.append(f"default {lib} {drv} {lib2} {drv2}")
+        nj.append(f"default {lib} {drv} {lib2} {drv2} {lib3} {drv3}")
     else:
         nj.append(f"default {lib} {drv}")
     njp = os.path.join(OUT, "build.ninja")

@@ -1,0 +1,32 @@
+"""The engine's HiPDLP mode (b200pdlp_solve_hipdlp: reflected Halpern PDHG on the GPU)
+against the HiPDLP oracle, which is pinned bit for bit against the unmodified reference (tests/test_hipdlp_oracle.py):
+iteration counts, termination and solution vectors on the reference's own LP instances under five option sets.
+
+The cases run in a child process: a faulting kernel must not poison the CUDA context of the test session.
+
+STATUS: the device side of the mode was written after this round's GPU budget was spent; compiled, not yet run on hardware,
+hence xfail(strict=False): a pass shows up as XPASS, a failure does not turn the suite red."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CHILD = os.path.join(ROOT, "tests", "hipdlp_child.py")
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="HiPDLP device mode not yet run on hardware (written after the GPU budget was spent)")]
+
+
+def test_hipdlp_mode_matches_oracle():
+    try:
+        r = subprocess.run([sys.executable, CHILD], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    except subprocess.TimeoutExpired:
+        pytest.fail("HiPDLP child did not finish in 600 s (killed)")
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert lines, (r.stdout[-2000:], r.stderr[-2000:])
+    out = json.loads(lines[-1])
+    bad = {k: v for k, v in out.items() if v != "ok"}
+    assert len(out) >= 100 and not bad and r.returncode == 0, dict(list(bad.items())[:10])

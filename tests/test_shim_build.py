@@ -34,3 +34,16 @@ def test_dropin_fails_loudly_without_gpu(engine_lib):
     res = _parse_json_line(out.stdout)
     assert res["run_status"] == -1 and res["model_status_code"] == 4          # HighsStatus::kError, kSolveError
     assert res["pdlp_iteration_count"] == -1
+
+
+LIB3 = os.path.join(ROOT, "oracle", "_ref", "libhighs_b200_hipdlp.so")
+
+
+@pytest.mark.skipif(not os.path.exists(LIB3), reason="oracle/_ref/libhighs_b200_hipdlp.so not built (python oracle/build_ref.py --shim)")
+def test_hipdlp_shim_exports_the_boundary_symbols():
+    """the second drop-in point, solveLpHiPdlp (HiPdlpWrapper.h; call site HighsSolve.cpp:107-117), forwarded to the C ABI"""
+    syms = subprocess.check_output(["nm", "-D", "--defined-only", LIB3], text=True)
+    assert "_Z13solveLpHiPdlpR19HighsLpSolverObject" in syms
+    assert "_Z13solveLpCupdlpR19HighsLpSolverObject" in syms
+    und = subprocess.check_output(["nm", "-D", "--undefined-only", LIB3], text=True)
+    assert "b200pdlp_solve_hipdlp" in und and "b200pdlp_solve" in und
