@@ -62,6 +62,8 @@ def test_no_cpu_fallback(engine_lib):
         engine.solve_multi(lp, 2)          # several GPUs from one process: same rule, and a clean error path
     with pytest.raises(engine.EngineError):
         engine.solve_logical_shards(lp, 2)
+    with pytest.raises(engine.EngineError, match="no CUDA device"):
+        engine.solve_hipdlp(lp)            # the HiPDLP mode as well
 
 
 def test_bad_arguments(engine_lib):
