@@ -1353,7 +1353,29 @@ static void solve_hipdlp_on_device(b200pdlp_problem* p, const b200pdlp_lp& lp, c
   double omega = (f.norm_cost + 1.0) / (f.norm_rhs + 1.0);
   double primal_weight = omega, best_primal_weight = omega, best_gap = std::numeric_limits<double>::infinity();
   double err_sum = 0.0, last_err = 0.0;
-  const double op_norm_sq = power_method_hipdlp(f);
+  // PDLPSolver::powerMethod (pdhg.cc:1529-1671) on the device: 20 iterations of q <- A A'q / |A A'q| from the ones vector,
+  // lambda = |A'q|^2; no host round trip inside (the norm stays on the device), one read-back at the end
+  double op_norm_sq = 1.0;
+  if (n > 0 && m > 0) {
+    double* xq = h.dy.p;      // m-vectors: q (dy), z (axp); n-vector: w = A'q (atdy)
+    double* zq = h.axp.p;
+    double* wq = h.atdy.p;
+    double* sc = p->outs.p + 16;
+    launch_fill(s, m, xq, 1.0);
+    for (int it = 0; it < 20; it++) {
+      launch_spmv_plain(s, p->AT.dev, xq, wq);
+      launch_spmv_plain(s, p->A.dev, wq, zq);
+      launch_hip_dot(s, m, zq, zq, p->ordered ? 1 : 0, p->rs(kSlotChk, m), sc);
+      launch_hip_div_norm(s, m, zq, sc);
+      launch_spmv_plain(s, p->AT.dev, zq, wq);
+      launch_hip_dot(s, n, wq, wq, p->ordered ? 1 : 0, p->rs(kSlotChk, n), sc + 1);
+      CUDA_OK(cudaMemcpyAsync(xq, zq, (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      p->launches += 6;
+    }
+    CUDA_OK(cudaMemcpyAsync(p->houts + 16, sc + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    op_norm_sq = p->houts[16];
+  }
   const double eta = 0.998 / std::sqrt(op_norm_sq);
   double primal_step = eta / omega, dual_step = eta * omega;
   // x = proj_[l,u](0), y = 0; anchors = iterates; A'y (:512-552)

@@ -1415,3 +1415,31 @@ void launch_hip_check(cudaStream_t s, const HipCheckArgs& a, int with_fpe, int o
 }
 
 }  // namespace b200
+
+// ---- HiPDLP power method on the device (pdhg.cc:1529-1671): dot products in index order (one warp) or as tree sums
+namespace b200 {
+__global__ void __launch_bounds__(32) hip_dot_ordered_kernel(int len, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+  const double v = warp_ordered_sum(len, 0.0, [&](int i) { return a[i] * b[i]; });
+  if (threadIdx.x == 0) out[0] = v;
+}
+__global__ void __launch_bounds__(kThreads) hip_dot_tree_kernel(int len, const double* __restrict__ a, const double* __restrict__ b, ReduceScratch rs, double* __restrict__ out) {
+  double acc[1] = {0.0};
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < len; i += stride) acc[0] += a[i] * b[i];
+  double res[1];
+  if (grid_reduce<1>(acc, rs, res) && threadIdx.x == 0) out[0] = res[0];
+}
+// v[i] /= sqrt(*norm_sq)   (z /= ||z||, :1646-1648)
+__global__ void __launch_bounds__(kThreads) hip_div_norm_kernel(int len, double* __restrict__ v, const double* __restrict__ norm_sq) {
+  const double nrm = sqrt(*norm_sq);
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < len; i += stride) v[i] = v[i] / nrm;
+}
+void launch_hip_dot(cudaStream_t s, int len, const double* a, const double* b, int ordered, ReduceScratch rs, double* out) {
+  if (ordered) hip_dot_ordered_kernel<<<1, 32, 0, s>>>(len, a, b, out);
+  else { rs.terms = nullptr; hip_dot_tree_kernel<<<ew_grid(len), kThreads, 0, s>>>(len, a, b, rs, out); }
+}
+void launch_hip_div_norm(cudaStream_t s, int len, double* v, const double* norm_sq) {
+  if (len > 0) hip_div_norm_kernel<<<ew_grid(len), kThreads, 0, s>>>(len, v, norm_sq);
+}
+}  // namespace b200

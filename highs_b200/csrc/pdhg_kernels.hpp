@@ -87,5 +87,7 @@ void launch_hip_diff(cudaStream_t s, int len, const double* a, const double* b, 
 void launch_hip_slack(cudaStream_t s, int n, int use_cached, const double* hslack, const double* c, const double* aty,
                       const double* lo, const double* up, double* sp, double* sn);
 void launch_hip_check(cudaStream_t s, const HipCheckArgs& a, int with_fpe, int ordered, ReduceScratch rs, double* out);
+void launch_hip_dot(cudaStream_t s, int len, const double* a, const double* b, int ordered, ReduceScratch rs, double* out);
+void launch_hip_div_norm(cudaStream_t s, int len, double* v, const double* norm_sq);
 
 }  // namespace b200
