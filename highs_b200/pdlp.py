@@ -77,6 +77,10 @@ class HighsOptions:
     time_limit: float = kHighsInf
     output_flag: bool = False
     log_dev_level: int = 0
+    # read by the HiPDLP wrapper only (HighsOptions.h:1345-1379; PDLPSolver::setup, hipdlp/pdhg.cc:1820-1863)
+    pdlp_scaling_mode: int = 5            # 1 Ruiz + 4 Pock-Chambolle (+ 2 L2)
+    pdlp_ruiz_iterations: int = 10
+    pdlp_step_size_strategy: int = 1      # anything but 0 (fixed) means the PID primal weight
 
 
 class HighsTimer:
@@ -178,4 +182,43 @@ def solveLpCupdlp(options: HighsOptions, timer: HighsTimer, lp: HighsLp, highs_b
                         else HighsModelStatus.kTimeLimit)             # :233-236
     else:
         model_status = HighsModelStatus.kUnknown
+    return HighsStatus.kOk, model_status
+
+
+def solveLpHiPdlp(options: HighsOptions, timer: HighsTimer, lp: HighsLp, highs_basis: HighsBasis,
+                  highs_solution: HighsSolution, highs_info: HighsInfo, callback=None, **engine_params):
+    """Mirror of  HighsStatus solveLpHiPdlp(const HighsOptions&, HighsTimer&, const HighsLp&, HighsBasis&, HighsSolution&,
+    HighsModelStatus&, HighsInfo&, HighsCallback&)  (/root/reference/highs/pdlp/HiPdlpWrapper.cpp:26-141, solver=hipdlp):
+    options as PDLPSolver::setup reads them (hipdlp/pdhg.cc:1820-1863), the engine's HiPDLP mode through the C ABI
+    (b200pdlp_solve_hipdlp), status mapping of :96-127.  Returns (HighsStatus, HighsModelStatus).  The C++ twin is
+    highs_b200/csrc/highs_shim_hipdlp.cpp.  No CPU fallback."""
+    model_status = HighsModelStatus.kNotset
+    highs_info.valid = False
+    highs_info.pdlp_iteration_count = -1
+    tol = options.pdlp_optimality_tolerance
+    if options.kkt_tolerance != kDefaultKktTolerance:
+        tol = options.kkt_tolerance
+    params = dict(tolerance=tol, iter_limit=int(min(options.pdlp_iteration_limit, kHighsIInf)),
+                  time_limit=options.time_limit if options.time_limit < kHighsInf else 0.0,
+                  scaling_mode=options.pdlp_scaling_mode if (options.pdlp_features_off & kPdlpScalingOff) == 0 else 0,
+                  ruiz_iterations=options.pdlp_ruiz_iterations,
+                  step_size_strategy=0 if options.pdlp_step_size_strategy == 0 else 3,
+                  log_level=(2 if options.log_dev_level else 1) if options.output_flag else 0)
+    params.update(engine_params)
+    try:
+        res = engine.solve_hipdlp(lp, **params)
+    except engine.EngineError:
+        return HighsStatus.kError, HighsModelStatus.kUnknown
+    highs_solution.col_value, highs_solution.col_dual = res["col_value"], res["col_dual"]
+    highs_solution.row_value, highs_solution.row_dual = res["row_value"], res["row_dual"]
+    highs_info.pdlp_iteration_count = res["iters"]
+    highs_info.b200 = {k: v for k, v in res.items() if not isinstance(v, np.ndarray)}
+    highs_solution.value_valid = highs_solution.dual_valid = True
+    highs_basis.valid = False
+    if res["term_code"] == 0:
+        model_status = HighsModelStatus.kOptimal
+    elif res["term_iterate"] == 2:
+        model_status = HighsModelStatus.kTimeLimit
+    else:
+        model_status = HighsModelStatus.kIterationLimit
     return HighsStatus.kOk, model_status
