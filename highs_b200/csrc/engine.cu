@@ -1349,10 +1349,6 @@ static void solve_hipdlp_on_device(b200pdlp_problem* p, const b200pdlp_lp& lp, c
   cudaStream_t s = p->stream;
   const int n = p->n, m = p->m;
   const long long launches0 = p->launches;
-  // initializeStepSizes (pdhg.cc:1944-1977); the power method runs on the host copy of the scaled matrix for now
-  double omega = (f.norm_cost + 1.0) / (f.norm_rhs + 1.0);
-  double primal_weight = omega, best_primal_weight = omega, best_gap = std::numeric_limits<double>::infinity();
-  double err_sum = 0.0, last_err = 0.0;
   // PDLPSolver::powerMethod (pdhg.cc:1529-1671) on the device: 20 iterations of q <- A A'q / |A A'q| from the ones vector,
   // lambda = |A'q|^2; no host round trip inside (the norm stays on the device), one read-back at the end
   double op_norm_sq = 1.0;
@@ -1376,8 +1372,8 @@ static void solve_hipdlp_on_device(b200pdlp_problem* p, const b200pdlp_lp& lp, c
     CUDA_OK(cudaStreamSynchronize(s));
     op_norm_sq = p->houts[16];
   }
-  const double eta = 0.998 / std::sqrt(op_norm_sq);
-  double primal_step = eta / omega, dual_step = eta * omega;
+  HipController ctl;   // step sizes, fixed-point error, convergence test, restart criteria, PID weight (host_prep_hipdlp.cpp)
+  ctl.init(f.norm_cost, f.norm_rhs, op_norm_sq, prm.tolerance, prm.step_size_strategy);
   // x = proj_[l,u](0), y = 0; anchors = iterates; A'y (:512-552)
   {
     std::vector<double> x0(std::max(n, 1), 0.0);
@@ -1397,8 +1393,8 @@ static void solve_hipdlp_on_device(b200pdlp_problem* p, const b200pdlp_lp& lp, c
     launch_spmv_plain(s, p->AT.dev, h.y.p, h.aty.p);
     CUDA_OK(cudaStreamSynchronize(s));
   }
-  auto push_state = [&](int halpern_iteration) {
-    h.hstate->primal_step = primal_step; h.hstate->dual_step = dual_step; h.hstate->halpern_iteration = halpern_iteration;
+  auto push_state = [&]() {
+    h.hstate->primal_step = ctl.primal_step; h.hstate->dual_step = ctl.dual_step; h.hstate->halpern_iteration = ctl.halpern_iteration;
     CUDA_OK(cudaMemcpyAsync(h.state.p, h.hstate, sizeof(HipState), cudaMemcpyHostToDevice, s));
   };
   if (!h.graph) {   // steps 2 .. 40 of a block: 38 minor steps and the closing major step (:629-632)
@@ -1411,91 +1407,45 @@ static void solve_hipdlp_on_device(b200pdlp_problem* p, const b200pdlp_lp& lp, c
     CUDA_OK(cudaGraphDestroy(g));
     p->launches -= 39 * 3;   // counted when replayed
   }
-  const double tol = prm.tolerance;
-  const double tol_p = tol * (1.0 + f.norm_rhs), tol_d = tol * (1.0 + f.norm_cost);
-  double pfeas = 0.0, dfeas = 0.0, pobj = 0.0, dobj = 0.0, relgap = 0.0;
-  auto read_check = [&]() {   // checkConvergence, :1474-1527
-    pfeas = std::sqrt(p->houts[3]); dfeas = std::sqrt(p->houts[4]);
-    pobj = p->houts[5]; dobj = p->houts[6];
-    const double gap = pobj - dobj;
-    relgap = std::fabs(gap) / (1.0 + std::fabs(pobj) + std::fabs(dobj));
-    return pfeas < tol_p && dfeas < tol_d && relgap < tol;
-  };
-  auto fpe_from_outs = [&]() {   // computeFixedPointError, :733-739
-    const double movement = p->houts[0] * omega + p->houts[1] / omega;
-    const double interaction = 2.0 * eta * p->houts[2];
-    return std::sqrt(std::max(0.0, movement + interaction));
-  };
   const double t_lim = (prm.time_limit > 0 && std::isfinite(prm.time_limit)) ? prm.time_limit : 0.0;
-  int term = B200PDLP_TIMELIMIT_OR_ITERLIMIT, iters = 0, halpern_iteration = 0, restarts = 0;
-  bool converged = false, do_restart = false, timed_out = false;
-  double fpe = 0.0, fpe0 = 0.0, last_trial = std::numeric_limits<double>::infinity();
+  int term = B200PDLP_TIMELIMIT_OR_ITERLIMIT;
+  bool converged = false, timed_out = false;
   const auto t_loop = clk::now();
   hip_check(p, h.x.p, h.y.p, 0, 0);   // iteration 0 (:566-572)
   const double* sol_x = h.x.p;
   const double* sol_y = h.y.p;
-  if (read_check()) { converged = true; }
+  if (ctl.converged(p->houts)) { converged = true; }
   else {
-    while (iters < prm.iter_limit) {
+    while (ctl.iters < prm.iter_limit) {
       if (t_lim > 0 && std::chrono::duration<double>(clk::now() - t_loop).count() > t_lim) { timed_out = true; break; }
-      push_state(halpern_iteration);
+      push_state();
       hip_step(p, 1, 1);
-      if (do_restart) {   // the restart's reference fixed-point error is that of the first step after it (:600-608)
+      if (ctl.pending_restart_fpe) {   // the restart's reference fixed-point error is that of the first step after it (:600-608)
         hip_check(p, h.xn.p, h.yn.p, 1, 1);
-        fpe = fpe_from_outs(); fpe0 = fpe; do_restart = false;
+        ctl.restart_reference(p->houts);
       }
       CUDA_OK(cudaGraphLaunch(h.graph, s));
       p->launches += 39 * 3;
       hip_check(p, h.xn.p, h.yn.p, 1, 1);
-      fpe = fpe_from_outs();
-      halpern_iteration += 40;
-      iters += 40;
+      const bool restart = ctl.after_block(p->houts);
       if (prm.log_level >= 2)
-        printf("[b200pdlp hipdlp] it %8d  pobj %+.8e dobj %+.8e  pfeas %.2e dfeas %.2e  fpe %.3e  weight %.3e\n", iters,
-               p->houts[5], p->houts[6], std::sqrt(p->houts[3]), std::sqrt(p->houts[4]), fpe, primal_weight);
-      if (read_check()) { converged = true; sol_x = h.xn.p; sol_y = h.yn.p; break; }
-      // checkRestartCriteria, :901-927
-      do_restart = false;
-      if (iters == 40) do_restart = true;
-      else if (iters > 40) {
-        if (fpe <= 0.2 * fpe0) do_restart = true;
-        else if (fpe <= 0.8 * fpe0 && fpe > last_trial) do_restart = true;
-        else if (halpern_iteration >= 0.36 * iters) do_restart = true;
+        printf("[b200pdlp hipdlp] it %8d  pobj %+.8e dobj %+.8e  pfeas %.2e dfeas %.2e  fpe %.3e  weight %.3e\n", ctl.iters,
+               ctl.pobj, ctl.dobj, ctl.pfeas, ctl.dfeas, ctl.fpe, ctl.primal_weight);
+      if (ctl.pfeas < ctl.tol * (1.0 + f.norm_rhs) && ctl.dfeas < ctl.tol * (1.0 + f.norm_cost) && ctl.relgap < ctl.tol) {
+        converged = true; sol_x = h.xn.p; sol_y = h.yn.p; break;
       }
-      last_trial = fpe;
-      if (do_restart) {
-        restarts++;
-        if (prm.step_size_strategy != 0) {   // updatePrimalWeightAtRestart (PID), :1979-2050
-          const double pd = std::sqrt(p->houts[7]), dd = std::sqrt(p->houts[8]);
-          const double rel_p = pfeas / (1.0 + f.norm_rhs), rel_d = dfeas / (1.0 + f.norm_cost);
-          const double ratio = (rel_p > 0.0) ? (rel_d / rel_p) : 1e300;
-          if (pd > 1e-16 && dd > 1e-16 && pd < 1e12 && dd < 1e12 && ratio > 1e-8 && ratio < 1e8) {
-            const double error = std::log(dd) - std::log(pd) - std::log(primal_weight);
-            err_sum = 0.3 * err_sum + error;
-            const double delta = error - last_err;
-            primal_weight *= std::exp(0.99 * error + 0.01 * err_sum + 0.0 * delta);
-            last_err = error;
-          } else {
-            primal_weight = best_primal_weight; err_sum = 0.0; last_err = 0.0;
-          }
-          const double gap = (rel_p > 0.0 && rel_d > 0.0) ? std::fabs(std::log10(rel_d / rel_p)) : best_gap;
-          if (gap < best_gap) { best_gap = gap; best_primal_weight = primal_weight; }
-          const double e2 = std::sqrt(primal_step * dual_step);
-          primal_step = e2 / primal_weight;
-          dual_step = e2 * primal_weight;
-          omega = primal_weight;
-        }
+      if (restart) {   // anchors and iterates <- the PDHG iterate of the last major step (:664-688)
         CUDA_OK(cudaMemcpyAsync(h.xa.p, h.xn.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
         CUDA_OK(cudaMemcpyAsync(h.ya.p, h.yn.p, (size_t)std::max(m, 1) * sizeof(double), cudaMemcpyDeviceToDevice, s));
         CUDA_OK(cudaMemcpyAsync(h.x.p, h.xn.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
         CUDA_OK(cudaMemcpyAsync(h.y.p, h.yn.p, (size_t)std::max(m, 1) * sizeof(double), cudaMemcpyDeviceToDevice, s));
         launch_spmv_plain(s, p->AT.dev, h.y.p, h.aty.p);
         p->launches++;
-        halpern_iteration = 0;
-        last_trial = std::numeric_limits<double>::infinity();
       }
     }
   }
+  const int iters = ctl.iters, restarts = ctl.restarts;
+  const double pfeas = ctl.pfeas, dfeas = ctl.dfeas, pobj = ctl.pobj, dobj = ctl.dobj, relgap = ctl.relgap;
   if (converged) term = B200PDLP_OPTIMAL;
   const double solve_seconds = std::chrono::duration<double>(clk::now() - t_loop).count();
   // unscaleSolution + postprocess (pdhg.cc:1883-1897, :359-492): the iterate is copied out ONLY on convergence --
@@ -1878,6 +1828,22 @@ int b200pdlp_solve_multi(const b200pdlp_lp* lp, const b200pdlp_params* params, c
   for (b200pdlp_problem* p : probs)
     if (p) { cudaSetDevice(p->device); p->p2p = false; delete p; }
   return rc;
+}
+
+int b200pdlp_hipdlp_controller_replay(double norm_cost, double norm_rhs, double op_norm_sq, double tolerance, int32_t strategy,
+                                       int32_t nblocks, const double* sums, const double* restart_sums, double* out) {
+  if (nblocks < 0 || (nblocks > 0 && (!sums || !restart_sums || !out))) return B200PDLP_ERR_ARG;
+  HipController ctl;
+  ctl.init(norm_cost, norm_rhs, op_norm_sq, tolerance, strategy);
+  for (int b = 0; b < nblocks; b++) {
+    if (ctl.pending_restart_fpe) ctl.restart_reference(restart_sums + 3 * (size_t)b);
+    const bool restart = ctl.after_block(sums + 9 * (size_t)b);
+    double* o = out + 8 * (size_t)b;
+    o[0] = restart ? 1.0 : 0.0; o[1] = ctl.primal_weight; o[2] = ctl.primal_step; o[3] = ctl.dual_step; o[4] = ctl.fpe;
+    o[5] = (ctl.pfeas < ctl.tol * (1.0 + norm_rhs) && ctl.dfeas < ctl.tol * (1.0 + norm_cost) && ctl.relgap < ctl.tol) ? 1.0 : 0.0;
+    o[6] = ctl.iters; o[7] = ctl.halpern_iteration;
+  }
+  return B200PDLP_OK;
 }
 
 void b200pdlp_hipdlp_default_params(b200pdlp_hipdlp_params* p) {

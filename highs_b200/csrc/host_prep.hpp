@@ -94,6 +94,29 @@ void formulate(const b200pdlp_lp& lp, StdForm& f);
 void formulate_hipdlp(const b200pdlp_lp& lp, StdForm& f);
 void scale_hipdlp(StdForm& f, int scaling_mode, int ruiz_iterations);
 double power_method_hipdlp(const StdForm& f);
+// Host control of the HiPDLP loop between blocks of 40 Halpern steps (PDLPSolver::solve, hipdlp/pdhg.cc:494-707):
+// step sizes from the power method, fixed-point error, convergence test, restart criteria and the PID primal weight.
+// The device (or, in the CPU tests, the oracle's trace) supplies nine sums per check:
+//   s[0] |x_next - refl_x|^2  s[1] |y_next - refl_y|^2  s[2] (x_next - refl_x).A'(y_next - refl_y)
+//   s[3] |primal residual|^2  s[4] |dual residual|^2    s[5] primal objective   s[6] dual objective
+//   s[7] |x_next - x_anchor|^2  s[8] |y_next - y_anchor|^2
+struct HipController {
+  double tol = 1e-7, norm_cost = 0.0, norm_rhs = 0.0, eta = 0.0;
+  int strategy = 3;                        // 0: fixed primal weight, otherwise PID
+  double omega = 1.0, primal_weight = 1.0, best_primal_weight = 1.0, best_gap = 0.0, err_sum = 0.0, last_err = 0.0;
+  double primal_step = 0.0, dual_step = 0.0;
+  int iters = 0, halpern_iteration = 0, restarts = 0;
+  bool pending_restart_fpe = false;        // the next block's first step defines the restart's reference error
+  double fpe = 0.0, fpe0 = 0.0, last_trial = 0.0;
+  double pfeas = 0.0, dfeas = 0.0, pobj = 0.0, dobj = 0.0, relgap = 0.0;
+  void init(double norm_cost_, double norm_rhs_, double op_norm_sq, double tol_, int strategy_);   // initializeStepSizes, :1944-1977
+  double fixed_point_error(const double* s) const;                                                 // :733-739
+  bool converged(const double* s);                                                                 // checkConvergence, :1474-1527
+  void restart_reference(const double* s) { fpe = fixed_point_error(s); fpe0 = fpe; pending_restart_fpe = false; }   // :600-608
+  // after steps 2..40 of a block (s = the block-end check); returns true if the loop restarts now (anchors <- iterate),
+  // with the primal weight and the step sizes already updated
+  bool after_block(const double* s);
+};
 void build_row_index(StdForm& f);   // fills f.rptr / f.rpos (parallel counting sort)
 void scale(StdForm& f, bool do_scale);
 // nnz-balanced contiguous partition of the m rows into `world` parts

@@ -218,4 +218,76 @@ double power_method_hipdlp(const StdForm& f) {
   return lambda;
 }
 
+void HipController::init(double norm_cost_, double norm_rhs_, double op_norm_sq, double tol_, int strategy_) {
+  *this = HipController();
+  tol = tol_; norm_cost = norm_cost_; norm_rhs = norm_rhs_; strategy = strategy_;
+  omega = (norm_cost + 1.0) / (norm_rhs + 1.0);
+  primal_weight = omega;
+  best_primal_weight = primal_weight;
+  best_gap = std::numeric_limits<double>::infinity();
+  eta = 0.998 / std::sqrt(op_norm_sq);
+  primal_step = eta / omega;
+  dual_step = eta * omega;
+  last_trial = std::numeric_limits<double>::infinity();
+}
+
+double HipController::fixed_point_error(const double* s) const {
+  const double movement = s[0] * omega + s[1] / omega;
+  const double interaction = 2.0 * eta * s[2];
+  return std::sqrt(std::max(0.0, movement + interaction));
+}
+
+bool HipController::converged(const double* s) {
+  pfeas = std::sqrt(s[3]);
+  dfeas = std::sqrt(s[4]);
+  pobj = s[5];
+  dobj = s[6];
+  const double gap = pobj - dobj;
+  relgap = std::fabs(gap) / (1.0 + std::fabs(pobj) + std::fabs(dobj));
+  return pfeas < tol * (1.0 + norm_rhs) && dfeas < tol * (1.0 + norm_cost) && relgap < tol;
+}
+
+bool HipController::after_block(const double* s) {
+  fpe = fixed_point_error(s);
+  halpern_iteration += 40;
+  iters += 40;
+  if (converged(s)) return false;
+  bool restart = false;                     // checkRestartCriteria, :901-927
+  if (iters == 40) restart = true;
+  else if (iters > 40) {
+    if (fpe <= 0.2 * fpe0) restart = true;
+    else if (fpe <= 0.8 * fpe0 && fpe > last_trial) restart = true;
+    else if (halpern_iteration >= 0.36 * iters) restart = true;
+  }
+  last_trial = fpe;
+  if (!restart) return false;
+  restarts++;
+  if (strategy != 0) {                      // updatePrimalWeightAtRestart (PID controller), :1979-2050
+    const double pd = std::sqrt(s[7]), dd = std::sqrt(s[8]);
+    const double rel_p = pfeas / (1.0 + norm_rhs), rel_d = dfeas / (1.0 + norm_cost);
+    const double ratio = (rel_p > 0.0) ? (rel_d / rel_p) : 1e300;
+    if (pd > 1e-16 && dd > 1e-16 && pd < 1e12 && dd < 1e12 && ratio > 1e-8 && ratio < 1e8) {
+      const double error = std::log(dd) - std::log(pd) - std::log(primal_weight);
+      err_sum = 0.3 * err_sum + error;
+      const double delta = error - last_err;
+      primal_weight *= std::exp(0.99 * error + 0.01 * err_sum + 0.0 * delta);
+      last_err = error;
+    } else {
+      primal_weight = best_primal_weight;
+      err_sum = 0.0;
+      last_err = 0.0;
+    }
+    const double gap = (rel_p > 0.0 && rel_d > 0.0) ? std::fabs(std::log10(rel_d / rel_p)) : best_gap;
+    if (gap < best_gap) { best_gap = gap; best_primal_weight = primal_weight; }
+    const double e2 = std::sqrt(primal_step * dual_step);
+    primal_step = e2 / primal_weight;
+    dual_step = e2 * primal_weight;
+    omega = primal_weight;
+  }
+  halpern_iteration = 0;
+  last_trial = std::numeric_limits<double>::infinity();
+  pending_restart_fpe = true;
+  return true;
+}
+
 }  // namespace b200

@@ -73,7 +73,7 @@ ABI_SYMBOLS = [
     "b200pdlp_form_get_vector", "b200pdlp_form_get_csc", "b200pdlp_form_get_csr", "b200pdlp_form_get_row_map",
     "b200pdlp_form_layout_eval", "b200pdlp_p2p_link_local", "b200pdlp_solve_multi",
     "b200pdlp_hipdlp_form_create", "b200pdlp_hipdlp_power_method", "b200pdlp_hipdlp_default_params",
-    "b200pdlp_solve_hipdlp",
+    "b200pdlp_solve_hipdlp", "b200pdlp_hipdlp_controller_replay",
 ]
 
 _lib = None
@@ -209,6 +209,20 @@ def solve(lp: HighsLp, warm=None, trace_cap: int = 0, **params) -> dict:
     w, wk = _mk_warm(warm)
     _check(L.b200pdlp_solve(C.byref(clp), C.byref(prm), C.byref(w) if w else None, C.byref(res)), "b200pdlp_solve")
     return _result_dict(res, arrays)
+
+
+def hipdlp_controller_replay(norm_cost, norm_rhs, op_norm_sq, tolerance, strategy, sums, restart_sums) -> np.ndarray:
+    """Host-only: replay the HiPDLP host control over recorded per-block sums (b200pdlp_hipdlp_controller_replay)."""
+    L = lib()
+    L.b200pdlp_hipdlp_controller_replay.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32, _dp, _dp, _dp]
+    sums = np.ascontiguousarray(sums, dtype=np.float64).reshape(-1, 9)
+    rs = np.ascontiguousarray(restart_sums, dtype=np.float64).reshape(-1, 3)
+    nb = sums.shape[0]
+    out = np.zeros((max(nb, 1), 8))
+    _check(L.b200pdlp_hipdlp_controller_replay(norm_cost, norm_rhs, op_norm_sq, tolerance, strategy, nb,
+                                               _p(sums if nb else np.zeros(9), _dp), _p(rs if nb else np.zeros(3), _dp), _p(out, _dp)),
+           "b200pdlp_hipdlp_controller_replay")
+    return out[:nb]
 
 
 def solve_hipdlp(lp: HighsLp, **params) -> dict:

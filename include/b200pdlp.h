@@ -233,6 +233,14 @@ typedef struct {
 void b200pdlp_hipdlp_default_params(b200pdlp_hipdlp_params* p);
 int b200pdlp_solve_hipdlp(const b200pdlp_lp* lp, const b200pdlp_hipdlp_params* params, b200pdlp_result* out);
 
+/* host-only (no GPU; parity tests): the HOST control of the HiPDLP loop -- step sizes, fixed-point error, convergence test,
+ * restart criteria, PID primal weight (HipController, host_prep_hipdlp.cpp; hipdlp/pdhg.cc:494-707,901-927,1944-2050) --
+ * replayed over `nblocks` blocks of 40 steps from recorded sums: sums[b][9] = the nine sums of block b's closing check,
+ * restart_sums[b][3] = the three fixed-point sums of block b's first step (used when block b follows a restart);
+ * out[b][8] = restart decided, primal weight, primal step, dual step, fixed-point error, converged, iterations, halpern_iteration */
+int b200pdlp_hipdlp_controller_replay(double norm_cost, double norm_rhs, double op_norm_sq, double tolerance, int32_t strategy,
+                                       int32_t nblocks, const double* sums, const double* restart_sums, double* out);
+
 /* PDLPSolver::powerMethod (hipdlp/pdhg.cc:1529-1671): 20 iterations on A A' from the ones vector -> estimate of |A|_2^2 */
 int b200pdlp_hipdlp_power_method(const b200pdlp_form* f, double* lambda);
 

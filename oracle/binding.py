@@ -132,10 +132,11 @@ class HipResult(C.Structure):
     _fields_ = [("col_value", _dp), ("col_dual", _dp), ("row_value", _dp), ("row_dual", _dp),
                 ("term_code", C.c_int), ("iters", C.c_int), ("pfeas", C.c_double), ("dfeas", C.c_double),
                 ("pobj", C.c_double), ("dobj", C.c_double), ("relgap", C.c_double), ("primal_weight", C.c_double),
-                ("op_norm_sq", C.c_double)]
+                ("op_norm_sq", C.c_double), ("trace", _dp), ("trace_cap", C.c_int), ("trace_len", C.c_int)]
 
 
-def hipdlp_solve(lp, tolerance=1e-7, max_iterations=2147483647, scaling_mode=5, ruiz_iterations=10, step_size_strategy=3) -> dict:
+def hipdlp_solve(lp, tolerance=1e-7, max_iterations=2147483647, scaling_mode=5, ruiz_iterations=10, step_size_strategy=3,
+                 trace_cap=0) -> dict:
     """The HiPDLP restatement (oracle/hipdlp_oracle.c).  Arguments are the HighsOptions of the same names
     (pdlp_scaling_mode bits: 1 Ruiz, 2 L2, 4 PC; pdlp_step_size_strategy: 0 fixed, anything else PID)."""
     L = lib()
@@ -144,13 +145,16 @@ def hipdlp_solve(lp, tolerance=1e-7, max_iterations=2147483647, scaling_mode=5, 
     cv, cd, rv, rd = np.zeros(max(n, 1)), np.zeros(max(n, 1)), np.zeros(max(m, 1)), np.zeros(max(m, 1))
     prm = HipParams(tolerance, int(min(max_iterations, 2147483647)), int(bool(scaling_mode & 1)), int(bool(scaling_mode & 4)),
                     int(bool(scaling_mode & 2)), ruiz_iterations, 0 if step_size_strategy == 0 else 3)
-    res = HipResult(_p(cv, _dp), _p(cd, _dp), _p(rv, _dp), _p(rd, _dp), 0, 0, 0, 0, 0, 0, 0, 0, 0)
+    tr = np.zeros((max(trace_cap, 1), 20))
+    res = HipResult(_p(cv, _dp), _p(cd, _dp), _p(rv, _dp), _p(rd, _dp), 0, 0, 0, 0, 0, 0, 0, 0, 0,
+                    _p(tr, _dp) if trace_cap else None, trace_cap, 0)
     L.hip_solve.argtypes = [C.POINTER(OrcLp), C.POINTER(HipParams), C.POINTER(HipResult)]
     rc = L.hip_solve(C.byref(clp), C.byref(prm), C.byref(res))
     assert rc == 0
     return dict(col_value=cv[:n], col_dual=cd[:n], row_value=rv[:m], row_dual=rd[:m], term_code=res.term_code,
                 term_name={0: "OPTIMAL", 1: "MAXITER"}[res.term_code], iters=res.iters, pfeas=res.pfeas, dfeas=res.dfeas,
-                pobj=res.pobj, dobj=res.dobj, relgap=res.relgap, primal_weight=res.primal_weight, op_norm_sq=res.op_norm_sq)
+                pobj=res.pobj, dobj=res.dobj, relgap=res.relgap, primal_weight=res.primal_weight, op_norm_sq=res.op_norm_sq,
+                trace=tr[: res.trace_len].copy())
 
 
 class HipForm(C.Structure):

@@ -39,6 +39,7 @@ typedef struct {
   double *sp, *sn, *hslack;
   int hslack_valid, halpern_iteration;
   double pfeas, dfeas, pobj, dobj, gap, relgap;   /* results_ of the last check */
+  double sums[9];                                 /* raw sums behind the last FPE / check / PID distances (trace) */
 } hip;
 
 /* ------------------------------------------------------------------ linalg.cc */
@@ -283,6 +284,7 @@ static double fixed_point_error(const hip* s) {                        /* pdhg.c
   for (int i = 0; i < s->n; i++) cross += dx[i] * atdy[i];
   const double movement = pn * s->omega + dn / s->omega;
   const double interaction = 2.0 * s->eta * cross;
+  ((hip*)s)->sums[0] = pn; ((hip*)s)->sums[1] = dn; ((hip*)s)->sums[2] = cross;
   free(dx); free(dy); free(atdy);
   return sqrt(dmax(0.0, movement + interaction));
 }
@@ -298,6 +300,7 @@ static int check_convergence(hip* s, const double* x, const double* y, const dou
     if (!s->is_eq[i]) r[i] = dmin(0.0, r[i]);
   }
   if (s->is_scaled) for (int i = 0; i < m; i++) r[i] *= s->row_scale[i];
+  s->sums[3] = l_dot(m, r, r);
   s->pfeas = l_norm2(m, r);
   double* dres = NEW(double, n);                                         /* computeDualFeasibility, :1380-1408 */
   for (int i = 0; i < n; i++) dres[i] = s->cost[i] - aty[i];
@@ -315,6 +318,7 @@ static int check_convergence(hip* s, const double* x, const double* y, const dou
   }
   for (int i = 0; i < n; i++) r[i] = dres[i] - s->sp[i] + s->sn[i];
   if (s->is_scaled) for (int i = 0; i < n; i++) r[i] *= s->col_scale[i];
+  s->sums[4] = l_dot(n, r, r);
   s->dfeas = l_norm2(n, r);
   double pobj = s->pobj;                                                /* caller preset pobj = offset */
   for (int i = 0; i < n; i++) pobj += s->cost[i] * x[i];
@@ -324,6 +328,7 @@ static int check_convergence(hip* s, const double* x, const double* y, const dou
   for (int i = 0; i < n; i++) if (s->lower[i] > -INFINITY) dobj += s->lower[i] * s->sp[i];
   for (int i = 0; i < n; i++) if (s->upper[i] < INFINITY) dobj -= s->upper[i] * s->sn[i];
   s->dobj = dobj;
+  s->sums[5] = pobj; s->sums[6] = dobj;
   const double gap = pobj - dobj;
   s->gap = fabs(gap);
   s->relgap = fabs(gap) / (1.0 + fabs(pobj) + fabs(dobj));
@@ -367,6 +372,7 @@ static void update_primal_weight(hip* s) {                             /* pdhg.c
   double pd = 0.0, dd = 0.0;
   for (int i = 0; i < s->n; i++) { const double d = s->xn[i] - s->xa[i]; pd += d * d; }
   for (int j = 0; j < s->m; j++) { const double d = s->yn[j] - s->ya[j]; dd += d * d; }
+  s->sums[7] = pd; s->sums[8] = dd;
   pd = sqrt(pd); dd = sqrt(dd);
   const double rel_p = s->pfeas / (1.0 + s->rhs_norm), rel_d = s->dfeas / (1.0 + s->c_norm);
   const double ratio = (rel_p > 0.0) ? (rel_d / rel_p) : 1e300;
@@ -449,18 +455,37 @@ int hip_solve(const orc_lp* lp, const hip_params* prm, hip_result* out) {
   if (run_check(s, 0, lp->offset, prm->tolerance, ox, oy)) { term = HIP_OPTIMAL; }
   else {
     while (iters < prm->max_iterations) {
+      double* tr = (out->trace && out->trace_len < out->trace_cap) ? out->trace + (size_t)out->trace_len * HIP_TRACE_COLS : NULL;
+      if (tr) memset(tr, 0, sizeof(double) * HIP_TRACE_COLS);
       halpern_step(s, 1, 1);
-      if (do_restart) { fpe = fixed_point_error(s); fpe0 = fpe; do_restart = 0; }
+      if (do_restart) {
+        fpe = fixed_point_error(s); fpe0 = fpe; do_restart = 0;
+        if (tr) { tr[10] = s->sums[0]; tr[11] = s->sums[1]; tr[12] = s->sums[2]; tr[13] = 1.0; }
+      }
       for (int i = 2; i <= CHECK_INTERVAL - 1; i++) halpern_step(s, 0, i);
       halpern_step(s, 1, CHECK_INTERVAL);
       fpe = fixed_point_error(s);
       s->halpern_iteration += CHECK_INTERVAL;
       iters += CHECK_INTERVAL;
-      if (run_check(s, iters, lp->offset, prm->tolerance, ox, oy)) { term = HIP_OPTIMAL; break; }
+      const int conv = run_check(s, iters, lp->offset, prm->tolerance, ox, oy);
+      if (tr) {
+        /* the PID distances are part of the block's nine sums whether or not a restart follows */
+        double pd2 = 0.0, dd2 = 0.0;
+        for (int i = 0; i < n; i++) { const double d = s->xn[i] - s->xa[i]; pd2 += d * d; }
+        for (int j = 0; j < m; j++) { const double d = s->yn[j] - s->ya[j]; dd2 += d * d; }
+        s->sums[7] = pd2; s->sums[8] = dd2;
+        tr[0] = iters;
+        for (int q = 0; q < 9; q++) tr[1 + q] = s->sums[q];
+        tr[18] = fpe; tr[19] = conv;
+        out->trace_len++;
+      }
+      if (conv) { term = HIP_OPTIMAL; break; }
       do_restart = restart_criteria(fpe, fpe0, last_trial, s->halpern_iteration, iters);
       last_trial = fpe;
+      if (tr) tr[14] = do_restart;
       if (do_restart) {
         if (prm->step_size_strategy == 3) update_primal_weight(s);
+        if (tr) { tr[15] = s->primal_weight; tr[16] = s->primal_step; tr[17] = s->dual_step; }
         memcpy(s->xa, s->xn, sizeof(double) * (size_t)n); memcpy(s->ya, s->yn, sizeof(double) * (size_t)m);
         memcpy(s->x, s->xn, sizeof(double) * (size_t)n); memcpy(s->y, s->yn, sizeof(double) * (size_t)m);
         l_ax(s, s->x, s->ax_cache);

@@ -31,7 +31,14 @@ typedef struct {
   int term_code, iters;
   double pfeas, dfeas, pobj, dobj, relgap;               /* of the last convergence check (scaled-space objective) */
   double primal_weight, op_norm_sq;
+  /* optional trace, one row per block of 40 steps: 0 iterations, 1..9 the nine sums of the block-end check (|dx|^2, |dy|^2,
+   * cross term, |primal residual|^2, |dual residual|^2, primal objective, dual objective, |x_next - anchor|^2,
+   * |y_next - anchor|^2), 10..12 the three fixed-point sums of the step after a restart (13 = 1 when present),
+   * 14 restart decided, 15..17 primal weight / primal step / dual step after it, 18 fixed-point error, 19 converged */
+  double* trace;
+  int trace_cap, trace_len;
 } hip_result;
+#define HIP_TRACE_COLS 20
 
 int hip_solve(const orc_lp* lp, const hip_params* prm, hip_result* out);
 

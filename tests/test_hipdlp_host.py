@@ -53,3 +53,33 @@ def test_hipdlp_host_prologue_row_kinds(engine_lib, oracle):
     assert list(f["rlo"]) == [3, 0, 0, 1, -5] and list(f["rup"]) == [3, 0, 0, inf, inf]
     assert list(f["cidx"][:5]) == [0, 1, 2, 3, 4] and list(f["cval"][:5]) == [2, 3, 5, 1, -4]
     assert list(f["cidx"][5:10]) == [0, 1, 2, 3, 4]            # re-sorted by new row
+
+
+@pytest.mark.parametrize("name,kw", [("afiro", {}), ("adlittle", {}), ("sctest", dict(step_size_strategy=0)),
+                                     ("e226", dict(tolerance=1e-4)), ("25fv47", {}), ("stair", dict(scaling_mode=7, ruiz_iterations=3))])
+def test_hipdlp_host_control_replay(engine_lib, oracle, name, kw):
+    """The product's host control of the Halpern loop (HipController: fixed-point error, convergence test, restart criteria,
+    PID primal weight, step sizes) replayed over the sums the ORACLE recorded block by block must take the oracle's decisions
+    and reproduce its weights and step sizes bit for bit."""
+    from highs_b200 import engine
+    from highs_b200.lp import read_b2lp
+    lp = read_b2lp(os.path.join(GOLDEN, "instances", name + ".b2lp"))
+    prm = dict(tolerance=1e-7, scaling_mode=5, ruiz_iterations=10, step_size_strategy=3)
+    prm.update(kw)
+    ref = oracle.hipdlp_solve(lp, max_iterations=6000, trace_cap=200, **prm)
+    tr = ref["trace"]
+    assert len(tr) >= 5
+    form = oracle.hipdlp_form(lp, prm["scaling_mode"], prm["ruiz_iterations"])
+    out = engine.hipdlp_controller_replay(form["c_norm"], form["rhs_norm"], form["op_norm_sq"], prm["tolerance"],
+                                          prm["step_size_strategy"], tr[:, 1:10], tr[:, 10:13])
+    assert np.array_equal(out[:, 6], tr[:, 0])                       # iteration counts
+    assert np.array_equal(out[:, 4], tr[:, 18])                      # fixed-point errors
+    assert np.array_equal(out[:, 5], tr[:, 19])                      # convergence decisions
+    live = tr[:, 19] == 0
+    assert np.array_equal(out[live, 0], tr[live, 14])                # restart decisions
+    did = live & (tr[:, 14] == 1)
+    assert did.sum() >= 2
+    for col_out, col_tr in ((1, 15), (2, 16), (3, 17)):              # primal weight, primal / dual step after each restart
+        assert np.array_equal(out[did, col_out], tr[did, col_tr])
+    # a block that follows a restart carries the reference sums of its first step
+    assert np.array_equal(tr[1:, 13] == 1, tr[:-1, 14] == 1)
