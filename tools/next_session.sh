@@ -8,6 +8,12 @@ run() { local name=$1; shift; echo "=== $name: $*"; ( timeout "${T:-600}" "$@" )
 
 # 1. the GPU suite; -rxX lists every xfail / XPASS with its reason (logical shards, device-side setup, instance sweep)
 T=1500 run pytest_gpu python -m pytest tests -q -m gpu -rxX
+# 1b. the gated cases once more, directly, so that their details (which case, which array) land in the logs
+T=400 run child_devsetup1 python tests/device_scaling_child.py 1
+T=400 run child_devsetup2 python tests/device_scaling_child.py 2
+T=300 run child_shards2 python tests/logical_shards_child.py 2 synthetic threads
+T=300 run child_shards_c python tests/logical_shards_child.py 2 synthetic c_entry
+T=700 run child_hipdlp python tests/hipdlp_child.py
 # 2. where a short solve's time goes (setup / solve phases / teardown laps on stderr)
 B200PDLP_TIMING=1 run bench_default python bench.py
 # 3. device-side prologue: scaling only, scaling + sliced-ELL fill
