@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# First GPU call of the next round (one B200):  gpurun --timeout 1800 -- 'bash tools/next_session.sh'
+# First GPU call of the next round (one B200):  gpurun --timeout 3000 -- 'bash tools/next_session.sh'   (about 25-35 GPU-minutes)
 # Runs everything that was written after round 1's GPU budget was spent and collects the evidence in gpurun_out/.
 # Every step has its own timeout; a failing step does not stop the others.
 set -u
