@@ -156,6 +156,20 @@ def run_reference_arm(args, rank, world):
         path = os.path.join(td, "lp.b2lp")
         write_b2lp(path, lp)
         ref = reference_rate(path, iters)
+        hip = None
+        if ref is not None:
+            # second CPU baseline: the reference's other first-order engine, solver=hipdlp (40-step blocks)
+            try:
+                from oracle import binding as ob
+                runs = []
+                for lim in (40, 40 + 40 * max(1, min(iters, 120) // 40)):
+                    r = ob.run_reference(lp_path=path, options={"solver": "hipdlp", "pdlp_iteration_limit": lim})
+                    runs.append((r["pdlp_iteration_count"], r["run_seconds"]))
+                (ia, ta), (ib, tb) = runs
+                hip = {"value": (ib - ia) / max(tb - ta, 1e-9), "unit": "iter/s", "cores": 1, "kind": "reference",
+                       "sample": f"HiGHS CPU hipdlp, {ib - ia} steady-state iterations (two-point fit)"}
+            except Exception as e:   # noqa: BLE001 -- the extra baseline must never break the line
+                hip = {"unavailable": str(e)[:200]}
         tts = None
         if ref is not None and args.to_tolerance > 0:
             from oracle import binding as ob
@@ -188,6 +202,8 @@ def run_reference_arm(args, rank, world):
     }
     if tts is not None:
         line["time_to_solution"] = tts
+    if hip is not None:
+        line["cpu_baseline_hipdlp"] = hip
     print(json.dumps(line))
 
 
