@@ -1,7 +1,8 @@
 """Every LP the reference ships for its own tests (check/instances/*.mps, read by the unmodified reference through
 oracle/_ref/ref_driver) through the product's host prologue -- formulate + Ruiz/Pock-Chambolle scaling + transposition,
 bit for bit against the oracle -- and through the device layouts of 1 and 3 ranks, evaluated on the host; and the
-oracle itself against the live reference on each of them (three option sets -- 400 iterations, 240 without restarts, to 1e-3 -- iteration count and solution vectors, bit for bit).
+oracle itself against the live reference on each of them (three option sets -- 400 iterations, 240 without restarts, to 1e-3 -- and a hot start from the reference's own 1e-3
+solution: iteration count and solution vectors, bit for bit).
 Needs /root/reference and oracle/_ref (development container only); about 20 s."""
 import json
 import os
@@ -21,4 +22,4 @@ def test_reference_instances_through_host_prologue():
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert lines, (r.stdout[-1500:], r.stderr[-1500:])
     out = json.loads(lines[-1])
-    assert out["ok"] >= 60 and out["oracle_pinned_on"] >= 60 and not out["bad"], out
+    assert out["ok"] >= 60 and out["oracle_pinned_on"] >= 60 and out["hot_start_pinned_on"] >= 50 and not out["bad"], out

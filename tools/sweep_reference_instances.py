@@ -13,7 +13,7 @@ from oracle import binding as ob
 KEYS = ["cost", "lower", "upper", "rhs", "col_scale", "row_scale", "cbeg", "cidx", "cval", "row_new_idx", "row_type", "rbeg", "ridx", "rval"]
 drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
 tmp = __import__("tempfile").mkdtemp(prefix="b200inst_")
-bad = []; n_ok = 0; n_pinned = 0
+bad = []; n_ok = 0; n_pinned = 0; n_hot = 0
 for mps in sorted(glob.glob("/root/reference/check/instances/*.mps")):
     name = os.path.basename(mps)[:-4]
     out = f"{tmp}/{name}.b2lp"
@@ -51,10 +51,30 @@ for mps in sorted(glob.glob("/root/reference/check/instances/*.mps")):
                 o = ob.solve(lp, **prm)
                 if ref["pdlp_iteration_count"] != o["iters"] or not all(np.array_equal(ref[k], o[k]) for k in ("col_value", "col_dual", "row_value", "row_dual")):
                     diffs.append(f"oracle vs reference {opts}: {ref['pdlp_iteration_count']} / {o['iters']} iterations")
+            # hot start (PDHG_PreSolve, cupdlp_solver.c:1217-1279): restart both from the reference's own 1e-3 solution
+            # (Highs::setSolution recomputes the row activities of a user solution in quad precision before the wrapper sees
+            #  them -- Highs.cpp:2519-2530, calculateRowValuesQuad, HighsLpUtils.cpp:3011-3047 -- and ranged rows start
+            #  their slack from them, so the oracle is given the exactly rounded A x as well)
+            if lp.a_matrix_.numNz() <= 20000:
+                from fractions import Fraction
+                w = ob.run_reference(lp=lp, options={"pdlp_iteration_limit": 1200, "kkt_tolerance": 1e-3}, want_solution=True)
+                accq = [Fraction(0)] * lp.num_row_
+                Am = lp.a_matrix_
+                for jc in range(lp.num_col_):
+                    xj = Fraction(float(w["col_value"][jc]))
+                    for pe in range(Am.start_[jc], Am.start_[jc + 1]):
+                        accq[Am.index_[pe]] += xj * Fraction(float(Am.value_[pe]))
+                rvq = np.array([float(a_) for a_ in accq])
+                ref = ob.run_reference(lp=lp, options={"pdlp_iteration_limit": 200}, want_solution=True,
+                                       warm=(w["col_value"], w["col_dual"], w["row_value"], w["row_dual"]))
+                o = ob.solve(lp, iter_limit=200, warm=(w["col_value"], rvq, w["row_dual"]))
+                if ref["pdlp_iteration_count"] != o["iters"] or not all(np.array_equal(ref[k], o[k]) for k in ("col_value", "col_dual", "row_value", "row_dual")):
+                    diffs.append(f"oracle vs reference, hot start: {ref['pdlp_iteration_count']} / {o['iters']} iterations")
+                n_hot += 1
             n_pinned += 1
         if diffs: bad.append((name, diffs)); print(name, "DIFF", diffs)
         else: n_ok += 1
     except Exception as e:
         bad.append((name, repr(e))); print(name, "EXC", repr(e)[:200])
 import json
-print(json.dumps({"ok": n_ok, "oracle_pinned_on": n_pinned, "bad": [[k, str(v)] for k, v in bad]}))
+print(json.dumps({"ok": n_ok, "oracle_pinned_on": n_pinned, "hot_start_pinned_on": n_hot, "bad": [[k, str(v)] for k, v in bad]}))
