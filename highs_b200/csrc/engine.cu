@@ -22,6 +22,7 @@
 #include <thread>
 #include <vector>
 
+#include "device_prep.hpp"
 #include "host_prep.hpp"
 #include "pdhg_kernels.hpp"
 #include "setup_kernels.hpp"
@@ -89,6 +90,9 @@ static NcclApi& nccl() {
   return a;
 }
 
+// Device buffer; the memory comes from (and returns to) the process-wide block cache of device_prep.cu, so the ~60
+// allocations of a solve cost nothing after the first solve of a process (cudaMalloc / cudaFree are milliseconds each
+// at these sizes, and cudaFree synchronises the device).
 template <class T>
 struct DevBuf {
   T* p = nullptr;
@@ -96,12 +100,18 @@ struct DevBuf {
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  ~DevBuf() { if (p) cudaFree(p); }
+  ~DevBuf() { if (p) dev_cache_free(p); }
   void alloc(size_t count, bool zero = true) {
-    if (p) { cudaFree(p); p = nullptr; }
+    if (p) { dev_cache_free(p); p = nullptr; }
     n = count;
-    CUDA_OK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    try { p = static_cast<T*>(dev_cache_alloc(std::max<size_t>(count, 1) * sizeof(T))); }
+    catch (const std::exception& e) { throw Error(B200PDLP_ERR_ALLOC, e.what()); }
     if (zero) CUDA_OK(cudaMemset(p, 0, std::max<size_t>(count, 1) * sizeof(T)));
+  }
+  // take over a block that came from dev_cache_alloc
+  void adopt(T* ptr, size_t count) {
+    if (p) dev_cache_free(p);
+    p = ptr; n = count;
   }
   void upload(const T* src, size_t count) {
     if (count) CUDA_OK(cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
@@ -205,7 +215,7 @@ struct b200pdlp_problem {
     DevBuf<HipState> state;
     HipState* hstate = nullptr;    // pinned
     cudaGraphExec_t graph = nullptr;
-    ~HipBuffers() { if (graph) cudaGraphExecDestroy(graph); if (hstate) cudaFreeHost(hstate); }
+    ~HipBuffers() { if (graph) cudaGraphExecDestroy(graph); if (hstate) pinned_cache_free(hstate); }
   } hip;
   bool local_link = false;         // peers are problems of this process (logical shards, b200pdlp_p2p_link_local)
   bool p2p = false;
@@ -230,17 +240,37 @@ struct b200pdlp_problem {
   ncclComm_t comm = nullptr;
   cudaGraphExec_t graph_main = nullptr, graph_small = nullptr;
   int graph_main_passes = 0, graph_small_passes = 0;
+  // device-side check iterations (tree mode, one GPU): control block, its pinned mirror, the time-limit word the
+  // device reads from mapped host memory, graphs of 4/8/16/32 passes (captured on demand) and of the check sequence
+  // device-resident prologue (device_prep.cu): the standard form never exists on the host; the index maps of the
+  // formulation and the device orderings stay in HBM, the host keeps scalars only
+  bool dev_form = false;
+  DevicePrologue prep;
+  double beta_cost_sq = 0.0, beta_rhs_sq = 0.0;   // |c|^2, |b|^2 of the scaled data (tree sums)
+  DevBuf<double> io_col, io_row;   // staging of the hot start / the returned solution (original order)
+  DevBuf<SolveCtl> ctl;
+  SolveCtl* hctl = nullptr;        // pinned
+  int* htime = nullptr;            // pinned + mapped
+  DevBuf<double> trace_dev;
+  cudaGraphExec_t graph_pow2[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // 1 << k passes
+  cudaGraphExec_t graph_check = nullptr;
   long long launches = 0;
   int kernels_per_pass = 4;
 
   ~b200pdlp_problem() {
+    if (stream) cudaStreamSynchronize(stream);   // the buffers go back to the block cache: nothing may still use them
+    if (dev_form) { prep.release_arrays(); prep.release_form(); }
     if (graph_main) cudaGraphExecDestroy(graph_main);
     if (graph_small) cudaGraphExecDestroy(graph_small);
+    for (cudaGraphExec_t g : graph_pow2) if (g) cudaGraphExecDestroy(g);
+    if (graph_check) cudaGraphExecDestroy(graph_check);
+    if (hctl) pinned_cache_free(hctl);
+    if (htime) pinned_cache_free(htime);
     for (void* q : ipc_opened) cudaIpcCloseMemHandle(q);
     if (comm) NcclApi::get().CommDestroy(comm);
-    if (hstate) cudaFreeHost(hstate);
-    if (houts) cudaFreeHost(houts);
-    if (hflag) cudaFreeHost(hflag);
+    if (hstate) pinned_cache_free(hstate);
+    if (houts) pinned_cache_free(houts);
+    if (hflag) pinned_cache_free(hflag);
     if (stream) cudaStreamDestroy(stream);
   }
   ReduceScratch rs(int slot, int len) const {
@@ -368,6 +398,12 @@ struct DeviceSetup {
   }
 };
 
+static void alloc_host_mirrors(b200pdlp_problem* p) {
+  p->hstate = static_cast<PdhgState*>(pinned_cache_alloc(sizeof(PdhgState), false));
+  p->houts = static_cast<double*>(pinned_cache_alloc(kOutsCount * sizeof(double), false));
+  p->hflag = static_cast<double*>(pinned_cache_alloc(4 * sizeof(double), false));   // [0] time-limit flag, [2] read-back of the barrier fault word
+}
+
 // shared_form != nullptr: the standard form was formulated and scaled already (by another rank of this process)
 static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, int rank, int world, b200pdlp_problem* p,
                            const StdForm* shared_form = nullptr) {
@@ -475,13 +511,133 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   p->terms.alloc(p->ordered ? (size_t)kNumSlots * 16 * p->ordered_cap : 1);
   p->outs.alloc(kOutsCount);
   p->state.alloc(1);
-  CUDA_OK(cudaMallocHost(&p->hstate, sizeof(PdhgState)));
-  CUDA_OK(cudaMallocHost(&p->houts, kOutsCount * sizeof(double)));
-  CUDA_OK(cudaMallocHost(&p->hflag, 4 * sizeof(double)));   // [0] time-limit flag, [2] read-back of the barrier fault word
+  alloc_host_mirrors(p);   // [0] time-limit flag, [2] read-back of the barrier fault word
   memset(p->hflag, 0, 4 * sizeof(double));
   memset(p->hstate, 0, sizeof(PdhgState));
   CUDA_OK(cudaDeviceSynchronize());
   lap("vectors + scratch");
+}
+
+// One GPU, tree mode: the whole prologue on the device (device_prep.cu).  B200PDLP_DEVICE_PREP=0 keeps the host
+// prologue (its tested twin); ordered mode (small problems, bit-identical trajectories) and several GPUs always do.
+static bool use_device_prep(const b200pdlp_lp& lp, const b200pdlp_params& prm, int world) {
+  if (world != 1) return false;
+  if (const char* e = getenv("B200PDLP_DEVICE_PREP")) { if (atoi(e) == 0) return false; }
+  else if (prm.device_scaling != 0) return false;   // -1: host prologue; 1, 2: the staged variants of create_problem
+  if (getenv("B200PDLP_DEVICE_SETUP")) return false;        // the round-1 staged variants (host formulate + device scaling)
+  const int omax = prm.ordered_max == 0 ? 4096 : prm.ordered_max;
+  // ordered mode is decided on the standard form's size: n = num_col + (#BOUND rows) <= num_col + num_row
+  if (omax > 0 && std::max(lp.num_col + lp.num_row, lp.num_row) <= omax) return false;
+  if (lp.num_col <= 0 || lp.num_row <= 0 || lp.a_start[lp.num_col] <= 0) return false;
+  return true;
+}
+
+static void create_problem_device(const b200pdlp_lp& lp, const b200pdlp_params& prm, b200pdlp_problem* p) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    throw Error(B200PDLP_ERR_CUDA, std::string("no CUDA device: the B200 engine has no CPU fallback (") + cudaGetErrorString(e) + ")");
+  if (prm.device >= 0) p->device = prm.device; else CUDA_OK(cudaGetDevice(&p->device));
+  set_device(p);
+  p->rank = 0; p->world = 1;
+  Laps lap;
+  CUDA_OK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  cudaStream_t s = p->stream;
+  p->dev_form = true;
+  if (getenv("B200PDLP_KEEP_FORM")) p->prep.keep_form = true;
+  try {
+    p->prep.run(s, lp, prm.scaling != 0, /*long_threshold=*/512);
+  } catch (const std::invalid_argument& ex) {
+    throw Error(B200PDLP_ERR_ARG, ex.what());
+  } catch (const std::runtime_error& ex) {
+    throw Error(B200PDLP_ERR_CUDA, ex.what());
+  }
+  lap("setup", "device prologue");
+  DevicePrologue& P = p->prep;
+  StdForm& f = p->form;
+  f = StdForm();
+  f.n = P.arr.n; f.m = P.arr.m; f.nnz = P.arr.nnz; f.neq = P.arr.neq; f.n_orig = P.arr.n0;
+  f.sense = lp.sense; f.offset = lp.offset;
+  f.norm_cost = std::sqrt(P.sc.norm_cost_sq); f.norm_rhs = std::sqrt(P.sc.norm_rhs_sq);
+  f.amax = P.sc.amax;
+  p->beta_cost_sq = P.sc.beta_cost_sq; p->beta_rhs_sq = P.sc.beta_rhs_sq;
+  const int n = f.n, m = f.m;
+  p->n = n; p->m = m; p->ml = m; p->r0 = 0; p->r1 = m; p->neq_local = f.neq; p->ordered = false;
+  p->row_bounds = {0, m};
+  p->nl = p->nl_real = n; p->c0 = 0; p->shard_len = n; p->seg_len = n;
+  p->device_filled = true;
+  p->csr_local.nrows = m; p->csr_local.ncols = n; p->csr_local.nnz = f.nnz;   // dimensions only (built on demand)
+  auto adopt_matrix = [&](DeviceMatrix& M, DevSellOwned& O) {
+    M.slices.adopt(O.slices, O.nslices); M.col.adopt(O.col, (size_t)O.padded + 32); M.val.adopt(O.val, (size_t)O.padded + 32);
+    M.segs.adopt(O.segs, O.nsegs); M.long_rows.adopt(O.long_rows, O.nlong); M.lcol.adopt(O.lcol, (size_t)O.lcount);
+    M.lval.adopt(O.lval, (size_t)O.lcount); M.long_partial.adopt(O.long_partial, O.nsegs);
+    M.long_counter.adopt(O.long_counter, O.nlong);
+    M.host.nrows = O.nrows; M.host.ncols = O.ncols; M.host.padded = O.padded; M.host.lcount = O.lcount; M.host.n_partials = O.nsegs;
+    M.dev.nrows = O.nrows; M.dev.nslices = O.nslices;
+    M.dev.nblocks_body = (O.nslices + kThreads / 32 - 1) / (kThreads / 32);
+    M.dev.nsegs = O.nsegs;
+    M.dev.slices = M.slices.p; M.dev.col = M.col.p; M.dev.val = M.val.p; M.dev.segs = M.segs.p; M.dev.long_rows = M.long_rows.p;
+    M.dev.lcol = M.lcol.p; M.dev.lval = M.lval.p; M.dev.long_partial = M.long_partial.p; M.dev.long_counter = M.long_counter.p;
+    M.dev.padded_total = (int)O.padded; M.dev.prefetch_dist = 0;
+    O = DevSellOwned();   // ownership moved
+  };
+  adopt_matrix(p->A, P.A);
+  adopt_matrix(p->AT, P.AT);
+  p->cost.adopt(P.arr.cost, n); p->lower.adopt(P.arr.lower, n); p->upper.adopt(P.arr.upper, n); p->colscale.adopt(P.arr.colscale, n);
+  p->rhs.adopt(P.arr.rhs, m); p->rowscale.adopt(P.arr.rowscale, m);
+  P.arr.cost = P.arr.lower = P.arr.upper = P.arr.colscale = P.arr.rhs = P.arr.rowscale = nullptr;
+  if (const char* ev = getenv("B200PDLP_PDL")) { const int v = atoi(ev); p->pass_flags = v >= 2 ? 6 : (v == 1 ? 2 : 0); }
+  if (const char* ev = getenv("B200PDLP_PREFETCH")) { p->A.dev.prefetch_dist = atoi(ev); p->AT.dev.prefetch_dist = atoi(ev); }
+  // iterates and scratch: uninitialised (the solve's initial-point kernels write every entry they read)
+  for (int k = 0; k < 2; k++) { p->x[k].alloc(n, false); p->aty[k].alloc(n, false); p->y[k].alloc(m, false); p->ax[k].alloc(m, false); }
+  p->xsum.alloc(n, false); p->xavg.alloc(n, false); p->atyavg.alloc(n, false); p->xlr.alloc(n, false);
+  p->ysum.alloc(m, false); p->yavg.alloc(m, false); p->axavg.alloc(m, false); p->ylr.alloc(m, false);
+  p->io_col.alloc((size_t)2 * std::max(f.n_orig, 1), false);
+  p->io_row.alloc((size_t)2 * std::max(m, 1), false);
+  size_t maxgrid = std::max<size_t>(kMaxEwBlocks, std::max(p->A.grid(), p->AT.grid()));
+  p->scratch_stride = 24 * maxgrid;
+  p->partials.alloc(p->scratch_stride * kNumSlots, false);
+  p->counters.alloc(kNumSlots, false);
+  CUDA_OK(cudaMemsetAsync(p->counters.p, 0, kNumSlots * sizeof(unsigned), s));
+  p->ordered_cap = 0;
+  p->terms.alloc(1, false);
+  p->outs.alloc(kOutsCount, false);
+  p->state.alloc(1, false);
+  p->redbuf.alloc(16, false);
+  alloc_host_mirrors(p);
+  memset(p->hflag, 0, 4 * sizeof(double));
+  memset(p->hstate, 0, sizeof(PdhgState));
+  lap("setup", "vectors + scratch");
+}
+
+// host copies of what the device prologue keeps in HBM, fetched when a test accessor needs them
+static void ensure_host_maps(b200pdlp_problem* p) {
+  if (!p->dev_form || !p->rperm.empty() || p->m == 0) return;
+  const DevProblemArrays& a = p->prep.arr;
+  p->rperm.resize(p->m); p->rinv.resize(p->m); p->cperm.resize(p->n); p->cinv.resize(p->n);
+  p->form.row_new_idx.resize(p->m); p->form.row_class.resize(p->m);
+  CUDA_OK(cudaMemcpy(p->rperm.data(), a.rperm, (size_t)p->m * sizeof(int), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(p->rinv.data(), a.rinv, (size_t)p->m * sizeof(int), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(p->cperm.data(), a.cperm, (size_t)p->n * sizeof(int), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(p->cinv.data(), a.cinv, (size_t)p->n * sizeof(int), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(p->form.row_new_idx.data(), a.row_new_idx, (size_t)p->m * sizeof(int), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(p->form.row_class.data(), a.row_class, (size_t)p->m * sizeof(int), cudaMemcpyDeviceToHost));
+}
+
+// the scaled standard form itself (tests: b200pdlp_problem_get_vector / get_csr), when the prologue kept it
+static void ensure_host_form(b200pdlp_problem* p) {
+  if (!p->dev_form || !p->form.cbeg.empty()) return;
+  const DevStdForm& d = p->prep.form;
+  if (!d.cbeg) throw Error(B200PDLP_ERR_STATE, "the standard form was not kept on the device (one-shot solve)");
+  StdForm& f = p->form;
+  const int n = f.n, m = f.m, nnz = f.nnz;
+  f.cbeg.resize(n + 1); f.cidx.resize(nnz); f.cval.resize(nnz);
+  f.cost.resize(n); f.lower.resize(n); f.upper.resize(n); f.col_scale.resize(n); f.rhs.resize(m); f.row_scale.resize(m);
+  auto dn = [&](void* h, const void* dv, size_t bytes) { if (bytes) CUDA_OK(cudaMemcpy(h, dv, bytes, cudaMemcpyDeviceToHost)); };
+  dn(f.cbeg.data(), d.cbeg, (size_t)(n + 1) * 4); dn(f.cidx.data(), d.cidx, (size_t)nnz * 4); dn(f.cval.data(), d.cval, (size_t)nnz * 8);
+  dn(f.cost.data(), d.cost, (size_t)n * 8); dn(f.lower.data(), d.lower, (size_t)n * 8); dn(f.upper.data(), d.upper, (size_t)n * 8);
+  dn(f.col_scale.data(), d.colscale, (size_t)n * 8); dn(f.rhs.data(), d.rhs, (size_t)m * 8); dn(f.row_scale.data(), d.rowscale, (size_t)m * 8);
+  ensure_host_maps(p);
 }
 
 // ------------------------------------------------------------------ PDHG passes
@@ -921,6 +1077,73 @@ static void trace_row(b200pdlp_result* out, const PdhgState* h, const CheckResul
   out->trace_len++;
 }
 
+// ---------------------------------------------------------------- device-side check iterations (tree mode, one GPU)
+static bool use_device_checks(const b200pdlp_problem* p, const b200pdlp_params& prm) {
+  if (p->ordered || p->world != 1 || prm.log_level >= 2 || prm.iter_limit <= 0) return false;
+  if (const char* e = getenv("B200PDLP_HOST_CHECK")) if (atoi(e) != 0) return false;   // the round-1 host-driven checks
+  return true;
+}
+
+// the six launches of one check (pdhg_kernels.cu "device-side check iteration"); no-ops unless the check is due
+static void enqueue_check_device(b200pdlp_problem* p) {
+  cudaStream_t s = p->stream;
+  PdhgState* st = p->state.p;
+  SolveCtl* ctl = p->ctl.p;
+  const int n = p->n, ml = p->ml;
+  const ReduceScratch rrow = p->rs(kSlotChk, ml), rcol = p->rs(kSlotK3, n), rrst = p->rs(kSlotK1, n);
+  launch_check_avg_x(s, n, p->x[0].p, p->x[1].p, p->xsum.p, p->xavg.p, st, ctl);
+  launch_spmv_check_rows(s, p->A.dev, st, ctl, p->xavg.p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->ysum.p,
+                         p->yavg.p, p->axavg.p, p->rhs.p, p->rowscale.p, p->neq_local, rrow);
+  launch_spmv_check_cols(s, p->AT.dev, st, ctl, p->yavg.p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->xavg.p,
+                         p->atyavg.p, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, rcol);
+  launch_check_decide(s, st, ctl, rrow.partials, p->A.grid(), rcol.partials, p->AT.grid());
+  launch_restart_sweep(s, n, ml, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->xavg.p, p->atyavg.p, p->xsum.p,
+                       p->xlr.p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->yavg.p, p->axavg.p, p->ysum.p, p->ylr.p,
+                       st, ctl, rrst);
+  launch_check_finish(s, st, ctl, rrst.partials, restart_sweep_grid(n, ml));
+}
+static constexpr int kCheckLaunches = 6;
+
+static void launch_check_graph(b200pdlp_problem* p) {
+  if (!p->graph_check) {
+    cudaGraph_t g = nullptr;
+    CUDA_OK(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+    enqueue_check_device(p);
+    CUDA_OK(cudaStreamEndCapture(p->stream, &g));
+    CUDA_OK(cudaGraphInstantiate(&p->graph_check, g, 0));
+    CUDA_OK(cudaGraphDestroy(g));
+  }
+  CUDA_OK(cudaGraphLaunch(p->graph_check, p->stream));
+  p->launches += kCheckLaunches;
+}
+
+// `d` PDHG passes: the main graph (one check interval + spare passes) when d is about an interval, otherwise graphs of
+// 32/16/8/4 passes and single passes.  Kernels beyond the check iteration are no-ops.
+static void enqueue_passes_device(b200pdlp_problem* p, int d) {
+  if (d <= 0) return;
+  const int kp = p->kernels_per_pass;
+  if (d > p->graph_main_passes - 12 && !p->graph_main) p->graph_main = capture_passes(p, p->graph_main_passes);
+  if (d > p->graph_main_passes - 12 && d <= p->graph_main_passes) {
+    CUDA_OK(cudaGraphLaunch(p->graph_main, p->stream));
+    p->launches += (long long)p->graph_main_passes * kp;
+    return;
+  }
+  while (d > p->graph_main_passes) {
+    CUDA_OK(cudaGraphLaunch(p->graph_main, p->stream));
+    p->launches += (long long)p->graph_main_passes * kp;
+    d -= p->graph_main_passes;
+  }
+  for (int k = 5; k >= 2; k--) {
+    while (d >= (1 << k)) {
+      if (!p->graph_pow2[k]) p->graph_pow2[k] = capture_passes(p, 1 << k);
+      CUDA_OK(cudaGraphLaunch(p->graph_pow2[k], p->stream));
+      p->launches += (long long)(1 << k) * kp;
+      d -= 1 << k;
+    }
+  }
+  for (; d > 0; d--) { enqueue_pass(p); p->launches += kp; }
+}
+
 static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, const b200pdlp_warm* warm, b200pdlp_result* out) {
   using clk = std::chrono::steady_clock;
   set_device(p);
@@ -929,7 +1152,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   cudaStream_t s = p->stream;
   const int n = p->n, m = p->m, ml = p->ml;
   const int interval = prm.check_interval > 0 ? prm.check_interval : 40;
-  const double t_lim = (prm.time_limit > 0 && std::isfinite(prm.time_limit)) ? prm.time_limit : 0.0;
+  const double t_lim = (prm.time_limit >= 0 && std::isfinite(prm.time_limit)) ? prm.time_limit : -1.0;   // < 0: none
   const long long launches0 = p->launches;
   PdhgState* h = p->hstate;
   memset(h, 0, sizeof(PdhgState));
@@ -938,8 +1161,9 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   Laps lap;
 
   // ---- initial point: PDHG_PreSolve (hot start, cupdlp_solver.c:1217-1279) + PDHG_Init_Variables (:531-591)
-  std::vector<double> x0(n, 0.0), y0(m, 0.0);
-  if (warm && warm->col_value && warm->row_value && warm->row_dual) {
+  const bool dev_form = p->dev_form;
+  std::vector<double> x0(dev_form ? 0 : n, 0.0), y0(dev_form ? 0 : m, 0.0);
+  if (!dev_form && warm && warm->col_value && warm->row_value && warm->row_dual) {
     int jc = 0;
     for (; jc < f.n_orig; jc++) x0[jc] = warm->col_value[jc];
     for (int i = 0; i < m; i++) {
@@ -950,7 +1174,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
     for (int j = 0; j < n; j++) x0[j] *= f.col_scale[j];
     for (int i = 0; i < m; i++) y0[i] *= f.row_scale[i];
   }
-  for (int j = 0; j < n; j++) {  // PDHG_Project_Bounds: upper first, then lower
+  for (int j = 0; j < (dev_form ? 0 : n); j++) {  // PDHG_Project_Bounds: upper first, then lower
     double v = x0[j];
     v = v < f.upper[j] ? v : f.upper[j];
     v = v > f.lower[j] ? v : f.lower[j];
@@ -972,7 +1196,19 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
     if (p->p2p) CUDA_OK(cudaMemsetAsync(p->fault.p, 0, sizeof(int), s));
     if (p->p2p) { launch_p2p_exchange(s, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p); p->launches++; }
   }
-  {
+  if (dev_form) {
+    // maps and scales live in HBM: the hot start goes up in original order and is permuted / scaled / projected there
+    const double *wc = nullptr, *wv = nullptr, *wd = nullptr;
+    if (warm && warm->col_value && warm->row_value && warm->row_dual) {
+      CUDA_OK(cudaMemcpyAsync(p->io_col.p, warm->col_value, (size_t)f.n_orig * sizeof(double), cudaMemcpyHostToDevice, s));
+      CUDA_OK(cudaMemcpyAsync(p->io_row.p, warm->row_value, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, s));
+      CUDA_OK(cudaMemcpyAsync(p->io_row.p + m, warm->row_dual, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, s));
+      wc = p->io_col.p; wv = p->io_row.p; wd = p->io_row.p + m;
+    }
+    launch_init_point(s, p->prep.arr, f.sense, wc, wv, wd, p->colscale.p, p->lower.p, p->upper.p, p->rowscale.p, p->x[0].p,
+                      p->xsum.p, p->y[0].p);
+    p->launches += 2;
+  } else {
     std::vector<double> xp(std::max(nl, 1), 0.0), yp(std::max(ml, 1));
     for (int i = 0; i < p->nl_real; i++) xp[i] = x0[p->cperm[p->c0 + i]];
     for (int i = 0; i < ml; i++) yp[i] = y0[p->r0 + p->rperm[i]];
@@ -984,8 +1220,11 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   // ---- PDHG_Init_Step_Sizes (cupdlp_step.c:312-375)
   {
     double a = 0.0, b = 0.0;   // cupdlp_twoNormSquared = dot(x,x), sequential on the reference's CPU path
-    for (int j = 0; j < n; j++) a += f.cost[j] * f.cost[j];
-    for (int i = 0; i < m; i++) b += f.rhs[i] * f.rhs[i];
+    if (dev_form) { a = p->beta_cost_sq; b = p->beta_rhs_sq; }   // tree sums from the device prologue
+    else {
+      for (int j = 0; j < n; j++) a += f.cost[j] * f.cost[j];
+      for (int i = 0; i < m; i++) b += f.rhs[i] * f.rhs[i];
+    }
     h->beta = std::fmin(a, b) > 1e-6 ? a / b : 1.0;
     if (h->adaptive) {
       h->tau = (1.0 / f.amax) / std::sqrt(h->beta);
@@ -1001,7 +1240,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   full_ax(p, p->x[0].p, p->ax[0].p);
   full_aty(p, p->y[0].p, p->aty[0].p);
   // sums start at proj(0) like PDHG_Init_Variables :577-583; the average is recomputed at every check
-  {
+  if (!dev_form) {
     std::vector<double> z(std::max(nl, 1), 0.0);
     bool nz = false;
     for (int i = 0; i < p->nl_real; i++) {
@@ -1029,12 +1268,13 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   // a few spare passes per replay: a rejected line-search step then still reaches the next check iteration inside
   // the same replay (spare passes are no-ops once state.iter == state.stop_iter) instead of costing a host round trip
   const int want_main = std::min(prm.graph_passes > 0 ? prm.graph_passes : interval + 4, kPowTab - 16);   // the step-rule tables cover one replay
-  if (!p->graph_main || p->graph_main_passes != want_main) {
-    if (p->graph_main) cudaGraphExecDestroy(p->graph_main);
-    p->graph_main = capture_passes(p, want_main);
-    p->graph_main_passes = want_main;
+  const bool dev_checks = use_device_checks(p, prm);
+  if (p->graph_main && p->graph_main_passes != want_main) { cudaGraphExecDestroy(p->graph_main); p->graph_main = nullptr; }
+  p->graph_main_passes = want_main;
+  if (!dev_checks) {   // (the device-driven loop captures the graphs it needs when it first needs them)
+    if (!p->graph_main) p->graph_main = capture_passes(p, want_main);
+    if (!p->graph_small) { p->graph_small_passes = 4; p->graph_small = capture_passes(p, 4); }
   }
-  if (!p->graph_small) { p->graph_small_passes = 4; p->graph_small = capture_passes(p, 4); }
   p->kernels_per_pass = p->world == 1 ? 4 : ((p->p2p && p->p2p_pull) ? 5 : 6);   // ours; NCCL kernels not counted
   lap("solve", "graph capture");
 
@@ -1050,10 +1290,110 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   CUDA_OK(cudaEventRecord(evl0, s));
   const auto t_loop = clk::now();
 
+  if (dev_checks) {
+    // ---- device-driven loop: the checks decide on the device (termination, restarts, next check iteration); the host
+    // enqueues [check, passes to the next check] rounds ahead from the deterministic check schedule and reads the
+    // control block once per batch.  A rejected line-search step makes a round fall short; the following rounds make
+    // up for it (kernels are no-ops outside their turn) and the next read-back re-synchronises the prediction.
+    if (!p->hctl) {
+      p->hctl = static_cast<SolveCtl*>(pinned_cache_alloc(sizeof(SolveCtl), false));
+      p->htime = static_cast<int*>(pinned_cache_alloc(64, true));
+      p->ctl.alloc(1);
+    }
+    SolveCtl* c = p->hctl;
+    memset(c, 0, sizeof(SolveCtl));
+    c->tol_p = tol_p; c->tol_d = tol_d; c->tol_gap = prm.tol_gap;
+    c->sense = f.sense; c->offset = f.offset;
+    c->iter_limit = prm.iter_limit; c->interval = interval; c->restart_on = prm.restart != 0; c->world = 1;
+    *p->htime = (t_lim >= 0 && std::chrono::duration<double>(clk::now() - t_loop).count() > t_lim) ? 1 : 0;
+    {
+      int* dflag = nullptr;
+      CUDA_OK(cudaHostGetDevicePointer(&dflag, p->htime, 0));
+      c->time_flag = t_lim >= 0 ? dflag : nullptr;   // (no limit: spare the device the read over PCIe)
+    }
+    c->term = -1;
+    if (out->trace && out->trace_cap > 0) {
+      if (p->trace_dev.n < (size_t)out->trace_cap * B200PDLP_TRACE_COLS) p->trace_dev.alloc((size_t)out->trace_cap * B200PDLP_TRACE_COLS);
+      c->trace = p->trace_dev.p; c->trace_cap = out->trace_cap;
+    }
+    CUDA_OK(cudaMemcpyAsync(p->ctl.p, c, sizeof(SolveCtl), cudaMemcpyHostToDevice, s));
+    h->stop_iter = 0;   // the first check is due at once (iteration 0)
+    push_state(p);
+    auto next_stop = [&](int it) {
+      int next = it + 1;
+      while (!(next < 10 || next % interval == 0 || next == prm.iter_limit - 1)) next++;
+      return next;
+    };
+    std::vector<std::unique_ptr<CudaEvent>> evs;
+    int pred_iter = 0, carry = 0;   // carry: passes still owed before the next check (after a re-synchronisation)
+    while (true) {
+      size_t nev = 0;
+      auto ev = [&]() -> cudaEvent_t {
+        if (nev == evs.size()) evs.emplace_back(new CudaEvent());
+        return *evs[nev++];
+      };
+      int rounds = 0, passes = 0;
+      bool pred_term = false;
+      if (carry > 0) {
+        CUDA_OK(cudaEventRecord(ev(), s));
+        enqueue_passes_device(p, carry);
+        CUDA_OK(cudaEventRecord(ev(), s));
+        passes += carry; pred_iter += carry; carry = 0;
+      }
+      while (rounds < 12 && passes < 48) {
+        launch_check_graph(p);
+        rounds++;
+        if (pred_iter >= prm.iter_limit - 1) { pred_term = true; break; }
+        const int next = next_stop(pred_iter);
+        CUDA_OK(cudaEventRecord(ev(), s));
+        enqueue_passes_device(p, next - pred_iter);
+        CUDA_OK(cudaEventRecord(ev(), s));
+        passes += next - pred_iter;
+        pred_iter = next;
+      }
+      (void)pred_term;
+      CUDA_OK(cudaMemcpyAsync(c, p->ctl.p, sizeof(SolveCtl), cudaMemcpyDeviceToHost, s));
+      CUDA_OK(cudaMemcpyAsync(h, p->state.p, sizeof(PdhgState), cudaMemcpyDeviceToHost, s));
+      const size_t npairs = nev / 2;   // events so far come in (before, after) pairs around the passes
+      cudaEvent_t fin = ev();
+      CUDA_OK(cudaEventRecord(fin, s));
+      if (t_lim >= 0) {
+        // poll, so that the time-limit word can be raised while the batch runs
+        while (cudaEventQuery(fin) == cudaErrorNotReady) {
+          if (std::chrono::duration<double>(clk::now() - t_loop).count() > t_lim) *p->htime = 1;
+          std::this_thread::yield();
+        }
+      }
+      CUDA_OK(cudaEventSynchronize(fin));
+      for (size_t k = 0; k < npairs; k++) {
+        float ms = 0.f;
+        CUDA_OK(cudaEventElapsedTime(&ms, *evs[2 * k], *evs[2 * k + 1]));
+        iter_ms += ms;
+      }
+      if (c->term >= 0) break;
+      // not finished: continue from where the device really is
+      pred_iter = h->iter;
+      carry = std::max(0, h->stop_iter - h->iter);
+    }
+    term = c->term; term_iterate = c->term_iterate; restarts = c->restarts;
+    have_check = c->checks > 0;
+    for (int t = 0; t < 2; t++) {
+      const DevResiduals& d = c->res[t];
+      Residuals& R = chk.it[t];
+      R.pobj = d.pobj; R.dobj = d.dobj; R.pfeas = d.pfeas; R.dfeas = d.dfeas; R.gap = d.gap; R.relgap = d.relgap;
+      R.pinf_obj = d.pinf_obj; R.pinf_res = d.pinf_res; R.dinf_obj = d.dinf_obj; R.dinf_res = d.dinf_res;
+    }
+    if (c->trace) {
+      out->trace_len = std::min(c->trace_len, out->trace_cap);
+      if (out->trace_len > 0)
+        CUDA_OK(cudaMemcpyAsync(out->trace, p->trace_dev.p, (size_t)out->trace_len * B200PDLP_TRACE_COLS * sizeof(double),
+                                cudaMemcpyDeviceToHost, s));
+    }
+  } else
   // ---- main loop (cupdlp_solver.c:939-1106)
   while (h->iter < prm.iter_limit) {
     const double elapsed = std::chrono::duration<double>(clk::now() - t_loop).count();
-    const bool timed_out_local = t_lim > 0 && elapsed > t_lim;
+    const bool timed_out_local = t_lim >= 0 && elapsed > t_lim;
     if (have_spec) { chk = parse_fused_check(p, spec_flag); have_spec = false; }
     else chk = run_check(p, timed_out_local);
     have_check = true;
@@ -1106,7 +1446,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
       if (speculate) {
         if (!have_ev1) { CUDA_OK(cudaEventRecord(ev1, s)); have_ev1 = true; }
         const double el = std::chrono::duration<double>(clk::now() - t_loop).count();
-        spec_flag = t_lim > 0 && el > t_lim;
+        spec_flag = t_lim >= 0 && el > t_lim;
         enqueue_check_dev(p, spec_flag);
       }
       pull_state(p);
@@ -1145,6 +1485,22 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
     if (fault) throw Error(B200PDLP_ERR_STATE, "P2P barrier timed out (a peer rank did not arrive)");
   }
   const double* daty = use_avg ? p->atyavg.p : p->aty[p->world == 1 ? cur : 0].p;
+  if (dev_form) {
+    // PDHG_PostSolve on the device (device_prep.cu post_*_kernel): un-permute, un-scale, sign conventions, slacks of
+    // BOUND rows; four original-order vectors come back
+    if (out->col_value && out->col_dual && out->row_value && out->row_dual) {
+      const int n0 = f.n_orig;
+      launch_postsolve(s, p->prep.arr, f.sense, have_check ? 1 : 0, dx, daty, dy, dax, p->cost.p, p->lower.p, p->upper.p,
+                       p->colscale.p, p->rowscale.p, p->io_col.p, p->io_col.p + n0, p->io_row.p, p->io_row.p + m);
+      p->launches += 2;
+      CUDA_OK(cudaMemcpyAsync(out->col_value, p->io_col.p, (size_t)n0 * sizeof(double), cudaMemcpyDeviceToHost, s));
+      CUDA_OK(cudaMemcpyAsync(out->col_dual, p->io_col.p + n0, (size_t)n0 * sizeof(double), cudaMemcpyDeviceToHost, s));
+      CUDA_OK(cudaMemcpyAsync(out->row_value, p->io_row.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, s));
+      CUDA_OK(cudaMemcpyAsync(out->row_dual, p->io_row.p + m, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_OK(cudaStreamSynchronize(s));
+    lap("solve", "postsolve (device) + download");
+  } else {
   std::vector<double> hx(n), hy(m, 0.0), hax(m, 0.0), haty(n);
   {
     // device order -> standard-form order
@@ -1238,6 +1594,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
       out->row_dual[i] = v;
     }
   }
+  }   // host postsolve
   out->value_valid = 1; out->dual_valid = 1;
   out->term_code = term; out->term_iterate = term_iterate;
   out->iters = h->iter; out->passes = h->passes; out->restarts = restarts;
@@ -1294,7 +1651,7 @@ static void create_problem_hipdlp(const b200pdlp_lp& lp, const b200pdlp_hipdlp_p
   for (DevBuf<double>* b : {&h.x, &h.xn, &h.rx, &h.xa, &h.aty, &h.atyp, &h.atdy, &h.hslack, &h.sp, &h.sn}) b->alloc(n);
   for (DevBuf<double>* b : {&h.y, &h.yn, &h.ry, &h.ya, &h.axp, &h.dy}) b->alloc(m);
   h.state.alloc(1);
-  CUDA_OK(cudaMallocHost(&h.hstate, sizeof(HipState)));
+  h.hstate = static_cast<HipState*>(pinned_cache_alloc(sizeof(HipState), false));
   size_t maxgrid = std::max<size_t>(kMaxEwBlocks, std::max(p->A.grid(), p->AT.grid()));
   p->scratch_stride = 24 * maxgrid;
   p->partials.alloc(p->scratch_stride * kNumSlots);
@@ -1302,7 +1659,7 @@ static void create_problem_hipdlp(const b200pdlp_lp& lp, const b200pdlp_hipdlp_p
   p->terms.alloc(1);
   p->ordered_cap = 0;
   p->outs.alloc(kOutsCount);
-  CUDA_OK(cudaMallocHost(&p->houts, kOutsCount * sizeof(double)));
+  p->houts = static_cast<double*>(pinned_cache_alloc(kOutsCount * sizeof(double), false));
   CUDA_OK(cudaDeviceSynchronize());
 }
 
@@ -1407,7 +1764,7 @@ static void solve_hipdlp_on_device(b200pdlp_problem* p, const b200pdlp_lp& lp, c
     CUDA_OK(cudaGraphDestroy(g));
     p->launches -= 39 * 3;   // counted when replayed
   }
-  const double t_lim = (prm.time_limit > 0 && std::isfinite(prm.time_limit)) ? prm.time_limit : 0.0;
+  const double t_lim = (prm.time_limit >= 0 && std::isfinite(prm.time_limit)) ? prm.time_limit : -1.0;   // < 0: none
   int term = B200PDLP_TIMELIMIT_OR_ITERLIMIT;
   bool converged = false, timed_out = false;
   const auto t_loop = clk::now();
@@ -1417,7 +1774,7 @@ static void solve_hipdlp_on_device(b200pdlp_problem* p, const b200pdlp_lp& lp, c
   if (ctl.converged(p->houts)) { converged = true; }
   else {
     while (ctl.iters < prm.iter_limit) {
-      if (t_lim > 0 && std::chrono::duration<double>(clk::now() - t_loop).count() > t_lim) { timed_out = true; break; }
+      if (t_lim >= 0 && std::chrono::duration<double>(clk::now() - t_loop).count() > t_lim) { timed_out = true; break; }
       push_state();
       hip_step(p, 1, 1);
       if (ctl.pending_restart_fpe) {   // the restart's reference fixed-point error is that of the first step after it (:600-608)
@@ -1516,12 +1873,30 @@ static int guarded(F&& fn) {
   }
 }
 
-static void check_lp(const b200pdlp_lp* lp) {
+static void check_lp(const b200pdlp_lp* lp, bool deep = true) {
   if (!lp || lp->num_col < 0 || lp->num_row < 0 || !lp->a_start || (lp->a_start[lp->num_col] > 0 && (!lp->a_index || !lp->a_value)) ||
       (lp->num_col > 0 && (!lp->col_cost || !lp->col_lower || !lp->col_upper)) || (lp->num_row > 0 && (!lp->row_lower || !lp->row_upper)))
     throw Error(B200PDLP_ERR_ARG, "b200pdlp: malformed b200pdlp_lp");
   if (lp->sense != 1.0 && lp->sense != -1.0) throw Error(B200PDLP_ERR_ARG, "b200pdlp: sense must be +1 or -1");
+  // formulate() indexes per-row arrays with a_index and walks a_start: validate both once (O(nnz), a few ms at 8M nonzeros)
+  if (lp->a_start[0] != 0) throw Error(B200PDLP_ERR_ARG, "b200pdlp: a_start[0] must be 0");
+  for (int j = 0; j < lp->num_col; j++)
+    if (lp->a_start[j + 1] < lp->a_start[j]) throw Error(B200PDLP_ERR_ARG, "b200pdlp: a_start must be non-decreasing");
+  if (!deep) return;   // (the device prologue checks the index range in its first sweep over the nonzeros)
+  const int nnz = lp->a_start[lp->num_col], m = lp->num_row;
+  unsigned bad = 0;
+  for (int q = 0; q < nnz; q++) bad |= (unsigned)lp->a_index[q] >= (unsigned)m;
+  if (bad) throw Error(B200PDLP_ERR_ARG, "b200pdlp: a_index entry outside [0, num_row)");
 }
+
+// the public entry points select the problem's device; the caller's current device is restored on every exit path
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 extern "C" {
 
@@ -1537,23 +1912,30 @@ void b200pdlp_default_params(b200pdlp_params* p) {
   memset(p, 0, sizeof(*p));
   p->iter_limit = 2147483647;                 // kHighsIInf (HighsOptions.h:1341)
   p->tol_primal = p->tol_dual = p->tol_gap = 1e-7;
-  p->time_limit = 0.0;
+  p->time_limit = -1.0;                       // none (0 = already over: the first check ends the run)
   p->scaling = 1; p->adaptive_step = 1; p->restart = 1;
   p->log_level = 0; p->check_interval = 40; p->device = -1; p->graph_passes = 0;
 }
 
 int b200pdlp_problem_create(const b200pdlp_lp* lp, const b200pdlp_params* params, int32_t rank, int32_t world, b200pdlp_problem** out) {
+  DeviceGuard dg;
   return guarded([&] {
-    check_lp(lp);
     if (!params || !out || world < 1 || rank < 0 || rank >= world) throw Error(B200PDLP_ERR_ARG, "b200pdlp_problem_create: bad arguments");
+    check_lp(lp, false);
+    check_lp(lp, !use_device_prep(*lp, *params, world));
     auto* p = new b200pdlp_problem();
-    try { create_problem(*lp, *params, rank, world, p); } catch (...) { delete p; throw; }
+    try {
+      p->prep.keep_form = true;   // persistent handle: the accessors below may ask for the standard form
+      if (use_device_prep(*lp, *params, world)) create_problem_device(*lp, *params, p);
+      else create_problem(*lp, *params, rank, world, p);
+    } catch (...) { delete p; throw; }
     *out = p;
   });
 }
 
 void b200pdlp_problem_destroy(b200pdlp_problem* p) {
   if (!p) return;
+  DeviceGuard dg;
   cudaSetDevice(p->device);
   delete p;
 }
@@ -1568,6 +1950,11 @@ int b200pdlp_problem_dims(const b200pdlp_problem* p, int32_t dims[8]) {
 
 int b200pdlp_problem_get_vector(const b200pdlp_problem* p, int32_t which, double* dst, int32_t cap) {
   if (!p || !dst) return B200PDLP_ERR_ARG;
+  if (p->dev_form) {
+    DeviceGuard dg;
+    const int rc = guarded([&] { set_device(p); ensure_host_form(const_cast<b200pdlp_problem*>(p)); });
+    if (rc != B200PDLP_OK) return rc;
+  }
   const std::vector<double>* v = nullptr;
   switch (which) {
     case 0: v = &p->form.cost; break;
@@ -1586,6 +1973,11 @@ int b200pdlp_problem_get_vector(const b200pdlp_problem* p, int32_t which, double
 
 int b200pdlp_problem_get_csr(const b200pdlp_problem* p, int32_t* rowptr, int32_t* col, double* val) {
   if (!p || !rowptr || !col || !val) return B200PDLP_ERR_ARG;
+  if (p->dev_form) {
+    DeviceGuard dg;
+    const int rc = guarded([&] { set_device(p); ensure_host_form(const_cast<b200pdlp_problem*>(p)); });
+    if (rc != B200PDLP_OK) return rc;
+  }
   Csr lazy;
   if (p->csr_local.rowptr.empty()) {
     // device-filled layouts keep no host copy: rebuild it from the (downloaded) scaled form on demand
@@ -1601,9 +1993,11 @@ int b200pdlp_problem_get_csr(const b200pdlp_problem* p, int32_t* rowptr, int32_t
 }
 
 int b200pdlp_spmv_ax(b200pdlp_problem* p, const double* x, double* ax) {
+  DeviceGuard dg;
   return guarded([&] {
     if (!p || !x || !ax) throw Error(B200PDLP_ERR_ARG, "null argument");
     set_device(p);
+    ensure_host_maps(p);
     const size_t full = p->world == 1 ? (size_t)p->n : p->xfull.n;
     std::vector<double> t(std::max<size_t>(full, std::max(p->ml, 1)), 0.0);
     for (int j = 0; j < p->n; j++) t[seg_pos(p, j)] = x[p->cperm[j]];
@@ -1619,9 +2013,11 @@ int b200pdlp_spmv_ax(b200pdlp_problem* p, const double* x, double* ax) {
 }
 
 int b200pdlp_spmv_aty(b200pdlp_problem* p, const double* y, double* aty) {
+  DeviceGuard dg;
   return guarded([&] {
     if (!p || !y || !aty) throw Error(B200PDLP_ERR_ARG, "null argument");
     set_device(p);
+    ensure_host_maps(p);
     const size_t full = p->world == 1 ? (size_t)p->n : p->part.n;
     std::vector<double> t(std::max<size_t>(full, std::max(p->ml, 1)), 0.0);
     for (int i = 0; i < p->ml; i++) t[i] = y[p->rperm[i]];
@@ -1638,6 +2034,7 @@ int b200pdlp_spmv_aty(b200pdlp_problem* p, const double* y, double* aty) {
 }
 
 int b200pdlp_bench_spmv(b200pdlp_problem* p, int32_t which, int32_t reps, float* ms_total) {
+  DeviceGuard dg;
   return guarded([&] {
     if (!p || !ms_total || reps < 1) throw Error(B200PDLP_ERR_ARG, "bad argument");
     set_device(p);
@@ -1661,6 +2058,7 @@ int b200pdlp_bench_spmv(b200pdlp_problem* p, int32_t which, int32_t reps, float*
 }
 
 int b200pdlp_bench_pass(b200pdlp_problem* p, int32_t reps, float ms[4]) {
+  DeviceGuard dg;
   return guarded([&] {
     if (!p || !ms || reps < 1) throw Error(B200PDLP_ERR_ARG, "bad argument");
     set_device(p);
@@ -1744,6 +2142,7 @@ int b200pdlp_bench_pass(b200pdlp_problem* p, int32_t reps, float ms[4]) {
 }
 
 int b200pdlp_problem_solve(b200pdlp_problem* p, const b200pdlp_params* params, const b200pdlp_warm* warm, b200pdlp_result* out) {
+  DeviceGuard dg;
   return guarded([&] {
     if (!p || !params || !out) throw Error(B200PDLP_ERR_ARG, "null argument");
     out->setup_seconds = 0.0;
@@ -1753,13 +2152,16 @@ int b200pdlp_problem_solve(b200pdlp_problem* p, const b200pdlp_params* params, c
 }
 
 int b200pdlp_solve(const b200pdlp_lp* lp, const b200pdlp_params* params, const b200pdlp_warm* warm, b200pdlp_result* out) {
+  DeviceGuard dg;
   return guarded([&] {
-    check_lp(lp);
     if (!params || !out) throw Error(B200PDLP_ERR_ARG, "null argument");
+    check_lp(lp, false);
+    check_lp(lp, !use_device_prep(*lp, *params, 1));
     const auto t0 = std::chrono::steady_clock::now();
     b200pdlp_problem* p = new b200pdlp_problem();
     try {
-      create_problem(*lp, *params, 0, 1, p);
+      if (use_device_prep(*lp, *params, 1)) create_problem_device(*lp, *params, p);
+      else create_problem(*lp, *params, 0, 1, p);
       out->setup_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
       solve_on_device(p, *params, warm, out);
       CUDA_OK(cudaGetLastError());
@@ -1781,6 +2183,9 @@ int b200pdlp_solve(const b200pdlp_lp* lp, const b200pdlp_params* params, const b
 int b200pdlp_solve_multi(const b200pdlp_lp* lp, const b200pdlp_params* params, const b200pdlp_warm* warm,
                          b200pdlp_result* out, int32_t ngpus, const int32_t* devices) {
   if (ngpus <= 1) return b200pdlp_solve(lp, params, warm, out);
+  // fixed-step mode needs the power method, which is single-GPU (power_method): fall back instead of failing
+  if (params && params->adaptive_step == 0) return b200pdlp_solve(lp, params, warm, out);
+  DeviceGuard dg;
   std::vector<b200pdlp_problem*> probs((size_t)ngpus, nullptr);
   const int rc = guarded([&] {
     check_lp(lp);
@@ -1853,10 +2258,12 @@ void b200pdlp_hipdlp_default_params(b200pdlp_hipdlp_params* p) {
   p->scaling_mode = 5;
   p->ruiz_iterations = 10;
   p->step_size_strategy = 3;
+  p->time_limit = -1.0;
   p->device = -1;
 }
 
 int b200pdlp_solve_hipdlp(const b200pdlp_lp* lp, const b200pdlp_hipdlp_params* params, b200pdlp_result* out) {
+  DeviceGuard dg;
   return guarded([&] {
     check_lp(lp);
     if (!params || !out) throw Error(B200PDLP_ERR_ARG, "null argument");
@@ -1887,6 +2294,7 @@ int b200pdlp_nccl_unique_id(uint8_t id[128]) {
 }
 
 int b200pdlp_comm_init(b200pdlp_problem* p, const uint8_t id[128]) {
+  DeviceGuard dg;
   return guarded([&] {
     if (!p || !id) throw Error(B200PDLP_ERR_ARG, "null argument");
     set_device(p);
@@ -1897,6 +2305,7 @@ int b200pdlp_comm_init(b200pdlp_problem* p, const uint8_t id[128]) {
 }
 
 int b200pdlp_p2p_timeline(b200pdlp_problem* p, double out_us[8]) {
+  DeviceGuard dg;
   return guarded([&] {
     if (!p || !out_us || !p->p2p) throw Error(B200PDLP_ERR_ARG, "p2p_timeline needs the fused multi-GPU path");
     set_device(p);
@@ -1913,6 +2322,7 @@ int b200pdlp_p2p_timeline(b200pdlp_problem* p, double out_us[8]) {
 }
 
 int b200pdlp_p2p_export(b200pdlp_problem* p, uint8_t handles[B200PDLP_IPC_BYTES]) {
+  DeviceGuard dg;
   return guarded([&] {
     static_assert(4 * sizeof(cudaIpcMemHandle_t) == B200PDLP_IPC_BYTES, "IPC blob size");
     if (!p || !handles || p->world < 2) throw Error(B200PDLP_ERR_ARG, "p2p_export needs a multi-GPU problem");
@@ -1927,6 +2337,7 @@ int b200pdlp_p2p_export(b200pdlp_problem* p, uint8_t handles[B200PDLP_IPC_BYTES]
 }
 
 int b200pdlp_p2p_import(b200pdlp_problem* p, const uint8_t* all_handles) {
+  DeviceGuard dg;
   return guarded([&] {
     if (!p || !all_handles || p->world < 2) throw Error(B200PDLP_ERR_ARG, "p2p_import needs a multi-GPU problem");
     if (p->world > kMaxPeers) throw Error(B200PDLP_ERR_ARG, "too many ranks for the P2P path");
@@ -1957,6 +2368,7 @@ int b200pdlp_p2p_import(b200pdlp_problem* p, const uint8_t* all_handles) {
 }
 
 int b200pdlp_p2p_link_local(b200pdlp_problem** probs, int32_t count) {
+  DeviceGuard dg;
   return guarded([&] {
     if (!probs || count < 2 || count > kMaxPeers) throw Error(B200PDLP_ERR_ARG, "p2p_link_local: bad arguments");
     std::vector<b200pdlp_problem*> by_rank(count, nullptr);
@@ -1994,6 +2406,7 @@ int b200pdlp_p2p_link_local(b200pdlp_problem** probs, int32_t count) {
 }
 
 int b200pdlp_p2p_release(b200pdlp_problem* p) {
+  DeviceGuard dg;
   return guarded([&] {
     if (!p) throw Error(B200PDLP_ERR_ARG, "null argument");
     set_device(p);
@@ -2139,6 +2552,92 @@ int b200pdlp_form_layout_eval(b200pdlp_form* fh, int32_t rank, int32_t world, in
     stats[9] = L.shard_len; stats[10] = L.seg_len; stats[11] = ms;
   });
 }
+
+// Test entry point: the device prologue (device_prep.cu) against its host twin (host_prep.cpp), array by array, bit for
+// bit.  report[k] = number of mismatching entries of item k (0 everywhere = identical), see include/b200pdlp.h.
+int b200pdlp_debug_prep_compare(const b200pdlp_lp* lp, int32_t scaling, double report[32]) {
+  DeviceGuard dg;
+  return guarded([&] {
+    check_lp(lp);
+    if (!report) throw Error(B200PDLP_ERR_ARG, "null argument");
+    for (int k = 0; k < 32; k++) report[k] = 0.0;
+    StdForm f;
+    formulate(*lp, f);
+    scale(f, scaling != 0);
+    if (f.rptr.empty()) build_row_index(f);
+    HostLayout L;
+    build_layout(f, 0, 1, /*ordered_max=*/-1, L);
+    cudaStream_t s = nullptr;
+    CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    DevicePrologue P;
+    P.keep_form = true;
+    struct Cleanup { DevicePrologue& P; cudaStream_t s; ~Cleanup() { P.A.release(); P.AT.release(); P.release_arrays(); P.release_form(); cudaStreamDestroy(s); } } cleanup{P, s};
+    try { P.run(s, *lp, scaling != 0, 512); }
+    catch (const std::exception& ex) { throw Error(B200PDLP_ERR_CUDA, ex.what()); }
+    auto cmp_i = [&](const int* dev, const int* host, size_t cnt) {
+      std::vector<int> t(cnt);
+      if (cnt) CUDA_OK(cudaMemcpy(t.data(), dev, cnt * sizeof(int), cudaMemcpyDeviceToHost));
+      double bad = 0;
+      for (size_t i = 0; i < cnt; i++) bad += t[i] != host[i];
+      return bad;
+    };
+    auto cmp_d = [&](const double* dev, const double* host, size_t cnt) {
+      std::vector<double> t(cnt);
+      if (cnt) CUDA_OK(cudaMemcpy(t.data(), dev, cnt * sizeof(double), cudaMemcpyDeviceToHost));
+      double bad = 0;
+      for (size_t i = 0; i < cnt; i++) bad += memcmp(&t[i], &host[i], sizeof(double)) != 0;
+      return bad;
+    };
+    const DevProblemArrays& a = P.arr;
+    const int n = f.n, m = f.m, nnz = f.nnz;
+    report[0] = a.n != n; report[1] = a.m != m; report[2] = a.nnz != nnz; report[3] = a.neq != f.neq;
+    if (report[0] + report[1] + report[2] + report[3] > 0) return;
+    report[4] = cmp_i(P.form.cbeg, f.cbeg.data(), n + 1);
+    report[5] = cmp_i(P.form.cidx, f.cidx.data(), nnz);
+    report[6] = cmp_d(P.form.cval, f.cval.data(), nnz);
+    report[7] = cmp_d(P.form.cost, f.cost.data(), n);
+    report[8] = cmp_d(P.form.lower, f.lower.data(), n);
+    report[9] = cmp_d(P.form.upper, f.upper.data(), n);
+    report[10] = cmp_d(P.form.colscale, f.col_scale.data(), n);
+    report[11] = cmp_d(P.form.rhs, f.rhs.data(), m);
+    report[12] = cmp_d(P.form.rowscale, f.row_scale.data(), m);
+    report[13] = cmp_i(P.form.rptr, f.rptr.data(), m + 1);
+    report[14] = cmp_i(P.form.rpos, f.rpos.data(), nnz);
+    report[15] = cmp_i(a.row_new_idx, f.row_new_idx.data(), m);
+    report[16] = cmp_i(a.row_class, f.row_class.data(), m);
+    report[17] = cmp_i(a.rperm, L.rperm.data(), m);
+    report[18] = cmp_i(a.cperm, L.cperm.data(), n);
+    auto cmp_sell = [&](const DevSellOwned& D, const SellMatrix& H, double* r_slices, double* r_col, double* r_val, double* r_long) {
+      if ((size_t)D.nslices != H.slices.size() || D.padded != H.padded || (size_t)D.nlong != H.long_rows.size() ||
+          (size_t)D.nsegs != H.segs.size() || D.lcount != H.lcount) { *r_slices = -1; return; }
+      *r_slices = cmp_i(reinterpret_cast<const int*>(D.slices), reinterpret_cast<const int*>(H.slices.data()), 4 * H.slices.size());
+      *r_col = cmp_i(D.col, H.col.data(), (size_t)H.padded);
+      *r_val = cmp_d(D.val, H.val.data(), (size_t)H.padded);
+      *r_long = cmp_i(reinterpret_cast<const int*>(D.long_rows), reinterpret_cast<const int*>(H.long_rows.data()), 4 * H.long_rows.size()) +
+                cmp_i(reinterpret_cast<const int*>(D.segs), reinterpret_cast<const int*>(H.segs.data()), 4 * H.segs.size()) +
+                cmp_i(D.lcol, H.lcol.data(), H.lcol.size()) + cmp_d(D.lval, H.lval.data(), H.lval.size());
+    };
+    cmp_sell(P.A, L.A, report + 19, report + 20, report + 21, report + 25);
+    cmp_sell(P.AT, L.AT, report + 22, report + 23, report + 24, report + 26);
+    report[27] = P.sc.amax != f.amax;
+    report[28] = std::fabs(std::sqrt(P.sc.norm_cost_sq) - f.norm_cost) / (1.0 + f.norm_cost);
+    report[29] = std::fabs(std::sqrt(P.sc.norm_rhs_sq) - f.norm_rhs) / (1.0 + f.norm_rhs);
+    {
+      std::vector<double> t(std::max(n, m));
+      double bad = 0;
+      auto cmp_perm = [&](const double* dev, const std::vector<double>& v, const std::vector<int>& perm, int len) {
+        for (int i = 0; i < len; i++) t[i] = v[perm[i]];
+        bad += cmp_d(dev, t.data(), len);
+      };
+      cmp_perm(a.cost, f.cost, L.cperm, n); cmp_perm(a.lower, f.lower, L.cperm, n); cmp_perm(a.upper, f.upper, L.cperm, n);
+      cmp_perm(a.colscale, f.col_scale, L.cperm, n); cmp_perm(a.rhs, f.rhs, L.rperm, m); cmp_perm(a.rowscale, f.row_scale, L.rperm, m);
+      report[30] = bad;
+    }
+    report[31] = P.sc.cols_sorted;
+  });
+}
+
+void b200pdlp_release_cache(void) { dev_cache_release(); }
 
 int b200pdlp_partition_rows(const b200pdlp_lp* lp, int32_t world, int32_t* bounds) {
   return guarded([&] {

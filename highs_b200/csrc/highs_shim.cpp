@@ -65,7 +65,7 @@ HighsStatus solveLpCupdlp(const HighsOptions& options, HighsTimer& timer, const 
   prm.tol_gap = options.pdlp_optimality_tolerance;
   if (options.kkt_tolerance != kDefaultKktTolerance)
     prm.tol_primal = prm.tol_dual = prm.tol_gap = options.kkt_tolerance;
-  prm.time_limit = options.time_limit < kHighsInf ? options.time_limit : 0.0;
+  prm.time_limit = options.time_limit < kHighsInf ? options.time_limit : -1.0;   // < 0 = none; 0 ends the run at the first check
   int restart_on = (options.pdlp_features_off & kPdlpRestartOff) == 0 ? 1 : 0;
   if (options.pdlp_cupdlpc_restart_method == 0) restart_on = 0;
   prm.restart = restart_on;

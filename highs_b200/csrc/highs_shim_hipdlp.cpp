@@ -41,7 +41,7 @@ HighsStatus solveLpHiPdlp(const HighsOptions& options, HighsTimer& timer, const 
   prm.tolerance = options.pdlp_optimality_tolerance;
   if (options.kkt_tolerance != kDefaultKktTolerance) prm.tolerance = options.kkt_tolerance;
   prm.iter_limit = (int32_t)std::min<int64_t>((int64_t)options.pdlp_iteration_limit, (int64_t)kHighsIInf32);
-  prm.time_limit = options.time_limit < kHighsInf ? options.time_limit : 0.0;
+  prm.time_limit = options.time_limit < kHighsInf ? options.time_limit : -1.0;   // < 0 = none; 0 ends the run at the first check
   prm.scaling_mode = (options.pdlp_features_off & kPdlpScalingOff) == 0 ? (int32_t)options.pdlp_scaling_mode : 0;
   prm.ruiz_iterations = (int32_t)options.pdlp_ruiz_iterations;
   prm.step_size_strategy = options.pdlp_step_size_strategy == kPdlpStepSizeStrategyFixed ? 0 : 3;

@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <exception>
 #include <functional>
 #include <limits>
 #include <stdexcept>
@@ -63,8 +64,14 @@ class Pool {
     // wait for the stragglers (short: spin, then yield)
     for (int spins = 0; remaining_.load(std::memory_order_acquire) > 0; spins++)
       if (spins > 2000) std::this_thread::yield();
-    std::lock_guard<std::mutex> lk(m_);
-    job_ = nullptr;
+    std::exception_ptr err;
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      job_ = nullptr;
+      err = error_;
+      error_ = nullptr;
+    }
+    if (err) std::rethrow_exception(err);   // first exception of any task, on the calling thread, after ALL tasks ended
   }
  private:
   Pool() {
@@ -80,7 +87,12 @@ class Pool {
       const unsigned t = (unsigned)(tk & 0xffffffffull);
       if ((int)t >= k) return;
       if (!ticket_.compare_exchange_weak(tk, tk + 1, std::memory_order_acq_rel)) continue;
-      fn((int)t);
+      try {
+        fn((int)t);
+      } catch (...) {   // e.g. std::bad_alloc in a task: hand it to the caller instead of std::terminate on a worker
+        std::lock_guard<std::mutex> lk(m_);
+        if (!error_) error_ = std::current_exception();
+      }
       remaining_.fetch_sub(1, std::memory_order_acq_rel);
     }
   }
@@ -115,6 +127,7 @@ class Pool {
   std::atomic<unsigned long long> wake_{0}, ticket_{0};
   std::atomic<int> remaining_{0};
   std::atomic<bool> dead_{false};
+  std::exception_ptr error_;   // guarded by m_
 };
 }  // namespace
 

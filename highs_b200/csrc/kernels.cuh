@@ -55,6 +55,32 @@ struct PdhgState {
   double pow_grow[kPowTab];          // (k+1)^-0.6
 };
 
+// Device-resident control of a whole solve (tree mode): the check iterations decide ON THE DEVICE -- termination,
+// infeasibility, restarts, the next check iteration -- so that the host only enqueues work and reads this block
+// (cupdlp_solver.c:939-1106 is the host loop this replaces; cupdlp_restart.c:3-99, cupdlp_proj.c:88-148).
+struct DevResiduals {   // CUPDLPresobj of one iterate
+  double pobj, dobj, pfeas, dfeas, gap, relgap, pinf_obj, pinf_res, dinf_obj, dinf_res;
+};
+struct SolveCtl {
+  // constants of the solve
+  double tol_p, tol_d, tol_gap;      // tol_p / tol_d already multiplied by (1 + |b|) / (1 + |c|)
+  double sense, offset;
+  int iter_limit, interval, restart_on, world;
+  const volatile int* time_flag;     // mapped pinned host word: nonzero once the time limit has passed
+  // restart memo (cupdlp_restart.c: dPrimalFeasLastRestart ..., dPrimalFeasLastCandidate ...)
+  double pf_lr, df_lr, gap_lr, pf_lc, df_lc, gap_lc;
+  int last_restart_iter;
+  // per-check scratch
+  int restart_choice;                // 0 none, 1 to the average, 2 to the current iterate (this check)
+  // results
+  int term;                          // -1 while running, else a b200pdlp_term
+  int term_iterate, restarts, checks;
+  DevResiduals res[2];               // residuals of the last check: current, average
+  double* trace;                     // device [trace_cap][16] or nullptr
+  int trace_cap, trace_len;
+  double sums[32];                   // the reduced sums of the last check (diagnostics)
+};
+
 // HiPDLP mode: the few scalars a Halpern step reads on the device (so that a block of steps is graph-capturable)
 struct HipState {
   double primal_step, dual_step;

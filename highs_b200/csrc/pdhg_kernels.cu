@@ -556,6 +556,7 @@ __global__ void p2p_exchange_kernel(double* vals, int k, PeerPtrs pp, int world,
     } while (seen < e);
   }
   __syncwarp();
+  if (*reinterpret_cast<volatile int*>(fault)) return;   // a peer never arrived: leave the (stale) mailboxes alone
   if (lane < k) {
     const double* mb = reinterpret_cast<const double*>(pp.flags[rank] + box);
     double s = 0.0;
@@ -645,6 +646,7 @@ p2p_barrier_kernel(int mode, PdhgState* st, const double* __restrict__ partials,
       } while (seen < e);
     }
     __syncwarp();
+    if (*reinterpret_cast<volatile int*>(fault)) return;   // timed out: no reduce, no step rule on stale scalars (the host raises the error)
     if (lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_done));
     if (mode == 1 && lane == 0) {
       const double* mb = reinterpret_cast<const double*>(pp.flags[rank] + 3 * kMaxPeers);
@@ -1007,6 +1009,341 @@ __global__ void __launch_bounds__(kThreads) fill_kernel(int len, double* __restr
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < len; i += stride) v[i] = w;
 }
 
+// ================================================== device-side check iteration (tree mode, one GPU)
+// The whole check -- averages, A xbar and A'ybar, residuals of both iterates, termination, infeasibility, restart --
+// without a host round trip (cupdlp_solver.c:953-1106 on the host in the reference; host_check path of engine.cu for
+// ordered mode / several GPUs).  Six launches:
+//   C1 check_avg_x_kernel          xbar = (xSum + w x) / sum(w)                  (cupdlp_step.c:377-420)
+//   C2 spmv<CheckRowEpilogue>      A xbar; ybar formed on the fly; row-side sums of BOTH iterates in the epilogue
+//   C3 spmv<CheckColEpilogue>      A'ybar; column-side sums of both iterates in the epilogue
+//   C4 check_decide_kernel         adds the block partials, forms the residuals, decides (1 CTA)
+//   C5 restart_sweep_kernel        only if C4 chose a restart: copies, clears the sums, |x - x_lr|^2, |y - y_lr|^2
+//   C6 check_finish_kernel         restart scalars (beta, tau, sigma), trace row, next check iteration, power tables
+// Every kernel is a no-op unless the check iteration has been reached and the solve is still running, so the host can
+// enqueue checks speculatively between graphs of passes.
+__device__ __forceinline__ bool check_live(const PdhgState* st, const SolveCtl* ctl) {
+  return ctl->term < 0 && st->iter >= st->stop_iter;
+}
+
+__global__ void __launch_bounds__(kThreads)
+check_avg_x_kernel(int n, const double* __restrict__ x0, const double* __restrict__ x1, double* __restrict__ xsum,
+                   double* __restrict__ xavg, const PdhgState* __restrict__ st, const SolveCtl* __restrict__ ctl) {
+  if (!check_live(st, ctl)) return;
+  const double* __restrict__ x = st->cur ? x1 : x0;
+  const bool pending = st->pending != 0;
+  const double w = st->w_pending;
+  const double scale = st->sum_step > 0.0 ? 1.0 / st->sum_step : 1.0;
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    double s = xsum[i];
+    if (pending) { s = s + w * x[i]; xsum[i] = s; }
+    xavg[i] = s * scale;
+  }
+}
+
+// row-side sums of one iterate (row_check_fused_kernel's terms): 0 y.b, 1 |primal residual|^2, 2 |y|^2,
+// 3 |[ax]_eq, min([ax]_ineq, 0) rowScale|^2
+__device__ __forceinline__ void row_terms(double y, double ax, double bi, double sc, bool ineq, double* t) {
+  double r = ax - bi;
+  if (ineq) r = r < 0.0 ? r : 0.0;
+  r = r * sc;
+  double k = ax;
+  if (ineq) k = k < 0.0 ? k : 0.0;
+  k = k * sc;
+  t[0] = y * bi; t[1] = r * r; t[2] = y * y; t[3] = k * k;
+}
+// column-side sums of one iterate (col_check_fused_kernel's terms, 10 of them)
+__device__ __forceinline__ void col_terms(double x, double aty, double ci, double l, double u, double sc, double* t) {
+  const bool hl = l > -INFINITY, hu = u < INFINITY;
+  const double lf = hl ? l : 0.0, uf = hu ? u : 0.0;
+  const double isc = 1.0 / sc;
+  const double rc = ci - aty;
+  const double sp = hl ? (rc > 0.0 ? rc : 0.0) : 0.0;
+  const double sn = hu ? (rc < 0.0 ? -rc : 0.0) : 0.0;
+  const double rr = (rc - sp + sn) * sc;
+  const double k = (aty + sp - sn) * sc;
+  const double bl = hl ? (x < 0.0 ? x : 0.0) * isc : 0.0;
+  const double bu = hu ? (x > 0.0 ? x : 0.0) * isc : 0.0;
+  t[0] = x * ci; t[1] = sp * lf; t[2] = sn * uf; t[3] = rr * rr; t[4] = sp * sp; t[5] = sn * sn;
+  t[6] = x * x; t[7] = k * k; t[8] = bl * bl; t[9] = bu * bu;
+}
+
+struct CheckRowEpilogue {
+  static constexpr int NACC = 8;
+  const PdhgState* st;
+  const SolveCtl* ctl;
+  const double* xavg;
+  const double *y0, *y1, *ax0, *ax1;
+  double *ysum, *yavg, *axavg;
+  const double *b, *rsc;
+  int neq;
+  const double *y, *ax;
+  double w, scale;
+  bool pend;
+  __device__ bool begin() {
+    if (!check_live(st, ctl)) return false;
+    const int cur = st->cur;
+    y = cur ? y1 : y0; ax = cur ? ax1 : ax0;
+    w = st->w_pending; pend = st->pending != 0;
+    scale = st->sum_step > 0.0 ? 1.0 / st->sum_step : 1.0;
+    return true;
+  }
+  __device__ const double* input() const { return xavg; }
+  double p_y, p_ax, p_ys, p_b, p_sc;
+  __device__ void prefetch(int r) { p_y = y[r]; p_ax = ax[r]; p_ys = ysum[r]; p_b = b[r]; p_sc = rsc[r]; }
+  __device__ void row(int r, double s, double* t) const {
+    axavg[r] = s;
+    double ys = p_ys;
+    if (pend) { ys = ys + w * p_y; ysum[r] = ys; }
+    const double ya = ys * scale;
+    yavg[r] = ya;
+    const bool ineq = r >= neq;
+    row_terms(p_y, p_ax, p_b, p_sc, ineq, t);
+    row_terms(ya, s, p_b, p_sc, ineq, t + 4);
+  }
+};
+
+struct CheckColEpilogue {
+  static constexpr int NACC = 20;
+  const PdhgState* st;
+  const SolveCtl* ctl;
+  const double* yavg;
+  const double *x0, *x1, *aty0, *aty1, *xavg;
+  double* atyavg;
+  const double *c, *lo, *up, *cs;
+  const double *x, *aty;
+  __device__ bool begin() {
+    if (!check_live(st, ctl)) return false;
+    const int cur = st->cur;
+    x = cur ? x1 : x0; aty = cur ? aty1 : aty0;
+    return true;
+  }
+  __device__ const double* input() const { return yavg; }
+  double p_x, p_aty, p_xa, p_c, p_lo, p_up, p_cs;
+  __device__ void prefetch(int j) {
+    p_x = x[j]; p_aty = aty[j]; p_xa = xavg[j]; p_c = c[j]; p_lo = lo[j]; p_up = up[j]; p_cs = cs[j];
+  }
+  __device__ void row(int j, double s, double* t) const {
+    atyavg[j] = s;
+    col_terms(p_x, p_aty, p_c, p_lo, p_up, p_cs, t);
+    col_terms(p_xa, s, p_c, p_lo, p_up, p_cs, t + 10);
+  }
+};
+
+// PDHG_Check_Restart_GPU (cupdlp_restart.c:3-99): 0 none, 1 to the average, 2 to the current iterate
+__device__ double restart_score_dev(double beta, double pf, double df, double gap) {   // cupdlp_restart.c:113-124
+  return sqrt(beta * pf * pf + df * df / beta + gap * gap);
+}
+__device__ int decide_restart_dev(const PdhgState* st, SolveCtl* c) {
+  const DevResiduals &L = c->res[0], &A = c->res[1];
+  if (st->iter == c->last_restart_iter) {
+    c->pf_lr = L.pfeas; c->df_lr = L.dfeas; c->gap_lr = L.gap;
+    c->pf_lc = L.pfeas; c->df_lc = L.dfeas; c->gap_lc = L.gap;
+    return 0;
+  }
+  const double mu_cur = restart_score_dev(st->beta, L.pfeas, L.dfeas, L.gap);
+  const double mu_avg = restart_score_dev(st->beta, A.pfeas, A.dfeas, A.gap);
+  int choice = mu_cur < mu_avg ? 2 : 1;
+  const double mu_cand = mu_cur < mu_avg ? mu_cur : mu_avg;
+  if ((st->iter - c->last_restart_iter) >= 0.36 * st->iter) {
+    // artificial restart
+  } else {
+    const double mu_lr = restart_score_dev(st->beta, c->pf_lr, c->df_lr, c->gap_lr);
+    if (!(mu_cand < 0.2 * mu_lr)) {
+      const double mu_lc = restart_score_dev(st->beta, c->pf_lc, c->df_lc, c->gap_lc);
+      if (!(mu_cand < 0.8 * mu_lr && mu_cand > mu_lc)) choice = 0;
+    }
+  }
+  const DevResiduals& C = mu_cur < mu_avg ? L : A;
+  c->pf_lc = C.pfeas; c->df_lc = C.dfeas; c->gap_lc = C.gap;
+  return choice;
+}
+
+__device__ void trace_row_dev(SolveCtl* c, const PdhgState* st, int restart) {
+  if (!c->trace || c->trace_len >= c->trace_cap) return;
+  double* t = c->trace + (size_t)c->trace_len * 16;
+  const DevResiduals &L = restart == 1 ? c->res[1] : c->res[0], &A = c->res[1];
+  t[0] = st->iter; t[1] = L.pobj; t[2] = L.dobj; t[3] = L.pfeas; t[4] = L.dfeas;
+  t[5] = A.pobj; t[6] = A.dobj; t[7] = A.pfeas; t[8] = A.dfeas;
+  t[9] = st->tau; t[10] = st->sigma; t[11] = st->beta; t[12] = restart; t[13] = st->step_iter;
+  t[14] = st->sum_step; t[15] = 0;
+  c->trace_len++;
+}
+
+// C4: sums (fixed order) -> residuals (PDHG_Compute_Residuals / _Infeas_Residuals, cupdlp_solver.c:473-529, :433-471)
+// -> PDHG_Check_Termination[_Average] (:797-841), PDHG_Check_Infeasibility (:740-795), limits (:1057-1067), restart choice
+constexpr int kCheckSums = 28;
+__global__ void __launch_bounds__(kStepThreads)
+check_decide_kernel(PdhgState* __restrict__ st, SolveCtl* __restrict__ ctl, const double* __restrict__ prow, int nbr,
+                    const double* __restrict__ pcol, int nbc) {
+  if (!check_live(st, ctl)) return;
+  __shared__ double sm[kCheckSums][kStepThreads / 32];
+  __shared__ double tot[kCheckSums];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int a = 0; a < kCheckSums; a++) {
+    const double* p = a < 8 ? prow + (size_t)a * nbr : pcol + (size_t)(a - 8) * nbc;
+    const int nb = a < 8 ? nbr : nbc;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nb; i += kStepThreads) s += p[i];
+    s = warp_sum(s);
+    if (lane == 0) sm[a][wid] = s;
+  }
+  __syncthreads();
+  if (wid == 0) {
+    for (int a = 0; a < kCheckSums; a++) {
+      double s = sm[a][lane];
+      s = warp_sum(s);
+      if (lane == 0) tot[a] = s;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const double sense = ctl->sense, offset = ctl->offset;
+  for (int t = 0; t < 2; t++) {
+    const double* a = tot + 8 + 10 * t;
+    const double* r = tot + 4 * t;
+    DevResiduals& R = ctl->res[t];
+    R.pobj = a[0] * sense + offset;
+    R.pfeas = sqrt(r[1]);
+    R.dobj = ((r[0] + a[1]) - a[2]) * sense + offset;
+    R.dfeas = sqrt(a[3]);
+    R.gap = R.pobj - R.dobj;
+    R.relgap = fabs(R.pobj - R.dobj) / (1.0 + fabs(R.pobj) + fabs(R.dobj));
+    double dscale = sqrt(r[2] + a[4] + a[5]);
+    if (dscale < 1e-8) dscale = 1.0;
+    double pscale = sqrt(a[6]);
+    if (pscale < 1e-8) pscale = 1.0;
+    R.pinf_obj = (R.dobj - offset) / sense / dscale;
+    R.pinf_res = sqrt(a[7]) / dscale;
+    R.dinf_obj = (R.pobj - offset) / sense / pscale;
+    R.dinf_res = sqrt(r[3] + a[8] + a[9]) / pscale;
+  }
+  for (int a = 0; a < kCheckSums; a++) ctl->sums[a] = tot[a];
+  ctl->checks++;
+  ctl->restart_choice = 0;
+  const DevResiduals &L = ctl->res[0], &A = ctl->res[1];
+  int term = -1, term_iterate = 0;
+  if (L.pfeas < ctl->tol_p && L.dfeas < ctl->tol_d && L.relgap < ctl->tol_gap) { term = 0; term_iterate = 0; }
+  else if (A.pfeas < ctl->tol_p && A.dfeas < ctl->tol_d && A.relgap < ctl->tol_gap) { term = 0; term_iterate = 1; }
+  else {
+    const double ft = 1e-8;   // dFeasTol, cupdlp_utils.c:889
+    bool inf = false;
+    for (int t = 0; t < 2; t++) {
+      const DevResiduals& R = ctl->res[t];
+      if (R.pinf_obj > 0.0 && R.pinf_res < ft * R.pinf_obj) inf = true;
+      if (R.dinf_obj < 0.0 && R.dinf_res < -ft * R.dinf_obj) inf = true;
+    }
+    if (inf) term = 3;                                              // INFEASIBLE_OR_UNBOUNDED
+    else if (ctl->time_flag && *ctl->time_flag) term = 4;           // TIMELIMIT_OR_ITERLIMIT
+    else if (st->iter >= ctl->iter_limit - 1) term = 4;
+  }
+  if (term >= 0) {
+    trace_row_dev(ctl, st, 0);
+    ctl->term_iterate = term_iterate;
+    __threadfence();
+    ctl->term = term;   // from here on every kernel of the solve is a no-op
+    return;
+  }
+  if (ctl->restart_on) ctl->restart_choice = decide_restart_dev(st, ctl);
+}
+
+// C5: PDHG_Restart_Iterate_GPU (cupdlp_proj.c:88-148) -- the vector part.  acc 0: |x - x_lastRestart|^2, 1: |y - y_lr|^2
+__global__ void __launch_bounds__(kThreads)
+restart_sweep_kernel(int n, int m, double* __restrict__ x0, double* __restrict__ x1, double* __restrict__ aty0,
+                     double* __restrict__ aty1, const double* __restrict__ xavg, const double* __restrict__ atyavg,
+                     double* __restrict__ xsum, double* __restrict__ xlr, double* __restrict__ y0, double* __restrict__ y1,
+                     double* __restrict__ ax0, double* __restrict__ ax1, const double* __restrict__ yavg,
+                     const double* __restrict__ axavg, double* __restrict__ ysum, double* __restrict__ ylr,
+                     const PdhgState* __restrict__ st, const SolveCtl* __restrict__ ctl, ReduceScratch rs) {
+  if (!check_live(st, ctl) || ctl->restart_choice == 0) return;
+  const bool to_avg = ctl->restart_choice == 1;
+  const int cur = st->cur;
+  double* __restrict__ x = cur ? x1 : x0;
+  double* __restrict__ aty = cur ? aty1 : aty0;
+  double* __restrict__ y = cur ? y1 : y0;
+  double* __restrict__ ax = cur ? ax1 : ax0;
+  double acc[2] = {0.0, 0.0};
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    double v = x[i];
+    if (to_avg) { v = xavg[i]; x[i] = v; aty[i] = atyavg[i]; }
+    xsum[i] = 0.0;
+    const double d = v + -1.0 * xlr[i];
+    acc[0] += d * d;
+    xlr[i] = v;
+  }
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < m; i += stride) {
+    double v = y[i];
+    if (to_avg) { v = yavg[i]; y[i] = v; ax[i] = axavg[i]; }
+    ysum[i] = 0.0;
+    const double d = v + -1.0 * ylr[i];
+    acc[1] += d * d;
+    ylr[i] = v;
+  }
+  block_partials<2>(acc, rs);
+}
+
+// C6: the scalar part of the restart (PDHG_Compute_Step_Size_Ratio, cupdlp_step.c:147-176), then the bookkeeping the
+// host loop does after a check: trace row, next check iteration (cupdlp_solver.c:953-962), step-rule power tables
+constexpr int kFinishThreads = 128;
+static_assert(kFinishThreads == kPowTab, "one thread per power-table entry");
+__global__ void __launch_bounds__(kFinishThreads)
+check_finish_kernel(PdhgState* __restrict__ st, SolveCtl* __restrict__ ctl, const double* __restrict__ prst, int nbs) {
+  if (!check_live(st, ctl)) return;
+  __shared__ double sm[2][kFinishThreads / 32];
+  const int choice = ctl->restart_choice;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (choice) {
+    for (int a = 0; a < 2; a++) {
+      double s = 0.0;
+      for (int i = threadIdx.x; i < nbs; i += kFinishThreads) s += prst[(size_t)a * nbs + i];
+      s = warp_sum(s);
+      if (lane == 0) sm[a][wid] = s;
+    }
+  }
+  const int step_iter = st->step_iter;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (choice) {
+      double d2[2];
+      for (int a = 0; a < 2; a++) { double s = 0.0; for (int w = 0; w < kFinishThreads / 32; w++) s += sm[a][w]; d2[a] = s; }
+      const DevResiduals& R = choice == 1 ? ctl->res[1] : ctl->res[0];
+      ctl->pf_lr = R.pfeas; ctl->df_lr = R.dfeas; ctl->gap_lr = R.gap;
+      const double mean = sqrt(st->tau * st->sigma);
+      const double dxn = sqrt(d2[0]), dyn = sqrt(d2[1]);
+      double beta = st->beta;
+      if (fmin(dxn, dyn) > 1e-10) {
+        const double upd = dyn / dxn;
+        const double lg = 0.5 * log(upd) + 0.5 * log(sqrt(beta));
+        beta = exp(lg) * exp(lg);
+      }
+      st->beta = beta;
+      st->tau = mean / sqrt(beta);
+      st->sigma = st->tau * beta;
+      st->sum_step = 0.0;
+      ctl->last_restart_iter = st->iter;
+      ctl->restarts++;
+      // arm the next pass (start of PDHG_Update_Iterate_Adaptive_Step_Size, cupdlp_step.c:230-242)
+      st->eta = sqrt(st->tau * st->sigma);
+      if (st->adaptive) { st->tau_try = st->eta / sqrt(beta); st->sigma_try = st->eta * sqrt(beta); }
+      else { st->tau_try = st->tau; st->sigma_try = st->sigma; }
+    }
+    trace_row_dev(ctl, st, choice);
+    ctl->restart_choice = 0;
+    st->pending = 0;        // the average flush consumed the pending weight (or the sums were just cleared)
+    st->accepted_last = 0;
+    const int it = st->iter, lim = ctl->iter_limit, iv = ctl->interval;
+    int next = it + 1;
+    while (!(next < 10 || next % iv == 0 || next == lim - 1)) next++;
+    st->stop_iter = next;
+    st->pow_base = step_iter;
+  }
+  // (k+1)^-0.3, (k+1)^-0.6 for k = step_iter + 1 + t  (cupdlp_step.c:279-284)
+  const double k = (double)(step_iter + 1 + (int)threadIdx.x);
+  st->pow_red[threadIdx.x] = pow(k + 1.0, -0.3);
+  st->pow_grow[threadIdx.x] = pow(k + 1.0, -0.6);
+}
+
 // ==================================================================== launchers
 // plain <<<>>> launch, or (flags bit 1) a launch with the programmatic-stream-serialization attribute: the grid may be
 // scheduled while its predecessor in the stream is still running; the kernel then waits in pdl_entry()
@@ -1152,6 +1489,49 @@ void launch_step_rule(cudaStream_t s, PdhgState* st, ReduceScratch r1, int nb1, 
 }
 
 int primal_step_grid(int n) { return ew_grid((n + 1) / 2); }
+
+// ---- device-side check iteration
+void launch_check_avg_x(cudaStream_t s, int n, const double* x0, const double* x1, double* xsum, double* xavg,
+                        const PdhgState* st, const SolveCtl* ctl) {
+  if (n > 0) check_avg_x_kernel<<<ew_grid(n), kThreads, 0, s>>>(n, x0, x1, xsum, xavg, st, ctl);
+}
+void launch_spmv_check_rows(cudaStream_t s, const DevSell& A, const PdhgState* st, const SolveCtl* ctl, const double* xavg,
+                            const double* y0, const double* y1, const double* ax0, const double* ax1, double* ysum,
+                            double* yavg, double* axavg, const double* b, const double* rsc, int neq, ReduceScratch rs) {
+  if (A.nblocks_body + A.nsegs == 0) return;
+  CheckRowEpilogue e{};
+  e.st = st; e.ctl = ctl; e.xavg = xavg; e.y0 = y0; e.y1 = y1; e.ax0 = ax0; e.ax1 = ax1; e.ysum = ysum; e.yavg = yavg;
+  e.axavg = axavg; e.b = b; e.rsc = rsc; e.neq = neq;
+  rs.terms = nullptr; rs.flags = 0;
+  spmv_sell_kernel<CheckRowEpilogue><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, rs);
+}
+void launch_spmv_check_cols(cudaStream_t s, const DevSell& AT, const PdhgState* st, const SolveCtl* ctl, const double* yavg,
+                            const double* x0, const double* x1, const double* aty0, const double* aty1, const double* xavg,
+                            double* atyavg, const double* c, const double* lo, const double* up, const double* cs,
+                            ReduceScratch rs) {
+  if (AT.nblocks_body + AT.nsegs == 0) return;
+  CheckColEpilogue e{};
+  e.st = st; e.ctl = ctl; e.yavg = yavg; e.x0 = x0; e.x1 = x1; e.aty0 = aty0; e.aty1 = aty1; e.xavg = xavg;
+  e.atyavg = atyavg; e.c = c; e.lo = lo; e.up = up; e.cs = cs;
+  rs.terms = nullptr; rs.flags = 0;
+  spmv_sell_kernel<CheckColEpilogue><<<AT.nblocks_body + AT.nsegs, kThreads, 0, s>>>(AT, e, rs);
+}
+void launch_check_decide(cudaStream_t s, PdhgState* st, SolveCtl* ctl, const double* prow, int nbr, const double* pcol,
+                         int nbc) {
+  check_decide_kernel<<<1, kStepThreads, 0, s>>>(st, ctl, prow, nbr, pcol, nbc);
+}
+int restart_sweep_grid(int n, int m) { return ew_grid(n > m ? n : m); }
+void launch_restart_sweep(cudaStream_t s, int n, int m, double* x0, double* x1, double* aty0, double* aty1,
+                          const double* xavg, const double* atyavg, double* xsum, double* xlr, double* y0, double* y1,
+                          double* ax0, double* ax1, const double* yavg, const double* axavg, double* ysum, double* ylr,
+                          const PdhgState* st, const SolveCtl* ctl, ReduceScratch rs) {
+  rs.terms = nullptr; rs.flags = 0;
+  restart_sweep_kernel<<<restart_sweep_grid(n, m), kThreads, 0, s>>>(n, m, x0, x1, aty0, aty1, xavg, atyavg, xsum, xlr, y0,
+                                                                    y1, ax0, ax1, yavg, axavg, ysum, ylr, st, ctl, rs);
+}
+void launch_check_finish(cudaStream_t s, PdhgState* st, SolveCtl* ctl, const double* prst, int nbs) {
+  check_finish_kernel<<<1, kFinishThreads, 0, s>>>(st, ctl, prst, nbs);
+}
 
 
 void launch_average(cudaStream_t s, int len, const double* v, double* sum, double* avg, int pending, double w,

@@ -69,6 +69,25 @@ void launch_diff_norm2(cudaStream_t s, int len, const double* a, const double* b
 void launch_scale(cudaStream_t s, int len, double* v, double w);
 void launch_fill(cudaStream_t s, int len, double* v, double w);
 
+// ---- device-side check iteration (tree mode, one GPU): see pdhg_kernels.cu "device-side check iteration"
+void launch_check_avg_x(cudaStream_t s, int n, const double* x0, const double* x1, double* xsum, double* xavg,
+                        const PdhgState* st, const SolveCtl* ctl);
+void launch_spmv_check_rows(cudaStream_t s, const DevSell& A, const PdhgState* st, const SolveCtl* ctl, const double* xavg,
+                            const double* y0, const double* y1, const double* ax0, const double* ax1, double* ysum,
+                            double* yavg, double* axavg, const double* b, const double* rsc, int neq, ReduceScratch rs);
+void launch_spmv_check_cols(cudaStream_t s, const DevSell& AT, const PdhgState* st, const SolveCtl* ctl, const double* yavg,
+                            const double* x0, const double* x1, const double* aty0, const double* aty1, const double* xavg,
+                            double* atyavg, const double* c, const double* lo, const double* up, const double* cs,
+                            ReduceScratch rs);
+void launch_check_decide(cudaStream_t s, PdhgState* st, SolveCtl* ctl, const double* prow, int nbr, const double* pcol,
+                         int nbc);
+int restart_sweep_grid(int n, int m);
+void launch_restart_sweep(cudaStream_t s, int n, int m, double* x0, double* x1, double* aty0, double* aty1,
+                          const double* xavg, const double* atyavg, double* xsum, double* xlr, double* y0, double* y1,
+                          double* ax0, double* ax1, const double* yavg, const double* axavg, double* ysum, double* ylr,
+                          const PdhgState* st, const SolveCtl* ctl, ReduceScratch rs);
+void launch_check_finish(cudaStream_t s, PdhgState* st, SolveCtl* ctl, const double* prst, int nbs);
+
 // ---- HiPDLP mode (reflected Halpern PDHG; pdhg_kernels.cu, last section)
 struct HipCheckArgs {
   int n, m, neq, scaled;

@@ -134,6 +134,16 @@ ordered_abs_sums_kernel(int nrows, const int* __restrict__ ptr, const int* __res
   if (lane == 0) out[r] = sum;
 }
 
+// max |a_ij| of an unscaled matrix (scaling switched off: PDHG_Init_Step_Sizes still needs it)
+__global__ void __launch_bounds__(kTpb) abs_max_kernel(int nnz, const double* __restrict__ val, double* __restrict__ amax) {
+  double am = 0.0;
+  const int stride = gridDim.x * kTpb;
+  for (int p = blockIdx.x * kTpb + threadIdx.x; p < nnz; p += stride) { const double a = fabs(val[p]); am = a > am ? a : am; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_down_sync(0xffffffffu, am, o); am = t > am ? t : am; }
+  if ((threadIdx.x & 31) == 0) atomic_max_nonneg(amax, am);
+}
+
 inline int grid_for(long long work) {
   long long g = (work + kTpb - 1) / kTpb;
   if (g < 1) g = 1;
@@ -142,8 +152,13 @@ inline int grid_for(long long work) {
 inline int warp_grid(int rows) { return (int)(((long long)rows * 32 + kTpb - 1) / kTpb); }
 }  // namespace
 
-void device_scale_ruiz(cudaStream_t s, const DevForm& F, DevScaleScratch& w) {
-  if (F.n > 0) colof_kernel<<<warp_grid(F.n), kTpb, 0, s>>>(F.n, F.cbeg, F.colof);
+void device_abs_max(cudaStream_t s, int nnz, const double* val, double* amax) {
+  cudaMemsetAsync(amax, 0, sizeof(double), s);
+  if (nnz > 0) abs_max_kernel<<<grid_for(nnz), kTpb, 0, s>>>(nnz, val, amax);
+}
+
+void device_scale_ruiz(cudaStream_t s, const DevForm& F, DevScaleScratch& w, bool have_colof) {
+  if (F.n > 0 && !have_colof) colof_kernel<<<warp_grid(F.n), kTpb, 0, s>>>(F.n, F.cbeg, F.colof);
   cudaMemsetAsync(w.cnorm, 0, sizeof(double) * (size_t)(F.n > 0 ? F.n : 1), s);
   cudaMemsetAsync(w.rnorm, 0, sizeof(double) * (size_t)(F.m > 0 ? F.m : 1), s);
   if (F.nnz > 0) first_norms_kernel<<<grid_for(F.nnz), kTpb, 0, s>>>(F.nnz, F.cidx, F.colof, F.cval, w.cnorm, w.rnorm);

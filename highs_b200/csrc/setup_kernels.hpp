@@ -21,7 +21,10 @@ struct DevScaleScratch {
 };
 
 // the 10 Ruiz passes (cupdlp_scaling.c:47-120); needs nothing but the column-major matrix
-void device_scale_ruiz(cudaStream_t s, const DevForm& F, DevScaleScratch& w);
+// have_colof: F.colof is filled already
+void device_scale_ruiz(cudaStream_t s, const DevForm& F, DevScaleScratch& w, bool have_colof = false);
+// *amax = max |val[p]|
+void device_abs_max(cudaStream_t s, int nnz, const double* val, double* amax);
 // the Pock-Chambolle pass (:174-231); rptr[m+1] / rpos[nnz] = device copy of the row-major index of the nonzeros
 void device_scale_pock_chambolle(cudaStream_t s, const DevForm& F, DevScaleScratch& w, const int* rptr, const int* rpos);
 

@@ -73,7 +73,7 @@ ABI_SYMBOLS = [
     "b200pdlp_form_get_vector", "b200pdlp_form_get_csc", "b200pdlp_form_get_csr", "b200pdlp_form_get_row_map",
     "b200pdlp_form_layout_eval", "b200pdlp_p2p_link_local", "b200pdlp_solve_multi",
     "b200pdlp_hipdlp_form_create", "b200pdlp_hipdlp_power_method", "b200pdlp_hipdlp_default_params",
-    "b200pdlp_solve_hipdlp", "b200pdlp_hipdlp_controller_replay",
+    "b200pdlp_solve_hipdlp", "b200pdlp_hipdlp_controller_replay", "b200pdlp_debug_prep_compare", "b200pdlp_release_cache",
 ]
 
 _lib = None
@@ -139,6 +139,9 @@ def lib():
         L.b200pdlp_form_get_row_map.argtypes = [C.c_void_p, _ip, _ip]
         L.b200pdlp_form_get_csr.argtypes = [C.c_void_p, _ip, _ip, _dp]
         L.b200pdlp_form_layout_eval.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, _dp]
+        L.b200pdlp_debug_prep_compare.argtypes = [C.POINTER(CLp), C.c_int32, _dp]
+        L.b200pdlp_release_cache.argtypes = []
+        L.b200pdlp_release_cache.restype = None
         _lib = L
     return _lib
 
@@ -209,6 +212,19 @@ def solve(lp: HighsLp, warm=None, trace_cap: int = 0, **params) -> dict:
     w, wk = _mk_warm(warm)
     _check(L.b200pdlp_solve(C.byref(clp), C.byref(prm), C.byref(w) if w else None, C.byref(res)), "b200pdlp_solve")
     return _result_dict(res, arrays)
+
+
+PREP_ITEMS = ["n", "m", "nnz", "neq", "cbeg", "cidx", "cval", "cost", "lower", "upper", "col_scale", "rhs", "row_scale", "rptr",
+              "rpos", "row_new_idx", "row_class", "rperm", "cperm", "A.slices", "A.col", "A.val", "AT.slices", "AT.col", "AT.val",
+              "A.long", "AT.long", "amax", "norm_cost_relerr", "norm_rhs_relerr", "device_order_vectors", "cols_sorted"]
+
+
+def prep_compare(lp: HighsLp, scaling: int = 1) -> dict:
+    """b200pdlp_debug_prep_compare: the device-resident prologue against its host twin, mismatches per array."""
+    clp, keep = make_clp(lp)
+    rep = np.zeros(32)
+    _check(lib().b200pdlp_debug_prep_compare(C.byref(clp), scaling, _p(rep, _dp)), "b200pdlp_debug_prep_compare")
+    return dict(zip(PREP_ITEMS, rep.tolist()))
 
 
 def hipdlp_controller_replay(norm_cost, norm_rhs, op_norm_sq, tolerance, strategy, sums, restart_sums) -> np.ndarray:

@@ -135,7 +135,7 @@ def getUserParamsFromOptions(options: HighsOptions, timer: HighsTimer) -> dict:
     if options.kkt_tolerance != kDefaultKktTolerance:
         p["tol_primal"] = p["tol_dual"] = p["tol_gap"] = options.kkt_tolerance
     # the reference computes the remaining time (:701-705) but then passes the FULL limit (:707)
-    p["time_limit"] = options.time_limit if options.time_limit < kHighsInf else 0.0
+    p["time_limit"] = options.time_limit if options.time_limit < kHighsInf else -1.0
     restart_on = 1 if (options.pdlp_features_off & kPdlpRestartOff) == 0 else 0
     if options.pdlp_cupdlpc_restart_method == 0:
         restart_on = 0
@@ -199,7 +199,7 @@ def solveLpHiPdlp(options: HighsOptions, timer: HighsTimer, lp: HighsLp, highs_b
     if options.kkt_tolerance != kDefaultKktTolerance:
         tol = options.kkt_tolerance
     params = dict(tolerance=tol, iter_limit=int(min(options.pdlp_iteration_limit, kHighsIInf)),
-                  time_limit=options.time_limit if options.time_limit < kHighsInf else 0.0,
+                  time_limit=options.time_limit if options.time_limit < kHighsInf else -1.0,
                   scaling_mode=options.pdlp_scaling_mode if (options.pdlp_features_off & kPdlpScalingOff) == 0 else 0,
                   ruiz_iterations=options.pdlp_ruiz_iterations,
                   step_size_strategy=0 if options.pdlp_step_size_strategy == 0 else 3,

@@ -67,7 +67,7 @@ typedef struct {
   double tol_primal;         /* D_PRIMAL_TOL */
   double tol_dual;           /* D_DUAL_TOL */
   double tol_gap;            /* D_GAP_TOL */
-  double time_limit;         /* D_TIME_LIM, seconds; <= 0 or inf = none */
+  double time_limit;         /* D_TIME_LIM, seconds; < 0 or inf = none; 0 = already over (the first check ends the run) */
   int32_t scaling;           /* IF_SCALING: 1 = Ruiz x10 + Pock-Chambolle(1) */
   int32_t adaptive_step;     /* E_LINE_SEARCH_METHOD: 1 adaptive, 0 fixed (power method) */
   int32_t restart;           /* E_RESTART_METHOD: 1 on, 0 off */
@@ -77,8 +77,9 @@ typedef struct {
   int32_t graph_passes;      /* PDHG passes captured per CUDA graph; 0 -> check_interval */
   int32_t ordered_max;       /* problems with max(cols,rows) <= this reduce in the reference's
                                 sequential order (bit-identical trajectories); 0 -> 4096, <0 -> off */
-  int32_t device_scaling;    /* 1 = run the Ruiz / Pock-Chambolle scaling passes on the GPU (bit-identical to the host
-                                passes; opt-in until it has been validated on hardware); 0 = host threads */
+  int32_t device_scaling;    /* where the prologue (formulate, scaling, transposition, layouts) runs: 0 = on the device for one
+                                GPU in tree mode (device_prep.cu; host threads otherwise), -1 = always host threads,
+                                1 / 2 = round-1 staged variants (host formulate + device scaling [+ device ELL fill]) */
   int32_t reserved[2];
 } b200pdlp_params;
 
@@ -224,7 +225,7 @@ typedef struct {
   int32_t scaling_mode;       /* pdlp_scaling_mode: bits 1 Ruiz, 2 L2, 4 Pock-Chambolle (default 5); 0 when scaling is off */
   int32_t ruiz_iterations;    /* pdlp_ruiz_iterations (default 10) */
   int32_t step_size_strategy; /* pdlp_step_size_strategy: 0 fixed primal weight, anything else PID */
-  double time_limit;          /* seconds; <= 0 or inf = none */
+  double time_limit;          /* seconds; < 0 or inf = none */
   int32_t ordered_max;        /* as in b200pdlp_params: checks add in the reference's order up to this size */
   int32_t device;             /* CUDA device ordinal; -1 = current */
   int32_t log_level;
@@ -256,6 +257,20 @@ int b200pdlp_form_layout_eval(b200pdlp_form* f, int32_t rank, int32_t world, int
 /* host-only helper (no GPU): nnz-balanced contiguous row partition of the
  * formulated LP; bounds[world+1] receives the row offsets */
 int b200pdlp_partition_rows(const b200pdlp_lp* lp, int32_t world, int32_t* bounds);
+
+/* Test entry point (needs a GPU): run the device-resident prologue (formulate + scale + row index + orderings +
+ * sliced-ELL layouts as kernels, highs_b200/csrc/device_prep.cu) and its host twin (host_prep.cpp) on the same LP and
+ * compare them array by array, bit for bit.  report[k] = number of mismatching entries:
+ *  0-3 n, m, nnz, neq   4 cbeg 5 cidx 6 cval 7 cost 8 lower 9 upper 10 col_scale 11 rhs 12 row_scale (standard-form order)
+ *  13 rptr 14 rpos (row-major index)  15 row_new_idx 16 row_class  17 row ordering 18 column ordering
+ *  19-21 A: slice descriptors (-1: sizes differ), col, val   22-24 the same for A'   25, 26 long-row arrays of A, A'
+ *  27 max|a_ij|  28, 29 relative error of |c|_2, |b|_2 (tree sums vs sequential)  30 vectors in device order
+ *  31 (info) 1 if every column is stored with ascending rows */
+int b200pdlp_debug_prep_compare(const b200pdlp_lp* lp, int32_t scaling, double report[32]);
+
+/* The engine keeps the device blocks of finished solves in a process-wide cache (a solve allocates ~60 buffers; cudaMalloc /
+ * cudaFree would cost more than the prologue).  This returns them to the driver.  B200PDLP_CACHE_MB caps the cache. */
+void b200pdlp_release_cache(void);
 
 const char* b200pdlp_last_error(void);
 int b200pdlp_version(void);

@@ -57,8 +57,7 @@ def term_to_model_status(term_code, iters, iter_limit=2147483647):
 @pytest.fixture(scope="session")
 def engine_lib():
     from highs_b200 import build, engine
-    if not os.path.exists(engine.LIB_PATH):
-        build.build()
+    build.build()   # compares mtimes: rebuilds only what changed, so the tests never run against a stale library
     return engine.lib()
 
 

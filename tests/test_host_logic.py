@@ -14,7 +14,7 @@ def test_option_mapping_matches_wrapper():
     o = pdlp.HighsOptions()
     p = pdlp.getUserParamsFromOptions(o, pdlp.HighsTimer())
     assert p == dict(iter_limit=2147483647, log_level=0, scaling=1, adaptive_step=1, tol_primal=1e-7, tol_dual=1e-7,
-                     tol_gap=1e-7, time_limit=0.0, restart=1)
+                     tol_gap=1e-7, time_limit=-1.0, restart=1)   # no limit: < 0 (0 would end the run at the first check)
     o = pdlp.HighsOptions(kkt_tolerance=1e-4, primal_feasibility_tolerance=1e-9, pdlp_iteration_limit=80,
                           pdlp_features_off=pdlp.kPdlpScalingOff | pdlp.kPdlpAdaptiveStepSizeOff, time_limit=12.5,
                           output_flag=True, log_dev_level=1)
