@@ -51,42 +51,66 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons WHILE the GPU works (B200_PROFILING.md).  NVML is polled from a thread (about
+    10 kHz, so that even a 3 ms timed region gets samples); `mark()` brackets the timed region, whose samples are
+    reported separately from those of the whole measurement phase (warm-up, timed region, per-kernel timing)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.gpu, self.rows, self.marks, self.stop_flag, self.thread, self.err = gpu_index, [], [], False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:   # noqa: BLE001
+            self.err = f"NVML unavailable: {e}"[:160]
+            return
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _poll(self):
+        nv, h = self.nv, self.h
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:   # noqa: BLE001 -- older bindings
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((time.monotonic(), float(mhz), int(rs)))
+            except Exception as e:   # noqa: BLE001
+                self.err = str(e)[:160]
+                return
+
+    def mark(self):
+        self.marks.append(time.monotonic())
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) > 8:
-                for k, nm in enumerate(names):
-                    if r[5 + k].lower().startswith("active"):
-                        reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "no samples"], "samples": 0}
+
+        def summary(rows):
+            names = sorted(k for k, bit in self.REASONS.items() if any(r[2] & bit for r in rows))
+            return {"sm_mhz": float(np.median([r[1] for r in rows])), "min_sm_mhz": float(min(r[1] for r in rows)),
+                    "reasons": names, "samples": len(rows)}
+        out = summary(self.rows)
+        out["sm_max_mhz"] = self.max_mhz
+        out["window"] = "warm-up + timed region + per-kernel timing (GPU busy)"
+        if len(self.marks) >= 2:
+            inside = [r for r in self.rows if self.marks[0] <= r[0] <= self.marks[1]]
+            if inside:
+                out["timed_region"] = summary(inside)
+        return out
 
 
 def ncu_traffic_bytes(kernel_tag):
@@ -130,13 +154,44 @@ def reference_rate(lp_path, iters, limit_a=20):
     if not ob.ref_available():
         return None
     out = []
+    first = None
     for lim in (limit_a, limit_a + iters):
         t = time.monotonic()
         r = ob.run_reference(lp_path=lp_path, options={"pdlp_iteration_limit": lim + 1})
+        first = first or r
         out.append((r["pdlp_iteration_count"], r["run_seconds"], time.monotonic() - t))
     (ia, ta, _), (ib, tb, _) = out
     rate = (ib - ia) / max(tb - ta, 1e-9)
-    return dict(rate=rate, iters=ib - ia, seconds=tb - ta, setup_seconds=ta - ia / rate, runs=out)
+    return dict(rate=rate, iters=ib - ia, seconds=tb - ta, setup_seconds=ta - ia / rate, runs=out, first=first)
+
+
+PARITY_FIELDS = ("objective_function_value", "max_primal_infeasibility", "max_dual_infeasibility", "sum_primal_infeasibilities",
+                 "sum_dual_infeasibilities", "max_complementarity_violation", "primal_dual_objective_error")
+
+
+def parity_block(lp, lp_path, ours, L, ref_run):
+    """The north-star parity criterion on THIS workload: after the same L PDHG iterations from the same start, the
+    reference's CPU pdlp (oracle/_ref, run through Highs::run()) and this engine return iterates whose objective and
+    KKT measures -- both evaluated by the reference's own lpKktCheck (HighsSolution.cpp:1043-1320; ours through
+    ref_driver --kkt-of) -- agree to 1e-6 (1 + |ref|).  (Trajectories differ only by the order of the long sums.)"""
+    from oracle import binding as ob
+    if ours is None or not ob.ref_available():
+        return None
+    try:
+        if ref_run is None:
+            ref_run = ob.run_reference(lp_path=lp_path, options={"pdlp_iteration_limit": L + 1})
+        mine = ob.reference_kkt(lp, ours, model_status_code=14)   # kIterationLimit
+        rows, ok = {}, ours["iters"] == ref_run["pdlp_iteration_count"]
+        for k in PARITY_FIELDS:
+            if k in ref_run and k in mine:
+                a, b = float(mine[k]), float(ref_run[k])
+                good = abs(a - b) <= 1e-6 * (1 + abs(b))
+                rows[k] = {"ours": a, "reference": b, "ok": bool(good)}
+                ok &= good
+        return {"iterations": [ours["iters"], ref_run["pdlp_iteration_count"]], "tolerance": "1e-6 * (1 + |reference|)",
+                "checked_by": "reference lpKktCheck on both solutions", "fields": rows, "ok": bool(ok)}
+    except Exception as e:   # noqa: BLE001 -- the parity block must never break the bench line
+        return {"error": str(e)[:300], "ok": False}
 
 
 def cpu_cores():
@@ -215,6 +270,7 @@ def main():
     ap.add_argument("--workload", default="S3", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity", action="store_true", help="compute the parity block even with --no-cpu-baseline")
     ap.add_argument("--to-tolerance", type=float, default=0.0,
                     help="additionally solve the workload to this kkt_tolerance through the host-buffer call and report the "
                          "wall-clock time to solution (SURVEY.md 8(d)); single GPU / reference arm")
@@ -261,21 +317,22 @@ def main():
             handles = [None] * world
             dist.all_gather_object(handles, prob.p2p_export())
             prob.p2p_import(b"".join(handles))
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     # ---- warm-up: W iterations (also captures the CUDA graphs)
     prob.solve(iter_limit=W + 1)
     use_p2p = world > 1 and os.environ.get("B200PDLP_NO_P2P", "0") != "1"
     if use_p2p:
         prob.p2p_timeline()   # reset the device-side timeline
     # ---- timed: exactly K iterations, inputs resident in HBM
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     barrier()
+    sampler.mark()
     t0 = time.monotonic()
     res = prob.solve(iter_limit=K + 1)
     barrier()
     wall = time.monotonic() - t0
-    clocks = sampler.stop() if rank == 0 else None
+    sampler.mark()
     assert res["iters"] == K, (res["iters"], K)
     timeline = prob.p2p_timeline() if use_p2p else None
     loop_ms = res["loop_device_ms"]
@@ -298,6 +355,12 @@ def main():
     else:
         dom, dom_bytes, dom_name = 1, None, "K2 spmv_blocked<Dual> on the local row block"
     spmv_ms = [prob.bench_spmv(w, 5) and prob.bench_spmv(w, 30) / 30 for w in (0, 1)]
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- parity: L iterations of this engine (same resident problem, all ranks) for the comparison with the reference
+    L_par = 20
+    par_sol = None
+    if not args.no_cpu_baseline or args.parity:
+        par_sol = prob.solve(iter_limit=L_par + 1)
     roofline = None
     if world == 1:
         ach = dom_bytes / (k_us[dom] * 1e-6) / 1e9
@@ -317,23 +380,38 @@ def main():
     tts = None
     if world == 1:
         prob.close()
+        # the caller's HighsLp arrays and HighsSolution storage are page-locked once (cudaHostRegister), outside the
+        # timed call -- the contract's "inputs in pinned host memory"; B200PDLP_BENCH_PAGEABLE=1 leaves them pageable
+        out_arrays = tuple(np.zeros(k) for k in (n, n, m, m))
+        pinned = []
+        if os.environ.get("B200PDLP_BENCH_PAGEABLE", "0") != "1":
+            pinned = engine.pin_arrays(engine.lp_arrays(lp) + list(out_arrays))
+        engine.solve(lp, iter_limit=3, device=local_rank, out_arrays=out_arrays)   # untimed: block cache / first-use paths warm
         t0 = time.monotonic()
-        r2 = engine.solve(lp, iter_limit=K + 1, device=local_rank)
+        r2 = engine.solve(lp, iter_limit=K + 1, device=local_rank, out_arrays=out_arrays)
         e2e_wall = time.monotonic() - t0
         a = lp.a_matrix_
-        h2d = 2 * (12 * nnz + 4 * (n + m)) + 8 * (5 * n + 3 * m)   # both layouts + cost/bounds/scales/x0 + rhs/scale/y0
+        dev_prep = os.environ.get("B200PDLP_DEVICE_PREP", "1") != "0"
+        # device prologue: the HighsLp arrays go up once (CSC + 3 n-vectors + 2 m-vectors); host prologue: both layouts + vectors
+        h2d = (12 * nnz + 4 * (n + 1) + 24 * n + 16 * m) if dev_prep else (2 * (12 * nnz + 4 * (n + m)) + 8 * (5 * n + 3 * m))
         d2h = 8 * (2 * n + 2 * m)
         e2e = {"value": K / e2e_wall, "unit": "iter/s", "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
                "wall_seconds": e2e_wall, "setup_seconds": r2["setup_seconds"], "solve_seconds": r2["solve_seconds"],
-               "note": "one b200pdlp_solve call on host buffers: formulate+scale+layout (host), H2D, K iterations, D2H; "
-                       "bytes are per call divided by K"}
+               "host_buffers": "page-locked (cudaHostRegister, outside the timed call)" if pinned else "pageable",
+               "note": "one b200pdlp_solve call on host buffers: H2D of the HighsLp arrays, prologue (formulate + scaling + "
+                       "transposition + layouts"
+                       + (" on the device" if dev_prep else " on host threads") + "), K iterations, postsolve, D2H of the "
+                       "HighsSolution; bytes are per call divided by K"}
         if args.to_tolerance > 0:
             tol = args.to_tolerance
             t0 = time.monotonic()
-            r3 = engine.solve(lp, tol_primal=tol, tol_dual=tol, tol_gap=tol, iter_limit=2_000_000, device=local_rank)
+            r3 = engine.solve(lp, tol_primal=tol, tol_dual=tol, tol_gap=tol, iter_limit=2_000_000, device=local_rank,
+                              out_arrays=out_arrays)
             tts = {"kkt_tolerance": tol, "seconds": time.monotonic() - t0, "iterations": r3["iters"], "status": r3["term_name"],
                    "objective": lp.objectiveValue(r3["col_value"]), "setup_seconds": r3["setup_seconds"],
                    "solve_seconds": r3["solve_seconds"]}
+        if pinned:
+            engine.unpin_arrays(pinned)
     else:
         # N > 1: host buffers -> row/column shards on every GPU (formulate+scale on every rank, layouts, H2D),
         # communicator + peer-memory setup, K iterations, assembled HighsSolution back on the host
@@ -375,12 +453,14 @@ def main():
         return
     # ---- CPU baseline: the reference itself on this box's host cores (bounded sample)
     cpu = None
-    if not args.no_cpu_baseline:
+    parity = None
+    if not args.no_cpu_baseline or args.parity:
         from highs_b200.lp import write_b2lp
         with tempfile.TemporaryDirectory() as td:
             path = os.path.join(td, "lp.b2lp")
             write_b2lp(path, lp)
-            ref = reference_rate(path, 40 if args.workload != "S2" else 400)
+            ref = reference_rate(path, 40 if args.workload != "S2" else 400, limit_a=L_par) if not args.no_cpu_baseline else None
+            parity = parity_block(lp, path, par_sol, L_par, ref["first"] if ref else None)
         if ref:
             cpu = {"value": ref["rate"], "unit": "iter/s", "cores": 1, "kind": "reference",
                    "host_cores_available": cpu_cores(),
@@ -404,6 +484,7 @@ def main():
         "phase_us": (None if world == 1 else {"primal_shard+allgather": k_us[0], "Ax+dual": k_us[1], "partial_ATy": k_us[2],
                                               "reduce_scatter+step_rule": k_us[3]}),
         "p2p_timeline_us": timeline, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "parity": parity,
     }
     if tts is not None:
         line["time_to_solution"] = tts

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstddef>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -259,7 +260,7 @@ struct b200pdlp_problem {
 
   ~b200pdlp_problem() {
     if (stream) cudaStreamSynchronize(stream);   // the buffers go back to the block cache: nothing may still use them
-    if (dev_form) { prep.release_arrays(); prep.release_form(); }
+    if (dev_form) { prep.A.release(); prep.AT.release(); prep.release_arrays(); prep.release_form(); }   // (A / AT: only if never adopted)
     if (graph_main) cudaGraphExecDestroy(graph_main);
     if (graph_small) cudaGraphExecDestroy(graph_small);
     for (cudaGraphExec_t g : graph_pow2) if (g) cudaGraphExecDestroy(g);
@@ -1298,7 +1299,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
     if (!p->hctl) {
       p->hctl = static_cast<SolveCtl*>(pinned_cache_alloc(sizeof(SolveCtl), false));
       p->htime = static_cast<int*>(pinned_cache_alloc(64, true));
-      p->ctl.alloc(1);
+      p->ctl.alloc(1, false);   // (filled by the copy below; a cudaMemset on the legacy stream would not be ordered against p->stream)
     }
     SolveCtl* c = p->hctl;
     memset(c, 0, sizeof(SolveCtl));
@@ -1313,7 +1314,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
     }
     c->term = -1;
     if (out->trace && out->trace_cap > 0) {
-      if (p->trace_dev.n < (size_t)out->trace_cap * B200PDLP_TRACE_COLS) p->trace_dev.alloc((size_t)out->trace_cap * B200PDLP_TRACE_COLS);
+      if (p->trace_dev.n < (size_t)out->trace_cap * B200PDLP_TRACE_COLS) p->trace_dev.alloc((size_t)out->trace_cap * B200PDLP_TRACE_COLS, false);
       c->trace = p->trace_dev.p; c->trace_cap = out->trace_cap;
     }
     CUDA_OK(cudaMemcpyAsync(p->ctl.p, c, sizeof(SolveCtl), cudaMemcpyHostToDevice, s));
@@ -2033,6 +2034,129 @@ int b200pdlp_spmv_aty(b200pdlp_problem* p, const double* y, double* aty) {
   });
 }
 
+// ---- kernel-level entry points (_primal_step, _dual_step, _residuals): one fused kernel of the hot
+// path on host vectors in standard-form order (H2D, kernel, D2H), single GPU.  They use the problem's iterate buffers as
+// scratch, so a solve on the same handle starts from scratch afterwards (it always does).
+static void kernel_api_state(b200pdlp_problem* p, double tau, double sigma) {
+  PdhgState* h = p->hstate;
+  memset(h, 0, sizeof(PdhgState));
+  h->adaptive = 1; h->beta = 1.0;
+  h->tau = h->tau_try = tau; h->sigma = h->sigma_try = sigma;
+  h->stop_iter = 2147483647;
+  push_state(p);
+}
+static double sum_partials(b200pdlp_problem* p, const ReduceScratch& r, int nb) {   // what K4 does with one accumulator
+  std::vector<double> t((size_t)std::max(nb, 1));
+  if (r.terms) {
+    std::vector<double> terms((size_t)r.len);
+    CUDA_OK(cudaMemcpy(terms.data(), r.terms, (size_t)r.len * sizeof(double), cudaMemcpyDeviceToHost));
+    double s = 0.0;
+    for (double v : terms) s += v;
+    return s;
+  }
+  CUDA_OK(cudaMemcpy(t.data(), r.partials, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost));
+  double s = 0.0;
+  for (int i = 0; i < nb; i++) s += t[i];
+  return s;
+}
+
+int b200pdlp_primal_step(b200pdlp_problem* p, const double* x, const double* aty, double tau, double* x_new, double* dx2) {
+  DeviceGuard dg;
+  return guarded([&] {
+    if (!p || !x || !aty || !x_new) throw Error(B200PDLP_ERR_ARG, "null argument");
+    if (p->world != 1) throw Error(B200PDLP_ERR_ARG, "kernel-level entry points are single-GPU");
+    set_device(p);
+    ensure_host_maps(p);
+    const int n = p->n;
+    std::vector<double> t(n);
+    for (int j = 0; j < n; j++) t[j] = x[p->cperm[j]];
+    CUDA_OK(cudaMemcpyAsync(p->x[0].p, t.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    CUDA_OK(cudaStreamSynchronize(p->stream));
+    for (int j = 0; j < n; j++) t[j] = aty[p->cperm[j]];
+    CUDA_OK(cudaMemcpyAsync(p->aty[0].p, t.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    kernel_api_state(p, tau, tau);
+    const ReduceScratch r1 = p->rs(kSlotK1, n);
+    launch_primal_step(p->stream, n, p->state.p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->cost.p, p->lower.p,
+                       p->upper.p, p->xsum.p, r1);
+    p->launches++;
+    CUDA_OK(cudaMemcpyAsync(t.data(), p->x[1].p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CUDA_OK(cudaStreamSynchronize(p->stream));
+    for (int j = 0; j < n; j++) x_new[p->cperm[j]] = t[j];
+    if (dx2) *dx2 = sum_partials(p, r1, primal_step_grid(n));
+    CUDA_OK(cudaGetLastError());
+  });
+}
+
+int b200pdlp_dual_step(b200pdlp_problem* p, const double* x_new, const double* y, const double* ax, double sigma,
+                       double* y_new, double* ax_new, double* dy2) {
+  DeviceGuard dg;
+  return guarded([&] {
+    if (!p || !x_new || !y || !ax || !y_new || !ax_new) throw Error(B200PDLP_ERR_ARG, "null argument");
+    if (p->world != 1) throw Error(B200PDLP_ERR_ARG, "kernel-level entry points are single-GPU");
+    set_device(p);
+    ensure_host_maps(p);
+    const int n = p->n, m = p->m;
+    std::vector<double> t(std::max(n, m));
+    cudaStream_t s = p->stream;
+    for (int j = 0; j < n; j++) t[j] = x_new[p->cperm[j]];
+    CUDA_OK(cudaMemcpyAsync(p->x[1].p, t.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    for (int i = 0; i < m; i++) t[i] = y[p->rperm[i]];
+    CUDA_OK(cudaMemcpyAsync(p->y[0].p, t.data(), (size_t)m * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    for (int i = 0; i < m; i++) t[i] = ax[p->rperm[i]];
+    CUDA_OK(cudaMemcpyAsync(p->ax[0].p, t.data(), (size_t)m * sizeof(double), cudaMemcpyHostToDevice, s));
+    kernel_api_state(p, sigma, sigma);
+    const ReduceScratch r2 = p->rs(kSlotK2, m);
+    launch_spmv_dual(s, p->A.dev, p->state.p, p->x[0].p, p->x[1].p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->rhs.p,
+                     p->ysum.p, p->neq_local, 0, r2);
+    p->launches++;
+    CUDA_OK(cudaMemcpyAsync(t.data(), p->y[1].p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    for (int i = 0; i < m; i++) y_new[p->rperm[i]] = t[i];
+    CUDA_OK(cudaMemcpyAsync(t.data(), p->ax[1].p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    for (int i = 0; i < m; i++) ax_new[p->rperm[i]] = t[i];
+    if (dy2) *dy2 = sum_partials(p, r2, p->A.grid());
+    CUDA_OK(cudaGetLastError());
+  });
+}
+
+// out[10]: pobj, dobj, pfeas, dfeas, gap, relgap, primal-ray objective, primal-ray residual, dual-ray objective,
+// dual-ray residual of the iterate (x, y) (PDHG_Compute_Residuals / _Infeas_Residuals); A x and A'y are formed here
+int b200pdlp_residuals(b200pdlp_problem* p, const double* x, const double* y, double out[10]) {
+  DeviceGuard dg;
+  return guarded([&] {
+    if (!p || !x || !y || !out) throw Error(B200PDLP_ERR_ARG, "null argument");
+    if (p->world != 1) throw Error(B200PDLP_ERR_ARG, "kernel-level entry points are single-GPU");
+    set_device(p);
+    ensure_host_maps(p);
+    const int n = p->n, m = p->m;
+    std::vector<double> t(std::max(n, m));
+    cudaStream_t s = p->stream;
+    for (int j = 0; j < n; j++) t[j] = x[p->cperm[j]];
+    CUDA_OK(cudaMemcpyAsync(p->x[0].p, t.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    for (int i = 0; i < m; i++) t[i] = y[p->rperm[i]];
+    CUDA_OK(cudaMemcpyAsync(p->y[0].p, t.data(), (size_t)m * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    // the check machinery with sums = the iterate itself: "average" == current
+    PdhgState* h = p->hstate;
+    memset(h, 0, sizeof(PdhgState));
+    h->sum_step = 1.0; h->beta = 1.0;
+    push_state(p);
+    CUDA_OK(cudaMemcpyAsync(p->xsum.p, p->x[0].p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(p->ysum.p, p->y[0].p, (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    full_ax(p, p->x[0].p, p->ax[0].p);
+    full_aty(p, p->y[0].p, p->aty[0].p);
+    const CheckResult c = run_check(p, false);
+    const Residuals& R = c.it[0];
+    out[0] = R.pobj; out[1] = R.dobj; out[2] = R.pfeas; out[3] = R.dfeas; out[4] = R.gap; out[5] = R.relgap;
+    out[6] = R.pinf_obj; out[7] = R.pinf_res; out[8] = R.dinf_obj; out[9] = R.dinf_res;
+    CUDA_OK(cudaGetLastError());
+  });
+}
+
 int b200pdlp_bench_spmv(b200pdlp_problem* p, int32_t which, int32_t reps, float* ms_total) {
   DeviceGuard dg;
   return guarded([&] {
@@ -2638,6 +2762,21 @@ int b200pdlp_debug_prep_compare(const b200pdlp_lp* lp, int32_t scaling, double r
 }
 
 void b200pdlp_release_cache(void) { dev_cache_release(); }
+
+// page-lock / unlock caller memory (cudaHostRegister): H2D / D2H copies of registered buffers run at PCIe speed and
+// truly asynchronously; pageable buffers are staged by the driver at a fraction of that
+int b200pdlp_host_register(void* ptr, size_t bytes) {
+  return guarded([&] {
+    if (!ptr || bytes == 0) throw Error(B200PDLP_ERR_ARG, "null argument");
+    CUDA_OK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  });
+}
+int b200pdlp_host_unregister(void* ptr) {
+  return guarded([&] {
+    if (!ptr) throw Error(B200PDLP_ERR_ARG, "null argument");
+    CUDA_OK(cudaHostUnregister(ptr));
+  });
+}
 
 int b200pdlp_partition_rows(const b200pdlp_lp* lp, int32_t world, int32_t* bounds) {
   return guarded([&] {

@@ -74,6 +74,7 @@ ABI_SYMBOLS = [
     "b200pdlp_form_layout_eval", "b200pdlp_p2p_link_local", "b200pdlp_solve_multi",
     "b200pdlp_hipdlp_form_create", "b200pdlp_hipdlp_power_method", "b200pdlp_hipdlp_default_params",
     "b200pdlp_solve_hipdlp", "b200pdlp_hipdlp_controller_replay", "b200pdlp_debug_prep_compare", "b200pdlp_release_cache",
+    "b200pdlp_host_register", "b200pdlp_host_unregister", "b200pdlp_primal_step", "b200pdlp_dual_step", "b200pdlp_residuals",
 ]
 
 _lib = None
@@ -142,6 +143,11 @@ def lib():
         L.b200pdlp_debug_prep_compare.argtypes = [C.POINTER(CLp), C.c_int32, _dp]
         L.b200pdlp_release_cache.argtypes = []
         L.b200pdlp_release_cache.restype = None
+        L.b200pdlp_host_register.argtypes = [C.c_void_p, C.c_size_t]
+        L.b200pdlp_host_unregister.argtypes = [C.c_void_p]
+        L.b200pdlp_primal_step.argtypes = [C.c_void_p, _dp, _dp, C.c_double, _dp, _dp]
+        L.b200pdlp_dual_step.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp]
+        L.b200pdlp_residuals.argtypes = [C.c_void_p, _dp, _dp, _dp]
         _lib = L
     return _lib
 
@@ -203,12 +209,16 @@ def _mk_warm(warm):
     return CWarm(_p(arrs[0], _dp), _p(arrs[1], _dp), _p(arrs[2], _dp)), arrs
 
 
-def solve(lp: HighsLp, warm=None, trace_cap: int = 0, **params) -> dict:
-    """b200pdlp_solve: host buffers in, host buffers out (formulate+scale+upload+PDHG+download)."""
+def solve(lp: HighsLp, warm=None, trace_cap: int = 0, out_arrays=None, **params) -> dict:
+    """b200pdlp_solve: host buffers in, host buffers out (prologue + upload + PDHG + download).
+    out_arrays = (col_value, col_dual, row_value, row_dual): caller-owned (e.g. page-locked) result storage."""
     L = lib()
     clp, keep = make_clp(lp)
     prm = make_params(**params)
     res, arrays = _mk_result(lp, trace_cap)
+    if out_arrays is not None:
+        arrays = tuple(out_arrays) + arrays[4:]
+        res.col_value, res.col_dual, res.row_value, res.row_dual = (_p(a, _dp) for a in arrays[:4])
     w, wk = _mk_warm(warm)
     _check(L.b200pdlp_solve(C.byref(clp), C.byref(prm), C.byref(w) if w else None, C.byref(res)), "b200pdlp_solve")
     return _result_dict(res, arrays)
@@ -225,6 +235,25 @@ def prep_compare(lp: HighsLp, scaling: int = 1) -> dict:
     rep = np.zeros(32)
     _check(lib().b200pdlp_debug_prep_compare(C.byref(clp), scaling, _p(rep, _dp)), "b200pdlp_debug_prep_compare")
     return dict(zip(PREP_ITEMS, rep.tolist()))
+
+
+def lp_arrays(lp: HighsLp):
+    a = lp.a_matrix_
+    return [a.start_, a.index_, a.value_, lp.col_cost_, lp.col_lower_, lp.col_upper_, lp.row_lower_, lp.row_upper_]
+
+
+def pin_arrays(arrays) -> list:
+    """cudaHostRegister the given numpy arrays (b200pdlp_host_register); returns the ones that were pinned."""
+    done = []
+    for a in arrays:
+        if a.nbytes and lib().b200pdlp_host_register(a.ctypes.data_as(C.c_void_p), a.nbytes) == 0:
+            done.append(a)
+    return done
+
+
+def unpin_arrays(arrays):
+    for a in arrays:
+        lib().b200pdlp_host_unregister(a.ctypes.data_as(C.c_void_p))
 
 
 def hipdlp_controller_replay(norm_cost, norm_rhs, op_norm_sq, tolerance, strategy, sums, restart_sums) -> np.ndarray:
@@ -329,6 +358,27 @@ class Problem:
         out = np.zeros(self.n)
         _check(lib().b200pdlp_spmv_aty(self._h, _p(y, _dp), _p(out, _dp)), "b200pdlp_spmv_aty")
         return out
+
+    def primal_step(self, x, aty, tau):
+        """K1 on host vectors (standard-form order): returns (x_new, |x - x_new|^2)"""
+        x, aty = (np.ascontiguousarray(v, dtype=np.float64) for v in (x, aty))
+        out, d = np.zeros(self.n), C.c_double()
+        _check(lib().b200pdlp_primal_step(self._h, _p(x, _dp), _p(aty, _dp), float(tau), _p(out, _dp), C.byref(d)), "b200pdlp_primal_step")
+        return out, d.value
+
+    def dual_step(self, x_new, y, ax, sigma):
+        """K2 on host vectors: returns (y_new, ax_new = A x_new, |y - y_new|^2)"""
+        x_new, y, ax = (np.ascontiguousarray(v, dtype=np.float64) for v in (x_new, y, ax))
+        yn, axn, d = np.zeros(self.m), np.zeros(self.m), C.c_double()
+        _check(lib().b200pdlp_dual_step(self._h, _p(x_new, _dp), _p(y, _dp), _p(ax, _dp), float(sigma), _p(yn, _dp), _p(axn, _dp),
+                                        C.byref(d)), "b200pdlp_dual_step")
+        return yn, axn, d.value
+
+    def residuals(self, x, y) -> dict:
+        x, y = (np.ascontiguousarray(v, dtype=np.float64) for v in (x, y))
+        out = np.zeros(10)
+        _check(lib().b200pdlp_residuals(self._h, _p(x, _dp), _p(y, _dp), _p(out, _dp)), "b200pdlp_residuals")
+        return dict(zip(("pobj", "dobj", "pfeas", "dfeas", "gap", "relgap", "pinf_obj", "pinf_res", "dinf_obj", "dinf_res"), out.tolist()))
 
     def bench_spmv(self, which: int, reps: int) -> float:
         ms = C.c_float()

@@ -18,6 +18,7 @@
 #ifndef B200PDLP_H_
 #define B200PDLP_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -157,6 +158,19 @@ int b200pdlp_problem_get_csr(const b200pdlp_problem* p, int32_t* rowptr, int32_t
  * ax[m_local] = A_local x[n];  aty[n] = A_local^T y[m_local] */
 int b200pdlp_spmv_ax(b200pdlp_problem* p, const double* x, double* ax);
 int b200pdlp_spmv_aty(b200pdlp_problem* p, const double* y, double* aty);
+/* single FUSED kernels of the hot path on host vectors in standard-form order (parity tests; single GPU).  Reference
+ * analogues: the extern "C" launchers of highs/pdlp/cupdlp/cuda/cupdlp_cudalinalg.cu:13-386.
+ *  primal step (K1): x_new = proj_[l,u](x - tau (c - aty))   (PDHG_primalGradientStep, cupdlp_step.c:16-40), *dx2 = |x - x_new|^2
+ *  dual step (K2):   ax_new = A x_new;  y_new = y + sigma (b - 2 ax_new + ax), max(.,0) on inequality rows
+ *                    (PDHG_dualGradientStep, cupdlp_step.c:43-69), *dy2 = |y - y_new|^2
+ *  residuals:        out[10] = pobj, dobj, primal feasibility, dual feasibility, gap, relative gap, primal-ray objective
+ *                    and residual, dual-ray objective and residual of (x, y) (cupdlp_solver.c:12-204, :206-471)
+ * all on the SCALED standard form the problem holds (b200pdlp_problem_get_vector / get_csr return it). */
+int b200pdlp_primal_step(b200pdlp_problem* p, const double* x, const double* aty, double tau, double* x_new, double* dx2);
+int b200pdlp_dual_step(b200pdlp_problem* p, const double* x_new, const double* y, const double* ax, double sigma,
+                       double* y_new, double* ax_new, double* dy2);
+int b200pdlp_residuals(b200pdlp_problem* p, const double* x, const double* y, double out[10]);
+
 /* device-pointer variants on the problem's stream (bench roofline loop):
  * time `reps` back-to-back launches with CUDA events; returns ms in *ms_total */
 int b200pdlp_bench_spmv(b200pdlp_problem* p, int32_t which /*0 Ax, 1 ATy*/, int32_t reps, float* ms_total);
@@ -271,6 +285,12 @@ int b200pdlp_debug_prep_compare(const b200pdlp_lp* lp, int32_t scaling, double r
 /* The engine keeps the device blocks of finished solves in a process-wide cache (a solve allocates ~60 buffers; cudaMalloc /
  * cudaFree would cost more than the prologue).  This returns them to the driver.  B200PDLP_CACHE_MB caps the cache. */
 void b200pdlp_release_cache(void);
+
+/* Page-lock / unlock caller memory (cudaHostRegister) so that the copies of b200pdlp_solve run at PCIe speed; optional
+ * (pageable buffers work, staged by the driver).  A host application that keeps its HighsLp / HighsSolution vectors for
+ * many solves registers them once. */
+int b200pdlp_host_register(void* ptr, size_t bytes);
+int b200pdlp_host_unregister(void* ptr);
 
 const char* b200pdlp_last_error(void);
 int b200pdlp_version(void);
