@@ -467,6 +467,8 @@ void make_perm_device(cudaStream_t s, Tmp& tmp, int len, int boundary, const int
 }  // namespace
 
 void DevicePrologue::run(cudaStream_t s, const b200pdlp_lp& lp, bool do_scale, int long_threshold) {
+  NvtxRange nvtx("b200pdlp: device prologue");
+  nvtxRangePushA("H2D of the HighsLp arrays + formulate");
   Tmp tmp;
   tmp.stream = s;
   const int n0 = lp.num_col, m = lp.num_row, nnz0 = lp.a_start[n0];
@@ -557,6 +559,8 @@ void DevicePrologue::run(cudaStream_t s, const b200pdlp_lp& lp, bool do_scale, i
   sumsq(cost, n, dsc + 0, 0);
   sumsq(rhs, m, dsc + 1, 1);
 
+  nvtxRangePop();
+  nvtxRangePushA("row-major index (radix sort)");
   // ---- row-major index of the nonzeros: stable radix sort of the positions by row (csc2csr, cupdlp_utils.c:1222-1254)
   int* rptr = tmp.get<int>(m + 2);
   int* rpos = tmp.get<int>(nnz);
@@ -590,6 +594,8 @@ void DevicePrologue::run(cudaStream_t s, const b200pdlp_lp& lp, bool do_scale, i
     PREP_OK(cub::DeviceRadixSort::SortPairs(w, bytes, k_in, k_out, rpos, cpos, nnz, 0, end_bit, s));
   }
 
+  nvtxRangePop();
+  nvtxRangePushA("Ruiz + Pock-Chambolle scaling");
   // ---- PDHG_Scale_Data (setup_kernels.cu): 10 Ruiz passes + Pock-Chambolle, bit-identical to host_prep.cpp::scale
   double* cs = tmp.get<double>(n);
   double* cnorm = tmp.get<double>(n);
@@ -609,6 +615,8 @@ void DevicePrologue::run(cudaStream_t s, const b200pdlp_lp& lp, bool do_scale, i
   sumsq(cost, n, dsc + 2, 2);
   sumsq(rhs, m, dsc + 3, 3);
 
+  nvtxRangePop();
+  nvtxRangePushA("orderings + sliced-ELL layouts");
   // ---- device orderings and sliced-ELL plans
   arr.rperm = keep<int>(m); arr.rinv = keep<int>(m);
   arr.cperm = keep<int>(n); arr.cinv = keep<int>(n);
@@ -726,6 +734,7 @@ void DevicePrologue::run(cudaStream_t s, const b200pdlp_lp& lp, bool do_scale, i
     form.rhs = dup_d(rhs, m); form.rowscale = dup_d(rowscale, m);
     form.rptr = dup_i(rptr, m + 1); form.rpos = dup_i(rpos, nnz);
   }
+  nvtxRangePop();
   int tb = 0;
   PREP_OK(cudaMemcpyAsync(&tb, too_big, sizeof(int), cudaMemcpyDeviceToHost, s));
   PREP_OK(cudaStreamSynchronize(s));   // the temporaries go back to the cache below: everything that reads them is done

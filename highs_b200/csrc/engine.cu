@@ -408,6 +408,7 @@ static void alloc_host_mirrors(b200pdlp_problem* p) {
 // shared_form != nullptr: the standard form was formulated and scaled already (by another rank of this process)
 static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, int rank, int world, b200pdlp_problem* p,
                            const StdForm* shared_form = nullptr) {
+  NvtxRange nvtx("b200pdlp: prologue (host threads) + upload");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -534,6 +535,7 @@ static bool use_device_prep(const b200pdlp_lp& lp, const b200pdlp_params& prm, i
 }
 
 static void create_problem_device(const b200pdlp_lp& lp, const b200pdlp_params& prm, b200pdlp_problem* p) {
+  NvtxRange nvtx("b200pdlp: prologue (device)");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -842,6 +844,7 @@ static void enqueue_check_dev(b200pdlp_problem* p, bool timed_out_local) {
 // PDHG_Compute_Average_Iterate + PDHG_Compute_Residuals + PDHG_Compute_Infeas_Residuals
 // (cupdlp_step.c:377-420, cupdlp_solver.c:473-529, :433-471) for current and average iterate
 static CheckResult run_check(b200pdlp_problem* p, bool timed_out_local) {
+  NvtxRange nvtx("b200pdlp: check iteration (host-driven)");
   cudaStream_t s = p->stream;
   PdhgState* h = p->hstate;
   const StdForm& f = p->form;
@@ -984,6 +987,7 @@ static int decide_restart(const PdhgState* h, const CheckResult& c, RestartMemo&
 
 // PDHG_Restart_Iterate_GPU (cupdlp_proj.c:88-148) + PDHG_Compute_Step_Size_Ratio (cupdlp_step.c:147-176)
 static void do_restart(b200pdlp_problem* p, int choice, const CheckResult& c, RestartMemo& mm) {
+  NvtxRange nvtx("b200pdlp: restart");
   cudaStream_t s = p->stream;
   PdhgState* h = p->hstate;
   const int n = p->nl, ml = p->ml, cur = h->cur;
@@ -1146,6 +1150,8 @@ static void enqueue_passes_device(b200pdlp_problem* p, int d) {
 }
 
 static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, const b200pdlp_warm* warm, b200pdlp_result* out) {
+  NvtxRange nvtx("b200pdlp: solve");
+  nvtxRangePushA("b200pdlp: initial point + graphs");
   using clk = std::chrono::steady_clock;
   set_device(p);
   const auto t_begin = clk::now();
@@ -1278,6 +1284,8 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   }
   p->kernels_per_pass = p->world == 1 ? 4 : ((p->p2p && p->p2p_pull) ? 5 : 6);   // ours; NCCL kernels not counted
   lap("solve", "graph capture");
+  nvtxRangePop();
+  nvtxRangePushA("b200pdlp: PDHG loop");
 
   const double tol_p = prm.tol_primal * (1.0 + f.norm_rhs), tol_d = prm.tol_dual * (1.0 + f.norm_cost);
   RestartMemo memo;
@@ -1329,6 +1337,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
     int pred_iter = 0, carry = 0;   // carry: passes still owed before the next check (after a re-synchronisation)
     while (true) {
       size_t nev = 0;
+      NvtxRange nvtx_batch("b200pdlp: batch of [check, passes] rounds");
       auto ev = [&]() -> cudaEvent_t {
         if (nev == evs.size()) evs.emplace_back(new CudaEvent());
         return *evs[nev++];
@@ -1468,6 +1477,8 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   const double solve_seconds = std::chrono::duration<double>(clk::now() - t_loop).count();
   out->loop_device_ms = loop_ms;
   lap("solve", "iterations");
+  nvtxRangePop();
+  NvtxRange nvtx_post("b200pdlp: postsolve + download");
 
   // ---- PDHG_PostSolve (cupdlp_solver.c:1281-1435)
   const int cur = h->cur;
@@ -1699,6 +1710,7 @@ static void hip_check(b200pdlp_problem* p, const double* x, const double* y, int
 }
 
 static void solve_hipdlp_on_device(b200pdlp_problem* p, const b200pdlp_lp& lp, const b200pdlp_hipdlp_params& prm, b200pdlp_result* out) {
+  NvtxRange nvtx("b200pdlp: solve (HiPDLP mode)");
   using clk = std::chrono::steady_clock;
   set_device(p);
   const auto t_begin = clk::now();

@@ -26,6 +26,18 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// NVTX ranges: phases of a solve show up by name in Nsight Systems / ncu --nvtx; header-only NVTX3,
+// a no-op when no tool is attached.
+#include <nvtx3/nvToolsExt.h>
+namespace b200 {
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+}  // namespace b200
+
 namespace b200 {
 
 constexpr int kThreads = 256;          // threads per block, every kernel
