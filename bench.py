@@ -36,7 +36,11 @@ WORKLOADS = {  # name -> (m, n, nnz_per_col, dense_col_nnz)   SURVEY.md 8(d)
     "S2": (100_000, 100_000, 10, 0),
     "S3": (1_000_000, 1_000_000, 8, 0),
     "S5": (1_000_000, 1_000_000, 8, 500_000),
+    # not a BASELINE config: S3's sizes with a banded (structured) pattern, to show what the SpMV kernels reach when the
+    # gathers share sectors as they do on real LP matrices; reported beside S3, never instead of it
+    "S3B": (1_000_000, 1_000_000, 8, 0),
 }
+BANDS = {"S3B": 2048}
 SEED = 12345
 
 
@@ -133,7 +137,7 @@ def ncu_traffic_bytes(kernel_tag):
 def make_lp(workload):
     from highs_b200.lp import synthetic_lp
     m, n, k, dense = WORKLOADS[workload]
-    return synthetic_lp(m, n, k, SEED, dense_col_nnz=dense)
+    return synthetic_lp(m, n, k, SEED, dense_col_nnz=dense, band=BANDS.get(workload, 0))
 
 
 def algorithmic_bytes(n, m, nnz):
@@ -262,6 +266,64 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line))
 
 
+def run_hipdlp_arm(args, device):
+    """HiPDLP mode: K Halpern steps (blocks of 40) through b200pdlp_solve_hipdlp on host buffers.
+    `value` = steps / CUDA-event time of the device loop (LP resident), `e2e` = steps / wall time of the call."""
+    from highs_b200 import engine
+    from highs_b200.lp import write_b2lp
+    lp = make_lp(args.workload)
+    m, n, k, dense = WORKLOADS[args.workload]
+    nnz = lp.a_matrix_.numNz()
+    K = max(40, (args.steps // 40) * 40)
+    W = max(40, (max(args.warmup, 3) + 39) // 40 * 40)
+    out_arrays = tuple(np.zeros(q) for q in (n, n, m, m))
+    pinned = engine.pin_arrays(engine.lp_arrays(lp) + list(out_arrays))
+    sampler = ClockSampler(device)
+    sampler.start()
+    engine.solve_hipdlp(lp, iter_limit=W, device=device)
+    sampler.mark()
+    t0 = time.monotonic()
+    r = engine.solve_hipdlp(lp, iter_limit=K, device=device)
+    wall = time.monotonic() - t0
+    sampler.mark()
+    clocks = sampler.stop()
+    engine.unpin_arrays(pinned)
+    assert r["iters"] == K, (r["iters"], K)
+    B = algorithmic_bytes(n, m, nnz)
+    peak, peak_src = measured_peak_gbs()
+    step_bytes = B["ax"] + B["aty"] + 8 * 8 * n + 7 * 8 * m   # 2 SpMV + the x-side (x, xa, c, aty, l, u -> rx, x) and y-side vectors
+    value = K / (r["loop_device_ms"] / 1e3)
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import binding as ob
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, "lp.b2lp")
+            write_b2lp(path, lp)
+            runs = []
+            for lim in (40, 40 + 40 * (2 if args.workload != "S2" else 10)):
+                q = ob.run_reference(lp_path=path, options={"solver": "hipdlp", "pdlp_iteration_limit": lim})
+                runs.append((q["pdlp_iteration_count"], q["run_seconds"]))
+        (ia, ta), (ib, tb) = runs
+        cpu = {"value": (ib - ia) / max(tb - ta, 1e-9), "unit": "iter/s", "cores": 1, "kind": "reference",
+               "host_cores_available": cpu_cores(), "sample": f"HiGHS CPU hipdlp, {ib - ia} steady-state steps (two-point fit)"}
+    print(json.dumps({
+        "metric": "pdhg_iterations_per_sec", "value": value, "unit": "iter/s", "n_gpus": 1, "steps": K, "warmup": W,
+        "ms_per_step": r["loop_device_ms"] / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: synthetic sparse LP m={m} n={n} nnz={nnz} seed={SEED}",
+                   "solver": "hipdlp (reflected Halpern PDHG, blocks of 40 steps, checks between blocks)",
+                   "l2": "inputs larger than L2" if args.workload != "S2" else "working set fits L2 (S2)", "parallelism": "single GPU"},
+        "gpu_launches": r["kernel_launches"], "wall_seconds": wall, "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": step_bytes * value / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": step_bytes * value / 1e9 / peak, "traffic": None, "kernel": "whole Halpern step (3 launches)",
+                     "algorithmic_bytes_per_launch": step_bytes, "peak_source": peak_src},
+        "cpu_baseline": cpu,
+        "e2e": {"value": K / wall, "unit": "iter/s", "h2d_bytes_per_step": (2 * (12 * nnz + 4 * (n + m)) + 8 * (5 * n + 4 * m)) / K,
+                "d2h_bytes_per_step": 8 * (2 * n + 2 * m) / K, "wall_seconds": wall, "setup_seconds": r["setup_seconds"],
+                "solve_seconds": r["solve_seconds"]},
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -271,6 +333,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity", action="store_true", help="compute the parity block even with --no-cpu-baseline")
+    ap.add_argument("--solver", default="pdlp", choices=["pdlp", "hipdlp"],
+                    help="pdlp: the cuPDLP-C algorithm (BASELINE's headline, default); hipdlp: the engine's HiPDLP mode "
+                         "(reflected Halpern PDHG, solver=hipdlp) against the reference's CPU hipdlp -- single GPU")
     ap.add_argument("--to-tolerance", type=float, default=0.0,
                     help="additionally solve the workload to this kkt_tolerance through the host-buffer call and report the "
                          "wall-clock time to solution (SURVEY.md 8(d)); single GPU / reference arm")
@@ -285,6 +350,10 @@ def main():
     from highs_b200 import engine
     if engine.device_count() == 0:
         raise SystemExit("bench.py needs a CUDA device; the engine has no CPU fallback")
+    if args.solver == "hipdlp":
+        if rank == 0:
+            run_hipdlp_arm(args, local_rank)
+        return
     dist = None
     if world > 1:
         import torch
@@ -471,7 +540,9 @@ def main():
         "ms_per_step": loop_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: synthetic random sparse LP m={m} n={n} nnz={nnz} seed={SEED}"
-                               + (f" + one column with {dense} nonzeros" if dense else ""),
+                               + (f" + one column with {dense} nonzeros" if dense else "")
+                               + (f" -- BANDED pattern (rows within {BANDS[args.workload]} of the diagonal; structured, "
+                                  "not a BASELINE config)" if args.workload in BANDS else ""),
                    "options": "solver=pdlp presolve=off, adaptive step + restarts, checks every 40 iterations",
                    "l2": "inputs larger than L2 (one iteration streams ~0.37 GB vs 126 MB L2)" if args.workload != "S2"
                          else "working set fits L2 (S2)",

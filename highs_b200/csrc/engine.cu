@@ -1781,6 +1781,8 @@ static void solve_hipdlp_on_device(b200pdlp_problem* p, const b200pdlp_lp& lp, c
   int term = B200PDLP_TIMELIMIT_OR_ITERLIMIT;
   bool converged = false, timed_out = false;
   const auto t_loop = clk::now();
+  CudaEvent evl0, evl1;
+  CUDA_OK(cudaEventRecord(evl0, s));
   hip_check(p, h.x.p, h.y.p, 0, 0);   // iteration 0 (:566-572)
   const double* sol_x = h.x.p;
   const double* sol_y = h.y.p;
@@ -1817,6 +1819,12 @@ static void solve_hipdlp_on_device(b200pdlp_problem* p, const b200pdlp_lp& lp, c
   const int iters = ctl.iters, restarts = ctl.restarts;
   const double pfeas = ctl.pfeas, dfeas = ctl.dfeas, pobj = ctl.pobj, dobj = ctl.dobj, relgap = ctl.relgap;
   if (converged) term = B200PDLP_OPTIMAL;
+  CUDA_OK(cudaEventRecord(evl1, s));
+  CUDA_OK(cudaEventSynchronize(evl1));
+  float loop_ms = 0.f;
+  CUDA_OK(cudaEventElapsedTime(&loop_ms, evl0, evl1));
+  out->loop_device_ms = loop_ms;
+  out->iter_device_ms = loop_ms;
   const double solve_seconds = std::chrono::duration<double>(clk::now() - t_loop).count();
   // unscaleSolution + postprocess (pdhg.cc:1883-1897, :359-492): the iterate is copied out ONLY on convergence --
   // an iteration-limited run returns x = y = 0, like the reference

@@ -89,7 +89,7 @@ def read_b2lp(path: str) -> HighsLp:
     return HighsLp(n, m, c, lo, up, rl, ru, HighsSparseMatrix(n, m, start, index, value), -1 if sense < 0 else 1, offset)
 
 
-def synthetic_lp(m: int, n: int, nnz_per_col: int, seed: int = 12345, dense_col_nnz: int = 0) -> HighsLp:
+def synthetic_lp(m: int, n: int, nnz_per_col: int, seed: int = 12345, dense_col_nnz: int = 0, band: int = 0) -> HighsLp:
     """Random sparse LP with a planted strictly-complementary optimal pair.
 
     min c.x  s.t.  A x >= b, x >= 0.   Each column draws `nnz_per_col` row
@@ -98,12 +98,19 @@ def synthetic_lp(m: int, n: int, nnz_per_col: int, seed: int = 12345, dense_col_
     U(0,1); c = A'y* + z with z_j = 0 where x*_j > 0 else U(0,1).  Every row is a
     GEQ row, so the cuPDLP standard form adds no slack columns and keeps (m, n).
     `dense_col_nnz` > 0 replaces column 0 by that many distinct random rows (the
-    "pathological" configuration S5).
+    "pathological" configuration S5).  `band` > 0: banded structure instead of uniformly random rows.
     numpy's PCG64 replaces the survey's mt19937_64: the generator defines the
     workload, it is not part of the parity contract.
     """
     rng = np.random.default_rng(seed)
-    rows = rng.integers(0, m, size=(n, nnz_per_col), dtype=np.int64)
+    if band > 0:
+        # structured variant (bench workload S3B): column j's rows lie within `band` of the diagonal position j m / n,
+        # like the staircase / block-angular matrices of real LPs -- neighbouring rows and columns share vector entries
+        centre = (np.arange(n, dtype=np.int64) * m) // max(n, 1)
+        rows = centre[:, None] + rng.integers(-band, band + 1, size=(n, nnz_per_col), dtype=np.int64)
+        rows = np.clip(rows, 0, m - 1)
+    else:
+        rows = rng.integers(0, m, size=(n, nnz_per_col), dtype=np.int64)
     rows.sort(axis=1)
     keep = np.ones_like(rows, dtype=bool)
     keep[:, 1:] = rows[:, 1:] != rows[:, :-1]
@@ -130,4 +137,5 @@ def synthetic_lp(m: int, n: int, nnz_per_col: int, seed: int = 12345, dense_col_
     c = A.T @ ys + z
     return HighsLp(n, m, c, np.zeros(n), np.full(n, kHighsInf), b, np.full(m, kHighsInf),
                    HighsSparseMatrix(n, m, start.astype(np.int32), index, value), 1, 0.0,
-                   f"synthetic_m{m}_n{n}_k{nnz_per_col}_s{seed}" + (f"_dense{dense_col_nnz}" if dense_col_nnz else ""))
+                   f"synthetic_m{m}_n{n}_k{nnz_per_col}_s{seed}" + (f"_dense{dense_col_nnz}" if dense_col_nnz else "")
+                   + (f"_band{band}" if band else ""))
