@@ -230,7 +230,7 @@ def dropin_available() -> bool:
 
 
 def run_reference(lp=None, mps=None, options=None, want_solution=False, warm=None, lp_path=None, timeout=None,
-                  driver=None) -> dict:
+                  driver=None, pdlp_cleanup=None, cleanup_tighten=1.0) -> dict:
     """Run the UNMODIFIED reference (oracle/_ref) through Highs::run(); returns its JSON line.
     driver=DROPIN_DRIVER runs the same Highs::run() with the B200 shim linked in place of
     CupdlpWrapper.cpp (the drop-in integration)."""
@@ -248,6 +248,8 @@ def run_reference(lp=None, mps=None, options=None, want_solution=False, warm=Non
             cmd += ["--lp", lp_path]
         for k, v in opts.items():
             cmd += ["--opt", f"{k}={v}"]
+        if pdlp_cleanup is not None:   # the product's clean-up flow (highs_b200/csrc/highs_pdlp_cleanup.hpp); value = margin
+            cmd += ["--pdlp-cleanup", "--cleanup-margin", repr(float(pdlp_cleanup)), "--cleanup-tighten", repr(float(cleanup_tighten))]
         sol = os.path.join(td, "sol.bin")
         if want_solution:
             cmd += ["--sol", sol]

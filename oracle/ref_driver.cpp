@@ -26,6 +26,8 @@
 #include "Highs.h"
 #include "lp_data/HighsSolution.h"
 
+#include "../highs_b200/csrc/highs_pdlp_cleanup.hpp"   // --pdlp-cleanup: the product's clean-up flow under test
+
 static const int64_t kMagic = 0x504C3242;  // "B2LP"
 
 static bool readB2lp(const std::string& path, HighsLp& lp) {
@@ -119,7 +121,8 @@ int main(int argc, char** argv) {
   std::string lp_path, mps_path, dump_lp, sol_path, warm_path, kkt_path;
   int kkt_status = (int)HighsModelStatus::kOptimal;
   std::vector<std::pair<std::string, std::string>> opts;
-  bool quiet = true;
+  bool quiet = true, pdlp_cleanup = false;
+  double cleanup_margin = 1e2, cleanup_tighten = 1.0;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     auto next = [&]() { return std::string(i + 1 < argc ? argv[++i] : ""); };
@@ -131,6 +134,9 @@ int main(int argc, char** argv) {
     else if (a == "--kkt-of") kkt_path = next();
     else if (a == "--kkt-status") kkt_status = atoi(next().c_str());
     else if (a == "--verbose") quiet = false;
+    else if (a == "--pdlp-cleanup") pdlp_cleanup = true;
+    else if (a == "--cleanup-margin") cleanup_margin = atof(next().c_str());
+    else if (a == "--cleanup-tighten") cleanup_tighten = atof(next().c_str());
     else if (a == "--opt") {
       std::string kv = next();
       size_t e = kv.find('=');
@@ -172,6 +178,7 @@ int main(int argc, char** argv) {
   HighsModelStatus kkt_model_status = (HighsModelStatus)kkt_status;
   double secs = 0.0;
   HighsStatus rs = HighsStatus::kOk;
+  B200PdlpCleanupReport cleanup;
   if (!kkt_path.empty()) {
     HighsSolution sol;
     if (!readSol(kkt_path, sol)) { fprintf(stderr, "cannot read solution\n"); return 3; }
@@ -181,7 +188,7 @@ int main(int argc, char** argv) {
     lpKktCheck(kkt_model_status, kkt_info, highs.getLp(), sol, basis, highs.getOptions(), "ref_driver --kkt-of");
   } else {
     auto t0 = std::chrono::steady_clock::now();
-    rs = highs.run();
+    rs = pdlp_cleanup ? b200RunWithPdlpCleanup(highs, &cleanup, cleanup_margin, cleanup_tighten) : highs.run();
     secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   }
   const HighsInfo& info = kkt_path.empty() ? highs.getInfo() : kkt_info;
@@ -198,6 +205,8 @@ int main(int argc, char** argv) {
          "\"max_relative_primal_residual_error\": %.17g, \"max_relative_dual_residual_error\": %.17g, "
          "\"max_complementarity_violation\": %.17g, \"num_complementarity_violations\": %d, "
          "\"primal_solution_status\": %d, \"dual_solution_status\": %d, "
+         "\"cleanup_considered\": %d, \"cleanup_attempted\": %d, \"cleanup_iteration_limit\": %d, \"cleanup_first_status_code\": %d, "
+         "\"cleanup_first_pdlp_iterations\": %d, \"cleanup_max_relative_violation\": %.17g, "
          "\"num_col\": %d, \"num_row\": %d, \"num_nz\": %d, \"run_seconds\": %.6f}\n",
          (int)rs, highs.modelStatusToString(final_status).c_str(), (int)final_status,
          (int)info.pdlp_iteration_count, info.objective_function_value,
@@ -209,6 +218,8 @@ int main(int argc, char** argv) {
          info.max_relative_primal_residual_error, info.max_relative_dual_residual_error,
          info.max_complementarity_violation, (int)info.num_complementarity_violations,
          (int)info.primal_solution_status, (int)info.dual_solution_status,
+         (int)cleanup.considered, (int)cleanup.attempted, (int)cleanup.iteration_limit, (int)cleanup.first_status,
+         (int)cleanup.first_pdlp_iterations, cleanup.max_relative_violation,
          (int)lp.num_col_, (int)lp.num_row_, (int)lp.a_matrix_.numNz(), secs);
   return 0;
 }

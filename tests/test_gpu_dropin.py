@@ -28,3 +28,49 @@ def test_highs_run_with_b200_shim(oracle, case):
         gold = golden_solution(case)
         for k in ("col_value", "col_dual", "row_value", "row_dual"):
             assert np.array_equal(res[k], gold[k]), k
+
+
+# ---- the boundary sits BELOW presolve -- with presolve=choose HiGHS hands the REDUCED LP to the
+# drop-in and postsolves what it returns (Highs.cpp:1554-1694, :1802-1931); then the clean-up flow of
+# highs_b200/csrc/highs_pdlp_cleanup.hpp (logic checked on the CPU in tests/test_pdlp_cleanup.py) with the engine behind it
+PRESOLVE_INSTANCES = ["afiro", "adlittle", "avgas", "blending", "chip", "e226", "etamacro", "standata", "scrs8", "sctest", "stair"]
+
+
+@pytest.mark.parametrize("name", PRESOLVE_INSTANCES)
+def test_presolved_lp_through_the_shim(oracle, name):
+    """same Highs::run() with presolve on, reference CPU pdlp vs the B200 shim: the presolved LP is small (ordered mode), so
+    status, iteration count and objective agree exactly"""
+    import os
+    from conftest import GOLDEN
+    from highs_b200.lp import read_b2lp
+    if not oracle.dropin_available():
+        pytest.skip("oracle/_ref/ref_driver_b200 not built")
+    path = os.path.join(GOLDEN, "instances", name + ".b2lp")
+    if not os.path.exists(path):
+        pytest.skip("instance fixture missing")
+    lp = read_b2lp(path)
+    opts = {"presolve": "choose", "pdlp_iteration_limit": 20000}
+    ref = oracle.run_reference(lp=lp, options=opts)
+    got = oracle.run_reference(lp=lp, options=opts, driver=oracle.DROPIN_DRIVER)
+    assert got["model_status_code"] == ref["model_status_code"], (got["model_status"], ref["model_status"])
+    assert got["pdlp_iteration_count"] == ref["pdlp_iteration_count"]
+    assert got["objective_function_value"] == pytest.approx(ref["objective_function_value"], rel=1e-12, abs=1e-12)
+
+
+def test_pdlp_cleanup_with_the_engine(oracle):
+    """postsolve leaves kUnknown (standata, kkt 1e-4); the clean-up solve of the ORIGINAL LP runs on the GPU from the
+    postsolved solution and ends kOptimal -- same decisions as with the reference's CPU solver behind the same flow"""
+    import os
+    from conftest import GOLDEN
+    from highs_b200.lp import read_b2lp
+    if not oracle.dropin_available():
+        pytest.skip("oracle/_ref/ref_driver_b200 not built")
+    lp = read_b2lp(os.path.join(GOLDEN, "instances", "standata.b2lp"))
+    opts = {"presolve": "choose", "kkt_tolerance": 1e-4}
+    ref = oracle.run_reference(lp=lp, options=opts, pdlp_cleanup=1e3, cleanup_tighten=0.1)
+    got = oracle.run_reference(lp=lp, options=opts, pdlp_cleanup=1e3, cleanup_tighten=0.1, driver=oracle.DROPIN_DRIVER)
+    for k in ("cleanup_considered", "cleanup_attempted", "cleanup_iteration_limit", "cleanup_first_status_code",
+              "cleanup_first_pdlp_iterations", "model_status_code", "pdlp_iteration_count"):
+        assert got[k] == ref[k], k
+    assert got["model_status"] == "Optimal"
+    assert got["objective_function_value"] == pytest.approx(ref["objective_function_value"], rel=1e-12, abs=1e-12)
