@@ -20,8 +20,8 @@ NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-fmad=false", "-Xcompile
                      "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 CXX_FLAGS = ["-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-Wall", "-Wno-sign-compare"]
 
-SOURCES = [("host_prep.cpp", "cxx"), ("host_prep_hipdlp.cpp", "cxx"), ("pdhg_kernels.cu", "nvcc"), ("setup_kernels.cu", "nvcc"), ("device_prep.cu", "nvcc"), ("engine.cu", "nvcc")]
-HEADERS = ["host_prep.hpp", "kernels.cuh", "pdhg_kernels.hpp", "setup_kernels.hpp", "device_prep.hpp", os.path.join("..", "..", "include", "b200pdlp.h")]
+SOURCES = [("host_prep.cpp", "cxx"), ("host_prep_hipdlp.cpp", "cxx"), ("pdhg_kernels.cu", "nvcc"), ("setup_kernels.cu", "nvcc"), ("device_prep.cu", "nvcc"), ("kkt_check.cu", "nvcc"), ("engine.cu", "nvcc")]
+HEADERS = ["host_prep.hpp", "kernels.cuh", "pdhg_kernels.hpp", "setup_kernels.hpp", "device_prep.hpp", "kkt_logic.hpp", os.path.join("..", "..", "include", "b200pdlp.h")]
 
 
 def _nvcc() -> str:

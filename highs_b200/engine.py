@@ -75,6 +75,7 @@ ABI_SYMBOLS = [
     "b200pdlp_hipdlp_form_create", "b200pdlp_hipdlp_power_method", "b200pdlp_hipdlp_default_params",
     "b200pdlp_solve_hipdlp", "b200pdlp_hipdlp_controller_replay", "b200pdlp_debug_prep_compare", "b200pdlp_release_cache",
     "b200pdlp_host_register", "b200pdlp_host_unregister", "b200pdlp_primal_step", "b200pdlp_dual_step", "b200pdlp_residuals",
+    "b200pdlp_kkt_check", "b200pdlp_kkt_check_host", "b200pdlp_kkt_default_tolerances",
 ]
 
 _lib = None
@@ -254,6 +255,44 @@ def pin_arrays(arrays) -> list:
 def unpin_arrays(arrays):
     for a in arrays:
         lib().b200pdlp_host_unregister(a.ctypes.data_as(C.c_void_p))
+
+
+class CKktTolerances(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("primal_feasibility_tolerance", "dual_feasibility_tolerance", "primal_residual_tolerance",
+                                          "dual_residual_tolerance", "optimality_tolerance")]
+
+
+class CKktInfo(C.Structure):
+    _fields_ = ([(k, C.c_double) for k in (
+        "objective_function_value", "dual_objective_value", "primal_dual_objective_error", "max_primal_infeasibility",
+        "sum_primal_infeasibilities", "max_dual_infeasibility", "sum_dual_infeasibilities", "max_relative_primal_infeasibility",
+        "max_relative_dual_infeasibility", "max_primal_residual_error", "max_dual_residual_error",
+        "max_relative_primal_residual_error", "max_relative_dual_residual_error", "max_complementarity_violation",
+        "norm_bounds", "norm_costs")] + [(k, C.c_int32) for k in (
+            "num_primal_infeasibilities", "num_dual_infeasibilities", "num_relative_primal_infeasibilities",
+            "num_relative_dual_infeasibilities", "num_primal_residual_errors", "num_dual_residual_errors",
+            "num_relative_primal_residual_errors", "num_relative_dual_residual_errors", "num_complementarity_violations",
+            "primal_solution_status", "dual_solution_status", "model_status")])
+
+
+def kkt_check(lp: HighsLp, solution, kkt_tolerance: float = 0.0, model_status: int = 7, on_device: bool = True) -> dict:
+    """lpKktCheck of a HighsSolution (b200pdlp_kkt_check on the GPU, b200pdlp_kkt_check_host = its host twin).
+    `solution`: mapping with col_value, col_dual, row_value, row_dual; model_status: HighsModelStatus code from the solver."""
+    L = lib()
+    clp, keep = make_clp(lp)
+    tol = CKktTolerances()
+    L.b200pdlp_kkt_default_tolerances.argtypes = [C.POINTER(CKktTolerances), C.c_double]
+    L.b200pdlp_kkt_default_tolerances.restype = None
+    L.b200pdlp_kkt_default_tolerances(C.byref(tol), float(kkt_tolerance))
+    info = CKktInfo()
+    info.model_status = int(model_status)
+    arrs = [np.ascontiguousarray(solution[k], dtype=np.float64) for k in ("col_value", "col_dual", "row_value", "row_dual")]
+    fn = L.b200pdlp_kkt_check if on_device else L.b200pdlp_kkt_check_host
+    fn.argtypes = [C.POINTER(CLp), _dp, _dp, _dp, _dp, C.POINTER(CKktTolerances), C.POINTER(CKktInfo)]
+    rc = fn(C.byref(clp), *(_p(a, _dp) for a in arrs), C.byref(tol), C.byref(info))
+    if rc != 0:
+        raise EngineError(f"b200pdlp_kkt_check{'_host' if not on_device else ''} failed ({rc})")
+    return {k: getattr(info, k) for k, _ in CKktInfo._fields_}
 
 
 def hipdlp_controller_replay(norm_cost, norm_rhs, op_norm_sq, tolerance, strategy, sums, restart_sums) -> np.ndarray:

@@ -286,6 +286,37 @@ int b200pdlp_debug_prep_compare(const b200pdlp_lp* lp, int32_t scaling, double r
  * cudaFree would cost more than the prologue).  This returns them to the driver.  B200PDLP_CACHE_MB caps the cache. */
 void b200pdlp_release_cache(void);
 
+/* ---- post-solve KKT assessment -------------------------------------------------
+ * What Highs::run() does with the HighsSolution after solveLpCupdlp returns: lpKktCheck -> getKktFailures
+ * (/root/reference/highs/lp_data/HighsSolution.cpp:1043-1327, :73-495): A x and A'y with double-double accumulation,
+ * bound / sign violations, absolute and relative measures (relative to 1 + |active bounds|_inf, 1 + |costs with ~0 dual|_inf),
+ * residual errors |A x - row_value|, |A'y - c + col_dual|, complementarity, P-D objective error, and the status rules for
+ * a solution without a basis.  b200pdlp_kkt_check runs on the GPU (no CPU fallback); b200pdlp_kkt_check_host is its host
+ * twin over the same per-variable arithmetic (highs_b200/csrc/kkt_logic.hpp), kept so that the logic is checked against
+ * the reference's own lpKktCheck without a GPU.  Tolerances: the five HighsOptions after the kkt_tolerance override. */
+typedef struct {
+  double primal_feasibility_tolerance, dual_feasibility_tolerance, primal_residual_tolerance, dual_residual_tolerance,
+         optimality_tolerance;
+} b200pdlp_kkt_tolerances;
+typedef struct {   /* HighsInfo fields of the same names (HighsInfo.h:91-131) */
+  double objective_function_value, dual_objective_value, primal_dual_objective_error;
+  double max_primal_infeasibility, sum_primal_infeasibilities, max_dual_infeasibility, sum_dual_infeasibilities;
+  double max_relative_primal_infeasibility, max_relative_dual_infeasibility;
+  double max_primal_residual_error, max_dual_residual_error, max_relative_primal_residual_error, max_relative_dual_residual_error;
+  double max_complementarity_violation;
+  double norm_bounds, norm_costs;   /* getKktFailures' highs_norm_bounds / highs_norm_costs */
+  int32_t num_primal_infeasibilities, num_dual_infeasibilities, num_relative_primal_infeasibilities, num_relative_dual_infeasibilities;
+  int32_t num_primal_residual_errors, num_dual_residual_errors, num_relative_primal_residual_errors, num_relative_dual_residual_errors;
+  int32_t num_complementarity_violations;
+  int32_t primal_solution_status, dual_solution_status;   /* kSolutionStatusInfeasible 1 / Feasible 2 */
+  int32_t model_status;   /* in: HighsModelStatus code returned by the solver; out: after lpKktCheck's adjustment */
+} b200pdlp_kkt_info;
+void b200pdlp_kkt_default_tolerances(b200pdlp_kkt_tolerances* t, double kkt_tolerance /* <= 0: the default 1e-7 */);
+int b200pdlp_kkt_check(const b200pdlp_lp* lp, const double* col_value, const double* col_dual, const double* row_value,
+                       const double* row_dual, const b200pdlp_kkt_tolerances* tol, b200pdlp_kkt_info* inout);
+int b200pdlp_kkt_check_host(const b200pdlp_lp* lp, const double* col_value, const double* col_dual, const double* row_value,
+                            const double* row_dual, const b200pdlp_kkt_tolerances* tol, b200pdlp_kkt_info* inout);
+
 /* Page-lock / unlock caller memory (cudaHostRegister) so that the copies of b200pdlp_solve run at PCIe speed; optional
  * (pageable buffers work, staged by the driver).  A host application that keeps its HighsLp / HighsSolution vectors for
  * many solves registers them once. */
