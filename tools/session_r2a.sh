@@ -21,6 +21,10 @@ B200PDLP_PDL=1 run bench_pdl1 python bench.py --no-cpu-baseline
 B200PDLP_PDL=2 run bench_pdl2 python bench.py --no-cpu-baseline
 run tts_ours python bench.py --workload S2 --no-cpu-baseline --to-tolerance 1e-4
 run tts_ours_s3 python bench.py --workload S3 --no-cpu-baseline --to-tolerance 1e-4
+T=120 run dsmem_gather tools/dsmem_gather_bench
+T=120 run gather_bench tools/gather_bench
+B200PDLP_TIMING=1 run bench_s3b python bench.py --workload S3B --no-cpu-baseline
+run bench_hipdlp python bench.py --solver hipdlp --steps 400
 T=900 run pytest_rest python -m pytest tests -q -m gpu --deselect tests/test_gpu_device_prep.py --deselect tests/test_gpu_solve.py --deselect tests/test_gpu_kernels.py -rxX
 grep -h '"metric"\|"impl"' $O/bench_*.log $O/tts_*.log | cut -c1-700
 tail -n 30 $O/diag.log $O/diag_old.log $O/pytest_prep.log $O/pytest_solve.log $O/child_shards2.log $O/child_shards2.err $O/child_shards_c.err | cut -c1-900
