@@ -227,3 +227,38 @@ def test_dense_column_s5_mini(engine_lib, oracle):
     res, orc = engine.solve(lp, **kw), oracle.solve(lp, **kw)
     assert res["term_name"] == orc["term_name"] == "OPTIMAL"
     assert _rel(lp.objectiveValue(res["col_value"]), lp.objectiveValue(orc["col_value"])) <= 1e-5
+
+
+@pytest.mark.parametrize("tol", ["0.0001", "1e-08"])
+def test_s2_converged_parity_with_the_reference(engine_lib, tol):
+    """config S2 (100k x 100k, 1M nonzeros; tree-mode reductions) solved to kkt_tolerance 1e-4 / 1e-8 against
+    the UNMODIFIED reference's run on the same LP (tests/golden/s2_converged.json, written by make_s2_golden.py from
+    oracle/_ref): same status, objective to 1e-6 (1 + |ref|) -- the north-star criterion --, iteration count within 10 %, and
+    the reference's KKT measures (lpKktCheck's definitions, evaluated on OUR solution by the device KKT check) on the same
+    side of the tolerance and within 1e-6 (1 + |ref|)."""
+    import json
+    import os
+    from conftest import GOLDEN
+    from highs_b200 import engine
+    from highs_b200.lp import synthetic_lp
+    path = os.path.join(GOLDEN, "s2_converged.json")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/s2_converged.json missing (python tests/golden/make_s2_golden.py)")
+    g = json.load(open(path))
+    w, ref = g["workload"], g["runs"][tol]
+    lp = synthetic_lp(w["m"], w["n"], w["nnz_per_col"], w["seed"])
+    assert lp.a_matrix_.numNz() == w["nnz"]
+    t = float(tol)
+    res = engine.solve(lp, tol_primal=t, tol_dual=t, tol_gap=t, iter_limit=2_000_000)
+    assert res["term_code"] == 0 and ref["model_status"] == "Optimal"
+    assert max(res["form_cols"], res["form_rows"]) > 4096          # tree mode
+    obj = lp.objectiveValue(res["col_value"])
+    assert abs(obj - ref["objective_function_value"]) <= 1e-6 * (1 + abs(ref["objective_function_value"]))
+    assert abs(res["iters"] - ref["pdlp_iteration_count"]) <= 0.1 * ref["pdlp_iteration_count"] + 40
+    kkt = engine.kkt_check(lp, res, kkt_tolerance=t, model_status=7)
+    assert kkt["model_status"] == ref["model_status_code"] == 7
+    for k in ("max_primal_infeasibility", "max_dual_infeasibility", "max_relative_primal_infeasibility",
+              "max_relative_dual_infeasibility", "max_primal_residual_error", "max_dual_residual_error",
+              "primal_dual_objective_error", "max_complementarity_violation"):
+        assert abs(kkt[k] - ref[k]) <= 1e-6 * (1 + abs(ref[k])), (k, kkt[k], ref[k])
+    assert kkt["num_primal_infeasibilities"] == ref["num_primal_infeasibilities"] or t > 1e-6
