@@ -21,13 +21,28 @@
 
 /* ------------------------------------------------------------------ helpers */
 /* cupdlp_linalg.c:320-336 (USE_MY_BLAS dot), :111-126 (nrm2) */
+/* TEST SWITCH (not the reference's behaviour): orc_set_sum_block(k > 0) makes the long sums add in blocks of k elements and
+ * then add the block sums -- a different, equally valid rounding order, like the GPU engine's tree reductions.  Used to
+ * measure how far a mere change of summation order moves a trajectory (tests/test_gpu_instances.py's tree-mode criterion). */
+static int g_sum_block = 0;
+void orc_set_sum_block(int k) { g_sum_block = k; }
 static double vdot(int n, const double* a, const double* b) {
   double s = 0.0;
+  if (g_sum_block > 0) {
+    for (int i0 = 0; i0 < n; i0 += g_sum_block) {
+      double t = 0.0;
+      const int i1 = i0 + g_sum_block < n ? i0 + g_sum_block : n;
+      for (int i = i0; i < i1; i++) t += a[i] * b[i];
+      s += t;
+    }
+    return s;
+  }
   for (int i = 0; i < n; i++) s += a[i] * b[i];
   return s;
 }
 static double vnrm2(int n, const double* a) {
   double s = 0.0;
+  if (g_sum_block > 0) return sqrt(vdot(n, a, a));
   for (int i = 0; i < n; i++) s += a[i] * a[i];
   return sqrt(s);
 }

@@ -1,10 +1,15 @@
-"""Extended parity sweep: every LP instance the reference ships for its own tests (tests/golden/instances/*.b2lp), 400 PDHG
-iterations on the GPU against the oracle -- iteration count, termination and all four HighsSolution vectors bit for bit
-(ordered mode: standard form with at most 4096 rows and columns); larger ones reduce in tree order and are compared to 1e-6.  The oracle itself
-is pinned against the live reference on the same instances (tests/test_reference_instances.py).
+"""Extended parity sweep: every LP instance the reference ships for its own tests (tests/golden/instances/*.b2lp) on the GPU
+against the oracle (itself pinned against the live reference on the same instances, tests/test_reference_instances.py).
 
-STATUS: added after this round's GPU budget was spent, so it has not run on hardware yet; it only uses the validated solve
-path, but one unexpected edge case would stop `pytest -x` -- hence xfail(strict=False) until its first run (XPASS = parity)."""
+* standard form with at most 4096 rows and columns (ordered mode: every reduction in the reference's order): 400 PDHG
+  iterations, iteration count, termination and all four HighsSolution vectors BIT FOR BIT;
+* larger instances (80bau3b, greenbea: fixed-order tree reductions): 120 iterations, same iteration count and termination, the
+  four vectors to 1e-6 (1 + |ref|_inf).  Why not 400 iterations to 1e-6 (round 1's criterion, which these two failed on
+  hardware): the adaptive step rule divides by a cancelling inner product, so ANY change of summation order is amplified --
+  the oracle ITSELF, with nothing changed but the order of its long sums (orc_set_sum_block), moves these trajectories by 1e-8
+  after 120 iterations and by 1e-2 .. 1e-4 after 400 (tests/test_oracle_golden.py::test_summation_order_sensitivity).  The
+  reference carries different goldens for its CPU and GPU builds for the same reason (check/CMakeLists.txt:304-335).  Converged
+  parity at scale is tests/test_gpu_solve.py::test_s2_converged_parity_with_the_reference."""
 import glob
 import os
 
@@ -15,24 +20,24 @@ from conftest import GOLDEN
 
 FILES = sorted(glob.glob(os.path.join(GOLDEN, "instances", "*.b2lp")))
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="extended instance sweep: first hardware run pending")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-5] for f in FILES])
-def test_instance_400_iterations(engine_lib, oracle, path):
+def test_instance_against_oracle(engine_lib, oracle, path):
     from highs_b200 import engine
     from highs_b200.lp import read_b2lp
     lp = read_b2lp(path)
     ref = oracle.solve(lp, iter_limit=400)
     out = engine.solve(lp, iter_limit=400)
-    assert out["term_code"] == ref["term_code"]
     if max(out["form_cols"], out["form_rows"]) <= 4096:
+        assert out["term_code"] == ref["term_code"]
         assert out["iters"] == ref["iters"]
         for k in ("col_value", "col_dual", "row_value", "row_dual"):
             assert np.array_equal(out[k], ref[k]), k
-    else:
-        # tree-mode reductions: trajectories may part after many iterations; after 400 they still agree closely
-        assert abs(out["iters"] - ref["iters"]) <= 40
-        if out["iters"] == ref["iters"]:
-            assert np.allclose(out["col_value"], ref["col_value"], rtol=1e-6, atol=1e-6 * (1 + np.abs(ref["col_value"]).max()))
+        return
+    ref = oracle.solve(lp, iter_limit=120)
+    out = engine.solve(lp, iter_limit=120)
+    assert out["term_code"] == ref["term_code"] and out["iters"] == ref["iters"]
+    for k in ("col_value", "col_dual", "row_value", "row_dual"):
+        assert np.abs(out[k] - ref[k]).max() <= 1e-6 * (1 + np.abs(ref[k]).max()), k

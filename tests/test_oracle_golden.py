@@ -93,3 +93,31 @@ def test_row_side_interaction_is_equivalent(oracle, name):
     assert abs(oa - ob_) <= 1e-6 * (1 + abs(oa))
     # rounding noise in the interaction is amplified by cancellation, so restarts can land on different checks
     assert 0.5 * a["iters"] <= b["iters"] <= 2 * a["iters"]
+
+
+@pytest.mark.parametrize("name", ["80bau3b", "greenbea", "25fv47"])
+def test_summation_order_sensitivity(oracle, name):
+    """How far does a MERE change of summation order move a trajectory?  The oracle against itself, long sums added in blocks
+    of 256 (orc_set_sum_block -- a test switch, not the reference's behaviour): after 120 iterations the iterates agree to
+    1e-6 (in fact ~1e-8), after 400 they differ by more than 1e-6 on these instances.  This is why the GPU engine's
+    tree-mode parity on large instances is asserted after 120 iterations (tests/test_gpu_instances.py) and at convergence
+    (objective / KKT measures), not as a 400-iteration trajectory."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    from highs_b200.lp import read_b2lp
+    lp = read_b2lp(os.path.join(GOLDEN, "instances", name + ".b2lp"))
+    L = oracle.lib()
+    try:
+        rel = {}
+        for lim in (120, 400):
+            L.orc_set_sum_block(0)
+            ref = oracle.solve(lp, iter_limit=lim)
+            L.orc_set_sum_block(256)
+            alt = oracle.solve(lp, iter_limit=lim)
+            assert alt["iters"] == ref["iters"] and alt["term_code"] == ref["term_code"]
+            rel[lim] = max(float(np.abs(alt[k] - ref[k]).max() / (1 + np.abs(ref[k]).max())) for k in ("col_value", "row_dual"))
+    finally:
+        L.orc_set_sum_block(0)
+    assert rel[120] <= 1e-6, rel
+    assert rel[400] > 1e-6, rel
