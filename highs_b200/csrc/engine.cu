@@ -1083,14 +1083,63 @@ static void trace_row(b200pdlp_result* out, const PdhgState* h, const CheckResul
 }
 
 // ---------------------------------------------------------------- device-side check iterations (tree mode, one GPU)
+// graphs bake pointers and launch shapes in: (re)wiring the peers invalidates all of them
+static void drop_graphs(b200pdlp_problem* p) {
+  if (p->graph_main) { cudaGraphExecDestroy(p->graph_main); p->graph_main = nullptr; }
+  if (p->graph_small) { cudaGraphExecDestroy(p->graph_small); p->graph_small = nullptr; }
+  for (cudaGraphExec_t& g : p->graph_pow2) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+  if (p->graph_check) { cudaGraphExecDestroy(p->graph_check); p->graph_check = nullptr; }
+}
+
 static bool use_device_checks(const b200pdlp_problem* p, const b200pdlp_params& prm) {
-  if (p->ordered || p->world != 1 || prm.log_level >= 2 || prm.iter_limit <= 0) return false;
+  if (p->ordered || prm.log_level >= 2 || prm.iter_limit <= 0) return false;
+  if (p->world != 1) {
+    // several GPUs: only on the fused peer-memory path (the checks' collectives are our own barrier / exchange kernels)
+    if (!(p->p2p && p->p2p_pull)) return false;
+    // opt-in until it has passed on hardware (tests/test_gpu_logical_shards.py, tests/test_gpu_multi.py run both settings)
+    const char* e = getenv("B200PDLP_MG_DEVICE_CHECK");
+    if (!e || atoi(e) == 0) return false;
+  }
   if (const char* e = getenv("B200PDLP_HOST_CHECK")) if (atoi(e) != 0) return false;   // the round-1 host-driven checks
   return true;
 }
 
+// several GPUs (fused peer-memory path): the same check with the vectors sharded -- xbar shards go to every peer's xfull,
+// the partial A_g'ybar are parked in `recv` and reduced by their owners after a barrier, the 28 sums (+ the time-limit
+// word) are all-reduced by the exchange kernel (identical on every rank, added in rank order), so every rank takes the
+// same decisions; a restart costs one more exchange of two scalars.  15 launches, 3 cross-GPU synchronisations.
+static int enqueue_check_device_mg(b200pdlp_problem* p) {
+  cudaStream_t s = p->stream;
+  PdhgState* st = p->state.p;
+  SolveCtl* ctl = p->ctl.p;
+  const int nl = p->nl, ml = p->ml;
+  double* o = p->outs.p;
+  const ReduceScratch rrow = p->rs(kSlotK2, ml), rcol = p->rs(kSlotChk, nl), rrst = p->rs(kSlotK1, nl);
+  launch_reduce_part_p2p(s, nl, p->aty[0].p, p->peers, p->world, p->rank, p->seg_len, 1, st, 1);   // if the last pass was accepted
+  launch_check_avg_x(s, nl, p->x[0].p, p->x[1].p, p->xsum.p, p->xavg.p, st, ctl);
+  launch_average_dev(s, ml, p->y[0].p, p->y[1].p, p->ysum.p, p->yavg.p, st);
+  launch_push_shard(s, p->xavg.p, nl, p->peers, p->world, p->rank, p->seg_len, st);
+  launch_spmv_partial_aty(s, p->AT.dev, nullptr, p->yavg.p, p->yavg.p, p->recv.p, p->at_outpos.p, st);
+  launch_p2p_exchange(s, o + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p, st);
+  launch_spmv_check_rows_mg(s, p->A.dev, st, ctl, p->xfull.p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->yavg.p,
+                            p->axavg.p, p->rhs.p, p->rowscale.p, p->neq_local, rrow);
+  launch_reduce_part_p2p(s, nl, p->atyavg.p, p->peers, p->world, p->rank, p->seg_len, 2, st, 0);
+  ColIter c0{p->x[0].p, p->aty[0].p}, calt{p->x[1].p, p->aty[0].p}, c1{p->xavg.p, p->atyavg.p};   // one current A'y shard
+  launch_col_check_fused(s, nl, c0, c1, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, rcol, o, st, calt);
+  launch_reduce_partials(s, st, ctl, 8, rrow.partials, p->A.grid(), o + 20, /*flag_slot=*/8, 0);   // o[20..27], flag at o[28]
+  launch_p2p_exchange(s, o, 29, p->peers, p->world, p->rank, p->epochs.p, p->fault.p, st);
+  launch_check_decide_sums(s, st, ctl, o);
+  launch_restart_sweep(s, nl, ml, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[0].p, p->xavg.p, p->atyavg.p, p->xsum.p, p->xlr.p,
+                       p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->yavg.p, p->axavg.p, p->ysum.p, p->ylr.p, st, ctl, rrst);
+  launch_reduce_partials(s, st, ctl, 2, rrst.partials, restart_sweep_grid(nl, ml), o + 40, -1, 1);
+  launch_p2p_exchange(s, o + 40, 2, p->peers, p->world, p->rank, p->epochs.p, p->fault.p, st);
+  launch_check_finish(s, st, ctl, rrst.partials, restart_sweep_grid(nl, ml), o + 40);
+  return 16;
+}
+
 // the six launches of one check (pdhg_kernels.cu "device-side check iteration"); no-ops unless the check is due
 static void enqueue_check_device(b200pdlp_problem* p) {
+  if (p->world > 1) { enqueue_check_device_mg(p); return; }
   cudaStream_t s = p->stream;
   PdhgState* st = p->state.p;
   SolveCtl* ctl = p->ctl.p;
@@ -1119,7 +1168,7 @@ static void launch_check_graph(b200pdlp_problem* p) {
     CUDA_OK(cudaGraphDestroy(g));
   }
   CUDA_OK(cudaGraphLaunch(p->graph_check, p->stream));
-  p->launches += kCheckLaunches;
+  p->launches += p->world > 1 ? 16 : kCheckLaunches;
 }
 
 // `d` PDHG passes: the main graph (one check interval + spare passes) when d is about an interval, otherwise graphs of
@@ -1313,7 +1362,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
     memset(c, 0, sizeof(SolveCtl));
     c->tol_p = tol_p; c->tol_d = tol_d; c->tol_gap = prm.tol_gap;
     c->sense = f.sense; c->offset = f.offset;
-    c->iter_limit = prm.iter_limit; c->interval = interval; c->restart_on = prm.restart != 0; c->world = 1;
+    c->iter_limit = prm.iter_limit; c->interval = interval; c->restart_on = prm.restart != 0; c->world = p->world;
     *p->htime = (t_lim >= 0 && std::chrono::duration<double>(clk::now() - t_loop).count() > t_lim) ? 1 : 0;
     {
       int* dflag = nullptr;
@@ -1364,6 +1413,8 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
       (void)pred_term;
       CUDA_OK(cudaMemcpyAsync(c, p->ctl.p, sizeof(SolveCtl), cudaMemcpyDeviceToHost, s));
       CUDA_OK(cudaMemcpyAsync(h, p->state.p, sizeof(PdhgState), cudaMemcpyDeviceToHost, s));
+      int* hfault = reinterpret_cast<int*>(p->hflag + 2);
+      if (p->p2p) CUDA_OK(cudaMemcpyAsync(hfault, p->fault.p, sizeof(int), cudaMemcpyDeviceToHost, s));
       const size_t npairs = nev / 2;   // events so far come in (before, after) pairs around the passes
       cudaEvent_t fin = ev();
       CUDA_OK(cudaEventRecord(fin, s));
@@ -1375,6 +1426,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
         }
       }
       CUDA_OK(cudaEventSynchronize(fin));
+      if (p->p2p && *hfault) throw Error(B200PDLP_ERR_STATE, "P2P barrier timed out (a peer rank did not arrive)");
       for (size_t k = 0; k < npairs; k++) {
         float ms = 0.f;
         CUDA_OK(cudaEventElapsedTime(&ms, *evs[2 * k], *evs[2 * k + 1]));
@@ -2506,8 +2558,7 @@ int b200pdlp_p2p_import(b200pdlp_problem* p, const uint8_t* all_handles) {
     p->p2p_pull = 1;   // measured slightly faster than the push variant at 2 and 4 GPUs (profiles/r01_multigpu.md)
     if (const char* e = getenv("B200PDLP_P2P_PULL")) p->p2p_pull = atoi(e);
     // graphs captured for the NCCL path are stale now
-    if (p->graph_main) { cudaGraphExecDestroy(p->graph_main); p->graph_main = nullptr; }
-    if (p->graph_small) { cudaGraphExecDestroy(p->graph_small); p->graph_small = nullptr; }
+    drop_graphs(p);
   });
 }
 
@@ -2543,8 +2594,7 @@ int b200pdlp_p2p_link_local(b200pdlp_problem** probs, int32_t count) {
       p->p2p = true;
       p->local_link = true;
       p->p2p_pull = 1;
-      if (p->graph_main) { cudaGraphExecDestroy(p->graph_main); p->graph_main = nullptr; }
-      if (p->graph_small) { cudaGraphExecDestroy(p->graph_small); p->graph_small = nullptr; }
+      drop_graphs(p);
     }
   });
 }
@@ -2559,8 +2609,7 @@ int b200pdlp_p2p_release(b200pdlp_problem* p) {
     p->ipc_opened.clear();
     p->p2p = false;
     p->local_link = false;
-    if (p->graph_main) { cudaGraphExecDestroy(p->graph_main); p->graph_main = nullptr; }
-    if (p->graph_small) { cudaGraphExecDestroy(p->graph_small); p->graph_small = nullptr; }
+    drop_graphs(p);
   });
 }
 

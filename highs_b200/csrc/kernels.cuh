@@ -63,6 +63,8 @@ struct PdhgState {
   int passes, rejects;
   int pow_base;                      // step_iter value that pow tables entry 0 belongs to
   int accepted_last;                 // multi-GPU: the previous pass was accepted (its A^T y' becomes current)
+  int done;                          // device-driven loop: the solve has terminated -- every later kernel is a no-op
+  int pad0;
   double pow_red[kPowTab];           // (k+1)^-0.3 for k = pow_base+1+i   (host-computed, glibc pow)
   double pow_grow[kPowTab];          // (k+1)^-0.6
 };

@@ -79,7 +79,7 @@ primal_step_kernel(int n, PdhgState* __restrict__ st, double* __restrict__ x0, d
 // (one CTA each, tree-summed); the last segment of a row to finish combines the partial sums in
 // segment order and runs the epilogue.
 // `due` != nullptr: speculative check-iteration launch -- run only if the check iteration has been reached
-__device__ __forceinline__ bool check_not_due(const PdhgState* due) { return due && due->iter < due->stop_iter; }
+__device__ __forceinline__ bool check_not_due(const PdhgState* due) { return due && (due->done || due->iter < due->stop_iter); }
 
 struct PlainEpilogue {
   static constexpr int NACC = 0;
@@ -733,7 +733,7 @@ average_kernel(int len, const double* __restrict__ v, double* __restrict__ sum, 
 __global__ void __launch_bounds__(kThreads)
 average_dev_kernel(int len, const double* __restrict__ v0, const double* __restrict__ v1, double* __restrict__ sum,
                    double* __restrict__ avg, const PdhgState* __restrict__ st) {
-  if (st->iter < st->stop_iter) return;
+  if (check_not_due(st)) return;
   const double* __restrict__ v = st->cur ? v1 : v0;
   const bool pending = st->pending != 0;
   const double w = st->w_pending;
@@ -747,7 +747,7 @@ average_dev_kernel(int len, const double* __restrict__ v0, const double* __restr
 }
 // after both averages (and the multi-GPU A^T y materialisation) consumed them
 __global__ void check_clear_kernel(PdhgState* st) {
-  if (st->iter < st->stop_iter) return;
+  if (check_not_due(st)) return;
   st->pending = 0;
   st->accepted_last = 0;
 }
@@ -812,7 +812,7 @@ col_check_fused_kernel(int n, ColIter it0, ColIter it1, const double* __restrict
                        double* __restrict__ out, const PdhgState* __restrict__ st, ColIter alt0) {
   // st != nullptr (speculative launch): skip unless due; the current iterate is it0 if cur == 0, alt0 otherwise
   if (st) {
-    if (st->iter < st->stop_iter) return;
+    if (check_not_due(st)) return;
     if (st->cur) it0 = alt0;
   }
   double acc[20];
@@ -850,7 +850,7 @@ __global__ void __launch_bounds__(kThreads)
 row_check_fused_kernel(int m, RowIter it0, RowIter it1, const double* __restrict__ b, const double* __restrict__ rsca,
                        int neq, ReduceScratch rs, double* __restrict__ out, const PdhgState* __restrict__ st, RowIter alt0) {
   if (st) {
-    if (st->iter < st->stop_iter) return;
+    if (check_not_due(st)) return;
     if (st->cur) it0 = alt0;
   }
   double acc[8];
@@ -1022,7 +1022,7 @@ __global__ void __launch_bounds__(kThreads) fill_kernel(int len, double* __restr
 // Every kernel is a no-op unless the check iteration has been reached and the solve is still running, so the host can
 // enqueue checks speculatively between graphs of passes.
 __device__ __forceinline__ bool check_live(const PdhgState* st, const SolveCtl* ctl) {
-  return ctl->term < 0 && st->iter >= st->stop_iter;
+  return ctl->term < 0 && !st->done && st->iter >= st->stop_iter;
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -1068,7 +1068,10 @@ __device__ __forceinline__ void col_terms(double x, double aty, double ci, doubl
   t[6] = x * x; t[7] = k * k; t[8] = bl * bl; t[9] = bu * bu;
 }
 
-struct CheckRowEpilogue {
+// FLUSH: ybar is formed here from ySum (one GPU).  !FLUSH (several GPUs: the partial A_g'ybar had to be launched before
+// this kernel could run, so ybar was formed by average_dev_kernel): ybar is read
+template <bool FLUSH>
+struct CheckRowEpilogueT {
   static constexpr int NACC = 8;
   const PdhgState* st;
   const SolveCtl* ctl;
@@ -1090,18 +1093,25 @@ struct CheckRowEpilogue {
   }
   __device__ const double* input() const { return xavg; }
   double p_y, p_ax, p_ys, p_b, p_sc;
-  __device__ void prefetch(int r) { p_y = y[r]; p_ax = ax[r]; p_ys = ysum[r]; p_b = b[r]; p_sc = rsc[r]; }
+  __device__ void prefetch(int r) { p_y = y[r]; p_ax = ax[r]; p_ys = FLUSH ? ysum[r] : yavg[r]; p_b = b[r]; p_sc = rsc[r]; }
   __device__ void row(int r, double s, double* t) const {
     axavg[r] = s;
-    double ys = p_ys;
-    if (pend) { ys = ys + w * p_y; ysum[r] = ys; }
-    const double ya = ys * scale;
-    yavg[r] = ya;
+    double ya;
+    if (FLUSH) {
+      double ys = p_ys;
+      if (pend) { ys = ys + w * p_y; ysum[r] = ys; }
+      ya = ys * scale;
+      yavg[r] = ya;
+    } else {
+      ya = p_ys;
+    }
     const bool ineq = r >= neq;
     row_terms(p_y, p_ax, p_b, p_sc, ineq, t);
     row_terms(ya, s, p_b, p_sc, ineq, t + 4);
   }
 };
+
+using CheckRowEpilogue = CheckRowEpilogueT<true>;
 
 struct CheckColEpilogue {
   static constexpr int NACC = 20;
@@ -1173,6 +1183,7 @@ __device__ void trace_row_dev(SolveCtl* c, const PdhgState* st, int restart) {
 // C4: sums (fixed order) -> residuals (PDHG_Compute_Residuals / _Infeas_Residuals, cupdlp_solver.c:473-529, :433-471)
 // -> PDHG_Check_Termination[_Average] (:797-841), PDHG_Check_Infeasibility (:740-795), limits (:1057-1067), restart choice
 constexpr int kCheckSums = 28;
+__device__ void decide_from_sums(PdhgState* st, SolveCtl* ctl, const double* tot, bool timed_out);
 __global__ void __launch_bounds__(kStepThreads)
 check_decide_kernel(PdhgState* __restrict__ st, SolveCtl* __restrict__ ctl, const double* __restrict__ prow, int nbr,
                     const double* __restrict__ pcol, int nbc) {
@@ -1198,6 +1209,20 @@ check_decide_kernel(PdhgState* __restrict__ st, SolveCtl* __restrict__ ctl, cons
   }
   __syncthreads();
   if (threadIdx.x != 0) return;
+  decide_from_sums(st, ctl, tot, ctl->time_flag && *ctl->time_flag);
+}
+
+// several GPUs: the 28 sums were all-reduced over the ranks (identical on every rank, added in rank order) into
+// outs[0..19] (column side, 10 per iterate), outs[20..27] (row side, 4 per iterate), outs[28] (# ranks past the time limit)
+__global__ void check_decide_sums_kernel(PdhgState* __restrict__ st, SolveCtl* __restrict__ ctl, const double* __restrict__ outs) {
+  if (threadIdx.x != 0 || !check_live(st, ctl)) return;
+  double tot[kCheckSums];
+  for (int a = 0; a < 8; a++) tot[a] = outs[20 + a];
+  for (int a = 0; a < 20; a++) tot[8 + a] = outs[a];
+  decide_from_sums(st, ctl, tot, outs[28] > 0.0);
+}
+
+__device__ void decide_from_sums(PdhgState* st, SolveCtl* ctl, const double* tot, bool timed_out) {
   const double sense = ctl->sense, offset = ctl->offset;
   for (int t = 0; t < 2; t++) {
     const double* a = tot + 8 + 10 * t;
@@ -1234,14 +1259,17 @@ check_decide_kernel(PdhgState* __restrict__ st, SolveCtl* __restrict__ ctl, cons
       if (R.dinf_obj < 0.0 && R.dinf_res < -ft * R.dinf_obj) inf = true;
     }
     if (inf) term = 3;                                              // INFEASIBLE_OR_UNBOUNDED
-    else if (ctl->time_flag && *ctl->time_flag) term = 4;           // TIMELIMIT_OR_ITERLIMIT
+    else if (timed_out) term = 4;                                   // TIMELIMIT_OR_ITERLIMIT
     else if (st->iter >= ctl->iter_limit - 1) term = 4;
   }
   if (term >= 0) {
     trace_row_dev(ctl, st, 0);
     ctl->term_iterate = term_iterate;
+    st->pending = 0;
+    st->accepted_last = 0;
+    st->done = 1;       // from here on every kernel of the solve is a no-op
     __threadfence();
-    ctl->term = term;   // from here on every kernel of the solve is a no-op
+    ctl->term = term;
     return;
   }
   if (ctl->restart_on) ctl->restart_choice = decide_restart_dev(st, ctl);
@@ -1287,13 +1315,40 @@ restart_sweep_kernel(int n, int m, double* __restrict__ x0, double* __restrict__
 // host loop does after a check: trace row, next check iteration (cupdlp_solver.c:953-962), step-rule power tables
 constexpr int kFinishThreads = 128;
 static_assert(kFinishThreads == kPowTab, "one thread per power-table entry");
+// several GPUs: block partials of the epilogue sums (acc-major, nb per accumulator) -> nacc scalars at out[], added in block
+// order; `flag_slot` >= 0: out[flag_slot] = 1 if this rank's host has raised the time-limit word (summed by the exchange)
+__global__ void __launch_bounds__(kStepThreads)
+reduce_partials_kernel(const PdhgState* __restrict__ st, const SolveCtl* __restrict__ ctl, int nacc,
+                       const double* __restrict__ partials, int nb, double* __restrict__ out, int flag_slot, int need_restart) {
+  if (!check_live(st, ctl)) return;
+  if (need_restart && ctl->restart_choice == 0) return;
+  __shared__ double sm[kStepThreads / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int a = 0; a < nacc; a++) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nb; i += kStepThreads) s += partials[(size_t)a * nb + i];
+    s = warp_sum(s);
+    __syncthreads();
+    if (lane == 0) sm[wid] = s;
+    __syncthreads();
+    if (wid == 0) {
+      double t = sm[lane];
+      t = warp_sum(t);
+      if (lane == 0) out[a] = t;
+    }
+  }
+  if (threadIdx.x == 0 && flag_slot >= 0) out[flag_slot] = (ctl->time_flag && *ctl->time_flag) ? 1.0 : 0.0;
+}
+
+// sums2 != nullptr (several GPUs): the two restart sums were reduced and all-reduced already
 __global__ void __launch_bounds__(kFinishThreads)
-check_finish_kernel(PdhgState* __restrict__ st, SolveCtl* __restrict__ ctl, const double* __restrict__ prst, int nbs) {
+check_finish_kernel(PdhgState* __restrict__ st, SolveCtl* __restrict__ ctl, const double* __restrict__ prst, int nbs,
+                    const double* __restrict__ sums2) {
   if (!check_live(st, ctl)) return;
   __shared__ double sm[2][kFinishThreads / 32];
   const int choice = ctl->restart_choice;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (choice) {
+  if (choice && !sums2) {
     for (int a = 0; a < 2; a++) {
       double s = 0.0;
       for (int i = threadIdx.x; i < nbs; i += kFinishThreads) s += prst[(size_t)a * nbs + i];
@@ -1306,7 +1361,8 @@ check_finish_kernel(PdhgState* __restrict__ st, SolveCtl* __restrict__ ctl, cons
   if (threadIdx.x == 0) {
     if (choice) {
       double d2[2];
-      for (int a = 0; a < 2; a++) { double s = 0.0; for (int w = 0; w < kFinishThreads / 32; w++) s += sm[a][w]; d2[a] = s; }
+      if (sums2) { d2[0] = sums2[0]; d2[1] = sums2[1]; }
+      else for (int a = 0; a < 2; a++) { double s = 0.0; for (int w = 0; w < kFinishThreads / 32; w++) s += sm[a][w]; d2[a] = s; }
       const DevResiduals& R = choice == 1 ? ctl->res[1] : ctl->res[0];
       ctl->pf_lr = R.pfeas; ctl->df_lr = R.dfeas; ctl->gap_lr = R.gap;
       const double mean = sqrt(st->tau * st->sigma);
@@ -1529,8 +1585,26 @@ void launch_restart_sweep(cudaStream_t s, int n, int m, double* x0, double* x1, 
   restart_sweep_kernel<<<restart_sweep_grid(n, m), kThreads, 0, s>>>(n, m, x0, x1, aty0, aty1, xavg, atyavg, xsum, xlr, y0,
                                                                     y1, ax0, ax1, yavg, axavg, ysum, ylr, st, ctl, rs);
 }
-void launch_check_finish(cudaStream_t s, PdhgState* st, SolveCtl* ctl, const double* prst, int nbs) {
-  check_finish_kernel<<<1, kFinishThreads, 0, s>>>(st, ctl, prst, nbs);
+void launch_check_finish(cudaStream_t s, PdhgState* st, SolveCtl* ctl, const double* prst, int nbs, const double* sums2) {
+  check_finish_kernel<<<1, kFinishThreads, 0, s>>>(st, ctl, prst, nbs, sums2);
+}
+// ---- several GPUs
+void launch_spmv_check_rows_mg(cudaStream_t s, const DevSell& A, const PdhgState* st, const SolveCtl* ctl, const double* xfull,
+                               const double* y0, const double* y1, const double* ax0, const double* ax1, const double* yavg,
+                               double* axavg, const double* b, const double* rsc, int neq, ReduceScratch rs) {
+  if (A.nblocks_body + A.nsegs == 0) return;
+  CheckRowEpilogueT<false> e{};
+  e.st = st; e.ctl = ctl; e.xavg = xfull; e.y0 = y0; e.y1 = y1; e.ax0 = ax0; e.ax1 = ax1; e.ysum = nullptr;
+  e.yavg = const_cast<double*>(yavg); e.axavg = axavg; e.b = b; e.rsc = rsc; e.neq = neq;
+  rs.terms = nullptr; rs.flags = 0;
+  spmv_sell_kernel<CheckRowEpilogueT<false>><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, rs);
+}
+void launch_reduce_partials(cudaStream_t s, const PdhgState* st, const SolveCtl* ctl, int nacc, const double* partials, int nb,
+                            double* out, int flag_slot, int need_restart) {
+  reduce_partials_kernel<<<1, kStepThreads, 0, s>>>(st, ctl, nacc, partials, nb, out, flag_slot, need_restart);
+}
+void launch_check_decide_sums(cudaStream_t s, PdhgState* st, SolveCtl* ctl, const double* outs) {
+  check_decide_sums_kernel<<<1, 32, 0, s>>>(st, ctl, outs);
 }
 
 

@@ -86,7 +86,14 @@ void launch_restart_sweep(cudaStream_t s, int n, int m, double* x0, double* x1, 
                           const double* xavg, const double* atyavg, double* xsum, double* xlr, double* y0, double* y1,
                           double* ax0, double* ax1, const double* yavg, const double* axavg, double* ysum, double* ylr,
                           const PdhgState* st, const SolveCtl* ctl, ReduceScratch rs);
-void launch_check_finish(cudaStream_t s, PdhgState* st, SolveCtl* ctl, const double* prst, int nbs);
+void launch_check_finish(cudaStream_t s, PdhgState* st, SolveCtl* ctl, const double* prst, int nbs, const double* sums2 = nullptr);
+// several GPUs (fused peer-memory path): row side with ybar already formed, partial sums -> scalars, decision from all-reduced sums
+void launch_spmv_check_rows_mg(cudaStream_t s, const DevSell& A, const PdhgState* st, const SolveCtl* ctl, const double* xfull,
+                               const double* y0, const double* y1, const double* ax0, const double* ax1, const double* yavg,
+                               double* axavg, const double* b, const double* rsc, int neq, ReduceScratch rs);
+void launch_reduce_partials(cudaStream_t s, const PdhgState* st, const SolveCtl* ctl, int nacc, const double* partials, int nb,
+                            double* out, int flag_slot, int need_restart);
+void launch_check_decide_sums(cudaStream_t s, PdhgState* st, SolveCtl* ctl, const double* outs);
 
 // ---- HiPDLP mode (reflected Halpern PDHG; pdhg_kernels.cu, last section)
 struct HipCheckArgs {
