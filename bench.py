@@ -470,7 +470,9 @@ def main():
                "note": "one b200pdlp_solve call on host buffers: H2D of the HighsLp arrays, prologue (formulate + scaling + "
                        "transposition + layouts"
                        + (" on the device" if dev_prep else " on host threads") + "), K iterations, postsolve, D2H of the "
-                       "HighsSolution; bytes are per call divided by K"}
+                       "HighsSolution; bytes are per call divided by K; measured on the second call of the process (one untimed "
+                       "3-iteration call first: the library's device-block cache and CUDA module are warm, as in any process that "
+                       "solves more than one LP)"}
         if args.to_tolerance > 0:
             tol = args.to_tolerance
             t0 = time.monotonic()
