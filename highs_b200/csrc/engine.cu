@@ -399,6 +399,20 @@ struct DeviceSetup {
   }
 };
 
+// experiment (B200PDLP_SPMV_CTAS_PER_SM=k, one GPU, tree mode): the SpMV bodies run on a persistent grid of k CTAs per SM and
+// walk their slices in a software pipeline (spmv_sell_kernel<Epi, true>) instead of one CTA per 8 slices
+static void apply_spmv_grid(b200pdlp_problem* p) {
+  const char* e = getenv("B200PDLP_SPMV_CTAS_PER_SM");
+  if (!e || p->world != 1 || p->ordered) return;
+  const int k = atoi(e);
+  if (k <= 0) return;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+  for (DeviceMatrix* M : {&p->A, &p->AT}) {
+    if (M->dev.nblocks_body > sms * k) { M->dev.nblocks_body = sms * k; M->dev.pipelined = 1; }
+  }
+}
+
 static void alloc_host_mirrors(b200pdlp_problem* p) {
   p->hstate = static_cast<PdhgState*>(pinned_cache_alloc(sizeof(PdhgState), false));
   p->houts = static_cast<double*>(pinned_cache_alloc(kOutsCount * sizeof(double), false));
@@ -479,6 +493,7 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
     if (world == 1) p->pass_flags = v >= 2 ? 6 : (v == 1 ? 2 : 0);
   }
   if (const char* e = getenv("B200PDLP_PREFETCH")) { p->A.dev.prefetch_dist = atoi(e); p->AT.dev.prefetch_dist = atoi(e); }
+  apply_spmv_grid(p);
   const int nl = p->nl;
   for (int k = 0; k < 2; k++) { p->x[k].alloc(nl); p->aty[k].alloc(nl); p->y[k].alloc(ml); p->ax[k].alloc(ml); }
   p->xsum.alloc(nl); p->xavg.alloc(nl); p->atyavg.alloc(nl); p->xlr.alloc(nl);
@@ -591,6 +606,7 @@ static void create_problem_device(const b200pdlp_lp& lp, const b200pdlp_params& 
   P.arr.cost = P.arr.lower = P.arr.upper = P.arr.colscale = P.arr.rhs = P.arr.rowscale = nullptr;
   if (const char* ev = getenv("B200PDLP_PDL")) { const int v = atoi(ev); p->pass_flags = v >= 2 ? 6 : (v == 1 ? 2 : 0); }
   if (const char* ev = getenv("B200PDLP_PREFETCH")) { p->A.dev.prefetch_dist = atoi(ev); p->AT.dev.prefetch_dist = atoi(ev); }
+  apply_spmv_grid(p);
   // iterates and scratch: uninitialised (the solve's initial-point kernels write every entry they read)
   for (int k = 0; k < 2; k++) { p->x[k].alloc(n, false); p->aty[k].alloc(n, false); p->y[k].alloc(m, false); p->ax[k].alloc(m, false); }
   p->xsum.alloc(n, false); p->xavg.alloc(n, false); p->atyavg.alloc(n, false); p->xlr.alloc(n, false);

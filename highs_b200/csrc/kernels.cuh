@@ -118,6 +118,7 @@ struct DevSell {
   unsigned* long_counter;
   int prefetch_dist;                      // CTAs ahead whose col/val range is pulled into L2 (0 = off)
   int padded_total;                       // elements in col/val (end of the last slice)
+  int pipelined;                          // 1: nblocks_body is a persistent grid (a few CTAs per SM), slices walked in a software pipeline
 };
 
 // peer-memory view for the fused multi-GPU path (one process per GPU, buffers mapped with CUDA IPC)

@@ -270,7 +270,8 @@ step_rule_kernel(PdhgState* __restrict__ st, ReduceScratch r1, int nb1, ReduceSc
   }
 }
 
-template <class Epi>
+// PIPE: persistent grid (DevSell::pipelined), slices walked in a software pipeline; !PIPE: one CTA per 8 slices
+template <class Epi, bool PIPE = false>
 __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_arg, ReduceScratch rs) {
   Epi epi = epi_arg;
   pdl_entry(rs.flags);
@@ -292,7 +293,87 @@ __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_
       }
     }
   }
-  if ((int)blockIdx.x < A.nblocks_body) {
+  if (PIPE && (int)blockIdx.x < A.nblocks_body) {
+    // A warp walks the slices  w, w + W, w + 2W, ...  (W = warps of the body CTAs).  With one CTA per 8 slices (the default
+    // grid) that is exactly one slice per warp; with a persistent grid (DevSell::nblocks_body = a few CTAs per SM) the walk
+    // is software-pipelined: the descriptor is fetched two slices ahead and the first 8 column ids one slice ahead, so that
+    // a slice's gathers issue at once instead of after two dependent round trips (descriptor -> column ids -> gathers).
+    // Per-row arithmetic and its order are the same in both shapes.
+    const int lane = threadIdx.x & 31;
+    const int wstride = A.nblocks_body * (kThreads / 32);
+    int slice = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    int4 d = make_int4(0, 0, -1, 0), dn = make_int4(0, 0, -1, 0);
+    int cpre[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (slice < A.nslices) {
+      d = A.slices[slice];
+      if (slice + wstride < A.nslices) dn = A.slices[slice + wstride];
+      if (d.y >= 8) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) cpre[u] = A.col[d.x + lane + 32 * u];
+      }
+    }
+    while (slice < A.nslices) {
+      int4 dnn = make_int4(0, 0, -1, 0);
+      if (slice + 2 * wstride < A.nslices) dnn = A.slices[slice + 2 * wstride];
+      int cnx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (slice + wstride < A.nslices && dn.y >= 8) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) cnx[u] = A.col[dn.x + lane + 32 * u];
+      }
+      const int row = slice * 32 + lane;
+      const bool live = !((unsigned)d.z >> lane & 1u);
+      if (live) epi.prefetch(row);
+      const int* __restrict__ cp = A.col + d.x + lane;
+      const double* __restrict__ vp = A.val + d.x + lane;
+      double s = 0.0;
+      int k = 0;
+      if (d.y >= 8) {
+        double v[8], g[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) g[u] = xin[cpre[u]];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = vp[32 * u];
+#pragma unroll
+        for (int u = 0; u < 8; u++) s += v[u] * g[u];
+        k = 8;
+      }
+      for (; k + 8 <= d.y; k += 8) {
+        int c[8];
+        double v[8], g[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) c[u] = cp[32 * (k + u)];
+#pragma unroll
+        for (int u = 0; u < 8; u++) g[u] = xin[c[u]];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = vp[32 * (k + u)];
+#pragma unroll
+        for (int u = 0; u < 8; u++) s += v[u] * g[u];
+      }
+      for (; k + 4 <= d.y; k += 4) {
+        const int c0 = cp[32 * k], c1 = cp[32 * k + 32], c2 = cp[32 * k + 64], c3 = cp[32 * k + 96];
+        const double g0 = xin[c0], g1 = xin[c1], g2 = xin[c2], g3 = xin[c3];
+        const double v0 = vp[32 * k], v1 = vp[32 * k + 32], v2 = vp[32 * k + 64], v3 = vp[32 * k + 96];
+        s += v0 * g0;
+        s += v1 * g1;
+        s += v2 * g2;
+        s += v3 * g3;
+      }
+      for (; k < d.y; k++) s += vp[32 * k] * xin[cp[32 * k]];
+      if (live) {
+        double t[Epi::NACC > 0 ? Epi::NACC : 1];
+        epi.row(row, s, t);
+        if constexpr (Epi::NACC > 0) {
+#pragma unroll
+          for (int a = 0; a < Epi::NACC; a++) add_term(acc[a], t[a], rs, a, row);
+        }
+      }
+      d = dn;
+      dn = dnn;
+#pragma unroll
+      for (int u = 0; u < 8; u++) cpre[u] = cnx[u];
+      slice += wstride;
+    }
+  } else if ((int)blockIdx.x < A.nblocks_body) {
     const int slice = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (slice < A.nslices) {
@@ -1430,7 +1511,8 @@ void launch_primal_step(cudaStream_t s, int n, PdhgState* st, double* x0, double
 void launch_spmv_plain(cudaStream_t s, const DevSell& A, const double* in, double* out, const PdhgState* due) {
   if (A.nblocks_body + A.nsegs == 0) return;
   PlainEpilogue e{in, out, due};
-  spmv_sell_kernel<PlainEpilogue><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr, nullptr, 0, 0});
+  if (A.pipelined) spmv_sell_kernel<PlainEpilogue, true><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr, nullptr, 0, 0});
+  else spmv_sell_kernel<PlainEpilogue, false><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr, nullptr, 0, 0});
 }
 
 void launch_spmv_dual(cudaStream_t s, const DevSell& A, PdhgState* st, const double* x0, const double* x1,
@@ -1440,7 +1522,8 @@ void launch_spmv_dual(cudaStream_t s, const DevSell& A, PdhgState* st, const dou
   DualEpilogue e{};
   e.st = st; e.x0 = x0; e.x1 = x1; e.y0 = y0; e.y1 = y1; e.ax0 = ax0; e.ax1 = ax1; e.b = b; e.ysum = ysum;
   e.neq = neq; e.row_offset = row_offset;
-  launch_k(spmv_sell_kernel<DualEpilogue>, A.nblocks_body + A.nsegs, kThreads, s, rs.flags, A, e, rs);
+  if (A.pipelined) launch_k(spmv_sell_kernel<DualEpilogue, true>, A.nblocks_body + A.nsegs, kThreads, s, rs.flags, A, e, rs);
+  else launch_k(spmv_sell_kernel<DualEpilogue, false>, A.nblocks_body + A.nsegs, kThreads, s, rs.flags, A, e, rs);
 }
 
 void launch_spmv_primal(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
@@ -1448,7 +1531,8 @@ void launch_spmv_primal(cudaStream_t s, const DevSell& A, PdhgState* st, const d
   if (A.nblocks_body + A.nsegs == 0) return;   // no rows on this rank: nothing to launch, the partial count is 0
   PrimalEpilogue e{};
   e.st = st; e.y0 = y0; e.y1 = y1; e.x0 = x0; e.x1 = x1; e.aty0 = aty0; e.aty1 = aty1;
-  launch_k(spmv_sell_kernel<PrimalEpilogue>, A.nblocks_body + A.nsegs, kThreads, s, rs.flags, A, e, rs);
+  if (A.pipelined) launch_k(spmv_sell_kernel<PrimalEpilogue, true>, A.nblocks_body + A.nsegs, kThreads, s, rs.flags, A, e, rs);
+  else launch_k(spmv_sell_kernel<PrimalEpilogue, false>, A.nblocks_body + A.nsegs, kThreads, s, rs.flags, A, e, rs);
 }
 
 // multi-GPU K3a: partial A_g' y' into buf (input chosen by the device state)
@@ -1559,7 +1643,8 @@ void launch_spmv_check_rows(cudaStream_t s, const DevSell& A, const PdhgState* s
   e.st = st; e.ctl = ctl; e.xavg = xavg; e.y0 = y0; e.y1 = y1; e.ax0 = ax0; e.ax1 = ax1; e.ysum = ysum; e.yavg = yavg;
   e.axavg = axavg; e.b = b; e.rsc = rsc; e.neq = neq;
   rs.terms = nullptr; rs.flags = 0;
-  spmv_sell_kernel<CheckRowEpilogue><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, rs);
+  if (A.pipelined) spmv_sell_kernel<CheckRowEpilogue, true><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, rs);
+  else spmv_sell_kernel<CheckRowEpilogue, false><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, rs);
 }
 void launch_spmv_check_cols(cudaStream_t s, const DevSell& AT, const PdhgState* st, const SolveCtl* ctl, const double* yavg,
                             const double* x0, const double* x1, const double* aty0, const double* aty1, const double* xavg,
@@ -1570,7 +1655,8 @@ void launch_spmv_check_cols(cudaStream_t s, const DevSell& AT, const PdhgState* 
   e.st = st; e.ctl = ctl; e.yavg = yavg; e.x0 = x0; e.x1 = x1; e.aty0 = aty0; e.aty1 = aty1; e.xavg = xavg;
   e.atyavg = atyavg; e.c = c; e.lo = lo; e.up = up; e.cs = cs;
   rs.terms = nullptr; rs.flags = 0;
-  spmv_sell_kernel<CheckColEpilogue><<<AT.nblocks_body + AT.nsegs, kThreads, 0, s>>>(AT, e, rs);
+  if (AT.pipelined) spmv_sell_kernel<CheckColEpilogue, true><<<AT.nblocks_body + AT.nsegs, kThreads, 0, s>>>(AT, e, rs);
+  else spmv_sell_kernel<CheckColEpilogue, false><<<AT.nblocks_body + AT.nsegs, kThreads, 0, s>>>(AT, e, rs);
 }
 void launch_check_decide(cudaStream_t s, PdhgState* st, SolveCtl* ctl, const double* prow, int nbr, const double* pcol,
                          int nbc) {

@@ -21,6 +21,8 @@ B200PDLP_PDL=1 run bench_pdl1 python bench.py --no-cpu-baseline
 B200PDLP_PDL=2 run bench_pdl2 python bench.py --no-cpu-baseline
 run tts_ours python bench.py --workload S2 --no-cpu-baseline --to-tolerance 1e-4
 run tts_ours_s3 python bench.py --workload S3 --no-cpu-baseline --to-tolerance 1e-4
+B200PDLP_SPMV_CTAS_PER_SM=4 T=400 run pytest_pipe python -m pytest tests/test_gpu_kernels.py tests/test_gpu_solve.py -q -m gpu -k 'synthetic or s2 or long_rows or dense or step_kernels'
+for k in 3 4 6; do B200PDLP_SPMV_CTAS_PER_SM=$k run bench_pipe$k python bench.py --no-cpu-baseline; done
 T=120 run dsmem_gather tools/dsmem_gather_bench
 T=120 run gather_bench tools/gather_bench
 B200PDLP_TIMING=1 run bench_s3b python bench.py --workload S3B --no-cpu-baseline
