@@ -617,6 +617,28 @@ void DevicePrologue::run(cudaStream_t s, const b200pdlp_lp& lp, bool do_scale, i
 
   nvtxRangePop();
   nvtxRangePushA("orderings + sliced-ELL layouts");
+  auto keep_the_form = [&]() {
+    // the standard form in standard-form order survives the prologue (tests: b200pdlp_problem_get_*; several GPUs: the host
+    // builds every rank's layouts from it)
+    auto dup_i = [&](const int* src, size_t cnt) { int* d = keep<int>(cnt); PREP_OK(cudaMemcpyAsync(d, src, cnt * sizeof(int), cudaMemcpyDeviceToDevice, s)); return d; };
+    auto dup_d = [&](const double* src, size_t cnt) { double* d = keep<double>(cnt); PREP_OK(cudaMemcpyAsync(d, src, cnt * sizeof(double), cudaMemcpyDeviceToDevice, s)); return d; };
+    form.cbeg = dup_i(cbeg, n + 1); form.cidx = dup_i(cidx, nnz); form.cval = dup_d(cval, nnz);
+    form.cost = dup_d(cost, n); form.lower = dup_d(lower, n); form.upper = dup_d(upper, n); form.colscale = dup_d(colscale, n);
+    form.rhs = dup_d(rhs, m); form.rowscale = dup_d(rowscale, m);
+    form.rptr = dup_i(rptr, m + 1); form.rpos = dup_i(rpos, nnz);
+    form.rcol = keep<int>(nnz);
+    if (nnz > 0) gather_i_kernel<<<grid_for(nnz), kTpb, 0, s>>>(nnz, colof, rpos, form.rcol);
+  };
+  if (stop_after_scaling) {
+    keep_the_form();
+    double hd[5] = {0, 0, 0, 0, 0};
+    PREP_OK(cudaMemcpyAsync(hd, dsc, 5 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    PREP_OK(cudaStreamSynchronize(s));
+    sc.norm_cost_sq = hd[0]; sc.norm_rhs_sq = hd[1]; sc.beta_cost_sq = hd[2]; sc.beta_rhs_sq = hd[3]; sc.amax = hd[4];
+    nvtxRangePop();
+    return;
+  }
+
   // ---- device orderings and sliced-ELL plans
   arr.rperm = keep<int>(m); arr.rinv = keep<int>(m);
   arr.cperm = keep<int>(n); arr.cinv = keep<int>(n);
@@ -725,15 +747,7 @@ void DevicePrologue::run(cudaStream_t s, const b200pdlp_lp& lp, bool do_scale, i
     gather_d_kernel<<<grid_for(m), kTpb, 0, s>>>(m, rowscale, arr.rperm, arr.rowscale);
   }
   PREP_OK(cudaGetLastError());
-  if (keep_form) {
-    // tests: the standard form in standard-form order survives the prologue (b200pdlp_problem_get_* read it back)
-    auto dup_i = [&](const int* src, size_t cnt) { int* d = keep<int>(cnt); PREP_OK(cudaMemcpyAsync(d, src, cnt * sizeof(int), cudaMemcpyDeviceToDevice, s)); return d; };
-    auto dup_d = [&](const double* src, size_t cnt) { double* d = keep<double>(cnt); PREP_OK(cudaMemcpyAsync(d, src, cnt * sizeof(double), cudaMemcpyDeviceToDevice, s)); return d; };
-    form.cbeg = dup_i(cbeg, n + 1); form.cidx = dup_i(cidx, nnz); form.cval = dup_d(cval, nnz);
-    form.cost = dup_d(cost, n); form.lower = dup_d(lower, n); form.upper = dup_d(upper, n); form.colscale = dup_d(colscale, n);
-    form.rhs = dup_d(rhs, m); form.rowscale = dup_d(rowscale, m);
-    form.rptr = dup_i(rptr, m + 1); form.rpos = dup_i(rpos, nnz);
-  }
+  if (keep_form) keep_the_form();
   nvtxRangePop();
   int tb = 0;
   PREP_OK(cudaMemcpyAsync(&tb, too_big, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -865,7 +879,7 @@ void DevSellOwned::release() {
 void DevicePrologue::release_form() {
   dev_cache_free(form.cbeg); dev_cache_free(form.cidx); dev_cache_free(form.cval); dev_cache_free(form.cost);
   dev_cache_free(form.lower); dev_cache_free(form.upper); dev_cache_free(form.colscale); dev_cache_free(form.rhs);
-  dev_cache_free(form.rowscale); dev_cache_free(form.rptr); dev_cache_free(form.rpos);
+  dev_cache_free(form.rowscale); dev_cache_free(form.rptr); dev_cache_free(form.rpos); dev_cache_free(form.rcol);
   form = DevStdForm();
 }
 

@@ -70,7 +70,7 @@ struct DevSellOwned {   // one sliced-ELL matrix, blocks owned through the cache
 };
 
 struct DevStdForm {     // tests only (keep_form): the scaled standard form, standard-form order
-  int *cbeg = nullptr, *cidx = nullptr, *rptr = nullptr, *rpos = nullptr;
+  int *cbeg = nullptr, *cidx = nullptr, *rptr = nullptr, *rpos = nullptr, *rcol = nullptr;   // rcol[q] = column of position rpos[q]
   double *cval = nullptr, *cost = nullptr, *lower = nullptr, *upper = nullptr, *colscale = nullptr, *rhs = nullptr,
          *rowscale = nullptr;
 };
@@ -81,6 +81,7 @@ struct DevicePrologue {
   DevSellOwned A, AT;
   DevStdForm form;
   bool keep_form = false;
+  bool stop_after_scaling = false;   // formulate + row index + scaling only (several GPUs: the layouts are built per rank by the host)
   size_t h2d_bytes = 0;
   // formulate + scale + row index + orderings + sliced-ELL layouts, all on stream `s`; returns with the stream idle.
   // Throws std::exception on bad input / CUDA errors (the caller releases what was produced so far).

@@ -419,6 +419,40 @@ static void alloc_host_mirrors(b200pdlp_problem* p) {
   p->hflag = static_cast<double*>(pinned_cache_alloc(4 * sizeof(double), false));   // [0] time-limit flag, [2] read-back of the barrier fault word
 }
 
+// Several GPUs (opt-in B200PDLP_MG_DEVICE_PREP=1): every rank needs the whole scaled standard form to cut its shard out of
+// it.  Instead of G processes running the host prologue side by side (they share the host's cores and memory bandwidth),
+// each rank formulates and scales on ITS GPU (a few milliseconds, identical bits on every rank) and downloads the result;
+// the per-rank layouts are then built by the host as before.
+static void device_form_to_host(const b200pdlp_lp& lp, const b200pdlp_params& prm, StdForm& f) {
+  cudaStream_t s = nullptr;
+  CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  DevicePrologue P;
+  P.keep_form = true;
+  P.stop_after_scaling = true;
+  struct Cleanup { DevicePrologue& P; cudaStream_t s; ~Cleanup() { P.release_arrays(); P.release_form(); cudaStreamDestroy(s); } } cleanup{P, s};
+  try { P.run(s, lp, prm.scaling != 0, 512); }
+  catch (const std::invalid_argument& ex) { throw Error(B200PDLP_ERR_ARG, ex.what()); }
+  catch (const std::exception& ex) { throw Error(B200PDLP_ERR_CUDA, ex.what()); }
+  f = StdForm();
+  const DevProblemArrays& a = P.arr;
+  const int n = a.n, m = a.m, nnz = a.nnz;
+  f.n = n; f.m = m; f.nnz = nnz; f.neq = a.neq; f.n_orig = a.n0;
+  f.sense = lp.sense; f.offset = lp.offset;
+  f.norm_cost = std::sqrt(P.sc.norm_cost_sq); f.norm_rhs = std::sqrt(P.sc.norm_rhs_sq); f.amax = P.sc.amax;
+  f.cbeg.resize(n + 1); f.cidx.resize(nnz); f.cval.resize(nnz);
+  f.cost.resize(n); f.lower.resize(n); f.upper.resize(n); f.col_scale.resize(n); f.rhs.resize(m); f.row_scale.resize(m);
+  f.row_new_idx.resize(m); f.row_class.resize(m);
+  f.rptr.resize(m + 1); f.rpos.resize(nnz); f.rcol.resize(nnz);
+  auto dn = [&](void* h, const void* d, size_t bytes) { if (bytes) CUDA_OK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s)); };
+  const DevStdForm& d = P.form;
+  dn(f.cbeg.data(), d.cbeg, (size_t)(n + 1) * 4); dn(f.cidx.data(), d.cidx, (size_t)nnz * 4); dn(f.cval.data(), d.cval, (size_t)nnz * 8);
+  dn(f.cost.data(), d.cost, (size_t)n * 8); dn(f.lower.data(), d.lower, (size_t)n * 8); dn(f.upper.data(), d.upper, (size_t)n * 8);
+  dn(f.col_scale.data(), d.colscale, (size_t)n * 8); dn(f.rhs.data(), d.rhs, (size_t)m * 8); dn(f.row_scale.data(), d.rowscale, (size_t)m * 8);
+  dn(f.rptr.data(), d.rptr, (size_t)(m + 1) * 4); dn(f.rpos.data(), d.rpos, (size_t)nnz * 4); dn(f.rcol.data(), d.rcol, (size_t)nnz * 4);
+  dn(f.row_new_idx.data(), a.row_new_idx, (size_t)m * 4); dn(f.row_class.data(), a.row_class, (size_t)m * 4);
+  CUDA_OK(cudaStreamSynchronize(s));
+}
+
 // shared_form != nullptr: the standard form was formulated and scaled already (by another rank of this process)
 static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, int rank, int world, b200pdlp_problem* p,
                            const StdForm* shared_form = nullptr) {
@@ -442,14 +476,20 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   std::unique_ptr<DeviceSetup> dev_setup;
   int dev_level = prm.device_scaling;
   if (const char* e = getenv("B200PDLP_DEVICE_SETUP")) dev_level = atoi(e);   // experiments: same switch from the environment
+  bool mg_dev_form = false;
+  if (!shared_form && world > 1 && lp.num_row > 0 && lp.num_col > 0 && lp.a_start[lp.num_col] > 0)
+    if (const char* ev = getenv("B200PDLP_MG_DEVICE_PREP")) mg_dev_form = atoi(ev) != 0;
   if (shared_form) {
     p->form = *shared_form;
     lap("copy of the scaled form");
+  } else if (mg_dev_form) {
+    device_form_to_host(lp, prm, p->form);
+    lap("formulate + scale on the device, download");
   } else {
     formulate(lp, p->form);
     lap("formulate");
   }
-  if (shared_form) {
+  if (shared_form || mg_dev_form) {
     // nothing to scale
   } else if (prm.scaling != 0 && dev_level != 0 && p->form.nnz > 0) {
     dev_setup.reset(new DeviceSetup());

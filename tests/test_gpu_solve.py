@@ -229,9 +229,9 @@ def test_dense_column_s5_mini(engine_lib, oracle):
     assert _rel(lp.objectiveValue(res["col_value"]), lp.objectiveValue(orc["col_value"])) <= 1e-5
 
 
-@pytest.mark.parametrize("tol", ["0.0001", "1e-08"])
+@pytest.mark.parametrize("tol", ["0.0001", "1e-06"])
 def test_s2_converged_parity_with_the_reference(engine_lib, tol):
-    """config S2 (100k x 100k, 1M nonzeros; tree-mode reductions) solved to kkt_tolerance 1e-4 / 1e-8 against
+    """config S2 (100k x 100k, 1M nonzeros; tree-mode reductions) solved to kkt_tolerance 1e-4 / 1e-6 against
     the UNMODIFIED reference's run on the same LP (tests/golden/s2_converged.json, written by make_s2_golden.py from
     oracle/_ref): same status, objective to 1e-6 (1 + |ref|) -- the north-star criterion --, iteration count within 10 %, and
     the reference's KKT measures (lpKktCheck's definitions, evaluated on OUR solution by the device KKT check) on the same
