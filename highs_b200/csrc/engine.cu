@@ -17,7 +17,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <limits>
+#include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -181,6 +184,26 @@ struct CudaEvent {   // RAII: released on every exit path
   operator cudaEvent_t() const { return e; }
 };
 
+// Logical shards (several ranks of ONE process, normally on one device): host-side rendezvous of the ranks' solve threads.
+// A rank's barrier kernel spins until its peers' kernels signal; on one device that needs the peers' kernels to be
+// schedulable -- anything on a peer's host thread that makes the driver serialise against running kernels (graph
+// instantiation / upload, allocations) must therefore happen BEFORE the first spinning kernel of any rank is launched.
+struct LocalGroup {
+  std::mutex m;
+  std::condition_variable cv;
+  int world = 0, count = 0;
+  unsigned long long gen = 0;
+  void arrive_and_wait() {
+    std::unique_lock<std::mutex> lk(m);
+    const unsigned long long g = gen;
+    if (++count == world) { count = 0; gen++; cv.notify_all(); return; }
+    if (!cv.wait_for(lk, std::chrono::seconds(120), [&] { return gen != g; })) {
+      count--;
+      throw std::runtime_error("logical shards: a peer rank's solve thread did not arrive");
+    }
+  }
+};
+
 struct Residuals {      // CUPDLPresobj for one iterate
   double pobj = 0, dobj = 0, pfeas = 0, dfeas = 0, gap = 0, relgap = 0;
   double pinf_obj = 0, pinf_res = 1, dinf_obj = 0, dinf_res = 1;
@@ -219,6 +242,8 @@ struct b200pdlp_problem {
     ~HipBuffers() { if (graph) cudaGraphExecDestroy(graph); if (hstate) pinned_cache_free(hstate); }
   } hip;
   bool local_link = false;         // peers are problems of this process (logical shards, b200pdlp_p2p_link_local)
+  std::shared_ptr<b200::LocalGroup> group;   // their host-side rendezvous
+  bool no_graph = false;           // B200PDLP_NO_GRAPH: every pass and check as direct launches (debugging aid)
   bool p2p = false;
   int p2p_pull = 0;                // 1: the primal kernel reads the peers' partials over NVLink; 0: peers push them
   PeerPtrs peers{};
@@ -327,14 +352,17 @@ static void allreduce_small(b200pdlp_problem* p, double* dptr, int k) {
 // B200PDLP_TIMING=1: wall-clock laps of the non-iterating parts on stderr (where does a short solve's time go)
 struct Laps {
   bool on = getenv("B200PDLP_TIMING") != nullptr;
+  int rank = -1;
   std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
   void operator()(const char* phase, const char* what) {
     if (!on) return;
     const auto t1 = std::chrono::steady_clock::now();
-    fprintf(stderr, "[b200pdlp %s] %-28s %8.1f ms\n", phase, what, std::chrono::duration<double, std::milli>(t1 - t).count());
+    if (rank >= 0) fprintf(stderr, "[b200pdlp %s r%d] %-28s %8.1f ms\n", phase, rank, what, std::chrono::duration<double, std::milli>(t1 - t).count());
+    else fprintf(stderr, "[b200pdlp %s] %-28s %8.1f ms\n", phase, what, std::chrono::duration<double, std::milli>(t1 - t).count());
     t = t1;
   }
 };
+
 
 // params.device_scaling >= 1: PDHG_Scale_Data on the GPU (setup_kernels.cu).  The unscaled column-major matrix and the
 // vectors go up once, the 10 Ruiz passes run while the host builds the row-major index of the nonzeros (which the
@@ -583,8 +611,16 @@ static bool use_device_prep(const b200pdlp_lp& lp, const b200pdlp_params& prm, i
   else if (prm.device_scaling != 0) return false;   // -1: host prologue; 1, 2: the staged variants of create_problem
   if (getenv("B200PDLP_DEVICE_SETUP")) return false;        // the round-1 staged variants (host formulate + device scaling)
   const int omax = prm.ordered_max == 0 ? 4096 : prm.ordered_max;
-  // ordered mode is decided on the standard form's size: n = num_col + (#BOUND rows) <= num_col + num_row
-  if (omax > 0 && std::max(lp.num_col + lp.num_row, lp.num_row) <= omax) return false;
+  // ordered mode (host_prep.cpp::build_layout) is decided on the STANDARD FORM's size: n = num_col + #BOUND rows
+  // (ranged and free rows get a slack column, CupdlpWrapper.cpp:328-345) -- count them when the answer depends on it
+  if (omax > 0 && lp.num_col <= omax && lp.num_row <= omax) {
+    int nbound = 0;
+    for (int i = 0; i < lp.num_row; i++) {
+      const bool lo = lp.row_lower[i] > -1e20, up = lp.row_upper[i] < 1e20;
+      nbound += (lo && up && lp.row_lower[i] != lp.row_upper[i]) || (!lo && !up);
+    }
+    if (lp.num_col + nbound <= omax) return false;
+  }
   if (lp.num_col <= 0 || lp.num_row <= 0 || lp.a_start[lp.num_col] <= 0) return false;
   return true;
 }
@@ -1206,7 +1242,7 @@ static void enqueue_check_device(b200pdlp_problem* p) {
                          p->yavg.p, p->axavg.p, p->rhs.p, p->rowscale.p, p->neq_local, rrow);
   launch_spmv_check_cols(s, p->AT.dev, st, ctl, p->yavg.p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->xavg.p,
                          p->atyavg.p, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, rcol);
-  launch_check_decide(s, st, ctl, rrow.partials, p->A.grid(), rcol.partials, p->AT.grid());
+  launch_check_decide(s, st, ctl, rrow.partials, p->A.grid(), rcol.partials, p->AT.grid(), rrow.counter);
   launch_restart_sweep(s, n, ml, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->xavg.p, p->atyavg.p, p->xsum.p,
                        p->xlr.p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->yavg.p, p->axavg.p, p->ysum.p, p->ylr.p,
                        st, ctl, rrst);
@@ -1215,6 +1251,7 @@ static void enqueue_check_device(b200pdlp_problem* p) {
 static constexpr int kCheckLaunches = 6;
 
 static void launch_check_graph(b200pdlp_problem* p) {
+  if (p->no_graph) { enqueue_check_device(p); p->launches += p->world > 1 ? 16 : kCheckLaunches; return; }
   if (!p->graph_check) {
     cudaGraph_t g = nullptr;
     CUDA_OK(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
@@ -1232,6 +1269,7 @@ static void launch_check_graph(b200pdlp_problem* p) {
 static void enqueue_passes_device(b200pdlp_problem* p, int d) {
   if (d <= 0) return;
   const int kp = p->kernels_per_pass;
+  if (p->no_graph) { for (; d > 0; d--) { enqueue_pass(p); p->launches += kp; } return; }
   if (d > p->graph_main_passes - 12 && !p->graph_main) p->graph_main = capture_passes(p, p->graph_main_passes);
   if (d > p->graph_main_passes - 12 && d <= p->graph_main_passes) {
     CUDA_OK(cudaGraphLaunch(p->graph_main, p->stream));
@@ -1271,6 +1309,42 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   h->adaptive = prm.adaptive_step != 0;
   out->trace_len = 0;
   Laps lap;
+  lap.rank = p->world > 1 ? p->rank : -1;
+  if (p->local_link && p->group) {
+    // logical shards: everything that allocates or instantiates happens before ANY rank launches a kernel that waits for
+    // its peers (see LocalGroup)
+    const int interval0 = prm.check_interval > 0 ? prm.check_interval : 40;
+    const int want0 = std::min(prm.graph_passes > 0 ? prm.graph_passes : interval0 + 4, kPowTab - 16);
+    p->kernels_per_pass = (p->p2p && p->p2p_pull) ? 5 : 6;
+    if (p->graph_main && p->graph_main_passes != want0) { cudaGraphExecDestroy(p->graph_main); p->graph_main = nullptr; }
+    p->graph_main_passes = want0;
+    if (!getenv("B200PDLP_NO_GRAPH")) {
+      if (!p->graph_main) p->graph_main = capture_passes(p, want0);
+      if (!p->graph_small) { p->graph_small_passes = 4; p->graph_small = capture_passes(p, 4); }
+      CUDA_OK(cudaGraphUpload(p->graph_main, s));
+      CUDA_OK(cudaGraphUpload(p->graph_small, s));
+      if (use_device_checks(p, prm)) {
+        if (!p->hctl) {
+          p->hctl = static_cast<SolveCtl*>(pinned_cache_alloc(sizeof(SolveCtl), false));
+          p->htime = static_cast<int*>(pinned_cache_alloc(64, true));
+          p->ctl.alloc(1, false);
+        }
+        for (int k = 2; k <= 5; k++) if (!p->graph_pow2[k]) { p->graph_pow2[k] = capture_passes(p, 1 << k); CUDA_OK(cudaGraphUpload(p->graph_pow2[k], s)); }
+        if (!p->graph_check) {
+          cudaGraph_t g = nullptr;
+          CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+          enqueue_check_device(p);
+          CUDA_OK(cudaStreamEndCapture(s, &g));
+          CUDA_OK(cudaGraphInstantiate(&p->graph_check, g, 0));
+          CUDA_OK(cudaGraphDestroy(g));
+          CUDA_OK(cudaGraphUpload(p->graph_check, s));
+        }
+      }
+    }
+    CUDA_OK(cudaStreamSynchronize(s));
+    lap("solve", "graphs ready (logical shards)");
+    p->group->arrive_and_wait();
+  }
 
   // ---- initial point: PDHG_PreSolve (hot start, cupdlp_solver.c:1217-1279) + PDHG_Init_Variables (:531-591)
   const bool dev_form = p->dev_form;
@@ -1383,7 +1457,8 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   const bool dev_checks = use_device_checks(p, prm);
   if (p->graph_main && p->graph_main_passes != want_main) { cudaGraphExecDestroy(p->graph_main); p->graph_main = nullptr; }
   p->graph_main_passes = want_main;
-  if (!dev_checks) {   // (the device-driven loop captures the graphs it needs when it first needs them)
+  p->no_graph = getenv("B200PDLP_NO_GRAPH") != nullptr;
+  if (!dev_checks && !p->no_graph) {   // (the device-driven loop captures the graphs it needs when it first needs them)
     if (!p->graph_main) p->graph_main = capture_passes(p, want_main);
     if (!p->graph_small) { p->graph_small_passes = 4; p->graph_small = capture_passes(p, 4); }
   }
@@ -1551,7 +1626,9 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
     bool have_ev1 = false;
     while (true) {
       const int need = next - h->iter;
-      if (need >= p->graph_main_passes / 2 || need > p->graph_small_passes) {
+      if (p->no_graph) {
+        for (int q = 0; q < std::min(need + 4, p->graph_main_passes); q++) { enqueue_pass(p); p->launches += p->kernels_per_pass; }
+      } else if (need >= p->graph_main_passes / 2 || need > p->graph_small_passes) {
         CUDA_OK(cudaGraphLaunch(p->graph_main, s));
         p->launches += (long long)p->graph_main_passes * p->kernels_per_pass;
       } else if (need > 1) {
@@ -2635,6 +2712,8 @@ int b200pdlp_p2p_link_local(b200pdlp_problem** probs, int32_t count) {
         CUDA_OK(cudaDeviceCanAccessPeer(&ok, by_rank[k]->device, by_rank[0]->device));
         if (!ok) throw Error(B200PDLP_ERR_ARG, "p2p_link_local: devices cannot access each other");
       }
+    auto group = std::make_shared<LocalGroup>();
+    group->world = count;
     for (int k = 0; k < count; k++) {
       b200pdlp_problem* p = by_rank[k];
       set_device(p);
@@ -2649,6 +2728,7 @@ int b200pdlp_p2p_link_local(b200pdlp_problem** probs, int32_t count) {
       }
       p->p2p = true;
       p->local_link = true;
+      p->group = group;
       p->p2p_pull = 1;
       drop_graphs(p);
     }
@@ -2665,6 +2745,7 @@ int b200pdlp_p2p_release(b200pdlp_problem* p) {
     p->ipc_opened.clear();
     p->p2p = false;
     p->local_link = false;
+    p->group.reset();
     drop_graphs(p);
   });
 }

@@ -277,7 +277,16 @@ __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_
   pdl_entry(rs.flags);
   if (!epi.begin()) return;
   const double* __restrict__ xin = epi.input();
-  double acc[Epi::NACC > 0 ? Epi::NACC : 1] = {0.0};
+  // Epilogues with many sums (the check iteration's 8 / 20): in the one-slice-per-warp shape every thread finishes at most
+  // ONE row, so its terms go straight to a shared-memory row instead of living in 2 x NACC registers next to the gather
+  // pipeline (CheckColEpilogue: 128 -> ~48 registers, i.e. 2 -> 5 resident CTAs per SM); the block tree is the same.
+  constexpr bool kSmemAcc = (Epi::NACC > 4) && !PIPE;
+  __shared__ double sacc[kSmemAcc ? kThreads : 1][kSmemAcc ? Epi::NACC : 1];
+  double acc[(Epi::NACC > 0 && !kSmemAcc) ? Epi::NACC : 1] = {0.0};
+  if constexpr (kSmemAcc) {
+#pragma unroll
+    for (int a = 0; a < Epi::NACC; a++) sacc[threadIdx.x][a] = 0.0;
+  }
   if (A.prefetch_dist > 0 && threadIdx.x == 0) {
     // pull the col/val range of a CTA that will run one residency wave later into L2, so that its
     // streaming loads hold their L1 miss slots for an L2 round trip instead of an HBM one
@@ -360,11 +369,15 @@ __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_
       }
       for (; k < d.y; k++) s += vp[32 * k] * xin[cp[32 * k]];
       if (live) {
-        double t[Epi::NACC > 0 ? Epi::NACC : 1];
-        epi.row(row, s, t);
-        if constexpr (Epi::NACC > 0) {
+        if constexpr (kSmemAcc) {
+          epi.row(row, s, sacc[threadIdx.x]);
+        } else {
+          double t[Epi::NACC > 0 ? Epi::NACC : 1];
+          epi.row(row, s, t);
+          if constexpr (Epi::NACC > 0) {
 #pragma unroll
-          for (int a = 0; a < Epi::NACC; a++) add_term(acc[a], t[a], rs, a, row);
+            for (int a = 0; a < Epi::NACC; a++) add_term(acc[a], t[a], rs, a, row);
+          }
         }
       }
       d = dn;
@@ -408,11 +421,15 @@ __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_
       }
       for (; k < d.y; k++) s += vp[32 * k] * xin[cp[32 * k]];
       if (live) {
-        double t[Epi::NACC > 0 ? Epi::NACC : 1];
-        epi.row(row, s, t);
-        if constexpr (Epi::NACC > 0) {
+        if constexpr (kSmemAcc) {
+          epi.row(row, s, sacc[threadIdx.x]);
+        } else {
+          double t[Epi::NACC > 0 ? Epi::NACC : 1];
+          epi.row(row, s, t);
+          if constexpr (Epi::NACC > 0) {
 #pragma unroll
-          for (int a = 0; a < Epi::NACC; a++) add_term(acc[a], t[a], rs, a, row);
+            for (int a = 0; a < Epi::NACC; a++) add_term(acc[a], t[a], rs, a, row);
+          }
         }
       }
     }
@@ -436,16 +453,42 @@ __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_
         for (int q = 0; q < lr.z; q++) tot += p[q];
         A.long_counter[sg.w] = 0u;
         epi.prefetch(lr.x);
-        double t[Epi::NACC > 0 ? Epi::NACC : 1];
-        epi.row(lr.x, tot, t);
-        if constexpr (Epi::NACC > 0) {
+        if constexpr (kSmemAcc) {
+          epi.row(lr.x, tot, sacc[threadIdx.x]);
+        } else {
+          double t[Epi::NACC > 0 ? Epi::NACC : 1];
+          epi.row(lr.x, tot, t);
+          if constexpr (Epi::NACC > 0) {
 #pragma unroll
-          for (int a = 0; a < Epi::NACC; a++) add_term(acc[a], t[a], rs, a, lr.x);
+            for (int a = 0; a < Epi::NACC; a++) add_term(acc[a], t[a], rs, a, lr.x);
+          }
         }
       }
     }
   }
-  if constexpr (Epi::NACC > 0) block_partials<Epi::NACC>(acc, rs);
+  if constexpr (kSmemAcc) {
+    // same tree as block_partials: lanes, then the block's warps in order
+    constexpr int kWarps = kThreads / 32;
+    __shared__ double smp2[Epi::NACC][kWarps];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < Epi::NACC; a++) {
+      const double v = warp_sum(sacc[threadIdx.x][a]);
+      if (lane == 0) smp2[a][wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int a = 0; a < Epi::NACC; a++) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; w++) v += smp2[a][w];
+        rs.partials[(size_t)a * gridDim.x + blockIdx.x] = v;
+      }
+    }
+  } else if constexpr (Epi::NACC > 0) {
+    block_partials<Epi::NACC>(acc, rs);
+  }
 }
 
 // ============================================================ multi-GPU kernels
@@ -1265,31 +1308,41 @@ __device__ void trace_row_dev(SolveCtl* c, const PdhgState* st, int restart) {
 // -> PDHG_Check_Termination[_Average] (:797-841), PDHG_Check_Infeasibility (:740-795), limits (:1057-1067), restart choice
 constexpr int kCheckSums = 28;
 __device__ void decide_from_sums(PdhgState* st, SolveCtl* ctl, const double* tot, bool timed_out);
-__global__ void __launch_bounds__(kStepThreads)
+// One CTA per sum (28 CTAs x 256 threads, fixed order inside each), the last CTA to finish (ticket) decides.
+constexpr int kDecideThreads = 256;
+__global__ void __launch_bounds__(kDecideThreads)
 check_decide_kernel(PdhgState* __restrict__ st, SolveCtl* __restrict__ ctl, const double* __restrict__ prow, int nbr,
-                    const double* __restrict__ pcol, int nbc) {
+                    const double* __restrict__ pcol, int nbc, unsigned* __restrict__ ticket) {
   if (!check_live(st, ctl)) return;
-  __shared__ double sm[kCheckSums][kStepThreads / 32];
-  __shared__ double tot[kCheckSums];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int a = 0; a < kCheckSums; a++) {
-    const double* p = a < 8 ? prow + (size_t)a * nbr : pcol + (size_t)(a - 8) * nbc;
-    const int nb = a < 8 ? nbr : nbc;
-    double s = 0.0;
-    for (int i = threadIdx.x; i < nb; i += kStepThreads) s += p[i];
-    s = warp_sum(s);
-    if (lane == 0) sm[a][wid] = s;
+  __shared__ double sm[kDecideThreads / 32];
+  __shared__ bool last;
+  const int a = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const double* p = a < 8 ? prow + (size_t)a * nbr : pcol + (size_t)(a - 8) * nbc;
+  const int nb = a < 8 ? nbr : nbc;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int i = threadIdx.x;
+  for (; i + 3 * kDecideThreads < nb; i += 4 * kDecideThreads) {
+    s0 += p[i]; s1 += p[i + kDecideThreads]; s2 += p[i + 2 * kDecideThreads]; s3 += p[i + 3 * kDecideThreads];
+  }
+  for (; i < nb; i += kDecideThreads) s0 += p[i];
+  double s = warp_sum((s0 + s1) + (s2 + s3));
+  if (lane == 0) sm[wid] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kDecideThreads / 32; w++) t += sm[w];
+    ctl->sums[a] = t;
+    __threadfence();
+    const unsigned k = atomicAdd(ticket, 1u);
+    last = k == (unsigned)gridDim.x - 1u;
   }
   __syncthreads();
-  if (wid == 0) {
-    for (int a = 0; a < kCheckSums; a++) {
-      double s = sm[a][lane];
-      s = warp_sum(s);
-      if (lane == 0) tot[a] = s;
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x != 0) return;
+  if (!last || threadIdx.x != 0) return;
+  __threadfence();
+  *ticket = 0u;
+  double tot[kCheckSums];
+  const volatile double* vs = ctl->sums;
+  for (int q = 0; q < kCheckSums; q++) tot[q] = vs[q];
   decide_from_sums(st, ctl, tot, ctl->time_flag && *ctl->time_flag);
 }
 
@@ -1659,8 +1712,8 @@ void launch_spmv_check_cols(cudaStream_t s, const DevSell& AT, const PdhgState* 
   else spmv_sell_kernel<CheckColEpilogue, false><<<AT.nblocks_body + AT.nsegs, kThreads, 0, s>>>(AT, e, rs);
 }
 void launch_check_decide(cudaStream_t s, PdhgState* st, SolveCtl* ctl, const double* prow, int nbr, const double* pcol,
-                         int nbc) {
-  check_decide_kernel<<<1, kStepThreads, 0, s>>>(st, ctl, prow, nbr, pcol, nbc);
+                         int nbc, unsigned* ticket) {
+  check_decide_kernel<<<kCheckSums, kDecideThreads, 0, s>>>(st, ctl, prow, nbr, pcol, nbc, ticket);
 }
 int restart_sweep_grid(int n, int m) { return ew_grid(n > m ? n : m); }
 void launch_restart_sweep(cudaStream_t s, int n, int m, double* x0, double* x1, double* aty0, double* aty1,

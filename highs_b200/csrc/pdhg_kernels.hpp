@@ -80,7 +80,7 @@ void launch_spmv_check_cols(cudaStream_t s, const DevSell& AT, const PdhgState* 
                             double* atyavg, const double* c, const double* lo, const double* up, const double* cs,
                             ReduceScratch rs);
 void launch_check_decide(cudaStream_t s, PdhgState* st, SolveCtl* ctl, const double* prow, int nbr, const double* pcol,
-                         int nbc);
+                         int nbc, unsigned* ticket /* zero-initialised, self-resetting */);
 int restart_sweep_grid(int n, int m);
 void launch_restart_sweep(cudaStream_t s, int n, int m, double* x0, double* x1, double* aty0, double* aty1,
                           const double* xavg, const double* atyavg, double* xsum, double* xlr, double* y0, double* y1,

@@ -17,7 +17,7 @@ VECS = ["cost", "lower", "upper", "rhs", "col_scale", "row_scale"]
 
 
 def compare(lp, level, **prm):
-    a = engine.Problem(lp, **prm)
+    a = engine.Problem(lp, device_scaling=-1, **prm)    # the host-thread prologue: the bit-reference of the staged variants
     b = engine.Problem(lp, device_scaling=level, **prm)
     try:
         for k in VECS:

@@ -18,8 +18,7 @@ for name in ("80bau3b", "greenbea", "25fv47", "ship12l"):
         d = {k: float(np.abs(out[k] - ref[k]).max()) for k in ("col_value", "col_dual", "row_value", "row_dual")}
         s = {k: float(np.abs(ref[k]).max()) for k in ("col_value", "col_dual", "row_value", "row_dual")}
         print(json.dumps(dict(name=name, lim=lim, form=(out["form_rows"], out["form_cols"]), term=(out["term_code"], ref["term_code"]),
-                              iters=(out["iters"], ref["iters"]), maxdiff=d, scale=s,
-                              pobj=(out["primal_obj"], ref["primal_obj"]))), flush=True)
+                              iters=(out["iters"], ref["iters"]), maxdiff=d, scale=s)), flush=True)
     # forced ordered mode on the same instance: is the engine bit-exact when the reductions are ordered?
     try:
         out = engine.solve(lp, iter_limit=400, ordered_max=1 << 30)
