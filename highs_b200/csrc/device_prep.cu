@@ -255,11 +255,15 @@ scatter_entries_kernel(int nnz0, const int* __restrict__ a_start, const int* __r
   }
 }
 
-// colof[p] = column of nonzero p (one warp per column; a dense column is written 32 entries at a time)
-__global__ void __launch_bounds__(kTpb) colof2_kernel(int n, const int* __restrict__ cbeg, int* __restrict__ colof) {
+// colof[p] = column of nonzero p (one warp per column; a dense column is written 32 entries at a time).  Also validates the
+// caller's a_start on the way (flags[3] |= not non-decreasing / outside [0, nnz]); ranges are clamped so that a malformed
+// a_start cannot make this kernel write out of bounds before the host has seen the flag.
+__global__ void __launch_bounds__(kTpb) colof2_kernel(int n, int nnz, const int* __restrict__ cbeg, int* __restrict__ colof, int* __restrict__ flags) {
   const int j = (blockIdx.x * kTpb + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (j >= n) return;
-  for (int p = cbeg[j] + lane; p < cbeg[j + 1]; p += 32) colof[p] = j;
+  int b = cbeg[j], e = cbeg[j + 1];
+  if (b > e || b < 0 || e > nnz) { if (lane == 0) atomicOr(&flags[3], 1); b = b < 0 ? 0 : b; e = e > nnz ? nnz : e; }
+  for (int p = b + lane; p < e; p += 32) colof[p] = j;
 }
 
 // deterministic sums of squares: block partials, then one block (fixed tree)
@@ -503,19 +507,20 @@ void DevicePrologue::run(cudaStream_t s, const b200pdlp_lp& lp, bool do_scale, i
   exclusive_scan_i(s, tmp, eqlike, eq_ex, m + 1);     // eq_ex[m] = number of eq-like rows
   exclusive_scan_i(s, tmp, isbound, bd_ex, m + 1);    // bd_ex[m] = number of BOUND rows
   int* colof0 = tmp.get<int>(nnz0);
-  if (n0 > 0) colof2_kernel<<<warp_grid(n0), kTpb, 0, s>>>(n0, a_start, colof0);
+  if (n0 > 0) colof2_kernel<<<warp_grid(n0), kTpb, 0, s>>>(n0, nnz0, a_start, colof0, flags);
   int* fl = tmp.get<int>(nnz0 + 1);
   int* fl_ex = tmp.get<int>(nnz0 + 1);
   PREP_OK(cudaMemsetAsync(fl + nnz0, 0, sizeof(int), s));
   if (nnz0 > 0) nnz_flags_kernel<<<grid_for(nnz0), kTpb, 0, s>>>(nnz0, m, a_index, colof0, eqlike, fl, flags);
   exclusive_scan_i(s, tmp, fl, fl_ex, nnz0 + 1);
   // read-back 1: sizes of the standard form
-  int h4[4] = {0, 0, 0, 0};
+  int h4[4] = {0, 0, 0, 0}, hflags[4] = {0, 0, 0, 0};
   PREP_OK(cudaMemcpyAsync(&h4[0], eq_ex + m, sizeof(int), cudaMemcpyDeviceToHost, s));
   PREP_OK(cudaMemcpyAsync(&h4[1], bd_ex + m, sizeof(int), cudaMemcpyDeviceToHost, s));
-  PREP_OK(cudaMemcpyAsync(&h4[2], flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  PREP_OK(cudaMemcpyAsync(hflags, flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
   PREP_OK(cudaStreamSynchronize(s));
-  sc.neq = h4[0]; sc.nbound = h4[1]; sc.bad_index = h4[2]; sc.cols_sorted = h4[3] ? 0 : 1;
+  sc.neq = h4[0]; sc.nbound = h4[1]; sc.bad_index = hflags[0]; sc.cols_sorted = hflags[1] ? 0 : 1;
+  if (hflags[3]) throw std::invalid_argument("b200pdlp: a_start must be non-decreasing and within [0, nnz]");
   if (sc.bad_index) throw std::invalid_argument("b200pdlp: a_index entry outside [0, num_row)");
   const int neq = sc.neq, nbound = sc.nbound;
   const int n = n0 + nbound, nnz = nnz0 + nbound;

@@ -2079,16 +2079,17 @@ static int guarded(F&& fn) {
   }
 }
 
+// deep: also the O(n) / O(nnz) validation of a_start and a_index (the device prologue does both in its first sweep)
 static void check_lp(const b200pdlp_lp* lp, bool deep = true) {
   if (!lp || lp->num_col < 0 || lp->num_row < 0 || !lp->a_start || (lp->a_start[lp->num_col] > 0 && (!lp->a_index || !lp->a_value)) ||
       (lp->num_col > 0 && (!lp->col_cost || !lp->col_lower || !lp->col_upper)) || (lp->num_row > 0 && (!lp->row_lower || !lp->row_upper)))
     throw Error(B200PDLP_ERR_ARG, "b200pdlp: malformed b200pdlp_lp");
   if (lp->sense != 1.0 && lp->sense != -1.0) throw Error(B200PDLP_ERR_ARG, "b200pdlp: sense must be +1 or -1");
   // formulate() indexes per-row arrays with a_index and walks a_start: validate both once (O(nnz), a few ms at 8M nonzeros)
-  if (lp->a_start[0] != 0) throw Error(B200PDLP_ERR_ARG, "b200pdlp: a_start[0] must be 0");
+  if (lp->a_start[0] != 0 || lp->a_start[lp->num_col] < 0) throw Error(B200PDLP_ERR_ARG, "b200pdlp: a_start[0] must be 0 and a_start[num_col] >= 0");
+  if (!deep) return;
   for (int j = 0; j < lp->num_col; j++)
     if (lp->a_start[j + 1] < lp->a_start[j]) throw Error(B200PDLP_ERR_ARG, "b200pdlp: a_start must be non-decreasing");
-  if (!deep) return;   // (the device prologue checks the index range in its first sweep over the nonzeros)
   const int nnz = lp->a_start[lp->num_col], m = lp->num_row;
   unsigned bad = 0;
   for (int q = 0; q < nnz; q++) bad |= (unsigned)lp->a_index[q] >= (unsigned)m;

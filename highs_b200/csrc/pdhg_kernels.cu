@@ -245,15 +245,21 @@ step_rule_kernel(PdhgState* __restrict__ st, ReduceScratch r1, int nb1, ReduceSc
     __syncthreads();
     tot[0] = sm[0][0]; tot[1] = sm[1][0]; tot[2] = sm[2][0];
   } else {
-    const double* pp[3] = {r1.partials, r2.partials, r3.partials};
-    const int nb[3] = {nb1, nb2, nb3};
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-      double s = 0.0;
-      for (int i = threadIdx.x; i < nb[a]; i += kStepThreads) s += pp[a][i];
-      s = warp_sum(s);
-      if (lane == 0) sm[a][wid] = s;
+    // the three partial arrays in ONE loop: their loads are independent, so the three latencies overlap (same per-thread
+    // order of additions as three separate loops: the sums are bit-identical)
+    const double* __restrict__ p1 = r1.partials;
+    const double* __restrict__ p2 = r2.partials;
+    const double* __restrict__ p3 = r3.partials;
+    const int nbmax = nb1 > nb2 ? (nb1 > nb3 ? nb1 : nb3) : (nb2 > nb3 ? nb2 : nb3);
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int i = threadIdx.x; i < nbmax; i += kStepThreads) {
+      const double v1 = i < nb1 ? p1[i] : 0.0, v2 = i < nb2 ? p2[i] : 0.0, v3 = i < nb3 ? p3[i] : 0.0;
+      if (i < nb1) s1 += v1;
+      if (i < nb2) s2 += v2;
+      if (i < nb3) s3 += v3;
     }
+    s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+    if (lane == 0) { sm[0][wid] = s1; sm[1][wid] = s2; sm[2][wid] = s3; }
     __syncthreads();
     if (wid == 0) {
 #pragma unroll
