@@ -74,3 +74,27 @@ def test_pdlp_cleanup_with_the_engine(oracle):
         assert got[k] == ref[k], k
     assert got["model_status"] == "Optimal"
     assert got["objective_function_value"] == pytest.approx(ref["objective_function_value"], rel=1e-12, abs=1e-12)
+
+
+# ---- solver=hipdlp through its own shim (highs_b200/csrc/highs_shim_hipdlp.cpp replaces pdlp/HiPdlpWrapper.cpp,
+# HighsSolve.cpp:107-117 dispatches to it): the reference's unmodified Highs::run() with the engine's HiPDLP mode behind it
+@pytest.mark.parametrize("name", ["afiro", "adlittle", "avgas", "blending", "chip", "sctest", "e226", "stair"])
+def test_highs_run_hipdlp_through_the_shim(oracle, name):
+    """same Highs::run(), solver=hipdlp: the reference's CPU HiPDLP vs the drop-in library -- status, iteration count and
+    objective (the device mode adds the check sums in the reference's order up to 4096 rows/columns: bit-equal)"""
+    import os
+    from conftest import GOLDEN
+    from highs_b200.lp import read_b2lp
+    drv = os.path.join(os.path.dirname(oracle.DROPIN_DRIVER), "ref_driver_b200_hipdlp")
+    if not os.path.exists(drv):
+        pytest.skip("oracle/_ref/ref_driver_b200_hipdlp not built")
+    path = os.path.join(GOLDEN, "instances", name + ".b2lp")
+    if not os.path.exists(path):
+        pytest.skip("instance fixture missing")
+    lp = read_b2lp(path)
+    opts = {"solver": "hipdlp", "presolve": "off", "pdlp_iteration_limit": 8000}
+    ref = oracle.run_reference(lp=lp, options=opts)
+    got = oracle.run_reference(lp=lp, options=opts, driver=drv)
+    assert got["model_status_code"] == ref["model_status_code"], (got["model_status"], ref["model_status"])
+    assert got["pdlp_iteration_count"] == ref["pdlp_iteration_count"]
+    assert got["objective_function_value"] == pytest.approx(ref["objective_function_value"], rel=1e-12, abs=1e-12)
