@@ -163,6 +163,7 @@ struct DeviceMatrix {
     dev.nrows = host.nrows;
     dev.nslices = (int)host.slices.size();
     dev.nblocks_body = (dev.nslices + kThreads / 32 - 1) / (kThreads / 32);
+    dev.nblocks_full = dev.nblocks_body;
     dev.nsegs = (int)host.segs.size();
     dev.slices = slices.p; dev.col = col.p; dev.val = val.p; dev.segs = segs.p; dev.long_rows = long_rows.p;
     dev.lcol = lcol.p; dev.lval = lval.p; dev.long_partial = long_partial.p; dev.long_counter = long_counter.p;
@@ -173,6 +174,7 @@ struct DeviceMatrix {
     std::vector<int>().swap(host.lcol); std::vector<double>().swap(host.lval);
   }
   int grid() const { return dev.nblocks_body + dev.nsegs; }
+  int grid_full() const { return dev.nblocks_full + dev.nsegs; }   // launch shape of the check kernels (and the larger of the two)
 };
 
 struct CudaEvent {   // RAII: released on every exit path
@@ -430,15 +432,20 @@ struct DeviceSetup {
 // experiment (B200PDLP_SPMV_CTAS_PER_SM=k, one GPU, tree mode): the SpMV bodies run on a persistent grid of k CTAs per SM and
 // walk their slices in a software pipeline (spmv_sell_kernel<Epi, true>) instead of one CTA per 8 slices
 static void apply_spmv_grid(b200pdlp_problem* p) {
-  const char* e = getenv("B200PDLP_SPMV_CTAS_PER_SM");
-  if (!e || p->world != 1 || p->ordered) return;
-  const int k = atoi(e);
-  if (k <= 0) return;
+  if (p->world != 1 || p->ordered) return;
+  auto val = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+  const int both = val("B200PDLP_SPMV_CTAS_PER_SM", -1);
+  // measured (profiles/r02_experiments.md): the pipelined walk helps A'y (K3: 49.3 -> 44.6 us at 3 CTAs per SM) and hurts
+  // A x (K2: 54.6 -> 56.5 us), so it is the default for A' only
+  const int ka = val("B200PDLP_SPMV_A_CTAS_PER_SM", both >= 0 ? both : 0);
+  const int kat = val("B200PDLP_SPMV_AT_CTAS_PER_SM", both >= 0 ? both : 3);
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
-  for (DeviceMatrix* M : {&p->A, &p->AT}) {
-    if (M->dev.nblocks_body > sms * k) { M->dev.nblocks_body = sms * k; M->dev.pipelined = 1; }
-  }
+  auto apply = [&](DeviceMatrix& M, int k) {
+    if (k > 0 && M.dev.nblocks_body > sms * k) { M.dev.nblocks_body = sms * k; M.dev.pipelined = 1; }
+  };
+  apply(p->A, ka);
+  apply(p->AT, kat);
 }
 
 static void alloc_host_mirrors(b200pdlp_problem* p) {
@@ -588,7 +595,7 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
     up_row(p->rhs, f.rhs); up_row(p->rowscale, f.row_scale);
   }
   p->redbuf.alloc((size_t)std::max(n, p->m) + 16);
-  size_t maxgrid = std::max<size_t>(kMaxEwBlocks, std::max(p->A.grid(), p->AT.grid()));
+  size_t maxgrid = std::max<size_t>(kMaxEwBlocks, std::max(p->A.grid_full(), p->AT.grid_full()));
   p->scratch_stride = 24 * maxgrid;
   p->partials.alloc(p->scratch_stride * kNumSlots);
   p->counters.alloc(kNumSlots);
@@ -669,6 +676,7 @@ static void create_problem_device(const b200pdlp_lp& lp, const b200pdlp_params& 
     M.host.nrows = O.nrows; M.host.ncols = O.ncols; M.host.padded = O.padded; M.host.lcount = O.lcount; M.host.n_partials = O.nsegs;
     M.dev.nrows = O.nrows; M.dev.nslices = O.nslices;
     M.dev.nblocks_body = (O.nslices + kThreads / 32 - 1) / (kThreads / 32);
+    M.dev.nblocks_full = M.dev.nblocks_body;
     M.dev.nsegs = O.nsegs;
     M.dev.slices = M.slices.p; M.dev.col = M.col.p; M.dev.val = M.val.p; M.dev.segs = M.segs.p; M.dev.long_rows = M.long_rows.p;
     M.dev.lcol = M.lcol.p; M.dev.lval = M.lval.p; M.dev.long_partial = M.long_partial.p; M.dev.long_counter = M.long_counter.p;
@@ -689,7 +697,7 @@ static void create_problem_device(const b200pdlp_lp& lp, const b200pdlp_params& 
   p->ysum.alloc(m, false); p->yavg.alloc(m, false); p->axavg.alloc(m, false); p->ylr.alloc(m, false);
   p->io_col.alloc((size_t)2 * std::max(f.n_orig, 1), false);
   p->io_row.alloc((size_t)2 * std::max(m, 1), false);
-  size_t maxgrid = std::max<size_t>(kMaxEwBlocks, std::max(p->A.grid(), p->AT.grid()));
+  size_t maxgrid = std::max<size_t>(kMaxEwBlocks, std::max(p->A.grid_full(), p->AT.grid_full()));
   p->scratch_stride = 24 * maxgrid;
   p->partials.alloc(p->scratch_stride * kNumSlots, false);
   p->counters.alloc(kNumSlots, false);
@@ -1242,7 +1250,7 @@ static void enqueue_check_device(b200pdlp_problem* p) {
                          p->yavg.p, p->axavg.p, p->rhs.p, p->rowscale.p, p->neq_local, rrow);
   launch_spmv_check_cols(s, p->AT.dev, st, ctl, p->yavg.p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->xavg.p,
                          p->atyavg.p, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, rcol);
-  launch_check_decide(s, st, ctl, rrow.partials, p->A.grid(), rcol.partials, p->AT.grid(), rrow.counter);
+  launch_check_decide(s, st, ctl, rrow.partials, p->A.grid_full(), rcol.partials, p->AT.grid_full(), rrow.counter);
   launch_restart_sweep(s, n, ml, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->xavg.p, p->atyavg.p, p->xsum.p,
                        p->xlr.p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->yavg.p, p->axavg.p, p->ysum.p, p->ylr.p,
                        st, ctl, rrst);
@@ -1849,7 +1857,7 @@ static void create_problem_hipdlp(const b200pdlp_lp& lp, const b200pdlp_hipdlp_p
   for (DevBuf<double>* b : {&h.y, &h.yn, &h.ry, &h.ya, &h.axp, &h.dy}) b->alloc(m);
   h.state.alloc(1);
   h.hstate = static_cast<HipState*>(pinned_cache_alloc(sizeof(HipState), false));
-  size_t maxgrid = std::max<size_t>(kMaxEwBlocks, std::max(p->A.grid(), p->AT.grid()));
+  size_t maxgrid = std::max<size_t>(kMaxEwBlocks, std::max(p->A.grid_full(), p->AT.grid_full()));
   p->scratch_stride = 24 * maxgrid;
   p->partials.alloc(p->scratch_stride * kNumSlots);
   p->counters.alloc(kNumSlots);
@@ -2715,6 +2723,7 @@ int b200pdlp_p2p_link_local(b200pdlp_problem** probs, int32_t count) {
       }
     auto group = std::make_shared<LocalGroup>();
     group->world = count;
+    for (int k = 0; k < count; k++) { set_device(by_rank[k]); preload_multi_gpu_kernels(); }
     for (int k = 0; k < count; k++) {
       b200pdlp_problem* p = by_rank[k];
       set_device(p);

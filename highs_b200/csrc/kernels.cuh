@@ -105,7 +105,8 @@ struct HipState {
 // device view of a SellMatrix (host_prep.hpp)
 struct DevSell {
   int nrows, nslices;
-  int nblocks_body;                       // CTAs that process slices (8 slices = 256 rows each)
+  int nblocks_body;                       // CTAs that process slices (8 slices = 256 rows each; fewer when `pipelined`)
+  int nblocks_full;                       // one CTA per 8 slices, whatever nblocks_body says (the check kernels use this shape)
   int nsegs;                              // + one CTA per long-row segment
   const int4* __restrict__ slices;        // {ptr, len, skipmask, -}
   const int* __restrict__ col;

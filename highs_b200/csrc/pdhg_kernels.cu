@@ -68,6 +68,14 @@ primal_step_kernel(int n, PdhgState* __restrict__ st, double* __restrict__ x0, d
   block_partials<1>(acc, rs);
 }
 
+// where an epilogue's terms go: a plain array (registers) or one thread's column of a [NACC][kThreads] shared-memory
+// array (consecutive threads -> consecutive doubles: conflict-free; a [kThreads][NACC] row per thread was measured at
+// 6.5 M bank conflicts per launch, r02 ncu)
+struct StridedOut {
+  double* p;
+  __device__ __forceinline__ double& operator[](int a) const { return p[a * kThreads]; }
+  __device__ __forceinline__ StridedOut operator+(int k) const { return StridedOut{p + k * kThreads}; }
+};
 // ===================================================================== SpMV
 // Sliced-ELL body: one warp per slice of 32 rows, one lane per row.  A warp reads the slice's
 // col / val arrays fully coalesced (k-major, lane-minor), every lane gathers its dense-vector
@@ -228,12 +236,12 @@ __global__ void __launch_bounds__(kStepThreads)
 step_rule_kernel(PdhgState* __restrict__ st, ReduceScratch r1, int nb1, ReduceScratch r2, int nb2, ReduceScratch r3,
                  int nb3, const double* __restrict__ dy2_override) {
   pdl_entry(r1.flags);
-  if (st->iter >= st->stop_iter) return;
   __shared__ double sm[3][kStepThreads / 32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double tot[3];
   if (r1.terms) {
     // ordered mode: thread a adds accumulator a's terms sequentially
+    if (st->iter >= st->stop_iter) return;
     const ReduceScratch* rr[3] = {&r1, &r2, &r3};
     double s = 0.0;
     if (threadIdx.x < 3) {
@@ -258,6 +266,9 @@ step_rule_kernel(PdhgState* __restrict__ st, ReduceScratch r1, int nb1, ReduceSc
       if (i < nb2) s2 += v2;
       if (i < nb3) s3 += v3;
     }
+    // (the partial arrays are always valid memory: their loads are issued before the state block is looked at, so the two
+    //  round trips overlap; a pass that turns out not to be due returns below without having written anything)
+    if (st->iter >= st->stop_iter) return;
     s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
     if (lane == 0) { sm[0][wid] = s1; sm[1][wid] = s2; sm[2][wid] = s3; }
     __syncthreads();
@@ -287,11 +298,11 @@ __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_
   // ONE row, so its terms go straight to a shared-memory row instead of living in 2 x NACC registers next to the gather
   // pipeline (CheckColEpilogue: 128 -> ~48 registers, i.e. 2 -> 5 resident CTAs per SM); the block tree is the same.
   constexpr bool kSmemAcc = (Epi::NACC > 4) && !PIPE;
-  __shared__ double sacc[kSmemAcc ? kThreads : 1][kSmemAcc ? Epi::NACC : 1];
+  __shared__ double sacc[kSmemAcc ? Epi::NACC : 1][kSmemAcc ? kThreads : 1];
   double acc[(Epi::NACC > 0 && !kSmemAcc) ? Epi::NACC : 1] = {0.0};
   if constexpr (kSmemAcc) {
 #pragma unroll
-    for (int a = 0; a < Epi::NACC; a++) sacc[threadIdx.x][a] = 0.0;
+    for (int a = 0; a < Epi::NACC; a++) sacc[a][threadIdx.x] = 0.0;
   }
   if (A.prefetch_dist > 0 && threadIdx.x == 0) {
     // pull the col/val range of a CTA that will run one residency wave later into L2, so that its
@@ -376,7 +387,7 @@ __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_
       for (; k < d.y; k++) s += vp[32 * k] * xin[cp[32 * k]];
       if (live) {
         if constexpr (kSmemAcc) {
-          epi.row(row, s, sacc[threadIdx.x]);
+          epi.row(row, s, StridedOut{&sacc[0][threadIdx.x]});
         } else {
           double t[Epi::NACC > 0 ? Epi::NACC : 1];
           epi.row(row, s, t);
@@ -428,7 +439,7 @@ __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_
       for (; k < d.y; k++) s += vp[32 * k] * xin[cp[32 * k]];
       if (live) {
         if constexpr (kSmemAcc) {
-          epi.row(row, s, sacc[threadIdx.x]);
+          epi.row(row, s, StridedOut{&sacc[0][threadIdx.x]});
         } else {
           double t[Epi::NACC > 0 ? Epi::NACC : 1];
           epi.row(row, s, t);
@@ -460,7 +471,7 @@ __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_
         A.long_counter[sg.w] = 0u;
         epi.prefetch(lr.x);
         if constexpr (kSmemAcc) {
-          epi.row(lr.x, tot, sacc[threadIdx.x]);
+          epi.row(lr.x, tot, StridedOut{&sacc[0][threadIdx.x]});
         } else {
           double t[Epi::NACC > 0 ? Epi::NACC : 1];
           epi.row(lr.x, tot, t);
@@ -479,7 +490,7 @@ __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
     for (int a = 0; a < Epi::NACC; a++) {
-      const double v = warp_sum(sacc[threadIdx.x][a]);
+      const double v = warp_sum(sacc[a][threadIdx.x]);
       if (lane == 0) smp2[a][wid] = v;
     }
     __syncthreads();
@@ -1173,7 +1184,8 @@ check_avg_x_kernel(int n, const double* __restrict__ x0, const double* __restric
 
 // row-side sums of one iterate (row_check_fused_kernel's terms): 0 y.b, 1 |primal residual|^2, 2 |y|^2,
 // 3 |[ax]_eq, min([ax]_ineq, 0) rowScale|^2
-__device__ __forceinline__ void row_terms(double y, double ax, double bi, double sc, bool ineq, double* t) {
+template <class T>
+__device__ __forceinline__ void row_terms(double y, double ax, double bi, double sc, bool ineq, T t) {
   double r = ax - bi;
   if (ineq) r = r < 0.0 ? r : 0.0;
   r = r * sc;
@@ -1183,7 +1195,8 @@ __device__ __forceinline__ void row_terms(double y, double ax, double bi, double
   t[0] = y * bi; t[1] = r * r; t[2] = y * y; t[3] = k * k;
 }
 // column-side sums of one iterate (col_check_fused_kernel's terms, 10 of them)
-__device__ __forceinline__ void col_terms(double x, double aty, double ci, double l, double u, double sc, double* t) {
+template <class T>
+__device__ __forceinline__ void col_terms(double x, double aty, double ci, double l, double u, double sc, T t) {
   const bool hl = l > -INFINITY, hu = u < INFINITY;
   const double lf = hl ? l : 0.0, uf = hu ? u : 0.0;
   const double isc = 1.0 / sc;
@@ -1224,7 +1237,8 @@ struct CheckRowEpilogueT {
   __device__ const double* input() const { return xavg; }
   double p_y, p_ax, p_ys, p_b, p_sc;
   __device__ void prefetch(int r) { p_y = y[r]; p_ax = ax[r]; p_ys = FLUSH ? ysum[r] : yavg[r]; p_b = b[r]; p_sc = rsc[r]; }
-  __device__ void row(int r, double s, double* t) const {
+  template <class T>
+  __device__ void row(int r, double s, T t) const {
     axavg[r] = s;
     double ya;
     if (FLUSH) {
@@ -1263,7 +1277,8 @@ struct CheckColEpilogue {
   __device__ void prefetch(int j) {
     p_x = x[j]; p_aty = aty[j]; p_xa = xavg[j]; p_c = c[j]; p_lo = lo[j]; p_up = up[j]; p_cs = cs[j];
   }
-  __device__ void row(int j, double s, double* t) const {
+  template <class T>
+  __device__ void row(int j, double s, T t) const {
     atyavg[j] = s;
     col_terms(p_x, p_aty, p_c, p_lo, p_up, p_cs, t);
     col_terms(p_xa, s, p_c, p_lo, p_up, p_cs, t + 10);
@@ -1432,22 +1447,38 @@ restart_sweep_kernel(int n, int m, double* __restrict__ x0, double* __restrict__
   double* __restrict__ ax = cur ? ax1 : ax0;
   double acc[2] = {0.0, 0.0};
   const int stride = gridDim.x * kThreads;
-  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
-    double v = x[i];
-    if (to_avg) { v = xavg[i]; x[i] = v; aty[i] = atyavg[i]; }
-    xsum[i] = 0.0;
-    const double d = v + -1.0 * xlr[i];
-    acc[0] += d * d;
-    xlr[i] = v;
-  }
-  for (int i = blockIdx.x * kThreads + threadIdx.x; i < m; i += stride) {
-    double v = y[i];
-    if (to_avg) { v = yavg[i]; y[i] = v; ax[i] = axavg[i]; }
-    ysum[i] = 0.0;
-    const double d = v + -1.0 * ylr[i];
-    acc[1] += d * d;
-    ylr[i] = v;
-  }
+  // pairs with 128-bit accesses (all vectors are allocation-aligned), then the odd tail
+  auto sweep = [&](int len, double* __restrict__ cur_v, double* __restrict__ cur_a, const double* __restrict__ avg_v,
+                   const double* __restrict__ avg_a, double* __restrict__ sum, double* __restrict__ lr, double& acc_out) {
+    const int npair = len >> 1;
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < npair; i += stride) {
+      double2 v;
+      if (to_avg) {
+        v = reinterpret_cast<const double2*>(avg_v)[i];
+        reinterpret_cast<double2*>(cur_v)[i] = v;
+        reinterpret_cast<double2*>(cur_a)[i] = reinterpret_cast<const double2*>(avg_a)[i];
+      } else {
+        v = reinterpret_cast<const double2*>(cur_v)[i];
+      }
+      reinterpret_cast<double2*>(sum)[i] = make_double2(0.0, 0.0);
+      const double2 l = reinterpret_cast<const double2*>(lr)[i];
+      const double d0 = v.x + -1.0 * l.x, d1 = v.y + -1.0 * l.y;
+      acc_out += d0 * d0;
+      acc_out += d1 * d1;
+      reinterpret_cast<double2*>(lr)[i] = v;
+    }
+    if ((len & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+      const int i = len - 1;
+      double v = cur_v[i];
+      if (to_avg) { v = avg_v[i]; cur_v[i] = v; cur_a[i] = avg_a[i]; }
+      sum[i] = 0.0;
+      const double d = v + -1.0 * lr[i];
+      acc_out += d * d;
+      lr[i] = v;
+    }
+  };
+  sweep(n, x, aty, xavg, atyavg, xsum, xlr, acc[0]);
+  sweep(m, y, ax, yavg, axavg, ysum, ylr, acc[1]);
   block_partials<2>(acc, rs);
 }
 
@@ -1689,6 +1720,37 @@ void launch_step_rule(cudaStream_t s, PdhgState* st, ReduceScratch r1, int nb1, 
 
 int primal_step_grid(int n) { return ew_grid((n + 1) / 2); }
 
+// CUDA loads kernels lazily (CUDA_MODULE_LOADING=LAZY, the default since 12.2), and loading may need a context-wide
+// synchronisation.  With several ranks on ONE device (logical shards) a rank's barrier kernel spins until its peers'
+// kernels signal -- if a peer's next kernel still has to be loaded, that load waits for the spinning kernel: deadlock
+// (observed on hardware: every direct launch of a not-yet-used kernel behind a peer's barrier timed out, while runs whose
+// kernels had all been instantiated into graphs beforehand went through).  So the kernels of the multi-GPU path are
+// loaded up front.
+void preload_multi_gpu_kernels() {
+  const void* fns[] = {
+      (const void*)primal_step_kernel, (const void*)primal_shard_kernel, (const void*)primal_shard_p2p_kernel,
+      (const void*)push_part_kernel, (const void*)push_shard_kernel, (const void*)push_rows_kernel,
+      (const void*)p2p_exchange_kernel, (const void*)reduce_part_p2p_kernel, (const void*)p2p_barrier_kernel,
+      (const void*)stash_scalars_kernel<1>, (const void*)stash_scalars_kernel<2>, (const void*)step_rule_mg_kernel,
+      (const void*)step_rule_kernel, (const void*)average_kernel, (const void*)average_dev_kernel,
+      (const void*)check_clear_kernel, (const void*)col_check_a_kernel, (const void*)col_check_b_kernel,
+      (const void*)row_check_a_kernel, (const void*)row_check_b_kernel, (const void*)col_check_fused_kernel,
+      (const void*)row_check_fused_kernel, (const void*)diff_norm2_kernel, (const void*)scale_kernel,
+      (const void*)fill_kernel, (const void*)check_avg_x_kernel, (const void*)check_decide_kernel,
+      (const void*)check_decide_sums_kernel, (const void*)restart_sweep_kernel, (const void*)reduce_partials_kernel,
+      (const void*)check_finish_kernel,
+      (const void*)spmv_sell_kernel<PlainEpilogue, false>, (const void*)spmv_sell_kernel<PlainEpilogue, true>,
+      (const void*)spmv_sell_kernel<DualEpilogue, false>, (const void*)spmv_sell_kernel<DualEpilogue, true>,
+      (const void*)spmv_sell_kernel<PrimalEpilogue, false>, (const void*)spmv_sell_kernel<PrimalEpilogue, true>,
+      (const void*)spmv_sell_kernel<DualEpilogueMg, false>, (const void*)spmv_sell_kernel<PartialAtyEpilogue, false>,
+      (const void*)spmv_sell_kernel<CheckRowEpilogue, false>, (const void*)spmv_sell_kernel<CheckColEpilogue, false>,
+      (const void*)spmv_sell_kernel<CheckRowEpilogueT<false>, false>,
+  };
+  cudaFuncAttributes at;
+  for (const void* f : fns) cudaFuncGetAttributes(&at, f);
+  cudaGetLastError();
+}
+
 // ---- device-side check iteration
 void launch_check_avg_x(cudaStream_t s, int n, const double* x0, const double* x1, double* xsum, double* xavg,
                         const PdhgState* st, const SolveCtl* ctl) {
@@ -1702,8 +1764,9 @@ void launch_spmv_check_rows(cudaStream_t s, const DevSell& A, const PdhgState* s
   e.st = st; e.ctl = ctl; e.xavg = xavg; e.y0 = y0; e.y1 = y1; e.ax0 = ax0; e.ax1 = ax1; e.ysum = ysum; e.yavg = yavg;
   e.axavg = axavg; e.b = b; e.rsc = rsc; e.neq = neq;
   rs.terms = nullptr; rs.flags = 0;
-  if (A.pipelined) spmv_sell_kernel<CheckRowEpilogue, true><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, rs);
-  else spmv_sell_kernel<CheckRowEpilogue, false><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, rs);
+  DevSell F = A;   // the check epilogues keep their sums in shared memory, which needs at most one row per thread
+  F.nblocks_body = A.nblocks_full; F.pipelined = 0;
+  spmv_sell_kernel<CheckRowEpilogue, false><<<F.nblocks_body + F.nsegs, kThreads, 0, s>>>(F, e, rs);
 }
 void launch_spmv_check_cols(cudaStream_t s, const DevSell& AT, const PdhgState* st, const SolveCtl* ctl, const double* yavg,
                             const double* x0, const double* x1, const double* aty0, const double* aty1, const double* xavg,
@@ -1714,8 +1777,9 @@ void launch_spmv_check_cols(cudaStream_t s, const DevSell& AT, const PdhgState* 
   e.st = st; e.ctl = ctl; e.yavg = yavg; e.x0 = x0; e.x1 = x1; e.aty0 = aty0; e.aty1 = aty1; e.xavg = xavg;
   e.atyavg = atyavg; e.c = c; e.lo = lo; e.up = up; e.cs = cs;
   rs.terms = nullptr; rs.flags = 0;
-  if (AT.pipelined) spmv_sell_kernel<CheckColEpilogue, true><<<AT.nblocks_body + AT.nsegs, kThreads, 0, s>>>(AT, e, rs);
-  else spmv_sell_kernel<CheckColEpilogue, false><<<AT.nblocks_body + AT.nsegs, kThreads, 0, s>>>(AT, e, rs);
+  DevSell F = AT;
+  F.nblocks_body = AT.nblocks_full; F.pipelined = 0;
+  spmv_sell_kernel<CheckColEpilogue, false><<<F.nblocks_body + F.nsegs, kThreads, 0, s>>>(F, e, rs);
 }
 void launch_check_decide(cudaStream_t s, PdhgState* st, SolveCtl* ctl, const double* prow, int nbr, const double* pcol,
                          int nbc, unsigned* ticket) {

@@ -45,6 +45,8 @@ void launch_step_rule_mg(cudaStream_t s, PdhgState* st, const double* xfull, int
 void launch_step_rule(cudaStream_t s, PdhgState* st, ReduceScratch r1, int nb1, ReduceScratch r2, int nb2,
                       ReduceScratch r3, int nb3, const double* dy2_override);
 int primal_step_grid(int n);
+// load every kernel of the multi-GPU path now (see pdhg_kernels.cu: lazy module loading vs. spinning barrier kernels)
+void preload_multi_gpu_kernels();
 void launch_average(cudaStream_t s, int len, const double* v, double* sum, double* avg, int pending, double w,
                     double scale);
 void launch_col_check_a(cudaStream_t s, int n, int nit, ColIter a, ColIter b, const double* c, const double* lo,
