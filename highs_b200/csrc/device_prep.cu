@@ -201,18 +201,21 @@ row_maps_kernel(int m, int n0, int nnz0, int neq, const double* __restrict__ rl,
 __global__ void __launch_bounds__(kTpb)
 col_vectors_kernel(int n0, int n, int nnz, double sense, const int* __restrict__ a_start, const double* __restrict__ cc,
                    const double* __restrict__ cl, const double* __restrict__ cu, double* __restrict__ cost,
-                   double* __restrict__ lower, double* __restrict__ upper, int* __restrict__ cbeg) {
+                   double* __restrict__ lower, double* __restrict__ upper, int* __restrict__ cbeg, int what) {
+  // what & 1: the column starts (structure);  what & 2: cost and bounds (values, which arrive on the second copy stream)
   const int stride = gridDim.x * kTpb;
   for (int j = blockIdx.x * kTpb + threadIdx.x; j < n0; j += stride) {
-    cost[j] = cc[j] * sense;
-    double l = cl[j], u = cu[j];
-    if (l < -1e20) l = -INFINITY;
-    if (u > 1e20) u = INFINITY;
-    lower[j] = l;
-    upper[j] = u;
-    cbeg[j] = a_start[j];
+    if (what & 2) {
+      cost[j] = cc[j] * sense;
+      double l = cl[j], u = cu[j];
+      if (l < -1e20) l = -INFINITY;
+      if (u > 1e20) u = INFINITY;
+      lower[j] = l;
+      upper[j] = u;
+    }
+    if (what & 1) cbeg[j] = a_start[j];
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) cbeg[n] = nnz;
+  if ((what & 1) && blockIdx.x == 0 && threadIdx.x == 0) cbeg[n] = nnz;
 }
 
 // per nonzero: is its row eq-like (for the stable partition of every column), is its row index in range, does the
@@ -236,9 +239,11 @@ nnz_flags_kernel(int nnz0, int m, const int* __restrict__ a_index, const int* __
 // (:410-433) = a stable partition; the exclusive scan of the eq-like flags gives every entry its place
 __global__ void __launch_bounds__(kTpb)
 scatter_entries_kernel(int nnz0, const int* __restrict__ a_start, const int* __restrict__ a_index,
-                       const double* __restrict__ a_value, const int* __restrict__ colof, const int* __restrict__ fl_ex,
+                       const int* __restrict__ colof, const int* __restrict__ fl_ex,
                        const int* __restrict__ cls, const int* __restrict__ new_idx, int* __restrict__ cidx,
-                       double* __restrict__ cval) {
+                       unsigned* __restrict__ dest) {
+  // structure only: the new row index goes to its place; dest[p] = the place (bit 31: a LEQ row, the value is negated) for
+  // scatter_values_kernel, which runs once the coefficient array has arrived
   const int stride = gridDim.x * kTpb;
   for (int p = blockIdx.x * kTpb + threadIdx.x; p < nnz0; p += stride) {
     const int j = colof[p];
@@ -250,8 +255,17 @@ scatter_entries_kernel(int nnz0, const int* __restrict__ a_start, const int* __r
     const bool eql = c == 0 || c == 3;
     const int q = eql ? s + k : s + ne + (p - s - k);
     cidx[q] = new_idx[r];
+    dest[p] = (unsigned)q | (c == 1 ? 0x80000000u : 0u);
+  }
+}
+
+__global__ void __launch_bounds__(kTpb)
+scatter_values_kernel(int nnz0, const double* __restrict__ a_value, const unsigned* __restrict__ dest, double* __restrict__ cval) {
+  const int stride = gridDim.x * kTpb;
+  for (int p = blockIdx.x * kTpb + threadIdx.x; p < nnz0; p += stride) {
+    const unsigned d = dest[p];
     const double v = a_value[p];
-    cval[q] = c == 1 ? -v : v;
+    cval[d & 0x7fffffffu] = (d >> 31) ? -v : v;
   }
 }
 
@@ -485,12 +499,32 @@ void DevicePrologue::run(cudaStream_t s, const b200pdlp_lp& lp, bool do_scale, i
   double* cu = tmp.get<double>(n0);
   double* rl = tmp.get<double>(m);
   double* ru = tmp.get<double>(m);
-  auto up = [&](void* d, const void* h, size_t bytes) { if (bytes) PREP_OK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s)); };
-  up(a_start, lp.a_start, (size_t)(n0 + 1) * 4);
-  up(a_index, lp.a_index, (size_t)nnz0 * 4);
-  up(a_value, lp.a_value, (size_t)nnz0 * 8);
-  up(cc, lp.col_cost, (size_t)n0 * 8); up(cl, lp.col_lower, (size_t)n0 * 8); up(cu, lp.col_upper, (size_t)n0 * 8);
-  up(rl, lp.row_lower, (size_t)m * 8); up(ru, lp.row_upper, (size_t)m * 8);
+  // Two copy streams: the STRUCTURE (column starts, row indices, row bounds: 4 n + 4 nnz + 16 m bytes) goes first on `s`; the
+  // VALUES (coefficients, cost, column bounds: 8 nnz + 24 n bytes, two thirds of the traffic) follow on a second stream, and
+  // everything that depends on the sparsity pattern alone -- classification, the stable partition, the row-major index
+  // (radix sort), both length orderings, the slice plans and the three size read-backs -- runs underneath that copy.
+  struct Side {
+    cudaStream_t st = nullptr; cudaEvent_t structure_up = nullptr, values_up = nullptr;
+    Side() {
+      PREP_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      PREP_OK(cudaEventCreateWithFlags(&structure_up, cudaEventDisableTiming));
+      PREP_OK(cudaEventCreateWithFlags(&values_up, cudaEventDisableTiming));
+    }
+    ~Side() {   // before `tmp` hands the staging buffers back: no copy may still be writing them (exception paths)
+      if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+      if (structure_up) cudaEventDestroy(structure_up);
+      if (values_up) cudaEventDestroy(values_up);
+    }
+  } side;
+  auto up = [&](cudaStream_t q, void* d, const void* h, size_t bytes) { if (bytes) PREP_OK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, q)); };
+  up(s, a_start, lp.a_start, (size_t)(n0 + 1) * 4);
+  up(s, a_index, lp.a_index, (size_t)nnz0 * 4);
+  up(s, rl, lp.row_lower, (size_t)m * 8); up(s, ru, lp.row_upper, (size_t)m * 8);
+  PREP_OK(cudaEventRecord(side.structure_up, s));
+  PREP_OK(cudaStreamWaitEvent(side.st, side.structure_up, 0));   // the structure first: the copy engine is shared
+  up(side.st, a_value, lp.a_value, (size_t)nnz0 * 8);
+  up(side.st, cc, lp.col_cost, (size_t)n0 * 8); up(side.st, cl, lp.col_lower, (size_t)n0 * 8); up(side.st, cu, lp.col_upper, (size_t)n0 * 8);
+  PREP_OK(cudaEventRecord(side.values_up, side.st));
   h2d_bytes = (size_t)(n0 + 1) * 4 + (size_t)nnz0 * 12 + (size_t)n0 * 24 + (size_t)m * 16;
 
   // ---- classification, row order
@@ -540,18 +574,15 @@ void DevicePrologue::run(cudaStream_t s, const b200pdlp_lp& lp, bool do_scale, i
   double* colscale = tmp.get<double>(n);
   double* rhs = tmp.get<double>(m);
   double* rowscale = tmp.get<double>(m);
-  col_vectors_kernel<<<grid_for(std::max(n0, 1)), kTpb, 0, s>>>(n0, n, nnz, lp.sense, a_start, cc, cl, cu, cost, lower, upper, cbeg);
+  col_vectors_kernel<<<grid_for(std::max(n0, 1)), kTpb, 0, s>>>(n0, n, nnz, lp.sense, a_start, cc, cl, cu, cost, lower, upper, cbeg, 1);
   if (m > 0)
     row_maps_kernel<<<grid_for(m), kTpb, 0, s>>>(m, n0, nnz0, neq, rl, ru, cls, eq_ex, bd_ex, arr.row_new_idx, arr.row_old,
                                                  arr.slack_row, rhs, cost, lower, upper, cbeg, cidx, cval, colof);
+  unsigned* dest = tmp.get<unsigned>(nnz0);
   if (nnz0 > 0) {
-    scatter_entries_kernel<<<grid_for(nnz0), kTpb, 0, s>>>(nnz0, a_start, a_index, a_value, colof0, fl_ex, cls,
-                                                           arr.row_new_idx, cidx, cval);
+    scatter_entries_kernel<<<grid_for(nnz0), kTpb, 0, s>>>(nnz0, a_start, a_index, colof0, fl_ex, cls, arr.row_new_idx, cidx, dest);
     PREP_OK(cudaMemcpyAsync(colof, colof0, (size_t)nnz0 * sizeof(int), cudaMemcpyDeviceToDevice, s));
   }
-  if (n > 0) fill_d_kernel<<<grid_for(n), kTpb, 0, s>>>(n, colscale, 1.0);
-  if (m > 0) fill_d_kernel<<<grid_for(m), kTpb, 0, s>>>(m, rowscale, 1.0);
-  // Init_Scaling (cupdlp_scaling.c:395-425): 2-norms of the unscaled cost and rhs
   double* part = tmp.get<double>(4 * 4736);
   double* dsc = tmp.get<double>(16);
   PREP_OK(cudaMemsetAsync(dsc, 0, 16 * sizeof(double), s));
@@ -561,8 +592,6 @@ void DevicePrologue::run(cudaStream_t s, const b200pdlp_lp& lp, bool do_scale, i
     sumsq_partial_kernel<<<g, kTpb, 0, s>>>(len, v, part + (size_t)slot * 4736);
     sum_final_kernel<<<1, kTpb, 0, s>>>(g, part + (size_t)slot * 4736, out);
   };
-  sumsq(cost, n, dsc + 0, 0);
-  sumsq(rhs, m, dsc + 1, 1);
 
   nvtxRangePop();
   nvtxRangePushA("row-major index (radix sort)");
@@ -599,29 +628,37 @@ void DevicePrologue::run(cudaStream_t s, const b200pdlp_lp& lp, bool do_scale, i
     PREP_OK(cub::DeviceRadixSort::SortPairs(w, bytes, k_in, k_out, rpos, cpos, nnz, 0, end_bit, s));
   }
 
-  nvtxRangePop();
-  nvtxRangePushA("Ruiz + Pock-Chambolle scaling");
-  // ---- PDHG_Scale_Data (setup_kernels.cu): 10 Ruiz passes + Pock-Chambolle, bit-identical to host_prep.cpp::scale
-  double* cs = tmp.get<double>(n);
-  double* cnorm = tmp.get<double>(n);
-  double* rs = tmp.get<double>(m);
-  double* rnorm = tmp.get<double>(m);
-  double* amax = dsc + 4;
-  DevForm F{n, m, nnz, cbeg, cidx, colof, cval, cost, lower, upper, colscale, rhs, rowscale};
-  DevScaleScratch w{cs, cnorm, rs, rnorm, amax};
-  if (do_scale && nnz > 0) {
-    device_scale_ruiz(s, F, w, /*have_colof=*/true);
-    device_scale_pock_chambolle(s, F, w, rptr, rpos);
-  } else if (nnz > 0) {
-    device_abs_max(s, nnz, cval, amax);
-  }
-  PREP_OK(cudaGetLastError());
-  // PDHG_Init_Step_Sizes: |c|^2, |b|^2 of the scaled data
-  sumsq(cost, n, dsc + 2, 2);
-  sumsq(rhs, m, dsc + 3, 3);
+  auto values_and_scaling = [&]() {
+    NvtxRange r2("values: formulate + Ruiz + Pock-Chambolle scaling");
+    // ---- the values have arrived (or the stream waits for them here)
+    PREP_OK(cudaStreamWaitEvent(s, side.values_up, 0));
+    col_vectors_kernel<<<grid_for(std::max(n0, 1)), kTpb, 0, s>>>(n0, n, nnz, lp.sense, a_start, cc, cl, cu, cost, lower, upper, cbeg, 2);
+    if (nnz0 > 0) scatter_values_kernel<<<grid_for(nnz0), kTpb, 0, s>>>(nnz0, a_value, dest, cval);
+    if (n > 0) fill_d_kernel<<<grid_for(n), kTpb, 0, s>>>(n, colscale, 1.0);
+    if (m > 0) fill_d_kernel<<<grid_for(m), kTpb, 0, s>>>(m, rowscale, 1.0);
+    // Init_Scaling (cupdlp_scaling.c:395-425): 2-norms of the unscaled cost and rhs
+    sumsq(cost, n, dsc + 0, 0);
+    sumsq(rhs, m, dsc + 1, 1);
+    // ---- PDHG_Scale_Data (setup_kernels.cu): 10 Ruiz passes + Pock-Chambolle, bit-identical to host_prep.cpp::scale
+    double* cs = tmp.get<double>(n);
+    double* cnorm = tmp.get<double>(n);
+    double* rs = tmp.get<double>(m);
+    double* rnorm = tmp.get<double>(m);
+    double* amax = dsc + 4;
+    DevForm F{n, m, nnz, cbeg, cidx, colof, cval, cost, lower, upper, colscale, rhs, rowscale};
+    DevScaleScratch w{cs, cnorm, rs, rnorm, amax};
+    if (do_scale && nnz > 0) {
+      device_scale_ruiz(s, F, w, /*have_colof=*/true);
+      device_scale_pock_chambolle(s, F, w, rptr, rpos);
+    } else if (nnz > 0) {
+      device_abs_max(s, nnz, cval, amax);
+    }
+    PREP_OK(cudaGetLastError());
+    // PDHG_Init_Step_Sizes: |c|^2, |b|^2 of the scaled data
+    sumsq(cost, n, dsc + 2, 2);
+    sumsq(rhs, m, dsc + 3, 3);
 
-  nvtxRangePop();
-  nvtxRangePushA("orderings + sliced-ELL layouts");
+  };
   auto keep_the_form = [&]() {
     // the standard form in standard-form order survives the prologue (tests: b200pdlp_problem_get_*; several GPUs: the host
     // builds every rank's layouts from it)
@@ -635,6 +672,7 @@ void DevicePrologue::run(cudaStream_t s, const b200pdlp_lp& lp, bool do_scale, i
     if (nnz > 0) gather_i_kernel<<<grid_for(nnz), kTpb, 0, s>>>(nnz, colof, rpos, form.rcol);
   };
   if (stop_after_scaling) {
+    values_and_scaling();
     keep_the_form();
     double hd[5] = {0, 0, 0, 0, 0};
     PREP_OK(cudaMemcpyAsync(hd, dsc, 5 * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -643,7 +681,8 @@ void DevicePrologue::run(cudaStream_t s, const b200pdlp_lp& lp, bool do_scale, i
     nvtxRangePop();
     return;
   }
-
+  nvtxRangePop();
+  nvtxRangePushA("orderings + sliced-ELL layouts");
   // ---- device orderings and sliced-ELL plans
   arr.rperm = keep<int>(m); arr.rinv = keep<int>(m);
   arr.cperm = keep<int>(n); arr.cinv = keep<int>(n);
@@ -679,17 +718,17 @@ void DevicePrologue::run(cudaStream_t s, const b200pdlp_lp& lp, bool do_scale, i
   };
   plan1(pa, m, arr.rperm, rptr);
   plan1(pat, n, arr.cperm, cbeg);
-  // read-back 2: sizes of the layouts + the scalars
-  struct { long long a_slots, at_slots; int a_nlong, at_nlong; double d[5]; int flags4[4]; } hb;
+  // read-back 2: sizes of the layouts
+  struct { long long a_slots, at_slots; int a_nlong, at_nlong; } hb;
   memset(&hb, 0, sizeof(hb));
-  PREP_OK(cudaMemcpyAsync(&hb.a_slots, pa.slot_ex + pa.nslices, sizeof(long long), cudaMemcpyDeviceToHost, s));
-  PREP_OK(cudaMemcpyAsync(&hb.at_slots, pat.slot_ex + pat.nslices, sizeof(long long), cudaMemcpyDeviceToHost, s));
-  PREP_OK(cudaMemcpyAsync(&hb.a_nlong, pa.nlong_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
-  PREP_OK(cudaMemcpyAsync(&hb.at_nlong, pat.nlong_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
-  PREP_OK(cudaMemcpyAsync(hb.d, dsc, 5 * sizeof(double), cudaMemcpyDeviceToHost, s));
-  PREP_OK(cudaStreamSynchronize(s));
+  if (!stop_after_scaling) {
+    PREP_OK(cudaMemcpyAsync(&hb.a_slots, pa.slot_ex + pa.nslices, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    PREP_OK(cudaMemcpyAsync(&hb.at_slots, pat.slot_ex + pat.nslices, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    PREP_OK(cudaMemcpyAsync(&hb.a_nlong, pa.nlong_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PREP_OK(cudaMemcpyAsync(&hb.at_nlong, pat.nlong_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PREP_OK(cudaStreamSynchronize(s));
+  }
   sc.a_padded = hb.a_slots; sc.at_padded = hb.at_slots; sc.a_nlong = hb.a_nlong; sc.at_nlong = hb.at_nlong;
-  sc.norm_cost_sq = hb.d[0]; sc.norm_rhs_sq = hb.d[1]; sc.beta_cost_sq = hb.d[2]; sc.beta_rhs_sq = hb.d[3]; sc.amax = hb.d[4];
   if (sc.a_padded > 2000000000LL || sc.at_padded > 2000000000LL)
     throw std::runtime_error("b200pdlp: matrix too large for 32-bit slice offsets");
   // long rows: count the segments first (sizes), then write the descriptors
@@ -705,6 +744,8 @@ void DevicePrologue::run(cudaStream_t s, const b200pdlp_lp& lp, bool do_scale, i
   sc.a_nsegs = (int)ht[0]; sc.a_lcount = ht[1]; sc.at_nsegs = (int)ht[2]; sc.at_lcount = ht[3];
   if (sc.a_lcount > 2000000000LL || sc.at_lcount > 2000000000LL)
     throw std::runtime_error("b200pdlp: long rows too large for 32-bit offsets");
+
+  values_and_scaling();
 
   // ---- allocate and fill the layouts
   auto build = [&](DevSellOwned& M, Plan& P, int nrows, int ncols, long long padded, int nlong, int nsegs, long long lcount,
@@ -754,10 +795,13 @@ void DevicePrologue::run(cudaStream_t s, const b200pdlp_lp& lp, bool do_scale, i
   PREP_OK(cudaGetLastError());
   if (keep_form) keep_the_form();
   nvtxRangePop();
-  int tb = 0;
-  PREP_OK(cudaMemcpyAsync(&tb, too_big, sizeof(int), cudaMemcpyDeviceToHost, s));
+  struct { double d[5]; int tb; } hfin;
+  memset(&hfin, 0, sizeof(hfin));
+  PREP_OK(cudaMemcpyAsync(hfin.d, dsc, 5 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  PREP_OK(cudaMemcpyAsync(&hfin.tb, too_big, sizeof(int), cudaMemcpyDeviceToHost, s));
   PREP_OK(cudaStreamSynchronize(s));   // the temporaries go back to the cache below: everything that reads them is done
-  if (tb) throw std::runtime_error("b200pdlp: matrix too large for 32-bit slice offsets");
+  sc.norm_cost_sq = hfin.d[0]; sc.norm_rhs_sq = hfin.d[1]; sc.beta_cost_sq = hfin.d[2]; sc.beta_rhs_sq = hfin.d[3]; sc.amax = hfin.d[4];
+  if (hfin.tb) throw std::runtime_error("b200pdlp: matrix too large for 32-bit slice offsets");
 }
 
 // ===================================================================================== solve boundary

@@ -97,7 +97,23 @@ sweep_kernel(int nnz, int mode, const int* __restrict__ cidx, const int* __restr
     cval[p] = v;
     const double a = fabs(v);
     if (mode == 0) {
-      atomic_max_nonneg(cnorm + j, a);
+      // the nonzeros are stored by column, so a warp's 32 consecutive entries fall into a few CONTIGUOUS runs of equal
+      // columns: a segmented suffix-maximum with shuffles (max is order-free: exact) leaves each run's maximum in its
+      // first lane, and only that lane issues the column atomic (~8x fewer same-address atomics)
+      if (__activemask() == 0xffffffffu) {
+        const int lane = threadIdx.x & 31;
+        double cm = a;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double v2 = __shfl_down_sync(0xffffffffu, cm, o);
+          const int j2 = __shfl_down_sync(0xffffffffu, j, o);
+          if (lane + o < 32 && j2 == j) cm = v2 > cm ? v2 : cm;
+        }
+        const int jprev = __shfl_up_sync(0xffffffffu, j, 1);
+        if (lane == 0 || jprev != j) atomic_max_nonneg(cnorm + j, cm);
+      } else {
+        atomic_max_nonneg(cnorm + j, a);
+      }
       atomic_max_nonneg(rnorm + i, a);
     } else if (mode == 2) {
       am = a > am ? a : am;
@@ -116,22 +132,38 @@ sweep_kernel(int nnz, int mode, const int* __restrict__ cidx, const int* __restr
   }
 }
 
-// out[r] = sum over q in [ptr[r], ptr[r+1]) of |val[pos ? pos[q] : q]|, added in q order (see the header)
+// out[r] = sum over q in [ptr[r], ptr[r+1]) of |val[pos ? pos[q] : q]|, added in q order (see the header).
+// One THREAD per row for rows of up to 64 entries (the usual case: a lane just walks its row; neighbouring lanes walk
+// neighbouring rows, so the lines are shared through L1); longer rows are then taken one at a time by the whole warp: the
+// lanes load 32 entries at once and every lane adds them in index order (shuffle broadcast) -- same order, parallel loads.
+constexpr int kShortRow = 64;
 __global__ void __launch_bounds__(kTpb)
 ordered_abs_sums_kernel(int nrows, const int* __restrict__ ptr, const int* __restrict__ pos,
                         const double* __restrict__ val, double* __restrict__ out) {
-  const int r = (blockIdx.x * kTpb + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (r >= nrows) return;   // whole warps leave together
-  const int b = ptr[r], e = ptr[r + 1];
-  double sum = 0.0;
-  for (int base = b; base < e; base += 32) {
-    const int q = base + lane;
-    double a = 0.0;
-    if (q < e) a = fabs(val[pos ? pos[q] : q]);
-    const int cnt = (e - base) < 32 ? (e - base) : 32;   // warp-uniform
-    for (int k = 0; k < cnt; k++) sum = sum + __shfl_sync(0xffffffffu, a, k);
+  const int r = blockIdx.x * kTpb + threadIdx.x, lane = threadIdx.x & 31;
+  int b = 0, e = 0;
+  if (r < nrows) { b = ptr[r]; e = ptr[r + 1]; }
+  const bool is_long = e - b > kShortRow;
+  if (r < nrows && !is_long) {
+    double sum = 0.0;
+    for (int q = b; q < e; q++) sum = sum + fabs(val[pos ? pos[q] : q]);
+    out[r] = sum;
   }
-  if (lane == 0) out[r] = sum;
+  unsigned todo = __ballot_sync(0xffffffffu, is_long);   // (whole warps reach this point together)
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int lb = __shfl_sync(0xffffffffu, b, src), le = __shfl_sync(0xffffffffu, e, src);
+    double sum = 0.0;
+    for (int base = lb; base < le; base += 32) {
+      const int q = base + lane;
+      double a = 0.0;
+      if (q < le) a = fabs(val[pos ? pos[q] : q]);
+      const int cnt = (le - base) < 32 ? (le - base) : 32;   // warp-uniform
+      for (int k = 0; k < cnt; k++) sum = sum + __shfl_sync(0xffffffffu, a, k);
+    }
+    if (lane == 0) out[(r - lane) + src] = sum;
+  }
 }
 
 // max |a_ij| of an unscaled matrix (scaling switched off: PDHG_Init_Step_Sizes still needs it)
@@ -174,8 +206,8 @@ void device_scale_ruiz(cudaStream_t s, const DevForm& F, DevScaleScratch& w, boo
 
 void device_scale_pock_chambolle(cudaStream_t s, const DevForm& F, DevScaleScratch& w, const int* rptr, const int* rpos) {
   // 1-norms in the reference's summation order (empty columns / rows sum to 0 -> factor 1)
-  if (F.n > 0) ordered_abs_sums_kernel<<<warp_grid(F.n), kTpb, 0, s>>>(F.n, F.cbeg, nullptr, F.cval, w.cnorm);
-  if (F.m > 0) ordered_abs_sums_kernel<<<warp_grid(F.m), kTpb, 0, s>>>(F.m, rptr, rpos, F.cval, w.rnorm);
+  if (F.n > 0) ordered_abs_sums_kernel<<<(F.n + kTpb - 1) / kTpb, kTpb, 0, s>>>(F.n, F.cbeg, nullptr, F.cval, w.cnorm);
+  if (F.m > 0) ordered_abs_sums_kernel<<<(F.m + kTpb - 1) / kTpb, kTpb, 0, s>>>(F.m, rptr, rpos, F.cval, w.rnorm);
   if (F.n > 0) col_factors_kernel<<<grid_for(F.n), kTpb, 0, s>>>(F.n, w.cnorm, w.cs, F.cost, F.lower, F.upper, F.colscale);
   if (F.m > 0) row_factors_kernel<<<grid_for(F.m), kTpb, 0, s>>>(F.m, w.rnorm, w.rs, F.rhs, F.rowscale);
   cudaMemsetAsync(w.amax, 0, sizeof(double), s);
