@@ -39,8 +39,11 @@ WORKLOADS = {  # name -> (m, n, nnz_per_col, dense_col_nnz)   SURVEY.md 8(d)
     # not a BASELINE config: S3's sizes with a banded (structured) pattern, to show what the SpMV kernels reach when the
     # gathers share sectors as they do on real LP matrices; reported beside S3, never instead of it
     "S3B": (1_000_000, 1_000_000, 8, 0),
+    # ... and with the same 8 offsets in every column (multi-diagonal / stencil-like): a warp's 32 gathers are 32 consecutive
+    # doubles, the upper end of sector sharing -- what the kernels reach when the gather pipe is not the limit
+    "S3D": (1_000_000, 1_000_000, 8, 0),
 }
-BANDS = {"S3B": 2048}
+BANDS = {"S3B": 2048, "S3D": -2048}   # > 0: random rows within the band; < 0: the same offsets in every column (multi-diagonal)
 SEED = 12345
 
 
@@ -544,7 +547,9 @@ def main():
         "config": {"workload": f"{args.workload}: synthetic random sparse LP m={m} n={n} nnz={nnz} seed={SEED}"
                                + (f" + one column with {dense} nonzeros" if dense else "")
                                + (f" -- BANDED pattern (rows within {BANDS[args.workload]} of the diagonal; structured, "
-                                  "not a BASELINE config)" if args.workload in BANDS else ""),
+                                  "not a BASELINE config)" if BANDS.get(args.workload, 0) > 0 else "")
+                               + (f" -- MULTI-DIAGONAL pattern (the same offsets within {-BANDS[args.workload]} of the diagonal in "
+                                  "every column; structured, not a BASELINE config)" if BANDS.get(args.workload, 0) < 0 else ""),
                    "options": "solver=pdlp presolve=off, adaptive step + restarts, checks every 40 iterations",
                    "l2": "inputs larger than L2 (one iteration streams ~0.37 GB vs 126 MB L2)" if args.workload != "S2"
                          else "working set fits L2 (S2)",

@@ -282,6 +282,8 @@ struct b200pdlp_problem {
   DevBuf<double> trace_dev;
   cudaGraphExec_t graph_pow2[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // 1 << k passes
   cudaGraphExec_t graph_check = nullptr;
+  cudaGraphExec_t graph_check_light = nullptr;   // the dense-check phase's check: two sweeps instead of two SpMV (see kDenseChecks)
+  DevBuf<double> axsum, atysum;                   // A xSum (ml), A'ySum (n): carried by the passes while iter < kDenseChecks
   long long launches = 0;
   int kernels_per_pass = 4;
 
@@ -292,6 +294,7 @@ struct b200pdlp_problem {
     if (graph_small) cudaGraphExecDestroy(graph_small);
     for (cudaGraphExec_t g : graph_pow2) if (g) cudaGraphExecDestroy(g);
     if (graph_check) cudaGraphExecDestroy(graph_check);
+    if (graph_check_light) cudaGraphExecDestroy(graph_check_light);
     if (hctl) pinned_cache_free(hctl);
     if (htime) pinned_cache_free(htime);
     for (void* q : ipc_opened) cudaIpcCloseMemHandle(q);
@@ -573,6 +576,7 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   for (int k = 0; k < 2; k++) { p->x[k].alloc(nl); p->aty[k].alloc(nl); p->y[k].alloc(ml); p->ax[k].alloc(ml); }
   p->xsum.alloc(nl); p->xavg.alloc(nl); p->atyavg.alloc(nl); p->xlr.alloc(nl);
   p->ysum.alloc(ml); p->yavg.alloc(ml); p->axavg.alloc(ml); p->ylr.alloc(ml);
+  if (world == 1 && !p->ordered) { p->axsum.alloc(ml); p->atysum.alloc(nl); }
   if (world > 1) {
     p->xfull.alloc((size_t)world * p->seg_len); p->part.alloc((size_t)world * p->seg_len);
     p->recv.alloc((size_t)world * p->seg_len);
@@ -695,6 +699,7 @@ static void create_problem_device(const b200pdlp_lp& lp, const b200pdlp_params& 
   for (int k = 0; k < 2; k++) { p->x[k].alloc(n, false); p->aty[k].alloc(n, false); p->y[k].alloc(m, false); p->ax[k].alloc(m, false); }
   p->xsum.alloc(n, false); p->xavg.alloc(n, false); p->atyavg.alloc(n, false); p->xlr.alloc(n, false);
   p->ysum.alloc(m, false); p->yavg.alloc(m, false); p->axavg.alloc(m, false); p->ylr.alloc(m, false);
+  p->axsum.alloc(m, false); p->atysum.alloc(n, false);
   p->io_col.alloc((size_t)2 * std::max(f.n_orig, 1), false);
   p->io_row.alloc((size_t)2 * std::max(m, 1), false);
   size_t maxgrid = std::max<size_t>(kMaxEwBlocks, std::max(p->A.grid_full(), p->AT.grid_full()));
@@ -753,8 +758,8 @@ static void enqueue_pass(b200pdlp_problem* p) {
   launch_primal_step(s, p->n, st, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->cost.p, p->lower.p,
                      p->upper.p, p->xsum.p, r1);
   launch_spmv_dual(s, p->A.dev, st, p->x[0].p, p->x[1].p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p,
-                   p->rhs.p, p->ysum.p, p->neq_local, 0, r2);
-  launch_spmv_primal(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, r3);
+                   p->rhs.p, p->ysum.p, p->neq_local, 0, r2, p->axsum.p);
+  launch_spmv_primal(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, r3, p->atysum.p);
   launch_step_rule(s, st, r1, primal_step_grid(p->n), r2, p->A.grid(), r3, p->AT.grid(), nullptr);
 }
 
@@ -1189,6 +1194,7 @@ static void drop_graphs(b200pdlp_problem* p) {
   if (p->graph_small) { cudaGraphExecDestroy(p->graph_small); p->graph_small = nullptr; }
   for (cudaGraphExec_t& g : p->graph_pow2) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
   if (p->graph_check) { cudaGraphExecDestroy(p->graph_check); p->graph_check = nullptr; }
+  if (p->graph_check_light) { cudaGraphExecDestroy(p->graph_check_light); p->graph_check_light = nullptr; }
 }
 
 static bool use_device_checks(const b200pdlp_problem* p, const b200pdlp_params& prm) {
@@ -1237,39 +1243,50 @@ static int enqueue_check_device_mg(b200pdlp_problem* p) {
   return 16;
 }
 
-// the six launches of one check (pdhg_kernels.cu "device-side check iteration"); no-ops unless the check is due
-static void enqueue_check_device(b200pdlp_problem* p) {
+// the six launches of one check (pdhg_kernels.cu "device-side check iteration"); no-ops unless the check is due.
+// light: the dense-check phase's variant (five launches: two sweeps over the carried A xSum / A'ySum instead of C1-C3)
+static void enqueue_check_device(b200pdlp_problem* p, bool light = false) {
   if (p->world > 1) { enqueue_check_device_mg(p); return; }
   cudaStream_t s = p->stream;
   PdhgState* st = p->state.p;
   SolveCtl* ctl = p->ctl.p;
   const int n = p->n, ml = p->ml;
   const ReduceScratch rrow = p->rs(kSlotChk, ml), rcol = p->rs(kSlotK3, n), rrst = p->rs(kSlotK1, n);
-  launch_check_avg_x(s, n, p->x[0].p, p->x[1].p, p->xsum.p, p->xavg.p, st, ctl);
-  launch_spmv_check_rows(s, p->A.dev, st, ctl, p->xavg.p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->ysum.p,
-                         p->yavg.p, p->axavg.p, p->rhs.p, p->rowscale.p, p->neq_local, rrow);
-  launch_spmv_check_cols(s, p->AT.dev, st, ctl, p->yavg.p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->xavg.p,
-                         p->atyavg.p, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, rcol);
-  launch_check_decide(s, st, ctl, rrow.partials, p->A.grid_full(), rcol.partials, p->AT.grid_full(), rrow.counter);
+  if (light) {
+    launch_check_light_cols(s, n, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->xsum.p, p->atysum.p, p->xavg.p,
+                            p->atyavg.p, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, st, ctl, rcol);
+    launch_check_light_rows(s, ml, p->neq_local, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->ysum.p, p->axsum.p,
+                            p->yavg.p, p->axavg.p, p->rhs.p, p->rowscale.p, st, ctl, rrow);
+    launch_check_decide(s, st, ctl, rrow.partials, check_light_grid(ml), rcol.partials, check_light_grid(n), rrow.counter);
+  } else {
+    launch_check_avg_x(s, n, p->x[0].p, p->x[1].p, p->xsum.p, p->xavg.p, st, ctl);
+    launch_spmv_check_rows(s, p->A.dev, st, ctl, p->xavg.p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->ysum.p,
+                           p->yavg.p, p->axavg.p, p->rhs.p, p->rowscale.p, p->neq_local, rrow, p->axsum.p);
+    launch_spmv_check_cols(s, p->AT.dev, st, ctl, p->yavg.p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->xavg.p,
+                           p->atyavg.p, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, rcol, p->atysum.p);
+    launch_check_decide(s, st, ctl, rrow.partials, p->A.grid_full(), rcol.partials, p->AT.grid_full(), rrow.counter);
+  }
   launch_restart_sweep(s, n, ml, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->xavg.p, p->atyavg.p, p->xsum.p,
                        p->xlr.p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->yavg.p, p->axavg.p, p->ysum.p, p->ylr.p,
-                       st, ctl, rrst);
+                       st, ctl, rrst, p->atysum.p, p->axsum.p);
   launch_check_finish(s, st, ctl, rrst.partials, restart_sweep_grid(n, ml));
 }
 static constexpr int kCheckLaunches = 6;
 
-static void launch_check_graph(b200pdlp_problem* p) {
-  if (p->no_graph) { enqueue_check_device(p); p->launches += p->world > 1 ? 16 : kCheckLaunches; return; }
-  if (!p->graph_check) {
+static void launch_check_graph(b200pdlp_problem* p, bool light = false) {
+  const int nl = p->world > 1 ? 16 : (light ? kCheckLaunches - 1 : kCheckLaunches);
+  if (p->no_graph) { enqueue_check_device(p, light); p->launches += nl; return; }
+  cudaGraphExec_t& ge = light ? p->graph_check_light : p->graph_check;
+  if (!ge) {
     cudaGraph_t g = nullptr;
     CUDA_OK(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
-    enqueue_check_device(p);
+    enqueue_check_device(p, light);
     CUDA_OK(cudaStreamEndCapture(p->stream, &g));
-    CUDA_OK(cudaGraphInstantiate(&p->graph_check, g, 0));
+    CUDA_OK(cudaGraphInstantiate(&ge, g, 0));
     CUDA_OK(cudaGraphDestroy(g));
   }
-  CUDA_OK(cudaGraphLaunch(p->graph_check, p->stream));
-  p->launches += p->world > 1 ? 16 : kCheckLaunches;
+  CUDA_OK(cudaGraphLaunch(ge, p->stream));
+  p->launches += nl;
 }
 
 // `d` PDHG passes: the main graph (one check interval + spare passes) when d is about an interval, otherwise graphs of
@@ -1482,6 +1499,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   bool have_check = false;
   bool have_spec = false, spec_flag = false;   // a speculative check already produced the next check's scalars
   const bool speculate = can_speculate_check(p);
+  bool h_light = false;
   CudaEvent ev0, ev1, evl0, evl1;
   double iter_ms = 0.0;
   CUDA_OK(cudaEventRecord(evl0, s));
@@ -1509,6 +1527,17 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
       c->time_flag = t_lim >= 0 ? dflag : nullptr;   // (no limit: spare the device the read over PCIe)
     }
     c->term = -1;
+    // dense-check phase (iterations 0 .. kDenseChecks-1 are all check iterations): the passes carry A xSum and A'ySum, the
+    // checks are two vector sweeps.  B200PDLP_LIGHT_CHECK=0: every check multiplies the average iterate by A and A'.
+    h_light = p->world == 1 && p->axsum.p && p->atysum.p;
+    if (const char* e = getenv("B200PDLP_LIGHT_CHECK")) if (atoi(e) == 0) h_light = false;
+    h->light_on = h_light ? 1 : 0;
+    if (h_light) {
+      // xSum starts at proj(0) (PDHG_Init_Variables): without a hot start that IS x, whose product is at hand
+      if (warm && warm->col_value && warm->row_value && warm->row_dual) { launch_spmv_plain(s, p->A.dev, p->xsum.p, p->axsum.p); p->launches++; }
+      else CUDA_OK(cudaMemcpyAsync(p->axsum.p, p->ax[0].p, (size_t)std::max(ml, 1) * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      CUDA_OK(cudaMemsetAsync(p->atysum.p, 0, (size_t)std::max(n, 1) * sizeof(double), s));
+    }
     if (out->trace && out->trace_cap > 0) {
       if (p->trace_dev.n < (size_t)out->trace_cap * B200PDLP_TRACE_COLS) p->trace_dev.alloc((size_t)out->trace_cap * B200PDLP_TRACE_COLS, false);
       c->trace = p->trace_dev.p; c->trace_cap = out->trace_cap;
@@ -1539,7 +1568,9 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
         passes += carry; pred_iter += carry; carry = 0;
       }
       while (rounds < 12 && passes < 48) {
-        launch_check_graph(p);
+        // pred_iter never runs behind the device's iteration count, so pred_iter < kDenseChecks implies the device is
+        // inside the dense phase as well (the light kernels check it once more themselves)
+        launch_check_graph(p, h_light && pred_iter < kDenseChecks);
         rounds++;
         if (pred_iter >= prm.iter_limit - 1) { pred_term = true; break; }
         const int next = next_stop(pred_iter);

@@ -46,6 +46,10 @@ constexpr int kPowTab = 128;           // entries of the step-rule power tables
 constexpr int kMaxEwBlocks = 148 * 16; // grid cap of the element-wise kernels
 
 // Device-resident control block of the PDHG loop (one per problem).
+// cuPDLP checks EVERY one of the first 10 iterations (cupdlp_solver.c:953-962).  During that phase the passes keep
+// axsum = A xSum and atysum = A'ySum up to date (the products of the accepted iterates are at hand in K2 / K3, weighted
+// like xSum / ySum), so that those checks need no SpMV of the average iterate: two vector sweeps instead.
+constexpr int kDenseChecks = 10;
 struct PdhgState {
   // step sizes (cupdlp_defs.h CUPDLPstepsize): eta = dStepSizeUpdate carried into the next pass
   double eta, beta, tau, sigma;      // tau/sigma = dPrimalStep/dDualStep of the last accepted step
@@ -64,7 +68,7 @@ struct PdhgState {
   int pow_base;                      // step_iter value that pow tables entry 0 belongs to
   int accepted_last;                 // multi-GPU: the previous pass was accepted (its A^T y' becomes current)
   int done;                          // device-driven loop: the solve has terminated -- every later kernel is a no-op
-  int pad0;
+  int light_on;                      // 1: while iter < kDenseChecks the passes also carry A xSum and A'ySum (see "light check")
   double pow_red[kPowTab];           // (k+1)^-0.3 for k = pow_base+1+i   (host-computed, glibc pow)
   double pow_grow[kPowTab];          // (k+1)^-0.6
 };

@@ -112,31 +112,35 @@ struct DualEpilogueT {
   const double* b;
   double* ysum;
   int neq, row_offset;         // neq = number of LOCAL equality rows (they come first); row_offset unused
+  double* axsum;               // A xSum, carried while the checks are dense (PdhgState::light_on); may be nullptr
   // cached from the state block by begin()
   const double *y, *ax;
   double *yn, *axn;
   double sigma, w;
-  bool pend;
+  bool pend, accum;
   __device__ bool begin() {
     if (st->iter >= st->stop_iter) return false;
     const int cur = st->cur;
     y = cur ? y1 : y0; yn = cur ? y0 : y1;
     ax = cur ? ax1 : ax0; axn = cur ? ax0 : ax1;
     sigma = st->sigma_try; w = st->w_pending; pend = st->pending != 0;
+    accum = pend && st->light_on && st->iter < kDenseChecks;
     x0 = cur ? x0 : x1;   // x0 now = input vector (the NEW x)
     return true;
   }
   __device__ const double* input() const { return x0; }
   // the row's epilogue operands are requested BEFORE the gather loop so that they arrive under it
-  double p_y, p_b, p_ax, p_ys;
+  double p_y, p_b, p_ax, p_ys, p_axs;
   __device__ void prefetch(int r) {
     p_y = y[r]; p_b = b[r]; p_ax = ax[r];
     p_ys = pend ? ysum[r] : 0.0;
+    p_axs = accum ? axsum[r] : 0.0;
   }
   __device__ void row(int r, double s, double* t) const {
     axn[r] = s;
     const double yc = p_y;
     if (pend) ysum[r] = p_ys + w * yc;
+    if (accum) axsum[r] = p_axs + w * p_ax;   // A xSum += w A x  (x = the iterate accepted by the previous pass)
     double v = yc + sigma * p_b;
     v = v + (-2.0 * sigma) * s;
     v = v + sigma * p_ax;
@@ -207,21 +211,27 @@ struct PrimalEpilogue {
   const double *y0, *y1;       // dual double buffer (input = the NEW y)
   const double *x0, *x1;
   double *aty0, *aty1;
+  double* atysum;              // A'ySum, carried while the checks are dense (PdhgState::light_on); may be nullptr
   const double *x, *xn, *aty;
   double* atyn;
+  double w;
+  bool accum;
   __device__ bool begin() {
     if (st->iter >= st->stop_iter) return false;
     const int cur = st->cur;
     x = cur ? x1 : x0; xn = cur ? x0 : x1;
     aty = cur ? aty1 : aty0; atyn = cur ? aty0 : aty1;
     y0 = cur ? y0 : y1;   // y0 now = input vector (the NEW y)
+    w = st->w_pending;
+    accum = st->pending != 0 && st->light_on && st->iter < kDenseChecks;
     return true;
   }
   __device__ const double* input() const { return y0; }
-  double p_x, p_xn, p_aty;
-  __device__ void prefetch(int r) { p_x = x[r]; p_xn = xn[r]; p_aty = aty[r]; }
+  double p_x, p_xn, p_aty, p_as;
+  __device__ void prefetch(int r) { p_x = x[r]; p_xn = xn[r]; p_aty = aty[r]; p_as = accum ? atysum[r] : 0.0; }
   __device__ void row(int r, double s, double* t) const {
     atyn[r] = s;
+    if (accum) atysum[r] = p_as + w * p_aty;   // A'ySum += w A'y
     const double dx = p_x - p_xn;
     const double da = p_aty - s;
     t[0] = dx * da;
@@ -322,7 +332,7 @@ __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_
   if (PIPE && (int)blockIdx.x < A.nblocks_body) {
     // A warp walks the slices  w, w + W, w + 2W, ...  (W = warps of the body CTAs).  With one CTA per 8 slices (the default
     // grid) that is exactly one slice per warp; with a persistent grid (DevSell::nblocks_body = a few CTAs per SM) the walk
-    // is software-pipelined: the descriptor is fetched two slices ahead and the first 8 column ids one slice ahead, so that
+    // is software-pipelined: the descriptor is fetched two slices ahead and the first (up to) 8 column ids one slice ahead, so that
     // a slice's gathers issue at once instead of after two dependent round trips (descriptor -> column ids -> gathers).
     // Per-row arithmetic and its order are the same in both shapes.
     const int lane = threadIdx.x & 31;
@@ -333,18 +343,16 @@ __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_
     if (slice < A.nslices) {
       d = A.slices[slice];
       if (slice + wstride < A.nslices) dn = A.slices[slice + wstride];
-      if (d.y >= 8) {
 #pragma unroll
-        for (int u = 0; u < 8; u++) cpre[u] = A.col[d.x + lane + 32 * u];
-      }
+      for (int u = 0; u < 8; u++) if (u < d.y) cpre[u] = A.col[d.x + lane + 32 * u];
     }
     while (slice < A.nslices) {
       int4 dnn = make_int4(0, 0, -1, 0);
       if (slice + 2 * wstride < A.nslices) dnn = A.slices[slice + 2 * wstride];
       int cnx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      if (slice + wstride < A.nslices && dn.y >= 8) {
+      if (slice + wstride < A.nslices) {
 #pragma unroll
-        for (int u = 0; u < 8; u++) cnx[u] = A.col[dn.x + lane + 32 * u];
+        for (int u = 0; u < 8; u++) if (u < dn.y) cnx[u] = A.col[dn.x + lane + 32 * u];
       }
       const int row = slice * 32 + lane;
       const bool live = !((unsigned)d.z >> lane & 1u);
@@ -353,15 +361,16 @@ __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_
       const double* __restrict__ vp = A.val + d.x + lane;
       double s = 0.0;
       int k = 0;
-      if (d.y >= 8) {
+      {
+        // the first min(len, 8) entries of every row: their column ids arrived one slice ago (u < d.y is warp-uniform)
         double v[8], g[8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) g[u] = xin[cpre[u]];
+        for (int u = 0; u < 8; u++) g[u] = u < d.y ? xin[cpre[u]] : 0.0;
 #pragma unroll
-        for (int u = 0; u < 8; u++) v[u] = vp[32 * u];
+        for (int u = 0; u < 8; u++) v[u] = u < d.y ? vp[32 * u] : 0.0;
 #pragma unroll
-        for (int u = 0; u < 8; u++) s += v[u] * g[u];
-        k = 8;
+        for (int u = 0; u < 8; u++) if (u < d.y) s += v[u] * g[u];
+        k = d.y < 8 ? d.y : 8;
       }
       for (; k + 8 <= d.y; k += 8) {
         int c[8];
@@ -1223,14 +1232,16 @@ struct CheckRowEpilogueT {
   double *ysum, *yavg, *axavg;
   const double *b, *rsc;
   int neq;
+  double* axsum;   // one GPU, dense-check phase: kept consistent with ySum's flush (may be nullptr)
   const double *y, *ax;
   double w, scale;
-  bool pend;
+  bool pend, accum;
   __device__ bool begin() {
     if (!check_live(st, ctl)) return false;
     const int cur = st->cur;
     y = cur ? y1 : y0; ax = cur ? ax1 : ax0;
     w = st->w_pending; pend = st->pending != 0;
+    accum = FLUSH && pend && axsum && st->light_on && st->iter < kDenseChecks;
     scale = st->sum_step > 0.0 ? 1.0 / st->sum_step : 1.0;
     return true;
   }
@@ -1244,6 +1255,7 @@ struct CheckRowEpilogueT {
     if (FLUSH) {
       double ys = p_ys;
       if (pend) { ys = ys + w * p_y; ysum[r] = ys; }
+      if (accum) axsum[r] = axsum[r] + w * p_ax;
       ya = ys * scale;
       yavg[r] = ya;
     } else {
@@ -1265,11 +1277,16 @@ struct CheckColEpilogue {
   const double *x0, *x1, *aty0, *aty1, *xavg;
   double* atyavg;
   const double *c, *lo, *up, *cs;
+  double* atysum;   // dense-check phase: kept consistent with xSum's flush (C1); may be nullptr
   const double *x, *aty;
+  double w;
+  bool accum;
   __device__ bool begin() {
     if (!check_live(st, ctl)) return false;
     const int cur = st->cur;
     x = cur ? x1 : x0; aty = cur ? aty1 : aty0;
+    w = st->w_pending;
+    accum = st->pending != 0 && atysum && st->light_on && st->iter < kDenseChecks;
     return true;
   }
   __device__ const double* input() const { return yavg; }
@@ -1280,10 +1297,83 @@ struct CheckColEpilogue {
   template <class T>
   __device__ void row(int j, double s, T t) const {
     atyavg[j] = s;
+    if (accum) atysum[j] = atysum[j] + w * p_aty;
     col_terms(p_x, p_aty, p_c, p_lo, p_up, p_cs, t);
     col_terms(p_xa, s, p_c, p_lo, p_up, p_cs, t + 10);
   }
 };
+
+// ---- light check (dense-check phase, PdhgState::light_on && iter < kDenseChecks): A xbar = (A xSum) / sum(w) and
+// A'ybar = (A'ySum) / sum(w) come from the sums the passes carried, so C1-C3 become two vector sweeps with the same
+// per-element terms (col_terms / row_terms) and the same downstream kernels (C4-C6).
+__global__ void __launch_bounds__(kThreads)
+check_light_cols_kernel(int n, const double* __restrict__ x0, const double* __restrict__ x1, const double* __restrict__ aty0,
+                        const double* __restrict__ aty1, double* __restrict__ xsum, double* __restrict__ atysum,
+                        double* __restrict__ xavg, double* __restrict__ atyavg, const double* __restrict__ c,
+                        const double* __restrict__ lo, const double* __restrict__ up, const double* __restrict__ cs,
+                        const PdhgState* __restrict__ st, const SolveCtl* __restrict__ ctl, ReduceScratch rs) {
+  if (!check_live(st, ctl) || !st->light_on || st->iter >= kDenseChecks) return;
+  const int cur = st->cur;
+  const double* __restrict__ x = cur ? x1 : x0;
+  const double* __restrict__ aty = cur ? aty1 : aty0;
+  const bool pending = st->pending != 0;
+  const double w = st->w_pending;
+  const double scale = st->sum_step > 0.0 ? 1.0 / st->sum_step : 1.0;
+  double acc[20];
+#pragma unroll
+  for (int a = 0; a < 20; a++) acc[a] = 0.0;
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const double xc = x[i], ac = aty[i];
+    double xs = xsum[i], as = atysum[i];
+    if (pending) { xs = xs + w * xc; xsum[i] = xs; as = as + w * ac; atysum[i] = as; }
+    const double xa = xs * scale, aa = as * scale;
+    xavg[i] = xa;
+    atyavg[i] = aa;
+    const double ci = c[i], l = lo[i], u = up[i], sc = cs[i];
+    double t[20];
+    col_terms(xc, ac, ci, l, u, sc, t);
+    col_terms(xa, aa, ci, l, u, sc, t + 10);
+#pragma unroll
+    for (int a = 0; a < 20; a++) acc[a] += t[a];
+  }
+  block_partials<20>(acc, rs);
+}
+
+__global__ void __launch_bounds__(kThreads)
+check_light_rows_kernel(int m, int neq, const double* __restrict__ y0, const double* __restrict__ y1,
+                        const double* __restrict__ ax0, const double* __restrict__ ax1, double* __restrict__ ysum,
+                        double* __restrict__ axsum, double* __restrict__ yavg, double* __restrict__ axavg,
+                        const double* __restrict__ b, const double* __restrict__ rsc, const PdhgState* __restrict__ st,
+                        const SolveCtl* __restrict__ ctl, ReduceScratch rs) {
+  if (!check_live(st, ctl) || !st->light_on || st->iter >= kDenseChecks) return;
+  const int cur = st->cur;
+  const double* __restrict__ y = cur ? y1 : y0;
+  const double* __restrict__ ax = cur ? ax1 : ax0;
+  const bool pending = st->pending != 0;
+  const double w = st->w_pending;
+  const double scale = st->sum_step > 0.0 ? 1.0 / st->sum_step : 1.0;
+  double acc[8];
+#pragma unroll
+  for (int a = 0; a < 8; a++) acc[a] = 0.0;
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < m; i += stride) {
+    const double yc = y[i], ac = ax[i];
+    double ys = ysum[i], as = axsum[i];
+    if (pending) { ys = ys + w * yc; ysum[i] = ys; as = as + w * ac; axsum[i] = as; }
+    const double ya = ys * scale, aa = as * scale;
+    yavg[i] = ya;
+    axavg[i] = aa;
+    const double bi = b[i], sc = rsc[i];
+    const bool ineq = i >= neq;
+    double t[8];
+    row_terms(yc, ac, bi, sc, ineq, t);
+    row_terms(ya, aa, bi, sc, ineq, t + 4);
+#pragma unroll
+    for (int a = 0; a < 8; a++) acc[a] += t[a];
+  }
+  block_partials<8>(acc, rs);
+}
 
 // PDHG_Check_Restart_GPU (cupdlp_restart.c:3-99): 0 none, 1 to the average, 2 to the current iterate
 __device__ double restart_score_dev(double beta, double pf, double df, double gap) {   // cupdlp_restart.c:113-124
@@ -1325,6 +1415,49 @@ __device__ void trace_row_dev(SolveCtl* c, const PdhgState* st, int restart) {
   c->trace_len++;
 }
 
+// the scalar part of C6 (one thread): restart scalars when a restart was chosen, trace row, next check iteration
+__device__ void finish_scalars(PdhgState* st, SolveCtl* ctl, int choice, const double* d2, int step_iter) {
+  if (choice) {
+    const DevResiduals& R = choice == 1 ? ctl->res[1] : ctl->res[0];
+    ctl->pf_lr = R.pfeas; ctl->df_lr = R.dfeas; ctl->gap_lr = R.gap;
+    const double mean = sqrt(st->tau * st->sigma);
+    const double dxn = sqrt(d2[0]), dyn = sqrt(d2[1]);
+    double beta = st->beta;
+    if (fmin(dxn, dyn) > 1e-10) {
+      const double upd = dyn / dxn;
+      const double lg = 0.5 * log(upd) + 0.5 * log(sqrt(beta));
+      beta = exp(lg) * exp(lg);
+    }
+    st->beta = beta;
+    st->tau = mean / sqrt(beta);
+    st->sigma = st->tau * beta;
+    st->sum_step = 0.0;
+    ctl->last_restart_iter = st->iter;
+    ctl->restarts++;
+    // arm the next pass (start of PDHG_Update_Iterate_Adaptive_Step_Size, cupdlp_step.c:230-242)
+    st->eta = sqrt(st->tau * st->sigma);
+    if (st->adaptive) { st->tau_try = st->eta / sqrt(beta); st->sigma_try = st->eta * sqrt(beta); }
+    else { st->tau_try = st->tau; st->sigma_try = st->sigma; }
+  }
+  trace_row_dev(ctl, st, choice);
+  ctl->restart_choice = 0;
+  st->pending = 0;        // the average flush consumed the pending weight (or the sums were just cleared)
+  st->accepted_last = 0;
+  const int it = st->iter, lim = ctl->iter_limit, iv = ctl->interval;
+  int next = it + 1;
+  while (!(next < 10 || next % iv == 0 || next == lim - 1)) next++;
+  st->stop_iter = next;
+  st->pow_base = step_iter;
+}
+// (k+1)^-0.3, (k+1)^-0.6 for k = step_iter + 1 + t  (cupdlp_step.c:279-284); threads 0 .. kPowTab-1 of one CTA
+__device__ __forceinline__ void finish_pow_tables(PdhgState* st, int step_iter) {
+  if (threadIdx.x < kPowTab) {
+    const double k = (double)(step_iter + 1 + (int)threadIdx.x);
+    st->pow_red[threadIdx.x] = pow(k + 1.0, -0.3);
+    st->pow_grow[threadIdx.x] = pow(k + 1.0, -0.6);
+  }
+}
+
 // C4: sums (fixed order) -> residuals (PDHG_Compute_Residuals / _Infeas_Residuals, cupdlp_solver.c:473-529, :433-471)
 // -> PDHG_Check_Termination[_Average] (:797-841), PDHG_Check_Infeasibility (:740-795), limits (:1057-1067), restart choice
 constexpr int kCheckSums = 28;
@@ -1358,13 +1491,22 @@ check_decide_kernel(PdhgState* __restrict__ st, SolveCtl* __restrict__ ctl, cons
     last = k == (unsigned)gridDim.x - 1u;
   }
   __syncthreads();
-  if (!last || threadIdx.x != 0) return;
-  __threadfence();
-  *ticket = 0u;
-  double tot[kCheckSums];
-  const volatile double* vs = ctl->sums;
-  for (int q = 0; q < kCheckSums; q++) tot[q] = vs[q];
-  decide_from_sums(st, ctl, tot, ctl->time_flag && *ctl->time_flag);
+  if (!last) return;
+  __shared__ int inline_finish;
+  const int step_iter = st->step_iter;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    *ticket = 0u;
+    double tot[kCheckSums];
+    const volatile double* vs = ctl->sums;
+    for (int q = 0; q < kCheckSums; q++) tot[q] = vs[q];
+    decide_from_sums(st, ctl, tot, ctl->time_flag && *ctl->time_flag);
+    // no restart, not finished: C6's bookkeeping right here (C5 and C6 then see a check that is no longer due and return)
+    inline_finish = (ctl->term < 0 && ctl->restart_choice == 0) ? 1 : 0;
+    if (inline_finish) { const double d2[2] = {0.0, 0.0}; finish_scalars(st, ctl, 0, d2, step_iter); }
+  }
+  __syncthreads();
+  if (inline_finish) finish_pow_tables(st, step_iter);
 }
 
 // several GPUs: the 28 sums were all-reduced over the ranks (identical on every rank, added in rank order) into
@@ -1437,8 +1579,10 @@ restart_sweep_kernel(int n, int m, double* __restrict__ x0, double* __restrict__
                      double* __restrict__ xsum, double* __restrict__ xlr, double* __restrict__ y0, double* __restrict__ y1,
                      double* __restrict__ ax0, double* __restrict__ ax1, const double* __restrict__ yavg,
                      const double* __restrict__ axavg, double* __restrict__ ysum, double* __restrict__ ylr,
-                     const PdhgState* __restrict__ st, const SolveCtl* __restrict__ ctl, ReduceScratch rs) {
+                     const PdhgState* __restrict__ st, const SolveCtl* __restrict__ ctl, ReduceScratch rs,
+                     double* __restrict__ atysum, double* __restrict__ axsum) {
   if (!check_live(st, ctl) || ctl->restart_choice == 0) return;
+  const bool dense = st->light_on && st->iter < kDenseChecks;   // A xSum / A'ySum restart with the sums they mirror
   const bool to_avg = ctl->restart_choice == 1;
   const int cur = st->cur;
   double* __restrict__ x = cur ? x1 : x0;
@@ -1449,8 +1593,13 @@ restart_sweep_kernel(int n, int m, double* __restrict__ x0, double* __restrict__
   const int stride = gridDim.x * kThreads;
   // pairs with 128-bit accesses (all vectors are allocation-aligned), then the odd tail
   auto sweep = [&](int len, double* __restrict__ cur_v, double* __restrict__ cur_a, const double* __restrict__ avg_v,
-                   const double* __restrict__ avg_a, double* __restrict__ sum, double* __restrict__ lr, double& acc_out) {
+                   const double* __restrict__ avg_a, double* __restrict__ sum, double* __restrict__ lr, double& acc_out,
+                   double* __restrict__ sum2) {
     const int npair = len >> 1;
+    if (dense && sum2) {
+      for (int i = blockIdx.x * kThreads + threadIdx.x; i < npair; i += stride) reinterpret_cast<double2*>(sum2)[i] = make_double2(0.0, 0.0);
+      if ((len & 1) && blockIdx.x == 0 && threadIdx.x == 0) sum2[len - 1] = 0.0;
+    }
     for (int i = blockIdx.x * kThreads + threadIdx.x; i < npair; i += stride) {
       double2 v;
       if (to_avg) {
@@ -1477,8 +1626,8 @@ restart_sweep_kernel(int n, int m, double* __restrict__ x0, double* __restrict__
       lr[i] = v;
     }
   };
-  sweep(n, x, aty, xavg, atyavg, xsum, xlr, acc[0]);
-  sweep(m, y, ax, yavg, axavg, ysum, ylr, acc[1]);
+  sweep(n, x, aty, xavg, atyavg, xsum, xlr, acc[0], atysum);
+  sweep(m, y, ax, yavg, axavg, ysum, ylr, acc[1], axsum);
   block_partials<2>(acc, rs);
 }
 
@@ -1530,45 +1679,14 @@ check_finish_kernel(PdhgState* __restrict__ st, SolveCtl* __restrict__ ctl, cons
   const int step_iter = st->step_iter;
   __syncthreads();
   if (threadIdx.x == 0) {
+    double d2[2] = {0.0, 0.0};
     if (choice) {
-      double d2[2];
       if (sums2) { d2[0] = sums2[0]; d2[1] = sums2[1]; }
       else for (int a = 0; a < 2; a++) { double s = 0.0; for (int w = 0; w < kFinishThreads / 32; w++) s += sm[a][w]; d2[a] = s; }
-      const DevResiduals& R = choice == 1 ? ctl->res[1] : ctl->res[0];
-      ctl->pf_lr = R.pfeas; ctl->df_lr = R.dfeas; ctl->gap_lr = R.gap;
-      const double mean = sqrt(st->tau * st->sigma);
-      const double dxn = sqrt(d2[0]), dyn = sqrt(d2[1]);
-      double beta = st->beta;
-      if (fmin(dxn, dyn) > 1e-10) {
-        const double upd = dyn / dxn;
-        const double lg = 0.5 * log(upd) + 0.5 * log(sqrt(beta));
-        beta = exp(lg) * exp(lg);
-      }
-      st->beta = beta;
-      st->tau = mean / sqrt(beta);
-      st->sigma = st->tau * beta;
-      st->sum_step = 0.0;
-      ctl->last_restart_iter = st->iter;
-      ctl->restarts++;
-      // arm the next pass (start of PDHG_Update_Iterate_Adaptive_Step_Size, cupdlp_step.c:230-242)
-      st->eta = sqrt(st->tau * st->sigma);
-      if (st->adaptive) { st->tau_try = st->eta / sqrt(beta); st->sigma_try = st->eta * sqrt(beta); }
-      else { st->tau_try = st->tau; st->sigma_try = st->sigma; }
     }
-    trace_row_dev(ctl, st, choice);
-    ctl->restart_choice = 0;
-    st->pending = 0;        // the average flush consumed the pending weight (or the sums were just cleared)
-    st->accepted_last = 0;
-    const int it = st->iter, lim = ctl->iter_limit, iv = ctl->interval;
-    int next = it + 1;
-    while (!(next < 10 || next % iv == 0 || next == lim - 1)) next++;
-    st->stop_iter = next;
-    st->pow_base = step_iter;
+    finish_scalars(st, ctl, choice, d2, step_iter);
   }
-  // (k+1)^-0.3, (k+1)^-0.6 for k = step_iter + 1 + t  (cupdlp_step.c:279-284)
-  const double k = (double)(step_iter + 1 + (int)threadIdx.x);
-  st->pow_red[threadIdx.x] = pow(k + 1.0, -0.3);
-  st->pow_grow[threadIdx.x] = pow(k + 1.0, -0.6);
+  finish_pow_tables(st, step_iter);
 }
 
 // ==================================================================== launchers
@@ -1607,20 +1725,20 @@ void launch_spmv_plain(cudaStream_t s, const DevSell& A, const double* in, doubl
 
 void launch_spmv_dual(cudaStream_t s, const DevSell& A, PdhgState* st, const double* x0, const double* x1,
                       double* y0, double* y1, double* ax0, double* ax1, const double* b, double* ysum,
-                      int neq, int row_offset, ReduceScratch rs) {
+                      int neq, int row_offset, ReduceScratch rs, double* axsum) {
   if (A.nblocks_body + A.nsegs == 0) return;   // no rows on this rank: nothing to launch, the partial count is 0
   DualEpilogue e{};
   e.st = st; e.x0 = x0; e.x1 = x1; e.y0 = y0; e.y1 = y1; e.ax0 = ax0; e.ax1 = ax1; e.b = b; e.ysum = ysum;
-  e.neq = neq; e.row_offset = row_offset;
+  e.neq = neq; e.row_offset = row_offset; e.axsum = axsum;
   if (A.pipelined) launch_k(spmv_sell_kernel<DualEpilogue, true>, A.nblocks_body + A.nsegs, kThreads, s, rs.flags, A, e, rs);
   else launch_k(spmv_sell_kernel<DualEpilogue, false>, A.nblocks_body + A.nsegs, kThreads, s, rs.flags, A, e, rs);
 }
 
 void launch_spmv_primal(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
-                        const double* x0, const double* x1, double* aty0, double* aty1, ReduceScratch rs) {
+                        const double* x0, const double* x1, double* aty0, double* aty1, ReduceScratch rs, double* atysum) {
   if (A.nblocks_body + A.nsegs == 0) return;   // no rows on this rank: nothing to launch, the partial count is 0
   PrimalEpilogue e{};
-  e.st = st; e.y0 = y0; e.y1 = y1; e.x0 = x0; e.x1 = x1; e.aty0 = aty0; e.aty1 = aty1;
+  e.st = st; e.y0 = y0; e.y1 = y1; e.x0 = x0; e.x1 = x1; e.aty0 = aty0; e.aty1 = aty1; e.atysum = atysum;
   if (A.pipelined) launch_k(spmv_sell_kernel<PrimalEpilogue, true>, A.nblocks_body + A.nsegs, kThreads, s, rs.flags, A, e, rs);
   else launch_k(spmv_sell_kernel<PrimalEpilogue, false>, A.nblocks_body + A.nsegs, kThreads, s, rs.flags, A, e, rs);
 }
@@ -1758,11 +1876,12 @@ void launch_check_avg_x(cudaStream_t s, int n, const double* x0, const double* x
 }
 void launch_spmv_check_rows(cudaStream_t s, const DevSell& A, const PdhgState* st, const SolveCtl* ctl, const double* xavg,
                             const double* y0, const double* y1, const double* ax0, const double* ax1, double* ysum,
-                            double* yavg, double* axavg, const double* b, const double* rsc, int neq, ReduceScratch rs) {
+                            double* yavg, double* axavg, const double* b, const double* rsc, int neq, ReduceScratch rs,
+                            double* axsum) {
   if (A.nblocks_body + A.nsegs == 0) return;
   CheckRowEpilogue e{};
   e.st = st; e.ctl = ctl; e.xavg = xavg; e.y0 = y0; e.y1 = y1; e.ax0 = ax0; e.ax1 = ax1; e.ysum = ysum; e.yavg = yavg;
-  e.axavg = axavg; e.b = b; e.rsc = rsc; e.neq = neq;
+  e.axavg = axavg; e.b = b; e.rsc = rsc; e.neq = neq; e.axsum = axsum;
   rs.terms = nullptr; rs.flags = 0;
   DevSell F = A;   // the check epilogues keep their sums in shared memory, which needs at most one row per thread
   F.nblocks_body = A.nblocks_full; F.pipelined = 0;
@@ -1771,11 +1890,11 @@ void launch_spmv_check_rows(cudaStream_t s, const DevSell& A, const PdhgState* s
 void launch_spmv_check_cols(cudaStream_t s, const DevSell& AT, const PdhgState* st, const SolveCtl* ctl, const double* yavg,
                             const double* x0, const double* x1, const double* aty0, const double* aty1, const double* xavg,
                             double* atyavg, const double* c, const double* lo, const double* up, const double* cs,
-                            ReduceScratch rs) {
+                            ReduceScratch rs, double* atysum) {
   if (AT.nblocks_body + AT.nsegs == 0) return;
   CheckColEpilogue e{};
   e.st = st; e.ctl = ctl; e.yavg = yavg; e.x0 = x0; e.x1 = x1; e.aty0 = aty0; e.aty1 = aty1; e.xavg = xavg;
-  e.atyavg = atyavg; e.c = c; e.lo = lo; e.up = up; e.cs = cs;
+  e.atyavg = atyavg; e.c = c; e.lo = lo; e.up = up; e.cs = cs; e.atysum = atysum;
   rs.terms = nullptr; rs.flags = 0;
   DevSell F = AT;
   F.nblocks_body = AT.nblocks_full; F.pipelined = 0;
@@ -1789,10 +1908,26 @@ int restart_sweep_grid(int n, int m) { return ew_grid(n > m ? n : m); }
 void launch_restart_sweep(cudaStream_t s, int n, int m, double* x0, double* x1, double* aty0, double* aty1,
                           const double* xavg, const double* atyavg, double* xsum, double* xlr, double* y0, double* y1,
                           double* ax0, double* ax1, const double* yavg, const double* axavg, double* ysum, double* ylr,
-                          const PdhgState* st, const SolveCtl* ctl, ReduceScratch rs) {
+                          const PdhgState* st, const SolveCtl* ctl, ReduceScratch rs, double* atysum, double* axsum) {
   rs.terms = nullptr; rs.flags = 0;
   restart_sweep_kernel<<<restart_sweep_grid(n, m), kThreads, 0, s>>>(n, m, x0, x1, aty0, aty1, xavg, atyavg, xsum, xlr, y0,
-                                                                    y1, ax0, ax1, yavg, axavg, ysum, ylr, st, ctl, rs);
+                                                                    y1, ax0, ax1, yavg, axavg, ysum, ylr, st, ctl, rs, atysum,
+                                                                    axsum);
+}
+int check_light_grid(int len) { return ew_grid(len); }
+void launch_check_light_cols(cudaStream_t s, int n, const double* x0, const double* x1, const double* aty0, const double* aty1,
+                             double* xsum, double* atysum, double* xavg, double* atyavg, const double* c, const double* lo,
+                             const double* up, const double* cs, const PdhgState* st, const SolveCtl* ctl, ReduceScratch rs) {
+  rs.terms = nullptr; rs.flags = 0;
+  check_light_cols_kernel<<<check_light_grid(n), kThreads, 0, s>>>(n, x0, x1, aty0, aty1, xsum, atysum, xavg, atyavg, c, lo, up,
+                                                                   cs, st, ctl, rs);
+}
+void launch_check_light_rows(cudaStream_t s, int m, int neq, const double* y0, const double* y1, const double* ax0,
+                             const double* ax1, double* ysum, double* axsum, double* yavg, double* axavg, const double* b,
+                             const double* rsc, const PdhgState* st, const SolveCtl* ctl, ReduceScratch rs) {
+  rs.terms = nullptr; rs.flags = 0;
+  check_light_rows_kernel<<<check_light_grid(m), kThreads, 0, s>>>(m, neq, y0, y1, ax0, ax1, ysum, axsum, yavg, axavg, b, rsc,
+                                                                   st, ctl, rs);
 }
 void launch_check_finish(cudaStream_t s, PdhgState* st, SolveCtl* ctl, const double* prst, int nbs, const double* sums2) {
   check_finish_kernel<<<1, kFinishThreads, 0, s>>>(st, ctl, prst, nbs, sums2);

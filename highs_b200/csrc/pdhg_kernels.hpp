@@ -13,9 +13,10 @@ void launch_primal_step(cudaStream_t s, int n, PdhgState* st, double* x0, double
 void launch_spmv_plain(cudaStream_t s, const DevSell& A, const double* in, double* out, const PdhgState* due = nullptr);
 void launch_spmv_dual(cudaStream_t s, const DevSell& A, PdhgState* st, const double* x0, const double* x1,
                       double* y0, double* y1, double* ax0, double* ax1, const double* b, double* ysum,
-                      int neq, int row_offset, ReduceScratch rs);
+                      int neq, int row_offset, ReduceScratch rs, double* axsum = nullptr);
 void launch_spmv_primal(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
-                        const double* x0, const double* x1, double* aty0, double* aty1, ReduceScratch rs);
+                        const double* x0, const double* x1, double* aty0, double* aty1, ReduceScratch rs,
+                        double* atysum = nullptr);
 void launch_spmv_partial_aty(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
                              double* part, const int* outpos, const PdhgState* due = nullptr);
 void launch_spmv_dual_mg(cudaStream_t s, const DevSell& A, PdhgState* st, const double* xfull, double* y0, double* y1,
@@ -76,18 +77,28 @@ void launch_check_avg_x(cudaStream_t s, int n, const double* x0, const double* x
                         const PdhgState* st, const SolveCtl* ctl);
 void launch_spmv_check_rows(cudaStream_t s, const DevSell& A, const PdhgState* st, const SolveCtl* ctl, const double* xavg,
                             const double* y0, const double* y1, const double* ax0, const double* ax1, double* ysum,
-                            double* yavg, double* axavg, const double* b, const double* rsc, int neq, ReduceScratch rs);
+                            double* yavg, double* axavg, const double* b, const double* rsc, int neq, ReduceScratch rs,
+                            double* axsum = nullptr);
 void launch_spmv_check_cols(cudaStream_t s, const DevSell& AT, const PdhgState* st, const SolveCtl* ctl, const double* yavg,
                             const double* x0, const double* x1, const double* aty0, const double* aty1, const double* xavg,
                             double* atyavg, const double* c, const double* lo, const double* up, const double* cs,
-                            ReduceScratch rs);
+                            ReduceScratch rs, double* atysum = nullptr);
 void launch_check_decide(cudaStream_t s, PdhgState* st, SolveCtl* ctl, const double* prow, int nbr, const double* pcol,
                          int nbc, unsigned* ticket /* zero-initialised, self-resetting */);
 int restart_sweep_grid(int n, int m);
 void launch_restart_sweep(cudaStream_t s, int n, int m, double* x0, double* x1, double* aty0, double* aty1,
                           const double* xavg, const double* atyavg, double* xsum, double* xlr, double* y0, double* y1,
                           double* ax0, double* ax1, const double* yavg, const double* axavg, double* ysum, double* ylr,
-                          const PdhgState* st, const SolveCtl* ctl, ReduceScratch rs);
+                          const PdhgState* st, const SolveCtl* ctl, ReduceScratch rs, double* atysum = nullptr,
+                          double* axsum = nullptr);
+// light check (dense-check phase): two vector sweeps in place of C1-C3, same partial-sum layout ([20][grid], [8][grid])
+int check_light_grid(int len);
+void launch_check_light_cols(cudaStream_t s, int n, const double* x0, const double* x1, const double* aty0, const double* aty1,
+                             double* xsum, double* atysum, double* xavg, double* atyavg, const double* c, const double* lo,
+                             const double* up, const double* cs, const PdhgState* st, const SolveCtl* ctl, ReduceScratch rs);
+void launch_check_light_rows(cudaStream_t s, int m, int neq, const double* y0, const double* y1, const double* ax0,
+                             const double* ax1, double* ysum, double* axsum, double* yavg, double* axavg, const double* b,
+                             const double* rsc, const PdhgState* st, const SolveCtl* ctl, ReduceScratch rs);
 void launch_check_finish(cudaStream_t s, PdhgState* st, SolveCtl* ctl, const double* prst, int nbs, const double* sums2 = nullptr);
 // several GPUs (fused peer-memory path): row side with ybar already formed, partial sums -> scalars, decision from all-reduced sums
 void launch_spmv_check_rows_mg(cudaStream_t s, const DevSell& A, const PdhgState* st, const SolveCtl* ctl, const double* xfull,

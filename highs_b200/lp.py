@@ -98,12 +98,20 @@ def synthetic_lp(m: int, n: int, nnz_per_col: int, seed: int = 12345, dense_col_
     U(0,1); c = A'y* + z with z_j = 0 where x*_j > 0 else U(0,1).  Every row is a
     GEQ row, so the cuPDLP standard form adds no slack columns and keeps (m, n).
     `dense_col_nnz` > 0 replaces column 0 by that many distinct random rows (the
-    "pathological" configuration S5).  `band` > 0: banded structure instead of uniformly random rows.
+    "pathological" configuration S5).  `band` > 0: banded structure instead of uniformly random rows; `band` < 0: the same
+    |band|-bounded offsets in every column (multi-diagonal).
     numpy's PCG64 replaces the survey's mt19937_64: the generator defines the
     workload, it is not part of the parity contract.
     """
     rng = np.random.default_rng(seed)
-    if band > 0:
+    if band < 0:
+        # multi-diagonal variant (bench workload S3D): the same `nnz_per_col` offsets (drawn once from [band, -band]) for every
+        # column, like a stencil / staircase LP -- consecutive rows hold consecutive columns, so a warp's 32 gathers fall into
+        # a few sectors.  This is the upper end of what sector sharing can give the SpMV kernels.
+        offs = rng.integers(band, -band + 1, size=nnz_per_col, dtype=np.int64)
+        centre = (np.arange(n, dtype=np.int64) * m) // max(n, 1)
+        rows = (centre[:, None] + offs[None, :]) % m
+    elif band > 0:
         # structured variant (bench workload S3B): column j's rows lie within `band` of the diagonal position j m / n,
         # like the staircase / block-angular matrices of real LPs -- neighbouring rows and columns share vector entries
         centre = (np.arange(n, dtype=np.int64) * m) // max(n, 1)

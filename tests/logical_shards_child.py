@@ -44,20 +44,35 @@ def main():
                one_gpu_iters=one["iters"], one_gpu_obj=lp.objectiveValue(one["col_value"]),
                iters=[r["iters"] for r in res], term=[r["term_code"] for r in res],
                obj=[lp.objectiveValue(r["col_value"]) for r in res])
-    ok = True
-    for r in res[1:]:   # every rank takes the same decisions and returns the same (complete) solution
+    fails = []
+    for g, r in enumerate(res[1:], start=1):   # every rank takes the same decisions and returns the same (complete) solution
         for k in ("col_value", "col_dual", "row_value", "row_dual"):
-            ok &= bool(np.array_equal(r[k], res[0][k]))
-        ok &= r["iters"] == res[0]["iters"] and r["term_code"] == res[0]["term_code"]
-    out["ranks_identical"] = ok
+            if not np.array_equal(r[k], res[0][k]):
+                bad = np.flatnonzero(r[k] != res[0][k])
+                fails.append(f"rank {g} {k}: {bad.size} of {r[k].size} entries differ from rank 0 (first at {int(bad[0])}, last at {int(bad[-1])})")
+        if not (r["iters"] == res[0]["iters"] and r["term_code"] == res[0]["term_code"]):
+            fails.append(f"rank {g}: iters/term {r['iters']}/{r['term_code']} vs rank 0 {res[0]['iters']}/{res[0]['term_code']}")
+    out["ranks_identical"] = not fails
     r0 = res[0]
-    ok &= r0["term_code"] == ref["term_code"] == 0
+    if not (r0["term_code"] == ref["term_code"] == 0):
+        fails.append(f"term {r0['term_code']} vs oracle {ref['term_code']}")
     # both runs stop at relative gap < tol: they bracket the optimum to ~tol (1 + |p| + |d|) each
-    ok &= abs(out["obj"][0] - o_ref) <= 3 * tol * (1 + 2 * abs(o_ref))
-    ok &= abs(r0["iters"] - ref["iters"]) <= 0.35 * ref["iters"] + 80
+    if not abs(out["obj"][0] - o_ref) <= 3 * tol * (1 + 2 * abs(o_ref)):
+        fails.append(f"objective {out['obj'][0]} vs oracle {o_ref}")
+    if not abs(r0["iters"] - ref["iters"]) <= 0.35 * ref["iters"] + 80:
+        fails.append(f"iterations {r0['iters']} vs oracle {ref['iters']}")
     # the assembled solution in the ORIGINAL space: row_value must be A x
     A = lp.a_matrix_.to_scipy()
-    ok &= bool(np.allclose(A @ r0["col_value"], r0["row_value"], rtol=1e-8, atol=1e-7 * (1 + np.abs(r0["row_value"]).max())))
+    ax = A @ r0["col_value"]
+    err = float(np.abs(ax - r0["row_value"]).max())
+    out["row_value_err"] = err
+    if not np.allclose(ax, r0["row_value"], rtol=1e-8, atol=1e-7 * (1 + np.abs(r0["row_value"]).max())):
+        bad = np.flatnonzero(np.abs(ax - r0["row_value"]) > 1e-7 * (1 + np.abs(r0["row_value"]).max()) + 1e-8 * np.abs(r0["row_value"]))
+        fails.append(f"row_value != A col_value: max err {err}, {bad.size} rows (first {int(bad[0])}, last {int(bad[-1])})")
+    out["restarts"] = [r.get("restarts") for r in res]
+    out["term_iterate"] = [r.get("term_iterate") for r in res]
+    out["fails"] = fails
+    ok = not fails
     out["ok"] = bool(ok)
     print(json.dumps(out))
     return 0 if ok else 1

@@ -14,6 +14,7 @@ ki, mi, vi = H.index("Kernel Name"), H.index("Metric Name"), H.index("Metric Val
 ui = H.index("Metric Unit")
 tot = collections.OrderedDict()
 cnt = collections.Counter()
+allv = {}
 for r in rows[hdr + 1:]:
     if r[mi] != "gpu__time_duration.sum":
         continue
@@ -25,13 +26,17 @@ for r in rows[hdr + 1:]:
     name = r[ki].split("(")[0].replace("void b200::", "").replace("b200::", "")
     tot[name] = tot.get(name, 0.0) + v
     cnt[name] += 1
+    allv.setdefault(name, []).append(v)
 total = sum(tot.values())
 out = [f"# {tag}: ncu launch list (gpu__time_duration.sum, --clock-control none)", "",
-       f"source: `{launches}`; command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 800 -c 500 python bench.py --steps 200 --warmup 40`",
-       "Per-launch times under ncu are cold-cache and serialised: read the SHARE column, not the absolute.", "",
-       "| kernel | launches | total us | avg us | share |", "|---|---:|---:|---:|---:|"]
+       f"source: `{launches}`; command: see the session script named in the tag's bench notes (`ncu --metrics gpu__time_duration.sum --clock-control none ... python bench.py ...`)",
+       "Per-launch times under ncu are cold-cache and serialised: read the SHARE column, not the absolute.",
+       "`working` = launches that did their work (longer than a third of the kernel's longest launch): a graph replay carries spare",
+       "passes and speculative checks whose kernels return at once when they are not due, which drags the plain average down.", "",
+       "| kernel | launches | total us | avg us | working launches | avg us of those | share |", "|---|---:|---:|---:|---:|---:|---:|"]
 for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
-    out.append(f"| `{k}` | {cnt[k]} | {v:.1f} | {v / cnt[k]:.2f} | {100 * v / total:.1f}% |")
+    w = [x for x in allv[k] if x > max(allv[k]) / 3.0]
+    out.append(f"| `{k}` | {cnt[k]} | {v:.1f} | {v / cnt[k]:.2f} | {len(w)} | {sum(w) / len(w):.2f} | {100 * v / total:.1f}% |")
 open(f"profiles/{tag}_launches.md", "w").write("\n".join(out) + "\n")
 
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
