@@ -122,12 +122,17 @@ class ClockSampler:
 
 def ncu_traffic_bytes(kernel_tag):
     """dram read + write per launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r01_ncu_summary.md, S3 workload); None if the summary is missing"""
+    (profiles/r02_ncu_summary.md, else round 1's; S3 workload); None if the summary is missing"""
     import re
-    path = os.path.join(ROOT, "profiles", "r01_ncu_summary.md")
-    try:
-        txt = open(path).read()
-    except OSError:
+    txt = None
+    for name in ("r02_ncu_summary.md", "r01_ncu_summary.md"):
+        try:
+            txt = open(os.path.join(ROOT, "profiles", name)).read()
+            ncu_traffic_bytes.source = f"profiles/{name} (ncu --set full, same kernel, S3)"
+            break
+        except OSError:
+            continue
+    if txt is None:
         return None
     for sec in txt.split("\n## ")[1:]:
         if kernel_tag in sec.splitlines()[0]:
@@ -438,7 +443,7 @@ def main():
         ach = dom_bytes / (k_us[dom] * 1e-6) / 1e9
         traffic = ncu_traffic_bytes("DualEpilogue" if dom == 1 else "PrimalEpilogue") if args.workload == "S3" else None
         roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                    "traffic_source": "profiles/r01_ncu_summary.md (ncu --set full, same kernel, S3)" if traffic else None,
+                    "traffic_source": getattr(ncu_traffic_bytes, "source", None) if traffic else None,
                     "kernel": dom_name.replace("spmv_blocked", "spmv_sell_kernel"), "algorithmic_bytes_per_launch": dom_bytes, "us_per_launch": k_us[dom],
                     "peak_source": peak_src,
                     "per_kernel_us": {"K1_primal_step": k_us[0], "K2_Ax_dual": k_us[1], "K3_ATy_interaction": k_us[2]},

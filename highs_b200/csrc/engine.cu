@@ -282,6 +282,7 @@ struct b200pdlp_problem {
   DevBuf<double> trace_dev;
   cudaGraphExec_t graph_pow2[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // 1 << k passes
   cudaGraphExec_t graph_check = nullptr;
+  bool fused_check = false;                       // B200PDLP_FUSED_CHECK=1: residual sums in the SpMV epilogues (C2/C3) instead of the split check
   cudaGraphExec_t graph_check_light = nullptr;   // the dense-check phase's check: two sweeps instead of two SpMV (see kDenseChecks)
   DevBuf<double> axsum, atysum;                   // A xSum (ml), A'ySum (n): carried by the passes while iter < kDenseChecks
   long long launches = 0;
@@ -1253,12 +1254,23 @@ static void enqueue_check_device(b200pdlp_problem* p, bool light = false) {
   const int n = p->n, ml = p->ml;
   const ReduceScratch rrow = p->rs(kSlotChk, ml), rcol = p->rs(kSlotK3, n), rrst = p->rs(kSlotK1, n);
   if (light) {
-    launch_check_light_cols(s, n, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->xsum.p, p->atysum.p, p->xavg.p,
+    launch_check_cols_sweep(s, false, n, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->xsum.p, p->atysum.p, p->xavg.p,
                             p->atyavg.p, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, st, ctl, rcol);
-    launch_check_light_rows(s, ml, p->neq_local, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->ysum.p, p->axsum.p,
+    launch_check_rows_sweep(s, false, ml, p->neq_local, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->ysum.p, p->axsum.p,
+                            p->yavg.p, p->axavg.p, p->rhs.p, p->rowscale.p, st, ctl, rrow);
+    launch_check_decide(s, st, ctl, rrow.partials, check_light_grid(ml), rcol.partials, check_light_grid(n), rrow.counter);
+  } else if (!p->fused_check) {
+    // split check: averages, two plain SpMV (as fast as the pass kernels), two vector sweeps for the 20 + 8 sums
+    launch_check_avg_xy(s, n, ml, p->x[0].p, p->x[1].p, p->xsum.p, p->xavg.p, p->y[0].p, p->y[1].p, p->ysum.p, p->yavg.p, st, ctl);
+    launch_spmv_plain(s, p->A.dev, p->xavg.p, p->axavg.p, st);
+    launch_spmv_plain(s, p->AT.dev, p->yavg.p, p->atyavg.p, st);
+    launch_check_cols_sweep(s, true, n, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->xsum.p, p->atysum.p, p->xavg.p,
+                            p->atyavg.p, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, st, ctl, rcol);
+    launch_check_rows_sweep(s, true, ml, p->neq_local, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->ysum.p, p->axsum.p,
                             p->yavg.p, p->axavg.p, p->rhs.p, p->rowscale.p, st, ctl, rrow);
     launch_check_decide(s, st, ctl, rrow.partials, check_light_grid(ml), rcol.partials, check_light_grid(n), rrow.counter);
   } else {
+    // B200PDLP_FUSED_CHECK=1: the sums in the epilogues of the two averaging SpMV (three launches instead of five)
     launch_check_avg_x(s, n, p->x[0].p, p->x[1].p, p->xsum.p, p->xavg.p, st, ctl);
     launch_spmv_check_rows(s, p->A.dev, st, ctl, p->xavg.p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->ysum.p,
                            p->yavg.p, p->axavg.p, p->rhs.p, p->rowscale.p, p->neq_local, rrow, p->axsum.p);
@@ -1271,10 +1283,10 @@ static void enqueue_check_device(b200pdlp_problem* p, bool light = false) {
                        st, ctl, rrst, p->atysum.p, p->axsum.p);
   launch_check_finish(s, st, ctl, rrst.partials, restart_sweep_grid(n, ml));
 }
-static constexpr int kCheckLaunches = 6;
+static constexpr int kCheckLaunches = 6;   // fused variant; split: 8, light: 5
 
 static void launch_check_graph(b200pdlp_problem* p, bool light = false) {
-  const int nl = p->world > 1 ? 16 : (light ? kCheckLaunches - 1 : kCheckLaunches);
+  const int nl = p->world > 1 ? 16 : (light ? 5 : (p->fused_check ? 6 : 8));
   if (p->no_graph) { enqueue_check_device(p, light); p->launches += nl; return; }
   cudaGraphExec_t& ge = light ? p->graph_check_light : p->graph_check;
   if (!ge) {
@@ -1529,6 +1541,12 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
     c->term = -1;
     // dense-check phase (iterations 0 .. kDenseChecks-1 are all check iterations): the passes carry A xSum and A'ySum, the
     // checks are two vector sweeps.  B200PDLP_LIGHT_CHECK=0: every check multiplies the average iterate by A and A'.
+    {
+      const char* e = getenv("B200PDLP_FUSED_CHECK");
+      const bool fused = e && atoi(e) != 0;
+      if (fused != p->fused_check && p->graph_check) { cudaGraphExecDestroy(p->graph_check); p->graph_check = nullptr; }
+      p->fused_check = fused;
+    }
     h_light = p->world == 1 && p->axsum.p && p->atysum.p;
     if (const char* e = getenv("B200PDLP_LIGHT_CHECK")) if (atoi(e) == 0) h_light = false;
     h->light_on = h_light ? 1 : 0;

@@ -1303,33 +1303,50 @@ struct CheckColEpilogue {
   }
 };
 
-// ---- light check (dense-check phase, PdhgState::light_on && iter < kDenseChecks): A xbar = (A xSum) / sum(w) and
-// A'ybar = (A'ySum) / sum(w) come from the sums the passes carried, so C1-C3 become two vector sweeps with the same
-// per-element terms (col_terms / row_terms) and the same downstream kernels (C4-C6).
+// ---- the residual sweeps of a check as plain vector kernels (one GPU).  Two uses:
+//  * SPLIT check (GIVEN = true; the default from iteration kDenseChecks on): C1 forms xbar AND ybar, two PLAIN SpMV give
+//    A xbar and A'ybar at the speed of the pass kernels, and these sweeps add the 20 + 8 terms.  The fused epilogues
+//    (CheckRowEpilogue / CheckColEpilogue: 67 + 108 us at S3, the 20 accumulators cost the column kernel its occupancy)
+//    are replaced by 42 + 42 us of SpMV and 11 + 8 us of sweeps.
+//  * LIGHT check (GIVEN = false; dense-check phase, PdhgState::light_on && iter < kDenseChecks): A xbar = (A xSum) / sum(w)
+//    and A'ybar = (A'ySum) / sum(w) come from the sums the passes carried: no SpMV at all.
+// Same per-element terms (col_terms / row_terms) and the same downstream kernels (C4-C6) in both.
+template <bool GIVEN>
 __global__ void __launch_bounds__(kThreads)
-check_light_cols_kernel(int n, const double* __restrict__ x0, const double* __restrict__ x1, const double* __restrict__ aty0,
+check_cols_sweep_kernel(int n, const double* __restrict__ x0, const double* __restrict__ x1, const double* __restrict__ aty0,
                         const double* __restrict__ aty1, double* __restrict__ xsum, double* __restrict__ atysum,
                         double* __restrict__ xavg, double* __restrict__ atyavg, const double* __restrict__ c,
                         const double* __restrict__ lo, const double* __restrict__ up, const double* __restrict__ cs,
                         const PdhgState* __restrict__ st, const SolveCtl* __restrict__ ctl, ReduceScratch rs) {
-  if (!check_live(st, ctl) || !st->light_on || st->iter >= kDenseChecks) return;
+  if (!check_live(st, ctl)) return;
+  const bool dense = st->light_on && st->iter < kDenseChecks;
+  if (!GIVEN && !dense) return;
   const int cur = st->cur;
   const double* __restrict__ x = cur ? x1 : x0;
   const double* __restrict__ aty = cur ? aty1 : aty0;
   const bool pending = st->pending != 0;
   const double w = st->w_pending;
   const double scale = st->sum_step > 0.0 ? 1.0 / st->sum_step : 1.0;
+  const bool flush2 = GIVEN && dense && pending && atysum != nullptr;   // keep A'ySum in step with xSum's flush (done by C1)
   double acc[20];
 #pragma unroll
   for (int a = 0; a < 20; a++) acc[a] = 0.0;
   const int stride = gridDim.x * kThreads;
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
     const double xc = x[i], ac = aty[i];
-    double xs = xsum[i], as = atysum[i];
-    if (pending) { xs = xs + w * xc; xsum[i] = xs; as = as + w * ac; atysum[i] = as; }
-    const double xa = xs * scale, aa = as * scale;
-    xavg[i] = xa;
-    atyavg[i] = aa;
+    double xa, aa;
+    if (GIVEN) {
+      xa = xavg[i];
+      aa = atyavg[i];
+      if (flush2) atysum[i] = atysum[i] + w * ac;
+    } else {
+      double xs = xsum[i], as = atysum[i];
+      if (pending) { xs = xs + w * xc; xsum[i] = xs; as = as + w * ac; atysum[i] = as; }
+      xa = xs * scale;
+      aa = as * scale;
+      xavg[i] = xa;
+      atyavg[i] = aa;
+    }
     const double ci = c[i], l = lo[i], u = up[i], sc = cs[i];
     double t[20];
     col_terms(xc, ac, ci, l, u, sc, t);
@@ -1340,30 +1357,42 @@ check_light_cols_kernel(int n, const double* __restrict__ x0, const double* __re
   block_partials<20>(acc, rs);
 }
 
+template <bool GIVEN>
 __global__ void __launch_bounds__(kThreads)
-check_light_rows_kernel(int m, int neq, const double* __restrict__ y0, const double* __restrict__ y1,
+check_rows_sweep_kernel(int m, int neq, const double* __restrict__ y0, const double* __restrict__ y1,
                         const double* __restrict__ ax0, const double* __restrict__ ax1, double* __restrict__ ysum,
                         double* __restrict__ axsum, double* __restrict__ yavg, double* __restrict__ axavg,
                         const double* __restrict__ b, const double* __restrict__ rsc, const PdhgState* __restrict__ st,
                         const SolveCtl* __restrict__ ctl, ReduceScratch rs) {
-  if (!check_live(st, ctl) || !st->light_on || st->iter >= kDenseChecks) return;
+  if (!check_live(st, ctl)) return;
+  const bool dense = st->light_on && st->iter < kDenseChecks;
+  if (!GIVEN && !dense) return;
   const int cur = st->cur;
   const double* __restrict__ y = cur ? y1 : y0;
   const double* __restrict__ ax = cur ? ax1 : ax0;
   const bool pending = st->pending != 0;
   const double w = st->w_pending;
   const double scale = st->sum_step > 0.0 ? 1.0 / st->sum_step : 1.0;
+  const bool flush2 = GIVEN && dense && pending && axsum != nullptr;
   double acc[8];
 #pragma unroll
   for (int a = 0; a < 8; a++) acc[a] = 0.0;
   const int stride = gridDim.x * kThreads;
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < m; i += stride) {
     const double yc = y[i], ac = ax[i];
-    double ys = ysum[i], as = axsum[i];
-    if (pending) { ys = ys + w * yc; ysum[i] = ys; as = as + w * ac; axsum[i] = as; }
-    const double ya = ys * scale, aa = as * scale;
-    yavg[i] = ya;
-    axavg[i] = aa;
+    double ya, aa;
+    if (GIVEN) {
+      ya = yavg[i];
+      aa = axavg[i];
+      if (flush2) axsum[i] = axsum[i] + w * ac;
+    } else {
+      double ys = ysum[i], as = axsum[i];
+      if (pending) { ys = ys + w * yc; ysum[i] = ys; as = as + w * ac; axsum[i] = as; }
+      ya = ys * scale;
+      aa = as * scale;
+      yavg[i] = ya;
+      axavg[i] = aa;
+    }
     const double bi = b[i], sc = rsc[i];
     const bool ineq = i >= neq;
     double t[8];
@@ -1373,6 +1402,31 @@ check_light_rows_kernel(int m, int neq, const double* __restrict__ y0, const dou
     for (int a = 0; a < 8; a++) acc[a] += t[a];
   }
   block_partials<8>(acc, rs);
+}
+
+// C1 of the split check: xbar and ybar in one launch (flushes the pending weight into xSum and ySum)
+__global__ void __launch_bounds__(kThreads)
+check_avg_xy_kernel(int n, int m, const double* __restrict__ x0, const double* __restrict__ x1, double* __restrict__ xsum,
+                    double* __restrict__ xavg, const double* __restrict__ y0, const double* __restrict__ y1,
+                    double* __restrict__ ysum, double* __restrict__ yavg, const PdhgState* __restrict__ st,
+                    const SolveCtl* __restrict__ ctl) {
+  if (!check_live(st, ctl)) return;
+  const double* __restrict__ x = st->cur ? x1 : x0;
+  const double* __restrict__ y = st->cur ? y1 : y0;
+  const bool pending = st->pending != 0;
+  const double w = st->w_pending;
+  const double scale = st->sum_step > 0.0 ? 1.0 / st->sum_step : 1.0;
+  const int stride = gridDim.x * kThreads;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    double s = xsum[i];
+    if (pending) { s = s + w * x[i]; xsum[i] = s; }
+    xavg[i] = s * scale;
+  }
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < m; i += stride) {
+    double s = ysum[i];
+    if (pending) { s = s + w * y[i]; ysum[i] = s; }
+    yavg[i] = s * scale;
+  }
 }
 
 // PDHG_Check_Restart_GPU (cupdlp_restart.c:3-99): 0 none, 1 to the average, 2 to the current iterate
@@ -1915,19 +1969,25 @@ void launch_restart_sweep(cudaStream_t s, int n, int m, double* x0, double* x1, 
                                                                     axsum);
 }
 int check_light_grid(int len) { return ew_grid(len); }
-void launch_check_light_cols(cudaStream_t s, int n, const double* x0, const double* x1, const double* aty0, const double* aty1,
-                             double* xsum, double* atysum, double* xavg, double* atyavg, const double* c, const double* lo,
-                             const double* up, const double* cs, const PdhgState* st, const SolveCtl* ctl, ReduceScratch rs) {
+void launch_check_cols_sweep(cudaStream_t s, bool given, int n, const double* x0, const double* x1, const double* aty0,
+                             const double* aty1, double* xsum, double* atysum, double* xavg, double* atyavg, const double* c,
+                             const double* lo, const double* up, const double* cs, const PdhgState* st, const SolveCtl* ctl,
+                             ReduceScratch rs) {
   rs.terms = nullptr; rs.flags = 0;
-  check_light_cols_kernel<<<check_light_grid(n), kThreads, 0, s>>>(n, x0, x1, aty0, aty1, xsum, atysum, xavg, atyavg, c, lo, up,
-                                                                   cs, st, ctl, rs);
+  if (given) check_cols_sweep_kernel<true><<<check_light_grid(n), kThreads, 0, s>>>(n, x0, x1, aty0, aty1, xsum, atysum, xavg, atyavg, c, lo, up, cs, st, ctl, rs);
+  else check_cols_sweep_kernel<false><<<check_light_grid(n), kThreads, 0, s>>>(n, x0, x1, aty0, aty1, xsum, atysum, xavg, atyavg, c, lo, up, cs, st, ctl, rs);
 }
-void launch_check_light_rows(cudaStream_t s, int m, int neq, const double* y0, const double* y1, const double* ax0,
+void launch_check_rows_sweep(cudaStream_t s, bool given, int m, int neq, const double* y0, const double* y1, const double* ax0,
                              const double* ax1, double* ysum, double* axsum, double* yavg, double* axavg, const double* b,
                              const double* rsc, const PdhgState* st, const SolveCtl* ctl, ReduceScratch rs) {
   rs.terms = nullptr; rs.flags = 0;
-  check_light_rows_kernel<<<check_light_grid(m), kThreads, 0, s>>>(m, neq, y0, y1, ax0, ax1, ysum, axsum, yavg, axavg, b, rsc,
-                                                                   st, ctl, rs);
+  if (given) check_rows_sweep_kernel<true><<<check_light_grid(m), kThreads, 0, s>>>(m, neq, y0, y1, ax0, ax1, ysum, axsum, yavg, axavg, b, rsc, st, ctl, rs);
+  else check_rows_sweep_kernel<false><<<check_light_grid(m), kThreads, 0, s>>>(m, neq, y0, y1, ax0, ax1, ysum, axsum, yavg, axavg, b, rsc, st, ctl, rs);
+}
+void launch_check_avg_xy(cudaStream_t s, int n, int m, const double* x0, const double* x1, double* xsum, double* xavg,
+                         const double* y0, const double* y1, double* ysum, double* yavg, const PdhgState* st, const SolveCtl* ctl) {
+  const int len = n > m ? n : m;
+  if (len > 0) check_avg_xy_kernel<<<ew_grid(len), kThreads, 0, s>>>(n, m, x0, x1, xsum, xavg, y0, y1, ysum, yavg, st, ctl);
 }
 void launch_check_finish(cudaStream_t s, PdhgState* st, SolveCtl* ctl, const double* prst, int nbs, const double* sums2) {
   check_finish_kernel<<<1, kFinishThreads, 0, s>>>(st, ctl, prst, nbs, sums2);

@@ -91,14 +91,19 @@ void launch_restart_sweep(cudaStream_t s, int n, int m, double* x0, double* x1, 
                           double* ax0, double* ax1, const double* yavg, const double* axavg, double* ysum, double* ylr,
                           const PdhgState* st, const SolveCtl* ctl, ReduceScratch rs, double* atysum = nullptr,
                           double* axsum = nullptr);
-// light check (dense-check phase): two vector sweeps in place of C1-C3, same partial-sum layout ([20][grid], [8][grid])
+// the residual sweeps as plain vector kernels: given = true (split check: xbar/ybar from launch_check_avg_xy, A xbar / A'ybar
+// from two plain SpMV) or false (light check of the dense-check phase: from the carried A xSum / A'ySum); partial-sum layout
+// [20][check_light_grid(n)], [8][check_light_grid(m)]
 int check_light_grid(int len);
-void launch_check_light_cols(cudaStream_t s, int n, const double* x0, const double* x1, const double* aty0, const double* aty1,
-                             double* xsum, double* atysum, double* xavg, double* atyavg, const double* c, const double* lo,
-                             const double* up, const double* cs, const PdhgState* st, const SolveCtl* ctl, ReduceScratch rs);
-void launch_check_light_rows(cudaStream_t s, int m, int neq, const double* y0, const double* y1, const double* ax0,
+void launch_check_cols_sweep(cudaStream_t s, bool given, int n, const double* x0, const double* x1, const double* aty0,
+                             const double* aty1, double* xsum, double* atysum, double* xavg, double* atyavg, const double* c,
+                             const double* lo, const double* up, const double* cs, const PdhgState* st, const SolveCtl* ctl,
+                             ReduceScratch rs);
+void launch_check_rows_sweep(cudaStream_t s, bool given, int m, int neq, const double* y0, const double* y1, const double* ax0,
                              const double* ax1, double* ysum, double* axsum, double* yavg, double* axavg, const double* b,
                              const double* rsc, const PdhgState* st, const SolveCtl* ctl, ReduceScratch rs);
+void launch_check_avg_xy(cudaStream_t s, int n, int m, const double* x0, const double* x1, double* xsum, double* xavg,
+                         const double* y0, const double* y1, double* ysum, double* yavg, const PdhgState* st, const SolveCtl* ctl);
 void launch_check_finish(cudaStream_t s, PdhgState* st, SolveCtl* ctl, const double* prst, int nbs, const double* sums2 = nullptr);
 // several GPUs (fused peer-memory path): row side with ybar already formed, partial sums -> scalars, decision from all-reduced sums
 void launch_spmv_check_rows_mg(cudaStream_t s, const DevSell& A, const PdhgState* st, const SolveCtl* ctl, const double* xfull,

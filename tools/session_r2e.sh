@@ -13,7 +13,10 @@ B200PDLP_MG_DEVICE_CHECK=1 T=300 run shards4_dense_dev python tests/logical_shar
 B200PDLP_MG_DEVICE_CHECK=1 T=300 run shards2_dense_dev python tests/logical_shards_child.py 2 dense threads
 run bench_s20 python bench.py --no-cpu-baseline --steps 20 --warmup 5
 B200PDLP_LIGHT_CHECK=0 run bench_s20_nolight python bench.py --no-cpu-baseline --steps 20 --warmup 5
+B200PDLP_LIGHT_CHECK=0 B200PDLP_FUSED_CHECK=1 run bench_s20_fused python bench.py --no-cpu-baseline --steps 20 --warmup 5
 run bench_default python bench.py --no-cpu-baseline --parity
+B200PDLP_FUSED_CHECK=1 run bench_default_fused python bench.py --no-cpu-baseline
+run s2_spread python tools/s2_gpu_spread.py 1e-4 1e-6
 for k in 3 4 6; do B200PDLP_SPMV_A_CTAS_PER_SM=$k run bench_a$k python bench.py --no-cpu-baseline; done
 run bench_s3d python bench.py --workload S3D --no-cpu-baseline
 B200PDLP_SPMV_A_CTAS_PER_SM=4 run bench_s3d_a4 python bench.py --workload S3D --no-cpu-baseline
