@@ -282,6 +282,7 @@ struct b200pdlp_problem {
   DevBuf<double> trace_dev;
   cudaGraphExec_t graph_pow2[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // 1 << k passes
   cudaGraphExec_t graph_check = nullptr;
+  int check_launches[2] = {0, 0};                 // kernels in graph_check / graph_check_light
   bool fused_check = false;                       // B200PDLP_FUSED_CHECK=1: residual sums in the SpMV epilogues (C2/C3) instead of the split check
   cudaGraphExec_t graph_check_light = nullptr;   // the dense-check phase's check: two sweeps instead of two SpMV (see kDenseChecks)
   DevBuf<double> axsum, atysum;                   // A xSum (ml), A'ySum (n): carried by the passes while iter < kDenseChecks
@@ -577,7 +578,7 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   for (int k = 0; k < 2; k++) { p->x[k].alloc(nl); p->aty[k].alloc(nl); p->y[k].alloc(ml); p->ax[k].alloc(ml); }
   p->xsum.alloc(nl); p->xavg.alloc(nl); p->atyavg.alloc(nl); p->xlr.alloc(nl);
   p->ysum.alloc(ml); p->yavg.alloc(ml); p->axavg.alloc(ml); p->ylr.alloc(ml);
-  if (world == 1 && !p->ordered) { p->axsum.alloc(ml); p->atysum.alloc(nl); }
+  if (!p->ordered) { p->axsum.alloc(ml); p->atysum.alloc(nl); }
   if (world > 1) {
     p->xfull.alloc((size_t)world * p->seg_len); p->part.alloc((size_t)world * p->seg_len);
     p->recv.alloc((size_t)world * p->seg_len);
@@ -772,11 +773,11 @@ static void enqueue_pass_mg(b200pdlp_problem* p) {
   if (p->p2p) {
     // fused compute + collective over NVLink peer memory (5 launches, no NCCL)
     launch_primal_shard_p2p(s, p->nl, st, p->x[0].p, p->x[1].p, p->aty[0].p, p->peers, p->world, p->rank, p->seg_len,
-                            p->p2p_pull, p->cost.p, p->lower.p, p->upper.p, p->xsum.p, r1);
+                            p->p2p_pull, p->cost.p, p->lower.p, p->upper.p, p->xsum.p, r1, p->atysum.p);
     launch_p2p_barrier(s, 0, st, r1.partials, primal_shard_p2p_grid(p->nl), p->peers, p->world, p->rank, p->seg_len,
                        p->shard_len, p->epochs.p, p->fault.p);
     launch_spmv_dual_mg(s, p->A.dev, st, p->xfull.p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->rhs.p,
-                        p->ysum.p, p->neq_local, r2);
+                        p->ysum.p, p->neq_local, r2, p->axsum.p);
     launch_spmv_partial_aty(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->part.p, p->at_outpos.p);
     if (!p->p2p_pull) launch_push_part(s, st, p->part.p, p->peers, p->world, p->rank, p->seg_len);
     launch_p2p_barrier(s, 1, st, r2.partials, p->A.grid(), p->peers, p->world, p->rank, p->seg_len, p->shard_len,
@@ -1215,39 +1216,55 @@ static bool use_device_checks(const b200pdlp_problem* p, const b200pdlp_params& 
 // the partial A_g'ybar are parked in `recv` and reduced by their owners after a barrier, the 28 sums (+ the time-limit
 // word) are all-reduced by the exchange kernel (identical on every rank, added in rank order), so every rank takes the
 // same decisions; a restart costs one more exchange of two scalars.  15 launches, 3 cross-GPU synchronisations.
-static int enqueue_check_device_mg(b200pdlp_problem* p) {
+static int enqueue_check_device_mg(b200pdlp_problem* p, bool light) {
   cudaStream_t s = p->stream;
   PdhgState* st = p->state.p;
   SolveCtl* ctl = p->ctl.p;
   const int nl = p->nl, ml = p->ml;
   double* o = p->outs.p;
   const ReduceScratch rrow = p->rs(kSlotK2, ml), rcol = p->rs(kSlotChk, nl), rrst = p->rs(kSlotK1, nl);
+  int launches = 0;
   launch_reduce_part_p2p(s, nl, p->aty[0].p, p->peers, p->world, p->rank, p->seg_len, 1, st, 1);   // if the last pass was accepted
-  launch_check_avg_x(s, nl, p->x[0].p, p->x[1].p, p->xsum.p, p->xavg.p, st, ctl);
-  launch_average_dev(s, ml, p->y[0].p, p->y[1].p, p->ysum.p, p->yavg.p, st);
-  launch_push_shard(s, p->xavg.p, nl, p->peers, p->world, p->rank, p->seg_len, st);
-  launch_spmv_partial_aty(s, p->AT.dev, nullptr, p->yavg.p, p->yavg.p, p->recv.p, p->at_outpos.p, st);
-  launch_p2p_exchange(s, o + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p, st);
-  launch_spmv_check_rows_mg(s, p->A.dev, st, ctl, p->xfull.p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->yavg.p,
-                            p->axavg.p, p->rhs.p, p->rowscale.p, p->neq_local, rrow);
-  launch_reduce_part_p2p(s, nl, p->atyavg.p, p->peers, p->world, p->rank, p->seg_len, 2, st, 0);
-  ColIter c0{p->x[0].p, p->aty[0].p}, calt{p->x[1].p, p->aty[0].p}, c1{p->xavg.p, p->atyavg.p};   // one current A'y shard
-  launch_col_check_fused(s, nl, c0, c1, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, rcol, o, st, calt);
-  launch_reduce_partials(s, st, ctl, 8, rrow.partials, p->A.grid(), o + 20, /*flag_slot=*/8, 0);   // o[20..27], flag at o[28]
+  if (light) {
+    // dense-check phase: the passes carried A_g xSum (my rows) and my shard of A'ySum -- no all-gather of xbar, no partial
+    // A_g'ybar, no reduce: two sweeps over my shard / my rows, then the same exchange of the 28 sums (+ time-limit word)
+    launch_check_cols_sweep(s, false, nl, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[0].p, p->xsum.p, p->atysum.p, p->xavg.p,
+                            p->atyavg.p, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, st, ctl, rcol);
+    launch_check_rows_sweep(s, false, ml, p->neq_local, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->ysum.p, p->axsum.p,
+                            p->yavg.p, p->axavg.p, p->rhs.p, p->rowscale.p, st, ctl, rrow);
+    launch_reduce_partials(s, st, ctl, 20, rcol.partials, check_light_grid(nl, true), o, -1, 0);                       // o[0..19]
+    launch_reduce_partials(s, st, ctl, 8, rrow.partials, check_light_grid(ml, false), o + 20, /*flag_slot=*/8, 0);       // o[20..27], flag at o[28]
+    launches = 5;
+  } else {
+    launch_check_light_off(s, st, ctl);
+    launch_check_avg_x(s, nl, p->x[0].p, p->x[1].p, p->xsum.p, p->xavg.p, st, ctl);
+    launch_average_dev(s, ml, p->y[0].p, p->y[1].p, p->ysum.p, p->yavg.p, st);
+    launch_push_shard(s, p->xavg.p, nl, p->peers, p->world, p->rank, p->seg_len, st);
+    launch_spmv_partial_aty(s, p->AT.dev, nullptr, p->yavg.p, p->yavg.p, p->recv.p, p->at_outpos.p, st);
+    launch_p2p_exchange(s, o + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p, st);
+    launch_spmv_check_rows_mg(s, p->A.dev, st, ctl, p->xfull.p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->yavg.p,
+                              p->axavg.p, p->rhs.p, p->rowscale.p, p->neq_local, rrow);
+    launch_reduce_part_p2p(s, nl, p->atyavg.p, p->peers, p->world, p->rank, p->seg_len, 2, st, 0);
+    ColIter c0{p->x[0].p, p->aty[0].p}, calt{p->x[1].p, p->aty[0].p}, c1{p->xavg.p, p->atyavg.p};   // one current A'y shard
+    launch_col_check_fused(s, nl, c0, c1, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, rcol, o, st, calt);
+    launch_reduce_partials(s, st, ctl, 8, rrow.partials, p->A.grid(), o + 20, /*flag_slot=*/8, 0);   // o[20..27], flag at o[28]
+    launches = 11;
+  }
   launch_p2p_exchange(s, o, 29, p->peers, p->world, p->rank, p->epochs.p, p->fault.p, st);
   launch_check_decide_sums(s, st, ctl, o);
   launch_restart_sweep(s, nl, ml, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[0].p, p->xavg.p, p->atyavg.p, p->xsum.p, p->xlr.p,
-                       p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->yavg.p, p->axavg.p, p->ysum.p, p->ylr.p, st, ctl, rrst);
+                       p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->yavg.p, p->axavg.p, p->ysum.p, p->ylr.p, st, ctl, rrst,
+                       p->atysum.p, p->axsum.p);
   launch_reduce_partials(s, st, ctl, 2, rrst.partials, restart_sweep_grid(nl, ml), o + 40, -1, 1);
   launch_p2p_exchange(s, o + 40, 2, p->peers, p->world, p->rank, p->epochs.p, p->fault.p, st);
   launch_check_finish(s, st, ctl, rrst.partials, restart_sweep_grid(nl, ml), o + 40);
-  return 16;
+  return launches + 6;
 }
 
 // the six launches of one check (pdhg_kernels.cu "device-side check iteration"); no-ops unless the check is due.
 // light: the dense-check phase's variant (five launches: two sweeps over the carried A xSum / A'ySum instead of C1-C3)
-static void enqueue_check_device(b200pdlp_problem* p, bool light = false) {
-  if (p->world > 1) { enqueue_check_device_mg(p); return; }
+static int enqueue_check_device(b200pdlp_problem* p, bool light = false) {
+  if (p->world > 1) return enqueue_check_device_mg(p, light);
   cudaStream_t s = p->stream;
   PdhgState* st = p->state.p;
   SolveCtl* ctl = p->ctl.p;
@@ -1258,7 +1275,7 @@ static void enqueue_check_device(b200pdlp_problem* p, bool light = false) {
                             p->atyavg.p, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, st, ctl, rcol);
     launch_check_rows_sweep(s, false, ml, p->neq_local, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->ysum.p, p->axsum.p,
                             p->yavg.p, p->axavg.p, p->rhs.p, p->rowscale.p, st, ctl, rrow);
-    launch_check_decide(s, st, ctl, rrow.partials, check_light_grid(ml), rcol.partials, check_light_grid(n), rrow.counter);
+    launch_check_decide(s, st, ctl, rrow.partials, check_light_grid(ml, false), rcol.partials, check_light_grid(n, true), rrow.counter);
   } else if (!p->fused_check) {
     // split check: averages, two plain SpMV (as fast as the pass kernels), two vector sweeps for the 20 + 8 sums
     launch_check_avg_xy(s, n, ml, p->x[0].p, p->x[1].p, p->xsum.p, p->xavg.p, p->y[0].p, p->y[1].p, p->ysum.p, p->yavg.p, st, ctl);
@@ -1268,7 +1285,7 @@ static void enqueue_check_device(b200pdlp_problem* p, bool light = false) {
                             p->atyavg.p, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, st, ctl, rcol);
     launch_check_rows_sweep(s, true, ml, p->neq_local, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->ysum.p, p->axsum.p,
                             p->yavg.p, p->axavg.p, p->rhs.p, p->rowscale.p, st, ctl, rrow);
-    launch_check_decide(s, st, ctl, rrow.partials, check_light_grid(ml), rcol.partials, check_light_grid(n), rrow.counter);
+    launch_check_decide(s, st, ctl, rrow.partials, check_light_grid(ml, false), rcol.partials, check_light_grid(n, true), rrow.counter);
   } else {
     // B200PDLP_FUSED_CHECK=1: the sums in the epilogues of the two averaging SpMV (three launches instead of five)
     launch_check_avg_x(s, n, p->x[0].p, p->x[1].p, p->xsum.p, p->xavg.p, st, ctl);
@@ -1282,21 +1299,25 @@ static void enqueue_check_device(b200pdlp_problem* p, bool light = false) {
                        p->xlr.p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->yavg.p, p->axavg.p, p->ysum.p, p->ylr.p,
                        st, ctl, rrst, p->atysum.p, p->axsum.p);
   launch_check_finish(s, st, ctl, rrst.partials, restart_sweep_grid(n, ml));
+  return light ? 5 : (p->fused_check ? 6 : 8);
 }
-static constexpr int kCheckLaunches = 6;   // fused variant; split: 8, light: 5
+
+static cudaGraphExec_t capture_check(b200pdlp_problem* p, bool light, int* launches) {
+  cudaGraph_t g = nullptr;
+  cudaGraphExec_t ge = nullptr;
+  CUDA_OK(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+  *launches = enqueue_check_device(p, light);
+  CUDA_OK(cudaStreamEndCapture(p->stream, &g));
+  CUDA_OK(cudaGraphInstantiate(&ge, g, 0));
+  CUDA_OK(cudaGraphDestroy(g));
+  return ge;
+}
 
 static void launch_check_graph(b200pdlp_problem* p, bool light = false) {
-  const int nl = p->world > 1 ? 16 : (light ? 5 : (p->fused_check ? 6 : 8));
-  if (p->no_graph) { enqueue_check_device(p, light); p->launches += nl; return; }
+  if (p->no_graph) { p->launches += enqueue_check_device(p, light); return; }
   cudaGraphExec_t& ge = light ? p->graph_check_light : p->graph_check;
-  if (!ge) {
-    cudaGraph_t g = nullptr;
-    CUDA_OK(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
-    enqueue_check_device(p, light);
-    CUDA_OK(cudaStreamEndCapture(p->stream, &g));
-    CUDA_OK(cudaGraphInstantiate(&ge, g, 0));
-    CUDA_OK(cudaGraphDestroy(g));
-  }
+  int& nl = p->check_launches[light ? 1 : 0];
+  if (!ge) ge = capture_check(p, light, &nl);
   CUDA_OK(cudaGraphLaunch(ge, p->stream));
   p->launches += nl;
 }
@@ -1367,15 +1388,8 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
           p->ctl.alloc(1, false);
         }
         for (int k = 2; k <= 5; k++) if (!p->graph_pow2[k]) { p->graph_pow2[k] = capture_passes(p, 1 << k); CUDA_OK(cudaGraphUpload(p->graph_pow2[k], s)); }
-        if (!p->graph_check) {
-          cudaGraph_t g = nullptr;
-          CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-          enqueue_check_device(p);
-          CUDA_OK(cudaStreamEndCapture(s, &g));
-          CUDA_OK(cudaGraphInstantiate(&p->graph_check, g, 0));
-          CUDA_OK(cudaGraphDestroy(g));
-          CUDA_OK(cudaGraphUpload(p->graph_check, s));
-        }
+        if (!p->graph_check) { p->graph_check = capture_check(p, false, &p->check_launches[0]); CUDA_OK(cudaGraphUpload(p->graph_check, s)); }
+        if (!p->graph_check_light) { p->graph_check_light = capture_check(p, true, &p->check_launches[1]); CUDA_OK(cudaGraphUpload(p->graph_check_light, s)); }
       }
     }
     CUDA_OK(cudaStreamSynchronize(s));
@@ -1547,14 +1561,15 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
       if (fused != p->fused_check && p->graph_check) { cudaGraphExecDestroy(p->graph_check); p->graph_check = nullptr; }
       p->fused_check = fused;
     }
-    h_light = p->world == 1 && p->axsum.p && p->atysum.p;
+    const bool hot = warm && warm->col_value && warm->row_value && warm->row_dual;
+    h_light = p->axsum.p && p->atysum.p && (p->world == 1 || !hot);   // (several GPUs: A_g xSum of a hot start would need the gathered xSum)
     if (const char* e = getenv("B200PDLP_LIGHT_CHECK")) if (atoi(e) == 0) h_light = false;
     h->light_on = h_light ? 1 : 0;
     if (h_light) {
       // xSum starts at proj(0) (PDHG_Init_Variables): without a hot start that IS x, whose product is at hand
-      if (warm && warm->col_value && warm->row_value && warm->row_dual) { launch_spmv_plain(s, p->A.dev, p->xsum.p, p->axsum.p); p->launches++; }
+      if (hot) { launch_spmv_plain(s, p->A.dev, p->xsum.p, p->axsum.p); p->launches++; }
       else CUDA_OK(cudaMemcpyAsync(p->axsum.p, p->ax[0].p, (size_t)std::max(ml, 1) * sizeof(double), cudaMemcpyDeviceToDevice, s));
-      CUDA_OK(cudaMemsetAsync(p->atysum.p, 0, (size_t)std::max(n, 1) * sizeof(double), s));
+      CUDA_OK(cudaMemsetAsync(p->atysum.p, 0, (size_t)std::max(nl, 1) * sizeof(double), s));
     }
     if (out->trace && out->trace_cap > 0) {
       if (p->trace_dev.n < (size_t)out->trace_cap * B200PDLP_TRACE_COLS) p->trace_dev.alloc((size_t)out->trace_cap * B200PDLP_TRACE_COLS, false);
@@ -1622,6 +1637,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
       }
       if (c->term >= 0) break;
       // not finished: continue from where the device really is
+      h_light = h_light && h->light_on != 0;
       pred_iter = h->iter;
       carry = std::max(0, h->stop_iter - h->iter);
     }
@@ -1722,6 +1738,21 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   nvtxRangePop();
   NvtxRange nvtx_post("b200pdlp: postsolve + download");
 
+  if (p->world > 1 && getenv("B200PDLP_DEBUG_MG")) {
+    // diagnostics: per-rank barrier / exchange counts and checksums of what the postsolve is about to assemble
+    unsigned long long ep[16] = {0};
+    if (p->epochs.p) CUDA_OK(cudaMemcpy(ep, p->epochs.p, sizeof(ep), cudaMemcpyDeviceToHost));
+    auto csum = [&](const double* d, int len) {
+      std::vector<double> t(std::max(len, 1));
+      if (len > 0) CUDA_OK(cudaMemcpy(t.data(), d, (size_t)len * sizeof(double), cudaMemcpyDeviceToHost));
+      double a = 0.0; for (int i = 0; i < len; i++) a += t[i] * (1.0 + (i % 7)); return a;
+    };
+    fprintf(stderr, "[b200pdlp mg-debug] rank %d iter %d cur %d term %d term_iterate %d light_on %d | barrier0 %llu barrier1 %llu exchange %llu | "
+            "x[cur] %.17g xavg %.17g y[cur] %.17g yavg %.17g ax[cur] %.17g axavg %.17g aty0 %.17g atyavg %.17g\n",
+            p->rank, h->iter, h->cur, term, term_iterate, h->light_on, ep[0], ep[1], ep[10],
+            csum(p->x[h->cur].p, p->nl), csum(p->xavg.p, p->nl), csum(p->y[h->cur].p, ml), csum(p->yavg.p, ml),
+            csum(p->ax[h->cur].p, ml), csum(p->axavg.p, ml), csum(p->aty[0].p, p->nl), csum(p->atyavg.p, p->nl));
+  }
   // ---- PDHG_PostSolve (cupdlp_solver.c:1281-1435)
   const int cur = h->cur;
   const bool use_avg = (term == B200PDLP_OPTIMAL && term_iterate == 1);

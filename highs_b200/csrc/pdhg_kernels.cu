@@ -124,7 +124,7 @@ struct DualEpilogueT {
     y = cur ? y1 : y0; yn = cur ? y0 : y1;
     ax = cur ? ax1 : ax0; axn = cur ? ax0 : ax1;
     sigma = st->sigma_try; w = st->w_pending; pend = st->pending != 0;
-    accum = pend && st->light_on && st->iter < kDenseChecks;
+    accum = pend && axsum != nullptr && st->light_on && st->iter < kDenseChecks;
     x0 = cur ? x0 : x1;   // x0 now = input vector (the NEW x)
     return true;
   }
@@ -223,7 +223,7 @@ struct PrimalEpilogue {
     aty = cur ? aty1 : aty0; atyn = cur ? aty0 : aty1;
     y0 = cur ? y0 : y1;   // y0 now = input vector (the NEW y)
     w = st->w_pending;
-    accum = st->pending != 0 && st->light_on && st->iter < kDenseChecks;
+    accum = st->pending != 0 && atysum != nullptr && st->light_on && st->iter < kDenseChecks;
     return true;
   }
   __device__ const double* input() const { return y0; }
@@ -580,11 +580,12 @@ __global__ void __launch_bounds__(kThreads)
 primal_shard_p2p_kernel(int len, PdhgState* __restrict__ st, double* __restrict__ xs0, double* __restrict__ xs1,
                         double* __restrict__ aty_s, PeerPtrs pp, int world, int rank, int seg_len, int pull,
                         const double* __restrict__ c, const double* __restrict__ lo, const double* __restrict__ up,
-                        double* __restrict__ xsum, ReduceScratch rs) {
+                        double* __restrict__ xsum, ReduceScratch rs, double* __restrict__ atysum) {
   if (st->iter >= st->stop_iter) return;
   const int cur = st->cur;
   const double tau = st->tau_try, ntau = -tau;
   const bool pend = st->pending != 0, take = st->accepted_last != 0;
+  const bool accum = pend && atysum != nullptr && st->light_on && st->iter < kDenseChecks;   // dense-check phase: carry A'ySum
   const double w = st->w_pending;
   const double* __restrict__ x = cur ? xs1 : xs0;
   double* __restrict__ xn = cur ? xs0 : xs1;
@@ -627,6 +628,12 @@ primal_shard_p2p_kernel(int len, PdhgState* __restrict__ st, double* __restrict_
       sm.x = sm.x + w * xc.x;
       sm.y = sm.y + w * xc.y;
       reinterpret_cast<double2*>(xsum)[i] = sm;
+    }
+    if (accum) {
+      double2 sa = reinterpret_cast<double2*>(atysum)[i];
+      sa.x = sa.x + w * ai.x;
+      sa.y = sa.y + w * ai.y;
+      reinterpret_cast<double2*>(atysum)[i] = sa;
     }
     double2 o;
     acc[0] += one(xc.x, ci.x, ai.x, u.x, l.x, o.x);
@@ -1332,6 +1339,7 @@ check_cols_sweep_kernel(int n, const double* __restrict__ x0, const double* __re
 #pragma unroll
   for (int a = 0; a < 20; a++) acc[a] = 0.0;
   const int stride = gridDim.x * kThreads;
+#pragma unroll 2
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
     const double xc = x[i], ac = aty[i];
     double xa, aa;
@@ -1378,6 +1386,7 @@ check_rows_sweep_kernel(int m, int neq, const double* __restrict__ y0, const dou
 #pragma unroll
   for (int a = 0; a < 8; a++) acc[a] = 0.0;
   const int stride = gridDim.x * kThreads;
+#pragma unroll 2
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < m; i += stride) {
     const double yc = y[i], ac = ax[i];
     double ya, aa;
@@ -1403,6 +1412,14 @@ check_rows_sweep_kernel(int m, int neq, const double* __restrict__ y0, const dou
   }
   block_partials<8>(acc, rs);
 }
+
+// several GPUs: a FULL check inside the dense-check phase (the host predicted past it while rejected steps held the device
+// back) flushes xSum / ySum but not the carried products -- the light variant is switched off for the rest of the solve
+// (the host reads the flag with the state block and stops choosing it)
+__global__ void check_light_off_kernel(PdhgState* st, const SolveCtl* ctl) {
+  if (check_live(st, ctl) && st->light_on && st->iter < kDenseChecks) st->light_on = 0;
+}
+void launch_check_light_off(cudaStream_t s, PdhgState* st, const SolveCtl* ctl) { check_light_off_kernel<<<1, 1, 0, s>>>(st, ctl); }
 
 // C1 of the split check: xbar and ybar in one launch (flushes the pending weight into xSum and ySum)
 __global__ void __launch_bounds__(kThreads)
@@ -1828,11 +1845,11 @@ void launch_spmv_partial_aty(cudaStream_t s, const DevSell& A, PdhgState* st, co
 }
 
 void launch_spmv_dual_mg(cudaStream_t s, const DevSell& A, PdhgState* st, const double* xfull, double* y0, double* y1,
-                         double* ax0, double* ax1, const double* b, double* ysum, int neq, ReduceScratch rs) {
+                         double* ax0, double* ax1, const double* b, double* ysum, int neq, ReduceScratch rs, double* axsum) {
   if (A.nblocks_body + A.nsegs == 0) return;   // no rows on this rank: nothing to launch, the partial count is 0
   DualEpilogueMg e{};
   e.st = st; e.x0 = xfull; e.x1 = xfull; e.y0 = y0; e.y1 = y1; e.ax0 = ax0; e.ax1 = ax1; e.b = b; e.ysum = ysum;
-  e.neq = neq; e.row_offset = 0;
+  e.neq = neq; e.row_offset = 0; e.axsum = axsum;
   spmv_sell_kernel<DualEpilogueMg><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, rs);
 }
 
@@ -1852,9 +1869,9 @@ void launch_stash_scalars(cudaStream_t s, int nv, PdhgState* st, const double* p
 
 void launch_primal_shard_p2p(cudaStream_t s, int len, PdhgState* st, double* xs0, double* xs1, double* aty_s,
                              const PeerPtrs& pp, int world, int rank, int seg_len, int pull, const double* c,
-                             const double* lo, const double* up, double* xsum, ReduceScratch rs) {
+                             const double* lo, const double* up, double* xsum, ReduceScratch rs, double* atysum) {
   primal_shard_p2p_kernel<<<ew_grid((len + 1) / 2), kThreads, 0, s>>>(len, st, xs0, xs1, aty_s, pp, world, rank, seg_len,
-                                                                      pull, c, lo, up, xsum, rs);
+                                                                      pull, c, lo, up, xsum, rs, atysum);
 }
 void launch_push_part(cudaStream_t s, PdhgState* st, const double* part, const PeerPtrs& pp, int world, int rank, int seg_len) {
   push_part_kernel<<<ew_grid((seg_len / 2) * world), kThreads, 0, s>>>(st, part, pp, world, rank, seg_len);
@@ -1910,7 +1927,9 @@ void preload_multi_gpu_kernels() {
       (const void*)row_check_fused_kernel, (const void*)diff_norm2_kernel, (const void*)scale_kernel,
       (const void*)fill_kernel, (const void*)check_avg_x_kernel, (const void*)check_decide_kernel,
       (const void*)check_decide_sums_kernel, (const void*)restart_sweep_kernel, (const void*)reduce_partials_kernel,
-      (const void*)check_finish_kernel,
+      (const void*)check_finish_kernel, (const void*)check_light_off_kernel, (const void*)check_avg_xy_kernel,
+      (const void*)check_cols_sweep_kernel<false>, (const void*)check_cols_sweep_kernel<true>,
+      (const void*)check_rows_sweep_kernel<false>, (const void*)check_rows_sweep_kernel<true>,
       (const void*)spmv_sell_kernel<PlainEpilogue, false>, (const void*)spmv_sell_kernel<PlainEpilogue, true>,
       (const void*)spmv_sell_kernel<DualEpilogue, false>, (const void*)spmv_sell_kernel<DualEpilogue, true>,
       (const void*)spmv_sell_kernel<PrimalEpilogue, false>, (const void*)spmv_sell_kernel<PrimalEpilogue, true>,
@@ -1968,21 +1987,26 @@ void launch_restart_sweep(cudaStream_t s, int n, int m, double* x0, double* x1, 
                                                                     y1, ax0, ax1, yavg, axavg, ysum, ylr, st, ctl, rs, atysum,
                                                                     axsum);
 }
-int check_light_grid(int len) { return ew_grid(len); }
+// few, long-lived CTAs: a block's tree over 20 (8) accumulators costs as much as its share of the sweep when the grid is the
+// element-wise default of ~2400 CTAs (measured: 40 us for the column sweep at S3, 2.4x its memory time)
+int check_light_grid(int len, bool cols) {
+  const int g = ew_grid(len), cap = 148 * (cols ? 2 : 4);
+  return g < cap ? g : cap;
+}
 void launch_check_cols_sweep(cudaStream_t s, bool given, int n, const double* x0, const double* x1, const double* aty0,
                              const double* aty1, double* xsum, double* atysum, double* xavg, double* atyavg, const double* c,
                              const double* lo, const double* up, const double* cs, const PdhgState* st, const SolveCtl* ctl,
                              ReduceScratch rs) {
   rs.terms = nullptr; rs.flags = 0;
-  if (given) check_cols_sweep_kernel<true><<<check_light_grid(n), kThreads, 0, s>>>(n, x0, x1, aty0, aty1, xsum, atysum, xavg, atyavg, c, lo, up, cs, st, ctl, rs);
-  else check_cols_sweep_kernel<false><<<check_light_grid(n), kThreads, 0, s>>>(n, x0, x1, aty0, aty1, xsum, atysum, xavg, atyavg, c, lo, up, cs, st, ctl, rs);
+  if (given) check_cols_sweep_kernel<true><<<check_light_grid(n, true), kThreads, 0, s>>>(n, x0, x1, aty0, aty1, xsum, atysum, xavg, atyavg, c, lo, up, cs, st, ctl, rs);
+  else check_cols_sweep_kernel<false><<<check_light_grid(n, true), kThreads, 0, s>>>(n, x0, x1, aty0, aty1, xsum, atysum, xavg, atyavg, c, lo, up, cs, st, ctl, rs);
 }
 void launch_check_rows_sweep(cudaStream_t s, bool given, int m, int neq, const double* y0, const double* y1, const double* ax0,
                              const double* ax1, double* ysum, double* axsum, double* yavg, double* axavg, const double* b,
                              const double* rsc, const PdhgState* st, const SolveCtl* ctl, ReduceScratch rs) {
   rs.terms = nullptr; rs.flags = 0;
-  if (given) check_rows_sweep_kernel<true><<<check_light_grid(m), kThreads, 0, s>>>(m, neq, y0, y1, ax0, ax1, ysum, axsum, yavg, axavg, b, rsc, st, ctl, rs);
-  else check_rows_sweep_kernel<false><<<check_light_grid(m), kThreads, 0, s>>>(m, neq, y0, y1, ax0, ax1, ysum, axsum, yavg, axavg, b, rsc, st, ctl, rs);
+  if (given) check_rows_sweep_kernel<true><<<check_light_grid(m, false), kThreads, 0, s>>>(m, neq, y0, y1, ax0, ax1, ysum, axsum, yavg, axavg, b, rsc, st, ctl, rs);
+  else check_rows_sweep_kernel<false><<<check_light_grid(m, false), kThreads, 0, s>>>(m, neq, y0, y1, ax0, ax1, ysum, axsum, yavg, axavg, b, rsc, st, ctl, rs);
 }
 void launch_check_avg_xy(cudaStream_t s, int n, int m, const double* x0, const double* x1, double* xsum, double* xavg,
                          const double* y0, const double* y1, double* ysum, double* yavg, const PdhgState* st, const SolveCtl* ctl) {

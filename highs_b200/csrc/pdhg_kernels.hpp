@@ -20,7 +20,8 @@ void launch_spmv_primal(cudaStream_t s, const DevSell& A, PdhgState* st, const d
 void launch_spmv_partial_aty(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
                              double* part, const int* outpos, const PdhgState* due = nullptr);
 void launch_spmv_dual_mg(cudaStream_t s, const DevSell& A, PdhgState* st, const double* xfull, double* y0, double* y1,
-                         double* ax0, double* ax1, const double* b, double* ysum, int neq, ReduceScratch rs);
+                         double* ax0, double* ax1, const double* b, double* ysum, int neq, ReduceScratch rs,
+                         double* axsum = nullptr);
 void launch_primal_shard(cudaStream_t s, int len, PdhgState* st, double* xs0, double* xs1, double* aty_s,
                          const double* red, const double* c, const double* lo, const double* up, double* xsum,
                          double* send, ReduceScratch rs);
@@ -30,7 +31,7 @@ void launch_stash_scalars(cudaStream_t s, int nv, PdhgState* st, const double* p
                           int stride);
 void launch_primal_shard_p2p(cudaStream_t s, int len, PdhgState* st, double* xs0, double* xs1, double* aty_s,
                              const PeerPtrs& pp, int world, int rank, int seg_len, int pull, const double* c,
-                             const double* lo, const double* up, double* xsum, ReduceScratch rs);
+                             const double* lo, const double* up, double* xsum, ReduceScratch rs, double* atysum = nullptr);
 void launch_push_shard(cudaStream_t s, const double* src, int len, const PeerPtrs& pp, int world, int rank, int seg_len,
                        const PdhgState* due = nullptr);
 void launch_push_rows(cudaStream_t s, const double* src, int len, const PeerPtrs& pp, int world, int rank, int seg_len);
@@ -93,8 +94,8 @@ void launch_restart_sweep(cudaStream_t s, int n, int m, double* x0, double* x1, 
                           double* axsum = nullptr);
 // the residual sweeps as plain vector kernels: given = true (split check: xbar/ybar from launch_check_avg_xy, A xbar / A'ybar
 // from two plain SpMV) or false (light check of the dense-check phase: from the carried A xSum / A'ySum); partial-sum layout
-// [20][check_light_grid(n)], [8][check_light_grid(m)]
-int check_light_grid(int len);
+// [20][check_light_grid(n, true)], [8][check_light_grid(m, false)]
+int check_light_grid(int len, bool cols);
 void launch_check_cols_sweep(cudaStream_t s, bool given, int n, const double* x0, const double* x1, const double* aty0,
                              const double* aty1, double* xsum, double* atysum, double* xavg, double* atyavg, const double* c,
                              const double* lo, const double* up, const double* cs, const PdhgState* st, const SolveCtl* ctl,
@@ -102,6 +103,7 @@ void launch_check_cols_sweep(cudaStream_t s, bool given, int n, const double* x0
 void launch_check_rows_sweep(cudaStream_t s, bool given, int m, int neq, const double* y0, const double* y1, const double* ax0,
                              const double* ax1, double* ysum, double* axsum, double* yavg, double* axavg, const double* b,
                              const double* rsc, const PdhgState* st, const SolveCtl* ctl, ReduceScratch rs);
+void launch_check_light_off(cudaStream_t s, PdhgState* st, const SolveCtl* ctl);
 void launch_check_avg_xy(cudaStream_t s, int n, int m, const double* x0, const double* x1, double* xsum, double* xavg,
                          const double* y0, const double* y1, double* ysum, double* yavg, const PdhgState* st, const SolveCtl* ctl);
 void launch_check_finish(cudaStream_t s, PdhgState* st, SolveCtl* ctl, const double* prst, int nbs, const double* sums2 = nullptr);

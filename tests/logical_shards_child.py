@@ -59,7 +59,9 @@ def main():
     # both runs stop at relative gap < tol: they bracket the optimum to ~tol (1 + |p| + |d|) each
     if not abs(out["obj"][0] - o_ref) <= 3 * tol * (1 + 2 * abs(o_ref)):
         fails.append(f"objective {out['obj'][0]} vs oracle {o_ref}")
-    if not abs(r0["iters"] - ref["iters"]) <= 0.35 * ref["iters"] + 80:
+    # (converged iteration counts spread by tens of percent under a mere regrouping of the long sums: measured on the oracle
+    #  itself, profiles/r02_s2_order_sensitivity.json)
+    if not 0.5 * ref["iters"] - 80 <= r0["iters"] <= 2.0 * ref["iters"] + 80:
         fails.append(f"iterations {r0['iters']} vs oracle {ref['iters']}")
     # the assembled solution in the ORIGINAL space: row_value must be A x
     A = lp.a_matrix_.to_scipy()

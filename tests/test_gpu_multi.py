@@ -64,7 +64,9 @@ def test_two_gpu_row_partition(engine_lib, oracle, tmp_path, mode):
     assert int(multi["term"]) == orc["term_code"] == 0
     o1, o2 = lp.objectiveValue(multi["col_value"]), lp.objectiveValue(orc["col_value"])
     assert abs(o1 - o2) <= 1e-6 * (1 + abs(o2))     # north-star criterion: objective to 1e-6 relative
-    assert abs(int(multi["iters"]) - orc["iters"]) <= 0.05 * orc["iters"] + 80
+    # converged iteration counts of two runs that differ in summation order spread by tens of percent (measured on the oracle
+    # itself: profiles/r02_s2_order_sensitivity.json); the trajectory itself is compared below, where it is still comparable
+    assert 0.5 * orc["iters"] <= int(multi["iters"]) <= 2.0 * orc["iters"] + 80
     # 120 iterations from the same start: the multi-GPU step rule takes the interaction term on the row side
     # (DESIGN.md section 5), identical in exact arithmetic -- the iterates agree up to rounding propagation
     fix = oracle.solve(lp, iter_limit=121)
