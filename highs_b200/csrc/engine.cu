@@ -282,6 +282,7 @@ struct b200pdlp_problem {
   DevBuf<double> trace_dev;
   cudaGraphExec_t graph_pow2[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // 1 << k passes
   cudaGraphExec_t graph_check = nullptr;
+  bool fuse_k4 = false;                           // B200PDLP_FUSE_K4=1: the step rule runs in K3's last CTA (tree mode, one GPU)
   int check_launches[2] = {0, 0};                 // kernels in graph_check / graph_check_light
   bool fused_check = false;                       // B200PDLP_FUSED_CHECK=1: residual sums in the SpMV epilogues (C2/C3) instead of the split check
   cudaGraphExec_t graph_check_light = nullptr;   // the dense-check phase's check: two sweeps instead of two SpMV (see kDenseChecks)
@@ -438,6 +439,7 @@ struct DeviceSetup {
 // walk their slices in a software pipeline (spmv_sell_kernel<Epi, true>) instead of one CTA per 8 slices
 static void apply_spmv_grid(b200pdlp_problem* p) {
   if (p->world != 1 || p->ordered) return;
+  if (const char* e = getenv("B200PDLP_FUSE_K4")) p->fuse_k4 = atoi(e) != 0 && p->AT.grid() > 0;
   auto val = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
   const int both = val("B200PDLP_SPMV_CTAS_PER_SM", -1);
   // measured (profiles/r02_experiments.md): the pipelined walk helps A'y (K3: 49.3 -> 44.6 us at 3 CTAs per SM) and hurts
@@ -761,6 +763,11 @@ static void enqueue_pass(b200pdlp_problem* p) {
                      p->upper.p, p->xsum.p, r1);
   launch_spmv_dual(s, p->A.dev, st, p->x[0].p, p->x[1].p, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p,
                    p->rhs.p, p->ysum.p, p->neq_local, 0, r2, p->axsum.p);
+  if (p->fuse_k4) {   // B200PDLP_FUSE_K4=1 (experiment): K3's last CTA applies the step rule, three launches per pass
+    launch_spmv_primal(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, r3, p->atysum.p,
+                       r1.partials, primal_step_grid(p->n), r2.partials, p->A.grid());
+    return;
+  }
   launch_spmv_primal(s, p->AT.dev, st, p->y[0].p, p->y[1].p, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, r3, p->atysum.p);
   launch_step_rule(s, st, r1, primal_step_grid(p->n), r2, p->A.grid(), r3, p->AT.grid(), nullptr);
 }
@@ -1513,7 +1520,7 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
     if (!p->graph_main) p->graph_main = capture_passes(p, want_main);
     if (!p->graph_small) { p->graph_small_passes = 4; p->graph_small = capture_passes(p, 4); }
   }
-  p->kernels_per_pass = p->world == 1 ? 4 : ((p->p2p && p->p2p_pull) ? 5 : 6);   // ours; NCCL kernels not counted
+  p->kernels_per_pass = p->world == 1 ? (p->fuse_k4 ? 3 : 4) : ((p->p2p && p->p2p_pull) ? 5 : 6);   // ours; NCCL kernels not counted
   lap("solve", "graph capture");
   nvtxRangePop();
   nvtxRangePushA("b200pdlp: PDHG loop");

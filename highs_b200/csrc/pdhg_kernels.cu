@@ -212,6 +212,10 @@ struct PrimalEpilogue {
   const double *x0, *x1;
   double *aty0, *aty1;
   double* atysum;              // A'ySum, carried while the checks are dense (PdhgState::light_on); may be nullptr
+  // fused step rule (B200PDLP_FUSE_K4): the last CTA of K3 to finish adds the block partials of K1, K2 and K3 and applies the
+  // step rule -- K4's work without K4's launch
+  const double *p1, *p2;
+  int nb1, nb2, fuse;
   const double *x, *xn, *aty;
   double* atyn;
   double w;
@@ -229,6 +233,25 @@ struct PrimalEpilogue {
   __device__ const double* input() const { return y0; }
   double p_x, p_xn, p_aty, p_as;
   __device__ void prefetch(int r) { p_x = x[r]; p_xn = xn[r]; p_aty = aty[r]; p_as = accum ? atysum[r] : 0.0; }
+  __device__ void tail(const ReduceScratch& rs, int nb3) const {
+    // same sums as step_rule_kernel (fixed order: thread-strided, lanes, warps), on this CTA's kThreads threads
+    __shared__ double smt[3][kThreads / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int i = threadIdx.x; i < nb1; i += kThreads) s1 += __ldcg(p1 + i);
+    for (int i = threadIdx.x; i < nb2; i += kThreads) s2 += __ldcg(p2 + i);
+    for (int i = threadIdx.x; i < nb3; i += kThreads) s3 += __ldcg(rs.partials + i);   // other CTAs of THIS kernel wrote them
+    s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+    if (lane == 0) { smt[0][wid] = s1; smt[1][wid] = s2; smt[2][wid] = s3; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+      for (int q = 0; q < kThreads / 32; q++) { t1 += smt[0][q]; t2 += smt[1][q]; t3 += smt[2][q]; }
+      st->dx2 = t1;
+      st->dy2 = t2;
+      step_rule(st, t3);
+    }
+  }
   __device__ void row(int r, double s, double* t) const {
     atyn[r] = s;
     if (accum) atysum[r] = p_as + w * p_aty;   // A'ySum += w A'y
@@ -296,6 +319,9 @@ step_rule_kernel(PdhgState* __restrict__ st, ReduceScratch r1, int nb1, ReduceSc
     step_rule(st, tot[2]);
   }
 }
+
+template <class E> struct HasTail { static constexpr bool value = false; };
+template <> struct HasTail<PrimalEpilogue> { static constexpr bool value = true; };
 
 // PIPE: persistent grid (DevSell::pipelined), slices walked in a software pipeline; !PIPE: one CTA per 8 slices
 template <class Epi, bool PIPE = false>
@@ -514,6 +540,21 @@ __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_
     }
   } else if constexpr (Epi::NACC > 0) {
     block_partials<Epi::NACC>(acc, rs);
+  }
+  if constexpr (HasTail<Epi>::value) {
+    // last-CTA-done: the epilogue's tail runs once, after every CTA of this launch has published its partial sums
+    if (epi.fuse) {
+      __shared__ int is_last;
+      if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = atomicAdd(rs.counter, 1u) == gridDim.x - 1u ? 1 : 0;
+      }
+      __syncthreads();
+      if (is_last) {
+        if (threadIdx.x == 0) { *rs.counter = 0u; __threadfence(); }
+        epi.tail(rs, (int)gridDim.x);
+      }
+    }
   }
 }
 
@@ -1806,10 +1847,12 @@ void launch_spmv_dual(cudaStream_t s, const DevSell& A, PdhgState* st, const dou
 }
 
 void launch_spmv_primal(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
-                        const double* x0, const double* x1, double* aty0, double* aty1, ReduceScratch rs, double* atysum) {
+                        const double* x0, const double* x1, double* aty0, double* aty1, ReduceScratch rs, double* atysum,
+                        const double* p1, int nb1, const double* p2, int nb2) {
   if (A.nblocks_body + A.nsegs == 0) return;   // no rows on this rank: nothing to launch, the partial count is 0
   PrimalEpilogue e{};
   e.st = st; e.y0 = y0; e.y1 = y1; e.x0 = x0; e.x1 = x1; e.aty0 = aty0; e.aty1 = aty1; e.atysum = atysum;
+  e.p1 = p1; e.nb1 = nb1; e.p2 = p2; e.nb2 = nb2; e.fuse = (p1 != nullptr && rs.terms == nullptr) ? 1 : 0;
   if (A.pipelined) launch_k(spmv_sell_kernel<PrimalEpilogue, true>, A.nblocks_body + A.nsegs, kThreads, s, rs.flags, A, e, rs);
   else launch_k(spmv_sell_kernel<PrimalEpilogue, false>, A.nblocks_body + A.nsegs, kThreads, s, rs.flags, A, e, rs);
 }

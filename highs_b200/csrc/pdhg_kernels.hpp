@@ -16,7 +16,8 @@ void launch_spmv_dual(cudaStream_t s, const DevSell& A, PdhgState* st, const dou
                       int neq, int row_offset, ReduceScratch rs, double* axsum = nullptr);
 void launch_spmv_primal(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
                         const double* x0, const double* x1, double* aty0, double* aty1, ReduceScratch rs,
-                        double* atysum = nullptr);
+                        double* atysum = nullptr, const double* k1_partials = nullptr, int nb1 = 0,
+                        const double* k2_partials = nullptr, int nb2 = 0 /* non-null: the last CTA also applies the step rule */);
 void launch_spmv_partial_aty(cudaStream_t s, const DevSell& A, PdhgState* st, const double* y0, const double* y1,
                              double* part, const int* outpos, const PdhgState* due = nullptr);
 void launch_spmv_dual_mg(cudaStream_t s, const DevSell& A, PdhgState* st, const double* xfull, double* y0, double* y1,
