@@ -1797,6 +1797,19 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
   {
     // device order -> standard-form order
     std::vector<double> t(std::max<size_t>(std::max(n, std::max(ml, 1)), p->xfull.n));
+    const bool dbg = p->world > 1 && getenv("B200PDLP_DEBUG_MG") != nullptr;
+    const bool rendezvous = p->local_link && p->group && getenv("B200PDLP_LOCAL_RENDEZVOUS") != nullptr;   // experiment
+    int dbg_stage = 0;
+    auto dbg_segments = [&](const char* what) {
+      if (!dbg) return;
+      char line[1024]; int k = snprintf(line, sizeof line, "[b200pdlp mg-debug] rank %d stage %d %s segments:", p->rank, dbg_stage++, what);
+      for (int g = 0; g < p->world && k < 900; g++) {
+        double a = 0.0;
+        for (int i = 0; i < p->seg_len; i++) a += t[(size_t)g * p->seg_len + i] * (1.0 + (i % 7));
+        k += snprintf(line + k, sizeof line - k, " %.15g", a);
+      }
+      fprintf(stderr, "%s\n", line);
+    };
     auto down_col = [&](const double* d, std::vector<double>& h) {
       if (p->world == 1) {
         CUDA_OK(cudaMemcpyAsync(t.data(), d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -1807,10 +1820,13 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
         // barrier before anyone reads and one before anyone overwrites
         launch_push_shard(s, d, nl, p->peers, p->world, p->rank, p->seg_len);
         launch_p2p_exchange(s, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p);
+        if (rendezvous) { CUDA_OK(cudaStreamSynchronize(s)); p->group->arrive_and_wait(); }
         CUDA_OK(cudaMemcpyAsync(t.data(), p->xfull.p, p->xfull.n * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (rendezvous) { CUDA_OK(cudaStreamSynchronize(s)); p->group->arrive_and_wait(); }
         launch_p2p_exchange(s, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p);
         p->launches += 3;
         CUDA_OK(cudaStreamSynchronize(s));
+        dbg_segments("columns");
         for (int j = 0; j < n; j++) h[p->cperm[j]] = t[seg_pos(p, j)];
       } else {   // all-gather the column shards, then unpack the segmented vector
         CUDA_OK(cudaMemcpyAsync(p->send.p, d, (size_t)nl * sizeof(double), cudaMemcpyDeviceToDevice, s));
@@ -1835,10 +1851,13 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
           const int off = c * p->seg_len;
           launch_push_rows(s, p->redbuf.p + off, std::max(0, std::min(ml - off, p->seg_len)), p->peers, p->world, p->rank, p->seg_len);
           launch_p2p_exchange(s, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p);
+          if (rendezvous) { CUDA_OK(cudaStreamSynchronize(s)); p->group->arrive_and_wait(); }
           CUDA_OK(cudaMemcpyAsync(t.data(), p->recv.p, (size_t)p->world * p->seg_len * sizeof(double), cudaMemcpyDeviceToHost, s));
+          if (rendezvous) { CUDA_OK(cudaStreamSynchronize(s)); p->group->arrive_and_wait(); }
           launch_p2p_exchange(s, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p);
           p->launches += 3;
           CUDA_OK(cudaStreamSynchronize(s));
+          dbg_segments("rows");
           for (int g = 0; g < p->world; g++) {
             const int mg = p->row_bounds[g + 1] - p->row_bounds[g];
             const int cnt = std::max(0, std::min(mg - off, p->seg_len));
