@@ -1872,6 +1872,12 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
       }
     };
     down_col(dx, hx); down_col(daty, haty); down_row(dy, hy); down_row(dax, hax);
+    if (p->p2p) {   // a barrier of the assembly that timed out leaves stale segments behind: an error, not a result
+      int fault = 0;
+      CUDA_OK(cudaMemcpyAsync(&fault, p->fault.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CUDA_OK(cudaStreamSynchronize(s));
+      if (fault) throw Error(B200PDLP_ERR_STATE, "P2P barrier timed out while the solution was being assembled (a peer rank did not arrive)");
+    }
   }
   lap("solve", "solution download");
   const double inf = std::numeric_limits<double>::infinity();
