@@ -383,6 +383,25 @@ slice_desc_kernel(int nslices, const int* __restrict__ slice_len, const unsigned
     slices[s] = make_int4((int)off, slice_len[s], (int)slice_mask[s], 0);
   }
 }
+// How much do a warp's gathers share 32-byte sectors?  One warp per sampled slice looks at the slice's first column ids.
+__global__ void __launch_bounds__(kTpb)
+sector_sharing_kernel(int nslices, int step, const int4* __restrict__ slices, const int* __restrict__ col, int* __restrict__ out) {
+  const int w = (blockIdx.x * kTpb + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const long long sl = (long long)w * step;
+  if (sl >= nslices) return;
+  const int4 d = slices[sl];
+  if (d.y < 1) return;
+  const bool live = !((unsigned)d.z >> lane & 1u);
+  const unsigned act = __ballot_sync(0xffffffffu, live);
+  bool leader = false;
+  if (live) {
+    const int sector = col[d.x + lane] >> 2;
+    const unsigned same = __match_any_sync(act, sector);
+    leader = lane == __ffs(same) - 1;
+  }
+  const unsigned leaders = __ballot_sync(0xffffffffu, leader);
+  if (lane == 0) { atomicAdd(out, __popc(leaders)); atomicAdd(out + 1, __popc(act)); }
+}
 // long rows -> descriptors and segments of kNnzBlk entries (plan_sell's second loop).  `list` holds the device-row ids of
 // the long rows in ascending order; one thread walks them (they are few).  totals: [0] n_partials (= segments),
 // [1] lcount (entries of lcol / lval incl. the tail of 8)
@@ -778,6 +797,15 @@ void DevicePrologue::run(cudaStream_t s, const b200pdlp_lp& lp, bool do_scale, i
   }
   build(A, pa, m, n, sc.a_padded, sc.a_nlong, sc.a_nsegs, sc.a_lcount, arr.rperm, rptr, SA);
   build(AT, pat, n, m, sc.at_padded, sc.at_nlong, sc.at_nsegs, sc.at_lcount, arr.cperm, cbeg, SAT);
+  int* sect = tmp.get<int>(4);
+  PREP_OK(cudaMemsetAsync(sect, 0, 4 * sizeof(int), s));
+  auto sample = [&](const DevSellOwned& M, int* out) {
+    if (M.nslices <= 0) return;
+    const int step = std::max(1, M.nslices / 4096), nw = (M.nslices + step - 1) / step;
+    sector_sharing_kernel<<<warp_grid(nw), kTpb, 0, s>>>(M.nslices, step, M.slices, M.col, out);
+  };
+  sample(A, sect);
+  sample(AT, sect + 2);
 
   // ---- vectors in device order
   arr.cost = keep<double>(n); arr.lower = keep<double>(n); arr.upper = keep<double>(n); arr.colscale = keep<double>(n);
@@ -795,12 +823,14 @@ void DevicePrologue::run(cudaStream_t s, const b200pdlp_lp& lp, bool do_scale, i
   PREP_OK(cudaGetLastError());
   if (keep_form) keep_the_form();
   nvtxRangePop();
-  struct { double d[5]; int tb; } hfin;
+  struct { double d[5]; int tb; int sect[4]; } hfin;
   memset(&hfin, 0, sizeof(hfin));
   PREP_OK(cudaMemcpyAsync(hfin.d, dsc, 5 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  PREP_OK(cudaMemcpyAsync(hfin.sect, sect, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
   PREP_OK(cudaMemcpyAsync(&hfin.tb, too_big, sizeof(int), cudaMemcpyDeviceToHost, s));
   PREP_OK(cudaStreamSynchronize(s));   // the temporaries go back to the cache below: everything that reads them is done
   sc.norm_cost_sq = hfin.d[0]; sc.norm_rhs_sq = hfin.d[1]; sc.beta_cost_sq = hfin.d[2]; sc.beta_rhs_sq = hfin.d[3]; sc.amax = hfin.d[4];
+  sc.a_sectors = hfin.sect[0]; sc.a_lanes = hfin.sect[1]; sc.at_sectors = hfin.sect[2]; sc.at_lanes = hfin.sect[3];
   if (hfin.tb) throw std::runtime_error("b200pdlp: matrix too large for 32-bit slice offsets");
 }
 

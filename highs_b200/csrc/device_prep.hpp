@@ -37,6 +37,9 @@ struct PrepScalars {
   double norm_cost_sq = 0, norm_rhs_sq = 0;                  // unscaled cost (x sense) and rhs: sums of squares
   double beta_cost_sq = 0, beta_rhs_sq = 0;                  // the same sums over the SCALED data (PDHG_Init_Step_Sizes)
   double amax = 0;                                           // max |a_ij| after scaling
+  // sector sharing of the SpMV gathers, sampled over <= 4096 slices of each layout: distinct 32-byte sectors among the first
+  // column ids of a slice's live lanes, and the number of those lanes (1.0 = every gather its own sector, 0.25 = consecutive)
+  int a_sectors = 0, a_lanes = 0, at_sectors = 0, at_lanes = 0;
 };
 
 // what the prologue leaves on the device for the solve

@@ -444,7 +444,12 @@ static void apply_spmv_grid(b200pdlp_problem* p) {
   const int both = val("B200PDLP_SPMV_CTAS_PER_SM", -1);
   // measured (profiles/r02_experiments.md): the pipelined walk helps A'y (K3: 49.3 -> 44.6 us at 3 CTAs per SM) and hurts
   // A x (K2: 54.6 -> 56.5 us), so it is the default for A' only
-  const int ka = val("B200PDLP_SPMV_A_CTAS_PER_SM", both >= 0 ? both : 0);
+  // ... unless the matrix is structured: where a warp's gathers share sectors (the device prologue samples it: distinct
+  // 32-byte sectors per live lane, 1.0 on a uniformly random pattern, 0.25 on consecutive columns) the gather pipe is not
+  // the limit and the persistent shape wins 20 % on A x as well (S3D: K2 42.9 -> 34.7 us)
+  int ka_default = 0;
+  if (p->dev_form && p->prep.sc.a_lanes > 0 && 2 * p->prep.sc.a_sectors <= p->prep.sc.a_lanes) ka_default = 4;
+  const int ka = val("B200PDLP_SPMV_A_CTAS_PER_SM", both >= 0 ? both : ka_default);
   const int kat = val("B200PDLP_SPMV_AT_CTAS_PER_SM", both >= 0 ? both : 3);
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
@@ -663,6 +668,9 @@ static void create_problem_device(const b200pdlp_lp& lp, const b200pdlp_params& 
   }
   lap("setup", "device prologue");
   DevicePrologue& P = p->prep;
+  if (getenv("B200PDLP_TIMING"))
+    fprintf(stderr, "[b200pdlp setup] sectors per gathered lane (sampled): A %.3f  A' %.3f\n",
+            P.sc.a_lanes ? (double)P.sc.a_sectors / P.sc.a_lanes : 0.0, P.sc.at_lanes ? (double)P.sc.at_sectors / P.sc.at_lanes : 0.0);
   StdForm& f = p->form;
   f = StdForm();
   f.n = P.arr.n; f.m = P.arr.m; f.nnz = P.arr.nnz; f.neq = P.arr.neq; f.n_orig = P.arr.n0;
@@ -1798,7 +1806,13 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
     // device order -> standard-form order
     std::vector<double> t(std::max<size_t>(std::max(n, std::max(ml, 1)), p->xfull.n));
     const bool dbg = p->world > 1 && getenv("B200PDLP_DEBUG_MG") != nullptr;
-    const bool rendezvous = p->local_link && p->group && getenv("B200PDLP_LOCAL_RENDEZVOUS") != nullptr;   // experiment
+    // Logical shards share ONE CUDA context: a context-synchronising driver call on one rank's host thread (a pageable copy
+    // that needs staging memory, a lazy module load, an allocation) waits for every running kernel, including a peer's
+    // barrier kernel that is spinning for THIS rank's next launch -- a deadlock that only the barrier's timeout breaks
+    // (measured, session G: the assembly then runs on with stale segments).  So with local links every host-blocking copy
+    // of the assembly sits between two host-side rendezvous, when no barrier kernel is in flight.  Separate processes
+    // (CUDA IPC) have separate contexts and do not need this.
+    const bool rendezvous = p->local_link && p->group;
     int dbg_stage = 0;
     auto dbg_segments = [&](const char* what) {
       if (!dbg) return;
@@ -1810,21 +1824,28 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
       }
       fprintf(stderr, "%s\n", line);
     };
+    // barrier of the assembly; with local links the ranks also meet on the host before AND after it (see above): nobody
+    // launches a kernel that spins for its peers while a peer's host may still sit in a blocking copy, and nobody starts a
+    // blocking copy while a peer's barrier kernel is still in flight
+    auto xchg = [&]() {
+      if (rendezvous) { CUDA_OK(cudaStreamSynchronize(s)); p->group->arrive_and_wait(); }
+      launch_p2p_exchange(s, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p);
+      p->launches++;
+      if (rendezvous) { CUDA_OK(cudaStreamSynchronize(s)); p->group->arrive_and_wait(); }
+    };
     auto down_col = [&](const double* d, std::vector<double>& h) {
       if (p->world == 1) {
         CUDA_OK(cudaMemcpyAsync(t.data(), d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
         CUDA_OK(cudaStreamSynchronize(s));
         for (int j = 0; j < n; j++) h[p->cperm[j]] = t[j];
       } else if (p->p2p && !p->comm) {
-        // no NCCL communicator (logical shards of one process): all-gather through the peers' xfull, with a
-        // barrier before anyone reads and one before anyone overwrites
+        // no NCCL communicator (logical shards of one process, or B200PDLP_NO_NCCL): all-gather through the peers' xfull,
+        // with a barrier before anyone reads and one before anyone overwrites
         launch_push_shard(s, d, nl, p->peers, p->world, p->rank, p->seg_len);
-        launch_p2p_exchange(s, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p);
-        if (rendezvous) { CUDA_OK(cudaStreamSynchronize(s)); p->group->arrive_and_wait(); }
+        p->launches++;
+        xchg();
         CUDA_OK(cudaMemcpyAsync(t.data(), p->xfull.p, p->xfull.n * sizeof(double), cudaMemcpyDeviceToHost, s));
-        if (rendezvous) { CUDA_OK(cudaStreamSynchronize(s)); p->group->arrive_and_wait(); }
-        launch_p2p_exchange(s, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p);
-        p->launches += 3;
+        xchg();
         CUDA_OK(cudaStreamSynchronize(s));
         dbg_segments("columns");
         for (int j = 0; j < n; j++) h[p->cperm[j]] = t[seg_pos(p, j)];
@@ -1850,12 +1871,10 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
         for (int c = 0; c < rounds; c++) {
           const int off = c * p->seg_len;
           launch_push_rows(s, p->redbuf.p + off, std::max(0, std::min(ml - off, p->seg_len)), p->peers, p->world, p->rank, p->seg_len);
-          launch_p2p_exchange(s, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p);
-          if (rendezvous) { CUDA_OK(cudaStreamSynchronize(s)); p->group->arrive_and_wait(); }
+          p->launches++;
+          xchg();
           CUDA_OK(cudaMemcpyAsync(t.data(), p->recv.p, (size_t)p->world * p->seg_len * sizeof(double), cudaMemcpyDeviceToHost, s));
-          if (rendezvous) { CUDA_OK(cudaStreamSynchronize(s)); p->group->arrive_and_wait(); }
-          launch_p2p_exchange(s, p->outs.p + 60, 0, p->peers, p->world, p->rank, p->epochs.p, p->fault.p);
-          p->launches += 3;
+          xchg();
           CUDA_OK(cudaStreamSynchronize(s));
           dbg_segments("rows");
           for (int g = 0; g < p->world; g++) {

@@ -727,6 +727,19 @@ push_rows_kernel(const double* __restrict__ src, int len, PeerPtrs pp, int world
   }
 }
 
+// Bounded wait of the cross-GPU barriers: a peer that has not arrived after kBarrierTimeoutNs raises the fault word (the host
+// turns it into an error) instead of hanging the device.  Measured in round 2: a spin COUNT of 2^26 is only 1-2 s of
+// ld.acquire.sys on an L2-resident flag -- too short for ranks whose hosts reach a barrier seconds apart.
+constexpr unsigned long long kBarrierTimeoutNs = 60ull * 1000000000ull;
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ bool barrier_expired(long long& spins, unsigned long long t0) {
+  return (++spins & 0xfff) == 0 && global_ns() - t0 > kBarrierTimeoutNs;
+}
+
 // barrier + all-reduce of k <= 32 scalars (k = 0: pure barrier): every rank writes its values into every
 // peer's mailbox (double-buffered by epoch parity), signals, waits, then adds all ranks' values in rank order
 constexpr int kBigBox = 32;
@@ -747,10 +760,11 @@ __global__ void p2p_exchange_kernel(double* vals, int k, PeerPtrs pp, int world,
     unsigned long long* theirs = pp.flags[lane] + 2 * kMaxPeers + rank;
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(e) : "memory");
     long long spins = 0;
+    const unsigned long long t0 = global_ns();
     unsigned long long seen = 0;
     do {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
-      if (++spins > (1LL << 26)) { *fault = 1; break; }
+      if (seen < e && barrier_expired(spins, t0)) { *fault = 1; break; }
     } while (seen < e);
   }
   __syncwarp();
@@ -837,10 +851,11 @@ p2p_barrier_kernel(int mode, PdhgState* st, const double* __restrict__ partials,
       asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(e) : "memory");
       if (lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_sig));
       long long spins = 0;
+      const unsigned long long t0 = global_ns();
       unsigned long long seen = 0;
       do {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
-        if (++spins > (1LL << 26)) { *fault = 1; break; }   // ~1 min: never hang the device
+        if (seen < e && barrier_expired(spins, t0)) { *fault = 1; break; }   // never hang the device
       } while (seen < e);
     }
     __syncwarp();
