@@ -381,7 +381,7 @@ def main():
             torch.cuda.synchronize()
 
     prob = engine.Problem(lp, rank=rank, world=world, device=local_rank)
-    # B200PDLP_NO_NCCL=1 (experiment, not yet run on hardware): no NCCL communicator at all -- the fused peer-memory path
+    # B200PDLP_NO_NCCL=1: no NCCL communicator at all -- the fused peer-memory path
     # also assembles the solution (push_rows_kernel); saves the communicator set-up inside the e2e region
     no_nccl = os.environ.get("B200PDLP_NO_NCCL", "0") == "1" and os.environ.get("B200PDLP_NO_P2P", "0") != "1"
     if world > 1:

@@ -1947,7 +1947,8 @@ static void solve_on_device(b200pdlp_problem* p, const b200pdlp_params& prm, con
 
 // =================================================================================================== HiPDLP mode
 // solveLpHiPdlp -> PDLPSolver::solve (/root/reference/highs/pdlp/hipdlp/pdhg.cc:494-707) on the device, single GPU.
-// STATUS: written after round 1's GPU budget was spent; compiled, not yet run on hardware.
+// STATUS (round 2): runs on hardware (tests/test_gpu_hipdlp.py, tests/test_gpu_dropin.py, bench.py --solver hipdlp); the
+// prologue of this mode is still the host's (host_prep_hipdlp.cpp).
 static void create_problem_hipdlp(const b200pdlp_lp& lp, const b200pdlp_hipdlp_params& prm, b200pdlp_problem* p) {
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);

@@ -5,8 +5,9 @@
 // behaviour of HiPdlpWrapper.cpp:26-141 -- reset status/info, read the options PDLPSolver::setup reads
 // (hipdlp/pdhg.cc:1783-1874), fill the HighsSolution, pdlp_iteration_count, invalidate the basis, map the termination
 // status -- and forwards the numerical work to b200pdlp_solve_hipdlp (include/b200pdlp.h).
-// STATUS: the device side of this mode has not run on hardware yet; oracle/build_ref.py --shim links it into a SEPARATE
-// library (oracle/_ref/libhighs_b200_hipdlp.so), the validated solver=pdlp drop-in (libhighs_b200.so) is untouched.
+// STATUS (round 2): runs on hardware (tests/test_gpu_dropin.py drives Highs::run() with solver=hipdlp through this shim);
+// oracle/build_ref.py --shim links it into a SEPARATE library (oracle/_ref/libhighs_b200_hipdlp.so) next to the solver=pdlp
+// drop-in (libhighs_b200.so).
 #include <algorithm>
 #include <cmath>
 

@@ -2167,7 +2167,7 @@ void launch_fill(cudaStream_t s, int len, double* v, double w) {
 // projection / reflection / blend of y -> A' y.  There is NO reduction and no step rule inside a step, so a block of
 // steps is a plain chain of kernels (graph) and the trajectory does not depend on any summation order; the reductions
 // live in the checks (fixed-point error, convergence test) every 40 steps.
-// STATUS: written after round 1's GPU budget was spent; compiled, not yet run on hardware (tests/test_gpu_hipdlp.py).
+// STATUS (round 2): bit-exact against the oracle on hardware (tests/test_gpu_hipdlp.py, ~160 solves).
 namespace b200 {
 
 __device__ __forceinline__ double std_max(double a, double b) { return a < b ? b : a; }   // std::max / std::min semantics

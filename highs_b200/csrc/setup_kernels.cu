@@ -15,8 +15,8 @@
 //     -prec-sqrt=true -prec-div=true; the file is compiled with -fmad=false like the rest), so the scaled
 //     data are bit-identical to host_prep.cpp::scale and to the reference.
 //
-// STATUS: written after this round's GPU budget was spent; compiled, not yet run on hardware.  Off by
-// default; tests/test_gpu_device_scaling.py compares it bit for bit with the host path.
+// STATUS (round 2): runs on hardware -- as the staged variants (device_scaling = 1, 2; tests/test_gpu_device_scaling.py compares
+// them bit for bit with the host path) and as the scaling stage of the device prologue (device_prep.cu, the default).
 #include "setup_kernels.hpp"
 
 #include <math.h>

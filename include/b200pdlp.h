@@ -232,7 +232,8 @@ int b200pdlp_hipdlp_form_create(const b200pdlp_lp* lp, int32_t scaling_mode, int
  * Parameters are the HighsOptions the reference's setup() reads (hipdlp/pdhg.cc:1783-1874).  term_code is B200PDLP_OPTIMAL or
  * B200PDLP_TIMELIMIT_OR_ITERLIMIT (term_iterate = 2 when it was the time limit); like the reference, a run that does not
  * converge returns x = y = 0 (the iterate is copied out only on convergence, pdhg.cc:784-899).
- * STATUS: written after round 1's GPU budget was spent -- compiled, not yet run on hardware. */
+ * STATUS (round 2): runs on hardware; tests/test_gpu_hipdlp.py (bit-exact against the oracle), tests/test_gpu_dropin.py (through
+ * the shim), bench.py --solver hipdlp. */
 typedef struct {
   double tolerance;           /* pdlp_optimality_tolerance, or kkt_tolerance when set */
   int32_t iter_limit;         /* pdlp_iteration_limit */
