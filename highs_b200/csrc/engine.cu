@@ -1247,9 +1247,9 @@ static int enqueue_check_device_mg(b200pdlp_problem* p, bool light) {
                             p->atyavg.p, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, st, ctl, rcol);
     launch_check_rows_sweep(s, false, ml, p->neq_local, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->ysum.p, p->axsum.p,
                             p->yavg.p, p->axavg.p, p->rhs.p, p->rowscale.p, st, ctl, rrow);
-    launch_reduce_partials(s, st, ctl, 20, rcol.partials, check_light_grid(nl, true), o, -1, 0);                       // o[0..19]
-    launch_reduce_partials(s, st, ctl, 8, rrow.partials, check_light_grid(ml, false), o + 20, /*flag_slot=*/8, 0);       // o[20..27], flag at o[28]
-    launches = 5;
+    launch_reduce_partials(s, st, ctl, 20, rcol.partials, check_light_grid(nl, true), o, /*flag_slot=*/8, 0,    // o[0..19]
+                           8, rrow.partials, check_light_grid(ml, false), o + 20);                             // o[20..27], flag at o[28]
+    launches = 4;
   } else {
     launch_check_light_off(s, st, ctl);
     launch_check_avg_x(s, nl, p->x[0].p, p->x[1].p, p->xsum.p, p->xavg.p, st, ctl);

@@ -1779,25 +1779,27 @@ static_assert(kFinishThreads == kPowTab, "one thread per power-table entry");
 // order; `flag_slot` >= 0: out[flag_slot] = 1 if this rank's host has raised the time-limit word (summed by the exchange)
 __global__ void __launch_bounds__(kStepThreads)
 reduce_partials_kernel(const PdhgState* __restrict__ st, const SolveCtl* __restrict__ ctl, int nacc,
-                       const double* __restrict__ partials, int nb, double* __restrict__ out, int flag_slot, int need_restart) {
+                       const double* __restrict__ partials, int nb, double* __restrict__ out, int flag_slot, int need_restart,
+                       int nacc2, const double* __restrict__ partials2, int nb2, double* __restrict__ out2) {
+  // one WARP per accumulator (nacc + nacc2 <= 32): lane-strided loads in a fixed order, shuffle tree, no block barrier
   if (!check_live(st, ctl)) return;
   if (need_restart && ctl->restart_choice == 0) return;
-  __shared__ double sm[kStepThreads / 32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int a = 0; a < nacc; a++) {
+  if (wid < nacc) {
+    const double* __restrict__ p = partials + (size_t)wid * nb;
     double s = 0.0;
-    for (int i = threadIdx.x; i < nb; i += kStepThreads) s += partials[(size_t)a * nb + i];
+    for (int i = lane; i < nb; i += 32) s += p[i];
     s = warp_sum(s);
-    __syncthreads();
-    if (lane == 0) sm[wid] = s;
-    __syncthreads();
-    if (wid == 0) {
-      double t = sm[lane];
-      t = warp_sum(t);
-      if (lane == 0) out[a] = t;
-    }
+    if (lane == 0) out[wid] = s;
+  } else if (wid < nacc + nacc2) {
+    const int a = wid - nacc;
+    const double* __restrict__ p = partials2 + (size_t)a * nb2;
+    double s = 0.0;
+    for (int i = lane; i < nb2; i += 32) s += p[i];
+    s = warp_sum(s);
+    if (lane == 0) out2[a] = s;
   }
-  if (threadIdx.x == 0 && flag_slot >= 0) out[flag_slot] = (ctl->time_flag && *ctl->time_flag) ? 1.0 : 0.0;
+  if (threadIdx.x == 0 && flag_slot >= 0) (nacc2 > 0 ? out2 : out)[flag_slot] = (ctl->time_flag && *ctl->time_flag) ? 1.0 : 0.0;
 }
 
 // sums2 != nullptr (several GPUs): the two restart sums were reduced and all-reduced already
@@ -2099,8 +2101,9 @@ void launch_spmv_check_rows_mg(cudaStream_t s, const DevSell& A, const PdhgState
   spmv_sell_kernel<CheckRowEpilogueT<false>><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, rs);
 }
 void launch_reduce_partials(cudaStream_t s, const PdhgState* st, const SolveCtl* ctl, int nacc, const double* partials, int nb,
-                            double* out, int flag_slot, int need_restart) {
-  reduce_partials_kernel<<<1, kStepThreads, 0, s>>>(st, ctl, nacc, partials, nb, out, flag_slot, need_restart);
+                            double* out, int flag_slot, int need_restart, int nacc2, const double* partials2, int nb2,
+                            double* out2) {
+  reduce_partials_kernel<<<1, kStepThreads, 0, s>>>(st, ctl, nacc, partials, nb, out, flag_slot, need_restart, nacc2, partials2, nb2, out2);
 }
 void launch_check_decide_sums(cudaStream_t s, PdhgState* st, SolveCtl* ctl, const double* outs) {
   check_decide_sums_kernel<<<1, 32, 0, s>>>(st, ctl, outs);

@@ -113,7 +113,8 @@ void launch_spmv_check_rows_mg(cudaStream_t s, const DevSell& A, const PdhgState
                                const double* y0, const double* y1, const double* ax0, const double* ax1, const double* yavg,
                                double* axavg, const double* b, const double* rsc, int neq, ReduceScratch rs);
 void launch_reduce_partials(cudaStream_t s, const PdhgState* st, const SolveCtl* ctl, int nacc, const double* partials, int nb,
-                            double* out, int flag_slot, int need_restart);
+                            double* out, int flag_slot /* in the LAST output array, or -1 */, int need_restart, int nacc2 = 0,
+                            const double* partials2 = nullptr, int nb2 = 0, double* out2 = nullptr);
 void launch_check_decide_sums(cudaStream_t s, PdhgState* st, SolveCtl* ctl, const double* outs);
 
 // ---- HiPDLP mode (reflected Halpern PDHG; pdhg_kernels.cu, last section)
