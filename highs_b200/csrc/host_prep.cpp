@@ -132,7 +132,7 @@ class Pool {
 }  // namespace
 
 // fn(chunk_index, begin, end) over [0, count) cut into host_threads() contiguous chunks
-static void parallel_chunks(long long count, const std::function<void(int, long long, long long)>& fn, long long min_per_thread = 1 << 15) {
+void parallel_chunks(long long count, const std::function<void(int, long long, long long)>& fn, long long min_per_thread) {
   int T = host_threads();
   if (count < 2 * min_per_thread) T = 1;
   T = (int)std::min<long long>(T, std::max<long long>(1, count / min_per_thread));

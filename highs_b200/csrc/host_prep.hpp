@@ -118,6 +118,8 @@ struct HipController {
   bool after_block(const double* s);
 };
 void build_row_index(StdForm& f);   // fills f.rptr / f.rpos (parallel counting sort)
+// fn(chunk_index, begin, end) over [0, count) cut into contiguous chunks, one per host thread of the persistent pool
+void parallel_chunks(long long count, const std::function<void(int, long long, long long)>& fn, long long min_per_thread = 1 << 15);
 void scale(StdForm& f, bool do_scale);
 // nnz-balanced contiguous partition of the m rows into `world` parts
 std::vector<int> partition_rows(const StdForm& f, int world);

@@ -74,18 +74,20 @@ void formulate_hipdlp(const b200pdlp_lp& lp, StdForm& f) {
   f.cval.resize(f.nnz);
   {
     // structural columns keep their entry count: column j starts at a_start[j]; entries sorted by (row, value) (:300-333)
-    std::vector<std::pair<int, double>> e;
-    for (int j = 0; j < n0; j++) {
-      e.clear();
-      for (int p = lp.a_start[j]; p < lp.a_start[j + 1]; p++) {
-        const int old = lp.a_index[p];
-        e.emplace_back(f.row_new_idx[old], f.row_class[old] == kLeq ? -lp.a_value[p] : lp.a_value[p]);
+    parallel_chunks(n0, [&](int, long long j0, long long j1) {   // columns are independent
+      std::vector<std::pair<int, double>> e;
+      for (int j = (int)j0; j < (int)j1; j++) {
+        e.clear();
+        for (int p = lp.a_start[j]; p < lp.a_start[j + 1]; p++) {
+          const int old = lp.a_index[p];
+          e.emplace_back(f.row_new_idx[old], f.row_class[old] == kLeq ? -lp.a_value[p] : lp.a_value[p]);
+        }
+        std::sort(e.begin(), e.end());
+        int k = lp.a_start[j];
+        f.cbeg[j] = k;
+        for (const auto& t : e) { f.cidx[k] = t.first; f.cval[k] = t.second; k++; }
       }
-      std::sort(e.begin(), e.end());
-      int k = lp.a_start[j];
-      f.cbeg[j] = k;
-      for (const auto& t : e) { f.cidx[k] = t.first; f.cval[k] = t.second; k++; }
-    }
+    }, 1 << 12);
   }
   int k = nnz0, j = n0;
   for (int i = 0; i < m; i++) {   // one slack column per BOUND / FREE row: A x - z = 0, z in the row's bounds (:235-244,336-346)
@@ -113,21 +115,35 @@ namespace {
 // one pass's factors into the data (Scaling::applyScaling, scaling.cc:232-263) and into the running scales
 void apply_hipdlp(StdForm& f, const std::vector<double>& cs, const std::vector<double>& rs) {
   const double inf = std::numeric_limits<double>::infinity();
-  for (int i = 0; i < f.n; i++) {
-    f.cost[i] /= cs[i];
-    if (f.lower[i] > -inf) f.lower[i] *= cs[i];
-    if (f.upper[i] < inf) f.upper[i] *= cs[i];
-    f.col_scale[i] *= cs[i];
-  }
-  for (int i = 0; i < f.m; i++) {
-    if (f.rhs[i] > -inf) f.rhs[i] /= rs[i];
-    if (f.row_upper[i] < inf) f.row_upper[i] /= rs[i];
-    f.row_scale[i] *= rs[i];
-  }
-  for (int c = 0; c < f.n; c++) {
-    const double cc = cs[c];
-    for (int p = f.cbeg[c]; p < f.cbeg[c + 1]; p++) f.cval[p] /= (rs[f.cidx[p]] * cc);
-  }
+  parallel_chunks(f.n, [&](int, long long b, long long e) {
+    for (int i = (int)b; i < (int)e; i++) {
+      f.cost[i] /= cs[i];
+      if (f.lower[i] > -inf) f.lower[i] *= cs[i];
+      if (f.upper[i] < inf) f.upper[i] *= cs[i];
+      f.col_scale[i] *= cs[i];
+      const double cc = cs[i];
+      for (int p = f.cbeg[i]; p < f.cbeg[i + 1]; p++) f.cval[p] /= (rs[f.cidx[p]] * cc);
+    }
+  }, 1 << 12);
+  parallel_chunks(f.m, [&](int, long long b, long long e) {
+    for (int i = (int)b; i < (int)e; i++) {
+      if (f.rhs[i] > -inf) f.rhs[i] /= rs[i];
+      if (f.row_upper[i] < inf) f.row_upper[i] /= rs[i];
+      f.row_scale[i] *= rs[i];
+    }
+  }, 1 << 14);
+}
+// per-row reductions in the order of the reference's column-major scatter (rs[row] op= term, columns ascending) = the row's
+// entries in row-major order: the row index (build_row_index) gives that order, so rows can be done in parallel
+template <class Term, class Op>
+void row_reduce(const StdForm& f, std::vector<double>& rs, Term term, Op op) {
+  parallel_chunks(f.m, [&](int, long long b, long long e) {
+    for (int i = (int)b; i < (int)e; i++) {
+      double a = 0.0;
+      for (int q = f.rptr[i]; q < f.rptr[i + 1]; q++) a = op(a, term(f.cval[f.rpos[q]]));
+      rs[i] = a;
+    }
+  }, 1 << 12);
 }
 }  // namespace
 
@@ -135,55 +151,60 @@ void scale_hipdlp(StdForm& f, int scaling_mode, int ruiz_iterations) {
   const int n = f.n, m = f.m;
   std::vector<double> cs(n), rs(m);
   f.scaled = false;
+  if ((scaling_mode & 7) && f.rptr.empty() && f.nnz > 0) build_row_index(f);   // row-major order of the entries (positions into cval)
+  const auto fmax = [](double a, double v) { return std::max(a, v); };
+  const auto fadd = [](double a, double v) { return a + v; };
   if (scaling_mode & 1) {   // Ruiz, infinity norm (scaling.cc:56-125)
     for (int it = 0; it < ruiz_iterations; it++) {
-      std::fill(rs.begin(), rs.end(), 0.0);
-      for (int c = 0; c < n; c++) {
-        double mx = 0.0;
-        for (int p = f.cbeg[c]; p < f.cbeg[c + 1]; p++) {
-          const double a = std::fabs(f.cval[p]);
-          mx = std::max(mx, a);
-          rs[f.cidx[p]] = std::max(rs[f.cidx[p]], a);
+      parallel_chunks(n, [&](int, long long b, long long e) {
+        for (int c = (int)b; c < (int)e; c++) {
+          double mx = 0.0;
+          for (int p = f.cbeg[c]; p < f.cbeg[c + 1]; p++) mx = std::max(mx, std::fabs(f.cval[p]));
+          double v = (f.cbeg[c] < f.cbeg[c + 1]) ? std::sqrt(mx) : 0.0;
+          if (v == 0.0) v = 1.0;
+          cs[c] = v;
         }
-        double v = (f.cbeg[c] < f.cbeg[c + 1]) ? std::sqrt(mx) : 0.0;
-        if (v == 0.0) v = 1.0;
-        cs[c] = v;
-      }
-      for (int i = 0; i < m; i++) rs[i] = (rs[i] == 0.0) ? 1.0 : std::sqrt(rs[i]);
+      }, 1 << 12);
+      row_reduce(f, rs, [](double v) { return std::fabs(v); }, fmax);
+      parallel_chunks(m, [&](int, long long b, long long e) {
+        for (int i = (int)b; i < (int)e; i++) rs[i] = (rs[i] == 0.0) ? 1.0 : std::sqrt(rs[i]);
+      }, 1 << 14);
       apply_hipdlp(f, cs, rs);
     }
     f.scaled = true;
   }
   if (scaling_mode & 4) {   // Pock-Chambolle, alpha = 1 (:127-178); pow() kept as in the reference
     const double alpha = 1.0;
-    std::fill(rs.begin(), rs.end(), 0.0);
-    for (int c = 0; c < n; c++) {
-      double sum = 0.0;
-      for (int p = f.cbeg[c]; p < f.cbeg[c + 1]; p++) {
-        sum += std::pow(std::fabs(f.cval[p]), alpha);
-        rs[f.cidx[p]] += std::pow(std::fabs(f.cval[p]), 2.0 - alpha);
+    parallel_chunks(n, [&](int, long long b, long long e) {
+      for (int c = (int)b; c < (int)e; c++) {
+        double sum = 0.0;
+        for (int p = f.cbeg[c]; p < f.cbeg[c + 1]; p++) sum += std::pow(std::fabs(f.cval[p]), alpha);
+        cs[c] = sum > 0.0 ? std::sqrt(std::pow(sum, 1.0 / alpha)) : 1.0;
       }
-      cs[c] = sum > 0.0 ? std::sqrt(std::pow(sum, 1.0 / alpha)) : 1.0;
-    }
-    for (int i = 0; i < m; i++) rs[i] = rs[i] > 0.0 ? std::sqrt(std::pow(rs[i], 1.0 / (2.0 - alpha))) : 1.0;
+    }, 1 << 12);
+    row_reduce(f, rs, [&](double v) { return std::pow(std::fabs(v), 2.0 - alpha); }, fadd);
+    parallel_chunks(m, [&](int, long long b, long long e) {
+      for (int i = (int)b; i < (int)e; i++) rs[i] = rs[i] > 0.0 ? std::sqrt(std::pow(rs[i], 1.0 / (2.0 - alpha))) : 1.0;
+    }, 1 << 14);
     apply_hipdlp(f, cs, rs);
     f.scaled = true;
   }
   if (scaling_mode & 2) {   // L2 (:180-230)
-    std::fill(rs.begin(), rs.end(), 0.0);
-    for (int c = 0; c < n; c++) {
-      double sq = 0.0;
-      for (int p = f.cbeg[c]; p < f.cbeg[c + 1]; p++) {
-        sq += f.cval[p] * f.cval[p];
-        rs[f.cidx[p]] += f.cval[p] * f.cval[p];
+    parallel_chunks(n, [&](int, long long b, long long e) {
+      for (int c = (int)b; c < (int)e; c++) {
+        double sq = 0.0;
+        for (int p = f.cbeg[c]; p < f.cbeg[c + 1]; p++) sq += f.cval[p] * f.cval[p];
+        cs[c] = sq > 0.0 ? std::sqrt(std::sqrt(sq)) : 1.0;
       }
-      cs[c] = sq > 0.0 ? std::sqrt(std::sqrt(sq)) : 1.0;
-    }
-    for (int i = 0; i < m; i++) rs[i] = rs[i] > 0.0 ? std::sqrt(std::sqrt(rs[i])) : 1.0;
+    }, 1 << 12);
+    row_reduce(f, rs, [](double v) { return v * v; }, fadd);
+    parallel_chunks(m, [&](int, long long b, long long e) {
+      for (int i = (int)b; i < (int)e; i++) rs[i] = rs[i] > 0.0 ? std::sqrt(std::sqrt(rs[i])) : 1.0;
+    }, 1 << 14);
     apply_hipdlp(f, cs, rs);
     f.scaled = true;
   }
-  double amax = 0.0;
+  double amax = 0.0;   // (max is order-free)
   for (int p = 0; p < f.nnz; p++) amax = std::max(amax, std::fabs(f.cval[p]));
   f.amax = amax;
 }
