@@ -744,8 +744,9 @@ __device__ __forceinline__ bool barrier_expired(long long& spins, unsigned long 
 // peer's mailbox (double-buffered by epoch parity), signals, waits, then adds all ranks' values in rank order
 constexpr int kBigBox = 32;
 __global__ void p2p_exchange_kernel(double* vals, int k, PeerPtrs pp, int world, int rank, unsigned long long* epochs,
-                                    int* fault, const PdhgState* due) {
+                                    int* fault, const PdhgState* due, const SolveCtl* only_if_restart) {
   if (check_not_due(due)) return;   // identical on every rank
+  if (only_if_restart && only_if_restart->restart_choice == 0) return;   // (the choice is identical on every rank too)
   if (*reinterpret_cast<volatile int*>(fault)) return;   // a barrier already timed out: do not wait another minute per launch
   const int lane = threadIdx.x;
   unsigned long long e = 0;
@@ -1542,6 +1543,8 @@ __device__ void trace_row_dev(SolveCtl* c, const PdhgState* st, int restart) {
   c->trace_len++;
 }
 
+constexpr int kFinishThreads = 128;
+static_assert(kFinishThreads == kPowTab, "one thread per power-table entry");
 // the scalar part of C6 (one thread): restart scalars when a restart was chosen, trace row, next check iteration
 __device__ void finish_scalars(PdhgState* st, SolveCtl* ctl, int choice, const double* d2, int step_iter) {
   if (choice) {
@@ -1638,12 +1641,22 @@ check_decide_kernel(PdhgState* __restrict__ st, SolveCtl* __restrict__ ctl, cons
 
 // several GPUs: the 28 sums were all-reduced over the ranks (identical on every rank, added in rank order) into
 // outs[0..19] (column side, 10 per iterate), outs[20..27] (row side, 4 per iterate), outs[28] (# ranks past the time limit)
-__global__ void check_decide_sums_kernel(PdhgState* __restrict__ st, SolveCtl* __restrict__ ctl, const double* __restrict__ outs) {
-  if (threadIdx.x != 0 || !check_live(st, ctl)) return;
-  double tot[kCheckSums];
-  for (int a = 0; a < 8; a++) tot[a] = outs[20 + a];
-  for (int a = 0; a < 20; a++) tot[8 + a] = outs[a];
-  decide_from_sums(st, ctl, tot, outs[28] > 0.0);
+__global__ void __launch_bounds__(kFinishThreads)
+check_decide_sums_kernel(PdhgState* __restrict__ st, SolveCtl* __restrict__ ctl, const double* __restrict__ outs) {
+  if (!check_live(st, ctl)) return;
+  __shared__ int inline_finish;
+  const int step_iter = st->step_iter;
+  if (threadIdx.x == 0) {
+    double tot[kCheckSums];
+    for (int a = 0; a < 8; a++) tot[a] = outs[20 + a];
+    for (int a = 0; a < 20; a++) tot[8 + a] = outs[a];
+    decide_from_sums(st, ctl, tot, outs[28] > 0.0);
+    // no restart, not finished: C6's bookkeeping right here (the restart exchange and C6 then have nothing to do)
+    inline_finish = (ctl->term < 0 && ctl->restart_choice == 0) ? 1 : 0;
+    if (inline_finish) { const double d2[2] = {0.0, 0.0}; finish_scalars(st, ctl, 0, d2, step_iter); }
+  }
+  __syncthreads();
+  if (inline_finish) finish_pow_tables(st, step_iter);
 }
 
 __device__ void decide_from_sums(PdhgState* st, SolveCtl* ctl, const double* tot, bool timed_out) {
@@ -1773,8 +1786,6 @@ restart_sweep_kernel(int n, int m, double* __restrict__ x0, double* __restrict__
 
 // C6: the scalar part of the restart (PDHG_Compute_Step_Size_Ratio, cupdlp_step.c:147-176), then the bookkeeping the
 // host loop does after a check: trace row, next check iteration (cupdlp_solver.c:953-962), step-rule power tables
-constexpr int kFinishThreads = 128;
-static_assert(kFinishThreads == kPowTab, "one thread per power-table entry");
 // several GPUs: block partials of the epilogue sums (acc-major, nb per accumulator) -> nacc scalars at out[], added in block
 // order; `flag_slot` >= 0: out[flag_slot] = 1 if this rank's host has raised the time-limit word (summed by the exchange)
 __global__ void __launch_bounds__(kStepThreads)
@@ -1958,8 +1969,8 @@ void launch_push_rows(cudaStream_t s, const double* src, int len, const PeerPtrs
   push_rows_kernel<<<ew_grid(len), kThreads, 0, s>>>(src, len, pp, world, rank, seg_len);
 }
 void launch_p2p_exchange(cudaStream_t s, double* vals, int k, const PeerPtrs& pp, int world, int rank,
-                         unsigned long long* epochs, int* fault, const PdhgState* due) {
-  p2p_exchange_kernel<<<1, 32, 0, s>>>(vals, k, pp, world, rank, epochs, fault, due);
+                         unsigned long long* epochs, int* fault, const PdhgState* due, const SolveCtl* only_if_restart) {
+  p2p_exchange_kernel<<<1, 32, 0, s>>>(vals, k, pp, world, rank, epochs, fault, due, only_if_restart);
 }
 void launch_reduce_part_p2p(cudaStream_t s, int len, double* dst, const PeerPtrs& pp, int world, int rank, int seg_len,
                             int pull, const PdhgState* due, int only_if_accepted) {
@@ -2106,7 +2117,7 @@ void launch_reduce_partials(cudaStream_t s, const PdhgState* st, const SolveCtl*
   reduce_partials_kernel<<<1, kStepThreads, 0, s>>>(st, ctl, nacc, partials, nb, out, flag_slot, need_restart, nacc2, partials2, nb2, out2);
 }
 void launch_check_decide_sums(cudaStream_t s, PdhgState* st, SolveCtl* ctl, const double* outs) {
-  check_decide_sums_kernel<<<1, 32, 0, s>>>(st, ctl, outs);
+  check_decide_sums_kernel<<<1, kFinishThreads, 0, s>>>(st, ctl, outs);
 }
 
 

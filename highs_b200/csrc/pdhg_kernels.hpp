@@ -37,7 +37,8 @@ void launch_push_shard(cudaStream_t s, const double* src, int len, const PeerPtr
                        const PdhgState* due = nullptr);
 void launch_push_rows(cudaStream_t s, const double* src, int len, const PeerPtrs& pp, int world, int rank, int seg_len);
 void launch_p2p_exchange(cudaStream_t s, double* vals, int k, const PeerPtrs& pp, int world, int rank,
-                         unsigned long long* epochs, int* fault, const PdhgState* due = nullptr);
+                         unsigned long long* epochs, int* fault, const PdhgState* due = nullptr,
+                         const SolveCtl* only_if_restart = nullptr /* skip (on every rank alike) unless the check chose a restart */);
 void launch_push_part(cudaStream_t s, PdhgState* st, const double* part, const PeerPtrs& pp, int world, int rank, int seg_len);
 void launch_reduce_part_p2p(cudaStream_t s, int len, double* dst, const PeerPtrs& pp, int world, int rank, int seg_len,
                             int pull, const PdhgState* due = nullptr, int only_if_accepted = 0);
