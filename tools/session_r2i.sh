@@ -4,16 +4,16 @@
 set -u
 mkdir -p gpurun_out/r2i
 O=gpurun_out/r2i
-run() { local name=$1; shift; echo "=== $name: $*"; ( timeout "${T:-400}" "$@" ) > "$O/$name.log" 2> "$O/$name.err"; echo "    exit $?"; tail -n 2 "$O/$name.log" | cut -c1-400; }
-tr() { local n=$1 port=$2; shift 2; python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port "$port" bench.py --gpus "$n" "$@"; }
+# (the helper must not be called `tr`: `timeout tr ...` runs /usr/bin/tr -- session D lost its bench lines to that)
+mg() { local name=$1 n=$2 port=$3; shift 3; echo "=== $name: bench.py --gpus $n $*"; timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port "$port" bench.py --gpus "$n" "$@" > "$O/$name.log" 2> "$O/$name.err"; echo "    exit $?"; tail -n 1 "$O/$name.log" | cut -c1-400; }
 nvidia-smi -L | head -8
-run bench8_s20 tr 8 29801 --no-cpu-baseline --steps 20 --warmup 5 --parity
-run bench8 tr 8 29802 --no-cpu-baseline
-run bench8_s5 tr 8 29803 --workload S5 --no-cpu-baseline --parity
-run bench4_s20 tr 4 29804 --no-cpu-baseline --steps 20 --warmup 5
-run bench4 tr 4 29805 --no-cpu-baseline
-run bench2_s20 tr 2 29806 --no-cpu-baseline --steps 20 --warmup 5
-run bench2 tr 2 29807 --no-cpu-baseline
-run bench1_s20 python bench.py --no-cpu-baseline --steps 20 --warmup 5
-B200PDLP_MG_DEVICE_CHECK=0 run bench8_hostcheck_s20 tr 8 29808 --no-cpu-baseline --steps 20 --warmup 5
+mg bench8_s20 8 29801 --no-cpu-baseline --steps 20 --warmup 5 --parity
+mg bench8 8 29802 --no-cpu-baseline
+mg bench8_s5 8 29803 --workload S5 --no-cpu-baseline --parity
+mg bench4_s20 4 29804 --no-cpu-baseline --steps 20 --warmup 5
+mg bench4 4 29805 --no-cpu-baseline
+mg bench2_s20 2 29806 --no-cpu-baseline --steps 20 --warmup 5
+mg bench2 2 29807 --no-cpu-baseline
+echo "=== bench1_s20"; timeout 300 python bench.py --no-cpu-baseline --steps 20 --warmup 5 > $O/bench1_s20.log 2> $O/bench1_s20.err
+B200PDLP_MG_DEVICE_CHECK=0 mg bench8_hostcheck_s20 8 29808 --no-cpu-baseline --steps 20 --warmup 5
 grep -h '"metric"' $O/bench*.log | cut -c1-1500
