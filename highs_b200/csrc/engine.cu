@@ -1219,9 +1219,10 @@ static bool use_device_checks(const b200pdlp_problem* p, const b200pdlp_params& 
   if (p->world != 1) {
     // several GPUs: only on the fused peer-memory path (the checks' collectives are our own barrier / exchange kernels)
     if (!(p->p2p && p->p2p_pull)) return false;
-    // opt-in until it has passed on hardware (tests/test_gpu_logical_shards.py, tests/test_gpu_multi.py run both settings)
+    // default since it passed on hardware against the oracle (2 GPUs: tests/test_gpu_multi.py; 2 / 3 / 4 logical shards:
+    // tests/test_gpu_logical_shards.py; both run both settings).  B200PDLP_MG_DEVICE_CHECK=0: round 1's host-driven checks.
     const char* e = getenv("B200PDLP_MG_DEVICE_CHECK");
-    if (!e || atoi(e) == 0) return false;
+    if (e && atoi(e) == 0) return false;
   }
   if (const char* e = getenv("B200PDLP_HOST_CHECK")) if (atoi(e) != 0) return false;   // the round-1 host-driven checks
   return true;

@@ -45,8 +45,20 @@ dist.destroy_process_group()
 ''' % ROOT
 
 
-@pytest.mark.parametrize("mode", ["p2p", "nccl"])
-def test_two_gpu_row_partition(engine_lib, oracle, tmp_path, mode):
+_ORACLE = {}
+
+
+def _oracle_runs(oracle, lp):
+    """the two oracle solves all variants are compared with (minutes of CPU: once per session)"""
+    if not _ORACLE:
+        _ORACLE["conv"] = oracle.solve(lp, tol_primal=1e-7, tol_dual=1e-7, tol_gap=1e-7, iter_limit=200000)
+        _ORACLE["fix"] = oracle.solve(lp, iter_limit=121)
+    return _ORACLE["conv"], _ORACLE["fix"]
+
+
+@pytest.mark.parametrize("mode,devcheck", [("p2p", 1), ("p2p", 0), ("nccl", 0)],
+                         ids=["p2p-device_checks", "p2p-host_checks", "nccl-host_checks"])
+def test_two_gpu_row_partition(engine_lib, oracle, tmp_path, mode, devcheck):
     from highs_b200 import engine
     from highs_b200.lp import synthetic_lp
     if engine.device_count() < 2:
@@ -55,12 +67,13 @@ def test_two_gpu_row_partition(engine_lib, oracle, tmp_path, mode):
     w.write_text(WORKER)
     out = tmp_path / "res.npz"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29611" if mode == "p2p" else "29612", str(w), str(out), mode]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+           "--master-port", str(29611 + 2 * devcheck + (mode == "nccl")), str(w), str(out), mode]
+    env = dict(os.environ, B200PDLP_MG_DEVICE_CHECK=str(devcheck))   # device-side (+ light) checks, or round 1's host-driven ones
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stderr[-3000:]
     multi = dict(np.load(out))
     lp = synthetic_lp(30000, 24000, 6, 17, dense_col_nnz=9000)
-    orc = oracle.solve(lp, tol_primal=1e-7, tol_dual=1e-7, tol_gap=1e-7, iter_limit=200000)
+    orc, fix = _oracle_runs(oracle, lp)
     assert int(multi["term"]) == orc["term_code"] == 0
     o1, o2 = lp.objectiveValue(multi["col_value"]), lp.objectiveValue(orc["col_value"])
     assert abs(o1 - o2) <= 1e-6 * (1 + abs(o2))     # north-star criterion: objective to 1e-6 relative
@@ -69,7 +82,6 @@ def test_two_gpu_row_partition(engine_lib, oracle, tmp_path, mode):
     assert 0.5 * orc["iters"] <= int(multi["iters"]) <= 2.0 * orc["iters"] + 80
     # 120 iterations from the same start: the multi-GPU step rule takes the interaction term on the row side
     # (DESIGN.md section 5), identical in exact arithmetic -- the iterates agree up to rounding propagation
-    fix = oracle.solve(lp, iter_limit=121)
     assert int(multi["fix_iters"]) == fix["iters"]
     for k in ("col_value", "row_dual"):
         assert np.abs(multi["fix_" + k] - fix[k]).max() <= 1e-6 * (1 + np.abs(fix[k]).max()), k
