@@ -383,7 +383,8 @@ def main():
     prob = engine.Problem(lp, rank=rank, world=world, device=local_rank)
     # B200PDLP_NO_NCCL=1: no NCCL communicator at all -- the fused peer-memory path
     # also assembles the solution (push_rows_kernel); saves the communicator set-up inside the e2e region
-    no_nccl = os.environ.get("B200PDLP_NO_NCCL", "0") == "1" and os.environ.get("B200PDLP_NO_P2P", "0") != "1"
+    # (default since session D' of round 2; B200PDLP_NO_NCCL=0 brings the communicator back, B200PDLP_NO_P2P=1 needs it)
+    no_nccl = os.environ.get("B200PDLP_NO_NCCL", "1") == "1" and os.environ.get("B200PDLP_NO_P2P", "0") != "1"
     if world > 1:
         if not no_nccl:
             ids = [engine.nccl_unique_id() if rank == 0 else None]
@@ -519,8 +520,9 @@ def main():
         h2d = (2 * (12 * nnz + 4 * (n + m)) + 8 * (5 * n + 3 * m)) / world
         e2e = {"value": K / e2e_wall, "unit": "iter/s", "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": 8 * (2 * n + 2 * m) / K,
                "wall_seconds": e2e_wall, "solve_seconds": r2["solve_seconds"],
-               "note": "per rank: Problem create (formulate+scale+layout on the host, H2D of its shard), NCCL communicator + "
-                       "CUDA-IPC peer mapping, K iterations, gather + D2H of the solution; max over ranks"}
+               "note": "per rank: Problem create (formulate + scale on the rank's GPU unless B200PDLP_MG_DEVICE_PREP=0, its layouts on "
+                       "the host, H2D of its shard), " + ("" if no_nccl else "NCCL communicator + ")
+                       + "CUDA-IPC peer mapping, K iterations, gather + D2H of the solution; max over ranks"}
         if use_p2p:
             prob2.p2p_release()
         barrier()

@@ -466,7 +466,7 @@ static void alloc_host_mirrors(b200pdlp_problem* p) {
   p->hflag = static_cast<double*>(pinned_cache_alloc(4 * sizeof(double), false));   // [0] time-limit flag, [2] read-back of the barrier fault word
 }
 
-// Several GPUs (opt-in B200PDLP_MG_DEVICE_PREP=1): every rank needs the whole scaled standard form to cut its shard out of
+// Several GPUs (default; B200PDLP_MG_DEVICE_PREP=0 for the host path): every rank needs the whole scaled standard form to cut its shard out of
 // it.  Instead of G processes running the host prologue side by side (they share the host's cores and memory bandwidth),
 // each rank formulates and scales on ITS GPU (a few milliseconds, identical bits on every rank) and downloads the result;
 // the per-rank layouts are then built by the host as before.
@@ -524,8 +524,11 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   int dev_level = prm.device_scaling;
   if (const char* e = getenv("B200PDLP_DEVICE_SETUP")) dev_level = atoi(e);   // experiments: same switch from the environment
   bool mg_dev_form = false;
-  if (!shared_form && world > 1 && lp.num_row > 0 && lp.num_col > 0 && lp.a_start[lp.num_col] > 0)
+  if (!shared_form && world > 1 && lp.num_row > 0 && lp.num_col > 0 && lp.a_start[lp.num_col] > 0) {
+    // default since session D' (2 GPUs, S3 and S5, parity block ok): B200PDLP_MG_DEVICE_PREP=0 keeps the host formulate + scale
+    mg_dev_form = true;
     if (const char* ev = getenv("B200PDLP_MG_DEVICE_PREP")) mg_dev_form = atoi(ev) != 0;
+  }
   if (shared_form) {
     p->form = *shared_form;
     lap("copy of the scaled form");
