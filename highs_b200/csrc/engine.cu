@@ -253,6 +253,10 @@ struct b200pdlp_problem {
   DevBuf<unsigned long long> flags, epochs;
   DevBuf<int> fault;
   cudaStream_t stream = nullptr;
+  // side stream + fork/join events: the two residual sweeps of a check are independent and neither fills the device
+  // (296 / 592 CTAs), so they run next to each other (inside the check's graph: two branches)
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // n-vectors (replicated across ranks)
   DevBuf<double> x[2], aty[2], xsum, xavg, atyavg, xlr, cost, lower, upper, colscale;
   // m_local-vectors
@@ -305,6 +309,9 @@ struct b200pdlp_problem {
     if (hstate) pinned_cache_free(hstate);
     if (houts) pinned_cache_free(houts);
     if (hflag) pinned_cache_free(hflag);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (side_stream) cudaStreamDestroy(side_stream);
     if (stream) cudaStreamDestroy(stream);
   }
   ReduceScratch rs(int slot, int len) const {
@@ -1280,6 +1287,22 @@ static int enqueue_check_device_mg(b200pdlp_problem* p, bool light) {
   return launches + 6;
 }
 
+// run `a` on the problem's stream and `b` next to it on the side stream (graph capture turns this into two branches)
+template <class FA, class FB>
+static void run_side_by_side(b200pdlp_problem* p, FA&& a, FB&& b) {
+  if (!p->side_stream) {
+    CUDA_OK(cudaStreamCreateWithFlags(&p->side_stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+  }
+  CUDA_OK(cudaEventRecord(p->ev_fork, p->stream));
+  CUDA_OK(cudaStreamWaitEvent(p->side_stream, p->ev_fork, 0));
+  b(p->side_stream);
+  CUDA_OK(cudaEventRecord(p->ev_join, p->side_stream));
+  a(p->stream);
+  CUDA_OK(cudaStreamWaitEvent(p->stream, p->ev_join, 0));
+}
+
 // the six launches of one check (pdhg_kernels.cu "device-side check iteration"); no-ops unless the check is due.
 // light: the dense-check phase's variant (five launches: two sweeps over the carried A xSum / A'ySum instead of C1-C3)
 static int enqueue_check_device(b200pdlp_problem* p, bool light = false) {
@@ -1289,21 +1312,27 @@ static int enqueue_check_device(b200pdlp_problem* p, bool light = false) {
   SolveCtl* ctl = p->ctl.p;
   const int n = p->n, ml = p->ml;
   const ReduceScratch rrow = p->rs(kSlotChk, ml), rcol = p->rs(kSlotK3, n), rrst = p->rs(kSlotK1, n);
+  const bool given = !light;
+  auto sweeps = [&]() {
+    run_side_by_side(p,
+        [&](cudaStream_t q) {
+          launch_check_cols_sweep(q, given, n, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->xsum.p, p->atysum.p, p->xavg.p,
+                                  p->atyavg.p, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, st, ctl, rcol);
+        },
+        [&](cudaStream_t q) {
+          launch_check_rows_sweep(q, given, ml, p->neq_local, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->ysum.p, p->axsum.p,
+                                  p->yavg.p, p->axavg.p, p->rhs.p, p->rowscale.p, st, ctl, rrow);
+        });
+  };
   if (light) {
-    launch_check_cols_sweep(s, false, n, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->xsum.p, p->atysum.p, p->xavg.p,
-                            p->atyavg.p, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, st, ctl, rcol);
-    launch_check_rows_sweep(s, false, ml, p->neq_local, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->ysum.p, p->axsum.p,
-                            p->yavg.p, p->axavg.p, p->rhs.p, p->rowscale.p, st, ctl, rrow);
+    sweeps();
     launch_check_decide(s, st, ctl, rrow.partials, check_light_grid(ml, false), rcol.partials, check_light_grid(n, true), rrow.counter);
   } else if (!p->fused_check) {
     // split check: averages, two plain SpMV (as fast as the pass kernels), two vector sweeps for the 20 + 8 sums
     launch_check_avg_xy(s, n, ml, p->x[0].p, p->x[1].p, p->xsum.p, p->xavg.p, p->y[0].p, p->y[1].p, p->ysum.p, p->yavg.p, st, ctl);
-    launch_spmv_plain(s, p->A.dev, p->xavg.p, p->axavg.p, st);
-    launch_spmv_plain(s, p->AT.dev, p->yavg.p, p->atyavg.p, st);
-    launch_check_cols_sweep(s, true, n, p->x[0].p, p->x[1].p, p->aty[0].p, p->aty[1].p, p->xsum.p, p->atysum.p, p->xavg.p,
-                            p->atyavg.p, p->cost.p, p->lower.p, p->upper.p, p->colscale.p, st, ctl, rcol);
-    launch_check_rows_sweep(s, true, ml, p->neq_local, p->y[0].p, p->y[1].p, p->ax[0].p, p->ax[1].p, p->ysum.p, p->axsum.p,
-                            p->yavg.p, p->axavg.p, p->rhs.p, p->rowscale.p, st, ctl, rrow);
+    run_side_by_side(p, [&](cudaStream_t q) { launch_spmv_plain(q, p->A.dev, p->xavg.p, p->axavg.p, st); },
+                     [&](cudaStream_t q) { launch_spmv_plain(q, p->AT.dev, p->yavg.p, p->atyavg.p, st); });
+    sweeps();
     launch_check_decide(s, st, ctl, rrow.partials, check_light_grid(ml, false), rcol.partials, check_light_grid(n, true), rrow.counter);
   } else {
     // B200PDLP_FUSED_CHECK=1: the sums in the epilogues of the two averaging SpMV (three launches instead of five)

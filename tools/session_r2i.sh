@@ -12,8 +12,4 @@ mg bench8 8 29802 --no-cpu-baseline
 mg bench8_s5 8 29803 --workload S5 --no-cpu-baseline --parity
 mg bench4_s20 4 29804 --no-cpu-baseline --steps 20 --warmup 5
 mg bench4 4 29805 --no-cpu-baseline
-mg bench2_s20 2 29806 --no-cpu-baseline --steps 20 --warmup 5
-mg bench2 2 29807 --no-cpu-baseline
-echo "=== bench1_s20"; timeout 300 python bench.py --no-cpu-baseline --steps 20 --warmup 5 > $O/bench1_s20.log 2> $O/bench1_s20.err
-B200PDLP_MG_DEVICE_CHECK=0 mg bench8_hostcheck_s20 8 29808 --no-cpu-baseline --steps 20 --warmup 5
 grep -h '"metric"' $O/bench*.log | cut -c1-1500
