@@ -332,6 +332,7 @@ static constexpr int kSlotK1 = 0, kSlotK2 = 1, kSlotK3 = 2, kSlotChk = 3, kNumSl
 static constexpr int kOutsCount = 64;
 
 static void set_device(const b200pdlp_problem* p) { CUDA_OK(cudaSetDevice(p->device)); }
+static void ensure_side_stream(b200pdlp_problem* p);
 
 static void allreduce_inplace(b200pdlp_problem* p, double* dptr, size_t count) {
   if (p->world <= 1) return;
@@ -575,6 +576,7 @@ static void create_problem(const b200pdlp_lp& lp, const b200pdlp_params& prm, in
   }
   const int n = p->n, ml = p->ml;
   CUDA_OK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  if (world == 1) ensure_side_stream(p);
   if (p->device_filled) {
     dev_setup->fill(p->A, 0, p->rperm, p->cinv);
     dev_setup->fill(p->AT, 1, p->cperm, p->rinv);
@@ -666,6 +668,7 @@ static void create_problem_device(const b200pdlp_lp& lp, const b200pdlp_params& 
   p->rank = 0; p->world = 1;
   Laps lap;
   CUDA_OK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  ensure_side_stream(p);
   cudaStream_t s = p->stream;
   p->dev_form = true;
   if (getenv("B200PDLP_KEEP_FORM")) p->prep.keep_form = true;
@@ -1288,13 +1291,15 @@ static int enqueue_check_device_mg(b200pdlp_problem* p, bool light) {
 }
 
 // run `a` on the problem's stream and `b` next to it on the side stream (graph capture turns this into two branches)
+static void ensure_side_stream(b200pdlp_problem* p) {   // at problem creation: never inside a stream capture
+  if (p->side_stream) return;
+  CUDA_OK(cudaStreamCreateWithFlags(&p->side_stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+}
 template <class FA, class FB>
 static void run_side_by_side(b200pdlp_problem* p, FA&& a, FB&& b) {
-  if (!p->side_stream) {
-    CUDA_OK(cudaStreamCreateWithFlags(&p->side_stream, cudaStreamNonBlocking));
-    CUDA_OK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
-    CUDA_OK(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
-  }
+  if (!p->side_stream) { a(p->stream); b(p->stream); return; }
   CUDA_OK(cudaEventRecord(p->ev_fork, p->stream));
   CUDA_OK(cudaStreamWaitEvent(p->side_stream, p->ev_fork, 0));
   b(p->side_stream);
