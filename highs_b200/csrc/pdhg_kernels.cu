@@ -649,12 +649,20 @@ primal_shard_p2p_kernel(int len, PdhgState* __restrict__ st, double* __restrict_
       // reduce-scatter, second half: the G partial A_h^T y' segments that the peers PUSHED into my receive
       // slots (push_part_kernel), added in rank order
       // (pull variant: read the peers' `part` segments over NVLink instead)
+      // all G loads are issued before the first add (measured at 8 GPUs, session I: with the loads inside the summing loop
+      // the thread paid G NVLink round trips one after the other -- 30 us for this kernel); the sum stays in rank order
+      double2 q[kMaxPeers];
+#pragma unroll
+      for (int h = 0; h < kMaxPeers; h++) {
+        if (h < world) {
+          const double* src = pull ? pp.part[h] + seg : pp.recv[rank] + (size_t)h * seg_len;
+          q[h] = __ldcg(reinterpret_cast<const double2*>(src) + i);
+        }
+      }
       ai = make_double2(0.0, 0.0);
-      for (int h = 0; h < world; h++) {
-        const double* src = pull ? pp.part[h] + seg : pp.recv[rank] + (size_t)h * seg_len;
-        const double2 q = __ldcg(reinterpret_cast<const double2*>(src) + i);
-        ai.x += q.x;
-        ai.y += q.y;
+#pragma unroll
+      for (int h = 0; h < kMaxPeers; h++) {
+        if (h < world) { ai.x += q[h].x; ai.y += q[h].y; }
       }
       reinterpret_cast<double2*>(aty_s)[i] = ai;
     } else {
@@ -787,11 +795,17 @@ reduce_part_p2p_kernel(int len, double* __restrict__ dst, PeerPtrs pp, int world
   const size_t seg = (size_t)rank * seg_len;
   const int stride = gridDim.x * kThreads;
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < len; i += stride) {
-    double ai = 0.0;
     // pull 0: the peers pushed into my receive slots; 1: read the peers' `part`; 2: read the peers' `recv`
     // (check iterations park their partial A_g^T ybar there so that `part` keeps the last pass's data)
-    for (int h = 0; h < world; h++)
-      ai += __ldcg(pull == 0 ? pp.recv[rank] + (size_t)h * seg_len + i : (pull == 1 ? pp.part[h] : pp.recv[h]) + seg + i);
+    // (loads first, then the sum in rank order: see primal_shard_p2p_kernel)
+    double q[kMaxPeers];
+#pragma unroll
+    for (int h = 0; h < kMaxPeers; h++)
+      if (h < world) q[h] = __ldcg(pull == 0 ? pp.recv[rank] + (size_t)h * seg_len + i : (pull == 1 ? pp.part[h] : pp.recv[h]) + seg + i);
+    double ai = 0.0;
+#pragma unroll
+    for (int h = 0; h < kMaxPeers; h++)
+      if (h < world) ai += q[h];
     dst[i] = ai;
   }
 }
