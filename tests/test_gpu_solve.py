@@ -229,8 +229,7 @@ def test_dense_column_s5_mini(engine_lib, oracle):
     assert _rel(lp.objectiveValue(res["col_value"]), lp.objectiveValue(orc["col_value"])) <= 1e-5
 
 
-@pytest.mark.parametrize("tol", ["0.0001", "1e-06"])
-def test_s2_converged_parity_with_the_reference(engine_lib, tol):
+def _converged_parity(golden, tol):
     """config S2 (100k x 100k, 1M nonzeros; tree-mode reductions) solved to kkt_tolerance 1e-4 / 1e-6 against
     the UNMODIFIED reference's run on the same LP (tests/golden/s2_converged.json, written by make_s2_golden.py from
     oracle/_ref).  What "the same result" means for two converged PDLP runs whose long sums are added in different orders is
@@ -248,9 +247,9 @@ def test_s2_converged_parity_with_the_reference(engine_lib, tol):
     from conftest import GOLDEN
     from highs_b200 import engine
     from highs_b200.lp import synthetic_lp
-    path = os.path.join(GOLDEN, "s2_converged.json")
+    path = os.path.join(GOLDEN, golden)
     if not os.path.exists(path):
-        pytest.skip("tests/golden/s2_converged.json missing (python tests/golden/make_s2_golden.py)")
+        pytest.skip(f"tests/golden/{golden} missing (python tests/golden/make_s2_golden.py / make_s3_golden.py)")
     g = json.load(open(path))
     w, ref = g["workload"], g["runs"][tol]
     lp = synthetic_lp(w["m"], w["n"], w["nnz_per_col"], w["seed"])
@@ -271,6 +270,18 @@ def test_s2_converged_parity_with_the_reference(engine_lib, tol):
               "primal_dual_objective_error", "max_complementarity_violation"):
         a, b = kkt[k], ref[k]
         assert a <= 10 * b + floor, (k, a, b)      # (a violation measure smaller than the reference's is no disagreement)
+
+
+
+@pytest.mark.parametrize("tol", ["0.0001", "1e-06"])
+def test_s2_converged_parity_with_the_reference(engine_lib, tol):
+    _converged_parity("s2_converged.json", tol)
+
+
+def test_s3_converged_parity_with_the_reference(engine_lib):
+    """The same comparison at the headline size (S3: 1M x 1M, 8M nonzeros), kkt_tolerance 1e-4: the reference needs minutes for
+    it (tests/golden/s3_converged.json, make_s3_golden.py), the engine a fraction of a second."""
+    _converged_parity("s3_converged.json", "0.0001")
 
 
 @pytest.mark.parametrize("warm", [False, True], ids=["cold", "hot_start"])
