@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <climits>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -401,6 +402,44 @@ sector_sharing_kernel(int nslices, int step, const int4* __restrict__ slices, co
   }
   const unsigned leaders = __ballot_sync(0xffffffffu, leader);
   if (lane == 0) { atomicAdd(out, __popc(leaders)); atomicAdd(out + 1, __popc(act)); }
+}
+// Window of the input vector touched by one tile of kTileSlices slices (DevSell::tiled): [lo, lo + w), lo even, w even (16-byte
+// granules for the bulk copy); w = 0 if it does not fit the staging buffer or would run past the vector.  Padding entries of
+// the layout (column 0, value 0) are not entries.  One CTA per tile; counts the tiles that fit in fit[0].
+__global__ void __launch_bounds__(kTpb)
+tile_window_kernel(int nslices, int ncols, const int4* __restrict__ slices, const int* __restrict__ col,
+                   const double* __restrict__ val, int* __restrict__ lo_out, int* __restrict__ w_out, int* __restrict__ fit) {
+  __shared__ int smin[kTpb / 32], smax[kTpb / 32];
+  const int tile = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int s0 = tile * kTileSlices, s1 = min(s0 + kTileSlices, nslices);
+  int mn = INT_MAX, mx = -1;
+  for (int sl = s0 + wid; sl < s1; sl += kTpb / 32) {
+    const int4 d = slices[sl];
+    for (int k = 0; k < d.y; k++) {
+      const size_t o = (size_t)d.x + 32 * (size_t)k + lane;
+      const int c = col[o];
+      if (c != 0 || val[o] != 0.0) { mn = min(mn, c); mx = max(mx, c); }
+    }
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    mn = min(mn, __shfl_down_sync(0xffffffffu, mn, off));
+    mx = max(mx, __shfl_down_sync(0xffffffffu, mx, off));
+  }
+  if (lane == 0) { smin[wid] = mn; smax[wid] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < kTpb / 32; q++) { mn = min(mn, smin[q]); mx = max(mx, smax[q]); }
+    int lo = 0, w = 0;
+    if (mx >= 0) {
+      lo = mn & ~1;
+      w = (mx - lo + 2) & ~1;
+      if (lo + w > ncols) w = (ncols & 1) ? 0 : ncols - lo;
+      if (w > kTileMaxWindow || w <= 0) { w = 0; lo = 0; }
+    }
+    lo_out[tile] = lo;
+    w_out[tile] = w;
+    if (w > 0) atomicAdd(fit, 1);
+  }
 }
 // long rows -> descriptors and segments of kNnzBlk entries (plan_sell's second loop).  `list` holds the device-row ids of
 // the long rows in ascending order; one thread walks them (they are few).  totals: [0] n_partials (= segments),
@@ -806,6 +845,18 @@ void DevicePrologue::run(cudaStream_t s, const b200pdlp_lp& lp, bool do_scale, i
   };
   sample(A, sect);
   sample(AT, sect + 2);
+  // tile windows for the shared-memory staged shape (decided by the engine from tiles_staged / ntiles)
+  int* fit = tmp.get<int>(2);
+  PREP_OK(cudaMemsetAsync(fit, 0, 2 * sizeof(int), s));
+  auto windows = [&](DevSellOwned& M, int* fit_out) {
+    M.ntiles = (M.nslices + kTileSlices - 1) / kTileSlices;
+    if (M.ntiles <= 0 || M.nsegs > 0) { M.ntiles = 0; return; }   // (long rows keep the standard shapes)
+    M.tile_lo = keep<int>(M.ntiles);
+    M.tile_w = keep<int>(M.ntiles);
+    tile_window_kernel<<<M.ntiles, kTpb, 0, s>>>(M.nslices, M.ncols, M.slices, M.col, M.val, M.tile_lo, M.tile_w, fit_out);
+  };
+  windows(A, fit);
+  windows(AT, fit + 1);
 
   // ---- vectors in device order
   arr.cost = keep<double>(n); arr.lower = keep<double>(n); arr.upper = keep<double>(n); arr.colscale = keep<double>(n);
@@ -823,14 +874,16 @@ void DevicePrologue::run(cudaStream_t s, const b200pdlp_lp& lp, bool do_scale, i
   PREP_OK(cudaGetLastError());
   if (keep_form) keep_the_form();
   nvtxRangePop();
-  struct { double d[5]; int tb; int sect[4]; } hfin;
+  struct { double d[5]; int tb; int sect[4]; int fit[2]; } hfin;
   memset(&hfin, 0, sizeof(hfin));
   PREP_OK(cudaMemcpyAsync(hfin.d, dsc, 5 * sizeof(double), cudaMemcpyDeviceToHost, s));
   PREP_OK(cudaMemcpyAsync(hfin.sect, sect, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  PREP_OK(cudaMemcpyAsync(hfin.fit, fit, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
   PREP_OK(cudaMemcpyAsync(&hfin.tb, too_big, sizeof(int), cudaMemcpyDeviceToHost, s));
   PREP_OK(cudaStreamSynchronize(s));   // the temporaries go back to the cache below: everything that reads them is done
   sc.norm_cost_sq = hfin.d[0]; sc.norm_rhs_sq = hfin.d[1]; sc.beta_cost_sq = hfin.d[2]; sc.beta_rhs_sq = hfin.d[3]; sc.amax = hfin.d[4];
   sc.a_sectors = hfin.sect[0]; sc.a_lanes = hfin.sect[1]; sc.at_sectors = hfin.sect[2]; sc.at_lanes = hfin.sect[3];
+  A.tiles_staged = hfin.fit[0]; AT.tiles_staged = hfin.fit[1];
   if (hfin.tb) throw std::runtime_error("b200pdlp: matrix too large for 32-bit slice offsets");
 }
 
@@ -952,6 +1005,7 @@ void launch_postsolve(cudaStream_t s, const DevProblemArrays& a, double sense, i
 void DevSellOwned::release() {
   dev_cache_free(slices); dev_cache_free(col); dev_cache_free(val); dev_cache_free(segs); dev_cache_free(long_rows);
   dev_cache_free(lcol); dev_cache_free(lval); dev_cache_free(long_partial); dev_cache_free(long_counter);
+  dev_cache_free(tile_lo); dev_cache_free(tile_w);
   *this = DevSellOwned();
 }
 

@@ -69,6 +69,10 @@ struct DevSellOwned {   // one sliced-ELL matrix, blocks owned through the cache
   double* lval = nullptr;
   double* long_partial = nullptr;
   unsigned* long_counter = nullptr;
+  // tiled SpMV shape (kernels.cuh DevSell::tiled): per tile of kTileSlices slices the window of the input vector its rows touch
+  int ntiles = 0, tiles_staged = 0;   // tiles_staged: tiles whose window fits the staging buffer
+  int* tile_lo = nullptr;
+  int* tile_w = nullptr;
   void release();
 };
 

@@ -129,6 +129,8 @@ struct DeviceMatrix {
   DevBuf<double> val, lval, long_partial;
   DevBuf<int4> slices, segs, long_rows;
   DevBuf<unsigned> long_counter;
+  DevBuf<int> tile_lo, tile_w;   // tiled shape (DevSell::tiled): windows of the input vector per tile of kTileSlices slices
+  int ntiles = 0, tiles_staged = 0;
   DevSell dev{};
   // descriptors only; col/val/lcol/lval are allocated (lcol/lval zeroed) for a device-side fill
   // (the long-row arrays are cleared on the stream the fill kernels run on: a cudaMemset on the legacy stream is not
@@ -464,8 +466,25 @@ static void apply_spmv_grid(b200pdlp_problem* p) {
   auto apply = [&](DeviceMatrix& M, int k) {
     if (k > 0 && M.dev.nblocks_body > sms * k) { M.dev.nblocks_body = sms * k; M.dev.pipelined = 1; }
   };
-  apply(p->A, ka);
-  apply(p->AT, kat);
+  // Tiled shape (shared-memory staged gathers, spmv_sell_tile_kernel): B200PDLP_TILE=1 (bulk copy by the TMA unit) or 2
+  // (cooperative loads) for both matrices, B200PDLP_TILE_A / _AT for one.  Only where every tile's window fits the staging
+  // buffer and there are enough tiles to occupy the device; not together with the fused step rule or PDL launches.
+  auto tile = [&](DeviceMatrix& M, int mode) {
+    if (mode <= 0 || M.ntiles <= 0 || M.tiles_staged != M.ntiles || M.dev.nsegs > 0 || p->fuse_k4 || p->pass_flags) return false;
+    if (2 * M.ntiles < sms && !getenv("B200PDLP_TILE_FORCE")) return false;   // fewer than half the SMs would have a tile (tests force it)
+    M.dev.tiled = mode; M.dev.tile_lo = M.tile_lo.p; M.dev.tile_w = M.tile_w.p;
+    M.dev.nblocks_body = M.ntiles; M.dev.pipelined = 0;
+    return true;
+  };
+  const int tboth = val("B200PDLP_TILE", 0);
+  if (!tile(p->A, val("B200PDLP_TILE_A", tboth))) apply(p->A, ka);
+  if (!tile(p->AT, val("B200PDLP_TILE_AT", tboth))) apply(p->AT, kat);
+  if (getenv("B200PDLP_TIMING"))
+    fprintf(stderr, "[b200pdlp setup] SpMV shapes: A %s (%d CTAs, tiles staged %d/%d)  A' %s (%d CTAs, tiles staged %d/%d)\n",
+            p->A.dev.tiled ? "tiled" : (p->A.dev.pipelined ? "persistent" : "one slice per warp"), p->A.dev.nblocks_body,
+            p->A.tiles_staged, p->A.ntiles,
+            p->AT.dev.tiled ? "tiled" : (p->AT.dev.pipelined ? "persistent" : "one slice per warp"), p->AT.dev.nblocks_body,
+            p->AT.tiles_staged, p->AT.ntiles);
 }
 
 static void alloc_host_mirrors(b200pdlp_problem* p) {
@@ -702,6 +721,8 @@ static void create_problem_device(const b200pdlp_lp& lp, const b200pdlp_params& 
     M.segs.adopt(O.segs, O.nsegs); M.long_rows.adopt(O.long_rows, O.nlong); M.lcol.adopt(O.lcol, (size_t)O.lcount);
     M.lval.adopt(O.lval, (size_t)O.lcount); M.long_partial.adopt(O.long_partial, O.nsegs);
     M.long_counter.adopt(O.long_counter, O.nlong);
+    if (O.ntiles > 0) { M.tile_lo.adopt(O.tile_lo, O.ntiles); M.tile_w.adopt(O.tile_w, O.ntiles); }
+    M.ntiles = O.ntiles; M.tiles_staged = O.tiles_staged;
     M.host.nrows = O.nrows; M.host.ncols = O.ncols; M.host.padded = O.padded; M.host.lcount = O.lcount; M.host.n_partials = O.nsegs;
     M.dev.nrows = O.nrows; M.dev.nslices = O.nslices;
     M.dev.nblocks_body = (O.nslices + kThreads / 32 - 1) / (kThreads / 32);

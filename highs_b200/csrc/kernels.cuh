@@ -124,7 +124,17 @@ struct DevSell {
   int prefetch_dist;                      // CTAs ahead whose col/val range is pulled into L2 (0 = off)
   int padded_total;                       // elements in col/val (end of the last slice)
   int pipelined;                          // 1: nblocks_body is a persistent grid (a few CTAs per SM), slices walked in a software pipeline
+  // TILED shape (structured matrices; spmv_sell_tile_kernel): one 1024-thread CTA per kTileSlices consecutive slices (= one
+  // 8192-row sort window); the window of the input vector those rows touch, [tile_lo[t], tile_lo[t] + tile_w[t]), is staged in
+  // shared memory by one bulk copy and the gathers read it there.  tile_w[t] == 0: window wider than the staging buffer, that
+  // tile gathers from global memory.  tiled != 0: nblocks_body counts tiles.
+  int tiled;                              // 0 off, 1 staged by cp.async.bulk (TMA unit) + mbarrier, 2 staged by cooperative loads
+  const int* __restrict__ tile_lo;
+  const int* __restrict__ tile_w;
 };
+constexpr int kTileSlices = 256;          // slices per tile (8192 rows)
+constexpr int kTileThreads = 1024;
+constexpr int kTileMaxWindow = 24576;     // doubles staged per tile (192 KB of the 227 KB a CTA may use)
 
 // peer-memory view for the fused multi-GPU path (one process per GPU, buffers mapped with CUDA IPC)
 constexpr int kMaxPeers = 16;

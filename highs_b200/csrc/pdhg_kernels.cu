@@ -558,6 +558,141 @@ __global__ void __launch_bounds__(kThreads) spmv_sell_kernel(DevSell A, Epi epi_
   }
 }
 
+// ============================================================ tiled SpMV (structured matrices)
+// DevSell::tiled.  Same sliced-ELL arrays, same per-row arithmetic in the same order as spmv_sell_kernel, same epilogues; what
+// changes is where the gathers go: a CTA owns kTileSlices consecutive slices (one length-sort window of 8192 rows), stages the
+// window of the input vector that its rows touch in shared memory -- ONE bulk copy by the TMA unit (cp.async.bulk + mbarrier),
+// 16-byte aligned, <= 192 KB -- and gathers from there: a gather then costs a shared-memory access (~4 bank-conflict cycles per
+// warp) instead of 32 L1TEX wavefronts.  Sized in DESIGN.md section 8: staging pays only when one CTA covers a whole sort window
+// (65 k gathers per staged window), which is why this is a separate kernel shape and not a variant of the 256-row CTA.
+// Padding entries of the layout carry column 0 and value 0: a padded lane's index may fall outside the window, it then
+// multiplies its 0 by 0 instead of by x[0] (the sum is unchanged; the sign of an all-zero row's zero may differ).
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <class Epi>
+__global__ void __launch_bounds__(kTileThreads, 1) spmv_sell_tile_kernel(DevSell A, Epi epi_arg, ReduceScratch rs) {
+  extern __shared__ __align__(16) double xs[];
+  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ double smp[Epi::NACC > 0 ? Epi::NACC : 1][kTileThreads / 32];
+  Epi epi = epi_arg;
+  if (!epi.begin()) return;
+  const double* __restrict__ xin = epi.input();
+  const int tile = blockIdx.x;
+  const int lo = A.tile_lo[tile], w = A.tile_w[tile];
+  const bool staged = w > 0;
+  if (staged) {
+    if (A.tiled == 1) {
+      const unsigned bar = smem_u32(&mbar);
+      if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned bytes = (unsigned)w * 8u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        for (unsigned off = 0; off < bytes; off += 32768u) {   // chunks of 32 KB (each a multiple of 16 bytes)
+          const unsigned n = bytes - off < 32768u ? bytes - off : 32768u;
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           smem_u32(xs) + off),
+                       "l"(reinterpret_cast<const char*>(xin + lo) + off), "r"(n), "r"(bar)
+                       : "memory");
+        }
+      }
+      unsigned done = 0;
+      do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(bar), "r"(0)
+                     : "memory");
+      } while (!done);
+    } else {
+      for (int i = threadIdx.x; i < w; i += kTileThreads) xs[i] = xin[lo + i];
+      __syncthreads();
+    }
+  }
+  double acc[Epi::NACC > 0 ? Epi::NACC : 1] = {0.0};
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int s0 = tile * kTileSlices;
+  const int s1 = s0 + kTileSlices < A.nslices ? s0 + kTileSlices : A.nslices;
+  const unsigned uw = (unsigned)w;
+  for (int slice = s0 + wid; slice < s1; slice += kTileThreads / 32) {
+    const int4 d = A.slices[slice];
+    const int row = slice * 32 + lane;
+    const bool live = !((unsigned)d.z >> lane & 1u);
+    if (live) epi.prefetch(row);
+    const int* __restrict__ cp = A.col + d.x + lane;
+    const double* __restrict__ vp = A.val + d.x + lane;
+    double s = 0.0;
+    int k = 0;
+    if (staged) {
+      for (; k + 8 <= d.y; k += 8) {
+        int c[8];
+        double v[8], g[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) c[u] = cp[32 * (k + u)];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = vp[32 * (k + u)];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const unsigned q = (unsigned)(c[u] - lo); g[u] = q < uw ? xs[q] : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) s += v[u] * g[u];
+      }
+      for (; k < d.y; k++) {
+        const unsigned q = (unsigned)(cp[32 * k] - lo);
+        s += vp[32 * k] * (q < uw ? xs[q] : 0.0);
+      }
+    } else {
+      for (; k + 8 <= d.y; k += 8) {
+        int c[8];
+        double v[8], g[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) c[u] = cp[32 * (k + u)];
+#pragma unroll
+        for (int u = 0; u < 8; u++) g[u] = xin[c[u]];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = vp[32 * (k + u)];
+#pragma unroll
+        for (int u = 0; u < 8; u++) s += v[u] * g[u];
+      }
+      for (; k < d.y; k++) s += vp[32 * k] * xin[cp[32 * k]];
+    }
+    if (live) {
+      double t[Epi::NACC > 0 ? Epi::NACC : 1];
+      epi.row(row, s, t);
+      if constexpr (Epi::NACC > 0) {
+#pragma unroll
+        for (int a = 0; a < Epi::NACC; a++) acc[a] += t[a];
+      }
+    }
+  }
+  if constexpr (Epi::NACC > 0) {
+    // lanes, then the CTA's 32 warps in order: a fixed tree
+#pragma unroll
+    for (int a = 0; a < Epi::NACC; a++) {
+      const double v = warp_sum(acc[a]);
+      if (lane == 0) smp[a][wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int a = 0; a < Epi::NACC; a++) {
+        double v = 0.0;
+        for (int q = 0; q < kTileThreads / 32; q++) v += smp[a][q];
+        rs.partials[(size_t)a * gridDim.x + blockIdx.x] = v;
+      }
+    }
+  }
+}
+
+template <class Epi>
+static void launch_tile(cudaStream_t s, const DevSell& A, const Epi& e, const ReduceScratch& rs) {
+  static bool attr_set = false;   // (one per instantiation; the attribute is per function and per device context)
+  const size_t smem = (size_t)kTileMaxWindow * sizeof(double);
+  if (!attr_set) { cudaFuncSetAttribute(spmv_sell_tile_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+  spmv_sell_tile_kernel<Epi><<<A.nblocks_body, kTileThreads, smem, s>>>(A, e, rs);
+}
+
 // ============================================================ multi-GPU kernels
 // World > 1: rank g owns a row block (A_g, A_g^T, y, ax, b) AND a column shard
 // of every n-vector (x, aty, c, l, u, xSum ...).  Full-length vectors exist only as the gather input
@@ -1886,6 +2021,7 @@ void launch_primal_step(cudaStream_t s, int n, PdhgState* st, double* x0, double
 void launch_spmv_plain(cudaStream_t s, const DevSell& A, const double* in, double* out, const PdhgState* due) {
   if (A.nblocks_body + A.nsegs == 0) return;
   PlainEpilogue e{in, out, due};
+  if (A.tiled) { launch_tile(s, A, e, ReduceScratch{nullptr, nullptr, nullptr, 0, 0}); return; }
   if (A.pipelined) spmv_sell_kernel<PlainEpilogue, true><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr, nullptr, 0, 0});
   else spmv_sell_kernel<PlainEpilogue, false><<<A.nblocks_body + A.nsegs, kThreads, 0, s>>>(A, e, ReduceScratch{nullptr, nullptr, nullptr, 0, 0});
 }
@@ -1897,6 +2033,7 @@ void launch_spmv_dual(cudaStream_t s, const DevSell& A, PdhgState* st, const dou
   DualEpilogue e{};
   e.st = st; e.x0 = x0; e.x1 = x1; e.y0 = y0; e.y1 = y1; e.ax0 = ax0; e.ax1 = ax1; e.b = b; e.ysum = ysum;
   e.neq = neq; e.row_offset = row_offset; e.axsum = axsum;
+  if (A.tiled) { launch_tile(s, A, e, rs); return; }   // (the engine tiles only in tree mode)
   if (A.pipelined) launch_k(spmv_sell_kernel<DualEpilogue, true>, A.nblocks_body + A.nsegs, kThreads, s, rs.flags, A, e, rs);
   else launch_k(spmv_sell_kernel<DualEpilogue, false>, A.nblocks_body + A.nsegs, kThreads, s, rs.flags, A, e, rs);
 }
@@ -1908,6 +2045,7 @@ void launch_spmv_primal(cudaStream_t s, const DevSell& A, PdhgState* st, const d
   PrimalEpilogue e{};
   e.st = st; e.y0 = y0; e.y1 = y1; e.x0 = x0; e.x1 = x1; e.aty0 = aty0; e.aty1 = aty1; e.atysum = atysum;
   e.p1 = p1; e.nb1 = nb1; e.p2 = p2; e.nb2 = nb2; e.fuse = (p1 != nullptr && rs.terms == nullptr) ? 1 : 0;
+  if (A.tiled) { launch_tile(s, A, e, rs); return; }   // (tree mode only; never together with the fused step rule: engine.cu)
   if (A.pipelined) launch_k(spmv_sell_kernel<PrimalEpilogue, true>, A.nblocks_body + A.nsegs, kThreads, s, rs.flags, A, e, rs);
   else launch_k(spmv_sell_kernel<PrimalEpilogue, false>, A.nblocks_body + A.nsegs, kThreads, s, rs.flags, A, e, rs);
 }
@@ -2055,7 +2193,7 @@ void launch_spmv_check_rows(cudaStream_t s, const DevSell& A, const PdhgState* s
   e.axavg = axavg; e.b = b; e.rsc = rsc; e.neq = neq; e.axsum = axsum;
   rs.terms = nullptr; rs.flags = 0;
   DevSell F = A;   // the check epilogues keep their sums in shared memory, which needs at most one row per thread
-  F.nblocks_body = A.nblocks_full; F.pipelined = 0;
+  F.nblocks_body = A.nblocks_full; F.pipelined = 0; F.tiled = 0;
   spmv_sell_kernel<CheckRowEpilogue, false><<<F.nblocks_body + F.nsegs, kThreads, 0, s>>>(F, e, rs);
 }
 void launch_spmv_check_cols(cudaStream_t s, const DevSell& AT, const PdhgState* st, const SolveCtl* ctl, const double* yavg,
@@ -2068,7 +2206,7 @@ void launch_spmv_check_cols(cudaStream_t s, const DevSell& AT, const PdhgState* 
   e.atyavg = atyavg; e.c = c; e.lo = lo; e.up = up; e.cs = cs; e.atysum = atysum;
   rs.terms = nullptr; rs.flags = 0;
   DevSell F = AT;
-  F.nblocks_body = AT.nblocks_full; F.pipelined = 0;
+  F.nblocks_body = AT.nblocks_full; F.pipelined = 0; F.tiled = 0;
   spmv_sell_kernel<CheckColEpilogue, false><<<F.nblocks_body + F.nsegs, kThreads, 0, s>>>(F, e, rs);
 }
 void launch_check_decide(cudaStream_t s, PdhgState* st, SolveCtl* ctl, const double* prow, int nbr, const double* pcol,
