@@ -585,6 +585,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) spmv_sell_tile_kernel(DevSell
       const unsigned bar = smem_u32(&mbar);
       if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // the init, visible to the async proxy that completes on it
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       }
       __syncthreads();
