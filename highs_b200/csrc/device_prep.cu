@@ -850,7 +850,7 @@ void DevicePrologue::run(cudaStream_t s, const b200pdlp_lp& lp, bool do_scale, i
   PREP_OK(cudaMemsetAsync(fit, 0, 2 * sizeof(int), s));
   auto windows = [&](DevSellOwned& M, int* fit_out) {
     M.ntiles = (M.nslices + kTileSlices - 1) / kTileSlices;
-    if (M.ntiles <= 0 || M.nsegs > 0) { M.ntiles = 0; return; }   // (long rows keep the standard shapes)
+    if (M.ntiles <= 0) { M.ntiles = 0; return; }
     M.tile_lo = keep<int>(M.ntiles);
     M.tile_w = keep<int>(M.ntiles);
     tile_window_kernel<<<M.ntiles, kTpb, 0, s>>>(M.nslices, M.ncols, M.slices, M.col, M.val, M.tile_lo, M.tile_w, fit_out);

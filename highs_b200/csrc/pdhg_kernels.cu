@@ -577,7 +577,45 @@ __global__ void __launch_bounds__(kTileThreads, 1) spmv_sell_tile_kernel(DevSell
   Epi epi = epi_arg;
   if (!epi.begin()) return;
   const double* __restrict__ xin = epi.input();
+  double acc[Epi::NACC > 0 ? Epi::NACC : 1] = {0.0};
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int tile = blockIdx.x;
+  if (tile >= A.nblocks_body) {
+    // one segment of a long row (same scheme as spmv_sell_kernel, on this kernel's 1024 threads): gathers from global memory
+    const int4 sg = A.segs[tile - A.nblocks_body];
+    double s = 0.0;
+    for (int e = sg.y + threadIdx.x; e < sg.z; e += kTileThreads) s += A.lval[e] * xin[A.lcol[e]];
+    s = warp_sum(s);
+    if (lane == 0) smp[0][wid] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot_seg = 0.0;
+      for (int q = 0; q < kTileThreads / 32; q++) tot_seg += smp[0][q];
+      const int4 lr = A.long_rows[sg.w];
+      const int seg = (tile - A.nblocks_body) - lr.y;
+      A.long_partial[lr.w + seg] = tot_seg;
+      __threadfence();
+      const unsigned t = atomicAdd(&A.long_counter[sg.w], 1u);
+      if (t == (unsigned)lr.z - 1u) {
+        __threadfence();
+        const volatile double* pp = A.long_partial + lr.w;
+        double tot = 0.0;
+        for (int q = 0; q < lr.z; q++) tot += pp[q];
+        A.long_counter[sg.w] = 0u;
+        epi.prefetch(lr.x);
+        double t2[Epi::NACC > 0 ? Epi::NACC : 1];
+        epi.row(lr.x, tot, t2);
+        if constexpr (Epi::NACC > 0) {
+#pragma unroll
+          for (int a = 0; a < Epi::NACC; a++) rs.partials[(size_t)a * gridDim.x + blockIdx.x] = t2[a];
+        }
+      } else if constexpr (Epi::NACC > 0) {
+#pragma unroll
+        for (int a = 0; a < Epi::NACC; a++) rs.partials[(size_t)a * gridDim.x + blockIdx.x] = 0.0;
+      }
+    }
+    return;
+  }
   const int lo = A.tile_lo[tile], w = A.tile_w[tile];
   const bool staged = w > 0;
   if (staged) {
@@ -612,8 +650,6 @@ __global__ void __launch_bounds__(kTileThreads, 1) spmv_sell_tile_kernel(DevSell
       __syncthreads();
     }
   }
-  double acc[Epi::NACC > 0 ? Epi::NACC : 1] = {0.0};
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int s0 = tile * kTileSlices;
   const int s1 = s0 + kTileSlices < A.nslices ? s0 + kTileSlices : A.nslices;
   const unsigned uw = (unsigned)w;
@@ -691,7 +727,7 @@ static void launch_tile(cudaStream_t s, const DevSell& A, const Epi& e, const Re
   static bool attr_set = false;   // (one per instantiation; the attribute is per function and per device context)
   const size_t smem = (size_t)kTileMaxWindow * sizeof(double);
   if (!attr_set) { cudaFuncSetAttribute(spmv_sell_tile_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
-  spmv_sell_tile_kernel<Epi><<<A.nblocks_body, kTileThreads, smem, s>>>(A, e, rs);
+  spmv_sell_tile_kernel<Epi><<<A.nblocks_body + A.nsegs, kTileThreads, smem, s>>>(A, e, rs);
 }
 
 // ============================================================ multi-GPU kernels
