@@ -477,15 +477,13 @@ static void apply_spmv_grid(b200pdlp_problem* p) {
     M.dev.nblocks_body = M.ntiles; M.dev.pipelined = 0;
     return true;
   };
-  // default: tiled (bulk copy) where the prologue found (a) windows that fit for >= 90 % of the tiles, (b) gathers that do NOT
-  // already share sectors (> 0.5 sectors per lane: otherwise the persistent shape is as good) and (c) no long rows (their
-  // segment path is exercised by the forced setting only).  Measured on S3B (session L): A'y + interaction 38.6 -> 33.2 us.
-  auto tile_default = [&](const DeviceMatrix& M, int sectors, int lanes) {
-    return (p->dev_form && M.dev.nsegs == 0 && lanes > 0 && 2 * sectors > lanes) ? 1 : 0;
-  };
+  // default: tiled (bulk copy) wherever the prologue found windows that fit for >= 90 % of the tiles (B200PDLP_TILE=0: off).
+  // Measured (sessions L, M): S3B K2 48.1 -> 37.0 us (0.68 of the HBM roofline), K3 38.6 -> 33.2; S3D K3 37.1 -> 32.7, K2 34.5
+  // -> 35.1 against the persistent shape; S3 (random columns): no window fits, never chosen.
+  const int tdef = p->dev_form ? 1 : 0;
   const int tboth = val("B200PDLP_TILE", -1);
-  const int ta = val("B200PDLP_TILE_A", tboth >= 0 ? tboth : tile_default(p->A, p->prep.sc.a_sectors, p->prep.sc.a_lanes));
-  const int tat = val("B200PDLP_TILE_AT", tboth >= 0 ? tboth : tile_default(p->AT, p->prep.sc.at_sectors, p->prep.sc.at_lanes));
+  const int ta = val("B200PDLP_TILE_A", tboth >= 0 ? tboth : tdef);
+  const int tat = val("B200PDLP_TILE_AT", tboth >= 0 ? tboth : tdef);
   if (!tile(p->A, ta)) apply(p->A, ka);
   if (!tile(p->AT, tat)) apply(p->AT, kat);
   if (getenv("B200PDLP_TIMING"))
