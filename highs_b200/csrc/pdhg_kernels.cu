@@ -724,9 +724,14 @@ __global__ void __launch_bounds__(kTileThreads, 1) spmv_sell_tile_kernel(DevSell
 
 template <class Epi>
 static void launch_tile(cudaStream_t s, const DevSell& A, const Epi& e, const ReduceScratch& rs) {
-  static bool attr_set = false;   // (one per instantiation; the attribute is per function and per device context)
+  static bool attr_set[64] = {false};   // per instantiation AND per device: the attribute belongs to the function in one context
   const size_t smem = (size_t)kTileMaxWindow * sizeof(double);
-  if (!attr_set) { cudaFuncSetAttribute(spmv_sell_tile_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaFuncSetAttribute(spmv_sell_tile_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
   spmv_sell_tile_kernel<Epi><<<A.nblocks_body + A.nsegs, kTileThreads, smem, s>>>(A, e, rs);
 }
 
