@@ -162,3 +162,43 @@ def test_slice_plan_model_matches_host_layout(engine_lib):
     t_pad, t_long, t_seg = plan(np.diff(h["cbeg"]).astype(np.int64), h["n"])
     assert (a_pad, a_long, a_seg) == (stats[3], stats[4], stats[5])
     assert (t_pad, t_long, t_seg) == (stats[6], stats[7], stats[8])
+
+
+def model_tile_window(cols, vals, ncols, max_window=24576):
+    """tile_window_kernel (device_prep.cu) in numpy: the window [lo, lo + w) of the input vector that a tile's real entries touch --
+    lo even and w even (16-byte granules of the bulk copy), inside the vector, w = 0 when it does not fit the staging buffer."""
+    real = (cols != 0) | (vals != 0.0)          # padding entries of the layout are (column 0, value 0)
+    if not real.any():
+        return 0, 0
+    mn, mx = int(cols[real].min()), int(cols[real].max())
+    lo = mn & ~1
+    w = (mx - lo + 2) & ~1
+    if lo + w > ncols:
+        w = 0 if (ncols & 1) else ncols - lo
+    if w > max_window or w <= 0:
+        return 0, 0
+    return lo, w
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_tile_window_model_covers_every_real_entry(seed):
+    """every real entry of a tile lies inside [lo, lo + w), the window is 16-byte aligned in position and size and never runs
+    past the vector; tiles that touch both ends of the vector (wrap-around patterns) or more than the buffer get w = 0"""
+    rng = np.random.default_rng(seed)
+    ncols = int(rng.integers(9000, 40000)) | (seed & 1)          # odd and even vector lengths
+    centre = int(rng.integers(0, ncols))
+    half = int(rng.integers(1, 14000))
+    cols = np.clip(centre + rng.integers(-half, half + 1, size=4096), 0, ncols - 1).astype(np.int64)
+    vals = rng.standard_normal(4096)
+    pad = rng.random(4096) < 0.2
+    cols[pad], vals[pad] = 0, 0.0
+    lo, w = model_tile_window(cols, vals, ncols)
+    real = (cols != 0) | (vals != 0.0)
+    if w == 0:
+        span = cols[real].max() - (cols[real].min() & ~1) + 1
+        assert span > 24576 - 2 or ((ncols & 1) and (cols[real].max() >= ncols - 1)), (span, ncols)
+        return
+    assert lo % 2 == 0 and w % 2 == 0 and 0 < w <= 24576 and lo + w <= ncols
+    assert ((cols[real] >= lo) & (cols[real] < lo + w)).all()
+    # a padded lane reads outside the window or inside it: either way it multiplies a zero value
+    assert (vals[~real] == 0.0).all()
